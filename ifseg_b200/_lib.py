@@ -1,0 +1,134 @@
+"""ctypes binding of libsegofa_b200.so (the C ABI declared in include/segofa_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised.  SGF_ERR_OOM is reported with "out of memory" in the message so that
+the reference trainer's OOM recovery (trainer.py:807-822) keeps working.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsegofa_b200.so")
+
+SGF_BF16, SGF_F32 = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+
+_vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", _vp), ("lda", _i64), ("a_batch_stride", _i64),
+        ("b", _vp), ("ldb", _i64), ("b_batch_stride", _i64),
+        ("c", _vp), ("ldc", _i64), ("c_batch_stride", _i64), ("c_dtype", _i32),
+        ("M", _i32), ("N", _i32), ("K", _i32), ("batch", _i32),
+        ("col_scale", _vp), ("col_bias", _vp),
+        ("residual", _vp), ("ldr", _i64), ("r_batch_stride", _i64), ("r_dtype", _i32),
+        ("act", _i32), ("alpha", _f32), ("alpha_cols", _i32),
+    ]
+
+
+class Conv3x3Args(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("w", _vp), ("y", _vp),
+        ("n", _i32), ("h", _i32), ("w_", _i32), ("cin", _i32), ("cout", _i32),
+        ("col_scale", _vp), ("col_bias", _vp), ("act", _i32),
+    ]
+
+
+class RowLnArgs(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("ldx", _i64), ("x_dtype", _i32),
+        ("gather_idx", _vp), ("pre_add", _vp),
+        ("g1", _vp), ("b1", _vp),
+        ("residual", _vp), ("ldr", _i64), ("r_dtype", _i32),
+        ("out1", _vp), ("ld1", _i64), ("out1_dtype", _i32),
+        ("g2", _vp), ("b2", _vp),
+        ("out2", _vp), ("ld2", _i64),
+        ("zero_row", _vp),
+        ("rows", _i32), ("D", _i32),
+        ("seg_len", _i32), ("seg_stride", _i32), ("seg_off", _i32),
+    ]
+
+
+class RelBiasArgs(C.Structure):
+    _fields_ = [
+        ("bias", _vp), ("head_stride", _i64), ("row_stride", _i64),
+        ("H", _i32), ("Tq", _i32), ("Tk", _i32),
+        ("bucket", _vp), ("bucket_ld", _i64), ("ids", _vp), ("table", _vp),
+        ("blk_lo", _i32), ("blk_hi", _i32),
+    ]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [
+        ("q", _vp), ("q_row_stride", _i64), ("q_batch_stride", _i64),
+        ("k", _vp), ("k_row_stride", _i64), ("k_batch_stride", _i64),
+        ("v", _vp), ("v_row_stride", _i64), ("v_batch_stride", _i64),
+        ("out", _vp), ("o_row_stride", _i64), ("o_batch_stride", _i64),
+        ("bias", _vp), ("bias_head_stride", _i64), ("bias_row_stride", _i64),
+        ("head_scale", _vp), ("key_padding_mask", _vp),
+        ("B", _i32), ("H", _i32), ("Tq", _i32), ("Tk", _i32), ("causal", _i32),
+    ]
+
+
+class SegmaskArgs(C.Structure):
+    _fields_ = [
+        ("logits", _vp), ("batch_stride", _i64), ("tok_stride", _i64),
+        ("B", _i32), ("C", _i32), ("hp", _i32), ("wp", _i32), ("h", _i32), ("w", _i32),
+        ("mask", _vp), ("target", _vp),
+        ("area_intersect", _vp), ("area_pred", _vp), ("area_label", _vp),
+    ]
+
+
+# every symbol include/segofa_b200.h declares: (name, restype, argtypes)
+EXPORTS = [
+    ("sgf_last_error", C.c_char_p, []),
+    ("sgf_abi_version", C.c_int, []),
+    ("sgf_launch_count", _i64, []),
+    ("sgf_reset_launch_count", None, []),
+    ("sgf_gemm_bf16", C.c_int, [C.POINTER(GemmArgs), _vp]),
+    ("sgf_conv3x3_s1_nhwc", C.c_int, [C.POINTER(Conv3x3Args), _vp]),
+    ("sgf_nchw_f32_to_nhwc_bf16", C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    ("sgf_im2col_nhwc", C.c_int, [_vp, _vp] + [_i32] * 10 + [_i64, _vp]),
+    ("sgf_maxpool3x3s2_nhwc", C.c_int, [_vp, _vp] + [_i32] * 6 + [_vp]),
+    ("sgf_row_layernorm", C.c_int, [C.POINTER(RowLnArgs), _vp]),
+    ("sgf_add_rel_bias", C.c_int, [C.POINTER(RelBiasArgs), _vp]),
+    ("sgf_attention_bf16", C.c_int, [C.POINTER(AttentionArgs), _vp]),
+    ("sgf_upsample_argmax", C.c_int, [C.POINTER(SegmaskArgs), _vp]),
+]
+
+_lib = None
+
+
+def load():
+    """Loads the library (once).  Raises RuntimeError with build instructions if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the segofa_b200 CUDA extension is not built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` (or ifseg_b200/csrc/build.py). "
+            "There is no CPU/PyTorch fallback for the hot path."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in EXPORTS:
+        fn = getattr(lib, name)  # AttributeError -> missing export
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sgf_abi_version() != 1:
+        raise RuntimeError("libsegofa_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    msg = load().sgf_last_error().decode("utf-8", "replace")
+    if rc == 3:
+        raise RuntimeError(f"CUDA out of memory in {what}: {msg}")
+    if rc == 1:
+        raise ValueError(f"{what}: {msg}")
+    raise RuntimeError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,433 @@
+// tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] * B[N,K]^T )     bf16 operands, fp32 accumulation in TMEM.
+//
+// One CTA per 128 x BN output tile, 192 threads, warp-specialised:
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (tcgen05.commit frees stages)
+//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> scale/bias/act/residual -> global)
+// The same main loop serves the 3x3/s1 convolution: the A tile of filter tap (ky,kx) is a 4-D
+// TMA box [64 ch, bw, bh, 1] of the NHWC input shifted by (kx-1, ky-1); TMA's out-of-bounds
+// zero fill is the convolution padding, so no im2col matrix ever exists.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace sgf {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int kGemmThreads = 192;
+
+struct GemmEpilogue {
+  void* c;
+  int64_t ldc, c_batch_stride;
+  int c_dtype;
+  const float* col_scale;
+  const float* col_bias;
+  const void* residual;
+  int64_t ldr, r_batch_stride;
+  int r_dtype;
+  int act;
+  float alpha;
+  int alpha_cols;
+};
+
+struct GemmShape {
+  int M, N, K;
+  // conv mode only
+  int H, W, bw, bh, tiles_w, tiles_h, cin_blocks;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+};
+
+template <int BN, int kStages, bool kConv>
+__global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                    const GemmShape shp, const GemmEpilogue ep) {
+  using S = GemmSmem<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only guaranteed 16B aligned: round up to the 1024B the 128B swizzle needs
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* accum_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int mt = blockIdx.y;
+  const int z = blockIdx.z;
+  const int num_kb = (shp.K + BK - 1) / BK;
+
+  // conv tile decomposition
+  int img = 0, h0 = 0, w0 = 0;
+  if constexpr (kConv) {
+    const int per_img = shp.tiles_w * shp.tiles_h;
+    img = mt / per_img;
+    const int t = mt - img * per_img;
+    h0 = (t / shp.tiles_w) * shp.bh;
+    w0 = (t % shp.tiles_w) * shp.bw;
+  }
+  const int m0 = mt * BM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::kStageBytes;
+        uint8_t* sb = sa + S::kABytes;
+        mbar_expect_tx(&full_bar[s], S::kStageBytes);
+        if constexpr (kConv) {
+          const int tap = kb / shp.cin_blocks;
+          const int kc = kb - tap * shp.cin_blocks;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          tma_load_4d(sa, &tmA, &full_bar[s], kc * BK, w0 + dx, h0 + dy, img);
+        } else {
+          tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, m0, z);
+        }
+        tma_load_3d(sb, &tmB, &full_bar[s], kb * BK, n0, z);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+        const uint32_t sb = sa + S::kABytes;
+        const uint64_t da = make_smem_desc_sw128(sa);
+        const uint64_t db = make_smem_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 16 K-elements = 32 bytes inside the 128B swizzle row: +2 in the (addr>>4) field
+          umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above retire
+      }
+      umma_commit(accum_bar);  // accumulator complete
+    }
+  } else {
+    // ------------------------------ epilogue warps ------------------------------
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+
+    int64_t out_row;
+    bool row_ok;
+    if constexpr (kConv) {
+      const int hh = h0 + r / shp.bw, ww = w0 + r % shp.bw;
+      row_ok = (hh < shp.H) && (ww < shp.W);
+      out_row = (static_cast<int64_t>(img) * shp.H + hh) * shp.W + ww;
+    } else {
+      row_ok = (m0 + r) < shp.M;
+      out_row = m0 + r;
+    }
+    const bool vec_ok = (shp.N % 8) == 0;
+    uint8_t* cptr = reinterpret_cast<uint8_t*>(ep.c) +
+                    (static_cast<int64_t>(z) * ep.c_batch_stride + out_row * ep.ldc) * (ep.c_dtype == SGF_F32 ? 4 : 2);
+    const uint8_t* rptr = nullptr;
+    if (ep.residual)
+      rptr = reinterpret_cast<const uint8_t*>(ep.residual) +
+             (static_cast<int64_t>(z) * ep.r_batch_stride + out_row * ep.ldr) * (ep.r_dtype == SGF_F32 ? 4 : 2);
+
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      const int c0 = n0 + ch * 32;
+      if (c0 >= shp.N) break;  // warp-uniform
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ch * 32, acc);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+      const bool full = vec_ok && (c0 + 32 <= shp.N);
+      if (full) {
+        if (ep.col_scale) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(ep.col_scale + c0 + j);
+            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+          }
+        }
+        if (ep.col_bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(ep.col_bias + c0 + j);
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (c0 + j < shp.N) {
+            if (ep.col_scale) v[j] *= ep.col_scale[c0 + j];
+            if (ep.col_bias) v[j] += ep.col_bias[c0 + j];
+          }
+        }
+      }
+      if (ep.alpha_cols > c0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < ep.alpha_cols) v[j] *= ep.alpha;
+      }
+      if (ep.act == SGF_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      }
+      if (row_ok) {
+        if (rptr) {
+          if (full) {
+            if (ep.r_dtype == SGF_F32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rptr + (c0 + j) * 4);
+                v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 r4 = *reinterpret_cast<const uint4*>(rptr + (c0 + j) * 2);
+                const float2 a = unpack_bf16x2(r4.x), b = unpack_bf16x2(r4.y), c = unpack_bf16x2(r4.z),
+                             d = unpack_bf16x2(r4.w);
+                v[j] += a.x; v[j + 1] += a.y; v[j + 2] += b.x; v[j + 3] += b.y;
+                v[j + 4] += c.x; v[j + 5] += c.y; v[j + 6] += d.x; v[j + 7] += d.y;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (c0 + j < shp.N) {
+                v[j] += (ep.r_dtype == SGF_F32)
+                            ? reinterpret_cast<const float*>(rptr)[c0 + j]
+                            : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rptr)[c0 + j]);
+              }
+            }
+          }
+        }
+        if (ep.act == SGF_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (full) {
+          if (ep.c_dtype == SGF_F32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(cptr + (c0 + j) * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o;
+              o.x = pack_bf16x2(v[j], v[j + 1]);
+              o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+              o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(cptr + (c0 + j) * 2) = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (c0 + j < shp.N) {
+              if (ep.c_dtype == SGF_F32)
+                reinterpret_cast<float*>(cptr)[c0 + j] = v[j];
+              else
+                reinterpret_cast<__nv_bfloat16*>(cptr)[c0 + j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------
+template <int BN, int kStages>
+static constexpr int gemm_smem_bytes() {
+  return kStages * GemmSmem<BN>::kStageBytes + (2 * kStages + 1) * 8 + 16 + 1024;
+}
+
+template <int BN, int kStages, bool kConv>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
+                       dim3 grid, cudaStream_t st) {
+  auto kern = gemm_tcgen05_kernel<BN, kStages, kConv>;
+  constexpr int smem = gemm_smem_bytes<BN, kStages>();
+  static bool configured = false;
+  if (!configured) {
+    SGF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, shp, ep);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
+
+static int check_epilogue_alignment(const GemmEpilogue& ep, int N) {
+  if (N % 8 == 0) {
+    const int cs = ep.c_dtype == SGF_F32 ? 4 : 2;
+    SGF_REQUIRE((reinterpret_cast<uintptr_t>(ep.c) % 16) == 0 && (ep.ldc * cs) % 16 == 0 &&
+                    (ep.c_batch_stride * cs) % 16 == 0,
+                "gemm: C must be 16-byte aligned with 16-byte multiple row stride");
+    if (ep.residual) {
+      const int rs = ep.r_dtype == SGF_F32 ? 4 : 2;
+      SGF_REQUIRE((reinterpret_cast<uintptr_t>(ep.residual) % 16) == 0 && (ep.ldr * rs) % 16 == 0 &&
+                      (ep.r_batch_stride * rs) % 16 == 0,
+                  "gemm: residual must be 16-byte aligned with 16-byte multiple row stride");
+    }
+    if (ep.col_scale) SGF_REQUIRE((reinterpret_cast<uintptr_t>(ep.col_scale) % 16) == 0, "gemm: col_scale align");
+    if (ep.col_bias) SGF_REQUIRE((reinterpret_cast<uintptr_t>(ep.col_bias) % 16) == 0, "gemm: col_bias align");
+  }
+  return SGF_OK;
+}
+
+static int pick_bn(int M_tiles, int N, int batch) {
+  // prefer the widest tile that still gives >= 1 wave of CTAs on 148 SMs
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  const long ctas128 = static_cast<long>(M_tiles) * ((N + 127) / 128) * batch;
+  if (N % 128 != 0 && N % 64 == 0 && N < 256) return 64;
+  if (ctas128 < 148) return 64;
+  return 128;
+}
+
+}  // namespace sgf
+
+using namespace sgf;
+
+extern "C" int sgf_gemm_bf16(const sgf_gemm_args* a, void* stream) {
+  SGF_REQUIRE(a != nullptr, "gemm: null args");
+  SGF_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0, "gemm: bad shape M=%d N=%d K=%d batch=%d", a->M,
+              a->N, a->K, a->batch);
+  SGF_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0 && a->a_batch_stride % 8 == 0 && a->b_batch_stride % 8 == 0,
+              "gemm: lda/ldb/batch strides must be multiples of 8 elements (TMA 16-byte strides)");
+  SGF_REQUIRE((reinterpret_cast<uintptr_t>(a->a) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->b) % 16) == 0,
+              "gemm: A/B must be 16-byte aligned");
+  SGF_REQUIRE(a->lda >= a->K && a->ldb >= a->K, "gemm: leading dimension smaller than K");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  GemmShape shp{};
+  shp.M = a->M; shp.N = a->N; shp.K = a->K;
+  GemmEpilogue ep{a->c, a->ldc, a->c_batch_stride, a->c_dtype, a->col_scale, a->col_bias, a->residual,
+                  a->ldr, a->r_batch_stride, a->r_dtype, a->act, a->alpha, a->alpha_cols};
+  if (int rc = check_epilogue_alignment(ep, a->N)) return rc;
+
+  const int m_tiles = (a->M + BM - 1) / BM;
+  const int bn = pick_bn(m_tiles, a->N, a->batch);
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M), static_cast<uint64_t>(a->batch)};
+    uint64_t strides[2] = {static_cast<uint64_t>(a->lda) * 2,
+                           static_cast<uint64_t>(a->batch > 1 ? a->a_batch_stride : a->lda * (int64_t)a->M) * 2};
+    uint32_t box[3] = {BK, BM, 1};
+    if (int rc = encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dims, strides, box,
+                             CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->batch)};
+    uint64_t strides[2] = {static_cast<uint64_t>(a->ldb) * 2,
+                           static_cast<uint64_t>(a->batch > 1 ? a->b_batch_stride : a->ldb * (int64_t)a->N) * 2};
+    uint32_t box[3] = {BK, static_cast<uint32_t>(bn), 1};
+    if (int rc = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->b, dims, strides, box,
+                             CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  dim3 grid((a->N + bn - 1) / bn, m_tiles, a->batch);
+  switch (bn) {
+    case 32: return launch_gemm<32, 4, false>(tmA, tmB, shp, ep, grid, st);
+    case 64: return launch_gemm<64, 4, false>(tmA, tmB, shp, ep, grid, st);
+    default: return launch_gemm<128, 3, false>(tmA, tmB, shp, ep, grid, st);
+  }
+}
+
+extern "C" int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* a, void* stream) {
+  SGF_REQUIRE(a != nullptr, "conv3x3: null args");
+  SGF_REQUIRE(a->cin % 64 == 0, "conv3x3: Cin must be a multiple of 64 (got %d)", a->cin);
+  SGF_REQUIRE(a->cout % 8 == 0, "conv3x3: Cout must be a multiple of 8 (got %d)", a->cout);
+  SGF_REQUIRE(a->n > 0 && a->h > 0 && a->w_ > 0, "conv3x3: bad shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  // 128-pixel tile = bw x bh rectangle; bw = smallest power of two >= min(W,128)
+  int bw = 1;
+  while (bw < a->w_ && bw < 128) bw <<= 1;
+  const int bh = 128 / bw;
+  GemmShape shp{};
+  shp.M = a->n * a->h * a->w_;
+  shp.N = a->cout;
+  shp.K = 9 * a->cin;
+  shp.H = a->h; shp.W = a->w_; shp.bw = bw; shp.bh = bh;
+  shp.tiles_w = (a->w_ + bw - 1) / bw;
+  shp.tiles_h = (a->h + bh - 1) / bh;
+  shp.cin_blocks = a->cin / 64;
+  GemmEpilogue ep{a->y, a->cout, 0, SGF_BF16, a->col_scale, a->col_bias, nullptr, 0, 0, SGF_BF16, a->act, 1.0f, 0};
+  if (int rc = check_epilogue_alignment(ep, a->cout)) return rc;
+
+  const int m_tiles = a->n * shp.tiles_w * shp.tiles_h;
+  const int bn = pick_bn(m_tiles, a->cout, 1);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(a->cin), static_cast<uint64_t>(a->w_), static_cast<uint64_t>(a->h),
+                        static_cast<uint64_t>(a->n)};
+    uint64_t strides[3] = {static_cast<uint64_t>(a->cin) * 2, static_cast<uint64_t>(a->cin) * a->w_ * 2,
+                           static_cast<uint64_t>(a->cin) * a->w_ * a->h * 2};
+    uint32_t box[4] = {BK, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), 1};
+    if (int rc = encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a->x, dims, strides, box,
+                             CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(shp.K), static_cast<uint64_t>(a->cout), 1};
+    uint64_t strides[2] = {static_cast<uint64_t>(shp.K) * 2, static_cast<uint64_t>(shp.K) * a->cout * 2};
+    uint32_t box[3] = {BK, static_cast<uint32_t>(bn), 1};
+    if (int rc = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->w, dims, strides, box,
+                             CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  dim3 grid((a->cout + bn - 1) / bn, m_tiles, 1);
+  switch (bn) {
+    case 32: return launch_gemm<32, 4, true>(tmA, tmB, shp, ep, grid, st);
+    case 64: return launch_gemm<64, 4, true>(tmA, tmB, shp, ep, grid, st);
+    default: return launch_gemm<128, 3, true>(tmA, tmB, shp, ep, grid, st);
+  }
+}

@@ -1,0 +1,346 @@
+// HBM-bound row / layout kernels: fused LayerNorm(+gather, +residual, +second LayerNorm),
+// attention rel-pos bias assembly, stem layout helpers (NCHW->NHWC, im2col for the few strided
+// convolutions, max-pool).  Warp-shuffle reductions, 128-bit global accesses.
+#include "common.cuh"
+
+namespace sgf {
+
+// ----------------------------------------------------------------------------------------
+// fused row LayerNorm: one warp per row, row kept in registers (CH chunks of 8 per lane)
+// ----------------------------------------------------------------------------------------
+struct RowLnParams {
+  const void* x; int64_t ldx; int x_dtype;
+  const int64_t* gather_idx;
+  const float* pre_add;
+  const float* g1; const float* b1;
+  const void* residual; int64_t ldr; int r_dtype;
+  void* out1; int64_t ld1; int out1_dtype;
+  const float* g2; const float* b2;
+  void* out2; int64_t ld2;
+  const uint8_t* zero_row;
+  int rows, D;
+  int seg_len, seg_stride, seg_off;
+};
+
+SGF_DEVICE void load8(const void* base, int dtype, int64_t elem_off, float (&v)[8]) {
+  if (dtype == SGF_F32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
+    const float4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+}
+SGF_DEVICE void store8(void* base, int dtype, int64_t elem_off, const float (&v)[8]) {
+  if (dtype == SGF_F32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = u;
+  }
+}
+
+template <int CH>
+SGF_DEVICE void warp_layernorm(float (&v)[CH][8], int D, int lane, const float* g, const float* b) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    if ((lane + 32 * i) * 8 < D) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    if ((lane + 32 * i) * 8 < D) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int e = (lane + 32 * i) * 8;
+    if (e < D) {
+      float gg[8], bb[8];
+      load8(g, SGF_F32, e, gg);
+      load8(b, SGF_F32, e, bb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
+    }
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) row_layernorm_kernel(const RowLnParams p) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int64_t src_row = p.gather_idx ? p.gather_idx[row] : row;
+  int64_t dst_row = row;
+  if (p.seg_len > 0) dst_row = static_cast<int64_t>(row / p.seg_len) * p.seg_stride + p.seg_off + row % p.seg_len;
+  const bool zero = p.zero_row && p.zero_row[row];
+
+  float v[CH][8];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int e = (lane + 32 * i) * 8;
+    if (e < p.D) {
+      load8(p.x, p.x_dtype, src_row * p.ldx + e, v[i]);
+      if (p.pre_add) {
+        float a[8];
+        load8(p.pre_add, SGF_F32, e, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] += a[j];
+      }
+    }
+  }
+  if (p.g1) warp_layernorm<CH>(v, p.D, lane, p.g1, p.b1);
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int e = (lane + 32 * i) * 8;
+    if (e < p.D) {
+      if (p.residual) {
+        float r[8];
+        load8(p.residual, p.r_dtype, dst_row * p.ldr + e, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] += r[j];
+      }
+      if (zero) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+      if (p.out1) {
+        store8(p.out1, p.out1_dtype, dst_row * p.ld1 + e, v[i]);
+        if (p.out1_dtype == SGF_BF16 && p.out2) {  // second LN sees exactly what was stored
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] = __bfloat162float(__float2bfloat16_rn(v[i][j]));
+        }
+      }
+    }
+  }
+  if (p.out2) {
+    warp_layernorm<CH>(v, p.D, lane, p.g2, p.b2);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int e = (lane + 32 * i) * 8;
+      if (e < p.D) {
+        if (zero) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+        }
+        store8(p.out2, SGF_BF16, dst_row * p.ld2 + e, v[i]);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// rel-pos bias: bias[h,i,j] += table[bucket[ids[i-lo], ids[j-lo]], h]   for i,j in [lo,hi)
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_rel_bias_kernel(float* bias, int64_t head_stride, int64_t row_stride, int H,
+                                                           const int64_t* __restrict__ bucket, int64_t bucket_ld,
+                                                           const int64_t* __restrict__ ids,
+                                                           const float* __restrict__ table, int lo, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= n) return;
+  const int64_t b = bucket[ids[i] * bucket_ld + ids[j]];
+  const float* t = table + b * H;
+  float* dst = bias + static_cast<int64_t>(lo + i) * row_stride + lo + j;
+  for (int h = 0; h < H; ++h) dst[h * head_stride] += t[h];
+}
+
+// ----------------------------------------------------------------------------------------
+// stem helpers
+// ----------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int c, int h,
+                                    int w) {
+  const int64_t total = static_cast<int64_t>(n) * h * w;
+  const int64_t pix = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (pix >= total) return;
+  const int64_t img = pix / (static_cast<int64_t>(h) * w);
+  const int64_t hw = pix - img * h * w;
+  for (int cc = 0; cc < c; ++cc)
+    y[pix * c + cc] = __float2bfloat16_rn(x[(img * c + cc) * static_cast<int64_t>(h) * w + hw]);
+}
+
+// generic im2col, one thread per (output pixel, tap, 8-channel group or single channel)
+template <bool kVec>
+__global__ void im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int n, int h,
+                              int w, int c, int kh, int kw, int stride, int pad, int ho, int wo, int64_t ld_out) {
+  const int cg = kVec ? c / 8 : c;
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * kh * kw * cg;
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int g = idx % cg;
+  int64_t t = idx / cg;
+  const int tap = t % (kh * kw);
+  t /= (kh * kw);
+  const int ox = t % wo;
+  t /= wo;
+  const int oy = t % ho;
+  const int img = t / ho;
+  const int ky = tap / kw, kx = tap % kw;
+  const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+  const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
+  const int64_t orow = (static_cast<int64_t>(img) * ho + oy) * wo + ox;
+  if (kVec) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ok) v = *reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(img) * h + iy) * w + ix) * c + g * 8);
+    *reinterpret_cast<uint4*>(out + orow * ld_out + static_cast<int64_t>(tap) * c + g * 8) = v;
+  } else {
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (ok) v = x[((static_cast<int64_t>(img) * h + iy) * w + ix) * c + g];
+    out[orow * ld_out + static_cast<int64_t>(tap) * c + g] = v;
+  }
+}
+
+__global__ void zero_pad_cols_kernel(__nv_bfloat16* out, int64_t rows, int k_valid, int64_t ld_out) {
+  const int padw = static_cast<int>(ld_out) - k_valid;
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= rows * padw) return;
+  out[(idx / padw) * ld_out + k_valid + idx % padw] = __float2bfloat16_rn(0.f);
+}
+
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h,
+                                    int w, int c, int ho, int wo) {
+  const int cg = c / 8;
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * cg;
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int g = idx % cg;
+  int64_t t = idx / cg;
+  const int ox = t % wo;
+  t /= wo;
+  const int oy = t % ho;
+  const int img = t / ho;
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 - 1 + ky;
+    if (iy < 0 || iy >= h) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 - 1 + kx;
+      if (ix < 0 || ix >= w) continue;
+      float v[8];
+      load8(x, SGF_BF16, ((static_cast<int64_t>(img) * h + iy) * w + ix) * c + g * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    }
+  }
+  store8(y, SGF_BF16, ((static_cast<int64_t>(img) * ho + oy) * wo + ox) * c + g * 8, m);
+}
+
+}  // namespace sgf
+
+using namespace sgf;
+
+extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
+  SGF_REQUIRE(a != nullptr, "row_layernorm: null args");
+  SGF_REQUIRE(a->rows > 0 && a->D > 0 && a->D % 8 == 0, "row_layernorm: D must be a positive multiple of 8 (D=%d)", a->D);
+  SGF_REQUIRE(a->D <= 5120, "row_layernorm: D=%d exceeds the 5120 register-resident limit", a->D);
+  SGF_REQUIRE((a->g1 == nullptr) == (a->b1 == nullptr), "row_layernorm: g1/b1 must both be set or both null");
+  SGF_REQUIRE(!a->out2 || (a->g2 && a->b2), "row_layernorm: out2 needs g2/b2");
+  SGF_REQUIRE(a->out1 || a->out2, "row_layernorm: no output");
+  SGF_REQUIRE(a->ldx % 8 == 0 && (!a->out1 || a->ld1 % 8 == 0) && (!a->out2 || a->ld2 % 8 == 0) &&
+                  (!a->residual || a->ldr % 8 == 0),
+              "row_layernorm: row strides must be multiples of 8 elements");
+  RowLnParams p{a->x, a->ldx, a->x_dtype, a->gather_idx, a->pre_add, a->g1, a->b1, a->residual, a->ldr, a->r_dtype,
+                a->out1, a->ld1, a->out1_dtype, a->g2, a->b2, a->out2, a->ld2, a->zero_row, a->rows, a->D,
+                a->seg_len, a->seg_stride, a->seg_off};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int warps = 8;
+  dim3 grid((a->rows + warps - 1) / warps), block(warps * 32);
+  const int ch = (a->D + 255) / 256;
+  if (ch <= 1) row_layernorm_kernel<1><<<grid, block, 0, st>>>(p);
+  else if (ch <= 2) row_layernorm_kernel<2><<<grid, block, 0, st>>>(p);
+  else if (ch <= 3) row_layernorm_kernel<3><<<grid, block, 0, st>>>(p);
+  else if (ch <= 4) row_layernorm_kernel<4><<<grid, block, 0, st>>>(p);
+  else if (ch <= 8) row_layernorm_kernel<8><<<grid, block, 0, st>>>(p);
+  else if (ch <= 12) row_layernorm_kernel<12><<<grid, block, 0, st>>>(p);
+  else if (ch <= 16) row_layernorm_kernel<16><<<grid, block, 0, st>>>(p);
+  else row_layernorm_kernel<20><<<grid, block, 0, st>>>(p);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
+
+extern "C" int sgf_add_rel_bias(const sgf_relbias_args* a, void* stream) {
+  SGF_REQUIRE(a != nullptr && a->bias && a->bucket && a->ids && a->table, "add_rel_bias: null pointer");
+  const int n = a->blk_hi - a->blk_lo;
+  SGF_REQUIRE(n > 0 && a->blk_lo >= 0 && a->blk_hi <= a->Tq && a->blk_hi <= a->Tk, "add_rel_bias: bad block [%d,%d)",
+              a->blk_lo, a->blk_hi);
+  dim3 grid((n + 255) / 256, n), block(256);
+  add_rel_bias_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      a->bias, a->head_stride, a->row_stride, a->H, a->bucket, a->bucket_ld, a->ids, a->table, a->blk_lo, n);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
+
+extern "C" int sgf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w,
+                                         void* stream) {
+  SGF_REQUIRE(x && y && n > 0 && c > 0 && h > 0 && w > 0, "nchw_to_nhwc: bad args");
+  const int64_t total = static_cast<int64_t>(n) * h * w;
+  nchw_to_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(y), n, c, h, w);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
+
+extern "C" int sgf_im2col_nhwc(const void* x, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t kh,
+                               int32_t kw, int32_t stride, int32_t pad, int32_t ho, int32_t wo, int64_t ld_out,
+                               void* stream) {
+  SGF_REQUIRE(x && out, "im2col: null pointer");
+  const int k_valid = kh * kw * c;
+  SGF_REQUIRE(ld_out >= k_valid && ld_out % 8 == 0, "im2col: ld_out=%lld must be >= %d and a multiple of 8",
+              (long long)ld_out, k_valid);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool vec = (c % 8) == 0;
+  const int64_t rows = static_cast<int64_t>(n) * ho * wo;
+  const int64_t total = rows * kh * kw * (vec ? c / 8 : c);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (vec)
+    im2col_kernel<true><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c, kh, kw, stride,
+                                                pad, ho, wo, ld_out);
+  else
+    im2col_kernel<false><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                 reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c, kh, kw, stride,
+                                                 pad, ho, wo, ld_out);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  if (ld_out > k_valid) {
+    const int64_t tp = rows * (ld_out - k_valid);
+    zero_pad_cols_kernel<<<static_cast<unsigned>((tp + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<__nv_bfloat16*>(out), rows, k_valid, ld_out);
+    SGF_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return SGF_OK;
+}
+
+extern "C" int sgf_maxpool3x3s2_nhwc(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho,
+                                     int32_t wo, void* stream) {
+  SGF_REQUIRE(x && y && c % 8 == 0, "maxpool: C must be a multiple of 8");
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * (c / 8);
+  maxpool3x3s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), n, h, w, c, ho, wo);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}

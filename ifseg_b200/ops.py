@@ -1,0 +1,187 @@
+"""Thin torch-tensor front-ends of the C ABI (one function per extern "C" entry point).
+
+PyTorch is plumbing only here: it owns device memory (caching allocator) and the current
+stream; every FLOP of the hot path runs in libsegofa_b200.so.  All wrappers launch on
+torch.cuda.current_stream() so that DDP hooks, record_function ranges and CUDA-graph capture
+see them.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, SGF_BF16, SGF_F32  # noqa: F401
+
+_DT = {torch.bfloat16: SGF_BF16, torch.float32: SGF_F32}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _req(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the segofa_b200 hot path has no CPU fallback")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def launch_count():
+    return int(_lib.load().sgf_launch_count())
+
+
+def reset_launch_count():
+    _lib.load().sgf_reset_launch_count()
+
+
+def gemm(a, b, out=None, *, bias=None, scale=None, residual=None, act=ACT_NONE, alpha=1.0, alpha_cols=0,
+         out_dtype=torch.bfloat16, batch=1, M=None, N=None, K=None, lda=None, ldb=None, ldc=None, ldr=None,
+         a_batch_stride=0, b_batch_stride=0, c_batch_stride=0, r_batch_stride=0):
+    """out[M,N] = epilogue(a[M,K] @ b[N,K]^T).  a, b bf16 with unit inner stride; explicit
+    M/N/K/ld*/batch strides allow strided views (heads, concatenated buffers)."""
+    lib = _lib.load()
+    _req(a, torch.bfloat16, "a")
+    _req(b, torch.bfloat16, "b")
+    if M is None:
+        M, K = a.shape[-2], a.shape[-1]
+    if N is None:
+        N = b.shape[-2]
+    lda = a.stride(-2) if lda is None else lda
+    ldb = b.stride(-2) if ldb is None else ldb
+    if out is None:
+        out = torch.empty((M, N) if batch == 1 else (batch, M, N), dtype=out_dtype, device=a.device)
+        if batch > 1:
+            c_batch_stride = M * N
+    ldc = out.stride(-2) if ldc is None else ldc
+    args = _lib.GemmArgs(
+        _p(a), lda, a_batch_stride, _p(b), ldb, b_batch_stride, _p(out), ldc, c_batch_stride, _DT[out.dtype],
+        M, N, K, batch, _p(scale), _p(bias), _p(residual),
+        (residual.stride(-2) if ldr is None else ldr) if residual is not None else 0, r_batch_stride,
+        _DT[residual.dtype] if residual is not None else SGF_BF16, act, float(alpha), int(alpha_cols))
+    _lib.check(lib.sgf_gemm_bf16(C.byref(args), _stream()), "sgf_gemm_bf16")
+    return out
+
+
+def conv3x3_s1(x, w, scale, bias, act=ACT_RELU, out=None):
+    """x [N,H,W,Cin] bf16 NHWC, w [Cout,3,3,Cin] bf16 -> [N,H,W,Cout] bf16."""
+    lib = _lib.load()
+    _req(x, torch.bfloat16, "x")
+    _req(w, torch.bfloat16, "w")
+    n, h, wd, cin = x.shape
+    cout = w.shape[0]
+    assert x.is_contiguous() and w.is_contiguous()
+    if out is None:
+        out = torch.empty((n, h, wd, cout), dtype=torch.bfloat16, device=x.device)
+    args = _lib.Conv3x3Args(_p(x), _p(w), _p(out), n, h, wd, cin, cout, _p(scale), _p(bias), act)
+    _lib.check(lib.sgf_conv3x3_s1_nhwc(C.byref(args), _stream()), "sgf_conv3x3_s1_nhwc")
+    return out
+
+
+def nchw_to_nhwc_bf16(x):
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    n, c, h, w = x.shape
+    x = x.contiguous()
+    y = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.sgf_nchw_f32_to_nhwc_bf16(_p(x), _p(y), n, c, h, w, _stream()), "sgf_nchw_f32_to_nhwc_bf16")
+    return y
+
+
+def im2col(x, kh, kw, stride, pad, ld_out=None):
+    """x [N,H,W,C] bf16 -> ([N*Ho*Wo, ld_out] bf16, Ho, Wo); K index = (ky*kw+kx)*C + c."""
+    lib = _lib.load()
+    _req(x, torch.bfloat16, "x")
+    n, h, w, c = x.shape
+    ho = (h + 2 * pad - kh) // stride + 1
+    wo = (w + 2 * pad - kw) // stride + 1
+    k = kh * kw * c
+    ld_out = (k + 7) // 8 * 8 if ld_out is None else ld_out
+    out = torch.empty((n * ho * wo, ld_out), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.sgf_im2col_nhwc(_p(x), _p(out), n, h, w, c, kh, kw, stride, pad, ho, wo, ld_out, _stream()),
+               "sgf_im2col_nhwc")
+    return out, ho, wo
+
+
+def maxpool3x3s2(x):
+    lib = _lib.load()
+    _req(x, torch.bfloat16, "x")
+    n, h, w, c = x.shape
+    ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    y = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.sgf_maxpool3x3s2_nhwc(_p(x), _p(y), n, h, w, c, ho, wo, _stream()), "sgf_maxpool3x3s2_nhwc")
+    return y
+
+
+def row_layernorm(x, *, rows=None, D=None, ldx=None, gather_idx=None, pre_add=None, ln1=None, residual=None,
+                  ldr=None, out1=None, ld1=None, ln2=None, out2=None, ld2=None, zero_row=None, seg=None):
+    """See sgf_row_layernorm in include/segofa_b200.h.  ln1/ln2 = (gamma, beta) fp32 tensors."""
+    lib = _lib.load()
+    _req(x, None, "x")
+    rows = x.shape[0] if rows is None else rows
+    D = x.shape[-1] if D is None else D
+    seg_len, seg_stride, seg_off = seg if seg is not None else (0, 0, 0)
+    args = _lib.RowLnArgs(
+        _p(x), x.stride(-2) if ldx is None else ldx, _DT[x.dtype], _p(gather_idx), _p(pre_add),
+        _p(ln1[0]) if ln1 else None, _p(ln1[1]) if ln1 else None,
+        _p(residual), (residual.stride(-2) if ldr is None else ldr) if residual is not None else 0,
+        _DT[residual.dtype] if residual is not None else SGF_BF16,
+        _p(out1), (out1.stride(-2) if ld1 is None else ld1) if out1 is not None else 0,
+        _DT[out1.dtype] if out1 is not None else SGF_BF16,
+        _p(ln2[0]) if ln2 else None, _p(ln2[1]) if ln2 else None,
+        _p(out2), (out2.stride(-2) if ld2 is None else ld2) if out2 is not None else 0,
+        _p(zero_row), rows, D, seg_len, seg_stride, seg_off)
+    _lib.check(lib.sgf_row_layernorm(C.byref(args), _stream()), "sgf_row_layernorm")
+
+
+def add_rel_bias(bias, bucket, ids, table, lo, hi):
+    """bias [H,Tq,Tk(padded stride)] fp32 += table[bucket[ids_i, ids_j], h] on [lo,hi)^2."""
+    lib = _lib.load()
+    _req(bias, torch.float32, "bias")
+    _req(bucket, torch.int64, "bucket")
+    _req(ids, torch.int64, "ids")
+    _req(table, torch.float32, "table")
+    H, Tq, _ = bias.shape
+    args = _lib.RelBiasArgs(_p(bias), bias.stride(0), bias.stride(1), H, Tq, bias.shape[2], _p(bucket),
+                            bucket.stride(0), _p(ids), _p(table), lo, hi)
+    _lib.check(lib.sgf_add_rel_bias(C.byref(args), _stream()), "sgf_add_rel_bias")
+
+
+def attention(q, k, v, out, *, B, H, Tq, Tk, q_strides, k_strides, v_strides, o_strides, bias=None,
+              head_scale=None, key_padding_mask=None, causal=False):
+    """q/k/v/out: bf16 tensors used as base pointers; *_strides = (row_stride, batch_stride) in elements."""
+    lib = _lib.load()
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _req(t, torch.bfloat16, n)
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+    args = _lib.AttentionArgs(
+        _p(q), q_strides[0], q_strides[1], _p(k), k_strides[0], k_strides[1], _p(v), v_strides[0], v_strides[1],
+        _p(out), o_strides[0], o_strides[1],
+        _p(bias), bias.stride(0) if bias is not None else 0, bias.stride(1) if bias is not None else 0,
+        _p(head_scale), _p(key_padding_mask), B, H, Tq, Tk, 1 if causal else 0)
+    _lib.check(lib.sgf_attention_bf16(C.byref(args), _stream()), "sgf_attention_bf16")
+    return out
+
+
+def upsample_argmax(logits, hp, wp, h, w, target=None, num_tokens=None):
+    """logits fp32 [B, >=hp*wp, C] -> mask int64 [B,h,w] (+ optional (intersect, pred, label) areas)."""
+    lib = _lib.load()
+    _req(logits, torch.float32, "logits")
+    B, _, Cn = logits.shape
+    assert logits.stride(2) == 1
+    mask = torch.empty((B, h, w), dtype=torch.int64, device=logits.device)
+    areas = None
+    if target is not None:
+        _req(target, torch.int64, "target")
+        areas = torch.zeros((3, Cn), dtype=torch.float32, device=logits.device)
+    args = _lib.SegmaskArgs(_p(logits), logits.stride(0), logits.stride(1), B, Cn, hp, wp, h, w, _p(mask),
+                            _p(target), _p(areas[0]) if areas is not None else None,
+                            _p(areas[1]) if areas is not None else None,
+                            _p(areas[2]) if areas is not None else None)
+    _lib.check(lib.sgf_upsample_argmax(C.byref(args), _stream()), "sgf_upsample_argmax")
+    return (mask, areas) if target is not None else mask

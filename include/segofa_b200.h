@@ -1,0 +1,185 @@
+/* segofa_b200 -- C ABI of the B200-native segofa hot path (libsegofa_b200.so).
+ *
+ * The reference (alinlab/ifseg) has NO native/FFI layer on this path: every op below is a
+ * PyTorch ATen call issued from Python.  Each entry point therefore cites
+ * the reference *Python call site* whose ATen ops it replaces; the binding a maintainer adds
+ * on the reference side is a ctypes stub.
+ *
+ * Conventions
+ *  - plain pointers + sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *  - every function takes the cudaStream_t to launch on as `void* stream` and is asynchronous;
+ *  - return value: 0 = SGF_OK, otherwise an SGF_ERR_* code; sgf_last_error() gives the message
+ *    (thread-local).  SGF_ERR_OOM messages contain "out of memory" so that the Python wrapper
+ *    raises the RuntimeError that trainer.py:807-822 knows how to recover from;
+ *  - no hidden allocations: scratch is passed in by the caller;
+ *  - dtype enums: SGF_BF16 = 0, SGF_F32 = 1.
+ */
+#ifndef SEGOFA_B200_H_
+#define SEGOFA_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { SGF_OK = 0, SGF_ERR_INVALID = 1, SGF_ERR_CUDA = 2, SGF_ERR_OOM = 3, SGF_ERR_UNSUPPORTED = 4 };
+enum { SGF_BF16 = 0, SGF_F32 = 1 };
+enum { SGF_ACT_NONE = 0, SGF_ACT_RELU = 1, SGF_ACT_GELU = 2 };
+
+const char* sgf_last_error(void);
+int sgf_abi_version(void);
+/* number of kernels launched by this library in the calling process since load / last reset */
+int64_t sgf_launch_count(void);
+void sgf_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Dense contraction  C[z] = epilogue( A[z] (MxK, K-major) * B[z]^T (NxK, K-major) )
+ *   tcgen05.mma (kind::f16, bf16 in / fp32 accumulate in TMEM), TMA-staged 128B-swizzled tiles.
+ * epilogue(v)[m,n]:  v *= col_scale[n]; v += col_bias[n]; if n < alpha_cols: v *= alpha;
+ *                    GELU (act==2); v += residual[m,n]; ReLU (act==1); store as c_dtype.
+ * Replaces torch.nn.functional.linear / addmm at:
+ *   models/segofa/unify_multihead_attention.py:328-345,513 (q/k/v/out_proj, q *= scaling :346)
+ *   models/segofa/unify_transformer_layer.py:279-283,556-560 (fc1+gelu, fc2 + residual :289,566)
+ *   models/segofa/encoder_module.py:416 (image_proj), :765-771 (pos_q/pos_k and their product)
+ *   models/segofa/decoder_module.py:290-294 (seg_projection), :350-364 (self/cross pos bias)
+ *   models/segofa/resnet.py:117-137 (1x1 convolutions as GEMMs over NHWC pixels, with the
+ *   FrozenBatchNorm2d affine frozen_bn.py:40-45, ReLU and the residual add in the epilogue)
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* a; int64_t lda; int64_t a_batch_stride; /* bf16, strides in elements */
+  const void* b; int64_t ldb; int64_t b_batch_stride; /* bf16 [N,K] */
+  void* c; int64_t ldc; int64_t c_batch_stride; int32_t c_dtype;
+  int32_t M, N, K, batch;
+  const float* col_scale; /* [N] or NULL */
+  const float* col_bias;  /* [N] or NULL */
+  const void* residual; int64_t ldr; int64_t r_batch_stride; int32_t r_dtype; /* [M,N] or NULL */
+  int32_t act;
+  float alpha; int32_t alpha_cols;
+} sgf_gemm_args;
+int sgf_gemm_bf16(const sgf_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * 3x3 / stride 1 / pad 1 convolution as an im2col-free implicit GEMM over NHWC bf16:
+ * for every filter tap the A tile is a TMA box of the input shifted by the tap offset
+ * (out-of-bounds pixels are zero-filled by TMA == the zero padding).  Same tcgen05 main loop
+ * and epilogue as sgf_gemm_bf16 (BN affine + ReLU).
+ * Replaces nn.Conv2d(3x3) + FrozenBatchNorm2d + ReLU at models/segofa/resnet.py:122-124.
+ *   x   [N,H,W,Cin]  bf16      w [Cout, 3,3, Cin] bf16 (tap-major K)      y [N,H,W,Cout] bf16
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x; const void* w; void* y;
+  int32_t n, h, w_, cin, cout;
+  const float* col_scale; const float* col_bias; int32_t act;
+} sgf_conv3x3_args;
+int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Stem helpers (HBM-bound layout/gather kernels), models/segofa/resnet.py:215-220:
+ *  - sgf_nchw_f32_to_nhwc_bf16: patch_images [N,3,H,W] fp32 -> [N,H,W,C] bf16
+ *  - sgf_im2col_nhwc: explicit patch matrix for the few strided convs (7x7/2 conv1, the two
+ *    3x3/2 convs, the 1x1/2 downsample convs): out [N*Ho*Wo, ld_out] with K index
+ *    (ky*kw+kx)*C+c, zero padded up to ld_out
+ *  - sgf_maxpool3x3s2_nhwc: nn.MaxPool2d(3,2,1)
+ * ------------------------------------------------------------------------------------- */
+int sgf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
+int sgf_im2col_nhwc(const void* x, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t kh, int32_t kw,
+                    int32_t stride, int32_t pad, int32_t ho, int32_t wo, int64_t ld_out, void* stream);
+int sgf_maxpool3x3s2_nhwc(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho,
+                          int32_t wo, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused row kernel (warp-shuffle LayerNorm, 128-bit loads), one warp per row of width D:
+ *     t    = x[r] (+ pre_add[d])                         x: bf16 or fp32
+ *     u    = ln1 ? LN(t; g1,b1) : t
+ *     v    = u (+ residual[r'])                          residual/out1 share the output row map
+ *     out1[r'] = v            (optional, dtype out1_dtype)
+ *     out2[r'] = LN(v; g2,b2) (optional, bf16)
+ * Output row map: r' = (r / seg_len) * seg_stride + seg_off + r % seg_len  (seg_len==0: r'=r),
+ * which writes straight into a concatenated [B, T, D] buffer (no torch.cat copy).
+ * If `gather_idx` is given, input row r is x[gather_idx[r]] (token embedding lookup).
+ * If `zero_row` is given and zero_row[r] != 0 the outputs are zero (padding rows).
+ * LayerNorm eps 1e-5, fp32 statistics (custom_fairseq/fairseq/modules/layer_norm.py:30-35).
+ * Replaces LayerNorm/residual/dropout(p=0)/cat at unify_transformer_layer.py:256-291,463-568;
+ * encoder_module.py:400-428,751-752,757-760,829-830; decoder_module.py:537,575-576,668-669.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x; int64_t ldx; int32_t x_dtype;
+  const int64_t* gather_idx;
+  const float* pre_add;
+  const float* g1; const float* b1;
+  const void* residual; int64_t ldr; int32_t r_dtype;
+  void* out1; int64_t ld1; int32_t out1_dtype;
+  const float* g2; const float* b2;
+  void* out2; int64_t ld2;
+  const uint8_t* zero_row;
+  int32_t rows, D;
+  int32_t seg_len, seg_stride, seg_off;
+} sgf_rowln_args;
+int sgf_row_layernorm(const sgf_rowln_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Attention bias assembly (batch-invariant, parameter-only):
+ *   bias[h,i,j] = abs[h,i,j] + rel(h,i,j),  fp32, with the rel-pos term a table lookup
+ *   rel = table[bucket[ids_q[i], ids_k[j]], h] inside the square block [blk_lo, blk_hi) of both
+ *   axes and 0 elsewhere; called once for the image block and once for the text block.
+ * Replaces encoder_module.py:313-331,790-809 and decoder_module.py:327-333,601-627 for the
+ * identity-interpolation case (actual grid == orig/seg grid; the general interpolated table is
+ * assembled host-side and added through `dense_add`).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  float* bias; int64_t head_stride; int64_t row_stride; /* in/out: [H,Tq,Tk] fp32 (holds abs on entry) */
+  int32_t H, Tq, Tk;
+  const int64_t* bucket; int64_t bucket_ld; /* int64 [*, bucket_ld] */
+  const int64_t* ids;                       /* [blk_hi-blk_lo] position ids into bucket rows/cols */
+  const float* table;                       /* fp32 [num_rel, H] */
+  int32_t blk_lo, blk_hi;
+} sgf_relbias_args;
+int sgf_add_rel_bias(const sgf_relbias_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused multi-head attention, head_dim 64:  O = softmax(Q K^T + bias + mask) V * head_scale
+ *   QK^T and PV on tcgen05 (S and O tiles in TMEM), K/V tiles by TMA, fp32 online softmax by the
+ *   row-owning threads, probabilities re-staged to shared memory as the bf16 A operand of PV.
+ *   q is expected pre-scaled (the QKV GEMM epilogue applies (2*d_h)^-1/2 to the q columns).
+ *   Element (b,t,h,d) of q/k/v/out lives at base + b*batch_stride + t*row_stride + h*64 + d.
+ *   bias fp32 [H,Tq,Tk] (batch-invariant) or NULL; key_padding_mask uint8 [B,Tk] (1 = masked) or
+ *   NULL; causal != 0 masks j > i (decoder_module.py:878-890).
+ * Replaces unify_multihead_attention.py:459-512 (bmm, bias add, masks, fp32 softmax, bmm,
+ * c_attn scale).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* q; int64_t q_row_stride; int64_t q_batch_stride;
+  const void* k; int64_t k_row_stride; int64_t k_batch_stride;
+  const void* v; int64_t v_row_stride; int64_t v_batch_stride;
+  void* out; int64_t o_row_stride; int64_t o_batch_stride;
+  const float* bias; int64_t bias_head_stride; int64_t bias_row_stride;
+  const float* head_scale;
+  const uint8_t* key_padding_mask;
+  int32_t B, H, Tq, Tk, causal;
+} sgf_attention_args;
+int sgf_attention_bf16(const sgf_attention_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Patch-grid -> mask: bilinear (align_corners=False) upsample of the per-patch logits to
+ * (h,w) fused with argmax over classes; full-resolution logits are never materialised.
+ * Arithmetic order follows ATen's upsample_bilinear2d so that, on identical input logits,
+ * the mask is bit-identical to F.interpolate(...).argmax(-1).
+ *   logits fp32 [B, ld_tok (>= hp*wp), C] (token stride ld_c)  ->  mask int64 [B,h,w]
+ *   optional per-class histograms (float [C] each, accumulated with atomics):
+ *   area_pred, and with `target` (int64 [B,h,w], class ids, <0 or >=C = ignore): area_label,
+ *   area_intersect  (seg_criterion.py:349-362).
+ * Replaces seg_criterion.py:237-244 + :351 (and visualize_segmentation_web.ipynb cell 4).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* logits; int64_t batch_stride; int64_t tok_stride;
+  int32_t B, C, hp, wp, h, w;
+  int64_t* mask;
+  const int64_t* target;
+  float* area_intersect; float* area_pred; float* area_label;
+} sgf_segmask_args;
+int sgf_upsample_argmax(const sgf_segmask_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGOFA_B200_H_ */

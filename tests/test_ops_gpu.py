@@ -1,0 +1,266 @@
+"""-m gpu: every C-ABI kernel against a plain torch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    from ifseg_b200 import ops as o
+
+    return o
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 768, 768), (7488, 2304, 768), (901, 3072, 768),
+                                   (1000, 64, 576), (257, 256, 2304), (77, 15, 768), (130, 40, 128)])
+def test_gemm_plain_and_bias(ops, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ b.float().t() + bias
+    out = ops.gemm(a, b, bias=bias, out_dtype=torch.float32)
+    assert _rel(out, ref) < 2e-5, _rel(out, ref)
+    out16 = ops.gemm(a, b, bias=bias)
+    assert out16.dtype == torch.bfloat16
+    assert _rel(out16, ref) < 4e-3
+
+
+def test_gemm_epilogues(ops):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    M, N, K = 515, 768, 1024
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    scale = torch.rand(N, device="cuda", generator=g) + 0.5
+    res16 = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    res32 = torch.randn(M, N, device="cuda", generator=g)
+    acc = a.float() @ b.float().t()
+    # scale+bias+relu after residual (bottleneck conv3)
+    out = ops.gemm(a, b, scale=scale, bias=bias, residual=res16, act=ops.ACT_RELU, out_dtype=torch.float32)
+    assert _rel(out, F.relu(acc * scale + bias + res16.float())) < 2e-5
+    # gelu (fc1)
+    out = ops.gemm(a, b, bias=bias, act=ops.ACT_GELU, out_dtype=torch.float32)
+    assert _rel(out, F.gelu(acc + bias)) < 2e-5
+    # fp32 residual stream (fc2)
+    out = ops.gemm(a, b, bias=bias, residual=res32, out_dtype=torch.float32)
+    assert _rel(out, acc + bias + res32) < 2e-5
+    # q scaling on the first 256 columns
+    out = ops.gemm(a, b, bias=bias, alpha=0.125, alpha_cols=256, out_dtype=torch.float32)
+    ref = acc + bias
+    ref[:, :256] *= 0.125
+    assert _rel(out, ref) < 2e-5
+
+
+def test_gemm_batched_heads(ops):
+    """abs-pos bias: per-head [T,64] x [T,64]^T out of [T, H*64] buffers, padded fp32 output rows."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    T, H, dh = 333, 12, 64
+    pq = torch.randn(T, H * dh, device="cuda", generator=g).bfloat16()
+    pk = torch.randn(T, H * dh, device="cuda", generator=g).bfloat16()
+    Tp = (T + 63) // 64 * 64
+    out = torch.zeros(H, T, Tp, device="cuda")
+    ops.gemm(pq, pk, out, M=T, N=T, K=dh, batch=H, lda=H * dh, ldb=H * dh, a_batch_stride=dh, b_batch_stride=dh,
+             ldc=Tp, c_batch_stride=T * Tp)
+    ref = torch.einsum("ihd,jhd->hij", pq.float().view(T, H, dh), pk.float().view(T, H, dh))
+    assert _rel(out[:, :, :T], ref) < 2e-5
+    assert out[:, :, T:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 30, 30, 256, 256), (1, 120, 120, 64, 64), (2, 60, 60, 128, 128),
+                                            (1, 8, 8, 64, 64), (1, 33, 17, 64, 128)])
+def test_conv3x3(ops, n, h, w, cin, cout):
+    g = torch.Generator(device="cuda").manual_seed(n * h + cin)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / math.sqrt(9 * cin)).bfloat16()
+    scale = torch.rand(cout, device="cuda", generator=g) + 0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1)
+    ref = F.relu(ref * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    out = ops.conv3x3_s1(x, wt.permute(0, 2, 3, 1).contiguous(), scale, bias, act=ops.ACT_RELU)
+    assert _rel(out, ref) < 4e-3, _rel(out, ref)
+
+
+def test_stem_helpers(ops):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(2, 3, 64, 48, device="cuda", generator=g)
+    y = ops.nchw_to_nhwc_bf16(x)
+    assert torch.equal(y, x.permute(0, 2, 3, 1).bfloat16())
+    # 7x7/2 im2col + GEMM == conv1
+    wt = (torch.randn(64, 3, 7, 7, device="cuda", generator=g) / 12).bfloat16()
+    cols, ho, wo = ops.im2col(y, 7, 7, 2, 3)
+    assert (ho, wo) == (32, 24) and cols.shape[1] == 152
+    wmat = torch.zeros(64, 152, device="cuda", dtype=torch.bfloat16)
+    wmat[:, :147] = wt.permute(0, 2, 3, 1).reshape(64, 147)
+    out = ops.gemm(cols, wmat, K=147, out_dtype=torch.float32).view(2, ho, wo, 64)
+    ref = F.conv2d(y.float().permute(0, 3, 1, 2), wt.float(), stride=2, padding=3).permute(0, 2, 3, 1)
+    assert _rel(out, ref) < 2e-5
+    # 3x3/2 im2col (vector path)
+    x2 = torch.randn(2, 20, 20, 64, device="cuda", generator=g).bfloat16()
+    w2 = (torch.randn(128, 64, 3, 3, device="cuda", generator=g) / 24).bfloat16()
+    cols, ho, wo = ops.im2col(x2, 3, 3, 2, 1)
+    out = ops.gemm(cols, w2.permute(0, 2, 3, 1).reshape(128, 576).contiguous(), out_dtype=torch.float32)
+    ref = F.conv2d(x2.float().permute(0, 3, 1, 2), w2.float(), stride=2, padding=1).permute(0, 2, 3, 1)
+    assert _rel(out.view(2, ho, wo, 128), ref) < 2e-5
+    # 1x1/2 "im2col" = strided subsample
+    cols, ho, wo = ops.im2col(x2, 1, 1, 2, 0)
+    assert torch.equal(cols.view(2, ho, wo, 64), x2[:, ::2, ::2])
+    # maxpool
+    mp = ops.maxpool3x3s2(x2)
+    ref = F.max_pool2d(x2.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).bfloat16()
+    assert torch.equal(mp, ref)
+
+
+@pytest.mark.parametrize("D", [768, 3072, 1024, 256, 4096])
+def test_row_layernorm(ops, D):
+    g = torch.Generator(device="cuda").manual_seed(D)
+    rows = 301
+    x = (torch.randn(rows, D, device="cuda", generator=g) * 3 + 1).bfloat16()
+    g1, b1 = torch.rand(D, device="cuda", generator=g) + 0.5, torch.randn(D, device="cuda", generator=g)
+    g2, b2 = torch.rand(D, device="cuda", generator=g) + 0.5, torch.randn(D, device="cuda", generator=g)
+    out = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    ops.row_layernorm(x, ln2=(g1, b1), out2=out)
+    ref = F.layer_norm(x.float(), (D,), g1, b1, 1e-5)
+    assert _rel(out, ref) < 4e-3
+    assert (out.float() - ref).abs().max() <= 0.02 * ref.abs().max()
+    # res + LN1(x) -> out1 (fp32 stream), LN2(out1) -> out2
+    res = torch.randn(rows, D, device="cuda", generator=g)
+    o1 = torch.empty(rows, D, device="cuda")
+    o2 = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    ops.row_layernorm(x, ln1=(g1, b1), residual=res, out1=o1, ln2=(g2, b2), out2=o2)
+    r1 = res + F.layer_norm(x.float(), (D,), g1, b1, 1e-5)
+    assert _rel(o1, r1) < 1e-5
+    assert _rel(o2, F.layer_norm(r1, (D,), g2, b2, 1e-5)) < 4e-3
+
+
+def test_row_layernorm_gather_segments(ops):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    D, V, B, Tt, P = 768, 1000, 3, 36, 64
+    table = torch.randn(V, D, device="cuda", generator=g)
+    tok = torch.randint(0, V, (B * Tt,), device="cuda", generator=g)
+    type_emb = torch.randn(D, device="cuda", generator=g)
+    gg, bb = torch.rand(D, device="cuda", generator=g) + 0.5, torch.randn(D, device="cuda", generator=g)
+    zero = torch.zeros(B * Tt, dtype=torch.uint8, device="cuda")
+    zero[5] = 1
+    xbuf = torch.full((B, P + Tt, D), 7.0, device="cuda")
+    ops.row_layernorm(table, rows=B * Tt, gather_idx=tok, pre_add=type_emb, ln1=(gg, bb), out1=xbuf.view(-1, D),
+                      zero_row=zero, seg=(Tt, P + Tt, P))
+    ref = F.layer_norm(table[tok] + type_emb, (D,), gg, bb, 1e-5).view(B, Tt, D)
+    ref.view(-1, D)[5] = 0
+    assert _rel(xbuf[:, P:], ref) < 1e-5
+    assert (xbuf[:, :P] == 7.0).all()
+
+
+def _attn_ref(q, k, v, bias, causal, kpm, head_scale):
+    s = torch.einsum("bihd,bjhd->bhij", q.float(), k.float())
+    if bias is not None:
+        s = s + bias[None, :, : s.shape[2], : s.shape[3]]
+    if causal:
+        s = s + torch.full(s.shape[-2:], float("-inf"), device=s.device).triu(1)
+    if kpm is not None:
+        s = s.masked_fill(kpm[:, None, None, :].bool(), float("-inf"))
+    p = s.softmax(-1)
+    o = torch.einsum("bhij,bjhd->bihd", p, v.float())
+    if head_scale is not None:
+        o = o * head_scale.view(1, 1, -1, 1)
+    return o
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,causal,use_bias,use_kpm", [
+    (2, 3, 200, 200, False, True, False),
+    (1, 12, 936, 936, False, True, False),
+    (2, 4, 133, 133, True, True, False),
+    (1, 12, 901, 901, True, True, False),
+    (2, 2, 130, 200, False, True, True),
+    (1, 2, 64, 64, False, False, False),
+    (1, 1, 65, 100, False, False, False),
+])
+def test_attention(ops, B, H, Tq, Tk, causal, use_bias, use_kpm):
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Tq + Tk)
+    dh = 64
+    D = H * dh
+    # self-attention layout: one [B, T, 3D] buffer when Tq == Tk, else separate q and kv buffers
+    q = torch.randn(B, Tq, H, dh, device="cuda", generator=g).bfloat16() * 0.35
+    k = torch.randn(B, Tk, H, dh, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Tk, H, dh, device="cuda", generator=g).bfloat16()
+    Tkp = (Tk + 63) // 64 * 64
+    bias = None
+    if use_bias:
+        bias = torch.zeros(H, Tq, Tkp, device="cuda")
+        bias[:, :, :Tk] = torch.randn(H, Tq, Tk, device="cuda", generator=g)
+    kpm = None
+    if use_kpm:
+        kpm = torch.zeros(B, Tk, dtype=torch.uint8, device="cuda")
+        kpm[0, Tk - 37:] = 1
+        kpm[1, 5] = 1
+    hs = torch.rand(H, device="cuda", generator=g) + 0.5
+    out = torch.empty(B, Tq, D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, out, B=B, H=H, Tq=Tq, Tk=Tk, q_strides=(D, Tq * D), k_strides=(D, Tk * D),
+                  v_strides=(D, Tk * D), o_strides=(D, Tq * D), bias=bias, head_scale=hs, key_padding_mask=kpm,
+                  causal=causal)
+    ref = _attn_ref(q, k, v, bias, causal, kpm, hs).reshape(B, Tq, D)
+    err = _rel(out, ref)
+    assert err < 8e-3, err
+
+
+def test_attention_fused_qkv_layout(ops):
+    g = torch.Generator(device="cuda").manual_seed(99)
+    B, T, H, dh = 2, 150, 12, 64
+    D = H * dh
+    qkv = (torch.randn(B, T, 3 * D, device="cuda", generator=g) * 0.5).bfloat16()
+    out = torch.empty(B, T, D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(qkv, qkv[:, :, D:], qkv[:, :, 2 * D:], out, B=B, H=H, Tq=T, Tk=T, q_strides=(3 * D, T * 3 * D),
+                  k_strides=(3 * D, T * 3 * D), v_strides=(3 * D, T * 3 * D), o_strides=(D, T * D))
+    q, k, v = (t.reshape(B, T, H, dh) for t in qkv.split(D, dim=-1))
+    ref = _attn_ref(q, k, v, None, False, None, None).reshape(B, T, D)
+    assert _rel(out, ref) < 8e-3
+
+
+@pytest.mark.parametrize("B,C,hp,wp,h,w", [(2, 15, 30, 30, 480, 480), (1, 150, 8, 8, 128, 128), (1, 171, 32, 32, 500, 375),
+                                           (2, 15, 30, 40, 480, 640)])
+def test_upsample_argmax_bit_exact(ops, B, C, hp, wp, h, w):
+    g = torch.Generator(device="cuda").manual_seed(C + h)
+    logits = torch.randn(B, hp * wp + 1, C, device="cuda", generator=g)
+    mask = ops.upsample_argmax(logits, hp, wp, h, w)
+    x = logits[:, :-1].reshape(B, hp, wp, C).permute(0, 3, 1, 2)
+    up_gpu = F.interpolate(x, size=(h, w), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    up_cpu = F.interpolate(x.cpu(), size=(h, w), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    ref_cpu = up_cpu.argmax(-1)
+    mism_cpu = (mask.cpu() != ref_cpu).sum().item()
+    mism_gpu = (mask != up_gpu.argmax(-1)).sum().item()
+    print(f"mismatch vs ATen CPU {mism_cpu}, vs ATen CUDA {mism_gpu} of {mask.numel()}")
+    assert mism_cpu == 0  # the oracle (CPU reference) mask is reproduced bit-exactly
+    # histograms
+    target = torch.randint(-1, C + 1, (B, h, w), device="cuda", generator=g)
+    mask2, areas = ops.upsample_argmax(logits, hp, wp, h, w, target=target)
+    assert torch.equal(mask2, mask)
+    valid = (target >= 0) & (target < C)
+    pred, tgt = mask[valid], target[valid]
+    inter = pred[pred == tgt]
+    ai = torch.histc(inter.float(), bins=C, min=0, max=C - 1)
+    ap = torch.histc(pred.float(), bins=C, min=0, max=C - 1)
+    al = torch.histc(tgt.float(), bins=C, min=0, max=C - 1)
+    assert torch.equal(areas[0], ai) and torch.equal(areas[1], ap) and torch.equal(areas[2], al)
+
+
+def test_add_rel_bias(ops):
+    g = torch.Generator(device="cuda").manual_seed(21)
+    H, T, lo, hi = 4, 100, 10, 74
+    bias = torch.randn(H, T, 128, device="cuda", generator=g)
+    before = bias.clone()
+    bucket = torch.randint(0, 50, (90, 90), device="cuda", generator=g)
+    ids = torch.randint(0, 90, (hi - lo,), device="cuda", generator=g)
+    table = torch.randn(50, H, device="cuda", generator=g)
+    ops.add_rel_bias(bias, bucket, ids, table, lo, hi)
+    ref = before.clone()
+    ref[:, lo:hi, lo:hi] += table[bucket[ids][:, ids]].permute(2, 0, 1)
+    assert torch.allclose(bias, ref, atol=1e-6)
