@@ -51,12 +51,14 @@ class RowLnArgs(C.Structure):
     ]
 
 
-class RelBiasArgs(C.Structure):
+class RelBlock(C.Structure):
+    _fields_ = [("bucket", _vp), ("bucket_ld", _i64), ("ids", _vp), ("table", _vp), ("lo", _i32), ("hi", _i32)]
+
+
+class BiasArgs(C.Structure):
     _fields_ = [
-        ("bias", _vp), ("head_stride", _i64), ("row_stride", _i64),
-        ("H", _i32), ("Tq", _i32), ("Tk", _i32),
-        ("bucket", _vp), ("bucket_ld", _i64), ("ids", _vp), ("table", _vp),
-        ("blk_lo", _i32), ("blk_hi", _i32),
+        ("out", _vp), ("abs", _vp), ("head_stride", _i64), ("row_stride", _i64), ("dense_add", _vp),
+        ("H", _i32), ("Tq", _i32), ("Tk", _i32), ("num_blocks", _i32), ("blocks", RelBlock * 2),
     ]
 
 
@@ -93,7 +95,7 @@ EXPORTS = [
     ("sgf_im2col_nhwc", C.c_int, [_vp, _vp] + [_i32] * 10 + [_i64, _vp]),
     ("sgf_maxpool3x3s2_nhwc", C.c_int, [_vp, _vp] + [_i32] * 6 + [_vp]),
     ("sgf_row_layernorm", C.c_int, [C.POINTER(RowLnArgs), _vp]),
-    ("sgf_add_rel_bias", C.c_int, [C.POINTER(RelBiasArgs), _vp]),
+    ("sgf_build_attn_bias", C.c_int, [C.POINTER(BiasArgs), _vp]),
     ("sgf_attention_bf16", C.c_int, [C.POINTER(AttentionArgs), _vp]),
     ("sgf_upsample_argmax", C.c_int, [C.POINTER(SegmaskArgs), _vp]),
 ]

@@ -135,31 +135,36 @@ __global__ void __launch_bounds__(256) row_layernorm_kernel(const RowLnParams p)
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       const int e = (lane + 32 * i) * 8;
-      if (e < p.D) {
-        if (zero) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
-        }
-        store8(p.out2, SGF_BF16, dst_row * p.ld2 + e, v[i]);
-      }
+      if (e < p.D) store8(p.out2, SGF_BF16, dst_row * p.ld2 + e, v[i]);
     }
   }
 }
 
 // ----------------------------------------------------------------------------------------
-// rel-pos bias: bias[h,i,j] += table[bucket[ids[i-lo], ids[j-lo]], h]   for i,j in [lo,hi)
+// attention bias: out = abs (+ dense_add) + rel-pos table lookups on up to two square blocks
 // ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) add_rel_bias_kernel(float* bias, int64_t head_stride, int64_t row_stride, int H,
-                                                           const int64_t* __restrict__ bucket, int64_t bucket_ld,
-                                                           const int64_t* __restrict__ ids,
-                                                           const float* __restrict__ table, int lo, int n) {
+struct BiasParams {
+  float* out; const float* abs; int64_t head_stride, row_stride; const float* dense_add;
+  int H, Tq, Tk, num_blocks;
+  sgf_relblock blk[2];
+};
+__global__ void __launch_bounds__(256) build_attn_bias_kernel(const BiasParams p) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;
-  if (j >= n) return;
-  const int64_t b = bucket[ids[i] * bucket_ld + ids[j]];
-  const float* t = table + b * H;
-  float* dst = bias + static_cast<int64_t>(lo + i) * row_stride + lo + j;
-  for (int h = 0; h < H; ++h) dst[h * head_stride] += t[h];
+  if (j >= p.Tk) return;
+  const float* t = nullptr;
+  for (int b = 0; b < p.num_blocks; ++b) {
+    const sgf_relblock& k = p.blk[b];
+    if (i >= k.lo && i < k.hi && j >= k.lo && j < k.hi)
+      t = k.table + k.bucket[k.ids[i - k.lo] * k.bucket_ld + k.ids[j - k.lo]] * p.H;
+  }
+  const int64_t off = static_cast<int64_t>(i) * p.row_stride + j;
+  for (int h = 0; h < p.H; ++h) {
+    float v = p.abs[h * p.head_stride + off];
+    if (p.dense_add) v += p.dense_add[h * p.head_stride + off];
+    if (t) v += t[h];
+    p.out[h * p.head_stride + off] = v;
+  }
 }
 
 // ----------------------------------------------------------------------------------------
@@ -278,14 +283,19 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
   return SGF_OK;
 }
 
-extern "C" int sgf_add_rel_bias(const sgf_relbias_args* a, void* stream) {
-  SGF_REQUIRE(a != nullptr && a->bias && a->bucket && a->ids && a->table, "add_rel_bias: null pointer");
-  const int n = a->blk_hi - a->blk_lo;
-  SGF_REQUIRE(n > 0 && a->blk_lo >= 0 && a->blk_hi <= a->Tq && a->blk_hi <= a->Tk, "add_rel_bias: bad block [%d,%d)",
-              a->blk_lo, a->blk_hi);
-  dim3 grid((n + 255) / 256, n), block(256);
-  add_rel_bias_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      a->bias, a->head_stride, a->row_stride, a->H, a->bucket, a->bucket_ld, a->ids, a->table, a->blk_lo, n);
+extern "C" int sgf_build_attn_bias(const sgf_bias_args* a, void* stream) {
+  SGF_REQUIRE(a != nullptr && a->out && a->abs, "build_attn_bias: null pointer");
+  SGF_REQUIRE(a->H > 0 && a->Tq > 0 && a->Tk > 0 && a->row_stride >= a->Tk, "build_attn_bias: bad shape");
+  SGF_REQUIRE(a->num_blocks >= 0 && a->num_blocks <= 2, "build_attn_bias: at most 2 blocks");
+  BiasParams p{a->out, a->abs, a->head_stride, a->row_stride, a->dense_add, a->H, a->Tq, a->Tk, a->num_blocks, {}};
+  for (int b = 0; b < a->num_blocks; ++b) {
+    const sgf_relblock& k = a->blocks[b];
+    SGF_REQUIRE(k.bucket && k.ids && k.table && k.lo >= 0 && k.hi > k.lo && k.hi <= a->Tq && k.hi <= a->Tk,
+                "build_attn_bias: bad block %d [%d,%d)", b, k.lo, k.hi);
+    p.blk[b] = k;
+  }
+  dim3 grid((a->Tk + 255) / 256, a->Tq), block(256);
+  build_attn_bias_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return SGF_OK;

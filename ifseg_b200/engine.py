@@ -1,0 +1,419 @@
+"""Flat execution plan of the segofa forward on one B200: a sequence of C-ABI kernel launches
+(ifseg_b200.ops -> libsegofa_b200.so) over device buffers owned by PyTorch's caching allocator.
+
+Data layout in HBM
+  * activations are batch-major row matrices [B*T, D]; the residual stream is fp32, every GEMM
+    operand (LayerNorm output, attention output, FFN hidden) is bf16;
+  * q/k/v live in one [B*T, 3D] bf16 buffer written by the fused QKV GEMM (q pre-scaled by
+    (2 d_h)^-1/2 in its epilogue) and are read in place by the attention kernel through 4-D TMA
+    maps (d, head, token, batch) -- no head transposes are materialised;
+  * the stem runs NHWC bf16; FrozenBatchNorm is folded to a per-channel (scale, bias) applied in
+    the convolution epilogue together with ReLU and the residual add;
+  * the additive attention bias is batch-invariant and parameter-only: it is built once per
+    forward as fp32 [H, Tq, Tk_pad] per layer (abs-pos q_pos k_pos^T by a head-batched GEMM +
+    rel-pos table lookups), never per batch element and never through clone/cat/interpolate
+    chains (those are 55-60% of the reference's forward time).
+
+Reference semantics followed (file:line under /root/reference/models/segofa/):
+  encoder_module.py:677-851 (encode), :499-675 (encode_with_artificial_image),
+  decoder_module.py:486-677 (surrogate decoder), :290-294 (seg_projection),
+  unify_transformer_layer.py:222-292, 431-581, unify_multihead_attention.py:327-523,
+  resnet.py:215-229, frozen_bn.py:40-45.
+"""
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .config import SegOFAConfig
+
+_BF16 = torch.bfloat16
+
+
+def _pad64(n):
+    return (n + 63) // 64 * 64
+
+
+class _ConvW:
+    __slots__ = ("w", "scale", "bias", "kh", "kw", "stride", "pad", "cin", "cout", "k", "ldk")
+
+
+class SegOFAEngine:
+    def __init__(self, model):
+        self.cfg: SegOFAConfig = model.cfg
+        p = next(model.parameters())
+        if not p.is_cuda:
+            raise RuntimeError(
+                "segofa_b200: the model is on %s; the hot path is CUDA-only (sm_100a) and has no CPU fallback -- "
+                "move the model to a B200 with .cuda()" % p.device
+            )
+        from . import _lib
+
+        _lib.load()  # fail loudly if the extension is missing
+        self.device = p.device
+        self.model = model
+        self._shape_cache: Dict = {}
+        self.cache_position_bias = False
+        self._bias_cache: Dict = {}
+        with torch.no_grad():
+            self._prepare(model)
+
+    # ------------------------------------------------------------------------------------
+    # parameter preparation (derived device tensors; rebuilt whenever the model invalidates)
+    # ------------------------------------------------------------------------------------
+    def _f32(self, t):
+        return t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _b16(self, t):
+        return t.detach().to(device=self.device, dtype=_BF16).contiguous()
+
+    def _ln(self, m):
+        return (self._f32(m.weight), self._f32(m.bias))
+
+    def _conv(self, conv, bn) -> _ConvW:
+        c = _ConvW()
+        w = conv.weight.detach().float()
+        c.cout, c.cin, c.kh, c.kw = w.shape
+        c.stride, c.pad = conv.stride[0], conv.padding[0]
+        c.k = c.kh * c.kw * c.cin
+        c.ldk = (c.k + 7) // 8 * 8
+        wm = torch.zeros(c.cout, c.ldk, dtype=torch.float32, device=w.device)
+        wm[:, : c.k] = w.permute(0, 2, 3, 1).reshape(c.cout, c.k)  # [Cout, (ky,kx,cin)]
+        c.w = self._b16(wm)
+        scale = bn.weight.detach().float() * (bn.running_var.detach().float() + bn.eps).rsqrt()  # frozen_bn.py:40-41
+        c.scale = self._f32(scale)
+        c.bias = self._f32(bn.bias.detach().float() - bn.running_mean.detach().float() * scale)
+        return c
+
+    def _attn(self, m, cross=False):
+        d = {}
+        if cross:
+            d["wq"], d["bq"] = self._b16(m.q_proj.weight), self._f32(m.q_proj.bias)
+            d["wkv"] = self._b16(torch.cat([m.k_proj.weight, m.v_proj.weight], 0))
+            d["bkv"] = self._f32(torch.cat([m.k_proj.bias, m.v_proj.bias], 0))
+        else:
+            d["wqkv"] = self._b16(torch.cat([m.q_proj.weight, m.k_proj.weight, m.v_proj.weight], 0))
+            d["bqkv"] = self._f32(torch.cat([m.q_proj.bias, m.k_proj.bias, m.v_proj.bias], 0))
+        d["wo"], d["bo"] = self._b16(m.out_proj.weight), self._f32(m.out_proj.bias)
+        d["c_attn"] = self._f32(m.c_attn) if m.c_attn is not None else None
+        return d
+
+    def _prepare(self, model):
+        enc, dec, cfg = model.encoder, model.decoder, self.cfg
+        s = enc.embed_images
+        self.stem_conv1 = self._conv(s.conv1, s.bn1)
+        self.stem_blocks = []
+        for li in (1, 2, 3):
+            for blk in getattr(s, f"layer{li}"):
+                b = dict(c1=self._conv(blk.conv1, blk.bn1), c2=self._conv(blk.conv2, blk.bn2),
+                         c3=self._conv(blk.conv3, blk.bn3), down=None, stride=blk.stride)
+                if blk.downsample is not None:
+                    b["down"] = self._conv(blk.downsample[0], blk.downsample[1])
+                self.stem_blocks.append(b)
+        type_emb = self._f32(enc.type_embedding.weight)
+        self.type_txt, self.type_img = type_emb[0].contiguous(), type_emb[1].contiguous()
+        self.embed_tokens = enc.embed_tokens.weight.detach()
+        if self.embed_tokens.dtype not in (torch.float32, _BF16) or not self.embed_tokens.is_contiguous():
+            self.embed_tokens = self._f32(self.embed_tokens)
+        self.w_image_proj, self.b_image_proj = self._b16(enc.image_proj.weight), self._f32(enc.image_proj.bias)
+        self.ln_emb, self.ln_patch = self._ln(enc.layernorm_embedding), self._ln(enc.patch_layernorm_embedding)
+        self.enc_pos_table = self._f32(enc.embed_positions.weight)
+        self.enc_img_pos_table = self._f32(enc.embed_image_positions.weight)
+        self.ln_pos, self.ln_img_pos = self._ln(enc.pos_ln), self._ln(enc.image_pos_ln)
+        self.w_pos_q, self.b_pos_q = self._b16(enc.pos_q_linear.weight), self._f32(enc.pos_q_linear.bias)
+        self.w_pos_k, self.b_pos_k = self._b16(enc.pos_k_linear.weight), self._f32(enc.pos_k_linear.bias)
+        self.enc_layers = []
+        for l in enc.layers:
+            self.enc_layers.append(dict(
+                attn=self._attn(l.self_attn), ln_self=self._ln(l.self_attn_layer_norm), ln_attn=self._ln(l.attn_ln),
+                ln_final=self._ln(l.final_layer_norm), ln_ffn=self._ln(l.ffn_layernorm),
+                w1=self._b16(l.fc1.weight), b1=self._f32(l.fc1.bias), w2=self._b16(l.fc2.weight),
+                b2=self._f32(l.fc2.bias)))
+        self.ln_enc_out = self._ln(enc.layer_norm)
+        self.enc_tok_rel = [self._f32(t.weight) for t in enc.token_rel_pos_table_list]
+        self.enc_img_rel = [self._f32(t.weight) for t in enc.image_rel_pos_table_list]
+        self.token_rp_bucket = enc.token_rp_bucket.to(self.device)
+        self.image_rp_bucket = enc.image_rp_bucket.to(self.device)
+        # decoder
+        self.dec_ln_emb = self._ln(dec.layernorm_embedding)
+        self.seg_pos_table = self._f32(dec.embed_seg_positions.weight)
+        self.ln_seg_pos = self._ln(dec.seg_pos_ln)
+        self.w_self_pq, self.b_self_pq = self._b16(dec.self_pos_q_linear.weight), self._f32(dec.self_pos_q_linear.bias)
+        self.w_self_pk, self.b_self_pk = self._b16(dec.self_pos_k_linear.weight), self._f32(dec.self_pos_k_linear.bias)
+        self.w_cross_pq, self.b_cross_pq = self._b16(dec.cross_pos_q_linear.weight), self._f32(dec.cross_pos_q_linear.bias)
+        self.w_cross_pk, self.b_cross_pk = self._b16(dec.cross_pos_k_linear.weight), self._f32(dec.cross_pos_k_linear.bias)
+        self.dec_layers = []
+        for l in dec.layers:
+            self.dec_layers.append(dict(
+                attn=self._attn(l.self_attn), cross=self._attn(l.encoder_attn, cross=True),
+                ln_self=self._ln(l.self_attn_layer_norm), ln_self_attn=self._ln(l.self_attn_ln),
+                ln_enc_attn=self._ln(l.encoder_attn_layer_norm), ln_cross_attn=self._ln(l.cross_attn_ln),
+                ln_final=self._ln(l.final_layer_norm), ln_ffn=self._ln(l.ffn_layernorm),
+                w1=self._b16(l.fc1.weight), b1=self._f32(l.fc1.bias), w2=self._b16(l.fc2.weight),
+                b2=self._f32(l.fc2.bias)))
+        # all decoder layers' cross-attention K/V projections of encoder_out as ONE GEMM (N = L*2D)
+        self.w_cross_kv_all = torch.cat([d["cross"]["wkv"] for d in self.dec_layers], 0).contiguous()
+        self.b_cross_kv_all = torch.cat([d["cross"]["bkv"] for d in self.dec_layers], 0).contiguous()
+        self.ln_dec_out = self._ln(dec.layer_norm)
+        self.dec_seg_rel = [self._f32(t.weight) for t in dec.seg_rel_pos_table_list]
+        self.seg_rp_bucket = dec.seg_rp_bucket.to(self.device)
+        self.w_seg_proj = self._b16(dec.seg_projection.weight)
+        self.seg_bucket_size = dec.seg_bucket_size
+
+    # ------------------------------------------------------------------------------------
+    # stem: resnet.py:215-229
+    # ------------------------------------------------------------------------------------
+    def _conv_gemm(self, x, c: _ConvW, act, residual=None):
+        """x [N,H,W,Cin] bf16 NHWC -> [N,Ho,Wo,Cout] bf16."""
+        n, h, w, _ = x.shape
+        if c.kh == 3 and c.stride == 1 and c.cin % 64 == 0 and residual is None:
+            return ops.conv3x3_s1(x, c.w, c.scale, c.bias, act=act)
+        if c.kh == 1 and c.stride == 1:
+            a, ho, wo = x.view(n * h * w, c.cin), h, w
+        else:  # the few strided convs: explicit patch matrix (7x7/2, 3x3/2, 1x1/2)
+            a, ho, wo = ops.im2col(x, c.kh, c.kw, c.stride, c.pad, ld_out=c.ldk)
+        out = torch.empty((n, ho, wo, c.cout), dtype=_BF16, device=x.device)
+        ops.gemm(a, c.w, out.view(-1, c.cout), M=n * ho * wo, N=c.cout, K=c.k, lda=a.stride(0), ldb=c.ldk,
+                 scale=c.scale, bias=c.bias, act=act,
+                 residual=residual.view(-1, c.cout) if residual is not None else None)
+        return out
+
+    def stem(self, patch_images):
+        x = ops.nchw_to_nhwc_bf16(patch_images.float())
+        x = self._conv_gemm(x, self.stem_conv1, ops.ACT_RELU)
+        x = ops.maxpool3x3s2(x)
+        for b in self.stem_blocks:
+            idn = x if b["down"] is None else self._conv_gemm(x, b["down"], ops.ACT_NONE)
+            y = self._conv_gemm(x, b["c1"], ops.ACT_RELU)
+            y = self._conv_gemm(y, b["c2"], ops.ACT_RELU)
+            x = self._conv_gemm(y, b["c3"], ops.ACT_RELU, residual=idn)  # relu(identity + bn3(conv3)) :128-135
+        return x  # [B,h,w,1024] NHWC == [B,P,1024] token-major
+
+    # ------------------------------------------------------------------------------------
+    # position bias (batch-invariant)
+    # ------------------------------------------------------------------------------------
+    def _image_position_ids(self, h, w):
+        b = self.cfg.image_bucket_size
+        return (torch.arange(w).unsqueeze(0).expand(h, w) + torch.arange(h).unsqueeze(1) * b + 1).reshape(-1).to(self.device)
+
+    def _abs_bias(self, pos_q_in, pos_k_in, wq, bq, wk, bk):
+        """fp32 [H, Tq, pad64(Tk)] = (pos_q W_q^T + b_q) * pos_scaling  .  (pos_k W_k^T + b_k)^T per head."""
+        cfg = self.cfg
+        D, H, dh = cfg.embed_dim, cfg.heads, cfg.head_dim
+        Tq, Tk = pos_q_in.shape[0], pos_k_in.shape[0]
+        pq = ops.gemm(pos_q_in, wq, bias=bq, alpha=cfg.pos_scaling, alpha_cols=D)
+        pk = ops.gemm(pos_k_in, wk, bias=bk)
+        Tkp = _pad64(Tk)
+        out = torch.zeros((H, Tq, Tkp), dtype=torch.float32, device=self.device)
+        ops.gemm(pq, pk, out, M=Tq, N=Tk, K=dh, batch=H, lda=D, ldb=D, a_batch_stride=dh, b_batch_stride=dh,
+                 ldc=Tkp, c_batch_stride=Tq * Tkp)
+        return out
+
+    def _interp_needed(self, h, w):
+        oh = self.cfg.orig_patch_image_size // 16
+        return (h, w) != (oh, oh)
+
+    def _encoder_bias(self, h, w, T_txt, artificial):
+        """list of fp32 [H,T_e,pad64(T_e)] per layer + the post-LN position embeddings [T_e,D] bf16."""
+        key = ("enc", h, w, T_txt, artificial)
+        if self.cache_position_bias and key in self._bias_cache:
+            return self._bias_cache[key]
+        cfg = self.cfg
+        P, D = h * w, cfg.embed_dim
+        T = P + T_txt
+        oh = cfg.orig_patch_image_size // 16
+        if P > oh * oh or (not artificial and self._interp_needed(h, w)):
+            raise NotImplementedError(
+                f"segofa_b200: patch grid {h}x{w} differs from the orig_patch_image_size grid {oh}x{oh}; the "
+                "interpolated position tables (encoder_module.py:358-370, 802-808) are a 'next' row (SURVEY.md s8f-2)")
+        ids = self._image_position_ids(h, w)
+        pos = torch.empty((T, D), dtype=_BF16, device=self.device)
+        ops.row_layernorm(self.enc_img_pos_table, rows=P, gather_idx=ids, ln2=self.ln_img_pos, out2=pos)
+        ops.row_layernorm(self.enc_pos_table, rows=T_txt, ln2=self.ln_pos, out2=pos[P:])
+        absb = self._abs_bias(pos, pos, self.w_pos_q, self.b_pos_q, self.w_pos_k, self.b_pos_k)
+        tok_ids = torch.arange(T_txt, device=self.device)
+        biases = []
+        for l in range(cfg.enc_layers):
+            blocks = [(self.image_rp_bucket, ids, self.enc_img_rel[l], 0, P),
+                      (self.token_rp_bucket, tok_ids, self.enc_tok_rel[l], P, T)]
+            biases.append(ops.build_attn_bias(absb, T, blocks))
+        res = (biases, pos)
+        if self.cache_position_bias:
+            self._bias_cache[key] = res
+        return res
+
+    def _decoder_bias(self, h, w, enc_pos):
+        key = ("dec", h, w, enc_pos.shape[0])
+        if self.cache_position_bias and key in self._bias_cache:
+            return self._bias_cache[key]
+        cfg = self.cfg
+        sb = self.seg_bucket_size
+        if (h, w) != (sb, sb):
+            raise NotImplementedError(
+                f"segofa_b200: patch grid {h}x{w} differs from the seg_bucket grid {sb}x{sb}; interpolated seg "
+                "position tables (decoder_module.py:541-548, 603-625) are a 'next' row (SURVEY.md s8f-2)")
+        Td, D = h * w + 1, cfg.embed_dim
+        tgt_pos = torch.empty((Td, D), dtype=_BF16, device=self.device)
+        ops.row_layernorm(self.seg_pos_table, rows=Td, ln2=self.ln_seg_pos, out2=tgt_pos)  # ids 0..n == table rows
+        self_abs = self._abs_bias(tgt_pos, tgt_pos, self.w_self_pq, self.b_self_pq, self.w_self_pk, self.b_self_pk)
+        cross_abs = self._abs_bias(tgt_pos, enc_pos, self.w_cross_pq, self.b_cross_pq, self.w_cross_pk, self.b_cross_pk)
+        seg_ids = torch.arange(Td, device=self.device)
+        self_biases = [ops.build_attn_bias(self_abs, Td, [(self.seg_rp_bucket, seg_ids, self.dec_seg_rel[l], 0, Td)])
+                       for l in range(cfg.dec_layers)]
+        res = (self_biases, cross_abs)
+        if self.cache_position_bias:
+            self._bias_cache[key] = res
+        return res
+
+    # ------------------------------------------------------------------------------------
+    # transformer blocks
+    # ------------------------------------------------------------------------------------
+    def _self_attention(self, a, L, B, T, bias, causal, kpm):
+        cfg = self.cfg
+        D, H = cfg.embed_dim, cfg.heads
+        qkv = ops.gemm(a, L["wqkv"], bias=L["bqkv"], alpha=cfg.attn_scaling, alpha_cols=D)  # [B*T,3D]
+        o = torch.empty((B * T, D), dtype=_BF16, device=self.device)
+        ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], o, B=B, H=H, Tq=T, Tk=T, q_strides=(3 * D, T * 3 * D),
+                      k_strides=(3 * D, T * 3 * D), v_strides=(3 * D, T * 3 * D), o_strides=(D, T * D), bias=bias,
+                      head_scale=L["c_attn"], key_padding_mask=kpm, causal=causal)
+        return ops.gemm(o, L["wo"], bias=L["bo"], out_dtype=torch.float32)
+
+    def _ffn(self, a, x, L):
+        f = ops.gemm(a, L["w1"], bias=L["b1"], act=ops.ACT_GELU)
+        g = torch.empty_like(f)
+        ops.row_layernorm(f, ln2=L["ln_ffn"], out2=g)
+        ops.gemm(g, L["w2"], x, bias=L["b2"], residual=x)  # x <- x + fc2(...)   (fp32 stream, in place)
+
+    # ------------------------------------------------------------------------------------
+    # encoder
+    # ------------------------------------------------------------------------------------
+    def encode(self, src_tokens, patch_images=None, patch_masks=None, bag_tokens=None, bag_offsets=None,
+               has_pads: Optional[bool] = None):
+        cfg = self.cfg
+        dev = self.device
+        D = cfg.embed_dim
+        src_tokens = src_tokens.to(dev)
+        B, T_txt = src_tokens.shape
+        artificial = bag_tokens is not None
+        feat = None
+        if artificial:
+            raise NotImplementedError(
+                "segofa_b200 round 1: the image-free (EmbeddingBag grid) encoder input is not built yet")
+        if patch_images is None:
+            raise NotImplementedError("segofa_b200: text-only encoding is not on the IFSeg hot path")
+        feat = self.stem(patch_images.to(dev))
+        h, w = feat.shape[1], feat.shape[2]
+        P = h * w
+        T = P + T_txt
+        # padding: encoder_module.py:730,737-742
+        pad = torch.zeros((B, T), dtype=torch.uint8, device=dev)
+        pad[:, P:] = src_tokens.eq(cfg.padding_idx)
+        if patch_masks is not None:
+            pad[:, :P] = (~patch_masks.to(dev).bool()).unsqueeze(1)
+        if has_pads is None:
+            has_pads = bool(pad.any())  # same host sync as encoder_module.py:742
+        kpm = pad if has_pads else None
+
+        biases, pos = self._encoder_bias(h, w, T_txt, artificial)
+        L0 = self.enc_layers[0]
+        x = torch.empty((B * T, D), dtype=torch.float32, device=dev)  # fp32 residual stream
+        a = torch.empty((B * T, D), dtype=_BF16, device=dev)
+        # image rows: image_proj -> +type_embedding(1) -> patch_layernorm_embedding  (:416-423)
+        proj = ops.gemm(feat.view(B * P, 1024), self.w_image_proj, bias=self.b_image_proj, out_dtype=torch.float32)
+        ops.row_layernorm(proj, pre_add=self.type_img, ln1=self.ln_patch, out1=x, ln2=L0["ln_self"], out2=a,
+                          zero_row=pad[:, :P].contiguous().view(-1) if has_pads else None, seg=(P, T, 0))
+        # text rows: embed_tokens -> +type_embedding(0) -> layernorm_embedding  (:400-408)
+        ops.row_layernorm(self.embed_tokens, rows=B * T_txt, D=D, gather_idx=src_tokens.reshape(-1).contiguous(),
+                          pre_add=self.type_txt, ln1=self.ln_emb, out1=x, ln2=L0["ln_self"], out2=a,
+                          zero_row=pad[:, P:].contiguous().view(-1) if has_pads else None, seg=(T_txt, T, P))
+        a2 = torch.empty_like(a)
+        for li, L in enumerate(self.enc_layers):
+            y = self._self_attention(a, L["attn"], B, T, biases[li], False, kpm)
+            ops.row_layernorm(y, ln1=L["ln_attn"], residual=x, out1=x, ln2=L["ln_final"], out2=a2)
+            self._ffn(a2, x, L)
+            nxt = self.enc_layers[li + 1]["ln_self"] if li + 1 < len(self.enc_layers) else self.ln_enc_out
+            ops.row_layernorm(x, ln2=nxt, out2=a)
+        return dict(encoder_out=a, B=B, T=T, P=P, hw=(h, w), pad=pad, has_pads=has_pads, pos=pos,
+                    image_features=feat, image_proj=proj)
+
+    def encoder_out_dict(self, enc):
+        """The dict encoder_module.py:839-851 returns (T x B x C tensors are strided views)."""
+        B, T, P, D = enc["B"], enc["T"], enc["P"], self.cfg.embed_dim
+        eo = enc["encoder_out"].view(B, T, D)
+        return {
+            "encoder_out": [eo.transpose(0, 1)],
+            "encoder_padding_mask": [enc["pad"].bool()],
+            "encoder_embedding": [],
+            "encoder_states": [],
+            "src_tokens": [],
+            "src_lengths": [],
+            "position_embeddings": [enc["pos"].unsqueeze(0).expand(B, -1, -1)],
+            "patch_images": [],
+            "image_embed_before_scale": [enc["image_proj"].view(B, P, D)],
+            "image_embed_shape": [enc["hw"]],
+            "image_embed_before_proj": [enc["image_features"].view(B, P, -1)],
+        }
+
+    # ------------------------------------------------------------------------------------
+    # decoder
+    # ------------------------------------------------------------------------------------
+    def decode(self, enc, prev_output_tokens, full_context_alignment=False, features_only=False):
+        cfg = self.cfg
+        dev = self.device
+        D, H = cfg.embed_dim, cfg.heads
+        B, Te, P = enc["B"], enc["T"], enc["P"]
+        h, w = enc["hw"]
+        Td = P + 1
+        enc_out = enc["encoder_out"]  # [B*Te, D] bf16
+        kpm = enc["pad"] if enc["has_pads"] else None
+        self_biases, cross_abs = self._decoder_bias(h, w, enc["pos"])
+        L0 = self.dec_layers[0]
+
+        x = torch.empty((B * Td, D), dtype=torch.float32, device=dev)
+        a = torch.empty((B * Td, D), dtype=_BF16, device=dev)
+        bos = prev_output_tokens.to(dev)[:, 0].contiguous()
+        # x = LN_emb(cat([embed_tokens(bos), dec_in]))  (decoder_module.py:530-538, 575-576); embed_scale == 1
+        ops.row_layernorm(self.embed_tokens, rows=B, D=D, gather_idx=bos, ln1=self.dec_ln_emb, out1=x,
+                          ln2=L0["ln_self"], out2=a, seg=(1, Td, 0))
+        key = ("dec_in_idx", B, Te, P)
+        idx = self._shape_cache.get(key)
+        if idx is None:
+            idx = (torch.arange(B, device=dev).unsqueeze(1) * Te + torch.arange(P, device=dev).unsqueeze(0)).reshape(-1)
+            self._shape_cache[key] = idx
+        if cfg.decoder_input_type == "encoder_output":
+            ops.row_layernorm(enc_out, rows=B * P, gather_idx=idx, ln1=self.dec_ln_emb, out1=x, ln2=L0["ln_self"],
+                              out2=a, seg=(P, Td, 1))
+        else:  # 'encoder_input': image_embed_before_scale
+            ops.row_layernorm(enc["image_proj"], rows=B * P, ln1=self.dec_ln_emb, out1=x, ln2=L0["ln_self"], out2=a,
+                              seg=(P, Td, 1))
+        # cross-attention K/V of every layer in one GEMM: [B*Te, L*2D]
+        nL = len(self.dec_layers)
+        kv_all = ops.gemm(enc_out, self.w_cross_kv_all, bias=self.b_cross_kv_all)
+        a2 = torch.empty_like(a)
+        o = torch.empty((B * Td, D), dtype=_BF16, device=dev)
+        for li, L in enumerate(self.dec_layers):
+            y = self._self_attention(a, L["attn"], B, Td, self_biases[li], not full_context_alignment, None)
+            ops.row_layernorm(y, ln1=L["ln_self_attn"], residual=x, out1=x, ln2=L["ln_enc_attn"], out2=a2)
+            C = L["cross"]
+            q = ops.gemm(a2, C["wq"], bias=C["bq"], alpha=cfg.attn_scaling, alpha_cols=D)
+            kbase = kv_all[:, li * 2 * D:]
+            ops.attention(q, kbase, kbase[:, D:], o, B=B, H=H, Tq=Td, Tk=Te, q_strides=(D, Td * D),
+                          k_strides=(nL * 2 * D, Te * nL * 2 * D), v_strides=(nL * 2 * D, Te * nL * 2 * D),
+                          o_strides=(D, Td * D), bias=cross_abs, head_scale=C["c_attn"], key_padding_mask=kpm)
+            y = ops.gemm(o, C["wo"], bias=C["bo"], out_dtype=torch.float32)
+            ops.row_layernorm(y, ln1=L["ln_cross_attn"], residual=x, out1=x, ln2=L["ln_final"], out2=a)
+            self._ffn(a, x, L)
+            nxt = self.dec_layers[li + 1]["ln_self"] if li + 1 < nL else self.ln_dec_out
+            ops.row_layernorm(x, ln2=nxt, out2=a)
+        feats = a.view(B, Td, D)
+        extra = {"attn": [None], "inner_states": [], "penultimate": feats}
+        if features_only:
+            return feats, extra
+        logits = ops.gemm(a, self.w_seg_proj, out_dtype=torch.float32)  # seg_projection (no bias) :290-294
+        return logits.view(B, Td, cfg.num_seg), extra
+
+    # ------------------------------------------------------------------------------------
+    # mask: seg_criterion.py:237-244 + :351 (argmax of the x16 bilinear upsample, eos slot dropped)
+    # ------------------------------------------------------------------------------------
+    def predict_mask(self, logits, hw, out_hw, target=None):
+        return ops.upsample_argmax(logits.float().contiguous(), hw[0], hw[1], out_hw[0], out_hw[1], target=target)

@@ -138,17 +138,27 @@ def row_layernorm(x, *, rows=None, D=None, ldx=None, gather_idx=None, pre_add=No
     _lib.check(lib.sgf_row_layernorm(C.byref(args), _stream()), "sgf_row_layernorm")
 
 
-def add_rel_bias(bias, bucket, ids, table, lo, hi):
-    """bias [H,Tq,Tk(padded stride)] fp32 += table[bucket[ids_i, ids_j], h] on [lo,hi)^2."""
+def build_attn_bias(abs_bias, Tk, blocks=(), out=None, dense_add=None):
+    """out[h,i,j] = abs[h,i,j] (+ dense_add) + rel-pos lookups.  abs_bias fp32 [H,Tq,row_stride>=Tk];
+    blocks: iterable of (bucket int64 2-D, ids int64 [hi-lo], table fp32 [num_rel,H], lo, hi)."""
     lib = _lib.load()
-    _req(bias, torch.float32, "bias")
-    _req(bucket, torch.int64, "bucket")
-    _req(ids, torch.int64, "ids")
-    _req(table, torch.float32, "table")
-    H, Tq, _ = bias.shape
-    args = _lib.RelBiasArgs(_p(bias), bias.stride(0), bias.stride(1), H, Tq, bias.shape[2], _p(bucket),
-                            bucket.stride(0), _p(ids), _p(table), lo, hi)
-    _lib.check(lib.sgf_add_rel_bias(C.byref(args), _stream()), "sgf_add_rel_bias")
+    _req(abs_bias, torch.float32, "abs_bias")
+    out = torch.empty_like(abs_bias) if out is None else out
+    assert out.stride() == abs_bias.stride() and abs_bias.stride(2) == 1
+    H, Tq, _ = abs_bias.shape
+    args = _lib.BiasArgs()
+    args.out, args.abs = out.data_ptr(), abs_bias.data_ptr()
+    args.head_stride, args.row_stride = abs_bias.stride(0), abs_bias.stride(1)
+    args.dense_add = dense_add.data_ptr() if dense_add is not None else None
+    args.H, args.Tq, args.Tk, args.num_blocks = H, Tq, Tk, len(blocks)
+    for i, (bucket, ids, table, lo, hi) in enumerate(blocks):
+        _req(bucket, torch.int64, "bucket")
+        _req(ids, torch.int64, "ids")
+        _req(table, torch.float32, "table")
+        assert table.is_contiguous() and table.shape[1] == H and ids.numel() == hi - lo
+        args.blocks[i] = _lib.RelBlock(bucket.data_ptr(), bucket.stride(0), ids.data_ptr(), table.data_ptr(), lo, hi)
+    _lib.check(lib.sgf_build_attn_bias(C.byref(args), _stream()), "sgf_build_attn_bias")
+    return out
 
 
 def attention(q, k, v, out, *, B, H, Tq, Tk, q_strides, k_strides, v_strides, o_strides, bias=None,

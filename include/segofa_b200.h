@@ -97,7 +97,8 @@ int sgf_maxpool3x3s2_nhwc(const void* x, void* y, int32_t n, int32_t h, int32_t 
  * Output row map: r' = (r / seg_len) * seg_stride + seg_off + r % seg_len  (seg_len==0: r'=r),
  * which writes straight into a concatenated [B, T, D] buffer (no torch.cat copy).
  * If `gather_idx` is given, input row r is x[gather_idx[r]] (token embedding lookup).
- * If `zero_row` is given and zero_row[r] != 0 the outputs are zero (padding rows).
+ * If `zero_row` is given and zero_row[r] != 0, v is forced to zero (padding rows, encoder_module.py:751-752);
+ * out2 is then LN(0) = beta, exactly what the reference's next LayerNorm sees.
  * LayerNorm eps 1e-5, fp32 statistics (custom_fairseq/fairseq/modules/layer_norm.py:30-35).
  * Replaces LayerNorm/residual/dropout(p=0)/cat at unify_transformer_layer.py:256-291,463-568;
  * encoder_module.py:400-428,751-752,757-760,829-830; decoder_module.py:537,575-576,668-669.
@@ -118,23 +119,30 @@ typedef struct {
 int sgf_row_layernorm(const sgf_rowln_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * Attention bias assembly (batch-invariant, parameter-only):
- *   bias[h,i,j] = abs[h,i,j] + rel(h,i,j),  fp32, with the rel-pos term a table lookup
- *   rel = table[bucket[ids_q[i], ids_k[j]], h] inside the square block [blk_lo, blk_hi) of both
- *   axes and 0 elsewhere; called once for the image block and once for the text block.
- * Replaces encoder_module.py:313-331,790-809 and decoder_module.py:327-333,601-627 for the
- * identity-interpolation case (actual grid == orig/seg grid; the general interpolated table is
- * assembled host-side and added through `dense_add`).
+ * Attention bias assembly (batch-invariant, parameter-only), one launch per layer:
+ *   out[h,i,j] = abs[h,i,j] + sum_{blocks b with lo_b <= i,j < hi_b}
+ *                               table_b[ bucket_b[ ids_b[i-lo_b], ids_b[j-lo_b] ], h ]      (fp32)
+ * `abs` is the layer-independent q_pos k_pos^T term (a batched sgf_gemm_bf16 over heads); the
+ * blocks are the image-image and text-text squares of the encoder, or the whole seg grid of
+ * the decoder.  out may alias abs.  Columns j >= Tk of the padded row stride are not touched.
+ * Replaces the per-layer clone + F.embedding + slice-add at encoder_module.py:313-331,790-809
+ * and decoder_module.py:327-333,601-627 for the identity-interpolation case (actual grid ==
+ * orig/seg grid, true for every BASELINE config); for other grids the host precomputes the
+ * interpolated table once and passes it as `dense_add` ([H,Tq,Tk] fp32, same strides as abs).
  * ------------------------------------------------------------------------------------- */
 typedef struct {
-  float* bias; int64_t head_stride; int64_t row_stride; /* in/out: [H,Tq,Tk] fp32 (holds abs on entry) */
-  int32_t H, Tq, Tk;
   const int64_t* bucket; int64_t bucket_ld; /* int64 [*, bucket_ld] */
-  const int64_t* ids;                       /* [blk_hi-blk_lo] position ids into bucket rows/cols */
+  const int64_t* ids;                       /* [hi-lo] position ids into bucket rows/cols */
   const float* table;                       /* fp32 [num_rel, H] */
-  int32_t blk_lo, blk_hi;
-} sgf_relbias_args;
-int sgf_add_rel_bias(const sgf_relbias_args* args, void* stream);
+  int32_t lo, hi;
+} sgf_relblock;
+typedef struct {
+  float* out; const float* abs; int64_t head_stride; int64_t row_stride; /* [H,Tq,row_stride] fp32 */
+  const float* dense_add;                                                /* optional */
+  int32_t H, Tq, Tk;
+  int32_t num_blocks; sgf_relblock blocks[2];
+} sgf_bias_args;
+int sgf_build_attn_bias(const sgf_bias_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused multi-head attention, head_dim 64:  O = softmax(Q K^T + bias + mask) V * head_scale

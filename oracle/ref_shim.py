@@ -264,7 +264,11 @@ _SHIPPED_FLAGS = dict(  # run_scripts/IFSeg/coco_unseen.sh:76-136
 
 def shipped_args(arch, num_seg, image_size, parser_cls_add_args):
     """argparse namespace as train.py would hand it to build_model."""
-    parser = argparse.ArgumentParser()
+    # fairseq adds the model flags to a group created with argument_default=SUPPRESS
+    # (custom_fairseq/fairseq/options.py:142-149): flags that are not passed and carry no explicit
+    # default are ABSENT from the namespace, so the arch preset's getattr defaults apply
+    # (e.g. no_scale_embedding=True -> embed_scale == 1).
+    parser = argparse.ArgumentParser(argument_default=argparse.SUPPRESS)
     parser_cls_add_args(parser)
     args = parser.parse_args([])
     for k in [k for k, v in vars(args).items() if v is None]:

@@ -252,15 +252,18 @@ def test_upsample_argmax_bit_exact(ops, B, C, hp, wp, h, w):
     assert torch.equal(areas[0], ai) and torch.equal(areas[1], ap) and torch.equal(areas[2], al)
 
 
-def test_add_rel_bias(ops):
+def test_build_attn_bias(ops):
     g = torch.Generator(device="cuda").manual_seed(21)
-    H, T, lo, hi = 4, 100, 10, 74
-    bias = torch.randn(H, T, 128, device="cuda", generator=g)
-    before = bias.clone()
+    H, T, Tp = 4, 100, 128
+    absb = torch.randn(H, T, Tp, device="cuda", generator=g)
     bucket = torch.randint(0, 50, (90, 90), device="cuda", generator=g)
-    ids = torch.randint(0, 90, (hi - lo,), device="cuda", generator=g)
-    table = torch.randn(50, H, device="cuda", generator=g)
-    ops.add_rel_bias(bias, bucket, ids, table, lo, hi)
-    ref = before.clone()
-    ref[:, lo:hi, lo:hi] += table[bucket[ids][:, ids]].permute(2, 0, 1)
-    assert torch.allclose(bias, ref, atol=1e-6)
+    ids_a = torch.randint(0, 90, (64,), device="cuda", generator=g)
+    ids_b = torch.randint(0, 90, (26,), device="cuda", generator=g)
+    tab_a = torch.randn(50, H, device="cuda", generator=g)
+    tab_b = torch.randn(50, H, device="cuda", generator=g)
+    dense = torch.randn(H, T, Tp, device="cuda", generator=g)
+    out = ops.build_attn_bias(absb, T, [(bucket, ids_a, tab_a, 0, 64), (bucket, ids_b, tab_b, 74, 100)], dense_add=dense)
+    ref = (absb + dense)[:, :, :T].clone()
+    ref[:, 0:64, 0:64] += tab_a[bucket[ids_a][:, ids_a]].permute(2, 0, 1)
+    ref[:, 74:100, 74:100] += tab_b[bucket[ids_b][:, ids_b]].permute(2, 0, 1)
+    assert torch.allclose(out[:, :, :T], ref, atol=1e-6)
