@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of the segofa forward->mask hot path (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2]
+
+A "step" is one pass of the hot path over one batch of synthetic images:
+  ResNet-101 stem -> OFA encoder -> surrogate decoder -> seg_projection -> x16 bilinear upsample
+  -> argmax mask   (SegOFAModel.forward + seg_criterion.upsample_logits/argmax; label-propagation
+  and CRF post-processing excluded).
+Workload at N=1: BASELINE.json configs[1] = OFA-Base, 480x480, 15 COCO-unseen classes, batch 8,
+bf16 tensor-core operands / fp32 accumulate, random-init weights of that architecture from the
+seeded generator (no checkpoint exists offline), synthetic randn images, the real 36-token prompt.
+N>1: one process per GPU (torchrun), independent replicas on per-rank seeded batches (weak
+scaling; inference has no data-path collective), barrier + device sync on both
+sides, max over ranks.
+
+value   : whole-job images/s with the inputs already resident in HBM (CUDA events on the
+          launching stream; the 22 MB input batch + ~1 GB of per-step workspace exceed nothing
+          special, so L2 is flushed between timed steps by a 256 MB memset, excluded from timing).
+e2e     : the same metric through the public serving API (ifseg_b200.serving.SegmentationSession):
+          pinned host images -> H2D -> forward -> mask -> D2H inside the timed region.
+roofline: dominant kernel family (tcgen05 GEMM incl. implicit-GEMM conv) -- algorithmic FLOPs of
+          its launches / their CUDA-event durations vs MEASURED_PEAKS.json bf16 sustained peak;
+          `step` gives the same for the whole forward (286.8 GFLOP/img).
+cpu_baseline / --impl reference: the reference algorithm on the host cores.  The reference's own
+          model cannot be imported on the GPU box (/root/reference is absent, fairseq not
+          installable: DESIGN.md), so this is the pinned oracle port (oracle/restated.py, fp32,
+          torch CPU, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_IMG = {2: 286.8e9, 4: 364.6e9}  # SURVEY.md s8d (forward, algorithmic)
+CONFIGS = {
+    # id: (arch, image, classes, batch, description)
+    1: ("segofa_base", 128, 15, 1, "OFA-Base segofa 128x128, 15 COCO-unseen classes, batch 1"),
+    2: ("segofa_base", 480, 15, 8, "OFA-Base segofa 480x480 inference, 15 COCO-unseen classes, batch 8"),
+    4: ("segofa_base", 512, 171, 8, "OFA-Base segofa 512x512 inference, 171 COCO-Stuff classes, batch 8"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"], source="measured")
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+def prompt_tokens(num_seg):
+    import torch
+
+    p = os.path.join(ROOT, "tests", "golden", "prompts.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if str(num_seg) in d:
+            return torch.tensor(d[str(num_seg)], dtype=torch.long)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(cfg_id, steps, warmup, sample_batch=None):
+    """Times the oracle port (reference algorithm, fp32 torch CPU) on all host threads."""
+    import torch
+
+    from ifseg_b200.config import preset
+    from ifseg_b200.synthetic import generate_state_dict, synthetic_inputs
+    from oracle import restated as R
+
+    arch, size, nseg, batch, _ = CONFIGS[cfg_id]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b = sample_batch or min(batch, 2)
+    cfg = preset(arch, num_seg=nseg, patch_image_size=size, orig_patch_image_size=size)
+    sd = generate_state_dict(cfg, 0)
+    ocfg = R.SegOFAConfig(**{k: getattr(cfg, k) for k in R.SegOFAConfig.__dataclass_fields__ if hasattr(cfg, k)})
+    inp = synthetic_inputs(cfg, b, size, seed=1, src_tokens=prompt_tokens(nseg))
+    hp = size // 16
+
+    def step():
+        with torch.no_grad():
+            lg, _ = R.segofa_forward(sd, ocfg, inp["src_tokens"], inp["patch_images"], inp["patch_masks"])
+            return R.predict_mask(lg, hp, hp, size, size)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=b / dt, unit="images/s", cores=cores, kind="port",
+                sample=f"{steps} timed + {warmup} warm-up forward->mask passes of batch {b} (of {batch}) at {size}x{size}, "
+                       f"fp32 torch CPU, {cores} threads; oracle/restated.py pinned on the reference"), dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-breakdown", action="store_true", help="print the per-kernel-family table to stderr")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    arch, size, nseg, batch, desc = CONFIGS[args.config]
+    config = {"workload": desc, "arch": arch, "image_size": size, "num_classes": nseg, "per_gpu_batch": batch,
+              "global_batch": batch * max(world, 1), "parallelism": f"dp{max(world, 1)} (independent replicas)",
+              "l2_policy": "256 MB memset between timed steps (not timed)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        cb, dt = cpu_reference_run(args.config, steps, min(args.warmup, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": "images/sec", "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0,
+                                        "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the segofa_b200 hot path has no CPU fallback "
+                         "(use --impl reference for the host baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl")
+    from ifseg_b200 import ops
+    from ifseg_b200.segofa import SegOFAModel
+    from ifseg_b200.serving import SegmentationSession
+    from ifseg_b200.synthetic import generate_state_dict, synthetic_inputs
+
+    peaks = load_peaks()
+    model = SegOFAModel.from_config(arch, nseg, size)
+    model.load_state_dict(generate_state_dict(model.cfg, 0), strict=True)
+    model = model.cuda().eval()
+    tokens = prompt_tokens(nseg)
+    inp = synthetic_inputs(model.cfg, batch, size, seed=1 + rank, src_tokens=tokens)
+    sess = SegmentationSession(model, batch, size, inp["src_tokens"][0], use_cuda_graph=not args.no_graph)
+    sess.images.copy_(inp["patch_images"].cuda())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(max(args.warmup, 3)):
+        sess.step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    ops.reset_launch_count()
+    with torch.cuda.stream(sess.compute):
+        for _ in range(args.steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(sess.compute)
+            sess.step_device()
+            e.record(sess.compute)
+            evs.append((s, e))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs) / args.steps
+    launches = sess.launches_per_step * args.steps + args.steps  # + the flush memset is torch's, not counted: ours only
+    launches = sess.launches_per_step * args.steps
+
+    # ---------------- end-to-end (host buffers) ----------------
+    pinned = [inp["patch_images"].clone().pin_memory() for _ in range(2)]
+    for _ in sess.infer_stream((pinned[i & 1] for i in range(max(args.warmup, 3))), pinned_inputs=True):
+        pass
+    barrier()
+    t0 = time.perf_counter()
+    n_out = 0
+    for out in sess.infer_stream((pinned[i & 1] for i in range(args.steps)), pinned_inputs=True):
+        n_out += 1
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    assert n_out == args.steps
+
+    # ---------------- per-kernel attribution (eager, CUDA events per launch) ----------------
+    timer = ops.KernelTimer()
+    ops.set_timer(timer)
+    with torch.no_grad(), torch.cuda.stream(sess.compute):
+        sess._forward()
+    fam = timer.summary()
+    ops.set_timer(None)
+    total_k_ms = sum(v["ms"] for v in fam.values())
+    dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    if args.kernel_breakdown and rank == 0:
+        for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+            sys.stderr.write(f"{k:20s} launches {v['launches']:4d}  {v['ms']:8.3f} ms  {100 * v['ms'] / total_k_ms:5.1f}%  "
+                             f"{v['flops'] / max(v['ms'], 1e-9) / 1e9:8.1f} TFLOP/s  {v['bytes'] / max(v['ms'], 1e-9) / 1e6:8.1f} GB/s\n")
+
+    # ---------------- reduce over ranks ----------------
+    t = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = t[0].item(), t[1].item()
+    n = max(world, 1)
+    value = n * batch / (dev_ms / 1e3)
+    e2e_value = n * batch * args.steps / e2e_s
+
+    if rank == 0:
+        gemm = fam.get("gemm_tcgen05", dom[1])
+        dom_name = "gemm_tcgen05" if "gemm_tcgen05" in fam and fam["gemm_tcgen05"]["ms"] >= 0.3 * dom[1]["ms"] else dom[0]
+        d = fam[dom_name]
+        achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
+        step_tflops = FLOPS_PER_IMG.get(args.config, 0.0) * batch / (dev_ms / 1e3) / 1e12
+        out = {
+            "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": n, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": sess.h2d_bytes_per_step,
+                    "d2h_bytes_per_step": sess.d2h_bytes_per_step},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peaks["bf16_sustained"],
+                         "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                         "peak_source": peaks["source"] + " (bf16 sustained: kernel timed inside a long step)",
+                         "launches_per_step": d["launches"], "share_of_step_kernel_time": d["ms"] / total_k_ms,
+                         "step": {"achieved": step_tflops, "frac": step_tflops / peaks["bf16_sustained"],
+                                  "flops_per_image": FLOPS_PER_IMG.get(args.config)}},
+            "kernel_families": {k: {"launches": v["launches"], "ms": round(v["ms"], 4)} for k, v in fam.items()},
+            "cuda_graph": not args.no_graph,
+        }
+        if not args.no_cpu_baseline:
+            cb, _ = cpu_reference_run(args.config, 1, 1, sample_batch=1 if size >= 256 else None)
+            out["cpu_baseline"] = cb
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

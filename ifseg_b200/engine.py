@@ -192,9 +192,18 @@ class SegOFAEngine:
     # ------------------------------------------------------------------------------------
     # position bias (batch-invariant)
     # ------------------------------------------------------------------------------------
+    def _cached(self, key, make):
+        """Shape-dependent index tensors are built once (outside any CUDA-graph capture)."""
+        t = self._shape_cache.get(key)
+        if t is None:
+            t = make().to(self.device)
+            self._shape_cache[key] = t
+        return t
+
     def _image_position_ids(self, h, w):
         b = self.cfg.image_bucket_size
-        return (torch.arange(w).unsqueeze(0).expand(h, w) + torch.arange(h).unsqueeze(1) * b + 1).reshape(-1).to(self.device)
+        return self._cached(("img_ids", h, w), lambda: (
+            torch.arange(w).unsqueeze(0).expand(h, w) + torch.arange(h).unsqueeze(1) * b + 1).reshape(-1))
 
     def _abs_bias(self, pos_q_in, pos_k_in, wq, bq, wk, bk):
         """fp32 [H, Tq, pad64(Tk)] = (pos_q W_q^T + b_q) * pos_scaling  .  (pos_k W_k^T + b_k)^T per head."""
@@ -231,7 +240,7 @@ class SegOFAEngine:
         ops.row_layernorm(self.enc_img_pos_table, rows=P, gather_idx=ids, ln2=self.ln_img_pos, out2=pos)
         ops.row_layernorm(self.enc_pos_table, rows=T_txt, ln2=self.ln_pos, out2=pos[P:])
         absb = self._abs_bias(pos, pos, self.w_pos_q, self.b_pos_q, self.w_pos_k, self.b_pos_k)
-        tok_ids = torch.arange(T_txt, device=self.device)
+        tok_ids = self._cached(("arange", T_txt), lambda: torch.arange(T_txt))
         biases = []
         for l in range(cfg.enc_layers):
             blocks = [(self.image_rp_bucket, ids, self.enc_img_rel[l], 0, P),
@@ -257,7 +266,7 @@ class SegOFAEngine:
         ops.row_layernorm(self.seg_pos_table, rows=Td, ln2=self.ln_seg_pos, out2=tgt_pos)  # ids 0..n == table rows
         self_abs = self._abs_bias(tgt_pos, tgt_pos, self.w_self_pq, self.b_self_pq, self.w_self_pk, self.b_self_pk)
         cross_abs = self._abs_bias(tgt_pos, enc_pos, self.w_cross_pq, self.b_cross_pq, self.w_cross_pk, self.b_cross_pk)
-        seg_ids = torch.arange(Td, device=self.device)
+        seg_ids = self._cached(("arange", Td), lambda: torch.arange(Td))
         self_biases = [ops.build_attn_bias(self_abs, Td, [(self.seg_rp_bucket, seg_ids, self.dec_seg_rel[l], 0, Td)])
                        for l in range(cfg.dec_layers)]
         res = (self_biases, cross_abs)
@@ -375,11 +384,8 @@ class SegOFAEngine:
         # x = LN_emb(cat([embed_tokens(bos), dec_in]))  (decoder_module.py:530-538, 575-576); embed_scale == 1
         ops.row_layernorm(self.embed_tokens, rows=B, D=D, gather_idx=bos, ln1=self.dec_ln_emb, out1=x,
                           ln2=L0["ln_self"], out2=a, seg=(1, Td, 0))
-        key = ("dec_in_idx", B, Te, P)
-        idx = self._shape_cache.get(key)
-        if idx is None:
-            idx = (torch.arange(B, device=dev).unsqueeze(1) * Te + torch.arange(P, device=dev).unsqueeze(0)).reshape(-1)
-            self._shape_cache[key] = idx
+        idx = self._cached(("dec_in_idx", B, Te, P), lambda: (
+            torch.arange(B).unsqueeze(1) * Te + torch.arange(P).unsqueeze(0)).reshape(-1))
         if cfg.decoder_input_type == "encoder_output":
             ops.row_layernorm(enc_out, rows=B * P, gather_idx=idx, ln1=self.dec_ln_emb, out1=x, ln2=L0["ln_self"],
                               out2=a, seg=(P, Td, 1))

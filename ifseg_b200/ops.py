@@ -31,6 +31,51 @@ def _req(t, dtype=None, name="tensor"):
     return t
 
 
+class KernelTimer:
+    """Optional per-launch CUDA-event timing (used by bench.py to attribute the step to kernel
+    families and to compute the roofline of the dominant one).  Off by default: zero overhead."""
+
+    def __init__(self):
+        self.records = []  # (family, start_event, end_event, flops, bytes)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, s, e, fl, by in self.records:
+            d = out.setdefault(fam, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += fl
+            d["bytes"] += by
+        return out
+
+
+_TIMER = None
+
+
+def set_timer(timer):
+    global _TIMER
+    _TIMER = timer
+
+
+class _timed:
+    def __init__(self, family, flops=0.0, nbytes=0.0):
+        self.family, self.flops, self.nbytes = family, flops, nbytes
+
+    def __enter__(self):
+        if _TIMER is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if _TIMER is not None:
+            self.e.record()
+            _TIMER.records.append((self.family, self.s, self.e, self.flops, self.nbytes))
+        return False
+
+
 def launch_count():
     return int(_lib.load().sgf_launch_count())
 
@@ -63,7 +108,8 @@ def gemm(a, b, out=None, *, bias=None, scale=None, residual=None, act=ACT_NONE, 
         M, N, K, batch, _p(scale), _p(bias), _p(residual),
         (residual.stride(-2) if ldr is None else ldr) if residual is not None else 0, r_batch_stride,
         _DT[residual.dtype] if residual is not None else SGF_BF16, act, float(alpha), int(alpha_cols))
-    _lib.check(lib.sgf_gemm_bf16(C.byref(args), _stream()), "sgf_gemm_bf16")
+    with _timed("gemm_tcgen05", 2.0 * M * N * K * batch):
+        _lib.check(lib.sgf_gemm_bf16(C.byref(args), _stream()), "sgf_gemm_bf16")
     return out
 
 
@@ -78,7 +124,8 @@ def conv3x3_s1(x, w, scale, bias, act=ACT_RELU, out=None):
     if out is None:
         out = torch.empty((n, h, wd, cout), dtype=torch.bfloat16, device=x.device)
     args = _lib.Conv3x3Args(_p(x), _p(w), _p(out), n, h, wd, cin, cout, _p(scale), _p(bias), act)
-    _lib.check(lib.sgf_conv3x3_s1_nhwc(C.byref(args), _stream()), "sgf_conv3x3_s1_nhwc")
+    with _timed("gemm_tcgen05", 2.0 * n * h * wd * cout * 9 * cin):
+        _lib.check(lib.sgf_conv3x3_s1_nhwc(C.byref(args), _stream()), "sgf_conv3x3_s1_nhwc")
     return out
 
 
@@ -88,7 +135,8 @@ def nchw_to_nhwc_bf16(x):
     n, c, h, w = x.shape
     x = x.contiguous()
     y = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.sgf_nchw_f32_to_nhwc_bf16(_p(x), _p(y), n, c, h, w, _stream()), "sgf_nchw_f32_to_nhwc_bf16")
+    with _timed("layout", nbytes=x.numel() * 6.0):
+        _lib.check(lib.sgf_nchw_f32_to_nhwc_bf16(_p(x), _p(y), n, c, h, w, _stream()), "sgf_nchw_f32_to_nhwc_bf16")
     return y
 
 
@@ -102,8 +150,9 @@ def im2col(x, kh, kw, stride, pad, ld_out=None):
     k = kh * kw * c
     ld_out = (k + 7) // 8 * 8 if ld_out is None else ld_out
     out = torch.empty((n * ho * wo, ld_out), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.sgf_im2col_nhwc(_p(x), _p(out), n, h, w, c, kh, kw, stride, pad, ho, wo, ld_out, _stream()),
-               "sgf_im2col_nhwc")
+    with _timed("im2col", nbytes=out.numel() * 2.0 + x.numel() * 2.0):
+        _lib.check(lib.sgf_im2col_nhwc(_p(x), _p(out), n, h, w, c, kh, kw, stride, pad, ho, wo, ld_out, _stream()),
+                   "sgf_im2col_nhwc")
     return out, ho, wo
 
 
@@ -113,7 +162,8 @@ def maxpool3x3s2(x):
     n, h, w, c = x.shape
     ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
     y = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.sgf_maxpool3x3s2_nhwc(_p(x), _p(y), n, h, w, c, ho, wo, _stream()), "sgf_maxpool3x3s2_nhwc")
+    with _timed("maxpool", nbytes=(x.numel() + y.numel()) * 2.0):
+        _lib.check(lib.sgf_maxpool3x3s2_nhwc(_p(x), _p(y), n, h, w, c, ho, wo, _stream()), "sgf_maxpool3x3s2_nhwc")
     return y
 
 
@@ -135,7 +185,10 @@ def row_layernorm(x, *, rows=None, D=None, ldx=None, gather_idx=None, pre_add=No
         _p(ln2[0]) if ln2 else None, _p(ln2[1]) if ln2 else None,
         _p(out2), (out2.stride(-2) if ld2 is None else ld2) if out2 is not None else 0,
         _p(zero_row), rows, D, seg_len, seg_stride, seg_off)
-    _lib.check(lib.sgf_row_layernorm(C.byref(args), _stream()), "sgf_row_layernorm")
+    nb = rows * D * (x.element_size() + (residual.element_size() if residual is not None else 0)
+                     + (out1.element_size() if out1 is not None else 0) + (2 if out2 is not None else 0))
+    with _timed("row_layernorm", nbytes=float(nb)):
+        _lib.check(lib.sgf_row_layernorm(C.byref(args), _stream()), "sgf_row_layernorm")
 
 
 def build_attn_bias(abs_bias, Tk, blocks=(), out=None, dense_add=None):
@@ -157,7 +210,8 @@ def build_attn_bias(abs_bias, Tk, blocks=(), out=None, dense_add=None):
         _req(table, torch.float32, "table")
         assert table.is_contiguous() and table.shape[1] == H and ids.numel() == hi - lo
         args.blocks[i] = _lib.RelBlock(bucket.data_ptr(), bucket.stride(0), ids.data_ptr(), table.data_ptr(), lo, hi)
-    _lib.check(lib.sgf_build_attn_bias(C.byref(args), _stream()), "sgf_build_attn_bias")
+    with _timed("attn_bias", nbytes=8.0 * H * Tq * Tk):
+        _lib.check(lib.sgf_build_attn_bias(C.byref(args), _stream()), "sgf_build_attn_bias")
     return out
 
 
@@ -174,7 +228,9 @@ def attention(q, k, v, out, *, B, H, Tq, Tk, q_strides, k_strides, v_strides, o_
         _p(out), o_strides[0], o_strides[1],
         _p(bias), bias.stride(0) if bias is not None else 0, bias.stride(1) if bias is not None else 0,
         _p(head_scale), _p(key_padding_mask), B, H, Tq, Tk, 1 if causal else 0)
-    _lib.check(lib.sgf_attention_bf16(C.byref(args), _stream()), "sgf_attention_bf16")
+    pairs = Tq * Tk if not causal else Tq * (Tq + 1) / 2.0
+    with _timed("attention_tcgen05", 4.0 * B * H * pairs * 64):
+        _lib.check(lib.sgf_attention_bf16(C.byref(args), _stream()), "sgf_attention_bf16")
     return out
 
 
@@ -193,5 +249,6 @@ def upsample_argmax(logits, hp, wp, h, w, target=None, num_tokens=None):
                             _p(target), _p(areas[0]) if areas is not None else None,
                             _p(areas[1]) if areas is not None else None,
                             _p(areas[2]) if areas is not None else None)
-    _lib.check(lib.sgf_upsample_argmax(C.byref(args), _stream()), "sgf_upsample_argmax")
+    with _timed("upsample_argmax", nbytes=float(mask.numel() * 8 + B * hp * wp * Cn * 4)):
+        _lib.check(lib.sgf_upsample_argmax(C.byref(args), _stream()), "sgf_upsample_argmax")
     return (mask, areas) if target is not None else mask
