@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-breakdown", action="store_true", help="print the per-kernel-family table to stderr")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="wrap ONE eager forward->mask step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,6 +239,14 @@ def main():
     e2e_s = time.perf_counter() - t0
     barrier()
     assert n_out == args.steps
+
+    if args.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        with torch.no_grad(), torch.cuda.stream(sess.compute):
+            sess._forward()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 
     # ---------------- per-kernel attribution (eager, CUDA events per launch) ----------------
     timer = ops.KernelTimer()

@@ -11,6 +11,8 @@
 //   O = O*alpha + T thread r: tcgen05.ld its row of T, rescale-accumulate in registers
 // K/V tiles are double-buffered by TMA; 64 KB of shared memory and 128 TMEM columns per CTA let
 // three CTAs share an SM so one CTA's MMAs overlap another's softmax.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace sgf {
@@ -39,21 +41,25 @@ struct AttnSmem {
   static constexpr int offK = offQ + kQ;       // 2 stages
   static constexpr int offV = offK + 2 * kKV;  // 2 stages
   static constexpr int offP = offV + 2 * kKV;
-  static constexpr int offBar = offP + kP;
+  static constexpr int kBias = kQTile * kKTile * 4;  // 32 KB fp32 bias tile: two 128B-swizzled [128 x 32] boxes
+  static constexpr int offBias = offP + kP;
+  static constexpr int offBar = offBias + kBias;
   static constexpr int kTotal = offBar + 64;
 };
 
 __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                          const __grid_constant__ CUtensorMap tmK,
                                                                          const __grid_constant__ CUtensorMap tmV,
+                                                                         const __grid_constant__ CUtensorMap tmB,
                                                                          const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + AttnSmem::offBar);
   uint64_t* bar_kv = bar_q + 1;  // [2]
-  uint64_t* bar_s = bar_q + 3;
-  uint64_t* bar_o = bar_q + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 5);
+  uint64_t* bar_s = bar_q + 3;  // [2]  S ping-pong
+  uint64_t* bar_o = bar_q + 5;
+  uint64_t* bar_b = bar_q + 6;  // bias tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 7);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -75,17 +81,20 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05_kernel(const _
     mbar_init(bar_q, 1);
     mbar_init(&bar_kv[0], 1);
     mbar_init(&bar_kv[1], 1);
-    mbar_init(bar_s, 1);
+    mbar_init(&bar_s[0], 1);
+    mbar_init(&bar_s[1], 1);
     mbar_init(bar_o, 1);
+    mbar_init(bar_b, 1);
     fence_mbar_init();
+    if (p.bias) tma_prefetch_desc(&tmB);
   }
-  if (warp == 0) tmem_alloc<128>(tmem_slot);
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;       // columns [0,64)
-  const uint32_t tmem_t = tmem_base + 64;  // columns [64,128)
+  const uint32_t tmem_s = tmem_base;        // S ping-pong: columns [0,64) and [64,128)
+  const uint32_t tmem_t = tmem_base + 128;  // T = P V: columns [128,192)
 
   if (tid == 0) {
     mbar_expect_tx(bar_q, AttnSmem::kQ);
@@ -94,6 +103,11 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05_kernel(const _
       mbar_expect_tx(&bar_kv[st], 2 * AttnSmem::kKV);
       tma_load_4d(smem + AttnSmem::offK + st * AttnSmem::kKV, &tmK, &bar_kv[st], 0, h, st * kKTile, b);
       tma_load_4d(smem + AttnSmem::offV + st * AttnSmem::kKV, &tmV, &bar_kv[st], 0, h, st * kKTile, b);
+    }
+    if (p.bias && n_kt > 0) {
+      mbar_expect_tx(bar_b, AttnSmem::kBias);
+      tma_load_3d(smem + AttnSmem::offBias, &tmB, bar_b, 0, q0, h);
+      tma_load_3d(smem + AttnSmem::offBias + AttnSmem::kBias / 2, &tmB, bar_b, 32, q0, h);
     }
   }
 
@@ -107,10 +121,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05_kernel(const _
   float m_run = -INFINITY;  // running max (log2 domain)
   float l_run = 0.f;
 
-  const int brow = min(row, p.Tq - 1);
-  const float* bias_row =
-      p.bias ? p.bias + static_cast<int64_t>(h) * p.bias_head_stride + static_cast<int64_t>(brow) * p.bias_row_stride
-             : nullptr;
+  const uint8_t* bias_row = smem + AttnSmem::offBias + tid * 128;  // this thread's row inside each bias box
   const uint8_t* kpm_row = p.kpm ? p.kpm + static_cast<int64_t>(b) * p.Tk : nullptr;
   uint8_t* p_row = smem + AttnSmem::offP + tid * 128;
 
@@ -119,25 +130,39 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05_kernel(const _
     const uint32_t kv_phase = (kt >> 1) & 1;
     const int k0 = kt * kKTile;
 
+    // S(kt) was issued one iteration ahead (S(0) below); issue S(kt+1) now so that the tensor core
+    // works on the next score tile while this tile's softmax runs on the CUDA cores.
     if (tid == 0) {
-      if (kt == 0) mbar_wait(bar_q, 0);
-      mbar_wait(&bar_kv[st], kv_phase);
-      tc_fence_after();
       const uint64_t dq = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offQ));
-      const uint64_t dk = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offK + st * AttnSmem::kKV));
+      if (kt == 0) {
+        mbar_wait(bar_q, 0);
+        mbar_wait(&bar_kv[0], 0);
+        tc_fence_after();
+        const uint64_t dk = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offK));
 #pragma unroll
-      for (int k = 0; k < kHeadDim / 16; ++k) umma_f16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-      umma_commit(bar_s);
+        for (int k = 0; k < kHeadDim / 16; ++k) umma_f16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&bar_s[0]);
+      }
+      if (kt + 1 < n_kt) {
+        const int sn = (kt + 1) & 1;
+        mbar_wait(&bar_kv[sn], ((kt + 1) >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dk = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offK + sn * AttnSmem::kKV));
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k)
+          umma_f16(tmem_s + sn * 64, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&bar_s[sn]);
+      }
     }
 
     // ---- softmax on this thread's row ----
-    mbar_wait(bar_s, kt & 1);
+    mbar_wait(&bar_s[st], kv_phase);
     tc_fence_after();
     float s[kKTile];
     {
       uint32_t r0[32], r1[32];
-      tmem_ld_32x32(tmem_s + lane_addr, r0);
-      tmem_ld_32x32(tmem_s + lane_addr + 32, r1);
+      tmem_ld_32x32(tmem_s + st * 64 + lane_addr, r0);
+      tmem_ld_32x32(tmem_s + st * 64 + lane_addr + 32, r1);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -145,11 +170,14 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05_kernel(const _
         s[32 + j] = __uint_as_float(r1[j]);
       }
     }
-    if (bias_row) {
+    if (p.bias) {  // bias tile staged by TMA (128B swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7))
+      mbar_wait(bar_b, kt & 1);
 #pragma unroll
-      for (int j = 0; j < kKTile; j += 4) {
-        if (k0 + j + 4 <= p.bias_row_stride) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_row + k0 + j));
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_row + half * (AttnSmem::kBias / 2) + ((c ^ (tid & 7)) << 4));
+          const int j = half * 32 + c * 4;
           s[j] += b4.x; s[j + 1] += b4.y; s[j + 2] += b4.z; s[j + 3] += b4.w;
         }
       }
@@ -193,6 +221,11 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05_kernel(const _
     __syncthreads();
 
     if (tid == 0) {
+      if (p.bias && kt + 1 < n_kt) {  // every thread has consumed this tile's bias (barrier above)
+        mbar_expect_tx(bar_b, AttnSmem::kBias);
+        tma_load_3d(smem + AttnSmem::offBias, &tmB, bar_b, (kt + 1) * kKTile, q0, h);
+        tma_load_3d(smem + AttnSmem::offBias + AttnSmem::kBias / 2, &tmB, bar_b, (kt + 1) * kKTile + 32, q0, h);
+      }
       tc_fence_after();
       const uint64_t dp = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offP));
       const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offV + st * AttnSmem::kKV));
@@ -242,7 +275,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05_kernel(const _
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<256>(tmem_base);
   }
 }
 
@@ -276,6 +309,15 @@ extern "C" int sgf_attention_bf16(const sgf_attention_args* a, void* stream) {
   if (int rc = make_qkv_map(&tmQ, a->q, a->q_row_stride, a->q_batch_stride, a->H, a->Tq, a->B, kQTile)) return rc;
   if (int rc = make_qkv_map(&tmK, a->k, a->k_row_stride, a->k_batch_stride, a->H, a->Tk, a->B, kKTile)) return rc;
   if (int rc = make_qkv_map(&tmV, a->v, a->v_row_stride, a->v_batch_stride, a->H, a->Tk, a->B, kKTile)) return rc;
+  CUtensorMap tmB;
+  memset(&tmB, 0, sizeof(tmB));
+  if (a->bias) {
+    uint64_t dims[3] = {static_cast<uint64_t>(a->bias_row_stride), static_cast<uint64_t>(a->Tq), static_cast<uint64_t>(a->H)};
+    uint64_t strides[2] = {static_cast<uint64_t>(a->bias_row_stride) * 4, static_cast<uint64_t>(a->bias_head_stride) * 4};
+    uint32_t box[3] = {32, kQTile, 1};
+    if (int rc = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a->bias, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
   AttnParams p{a->out, a->o_row_stride, a->o_batch_stride, a->bias, a->bias_head_stride, a->bias_row_stride,
                a->head_scale, a->key_padding_mask, a->B, a->H, a->Tq, a->Tk, a->causal};
   constexpr int smem = AttnSmem::kTotal + 1024;
@@ -286,7 +328,7 @@ extern "C" int sgf_attention_bf16(const sgf_attention_args* a, void* stream) {
     configured = true;
   }
   dim3 grid((a->Tq + kQTile - 1) / kQTile, a->H, a->B);
-  attention_tcgen05_kernel<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  attention_tcgen05_kernel<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmB, p);
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return SGF_OK;

@@ -98,6 +98,13 @@ SGF_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
 SGF_DEVICE void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// 1-D bulk copy global -> shared (no tensor map): size and both addresses multiples of 16 bytes
+SGF_DEVICE void bulk_load_1d(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem)),
+               "l"(reinterpret_cast<uint64_t>(gmem)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 SGF_DEVICE void tma_load_2d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

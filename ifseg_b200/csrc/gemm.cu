@@ -138,28 +138,16 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
     }
   } else {
     // ------------------------------ epilogue warps ------------------------------
+    // Phase 1: TMEM -> registers (thread = row), column-wise ops (scale, bias, q-scale, GELU), then
+    //          the row is parked in a per-warp smem staging tile (the pipeline stages are dead by now).
+    // Phase 2: the warp re-reads the tile with lanes along the columns, so the residual loads and
+    //          the output stores are fully coalesced 16/32-byte-per-lane row segments.
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int r = quarter * 32 + lane;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-
-    int64_t out_row;
-    bool row_ok;
-    if constexpr (kConv) {
-      const int hh = h0 + r / shp.bw, ww = w0 + r % shp.bw;
-      row_ok = (hh < shp.H) && (ww < shp.W);
-      out_row = (static_cast<int64_t>(img) * shp.H + hh) * shp.W + ww;
-    } else {
-      row_ok = (m0 + r) < shp.M;
-      out_row = m0 + r;
-    }
-    const bool vec_ok = (shp.N % 8) == 0;
-    uint8_t* cptr = reinterpret_cast<uint8_t*>(ep.c) +
-                    (static_cast<int64_t>(z) * ep.c_batch_stride + out_row * ep.ldc) * (ep.c_dtype == SGF_F32 ? 4 : 2);
-    const uint8_t* rptr = nullptr;
-    if (ep.residual)
-      rptr = reinterpret_cast<const uint8_t*>(ep.residual) +
-             (static_cast<int64_t>(z) * ep.r_batch_stride + out_row * ep.ldr) * (ep.r_dtype == SGF_F32 ? 4 : 2);
+    constexpr int kRowPitch = BN * 4 + 16;  // bytes; +16 keeps the thread-per-row float4 writes conflict-free
+    uint8_t* stage = smem + quarter * (32 * kRowPitch);
+    static_assert(4 * 32 * kRowPitch <= kStages * S::kStageBytes, "epilogue staging must fit in the pipeline smem");
 
 #pragma unroll 1
     for (int ch = 0; ch < BN / 32; ++ch) {
@@ -171,21 +159,14 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-      const bool full = vec_ok && (c0 + 32 <= shp.N);
-      if (full) {
+      if (c0 + 32 <= shp.N) {
         if (ep.col_scale) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 s4 = *reinterpret_cast<const float4*>(ep.col_scale + c0 + j);
-            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-          }
+          for (int j = 0; j < 32; ++j) v[j] *= __ldg(ep.col_scale + c0 + j);
         }
         if (ep.col_bias) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(ep.col_bias + c0 + j);
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.col_bias + c0 + j);
         }
       } else {
 #pragma unroll
@@ -205,65 +186,81 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
       }
-      if (row_ok) {
+      float4* dst = reinterpret_cast<float4*>(stage + lane * kRowPitch + ch * 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    __syncwarp();
+
+    constexpr int kLanesPerRow = BN / 8;
+    constexpr int kRowsPerIter = 32 / kLanesPerRow;
+    const int col = (lane % kLanesPerRow) * 8;
+    const int c = n0 + col;
+    const bool vec_ok = (shp.N % 8) == 0 && (c + 8 <= shp.N);
+    const int csz = ep.c_dtype == SGF_F32 ? 4 : 2;
+    const int rsz = ep.r_dtype == SGF_F32 ? 4 : 2;
+#pragma unroll 1
+    for (int it = 0; it < 32 / kRowsPerIter; ++it) {
+      const int rl = it * kRowsPerIter + lane / kLanesPerRow;
+      const int r = quarter * 32 + rl;
+      int64_t out_row;
+      bool row_ok;
+      if constexpr (kConv) {
+        const int hh = h0 + r / shp.bw, ww = w0 + r % shp.bw;
+        row_ok = (hh < shp.H) && (ww < shp.W);
+        out_row = (static_cast<int64_t>(img) * shp.H + hh) * shp.W + ww;
+      } else {
+        row_ok = (m0 + r) < shp.M;
+        out_row = m0 + r;
+      }
+      if (!row_ok || c >= shp.N) continue;
+      float v[8];
+      {
+        const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + col * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + col * 4 + 16);
+        v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+      }
+      uint8_t* cptr = reinterpret_cast<uint8_t*>(ep.c) + (static_cast<int64_t>(z) * ep.c_batch_stride + out_row * ep.ldc + c) * csz;
+      const uint8_t* rptr = ep.residual ? reinterpret_cast<const uint8_t*>(ep.residual) +
+                                              (static_cast<int64_t>(z) * ep.r_batch_stride + out_row * ep.ldr + c) * rsz
+                                        : nullptr;
+      if (vec_ok) {
         if (rptr) {
-          if (full) {
-            if (ep.r_dtype == SGF_F32) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r4 = *reinterpret_cast<const float4*>(rptr + (c0 + j) * 4);
-                v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 r4 = *reinterpret_cast<const uint4*>(rptr + (c0 + j) * 2);
-                const float2 a = unpack_bf16x2(r4.x), b = unpack_bf16x2(r4.y), c = unpack_bf16x2(r4.z),
-                             d = unpack_bf16x2(r4.w);
-                v[j] += a.x; v[j + 1] += a.y; v[j + 2] += b.x; v[j + 3] += b.y;
-                v[j + 4] += c.x; v[j + 5] += c.y; v[j + 6] += d.x; v[j + 7] += d.y;
-              }
-            }
+          if (ep.r_dtype == SGF_F32) {
+            const float4 r0 = *reinterpret_cast<const float4*>(rptr), r1 = *reinterpret_cast<const float4*>(rptr + 16);
+            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (c0 + j < shp.N) {
-                v[j] += (ep.r_dtype == SGF_F32)
-                            ? reinterpret_cast<const float*>(rptr)[c0 + j]
-                            : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rptr)[c0 + j]);
-              }
-            }
+            const uint4 r4 = *reinterpret_cast<const uint4*>(rptr);
+            const float2 a = unpack_bf16x2(r4.x), b2 = unpack_bf16x2(r4.y), c2 = unpack_bf16x2(r4.z), d = unpack_bf16x2(r4.w);
+            v[0] += a.x; v[1] += a.y; v[2] += b2.x; v[3] += b2.y; v[4] += c2.x; v[5] += c2.y; v[6] += d.x; v[7] += d.y;
           }
         }
         if (ep.act == SGF_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
         }
-        if (full) {
-          if (ep.c_dtype == SGF_F32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(cptr + (c0 + j) * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 o;
-              o.x = pack_bf16x2(v[j], v[j + 1]);
-              o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-              o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(cptr + (c0 + j) * 2) = o;
-            }
-          }
+        if (ep.c_dtype == SGF_F32) {
+          *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(cptr + 16) = make_float4(v[4], v[5], v[6], v[7]);
         } else {
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(cptr) = o;
+        }
+      } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (c0 + j < shp.N) {
-              if (ep.c_dtype == SGF_F32)
-                reinterpret_cast<float*>(cptr)[c0 + j] = v[j];
-              else
-                reinterpret_cast<__nv_bfloat16*>(cptr)[c0 + j] = __float2bfloat16_rn(v[j]);
-            }
+        for (int j = 0; j < 8; ++j) {
+          if (c + j < shp.N) {
+            float t = v[j];
+            if (rptr)
+              t += (ep.r_dtype == SGF_F32) ? reinterpret_cast<const float*>(rptr)[j]
+                                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rptr)[j]);
+            if (ep.act == SGF_ACT_RELU) t = fmaxf(t, 0.0f);
+            if (ep.c_dtype == SGF_F32)
+              reinterpret_cast<float*>(cptr)[j] = t;
+            else
+              reinterpret_cast<__nv_bfloat16*>(cptr)[j] = __float2bfloat16_rn(t);
           }
         }
       }

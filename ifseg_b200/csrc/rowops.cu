@@ -46,97 +46,178 @@ SGF_DEVICE void store8(void* base, int dtype, int64_t elem_off, const float (&v)
   }
 }
 
-template <int CH>
-SGF_DEVICE void warp_layernorm(float (&v)[CH][8], int D, int lane, const float* g, const float* b) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    if ((lane + 32 * i) * 8 < D) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
-    }
-  }
-  const float mean = warp_sum(s) / static_cast<float>(D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    if ((lane + 32 * i) * 8 < D) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mean;
-        q += d * d;
-      }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    const int e = (lane + 32 * i) * 8;
-    if (e < D) {
-      float gg[8], bb[8];
-      load8(g, SGF_F32, e, gg);
-      load8(b, SGF_F32, e, bb);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
-    }
+// Rows are staged through shared memory with 1-D bulk async copies (cp.async.bulk + mbarrier):
+// the bytes in flight per SM are bounded by shared memory (4 CTAs x 48 KB), not by registers, which
+// is what an HBM-latency-bound row kernel needs.  One warp then owns one row and makes a few
+// conflict-free 128-bit passes over it; the only cross-lane traffic is 2 shuffle reductions per LN.
+static constexpr int kLnMaxRows = 8;  // rows (= warps) per CTA (fewer when a row needs > 25 KB of staging)
+
+SGF_DEVICE void smem_load8(const uint8_t* row, int dtype, int e, float (&v)[8]) {
+  if (dtype == SGF_F32) {
+    const float4 a = *reinterpret_cast<const float4*>(row + e * 4);
+    const float4 b = *reinterpret_cast<const float4*>(row + e * 4 + 16);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + e * 2);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
   }
 }
 
-template <int CH>
-__global__ void __launch_bounds__(256) row_layernorm_kernel(const RowLnParams p) {
+__global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const RowLnParams p, const int x_row_bytes,
+                                                                        const int r_row_bytes, const int s_row_bytes) {
+  const int kLnRows = blockDim.x >> 5;
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  uint8_t* xbuf = ln_smem;                                   // [kLnRows][x_row_bytes]
+  uint8_t* rbuf = xbuf + kLnRows * x_row_bytes;              // [kLnRows][r_row_bytes]   (residual)
+  uint8_t* sbuf = rbuf + kLnRows * r_row_bytes;              // [kLnRows][s_row_bytes]   (fp32 stash for LN2)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sbuf + kLnRows * s_row_bytes);
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= p.rows) return;
-  const int64_t src_row = p.gather_idx ? p.gather_idx[row] : row;
+  const int warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * kLnRows;
+  const int nrows = min(kLnRows, p.rows - row0);
+  const int xs = p.x_dtype == SGF_F32 ? 4 : 2, rs = p.r_dtype == SGF_F32 ? 4 : 2;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int row = row0 + warp;
+  const bool live = warp < nrows;
   int64_t dst_row = row;
   if (p.seg_len > 0) dst_row = static_cast<int64_t>(row / p.seg_len) * p.seg_stride + p.seg_off + row % p.seg_len;
-  const bool zero = p.zero_row && p.zero_row[row];
+  if (threadIdx.x == 0) mbar_expect_tx(bar, nrows * (x_row_bytes + r_row_bytes));
+  __syncthreads();  // expect_tx is posted before any complete_tx can arrive
+  if (live && lane == 0) {
+    const int64_t src_row = p.gather_idx ? p.gather_idx[row] : row;
+    bulk_load_1d(xbuf + warp * x_row_bytes, reinterpret_cast<const uint8_t*>(p.x) + src_row * p.ldx * xs, x_row_bytes, bar);
+    if (p.residual)
+      bulk_load_1d(rbuf + warp * r_row_bytes, reinterpret_cast<const uint8_t*>(p.residual) + dst_row * p.ldr * rs,
+                   r_row_bytes, bar);
+  }
+  mbar_wait(bar, 0);
+  if (!live) return;
 
-  float v[CH][8];
-#pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    const int e = (lane + 32 * i) * 8;
-    if (e < p.D) {
-      load8(p.x, p.x_dtype, src_row * p.ldx + e, v[i]);
+  const uint8_t* xr = xbuf + warp * x_row_bytes;
+  const uint8_t* rr = rbuf + warp * r_row_bytes;
+  float* sr = reinterpret_cast<float*>(sbuf + warp * s_row_bytes);
+  const bool zero = p.zero_row && p.zero_row[row];
+  const float invD = 1.0f / static_cast<float>(p.D);
+  const int nchunk = p.D >> 3;
+
+  // ---- first LayerNorm statistics (over t = x + pre_add) ----
+  float mean1 = 0.f, rstd1 = 1.f;
+  if (p.g1) {
+    float s = 0.f;
+    for (int c = lane; c < nchunk; c += 32) {
+      float v[8];
+      smem_load8(xr, p.x_dtype, c * 8, v);
       if (p.pre_add) {
         float a[8];
-        load8(p.pre_add, SGF_F32, e, a);
+        load8(p.pre_add, SGF_F32, c * 8, a);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] += a[j];
+        for (int j = 0; j < 8; ++j) v[j] += a[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[j];
+    }
+    mean1 = warp_sum(s) * invD;
+    float q = 0.f;
+    for (int c = lane; c < nchunk; c += 32) {
+      float v[8];
+      smem_load8(xr, p.x_dtype, c * 8, v);
+      if (p.pre_add) {
+        float a[8];
+        load8(p.pre_add, SGF_F32, c * 8, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += a[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[j] - mean1;
+        q += d * d;
       }
     }
+    rstd1 = rsqrtf(warp_sum(q) * invD + 1e-5f);
   }
-  if (p.g1) warp_layernorm<CH>(v, p.D, lane, p.g1, p.b1);
+  // ---- v = LN1(t) + residual ; out1 ; stash for LN2 ----
+  const bool two_stage = p.out2 && (p.g1 || p.residual || p.pre_add || p.out1);
+  float s2 = 0.f;
+  if (two_stage || p.out1) {
+    for (int c = lane; c < nchunk; c += 32) {
+      float v[8];
+      smem_load8(xr, p.x_dtype, c * 8, v);
+      if (p.pre_add) {
+        float a[8];
+        load8(p.pre_add, SGF_F32, c * 8, a);
 #pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    const int e = (lane + 32 * i) * 8;
-    if (e < p.D) {
+        for (int j = 0; j < 8; ++j) v[j] += a[j];
+      }
+      if (p.g1) {
+        float g[8], b[8];
+        load8(p.g1, SGF_F32, c * 8, g);
+        load8(p.b1, SGF_F32, c * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean1) * rstd1 * g[j] + b[j];
+      }
       if (p.residual) {
         float r[8];
-        load8(p.residual, p.r_dtype, dst_row * p.ldr + e, r);
+        smem_load8(rr, p.r_dtype, c * 8, r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] += r[j];
+        for (int j = 0; j < 8; ++j) v[j] += r[j];
       }
       if (zero) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
       }
       if (p.out1) {
-        store8(p.out1, p.out1_dtype, dst_row * p.ld1 + e, v[i]);
-        if (p.out1_dtype == SGF_BF16 && p.out2) {  // second LN sees exactly what was stored
+        store8(p.out1, p.out1_dtype, dst_row * p.ld1 + c * 8, v);
+        if (p.out1_dtype == SGF_BF16) {  // second LN sees exactly what was stored
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[i][j] = __bfloat162float(__float2bfloat16_rn(v[i][j]));
+          for (int j = 0; j < 8; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
         }
+      }
+      if (p.out2) {
+        *reinterpret_cast<float4*>(sr + c * 8) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(sr + c * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s2 += v[j];
       }
     }
   }
-  if (p.out2) {
-    warp_layernorm<CH>(v, p.D, lane, p.g2, p.b2);
+  if (!p.out2) return;
+  // ---- second LayerNorm (over the stash, or directly over x for the plain x -> LN -> out2 form) ----
+  const uint8_t* vrow = two_stage ? reinterpret_cast<const uint8_t*>(sr) : xr;
+  const int vdt = two_stage ? SGF_F32 : p.x_dtype;
+  if (!two_stage) {
+    for (int c = lane; c < nchunk; c += 32) {
+      float v[8];
+      smem_load8(vrow, vdt, c * 8, v);
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-      const int e = (lane + 32 * i) * 8;
-      if (e < p.D) store8(p.out2, SGF_BF16, dst_row * p.ld2 + e, v[i]);
+      for (int j = 0; j < 8; ++j) s2 += v[j];
     }
+  }
+  const float mean2 = warp_sum(s2) * invD;
+  float q2 = 0.f;
+  for (int c = lane; c < nchunk; c += 32) {
+    float v[8];
+    smem_load8(vrow, vdt, c * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[j] - mean2;
+      q2 += d * d;
+    }
+  }
+  const float rstd2 = rsqrtf(warp_sum(q2) * invD + 1e-5f);
+  for (int c = lane; c < nchunk; c += 32) {
+    float v[8], g[8], b[8];
+    smem_load8(vrow, vdt, c * 8, v);
+    load8(p.g2, SGF_F32, c * 8, g);
+    load8(p.b2, SGF_F32, c * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean2) * rstd2 * g[j] + b[j];
+    store8(p.out2, SGF_BF16, dst_row * p.ld2 + c * 8, v);
   }
 }
 
@@ -267,17 +348,25 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
                 a->out1, a->ld1, a->out1_dtype, a->g2, a->b2, a->out2, a->ld2, a->zero_row, a->rows, a->D,
                 a->seg_len, a->seg_stride, a->seg_off};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int warps = 8;
-  dim3 grid((a->rows + warps - 1) / warps), block(warps * 32);
-  const int ch = (a->D + 255) / 256;
-  if (ch <= 1) row_layernorm_kernel<1><<<grid, block, 0, st>>>(p);
-  else if (ch <= 2) row_layernorm_kernel<2><<<grid, block, 0, st>>>(p);
-  else if (ch <= 3) row_layernorm_kernel<3><<<grid, block, 0, st>>>(p);
-  else if (ch <= 4) row_layernorm_kernel<4><<<grid, block, 0, st>>>(p);
-  else if (ch <= 8) row_layernorm_kernel<8><<<grid, block, 0, st>>>(p);
-  else if (ch <= 12) row_layernorm_kernel<12><<<grid, block, 0, st>>>(p);
-  else if (ch <= 16) row_layernorm_kernel<16><<<grid, block, 0, st>>>(p);
-  else row_layernorm_kernel<20><<<grid, block, 0, st>>>(p);
+  const int xs = a->x_dtype == SGF_F32 ? 4 : 2, rs = a->r_dtype == SGF_F32 ? 4 : 2;
+  const int x_row_bytes = a->D * xs;
+  const int r_row_bytes = a->residual ? a->D * rs : 0;
+  const bool two_stage = a->out2 && (a->g1 || a->residual || a->pre_add || a->out1);
+  const int s_row_bytes = two_stage ? a->D * 4 : 0;
+  int kLnRows = kLnMaxRows;
+  while (kLnRows > 1 && kLnRows * (x_row_bytes + r_row_bytes + s_row_bytes) > 96 * 1024) kLnRows >>= 1;
+  const int smem = kLnRows * (x_row_bytes + r_row_bytes + s_row_bytes) + 16;
+  SGF_REQUIRE(smem <= 200 * 1024, "row_layernorm: D=%d too wide for this operand combination (%d B smem)", a->D, smem);
+  SGF_REQUIRE(reinterpret_cast<uintptr_t>(a->x) % 16 == 0 && (a->ldx * xs) % 16 == 0 &&
+                  (!a->residual || (reinterpret_cast<uintptr_t>(a->residual) % 16 == 0 && (a->ldr * rs) % 16 == 0)),
+              "row_layernorm: x/residual rows must be 16-byte aligned");
+  static int configured_smem = 0;
+  if (smem > configured_smem) {
+    SGF_CHECK_CUDA(cudaFuncSetAttribute(row_layernorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured_smem = 200 * 1024;
+  }
+  dim3 block(kLnRows * 32), grid((a->rows + kLnRows - 1) / kLnRows);
+  row_layernorm_kernel<<<grid, block, smem, st>>>(p, x_row_bytes, r_row_bytes, s_row_bytes);
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return SGF_OK;
