@@ -317,7 +317,10 @@ static int check_epilogue_alignment(const GemmEpilogue& ep, int N) {
   return SGF_OK;
 }
 
+static int g_force_bn = 0, g_force_stages = 0;  // tuning hook (sgf_gemm_force_variant)
+
 static int pick_bn(int M_tiles, int N, int batch) {
+  if (g_force_bn) return g_force_bn;
   // prefer the widest tile that still gives >= 1 wave of CTAs on 148 SMs
   if (N <= 32) return 32;
   if (N <= 64) return 64;
@@ -373,9 +376,19 @@ extern "C" int sgf_gemm_bf16(const sgf_gemm_args* a, void* stream) {
   dim3 grid((a->N + bn - 1) / bn, m_tiles, a->batch);
   switch (bn) {
     case 32: return launch_gemm<32, 4, false>(tmA, tmB, shp, ep, grid, st);
-    case 64: return launch_gemm<64, 4, false>(tmA, tmB, shp, ep, grid, st);
-    default: return launch_gemm<128, 3, false>(tmA, tmB, shp, ep, grid, st);
+    case 64: return g_force_stages == 8 ? launch_gemm<64, 8, false>(tmA, tmB, shp, ep, grid, st)
+                                        : launch_gemm<64, 4, false>(tmA, tmB, shp, ep, grid, st);
+    case 256: return launch_gemm<256, 4, false>(tmA, tmB, shp, ep, grid, st);
+    default:
+      if (g_force_stages == 6) return launch_gemm<128, 6, false>(tmA, tmB, shp, ep, grid, st);
+      if (g_force_stages == 4) return launch_gemm<128, 4, false>(tmA, tmB, shp, ep, grid, st);
+      return launch_gemm<128, 3, false>(tmA, tmB, shp, ep, grid, st);
   }
+}
+
+extern "C" void sgf_gemm_force_variant(int bn, int stages) {
+  g_force_bn = bn;
+  g_force_stages = stages;
 }
 
 extern "C" int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* a, void* stream) {

@@ -293,6 +293,48 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
   }
 }
 
+// im2col for narrow channel counts (conv1: C = 3): one thread per (output pixel, ky) copies the
+// kw*C contiguous input elements of that filter row and pads the row to `pitch` (multiple of 8)
+// elements, so that every store is a 16-byte vector.  K index = ky*pitch + kx*C + c.
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          __nv_bfloat16* __restrict__ out, int n, int h, int w, int c,
+                                                          int kh, int kw, int stride, int pad, int ho, int wo,
+                                                          int pitch, int64_t ld_out) {
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * kh;
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int ky = idx % kh;
+  int64_t t = idx / kh;
+  const int ox = t % wo;
+  t /= wo;
+  const int oy = t % ho;
+  const int img = t / ho;
+  const int iy = oy * stride - pad + ky;
+  const int ix0 = ox * stride - pad;
+  const bool row_ok = iy >= 0 && iy < h;
+  const __nv_bfloat16* src = x + (static_cast<int64_t>(img) * h + (row_ok ? iy : 0)) * w * c;
+  __nv_bfloat16* dst = out + ((static_cast<int64_t>(img) * ho + oy) * wo + ox) * ld_out + ky * pitch;
+  const int run = kw * c;
+  for (int e0 = 0; e0 < pitch; e0 += 8) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo = 0.f, hi = 0.f;
+      const int e = e0 + 2 * j;
+      if (row_ok && e < run) {
+        const int ix = ix0 + e / c;
+        if (ix >= 0 && ix < w) lo = __bfloat162float(src[ix * c + e % c]);
+      }
+      if (row_ok && e + 1 < run) {
+        const int ix = ix0 + (e + 1) / c;
+        if (ix >= 0 && ix < w) hi = __bfloat162float(src[ix * c + (e + 1) % c]);
+      }
+      pk[j] = pack_bf16x2(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(dst + e0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
 __global__ void zero_pad_cols_kernel(__nv_bfloat16* out, int64_t rows, int k_valid, int64_t ld_out) {
   const int padw = static_cast<int>(ld_out) - k_valid;
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -405,22 +447,24 @@ extern "C" int sgf_im2col_nhwc(const void* x, void* out, int32_t n, int32_t h, i
                                int32_t kw, int32_t stride, int32_t pad, int32_t ho, int32_t wo, int64_t ld_out,
                                void* stream) {
   SGF_REQUIRE(x && out, "im2col: null pointer");
-  const int k_valid = kh * kw * c;
-  SGF_REQUIRE(ld_out >= k_valid && ld_out % 8 == 0, "im2col: ld_out=%lld must be >= %d and a multiple of 8",
-              (long long)ld_out, k_valid);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool vec = (c % 8) == 0;
+  const int pitch = vec ? kw * c : (kw * c + 7) / 8 * 8;  // elements per filter row in the patch matrix
+  const int k_valid = kh * pitch;
+  SGF_REQUIRE(ld_out >= k_valid && ld_out % 8 == 0, "im2col: ld_out=%lld must be >= %d and a multiple of 8",
+              (long long)ld_out, k_valid);
   const int64_t rows = static_cast<int64_t>(n) * ho * wo;
-  const int64_t total = rows * kh * kw * (vec ? c / 8 : c);
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  if (vec)
-    im2col_kernel<true><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c, kh, kw, stride,
-                                                pad, ho, wo, ld_out);
-  else
-    im2col_kernel<false><<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-                                                 reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c, kh, kw, stride,
-                                                 pad, ho, wo, ld_out);
+  if (vec) {
+    const int64_t total = rows * kh * kw * (c / 8);
+    im2col_kernel<true><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c, kh, kw, stride,
+        pad, ho, wo, ld_out);
+  } else {
+    const int64_t total = rows * kh;
+    im2col_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c, kh, kw, stride,
+        pad, ho, wo, pitch, ld_out);
+  }
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   if (ld_out > k_valid) {

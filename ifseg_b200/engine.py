@@ -53,7 +53,10 @@ class SegOFAEngine:
         self.device = p.device
         self.model = model
         self._shape_cache: Dict = {}
-        self.cache_position_bias = False
+        # The additive position bias is a pure function of the (frozen) parameters and the token grid,
+        # exactly like the folded BN / fused QKV weights prepared below: it is derived once per shape and
+        # dropped with the engine whenever the model's parameters may change (SegOFAModel.invalidate_engine).
+        self.cache_position_bias = True
         self._bias_cache: Dict = {}
         with torch.no_grad():
             self._prepare(model)
@@ -75,10 +78,12 @@ class SegOFAEngine:
         w = conv.weight.detach().float()
         c.cout, c.cin, c.kh, c.kw = w.shape
         c.stride, c.pad = conv.stride[0], conv.padding[0]
-        c.k = c.kh * c.kw * c.cin
-        c.ldk = (c.k + 7) // 8 * 8
-        wm = torch.zeros(c.cout, c.ldk, dtype=torch.float32, device=w.device)
-        wm[:, : c.k] = w.permute(0, 2, 3, 1).reshape(c.cout, c.k)  # [Cout, (ky,kx,cin)]
+        pitch = ops.im2col_pitch(c.kw, c.cin)  # filter-row pitch of the patch matrix (conv1: 21 -> 24)
+        c.k = c.kh * pitch
+        c.ldk = c.k
+        wm = torch.zeros(c.cout, c.kh, pitch, dtype=torch.float32, device=w.device)
+        wm[:, :, : c.kw * c.cin] = w.permute(0, 2, 3, 1).reshape(c.cout, c.kh, c.kw * c.cin)  # [Cout, ky, (kx,cin)]
+        wm = wm.reshape(c.cout, c.k)
         c.w = self._b16(wm)
         scale = bn.weight.detach().float() * (bn.running_var.detach().float() + bn.eps).rsqrt()  # frozen_bn.py:40-41
         c.scale = self._f32(scale)

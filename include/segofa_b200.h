@@ -57,6 +57,8 @@ typedef struct {
   float alpha; int32_t alpha_cols;
 } sgf_gemm_args;
 int sgf_gemm_bf16(const sgf_gemm_args* args, void* stream);
+/* tuning hook: force the N-tile (32/64/128/256, 0 = heuristic) and pipeline depth of sgf_gemm_bf16 */
+void sgf_gemm_force_variant(int bn, int stages);
 
 /* ---------------------------------------------------------------------------------------
  * 3x3 / stride 1 / pad 1 convolution as an im2col-free implicit GEMM over NHWC bf16:
@@ -78,7 +80,8 @@ int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* args, void* stream);
  *  - sgf_nchw_f32_to_nhwc_bf16: patch_images [N,3,H,W] fp32 -> [N,H,W,C] bf16
  *  - sgf_im2col_nhwc: explicit patch matrix for the few strided convs (7x7/2 conv1, the two
  *    3x3/2 convs, the 1x1/2 downsample convs): out [N*Ho*Wo, ld_out] with K index
- *    (ky*kw+kx)*C+c, zero padded up to ld_out
+ *    ky*pitch + kx*C + c where pitch = kw*C rounded up to a multiple of 8 (C % 8 == 0: no
+ *    padding; conv1, C = 3: pitch 24), zero padded inside each filter row and up to ld_out
  *  - sgf_maxpool3x3s2_nhwc: nn.MaxPool2d(3,2,1)
  * ------------------------------------------------------------------------------------- */
 int sgf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);

@@ -95,13 +95,13 @@ def test_stem_helpers(ops):
     x = torch.randn(2, 3, 64, 48, device="cuda", generator=g)
     y = ops.nchw_to_nhwc_bf16(x)
     assert torch.equal(y, x.permute(0, 2, 3, 1).bfloat16())
-    # 7x7/2 im2col + GEMM == conv1
+    # 7x7/2 im2col + GEMM == conv1 (filter rows padded 21 -> 24 elements)
     wt = (torch.randn(64, 3, 7, 7, device="cuda", generator=g) / 12).bfloat16()
     cols, ho, wo = ops.im2col(y, 7, 7, 2, 3)
-    assert (ho, wo) == (32, 24) and cols.shape[1] == 152
-    wmat = torch.zeros(64, 152, device="cuda", dtype=torch.bfloat16)
-    wmat[:, :147] = wt.permute(0, 2, 3, 1).reshape(64, 147)
-    out = ops.gemm(cols, wmat, K=147, out_dtype=torch.float32).view(2, ho, wo, 64)
+    assert (ho, wo) == (32, 24) and cols.shape[1] == 168
+    wmat = torch.zeros(64, 7, 24, device="cuda", dtype=torch.bfloat16)
+    wmat[:, :, :21] = wt.permute(0, 2, 3, 1).reshape(64, 7, 21)
+    out = ops.gemm(cols, wmat.view(64, 168), out_dtype=torch.float32).view(2, ho, wo, 64)
     ref = F.conv2d(y.float().permute(0, 3, 1, 2), wt.float(), stride=2, padding=3).permute(0, 2, 3, 1)
     assert _rel(out, ref) < 2e-5
     # 3x3/2 im2col (vector path)
