@@ -83,6 +83,14 @@ class SegmaskArgs(C.Structure):
     ]
 
 
+class SeglossArgs(C.Structure):
+    _fields_ = [
+        ("logits", _vp), ("batch_stride", _i64), ("tok_stride", _i64),
+        ("B", _i32), ("C", _i32), ("hp", _i32), ("wp", _i32), ("h", _i32), ("w", _i32),
+        ("target", _vp), ("label_smoothing", _f32), ("out", _vp),
+    ]
+
+
 # every symbol include/segofa_b200.h declares: (name, restype, argtypes)
 EXPORTS = [
     ("sgf_last_error", C.c_char_p, []),
@@ -99,6 +107,8 @@ EXPORTS = [
     ("sgf_build_attn_bias", C.c_int, [C.POINTER(BiasArgs), _vp]),
     ("sgf_attention_bf16", C.c_int, [C.POINTER(AttentionArgs), _vp]),
     ("sgf_upsample_argmax", C.c_int, [C.POINTER(SegmaskArgs), _vp]),
+    ("sgf_embedding_bag_mean", C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp]),
+    ("sgf_upsample_ce_loss", C.c_int, [C.POINTER(SeglossArgs), _vp]),
 ]
 
 _lib = None

@@ -372,9 +372,49 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
   store8(y, SGF_BF16, ((static_cast<int64_t>(img) * ho + oy) * wo + ox) * c + g * 8, m);
 }
 
+// ragged EmbeddingBag(mean): one warp per bag
+__global__ void __launch_bounds__(256) embedding_bag_mean_kernel(const int64_t* __restrict__ tokens, int64_t ld_tokens,
+                                                                 const int64_t* __restrict__ ends, int B, int P,
+                                                                 const void* table, int table_dtype, int64_t ld_table,
+                                                                 int D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int bag = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (bag >= B * P) return;
+  const int b = bag / P, i = bag - b * P;
+  const int64_t lo = i == 0 ? 0 : ends[bag - 1];
+  const int64_t hi = ends[bag];
+  const int64_t* row = tokens + static_cast<int64_t>(b) * ld_tokens;
+  const float inv = hi > lo ? 1.0f / static_cast<float>(hi - lo) : 0.f;
+  for (int e = lane * 8; e < D; e += 256) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int64_t t = lo; t < hi; ++t) {
+      float v[8];
+      load8(table, table_dtype, row[t] * ld_table + e, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    store8(out, SGF_F32, static_cast<int64_t>(bag) * D + e, acc);
+  }
+}
+
 }  // namespace sgf
 
 using namespace sgf;
+
+extern "C" int sgf_embedding_bag_mean(const int64_t* tokens, int64_t ld_tokens, const int64_t* ends, int32_t B,
+                                      int32_t P, const void* table, int32_t table_dtype, int64_t ld_table, int32_t D,
+                                      float* out, void* stream) {
+  SGF_REQUIRE(tokens && ends && table && out && B > 0 && P > 0 && D > 0 && D % 8 == 0 && ld_table % 8 == 0,
+              "embedding_bag_mean: bad arguments");
+  const int nb = B * P;
+  embedding_bag_mean_kernel<<<(nb + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tokens, ld_tokens, ends, B, P, table, table_dtype, ld_table, D, out);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
 
 extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
   SGF_REQUIRE(a != nullptr, "row_layernorm: null args");

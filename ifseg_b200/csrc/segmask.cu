@@ -91,9 +91,88 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(const SegmaskParam
   }
 }
 
+struct SeglossParams {
+  const float* logits;
+  int64_t batch_stride, tok_stride;
+  int B, C, hp, wp, h, w;
+  const int64_t* target;
+  float eps;
+  float* out;
+  float scale_h, scale_w;
+};
+
+__global__ void __launch_bounds__(256) upsample_ce_loss_kernel(const SeglossParams p) {
+  __shared__ float red[2][8];
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  float loss = 0.f, cnt = 0.f;
+  if (x < p.w) {
+    const int64_t pix = (static_cast<int64_t>(b) * p.h + y) * p.w + x;
+    const int64_t t = p.target[pix];
+    if (t >= 0 && t < p.C) {
+      int y0, y1, x0, x1;
+      float hl0, hl1, wl0, wl1;
+      src_index(p.scale_h, y, p.hp, y0, y1, hl0, hl1);
+      src_index(p.scale_w, x, p.wp, x0, x1, wl0, wl1);
+      const float* base = p.logits + static_cast<int64_t>(b) * p.batch_stride;
+      const float* p00 = base + static_cast<int64_t>(y0 * p.wp + x0) * p.tok_stride;
+      const float* p01 = base + static_cast<int64_t>(y0 * p.wp + x1) * p.tok_stride;
+      const float* p10 = base + static_cast<int64_t>(y1 * p.wp + x0) * p.tok_stride;
+      const float* p11 = base + static_cast<int64_t>(y1 * p.wp + x1) * p.tok_stride;
+      // online logsumexp over the C interpolated logits
+      float m = -INFINITY, ssum = 0.f, vt = 0.f, vsum = 0.f;
+      for (int c = 0; c < p.C; ++c) {
+        const float top = __fadd_rn(__fmul_rn(wl0, __ldg(p00 + c)), __fmul_rn(wl1, __ldg(p01 + c)));
+        const float bot = __fadd_rn(__fmul_rn(wl0, __ldg(p10 + c)), __fmul_rn(wl1, __ldg(p11 + c)));
+        const float v = __fadd_rn(__fmul_rn(hl0, top), __fmul_rn(hl1, bot));
+        if (c == t) vt = v;
+        vsum += v;
+        const float mn = fmaxf(m, v);
+        ssum = ssum * __expf(m - mn) + __expf(v - mn);
+        m = mn;
+      }
+      const float lse = m + __logf(ssum);
+      loss = (1.f - p.eps) * (lse - vt) + p.eps * (lse - vsum / static_cast<float>(p.C));
+      cnt = 1.f;
+    }
+  }
+  loss = warp_sum(loss);
+  cnt = warp_sum(cnt);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[0][warp] = loss;
+    red[1][warp] = cnt;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    loss = lane < 8 ? red[0][lane] : 0.f;
+    cnt = lane < 8 ? red[1][lane] : 0.f;
+    loss = warp_sum(loss);
+    cnt = warp_sum(cnt);
+    if (lane == 0 && cnt > 0.f) {
+      atomicAdd(&p.out[0], loss);
+      atomicAdd(&p.out[1], cnt);
+    }
+  }
+}
+
 }  // namespace sgf
 
 using namespace sgf;
+
+extern "C" int sgf_upsample_ce_loss(const sgf_segloss_args* a, void* stream) {
+  SGF_REQUIRE(a != nullptr && a->logits && a->target && a->out, "upsample_ce_loss: null pointer");
+  SGF_REQUIRE(a->B > 0 && a->C > 0 && a->hp > 0 && a->wp > 0 && a->h > 0 && a->w > 0, "upsample_ce_loss: bad shape");
+  SeglossParams p{a->logits, a->batch_stride, a->tok_stride, a->B, a->C, a->hp, a->wp, a->h, a->w, a->target,
+                  a->label_smoothing, a->out, static_cast<float>(a->hp) / static_cast<float>(a->h),
+                  static_cast<float>(a->wp) / static_cast<float>(a->w)};
+  dim3 block(256), grid((a->w + 255) / 256, a->h, a->B);
+  upsample_ce_loss_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
 
 extern "C" int sgf_upsample_argmax(const sgf_segmask_args* a, void* stream) {
   SGF_REQUIRE(a != nullptr && a->logits && a->mask, "upsample_argmax: null pointer");

@@ -310,19 +310,24 @@ class SegOFAEngine:
         B, T_txt = src_tokens.shape
         artificial = bag_tokens is not None
         feat = None
+        bag = None
         if artificial:
-            raise NotImplementedError(
-                "segofa_b200 round 1: the image-free (EmbeddingBag grid) encoder input is not built yet")
-        if patch_images is None:
+            # image-free branch (encoder_module.py:529-551): every patch is the mean token embedding of its
+            # category word; no ResNet, no image_proj
+            h = w = cfg.patch_image_size // 16
+            bag = ops.embedding_bag_mean(bag_tokens.to(dev).contiguous(), bag_offsets.to(dev).contiguous(),
+                                         self.embed_tokens, h * w)
+        elif patch_images is None:
             raise NotImplementedError("segofa_b200: text-only encoding is not on the IFSeg hot path")
-        feat = self.stem(patch_images.to(dev))
-        h, w = feat.shape[1], feat.shape[2]
+        else:
+            feat = self.stem(patch_images.to(dev))
+            h, w = feat.shape[1], feat.shape[2]
         P = h * w
         T = P + T_txt
         # padding: encoder_module.py:730,737-742
         pad = torch.zeros((B, T), dtype=torch.uint8, device=dev)
         pad[:, P:] = src_tokens.eq(cfg.padding_idx)
-        if patch_masks is not None:
+        if patch_masks is not None and not artificial:
             pad[:, :P] = (~patch_masks.to(dev).bool()).unsqueeze(1)
         if has_pads is None:
             has_pads = bool(pad.any())  # same host sync as encoder_module.py:742
@@ -333,7 +338,10 @@ class SegOFAEngine:
         x = torch.empty((B * T, D), dtype=torch.float32, device=dev)  # fp32 residual stream
         a = torch.empty((B * T, D), dtype=_BF16, device=dev)
         # image rows: image_proj -> +type_embedding(1) -> patch_layernorm_embedding  (:416-423)
-        proj = ops.gemm(feat.view(B * P, 1024), self.w_image_proj, bias=self.b_image_proj, out_dtype=torch.float32)
+        if artificial:
+            proj = bag
+        else:
+            proj = ops.gemm(feat.view(B * P, 1024), self.w_image_proj, bias=self.b_image_proj, out_dtype=torch.float32)
         ops.row_layernorm(proj, pre_add=self.type_img, ln1=self.ln_patch, out1=x, ln2=L0["ln_self"], out2=a,
                           zero_row=pad[:, :P].contiguous().view(-1) if has_pads else None, seg=(P, T, 0))
         # text rows: embed_tokens -> +type_embedding(0) -> layernorm_embedding  (:400-408)
@@ -365,7 +373,7 @@ class SegOFAEngine:
             "patch_images": [],
             "image_embed_before_scale": [enc["image_proj"].view(B, P, D)],
             "image_embed_shape": [enc["hw"]],
-            "image_embed_before_proj": [enc["image_features"].view(B, P, -1)],
+            "image_embed_before_proj": [enc["image_features"].view(B, P, -1) if enc["image_features"] is not None else None],
         }
 
     # ------------------------------------------------------------------------------------

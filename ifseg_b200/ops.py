@@ -258,3 +258,34 @@ def upsample_argmax(logits, hp, wp, h, w, target=None, num_tokens=None):
     with _timed("upsample_argmax", nbytes=float(mask.numel() * 8 + B * hp * wp * Cn * 4)):
         _lib.check(lib.sgf_upsample_argmax(C.byref(args), _stream()), "sgf_upsample_argmax")
     return (mask, areas) if target is not None else mask
+
+
+def embedding_bag_mean(tokens, ends, table, P):
+    """tokens int64 [B,L] (pads at the row tails), ends int64 [B*P] per-sample cumulative bag lengths,
+    table [V,D] fp32/bf16 -> fp32 [B*P, D] bag means (nn.EmbeddingBag(mode='mean') of the image-free branch)."""
+    lib = _lib.load()
+    _req(tokens, torch.int64, "tokens")
+    _req(ends, torch.int64, "ends")
+    _req(table, None, "table")
+    B = tokens.shape[0]
+    D = table.shape[1]
+    out = torch.empty((B * P, D), dtype=torch.float32, device=tokens.device)
+    with _timed("embedding_bag", nbytes=float(out.numel() * 4)):
+        _lib.check(lib.sgf_embedding_bag_mean(_p(tokens), tokens.stride(0), _p(ends), B, P, _p(table), _DT[table.dtype],
+                                              table.stride(0), D, _p(out), _stream()), "sgf_embedding_bag_mean")
+    return out
+
+
+def upsample_ce_loss(logits, target, hp, wp, label_smoothing=0.0):
+    """mean pixel cross-entropy of the bilinearly upsampled logits (fp32 [B,>=hp*wp,C]) against
+    target int64 [B,h,w] class ids (ids outside [0,C) are ignored).  Returns (loss 0-dim, count 0-dim)."""
+    lib = _lib.load()
+    _req(logits, torch.float32, "logits")
+    _req(target, torch.int64, "target")
+    B, h, w = target.shape
+    acc = torch.zeros(2, dtype=torch.float32, device=logits.device)
+    args = _lib.SeglossArgs(_p(logits), logits.stride(0), logits.stride(1), B, logits.shape[2], hp, wp, h, w,
+                            _p(target), float(label_smoothing), _p(acc))
+    with _timed("upsample_ce", nbytes=float(target.numel() * 8)):
+        _lib.check(lib.sgf_upsample_ce_loss(C.byref(args), _stream()), "sgf_upsample_ce_loss")
+    return acc[0] / acc[1], acc[1]

@@ -190,6 +190,35 @@ typedef struct {
 } sgf_segmask_args;
 int sgf_upsample_argmax(const sgf_segmask_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Ragged EmbeddingBag(mode="mean") of the image-free branch: patch (b,i) is the mean of the
+ * table rows of tokens[b, ends[b,i-1] : ends[b,i]] (ends = per-sample cumulative bag lengths,
+ * ends[b,-1] = 0; pads sit at the tail of each token row, so no flatten/compact pass is needed).
+ * One warp per bag, fp32 accumulation, out fp32 [B*P, D].
+ * Replaces encoder_module.py:529-542 (mask-select, offset arithmetic, nn.EmbeddingBag) and
+ * seg_criterion.py:386-393 (_lazy_initialization: B = 1, one bag per class name).
+ * ------------------------------------------------------------------------------------- */
+int sgf_embedding_bag_mean(const int64_t* tokens, int64_t ld_tokens, const int64_t* ends, int32_t B, int32_t P,
+                           const void* table, int32_t table_dtype, int64_t ld_table, int32_t D, float* out,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Pixel cross-entropy on the bilinearly upsampled logits without materialising them
+ * (seg_criterion.py:246-267 / :340): for every pixel of the (h,w) grid the C interpolated logits
+ * live in registers; loss_pix = logsumexp - logit[target] (label smoothing eps as in
+ * F.cross_entropy); pixels whose target is outside [0,C) are ignored.
+ *   out[0] += sum of pixel losses, out[1] += number of counted pixels (fp32 atomics; caller zeroes).
+ *   logits fp32 [B, >= hp*wp, C]; target int64 [B,h,w] class ids (dictionary ids minus seg_id_offset).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* logits; int64_t batch_stride; int64_t tok_stride;
+  int32_t B, C, hp, wp, h, w;
+  const int64_t* target;
+  float label_smoothing;
+  float* out; /* [2] */
+} sgf_segloss_args;
+int sgf_upsample_ce_loss(const sgf_segloss_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,3 +124,62 @@ def test_launches_are_ours(case15):
     n = ops.launch_count()
     print("kernel launches per forward:", n)
     assert n > 100
+
+
+def test_image_free_branch_vs_reference_golden(case15):
+    """models/segofa/segofa.py:136-151: aux_input -> extra['aux_output'][0] (always causal)."""
+    g, model, _ = case15
+    aux = {k: v.cuda() for k, v in g["aux_input"].items()}
+    with torch.no_grad():
+        x, extra = model(aux_input=aux)
+    assert x is None
+    ax = extra["aux_output"][0]
+    err = rel_l2(ax, g["aux_logits"])
+    print(f"image-free branch rel-L2 vs reference fp32: {err:.3e}")
+    assert ax.shape == g["aux_logits"].shape and err <= 0.75 * g["ref_bf16_rel_l2"]
+
+
+def test_criterion_eval_branch(case15):
+    """SegCriterion.forward (eval): areas == compute_metric on the oracle-upsampled logits of OUR logits,
+    display CE == F.cross_entropy; keys as seg_criterion.py:222-233."""
+    import types
+    from ifseg_b200.fairseq_compat import StubDictionary
+    from ifseg_b200.seg_criterion import SegCriterion, derive_metrics
+    from oracle import restated as R
+
+    g, model, _ = case15
+    S, C = g["image_size"], g["num_seg"]
+    task = types.SimpleNamespace(target_dictionary=StubDictionary(C),
+                                 cfg=types.SimpleNamespace(num_seg_tokens=C, category_list=",".join(f"c{i}" for i in range(C))))
+    crit = SegCriterion(task)
+    gen = torch.Generator().manual_seed(9)
+    classes = torch.randint(0, C + 1, (g["batch"], S * S), generator=gen)  # includes the 'unknown' id C
+    target = torch.cat([classes + 59457, torch.full((g["batch"], 1), 2)], 1)
+    inp = _inputs(g, model)
+    sample = {"net_input": inp, "target": target, "ntokens": 1, "nsentences": g["batch"]}
+    loss, sample_size, log = crit(model, sample)
+    for k in ("loss", "imfree_loss", "seg_loss", "ntokens", "nsentences", "sample_size", "area_intersect",
+              "area_pred_label", "area_label", "area_union", "nll_loss"):
+        assert k in log
+    with torch.no_grad():
+        x, _ = model(**inp)
+    up = R.upsample_logits(x.cpu(), S // 16, S // 16, S, S)[:, :-1].reshape(-1, C)
+    t = classes.reshape(-1)
+    valid = t < C
+    ai, ap, al, au = R.compute_metric(up[valid], t[valid])
+    assert torch.equal(log["area_intersect"].cpu(), ai) and torch.equal(log["area_pred_label"].cpu(), ap)
+    assert torch.equal(log["area_label"].cpu(), al) and torch.equal(log["area_union"].cpu(), au)
+    ref_loss = torch.nn.functional.cross_entropy(up[valid], t[valid])
+    assert abs(loss.item() - ref_loss.item()) < 1e-3
+    m = derive_metrics(ai, ap, al, au)
+    assert 0 <= m["mIoU"] <= 1 and 0 <= m["aAcc"] <= 1
+    # image-free loss value (training forward) against the oracle's imfree_loss on OUR aux logits
+    aux = {k: v.cuda() for k, v in g["aux_input"].items()}
+    t2s = torch.cat([torch.randint(0, C + 1, (g["batch"], S * S), generator=gen) + 59457,
+                     torch.full((g["batch"], 1), 2)], 1)
+    val = crit.imfree_loss_value(model, {"aux_input": aux, "text2seg_target": t2s})
+    with torch.no_grad():
+        _, extra = model(aux_input=aux)
+    ocfg = R.SegOFAConfig(num_seg=C, patch_image_size=S)
+    ref_val = R.imfree_loss(extra["aux_output"][0].cpu(), t2s, ocfg)
+    assert abs(val.item() - ref_val.item()) < 1e-3

@@ -267,3 +267,43 @@ def test_build_attn_bias(ops):
     ref[:, 0:64, 0:64] += tab_a[bucket[ids_a][:, ids_a]].permute(2, 0, 1)
     ref[:, 74:100, 74:100] += tab_b[bucket[ids_b][:, ids_b]].permute(2, 0, 1)
     assert torch.allclose(out[:, :, :T], ref, atol=1e-6)
+
+
+def test_embedding_bag_mean(ops):
+    g = torch.Generator(device="cuda").manual_seed(31)
+    V, D, B, P = 500, 768, 3, 16
+    table = torch.randn(V, D, device="cuda", generator=g)
+    lens = torch.randint(1, 5, (B, P), device="cuda", generator=g)
+    L = int(lens.sum(1).max())
+    tokens = torch.full((B, L), 1, dtype=torch.long, device="cuda")
+    for b in range(B):
+        n = int(lens[b].sum())
+        tokens[b, :n] = torch.randint(4, V, (n,), device="cuda", generator=g)
+    ends = lens.cumsum(1).reshape(-1)
+    out = ops.embedding_bag_mean(tokens, ends, table, P)
+    # reference: the flatten/offset arithmetic of encoder_module.py:529-538 + nn.EmbeddingBag(mean)
+    flat = tokens[tokens != 1]
+    off = ends.view(B, P)
+    off = torch.cat([off.new_zeros(B, 1), off], 1)
+    base = torch.cat([off.new_zeros(1), off[:-1, -1]]).cumsum(0)
+    starts = (off + base.unsqueeze(1))[:, :-1].flatten()
+    ref = F.embedding_bag(flat, table, starts, mode="mean")
+    assert torch.allclose(out, ref, atol=1e-5)
+    out16 = ops.embedding_bag_mean(tokens, ends, table.bfloat16(), P)
+    assert _rel(out16, ref) < 5e-3
+
+
+@pytest.mark.parametrize("C,hp,h,eps", [(15, 8, 128, 0.0), (150, 4, 64, 0.1), (171, 30, 480, 0.0)])
+def test_upsample_ce_loss(ops, C, hp, h, eps):
+    g = torch.Generator(device="cuda").manual_seed(C)
+    B = 2
+    logits = torch.randn(B, hp * hp + 1, C, device="cuda", generator=g) * 2
+    target = torch.randint(-1, C + 1, (B, h, h), device="cuda", generator=g)
+    loss, cnt = ops.upsample_ce_loss(logits, target, hp, hp, eps)
+    x = logits[:, :-1].reshape(B, hp, hp, C).permute(0, 3, 1, 2)
+    up = F.interpolate(x, size=(h, h), mode="bilinear", align_corners=False).permute(0, 2, 3, 1).reshape(-1, C)
+    t = target.reshape(-1)
+    valid = (t >= 0) & (t < C)
+    ref = F.cross_entropy(up[valid], t[valid], label_smoothing=eps)
+    assert int(cnt.item()) == int(valid.sum().item())
+    assert abs(loss.item() - ref.item()) < 2e-4 * max(1.0, abs(ref.item())), (loss.item(), ref.item())
