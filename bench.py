@@ -249,17 +249,22 @@ def main():
         torch.cuda.profiler.stop()
 
     # ---------------- per-kernel attribution (eager, CUDA events per launch) ----------------
-    timer = ops.KernelTimer()
+    timer = ops.KernelTimer(fine=args.kernel_breakdown)
     ops.set_timer(timer)
     with torch.no_grad(), torch.cuda.stream(sess.compute):
         sess._forward()
-    fam = timer.summary()
+    fam_fine = timer.summary()
     ops.set_timer(None)
+    fam = {}
+    for k, v in fam_fine.items():  # fold the call-site tags back into kernel families
+        d = fam.setdefault(k.split(":")[0], dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        for kk in d:
+            d[kk] += v[kk]
     total_k_ms = sum(v["ms"] for v in fam.values())
     dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
     if args.kernel_breakdown and rank == 0:
-        for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
-            sys.stderr.write(f"{k:20s} launches {v['launches']:4d}  {v['ms']:8.3f} ms  {100 * v['ms'] / total_k_ms:5.1f}%  "
+        for k, v in sorted(fam_fine.items(), key=lambda kv: -kv[1]["ms"]):
+            sys.stderr.write(f"{k:34s} launches {v['launches']:4d}  {v['ms']:8.3f} ms  {100 * v['ms'] / total_k_ms:5.1f}%  "
                              f"{v['flops'] / max(v['ms'], 1e-9) / 1e9:8.1f} TFLOP/s  {v['bytes'] / max(v['ms'], 1e-9) / 1e6:8.1f} GB/s\n")
 
     # ---------------- reduce over ranks ----------------

@@ -201,7 +201,19 @@ SGF_DEVICE float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-SGF_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf-GELU with the Abramowitz-Stegun 7.1.26 rational approximation of erf (|error| <= 1.5e-7,
+// far below the bf16 rounding of the result): 2 MUFU (rcp, ex2) + ~12 FMA-pipe ops, no branches.
+SGF_DEVICE float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = fast_exp2(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);  // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 SGF_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -19,7 +19,10 @@ namespace sgf {
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 static constexpr int UMMA_K = 16;
-static constexpr int kGemmThreads = 192;
+template <int BN>
+static constexpr int gemm_epi_warps() { return BN >= 128 ? 8 : 4; }
+template <int BN>
+static constexpr int gemm_threads() { return 64 + 32 * gemm_epi_warps<BN>(); }
 
 struct GemmEpilogue {
   void* c;
@@ -49,10 +52,11 @@ struct GemmSmem {
 };
 
 template <int BN, int kStages, bool kConv>
-__global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const GemmShape shp, const GemmEpilogue ep) {
   using S = GemmSmem<BN>;
+  constexpr int kEpiWarps = gemm_epi_warps<BN>();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16B aligned: round up to the 1024B the 128B swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -138,35 +142,57 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
     }
   } else {
     // ------------------------------ epilogue warps ------------------------------
-    // Phase 1: TMEM -> registers (thread = row), column-wise ops (scale, bias, q-scale, GELU), then
-    //          the row is parked in a per-warp smem staging tile (the pipeline stages are dead by now).
-    // Phase 2: the warp re-reads the tile with lanes along the columns, so the residual loads and
-    //          the output stores are fully coalesced 16/32-byte-per-lane row segments.
+    // kEpiWarps warps; warp (quarter, part) owns TMEM lanes [32*quarter, +32) and columns
+    // [part*kCols, +kCols) of the tile.
+    // Phase 1: TMEM -> registers (thread = row), column-wise ops (scale, bias, q-scale, GELU), row parked
+    //          in a per-warp smem staging tile (the pipeline stages are dead once the accumulator is done).
+    // Phase 2: the tile is re-read with lanes along the columns, so the residual add and the output
+    //          stores are fully coalesced 16/32-byte-per-lane row segments.
+    constexpr int kSplit = kEpiWarps / 4;
+    constexpr int kCols = BN / kSplit;
+    constexpr int kRowPitch = kCols * 4 + 16;  // bytes; +16 keeps the thread-per-row float4 writes conflict-free
+    constexpr int kLanesPerRow = kCols / 8;
+    constexpr int kRowsPerIter = 32 / kLanesPerRow;
+    constexpr int kIters = 32 / kRowsPerIter;
+    static_assert(kEpiWarps * 32 * kRowPitch <= kStages * S::kStageBytes, "epilogue staging must fit in the pipeline smem");
+    const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int part = ew >> 2;
+    uint8_t* stage = smem + ew * (32 * kRowPitch);
+    const int col = part * kCols + (lane % kLanesPerRow) * 8;
+    const int c = n0 + col;
+    const bool vec_ok = (shp.N % 8) == 0 && (c + 8 <= shp.N);
+    const int csz = ep.c_dtype == SGF_F32 ? 4 : 2;
+    const int rsz = ep.r_dtype == SGF_F32 ? 4 : 2;
+
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    constexpr int kRowPitch = BN * 4 + 16;  // bytes; +16 keeps the thread-per-row float4 writes conflict-free
-    uint8_t* stage = smem + quarter * (32 * kRowPitch);
-    static_assert(4 * 32 * kRowPitch <= kStages * S::kStageBytes, "epilogue staging must fit in the pipeline smem");
 
+    // ---- phase 1 ----
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      const int c0 = n0 + ch * 32;
+    for (int ch = 0; ch < kCols / 32; ++ch) {
+      const int c0 = n0 + part * kCols + ch * 32;
       if (c0 >= shp.N) break;  // warp-uniform
       uint32_t acc[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ch * 32, acc);
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + part * kCols + ch * 32, acc);
       tmem_ld_wait();
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-      if (c0 + 32 <= shp.N) {
+      if (c0 + 32 <= shp.N && (shp.N % 4) == 0) {
         if (ep.col_scale) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= __ldg(ep.col_scale + c0 + j);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + c0 + j));
+            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+          }
         }
         if (ep.col_bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.col_bias + c0 + j);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.col_bias + c0 + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
         }
       } else {
 #pragma unroll
@@ -192,17 +218,12 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
     }
     __syncwarp();
 
-    constexpr int kLanesPerRow = BN / 8;
-    constexpr int kRowsPerIter = 32 / kLanesPerRow;
-    const int col = (lane % kLanesPerRow) * 8;
-    const int c = n0 + col;
-    const bool vec_ok = (shp.N % 8) == 0 && (c + 8 <= shp.N);
-    const int csz = ep.c_dtype == SGF_F32 ? 4 : 2;
-    const int rsz = ep.r_dtype == SGF_F32 ? 4 : 2;
-#pragma unroll 1
-    for (int it = 0; it < 32 / kRowsPerIter; ++it) {
-      const int rl = it * kRowsPerIter + lane / kLanesPerRow;
-      const int r = quarter * 32 + rl;
+    // ---- phase 2a: row map + all residual loads of this warp issued back to back (one exposed latency) ----
+    int out_rows[kIters];
+    uint4 res_lo[kIters], res_hi[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int r = quarter * 32 + it * kRowsPerIter + lane / kLanesPerRow;
       int64_t out_row;
       bool row_ok;
       if constexpr (kConv) {
@@ -213,25 +234,41 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
         row_ok = (m0 + r) < shp.M;
         out_row = m0 + r;
       }
-      if (!row_ok || c >= shp.N) continue;
+      out_rows[it] = (row_ok && c < shp.N) ? static_cast<int>(out_row) : -1;
+      res_lo[it] = make_uint4(0, 0, 0, 0);
+      res_hi[it] = make_uint4(0, 0, 0, 0);
+      if (ep.residual && vec_ok && out_rows[it] >= 0) {
+        const uint8_t* rptr = reinterpret_cast<const uint8_t*>(ep.residual) +
+                              (static_cast<int64_t>(z) * ep.r_batch_stride + out_row * ep.ldr + c) * rsz;
+        res_lo[it] = *reinterpret_cast<const uint4*>(rptr);
+        if (ep.r_dtype == SGF_F32) res_hi[it] = *reinterpret_cast<const uint4*>(rptr + 16);
+      }
+    }
+
+    // ---- phase 2b ----
+    const int scol = (lane % kLanesPerRow) * 8;  // column inside this warp's staging tile
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      if (out_rows[it] < 0) continue;
+      const int rl = it * kRowsPerIter + lane / kLanesPerRow;
       float v[8];
       {
-        const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + col * 4);
-        const float4 b4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + col * 4 + 16);
+        const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + scol * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + scol * 4 + 16);
         v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
       }
-      uint8_t* cptr = reinterpret_cast<uint8_t*>(ep.c) + (static_cast<int64_t>(z) * ep.c_batch_stride + out_row * ep.ldc + c) * csz;
-      const uint8_t* rptr = ep.residual ? reinterpret_cast<const uint8_t*>(ep.residual) +
-                                              (static_cast<int64_t>(z) * ep.r_batch_stride + out_row * ep.ldr + c) * rsz
-                                        : nullptr;
+      uint8_t* cptr = reinterpret_cast<uint8_t*>(ep.c) +
+                      (static_cast<int64_t>(z) * ep.c_batch_stride + static_cast<int64_t>(out_rows[it]) * ep.ldc + c) * csz;
       if (vec_ok) {
-        if (rptr) {
+        if (ep.residual) {
           if (ep.r_dtype == SGF_F32) {
-            const float4 r0 = *reinterpret_cast<const float4*>(rptr), r1 = *reinterpret_cast<const float4*>(rptr + 16);
-            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+            v[0] += __uint_as_float(res_lo[it].x); v[1] += __uint_as_float(res_lo[it].y);
+            v[2] += __uint_as_float(res_lo[it].z); v[3] += __uint_as_float(res_lo[it].w);
+            v[4] += __uint_as_float(res_hi[it].x); v[5] += __uint_as_float(res_hi[it].y);
+            v[6] += __uint_as_float(res_hi[it].z); v[7] += __uint_as_float(res_hi[it].w);
           } else {
-            const uint4 r4 = *reinterpret_cast<const uint4*>(rptr);
-            const float2 a = unpack_bf16x2(r4.x), b2 = unpack_bf16x2(r4.y), c2 = unpack_bf16x2(r4.z), d = unpack_bf16x2(r4.w);
+            const float2 a = unpack_bf16x2(res_lo[it].x), b2 = unpack_bf16x2(res_lo[it].y),
+                         c2 = unpack_bf16x2(res_lo[it].z), d = unpack_bf16x2(res_lo[it].w);
             v[0] += a.x; v[1] += a.y; v[2] += b2.x; v[3] += b2.y; v[4] += c2.x; v[5] += c2.y; v[6] += d.x; v[7] += d.y;
           }
         }
@@ -249,6 +286,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tcgen05_kernel(const __grid
           *reinterpret_cast<uint4*>(cptr) = o;
         }
       } else {
+        const uint8_t* rptr = ep.residual ? reinterpret_cast<const uint8_t*>(ep.residual) +
+                                                (static_cast<int64_t>(z) * ep.r_batch_stride + static_cast<int64_t>(out_rows[it]) * ep.ldr + c) * rsz
+                                          : nullptr;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (c + j < shp.N) {
@@ -293,7 +333,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     SGF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, shp, ep);
+  kern<<<grid, gemm_threads<BN>(), smem, st>>>(tmA, tmB, shp, ep);
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return SGF_OK;

@@ -172,7 +172,7 @@ class SegOFAEngine:
         """x [N,H,W,Cin] bf16 NHWC -> [N,Ho,Wo,Cout] bf16."""
         n, h, w, _ = x.shape
         if c.kh == 3 and c.stride == 1 and c.cin % 64 == 0 and residual is None:
-            return ops.conv3x3_s1(x, c.w, c.scale, c.bias, act=act)
+            return ops.conv3x3_s1(x, c.w, c.scale, c.bias, act=act, tag=f"stem3x3_{h}")
         if c.kh == 1 and c.stride == 1:
             a, ho, wo = x.view(n * h * w, c.cin), h, w
         else:  # the few strided convs: explicit patch matrix (7x7/2, 3x3/2, 1x1/2)
@@ -180,7 +180,8 @@ class SegOFAEngine:
         out = torch.empty((n, ho, wo, c.cout), dtype=_BF16, device=x.device)
         ops.gemm(a, c.w, out.view(-1, c.cout), M=n * ho * wo, N=c.cout, K=c.k, lda=a.stride(0), ldb=c.ldk,
                  scale=c.scale, bias=c.bias, act=act,
-                 residual=residual.view(-1, c.cout) if residual is not None else None)
+                 residual=residual.view(-1, c.cout) if residual is not None else None,
+                 tag=f"stem{c.kh}x{c.kh}s{c.stride}_{ho}_k{c.k}_n{c.cout}")
         return out
 
     def stem(self, patch_images):
@@ -285,18 +286,18 @@ class SegOFAEngine:
     def _self_attention(self, a, L, B, T, bias, causal, kpm):
         cfg = self.cfg
         D, H = cfg.embed_dim, cfg.heads
-        qkv = ops.gemm(a, L["wqkv"], bias=L["bqkv"], alpha=cfg.attn_scaling, alpha_cols=D)  # [B*T,3D]
+        qkv = ops.gemm(a, L["wqkv"], bias=L["bqkv"], alpha=cfg.attn_scaling, alpha_cols=D, tag="qkv")  # [B*T,3D]
         o = torch.empty((B * T, D), dtype=_BF16, device=self.device)
         ops.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], o, B=B, H=H, Tq=T, Tk=T, q_strides=(3 * D, T * 3 * D),
                       k_strides=(3 * D, T * 3 * D), v_strides=(3 * D, T * 3 * D), o_strides=(D, T * D), bias=bias,
                       head_scale=L["c_attn"], key_padding_mask=kpm, causal=causal)
-        return ops.gemm(o, L["wo"], bias=L["bo"], out_dtype=torch.float32)
+        return ops.gemm(o, L["wo"], bias=L["bo"], out_dtype=torch.float32, tag="out_proj")
 
     def _ffn(self, a, x, L):
-        f = ops.gemm(a, L["w1"], bias=L["b1"], act=ops.ACT_GELU)
+        f = ops.gemm(a, L["w1"], bias=L["b1"], act=ops.ACT_GELU, tag="fc1")
         g = torch.empty_like(f)
         ops.row_layernorm(f, ln2=L["ln_ffn"], out2=g)
-        ops.gemm(g, L["w2"], x, bias=L["b2"], residual=x)  # x <- x + fc2(...)   (fp32 stream, in place)
+        ops.gemm(g, L["w2"], x, bias=L["b2"], residual=x, tag="fc2")  # x <- x + fc2(...)   (fp32 stream, in place)
 
     # ------------------------------------------------------------------------------------
     # encoder
@@ -407,19 +408,19 @@ class SegOFAEngine:
                               seg=(P, Td, 1))
         # cross-attention K/V of every layer in one GEMM: [B*Te, L*2D]
         nL = len(self.dec_layers)
-        kv_all = ops.gemm(enc_out, self.w_cross_kv_all, bias=self.b_cross_kv_all)
+        kv_all = ops.gemm(enc_out, self.w_cross_kv_all, bias=self.b_cross_kv_all, tag="cross_kv")
         a2 = torch.empty_like(a)
         o = torch.empty((B * Td, D), dtype=_BF16, device=dev)
         for li, L in enumerate(self.dec_layers):
             y = self._self_attention(a, L["attn"], B, Td, self_biases[li], not full_context_alignment, None)
             ops.row_layernorm(y, ln1=L["ln_self_attn"], residual=x, out1=x, ln2=L["ln_enc_attn"], out2=a2)
             C = L["cross"]
-            q = ops.gemm(a2, C["wq"], bias=C["bq"], alpha=cfg.attn_scaling, alpha_cols=D)
+            q = ops.gemm(a2, C["wq"], bias=C["bq"], alpha=cfg.attn_scaling, alpha_cols=D, tag="cross_q")
             kbase = kv_all[:, li * 2 * D:]
             ops.attention(q, kbase, kbase[:, D:], o, B=B, H=H, Tq=Td, Tk=Te, q_strides=(D, Td * D),
                           k_strides=(nL * 2 * D, Te * nL * 2 * D), v_strides=(nL * 2 * D, Te * nL * 2 * D),
                           o_strides=(D, Td * D), bias=cross_abs, head_scale=C["c_attn"], key_padding_mask=kpm)
-            y = ops.gemm(o, C["wo"], bias=C["bo"], out_dtype=torch.float32)
+            y = ops.gemm(o, C["wo"], bias=C["bo"], out_dtype=torch.float32, tag="out_proj")
             ops.row_layernorm(y, ln1=L["ln_cross_attn"], residual=x, out1=x, ln2=L["ln_final"], out2=a)
             self._ffn(a, x, L)
             nxt = self.dec_layers[li + 1]["ln_self"] if li + 1 < nL else self.ln_dec_out

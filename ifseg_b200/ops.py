@@ -35,7 +35,8 @@ class KernelTimer:
     """Optional per-launch CUDA-event timing (used by bench.py to attribute the step to kernel
     families and to compute the roofline of the dominant one).  Off by default: zero overhead."""
 
-    def __init__(self):
+    def __init__(self, fine=False):
+        self.fine = fine  # split the GEMM family by call-site tag
         self.records = []  # (family, start_event, end_event, flops, bytes)
 
     def summary(self):
@@ -86,7 +87,7 @@ def reset_launch_count():
 
 def gemm(a, b, out=None, *, bias=None, scale=None, residual=None, act=ACT_NONE, alpha=1.0, alpha_cols=0,
          out_dtype=torch.bfloat16, batch=1, M=None, N=None, K=None, lda=None, ldb=None, ldc=None, ldr=None,
-         a_batch_stride=0, b_batch_stride=0, c_batch_stride=0, r_batch_stride=0):
+         a_batch_stride=0, b_batch_stride=0, c_batch_stride=0, r_batch_stride=0, tag=None):
     """out[M,N] = epilogue(a[M,K] @ b[N,K]^T).  a, b bf16 with unit inner stride; explicit
     M/N/K/ld*/batch strides allow strided views (heads, concatenated buffers)."""
     lib = _lib.load()
@@ -108,12 +109,12 @@ def gemm(a, b, out=None, *, bias=None, scale=None, residual=None, act=ACT_NONE, 
         M, N, K, batch, _p(scale), _p(bias), _p(residual),
         (residual.stride(-2) if ldr is None else ldr) if residual is not None else 0, r_batch_stride,
         _DT[residual.dtype] if residual is not None else SGF_BF16, act, float(alpha), int(alpha_cols))
-    with _timed("gemm_tcgen05", 2.0 * M * N * K * batch):
+    with _timed("gemm_tcgen05" + (":" + tag if tag and _TIMER is not None and _TIMER.fine else ""), 2.0 * M * N * K * batch):
         _lib.check(lib.sgf_gemm_bf16(C.byref(args), _stream()), "sgf_gemm_bf16")
     return out
 
 
-def conv3x3_s1(x, w, scale, bias, act=ACT_RELU, out=None):
+def conv3x3_s1(x, w, scale, bias, act=ACT_RELU, out=None, tag=None):
     """x [N,H,W,Cin] bf16 NHWC, w [Cout,3,3,Cin] bf16 -> [N,H,W,Cout] bf16."""
     lib = _lib.load()
     _req(x, torch.bfloat16, "x")
@@ -124,7 +125,7 @@ def conv3x3_s1(x, w, scale, bias, act=ACT_RELU, out=None):
     if out is None:
         out = torch.empty((n, h, wd, cout), dtype=torch.bfloat16, device=x.device)
     args = _lib.Conv3x3Args(_p(x), _p(w), _p(out), n, h, wd, cin, cout, _p(scale), _p(bias), act)
-    with _timed("gemm_tcgen05", 2.0 * n * h * wd * cout * 9 * cin):
+    with _timed("gemm_tcgen05" + (":" + tag if tag and _TIMER is not None and _TIMER.fine else ""), 2.0 * n * h * wd * cout * 9 * cin):
         _lib.check(lib.sgf_conv3x3_s1_nhwc(C.byref(args), _stream()), "sgf_conv3x3_s1_nhwc")
     return out
 
