@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05_kernel(const _
   uint64_t* bar_b = bar_q + 6;  // bias tile landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 7);
 
+  pdl_trigger();
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int q0 = blockIdx.x * kQTile;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_tcgen05_kernel(const _
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;        // S ping-pong: columns [0,64) and [64,128)
   const uint32_t tmem_t = tmem_base + 128;  // T = P V: columns [128,192)
+  pdl_wait();
 
   if (tid == 0) {
     mbar_expect_tx(bar_q, AttnSmem::kQ);
@@ -328,8 +330,8 @@ extern "C" int sgf_attention_bf16(const sgf_attention_args* a, void* stream) {
     configured = true;
   }
   dim3 grid((a->Tq + kQTile - 1) / kQTile, a->H, a->B);
-  attention_tcgen05_kernel<<<grid, kAttnThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmB, p);
-  SGF_CHECK_CUDA(cudaGetLastError());
+  SGF_CHECK_CUDA(launch_pdl(attention_tcgen05_kernel, grid, dim3(kAttnThreads), smem,
+                            reinterpret_cast<cudaStream_t>(stream), tmQ, tmK, tmV, tmB, p));
   count_launch();
   return SGF_OK;
 }

@@ -39,6 +39,33 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* 
                 const uint32_t* elem_strides = nullptr);
 
 // ----------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the library is launched with the
+// programmatic-stream-serialization attribute, signals `launch_dependents` as its first
+// instruction and executes `griddepcontrol.wait` before its first global-memory access.  The
+// next kernel's launch latency and prologue (barrier init, TMEM allocation, descriptor
+// prefetch) then overlap the tail of the previous kernel; after the wait the previous grid has
+// completed and its writes are visible, so data hazards are exactly those of a plain stream.
+// ----------------------------------------------------------------------------------------
+SGF_DEVICE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+SGF_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ----------------------------------------------------------------------------------------
 // small helpers
 // ----------------------------------------------------------------------------------------
 SGF_DEVICE uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }

@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
   uint64_t* accum_bar = empty_bar + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -333,8 +335,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     SGF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, gemm_threads<BN>(), smem, st>>>(tmA, tmB, shp, ep);
-  SGF_CHECK_CUDA(cudaGetLastError());
+  SGF_CHECK_CUDA(launch_pdl(kern, grid, dim3(gemm_threads<BN>()), smem, st, tmA, tmB, shp, ep));
   count_launch();
   return SGF_OK;
 }

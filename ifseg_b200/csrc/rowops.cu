@@ -66,6 +66,7 @@ SGF_DEVICE void smem_load8(const uint8_t* row, int dtype, int e, float (&v)[8]) 
 
 __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const RowLnParams p, const int x_row_bytes,
                                                                         const int r_row_bytes, const int s_row_bytes) {
+  pdl_trigger();
   const int kLnRows = blockDim.x >> 5;
   extern __shared__ __align__(128) uint8_t ln_smem[];
   uint8_t* xbuf = ln_smem;                                   // [kLnRows][x_row_bytes]
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const Ro
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
   const int row = row0 + warp;
   const bool live = warp < nrows;
   int64_t dst_row = row;
@@ -448,7 +450,7 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
     configured_smem = 200 * 1024;
   }
   dim3 block(kLnRows * 32), grid((a->rows + kLnRows - 1) / kLnRows);
-  row_layernorm_kernel<<<grid, block, smem, st>>>(p, x_row_bytes, r_row_bytes, s_row_bytes);
+  SGF_CHECK_CUDA(launch_pdl(row_layernorm_kernel, grid, block, smem, st, p, x_row_bytes, r_row_bytes, s_row_bytes));
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return SGF_OK;
