@@ -25,6 +25,7 @@ class GemmArgs(C.Structure):
         ("col_scale", _vp), ("col_bias", _vp),
         ("residual", _vp), ("ldr", _i64), ("r_batch_stride", _i64), ("r_dtype", _i32),
         ("act", _i32), ("alpha", _f32), ("alpha_cols", _i32),
+        ("rowstats_out", _vp), ("rownorm_stats", _vp), ("rownorm_u", _vp), ("rownorm_dim", _i32),
     ]
 
 
@@ -48,6 +49,7 @@ class RowLnArgs(C.Structure):
         ("zero_row", _vp),
         ("rows", _i32), ("D", _i32),
         ("seg_len", _i32), ("seg_stride", _i32), ("seg_off", _i32),
+        ("clear_rowstats", _vp),
     ]
 
 
@@ -130,7 +132,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError -> missing export
         fn.restype = res
         fn.argtypes = args
-    if lib.sgf_abi_version() != 1:
+    if lib.sgf_abi_version() != 2:
         raise RuntimeError("libsegofa_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -36,6 +36,11 @@ struct GemmEpilogue {
   int act;
   float alpha;
   int alpha_cols;
+  float* rowstats_out;
+  const float* rownorm_stats;
+  const float* rownorm_u;
+  float rownorm_inv_dim;
+  int rownorm_parts;
 };
 
 struct GemmShape {
@@ -167,6 +172,26 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
     const int csz = ep.c_dtype == SGF_F32 ? 4 : 2;
     const int rsz = ep.r_dtype == SGF_F32 ? 4 : 2;
 
+    // folded-LayerNorm row statistics of this thread's row: summed (fixed order -> deterministic) while the
+    // main loop is still running
+    bool rn_on = false;
+    float rn_mean = 0.f, rn_rstd = 1.f;
+    if constexpr (!kConv) {
+      if (ep.rownorm_stats) {
+        rn_on = true;
+        const int mrow = min(m0 + quarter * 32 + lane, shp.M - 1);
+        const float4* sp = reinterpret_cast<const float4*>(ep.rownorm_stats) +
+                           (static_cast<int64_t>(z) * shp.M + mrow) * (ep.rownorm_parts / 2);
+        float s0 = 0.f, s1 = 0.f;
+        for (int q = 0; q < ep.rownorm_parts / 2; ++q) {
+          const float4 t = __ldg(sp + q);
+          s0 += t.x; s1 += t.y; s0 += t.z; s1 += t.w;
+        }
+        rn_mean = s0 * ep.rownorm_inv_dim;
+        rn_rstd = rsqrtf(fmaxf(s1 * ep.rownorm_inv_dim - rn_mean * rn_mean, 0.f) + 1e-5f);
+      }
+    }
+
     mbar_wait(accum_bar, 0);
     tc_fence_after();
 
@@ -181,6 +206,13 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+      if (rn_on) {  // folded LayerNorm of the A operand: v = rstd * (v - mean * u[n])
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float u = (c0 + j < shp.N) ? __ldg(ep.rownorm_u + c0 + j) : 0.f;
+          v[j] = rn_rstd * (v[j] - rn_mean * u);
+        }
+      }
       if (c0 + 32 <= shp.N && (shp.N % 4) == 0) {
         if (ep.col_scale) {
 #pragma unroll
@@ -251,7 +283,8 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
     const int scol = (lane % kLanesPerRow) * 8;  // column inside this warp's staging tile
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
-      if (out_rows[it] < 0) continue;
+      float st_sum = 0.f, st_sq = 0.f;
+      if (out_rows[it] >= 0) {
       const int rl = it * kRowsPerIter + lane / kLanesPerRow;
       float v[8];
       {
@@ -286,6 +319,15 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
           o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
           o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
           *reinterpret_cast<uint4*>(cptr) = o;
+          if (ep.rowstats_out) {  // statistics of exactly what was stored
+            const float2 a = unpack_bf16x2(o.x), b2 = unpack_bf16x2(o.y), c2 = unpack_bf16x2(o.z), d = unpack_bf16x2(o.w);
+            v[0] = a.x; v[1] = a.y; v[2] = b2.x; v[3] = b2.y; v[4] = c2.x; v[5] = c2.y; v[6] = d.x; v[7] = d.y;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              st_sum += v[j];
+              st_sq = fmaf(v[j], v[j], st_sq);
+            }
+          }
         }
       } else {
         const uint8_t* rptr = ep.residual ? reinterpret_cast<const uint8_t*>(ep.residual) +
@@ -304,6 +346,22 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
             else
               reinterpret_cast<__nv_bfloat16*>(cptr)[j] = __float2bfloat16_rn(t);
           }
+        }
+      }
+      }  // valid row
+      if constexpr (kCols == 64)
+      if (ep.rowstats_out) {  // warp-uniform: reduce over the lanes that share a row, one slot per row segment
+#pragma unroll
+        for (int o = kLanesPerRow / 2; o > 0; o >>= 1) {
+          st_sum += __shfl_xor_sync(0xffffffffu, st_sum, o);
+          st_sq += __shfl_xor_sync(0xffffffffu, st_sq, o);
+        }
+        if ((lane % kLanesPerRow) == 0 && out_rows[it] >= 0) {
+          // deterministic: one (sum, sumsq) slot per 64-column block of the row, summed in order by the consumer
+          const int nparts = (shp.N + 63) / 64;
+          float2* sp = reinterpret_cast<float2*>(ep.rowstats_out) +
+                       (static_cast<int64_t>(z) * shp.M + out_rows[it]) * nparts + (n0 + part * kCols) / 64;
+          *sp = make_float2(st_sum, st_sq);
         }
       }
     }
@@ -389,11 +447,18 @@ extern "C" int sgf_gemm_bf16(const sgf_gemm_args* a, void* stream) {
   GemmShape shp{};
   shp.M = a->M; shp.N = a->N; shp.K = a->K;
   GemmEpilogue ep{a->c, a->ldc, a->c_batch_stride, a->c_dtype, a->col_scale, a->col_bias, a->residual,
-                  a->ldr, a->r_batch_stride, a->r_dtype, a->act, a->alpha, a->alpha_cols};
+                  a->ldr, a->r_batch_stride, a->r_dtype, a->act, a->alpha, a->alpha_cols, a->rowstats_out,
+                  a->rownorm_stats, a->rownorm_u, a->rownorm_dim > 0 ? 1.0f / static_cast<float>(a->rownorm_dim) : 0.f,
+                  (a->rownorm_dim + 63) / 64};
+  SGF_REQUIRE(!a->rowstats_out || (a->c_dtype == SGF_BF16 && a->N % 64 == 0 && a->N >= 128),
+              "gemm: rowstats_out needs a bf16 output with N a multiple of 64 (>= 128)");
+  SGF_REQUIRE(!a->rownorm_stats || (a->rownorm_u && a->rownorm_dim > 0 && a->rownorm_dim % 128 == 0),
+              "gemm: rownorm_stats needs rownorm_u and rownorm_dim (a multiple of 128)");
   if (int rc = check_epilogue_alignment(ep, a->N)) return rc;
 
   const int m_tiles = (a->M + BM - 1) / BM;
-  const int bn = pick_bn(m_tiles, a->N, a->batch);
+  int bn = pick_bn(m_tiles, a->N, a->batch);
+  if (a->rowstats_out && bn != 64 && bn != 128) bn = 128;  // statistics are kept per 64-column block
 
   CUtensorMap tmA, tmB;
   {
@@ -451,7 +516,8 @@ extern "C" int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* a, void* stream) {
   shp.tiles_w = (a->w_ + bw - 1) / bw;
   shp.tiles_h = (a->h + bh - 1) / bh;
   shp.cin_blocks = a->cin / 64;
-  GemmEpilogue ep{a->y, a->cout, 0, SGF_BF16, a->col_scale, a->col_bias, nullptr, 0, 0, SGF_BF16, a->act, 1.0f, 0};
+  GemmEpilogue ep{a->y, a->cout, 0, SGF_BF16, a->col_scale, a->col_bias, nullptr, 0, 0, SGF_BF16, a->act, 1.0f, 0,
+                  nullptr, nullptr, nullptr, 0.f, 0};
   if (int rc = check_epilogue_alignment(ep, a->cout)) return rc;
 
   const int m_tiles = a->n * shp.tiles_w * shp.tiles_h;

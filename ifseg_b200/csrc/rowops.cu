@@ -20,6 +20,7 @@ struct RowLnParams {
   const uint8_t* zero_row;
   int rows, D;
   int seg_len, seg_stride, seg_off;
+  float* clear_rowstats;
 };
 
 SGF_DEVICE void load8(const void* base, int dtype, int64_t elem_off, float (&v)[8]) {
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const Ro
       bulk_load_1d(rbuf + warp * r_row_bytes, reinterpret_cast<const uint8_t*>(p.residual) + dst_row * p.ldr * rs,
                    r_row_bytes, bar);
   }
+  if (live && p.clear_rowstats && lane < 2) p.clear_rowstats[static_cast<int64_t>(row) * 2 + lane] = 0.f;
   mbar_wait(bar, 0);
   if (!live) return;
 
@@ -430,7 +432,7 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
               "row_layernorm: row strides must be multiples of 8 elements");
   RowLnParams p{a->x, a->ldx, a->x_dtype, a->gather_idx, a->pre_add, a->g1, a->b1, a->residual, a->ldr, a->r_dtype,
                 a->out1, a->ld1, a->out1_dtype, a->g2, a->b2, a->out2, a->ld2, a->zero_row, a->rows, a->D,
-                a->seg_len, a->seg_stride, a->seg_off};
+                a->seg_len, a->seg_stride, a->seg_off, a->clear_rowstats};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int xs = a->x_dtype == SGF_F32 ? 4 : 2, rs = a->r_dtype == SGF_F32 ? 4 : 2;
   const int x_row_bytes = a->D * xs;

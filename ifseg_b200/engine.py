@@ -103,6 +103,16 @@ class SegOFAEngine:
         d["c_attn"] = self._f32(m.c_attn) if m.c_attn is not None else None
         return d
 
+    def _ffn_fold(self, layer):
+        """ffn_layernorm folded into fc2 (see sgf_gemm_args row-norm): W2' = W2 * gamma, u = rowsum(W2'),
+        c = b2 + W2 beta."""
+        w2 = layer.fc2.weight.detach().float().to(self.device)
+        g, b = layer.ffn_layernorm.weight.detach().float().to(self.device), layer.ffn_layernorm.bias.detach().float().to(self.device)
+        w2f = (w2 * g.unsqueeze(0)).to(_BF16).contiguous()
+        u = w2f.float().sum(dim=1).contiguous()
+        c = (layer.fc2.bias.detach().float().to(self.device) + w2 @ b).contiguous()
+        return dict(w2f=w2f, u2=u, c2=c)
+
     def _prepare(self, model):
         enc, dec, cfg = model.encoder, model.decoder, self.cfg
         s = enc.embed_images
@@ -132,8 +142,7 @@ class SegOFAEngine:
             self.enc_layers.append(dict(
                 attn=self._attn(l.self_attn), ln_self=self._ln(l.self_attn_layer_norm), ln_attn=self._ln(l.attn_ln),
                 ln_final=self._ln(l.final_layer_norm), ln_ffn=self._ln(l.ffn_layernorm),
-                w1=self._b16(l.fc1.weight), b1=self._f32(l.fc1.bias), w2=self._b16(l.fc2.weight),
-                b2=self._f32(l.fc2.bias)))
+                w1=self._b16(l.fc1.weight), b1=self._f32(l.fc1.bias), **self._ffn_fold(l)))
         self.ln_enc_out = self._ln(enc.layer_norm)
         self.enc_tok_rel = [self._f32(t.weight) for t in enc.token_rel_pos_table_list]
         self.enc_img_rel = [self._f32(t.weight) for t in enc.image_rel_pos_table_list]
@@ -154,8 +163,7 @@ class SegOFAEngine:
                 ln_self=self._ln(l.self_attn_layer_norm), ln_self_attn=self._ln(l.self_attn_ln),
                 ln_enc_attn=self._ln(l.encoder_attn_layer_norm), ln_cross_attn=self._ln(l.cross_attn_ln),
                 ln_final=self._ln(l.final_layer_norm), ln_ffn=self._ln(l.ffn_layernorm),
-                w1=self._b16(l.fc1.weight), b1=self._f32(l.fc1.bias), w2=self._b16(l.fc2.weight),
-                b2=self._f32(l.fc2.bias)))
+                w1=self._b16(l.fc1.weight), b1=self._f32(l.fc1.bias), **self._ffn_fold(l)))
         # all decoder layers' cross-attention K/V projections of encoder_out as ONE GEMM (N = L*2D)
         self.w_cross_kv_all = torch.cat([d["cross"]["wkv"] for d in self.dec_layers], 0).contiguous()
         self.b_cross_kv_all = torch.cat([d["cross"]["bkv"] for d in self.dec_layers], 0).contiguous()
@@ -293,11 +301,12 @@ class SegOFAEngine:
                       head_scale=L["c_attn"], key_padding_mask=kpm, causal=causal)
         return ops.gemm(o, L["wo"], bias=L["bo"], out_dtype=torch.float32, tag="out_proj")
 
-    def _ffn(self, a, x, L):
-        f = ops.gemm(a, L["w1"], bias=L["b1"], act=ops.ACT_GELU, tag="fc1")
-        g = torch.empty_like(f)
-        ops.row_layernorm(f, ln2=L["ln_ffn"], out2=g)
-        ops.gemm(g, L["w2"], x, bias=L["b2"], residual=x, tag="fc2")  # x <- x + fc2(...)   (fp32 stream, in place)
+    def _ffn(self, a, x, L, stats):
+        """x <- x + fc2(ffn_layernorm(gelu(fc1(a)))) with the F-wide LayerNorm folded into the two GEMM
+        epilogues: fc1 writes per-row (sum, sumsq) of each 64-column block of its bf16 output into `stats`,
+        fc2 sums them in order and applies rstd * (acc - mean * u) + c."""
+        f = ops.gemm(a, L["w1"], bias=L["b1"], act=ops.ACT_GELU, rowstats_out=stats, tag="fc1")
+        ops.gemm(f, L["w2f"], x, bias=L["c2"], residual=x, rownorm=(stats, L["u2"], self.cfg.ffn_dim), tag="fc2")
 
     # ------------------------------------------------------------------------------------
     # encoder
@@ -350,10 +359,11 @@ class SegOFAEngine:
                           pre_add=self.type_txt, ln1=self.ln_emb, out1=x, ln2=L0["ln_self"], out2=a,
                           zero_row=pad[:, P:].contiguous().view(-1) if has_pads else None, seg=(T_txt, T, P))
         a2 = torch.empty_like(a)
+        stats = torch.empty((B * T, cfg.ffn_dim // 64, 2), dtype=torch.float32, device=dev)
         for li, L in enumerate(self.enc_layers):
             y = self._self_attention(a, L["attn"], B, T, biases[li], False, kpm)
             ops.row_layernorm(y, ln1=L["ln_attn"], residual=x, out1=x, ln2=L["ln_final"], out2=a2)
-            self._ffn(a2, x, L)
+            self._ffn(a2, x, L, stats)
             nxt = self.enc_layers[li + 1]["ln_self"] if li + 1 < len(self.enc_layers) else self.ln_enc_out
             ops.row_layernorm(x, ln2=nxt, out2=a)
         return dict(encoder_out=a, B=B, T=T, P=P, hw=(h, w), pad=pad, has_pads=has_pads, pos=pos,
@@ -410,6 +420,7 @@ class SegOFAEngine:
         nL = len(self.dec_layers)
         kv_all = ops.gemm(enc_out, self.w_cross_kv_all, bias=self.b_cross_kv_all, tag="cross_kv")
         a2 = torch.empty_like(a)
+        stats = torch.empty((B * Td, cfg.ffn_dim // 64, 2), dtype=torch.float32, device=dev)
         o = torch.empty((B * Td, D), dtype=_BF16, device=dev)
         for li, L in enumerate(self.dec_layers):
             y = self._self_attention(a, L["attn"], B, Td, self_biases[li], not full_context_alignment, None)
@@ -422,7 +433,7 @@ class SegOFAEngine:
                           o_strides=(D, Td * D), bias=cross_abs, head_scale=C["c_attn"], key_padding_mask=kpm)
             y = ops.gemm(o, C["wo"], bias=C["bo"], out_dtype=torch.float32, tag="out_proj")
             ops.row_layernorm(y, ln1=L["ln_cross_attn"], residual=x, out1=x, ln2=L["ln_final"], out2=a)
-            self._ffn(a, x, L)
+            self._ffn(a, x, L, stats)
             nxt = self.dec_layers[li + 1]["ln_self"] if li + 1 < nL else self.ln_dec_out
             ops.row_layernorm(x, ln2=nxt, out2=a)
         feats = a.view(B, Td, D)

@@ -87,7 +87,8 @@ def reset_launch_count():
 
 def gemm(a, b, out=None, *, bias=None, scale=None, residual=None, act=ACT_NONE, alpha=1.0, alpha_cols=0,
          out_dtype=torch.bfloat16, batch=1, M=None, N=None, K=None, lda=None, ldb=None, ldc=None, ldr=None,
-         a_batch_stride=0, b_batch_stride=0, c_batch_stride=0, r_batch_stride=0, tag=None):
+         a_batch_stride=0, b_batch_stride=0, c_batch_stride=0, r_batch_stride=0, tag=None,
+         rowstats_out=None, rownorm=None):
     """out[M,N] = epilogue(a[M,K] @ b[N,K]^T).  a, b bf16 with unit inner stride; explicit
     M/N/K/ld*/batch strides allow strided views (heads, concatenated buffers)."""
     lib = _lib.load()
@@ -108,7 +109,9 @@ def gemm(a, b, out=None, *, bias=None, scale=None, residual=None, act=ACT_NONE, 
         _p(a), lda, a_batch_stride, _p(b), ldb, b_batch_stride, _p(out), ldc, c_batch_stride, _DT[out.dtype],
         M, N, K, batch, _p(scale), _p(bias), _p(residual),
         (residual.stride(-2) if ldr is None else ldr) if residual is not None else 0, r_batch_stride,
-        _DT[residual.dtype] if residual is not None else SGF_BF16, act, float(alpha), int(alpha_cols))
+        _DT[residual.dtype] if residual is not None else SGF_BF16, act, float(alpha), int(alpha_cols),
+        _p(rowstats_out), _p(rownorm[0]) if rownorm else None, _p(rownorm[1]) if rownorm else None,
+        int(rownorm[2]) if rownorm else 0)
     with _timed("gemm_tcgen05" + (":" + tag if tag and _TIMER is not None and _TIMER.fine else ""), 2.0 * M * N * K * batch):
         _lib.check(lib.sgf_gemm_bf16(C.byref(args), _stream()), "sgf_gemm_bf16")
     return out
@@ -175,7 +178,8 @@ def maxpool3x3s2(x):
 
 
 def row_layernorm(x, *, rows=None, D=None, ldx=None, gather_idx=None, pre_add=None, ln1=None, residual=None,
-                  ldr=None, out1=None, ld1=None, ln2=None, out2=None, ld2=None, zero_row=None, seg=None):
+                  ldr=None, out1=None, ld1=None, ln2=None, out2=None, ld2=None, zero_row=None, seg=None,
+                  clear_rowstats=None):
     """See sgf_row_layernorm in include/segofa_b200.h.  ln1/ln2 = (gamma, beta) fp32 tensors."""
     lib = _lib.load()
     _req(x, None, "x")
@@ -191,7 +195,7 @@ def row_layernorm(x, *, rows=None, D=None, ldx=None, gather_idx=None, pre_add=No
         _DT[out1.dtype] if out1 is not None else SGF_BF16,
         _p(ln2[0]) if ln2 else None, _p(ln2[1]) if ln2 else None,
         _p(out2), (out2.stride(-2) if ld2 is None else ld2) if out2 is not None else 0,
-        _p(zero_row), rows, D, seg_len, seg_stride, seg_off)
+        _p(zero_row), rows, D, seg_len, seg_stride, seg_off, _p(clear_rowstats))
     nb = rows * D * (x.element_size() + (residual.element_size() if residual is not None else 0)
                      + (out1.element_size() if out1 is not None else 0) + (2 if out2 is not None else 0))
     with _timed("row_layernorm", nbytes=float(nb)):

@@ -35,8 +35,17 @@ void sgf_reset_launch_count(void);
 /* ---------------------------------------------------------------------------------------
  * Dense contraction  C[z] = epilogue( A[z] (MxK, K-major) * B[z]^T (NxK, K-major) )
  *   tcgen05.mma (kind::f16, bf16 in / fp32 accumulate in TMEM), TMA-staged 128B-swizzled tiles.
- * epilogue(v)[m,n]:  v *= col_scale[n]; v += col_bias[n]; if n < alpha_cols: v *= alpha;
- *                    GELU (act==2); v += residual[m,n]; ReLU (act==1); store as c_dtype.
+ * epilogue(v)[m,n]:  [row-norm: v = rstd[m] * (v - mean[m] * rownorm_u[n])]
+ *                    v *= col_scale[n]; v += col_bias[n]; if n < alpha_cols: v *= alpha;
+ *                    GELU (act==2); v += residual[m,n]; ReLU (act==1); store as c_dtype;
+ *                    [row-stats: rowstats_out[m] += (sum, sum of squares) of the STORED row segment]
+ * The two bracketed options fold a LayerNorm that sits between two GEMMs into their epilogues
+ * (LN(f) W^T = rstd (f (gamma.W)^T - mean * sum_k gamma_k W_nk) + W beta): the producer GEMM
+ * writes per-row (sum, sumsq) of every 64-column block of its bf16 output to rowstats_out
+ * [M, N/64, 2] (plain stores, no atomics: results are run-to-run deterministic), the consumer GEMM
+ * reads them as rownorm_stats [M, rownorm_dim/64, 2], sums the blocks in order, with rownorm_dim =
+ * row length of the normalised operand and rownorm_u[n] = sum_k W'[n,k].  Used for ffn_layernorm
+ * (unify_transformer_layer.py:281-283, 558-560): the [M, F] LayerNorm pass disappears.
  * Replaces torch.nn.functional.linear / addmm at:
  *   models/segofa/unify_multihead_attention.py:328-345,513 (q/k/v/out_proj, q *= scaling :346)
  *   models/segofa/unify_transformer_layer.py:279-283,556-560 (fc1+gelu, fc2 + residual :289,566)
@@ -55,6 +64,10 @@ typedef struct {
   const void* residual; int64_t ldr; int64_t r_batch_stride; int32_t r_dtype; /* [M,N] or NULL */
   int32_t act;
   float alpha; int32_t alpha_cols;
+  float* rowstats_out;          /* [M, N/64, 2] fp32 or NULL */
+  const float* rownorm_stats;   /* [M, rownorm_dim/64, 2] fp32 or NULL */
+  const float* rownorm_u;       /* [N] fp32 (required with rownorm_stats) */
+  int32_t rownorm_dim;
 } sgf_gemm_args;
 int sgf_gemm_bf16(const sgf_gemm_args* args, void* stream);
 /* tuning hook: force the N-tile (32/64/128/256, 0 = heuristic) and pipeline depth of sgf_gemm_bf16 */
@@ -118,6 +131,7 @@ typedef struct {
   const uint8_t* zero_row;
   int32_t rows, D;
   int32_t seg_len, seg_stride, seg_off;
+  float* clear_rowstats; /* optional [rows,2] fp32 scratch zeroed as a side effect (row-stats of a following GEMM) */
 } sgf_rowln_args;
 int sgf_row_layernorm(const sgf_rowln_args* args, void* stream);
 

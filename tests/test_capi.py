@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == bound, declared ^ bound
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.sgf_abi_version() == 1
+    assert lib.sgf_abi_version() == 2
     assert lib.sgf_launch_count() == 0
 
 

@@ -307,3 +307,30 @@ def test_upsample_ce_loss(ops, C, hp, h, eps):
     ref = F.cross_entropy(up[valid], t[valid], label_smoothing=eps)
     assert int(cnt.item()) == int(valid.sum().item())
     assert abs(loss.item() - ref.item()) < 2e-4 * max(1.0, abs(ref.item())), (loss.item(), ref.item())
+
+
+def test_gemm_folded_layernorm(ops):
+    """ffn_layernorm folded into the fc1/fc2 epilogues == explicit LayerNorm between the GEMMs."""
+    g = torch.Generator(device="cuda").manual_seed(77)
+    M, D, Fd = 515, 768, 3072
+    a = torch.randn(M, D, device="cuda", generator=g).bfloat16()
+    w1 = (torch.randn(Fd, D, device="cuda", generator=g) * 0.03).bfloat16()
+    b1 = torch.randn(Fd, device="cuda", generator=g) * 0.1
+    w2 = torch.randn(D, Fd, device="cuda", generator=g) * 0.02
+    b2 = torch.randn(D, device="cuda", generator=g) * 0.1
+    gam = 1 + 0.1 * torch.randn(Fd, device="cuda", generator=g)
+    bet = 0.05 * torch.randn(Fd, device="cuda", generator=g)
+    res = torch.randn(M, D, device="cuda", generator=g)
+    stats = torch.full((M, Fd // 64, 2), 123.0, device="cuda")
+    f = ops.gemm(a, w1, bias=b1, act=ops.ACT_GELU, rowstats_out=stats)
+    ff = f.float()
+    assert torch.allclose(stats[:, :, 0].sum(1), ff.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[:, :, 1].sum(1), (ff * ff).sum(1), rtol=1e-4, atol=1e-2)
+    stats2 = torch.zeros_like(stats)
+    f2 = ops.gemm(a, w1, bias=b1, act=ops.ACT_GELU, rowstats_out=stats2)
+    assert torch.equal(stats, stats2) and torch.equal(f, f2)  # deterministic
+    w2f = (w2 * gam).bfloat16()
+    out = ops.gemm(f, w2f, bias=b2 + w2 @ bet, residual=res, rownorm=(stats, w2f.float().sum(1).contiguous(), Fd),
+                   out_dtype=torch.float32)
+    ref = F.layer_norm(ff, (Fd,), gam, bet, 1e-5) @ w2.t() + b2 + res
+    assert _rel(out, ref) < 3e-3, _rel(out, ref)
