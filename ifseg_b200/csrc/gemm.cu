@@ -2,10 +2,11 @@
 //
 //   C[M,N] = epilogue( A[M,K] * B[N,K]^T )     bf16 operands, fp32 accumulation in TMEM.
 //
-// One CTA per 128 x BN output tile, 192 threads, warp-specialised:
+// One CTA per 128 x BN output tile, 192/320 threads, warp-specialised:
 //   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (tcgen05.commit frees stages)
-//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> scale/bias/act/residual -> global)
+//   warps 2..   : epilogue       (tcgen05.ld 32x32b -> column ops -> smem staging -> coalesced
+//                                 residual add / activation / store), 4 or 8 warps
 // The same main loop serves the 3x3/s1 convolution: the A tile of filter tap (ky,kx) is a 4-D
 // TMA box [64 ch, bw, bh, 1] of the NHWC input shifted by (kx-1, ky-1); TMA's out-of-bounds
 // zero fill is the convolution padding, so no im2col matrix ever exists.
@@ -56,12 +57,27 @@ struct GemmSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
 };
 
-template <int BN, int kStages, bool kConv>
+// Epilogue feature set.  Specialised kernels carry the flags as a template argument so that each
+// instantiation contains only its own code path (the all-runtime kernel was 130 KB of SASS and
+// stalled on instruction fetch: every CTA runs its epilogue exactly once); kEpiRuntime keeps the
+// fully general path for odd shapes (N not a multiple of 32, rare operand combinations).
+enum : int {
+  kEpiScale = 1, kEpiBias = 2, kEpiAlpha = 4, kEpiGelu = 8, kEpiRelu = 16, kEpiResBf16 = 32, kEpiResF32 = 64,
+  kEpiOutF32 = 128, kEpiRowStats = 256, kEpiRowNorm = 512, kEpiRuntime = 1 << 15
+};
+template <int kEpi, int kFlag>
+SGF_DEVICE bool epi_has(bool runtime_value) {
+  if constexpr ((kEpi & kEpiRuntime) != 0) return runtime_value;
+  else return (kEpi & kFlag) != 0;
+}
+
+template <int BN, int kStages, bool kConv, int kEpi>
 __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const GemmShape shp, const GemmEpilogue ep) {
   using S = GemmSmem<BN>;
   constexpr int kEpiWarps = gemm_epi_warps<BN>();
+  constexpr bool kRt = (kEpi & kEpiRuntime) != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16B aligned: round up to the 1024B the 128B swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -108,6 +124,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
 
   if (warp == 0) {
     if (lane == 0) {
+#pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
@@ -129,6 +146,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+#pragma unroll 1
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
@@ -151,8 +169,8 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
     // ------------------------------ epilogue warps ------------------------------
     // kEpiWarps warps; warp (quarter, part) owns TMEM lanes [32*quarter, +32) and columns
     // [part*kCols, +kCols) of the tile.
-    // Phase 1: TMEM -> registers (thread = row), column-wise ops (scale, bias, q-scale, GELU), row parked
-    //          in a per-warp smem staging tile (the pipeline stages are dead once the accumulator is done).
+    // Phase 1: TMEM -> registers (thread = row), column-wise ops (row-norm, scale, bias, q-scale, GELU),
+    //          row parked in a per-warp smem staging tile (the pipeline stages are dead by then).
     // Phase 2: the tile is re-read with lanes along the columns, so the residual add and the output
     //          stores are fully coalesced 16/32-byte-per-lane row segments.
     constexpr int kSplit = kEpiWarps / 4;
@@ -168,28 +186,31 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
     uint8_t* stage = smem + ew * (32 * kRowPitch);
     const int col = part * kCols + (lane % kLanesPerRow) * 8;
     const int c = n0 + col;
-    const bool vec_ok = (shp.N % 8) == 0 && (c + 8 <= shp.N);
-    const int csz = ep.c_dtype == SGF_F32 ? 4 : 2;
-    const int rsz = ep.r_dtype == SGF_F32 ? 4 : 2;
+    // specialised kernels are only dispatched for N % 32 == 0: a lane's 8 columns are all in or all out
+    const bool vec_ok = kRt ? ((shp.N % 8) == 0 && (c + 8 <= shp.N)) : (c < shp.N);
+    const bool out_f32 = epi_has<kEpi, kEpiOutF32>(ep.c_dtype == SGF_F32);
+    const bool res_f32 = epi_has<kEpi, kEpiResF32>(ep.residual && ep.r_dtype == SGF_F32);
+    const bool res_b16 = epi_has<kEpi, kEpiResBf16>(ep.residual && ep.r_dtype != SGF_F32);
+    const bool do_relu = epi_has<kEpi, kEpiRelu>(ep.act == SGF_ACT_RELU);
+    const int csz = out_f32 ? 4 : 2;
+    const int rsz = res_f32 ? 4 : 2;
 
     // folded-LayerNorm row statistics of this thread's row: summed (fixed order -> deterministic) while the
     // main loop is still running
-    bool rn_on = false;
     float rn_mean = 0.f, rn_rstd = 1.f;
-    if constexpr (!kConv) {
-      if (ep.rownorm_stats) {
-        rn_on = true;
-        const int mrow = min(m0 + quarter * 32 + lane, shp.M - 1);
-        const float4* sp = reinterpret_cast<const float4*>(ep.rownorm_stats) +
-                           (static_cast<int64_t>(z) * shp.M + mrow) * (ep.rownorm_parts / 2);
-        float s0 = 0.f, s1 = 0.f;
-        for (int q = 0; q < ep.rownorm_parts / 2; ++q) {
-          const float4 t = __ldg(sp + q);
-          s0 += t.x; s1 += t.y; s0 += t.z; s1 += t.w;
-        }
-        rn_mean = s0 * ep.rownorm_inv_dim;
-        rn_rstd = rsqrtf(fmaxf(s1 * ep.rownorm_inv_dim - rn_mean * rn_mean, 0.f) + 1e-5f);
+    const bool rn_on = !kConv && epi_has<kEpi, kEpiRowNorm>(ep.rownorm_stats != nullptr);
+    if (rn_on) {
+      const int mrow = min(m0 + quarter * 32 + lane, shp.M - 1);
+      const float4* sp = reinterpret_cast<const float4*>(ep.rownorm_stats) +
+                         (static_cast<int64_t>(z) * shp.M + mrow) * (ep.rownorm_parts / 2);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+      for (int q = 0; q < ep.rownorm_parts / 2; ++q) {
+        const float4 t = __ldg(sp + q);
+        s0 += t.x; s1 += t.y; s0 += t.z; s1 += t.w;
       }
+      rn_mean = s0 * ep.rownorm_inv_dim;
+      rn_rstd = rsqrtf(fmaxf(s1 * ep.rownorm_inv_dim - rn_mean * rn_mean, 0.f) + 1e-5f);
     }
 
     mbar_wait(accum_bar, 0);
@@ -206,43 +227,51 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-      if (rn_on) {  // folded LayerNorm of the A operand: v = rstd * (v - mean * u[n])
+      const bool full32 = kRt ? (c0 + 32 <= shp.N && (shp.N % 4) == 0) : true;
+      if (full32) {
+        if (rn_on) {  // folded LayerNorm of the A operand: v = rstd * (v - mean * u[n])
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float u = (c0 + j < shp.N) ? __ldg(ep.rownorm_u + c0 + j) : 0.f;
-          v[j] = rn_rstd * (v[j] - rn_mean * u);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 u4 = __ldg(reinterpret_cast<const float4*>(ep.rownorm_u + c0 + j));
+            v[j] = rn_rstd * (v[j] - rn_mean * u4.x); v[j + 1] = rn_rstd * (v[j + 1] - rn_mean * u4.y);
+            v[j + 2] = rn_rstd * (v[j + 2] - rn_mean * u4.z); v[j + 3] = rn_rstd * (v[j + 3] - rn_mean * u4.w);
+          }
         }
-      }
-      if (c0 + 32 <= shp.N && (shp.N % 4) == 0) {
-        if (ep.col_scale) {
+        if (epi_has<kEpi, kEpiScale>(ep.col_scale != nullptr)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + c0 + j));
             v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
           }
         }
-        if (ep.col_bias) {
+        if (epi_has<kEpi, kEpiBias>(ep.col_bias != nullptr)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.col_bias + c0 + j));
             v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
           }
         }
-      } else {
-#pragma unroll
+      } else if constexpr (kRt) {
+#pragma unroll 4
         for (int j = 0; j < 32; ++j) {
           if (c0 + j < shp.N) {
+            if (rn_on) v[j] = rn_rstd * (v[j] - rn_mean * ep.rownorm_u[c0 + j]);
             if (ep.col_scale) v[j] *= ep.col_scale[c0 + j];
             if (ep.col_bias) v[j] += ep.col_bias[c0 + j];
           }
         }
       }
-      if (ep.alpha_cols > c0) {
+      if (epi_has<kEpi, kEpiAlpha>(ep.alpha_cols > 0)) {
+        if (ep.alpha_cols >= c0 + 32) {  // warp-uniform: the whole chunk is scaled (q columns)
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < ep.alpha_cols) v[j] *= ep.alpha;
+          for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+        } else if (ep.alpha_cols > c0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < ep.alpha_cols) v[j] *= ep.alpha;
+        }
       }
-      if (ep.act == SGF_ACT_GELU) {
+      if (epi_has<kEpi, kEpiGelu>(ep.act == SGF_ACT_GELU)) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
       }
@@ -271,86 +300,84 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
       out_rows[it] = (row_ok && c < shp.N) ? static_cast<int>(out_row) : -1;
       res_lo[it] = make_uint4(0, 0, 0, 0);
       res_hi[it] = make_uint4(0, 0, 0, 0);
-      if (ep.residual && vec_ok && out_rows[it] >= 0) {
+      if ((res_f32 || res_b16) && vec_ok && out_rows[it] >= 0) {
         const uint8_t* rptr = reinterpret_cast<const uint8_t*>(ep.residual) +
                               (static_cast<int64_t>(z) * ep.r_batch_stride + out_row * ep.ldr + c) * rsz;
         res_lo[it] = *reinterpret_cast<const uint4*>(rptr);
-        if (ep.r_dtype == SGF_F32) res_hi[it] = *reinterpret_cast<const uint4*>(rptr + 16);
+        if (res_f32) res_hi[it] = *reinterpret_cast<const uint4*>(rptr + 16);
       }
     }
-
     // ---- phase 2b ----
     const int scol = (lane % kLanesPerRow) * 8;  // column inside this warp's staging tile
+    const bool want_stats = (kCols == 64) && epi_has<kEpi, kEpiRowStats>(ep.rowstats_out != nullptr);
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
       float st_sum = 0.f, st_sq = 0.f;
       if (out_rows[it] >= 0) {
-      const int rl = it * kRowsPerIter + lane / kLanesPerRow;
-      float v[8];
-      {
-        const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + scol * 4);
-        const float4 b4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + scol * 4 + 16);
-        v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
-      }
-      uint8_t* cptr = reinterpret_cast<uint8_t*>(ep.c) +
-                      (static_cast<int64_t>(z) * ep.c_batch_stride + static_cast<int64_t>(out_rows[it]) * ep.ldc + c) * csz;
-      if (vec_ok) {
-        if (ep.residual) {
-          if (ep.r_dtype == SGF_F32) {
+        const int rl = it * kRowsPerIter + lane / kLanesPerRow;
+        float v[8];
+        {
+          const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + scol * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + scol * 4 + 16);
+          v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+        }
+        uint8_t* cptr = reinterpret_cast<uint8_t*>(ep.c) +
+                        (static_cast<int64_t>(z) * ep.c_batch_stride + static_cast<int64_t>(out_rows[it]) * ep.ldc + c) * csz;
+        if (vec_ok) {
+          if (res_f32) {
             v[0] += __uint_as_float(res_lo[it].x); v[1] += __uint_as_float(res_lo[it].y);
             v[2] += __uint_as_float(res_lo[it].z); v[3] += __uint_as_float(res_lo[it].w);
             v[4] += __uint_as_float(res_hi[it].x); v[5] += __uint_as_float(res_hi[it].y);
             v[6] += __uint_as_float(res_hi[it].z); v[7] += __uint_as_float(res_hi[it].w);
-          } else {
+          } else if (res_b16) {
             const float2 a = unpack_bf16x2(res_lo[it].x), b2 = unpack_bf16x2(res_lo[it].y),
                          c2 = unpack_bf16x2(res_lo[it].z), d = unpack_bf16x2(res_lo[it].w);
             v[0] += a.x; v[1] += a.y; v[2] += b2.x; v[3] += b2.y; v[4] += c2.x; v[5] += c2.y; v[6] += d.x; v[7] += d.y;
           }
-        }
-        if (ep.act == SGF_ACT_RELU) {
+          if (do_relu) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
-        }
-        if (ep.c_dtype == SGF_F32) {
-          *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(cptr + 16) = make_float4(v[4], v[5], v[6], v[7]);
-        } else {
-          uint4 o;
-          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(cptr) = o;
-          if (ep.rowstats_out) {  // statistics of exactly what was stored
-            const float2 a = unpack_bf16x2(o.x), b2 = unpack_bf16x2(o.y), c2 = unpack_bf16x2(o.z), d = unpack_bf16x2(o.w);
-            v[0] = a.x; v[1] = a.y; v[2] = b2.x; v[3] = b2.y; v[4] = c2.x; v[5] = c2.y; v[6] = d.x; v[7] = d.y;
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+          }
+          if (out_f32) {
+            *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(cptr + 16) = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(cptr) = o;
+            if (want_stats) {  // statistics of exactly what was stored
+              const float2 a = unpack_bf16x2(o.x), b2 = unpack_bf16x2(o.y), c2 = unpack_bf16x2(o.z), d = unpack_bf16x2(o.w);
+              const float w[8] = {a.x, a.y, b2.x, b2.y, c2.x, c2.y, d.x, d.y};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              st_sum += v[j];
-              st_sq = fmaf(v[j], v[j], st_sq);
+              for (int j = 0; j < 8; ++j) {
+                st_sum += w[j];
+                st_sq = fmaf(w[j], w[j], st_sq);
+              }
+            }
+          }
+        } else if constexpr (kRt) {
+          const uint8_t* rptr = ep.residual ? reinterpret_cast<const uint8_t*>(ep.residual) +
+                                                  (static_cast<int64_t>(z) * ep.r_batch_stride +
+                                                   static_cast<int64_t>(out_rows[it]) * ep.ldr + c) * rsz
+                                            : nullptr;
+#pragma unroll 1
+          for (int j = 0; j < 8; ++j) {
+            if (c + j < shp.N) {
+              float t = v[j];
+              if (rptr)
+                t += res_f32 ? reinterpret_cast<const float*>(rptr)[j]
+                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rptr)[j]);
+              if (do_relu) t = fmaxf(t, 0.0f);
+              if (out_f32)
+                reinterpret_cast<float*>(cptr)[j] = t;
+              else
+                reinterpret_cast<__nv_bfloat16*>(cptr)[j] = __float2bfloat16_rn(t);
             }
           }
         }
-      } else {
-        const uint8_t* rptr = ep.residual ? reinterpret_cast<const uint8_t*>(ep.residual) +
-                                                (static_cast<int64_t>(z) * ep.r_batch_stride + static_cast<int64_t>(out_rows[it]) * ep.ldr + c) * rsz
-                                          : nullptr;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (c + j < shp.N) {
-            float t = v[j];
-            if (rptr)
-              t += (ep.r_dtype == SGF_F32) ? reinterpret_cast<const float*>(rptr)[j]
-                                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rptr)[j]);
-            if (ep.act == SGF_ACT_RELU) t = fmaxf(t, 0.0f);
-            if (ep.c_dtype == SGF_F32)
-              reinterpret_cast<float*>(cptr)[j] = t;
-            else
-              reinterpret_cast<__nv_bfloat16*>(cptr)[j] = __float2bfloat16_rn(t);
-          }
-        }
-      }
       }  // valid row
-      if constexpr (kCols == 64)
-      if (ep.rowstats_out) {  // warp-uniform: reduce over the lanes that share a row, one slot per row segment
+      if (want_stats) {  // warp-uniform: reduce over the lanes that share a row, one slot per row segment
 #pragma unroll
         for (int o = kLanesPerRow / 2; o > 0; o >>= 1) {
           st_sum += __shfl_xor_sync(0xffffffffu, st_sum, o);
@@ -383,10 +410,10 @@ static constexpr int gemm_smem_bytes() {
   return kStages * GemmSmem<BN>::kStageBytes + (2 * kStages + 1) * 8 + 16 + 1024;
 }
 
-template <int BN, int kStages, bool kConv>
+template <int BN, int kStages, bool kConv, int kEpi>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
                        dim3 grid, cudaStream_t st) {
-  auto kern = gemm_tcgen05_kernel<BN, kStages, kConv>;
+  auto kern = gemm_tcgen05_kernel<BN, kStages, kConv, kEpi>;
   constexpr int smem = gemm_smem_bytes<BN, kStages>();
   static bool configured = false;
   if (!configured) {
@@ -396,6 +423,51 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   SGF_CHECK_CUDA(launch_pdl(kern, grid, dim3(gemm_threads<BN>()), smem, st, tmA, tmB, shp, ep));
   count_launch();
   return SGF_OK;
+}
+
+// feature mask of a call; specialised kernels exist for the combinations the segofa path uses
+static int epilogue_mask(const GemmEpilogue& ep) {
+  int m = 0;
+  if (ep.col_scale) m |= kEpiScale;
+  if (ep.col_bias) m |= kEpiBias;
+  if (ep.alpha_cols > 0) m |= kEpiAlpha;
+  if (ep.act == SGF_ACT_GELU) m |= kEpiGelu;
+  if (ep.act == SGF_ACT_RELU) m |= kEpiRelu;
+  if (ep.residual) m |= (ep.r_dtype == SGF_F32 ? kEpiResF32 : kEpiResBf16);
+  if (ep.c_dtype == SGF_F32) m |= kEpiOutF32;
+  if (ep.rowstats_out) m |= kEpiRowStats;
+  if (ep.rownorm_stats) m |= kEpiRowNorm;
+  return m;
+}
+
+#define SGF_EPI_CASE(MASK)                                                                              \
+  case (MASK):                                                                                          \
+    return launch_gemm<BN, kStages, kConv, (MASK)>(tmA, tmB, shp, ep, grid, st);
+
+template <int BN, int kStages, bool kConv>
+static int dispatch_epilogue(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
+                             dim3 grid, cudaStream_t st) {
+  if (shp.N % 32 == 0) {
+    switch (epilogue_mask(ep)) {
+      SGF_EPI_CASE(kEpiScale | kEpiBias | kEpiRelu)                 // stem conv + BN + ReLU
+      SGF_EPI_CASE(kEpiScale | kEpiBias | kEpiRelu | kEpiResBf16)   // bottleneck conv3 + BN + residual + ReLU
+      SGF_EPI_CASE(kEpiScale | kEpiBias)                            // downsample conv + BN
+      default: break;
+    }
+    if constexpr (!kConv) {
+      switch (epilogue_mask(ep)) {
+        SGF_EPI_CASE(kEpiBias | kEpiAlpha)                          // fused QKV / cross q
+        SGF_EPI_CASE(kEpiBias | kEpiOutF32)                         // out_proj, image_proj
+        SGF_EPI_CASE(kEpiBias)                                      // cross k/v, position projections
+        SGF_EPI_CASE(kEpiBias | kEpiGelu | kEpiRowStats)            // fc1 (+ ffn_layernorm statistics)
+        SGF_EPI_CASE(kEpiBias | kEpiGelu)                           // fc1
+        SGF_EPI_CASE(kEpiBias | kEpiRowNorm | kEpiResF32 | kEpiOutF32)  // fc2 with folded ffn_layernorm
+        SGF_EPI_CASE(kEpiBias | kEpiResF32 | kEpiOutF32)            // fc2
+        default: break;
+      }
+    }
+  }
+  return launch_gemm<BN, kStages, kConv, kEpiRuntime>(tmA, tmB, shp, ep, grid, st);
 }
 
 static int check_epilogue_alignment(const GemmEpilogue& ep, int N) {
@@ -481,14 +553,10 @@ extern "C" int sgf_gemm_bf16(const sgf_gemm_args* a, void* stream) {
   }
   dim3 grid((a->N + bn - 1) / bn, m_tiles, a->batch);
   switch (bn) {
-    case 32: return launch_gemm<32, 4, false>(tmA, tmB, shp, ep, grid, st);
-    case 64: return g_force_stages == 8 ? launch_gemm<64, 8, false>(tmA, tmB, shp, ep, grid, st)
-                                        : launch_gemm<64, 4, false>(tmA, tmB, shp, ep, grid, st);
-    case 256: return launch_gemm<256, 4, false>(tmA, tmB, shp, ep, grid, st);
-    default:
-      if (g_force_stages == 6) return launch_gemm<128, 6, false>(tmA, tmB, shp, ep, grid, st);
-      if (g_force_stages == 4) return launch_gemm<128, 4, false>(tmA, tmB, shp, ep, grid, st);
-      return launch_gemm<128, 3, false>(tmA, tmB, shp, ep, grid, st);
+    case 32: return dispatch_epilogue<32, 4, false>(tmA, tmB, shp, ep, grid, st);
+    case 64: return dispatch_epilogue<64, 4, false>(tmA, tmB, shp, ep, grid, st);
+    case 256: return dispatch_epilogue<256, 4, false>(tmA, tmB, shp, ep, grid, st);
+    default: return dispatch_epilogue<128, 3, false>(tmA, tmB, shp, ep, grid, st);
   }
 }
 
@@ -543,8 +611,8 @@ extern "C" int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* a, void* stream) {
   }
   dim3 grid((a->cout + bn - 1) / bn, m_tiles, 1);
   switch (bn) {
-    case 32: return launch_gemm<32, 4, true>(tmA, tmB, shp, ep, grid, st);
-    case 64: return launch_gemm<64, 4, true>(tmA, tmB, shp, ep, grid, st);
-    default: return launch_gemm<128, 3, true>(tmA, tmB, shp, ep, grid, st);
+    case 32: return dispatch_epilogue<32, 4, true>(tmA, tmB, shp, ep, grid, st);
+    case 64: return dispatch_epilogue<64, 4, true>(tmA, tmB, shp, ep, grid, st);
+    default: return dispatch_epilogue<128, 3, true>(tmA, tmB, shp, ep, grid, st);
   }
 }

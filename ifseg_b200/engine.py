@@ -20,6 +20,7 @@ Reference semantics followed (file:line under /root/reference/models/segofa/):
   unify_transformer_layer.py:222-292, 431-581, unify_multihead_attention.py:327-523,
   resnet.py:215-229, frozen_bn.py:40-45.
 """
+import os
 from typing import Dict, Optional
 
 import torch
@@ -57,6 +58,8 @@ class SegOFAEngine:
         # exactly like the folded BN / fused QKV weights prepared below: it is derived once per shape and
         # dropped with the engine whenever the model's parameters may change (SegOFAModel.invalidate_engine).
         self.cache_position_bias = True
+        # ffn_layernorm folded into the fc1/fc2 epilogues (default) or run as a separate row kernel
+        self.fold_ffn_layernorm = os.environ.get("SGF_FOLD_FFN_LN", "1") != "0"
         self._bias_cache: Dict = {}
         with torch.no_grad():
             self._prepare(model)
@@ -111,7 +114,8 @@ class SegOFAEngine:
         w2f = (w2 * g.unsqueeze(0)).to(_BF16).contiguous()
         u = w2f.float().sum(dim=1).contiguous()
         c = (layer.fc2.bias.detach().float().to(self.device) + w2 @ b).contiguous()
-        return dict(w2f=w2f, u2=u, c2=c)
+        return dict(w2f=w2f, u2=u, c2=c, w2=self._b16(layer.fc2.weight), b2=self._f32(layer.fc2.bias),
+                    ln_ffn=self._ln(layer.ffn_layernorm))
 
     def _prepare(self, model):
         enc, dec, cfg = model.encoder, model.decoder, self.cfg
@@ -141,7 +145,7 @@ class SegOFAEngine:
         for l in enc.layers:
             self.enc_layers.append(dict(
                 attn=self._attn(l.self_attn), ln_self=self._ln(l.self_attn_layer_norm), ln_attn=self._ln(l.attn_ln),
-                ln_final=self._ln(l.final_layer_norm), ln_ffn=self._ln(l.ffn_layernorm),
+                ln_final=self._ln(l.final_layer_norm),
                 w1=self._b16(l.fc1.weight), b1=self._f32(l.fc1.bias), **self._ffn_fold(l)))
         self.ln_enc_out = self._ln(enc.layer_norm)
         self.enc_tok_rel = [self._f32(t.weight) for t in enc.token_rel_pos_table_list]
@@ -162,7 +166,7 @@ class SegOFAEngine:
                 attn=self._attn(l.self_attn), cross=self._attn(l.encoder_attn, cross=True),
                 ln_self=self._ln(l.self_attn_layer_norm), ln_self_attn=self._ln(l.self_attn_ln),
                 ln_enc_attn=self._ln(l.encoder_attn_layer_norm), ln_cross_attn=self._ln(l.cross_attn_ln),
-                ln_final=self._ln(l.final_layer_norm), ln_ffn=self._ln(l.ffn_layernorm),
+                ln_final=self._ln(l.final_layer_norm),
                 w1=self._b16(l.fc1.weight), b1=self._f32(l.fc1.bias), **self._ffn_fold(l)))
         # all decoder layers' cross-attention K/V projections of encoder_out as ONE GEMM (N = L*2D)
         self.w_cross_kv_all = torch.cat([d["cross"]["wkv"] for d in self.dec_layers], 0).contiguous()
@@ -305,6 +309,12 @@ class SegOFAEngine:
         """x <- x + fc2(ffn_layernorm(gelu(fc1(a)))) with the F-wide LayerNorm folded into the two GEMM
         epilogues: fc1 writes per-row (sum, sumsq) of each 64-column block of its bf16 output into `stats`,
         fc2 sums them in order and applies rstd * (acc - mean * u) + c."""
+        if not self.fold_ffn_layernorm:
+            f = ops.gemm(a, L["w1"], bias=L["b1"], act=ops.ACT_GELU, tag="fc1")
+            g = torch.empty_like(f)
+            ops.row_layernorm(f, ln2=L["ln_ffn"], out2=g)
+            ops.gemm(g, L["w2"], x, bias=L["b2"], residual=x, tag="fc2")
+            return
         f = ops.gemm(a, L["w1"], bias=L["b1"], act=ops.ACT_GELU, rowstats_out=stats, tag="fc1")
         ops.gemm(f, L["w2f"], x, bias=L["c2"], residual=x, rownorm=(stats, L["u2"], self.cfg.ffn_dim), tag="fc2")
 
