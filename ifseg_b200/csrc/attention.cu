@@ -242,9 +242,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
           if (dead) s[i] = -INFINITY;
         }
       }
-      float mx = s[0];
+      // 8 independent partial maxima (a single 64-deep fmax chain would serialise on FP latency)
+      float mxp[8];
 #pragma unroll
-      for (int i = 1; i < kKTile; ++i) mx = fmaxf(mx, s[i]);
+      for (int i = 0; i < 8; ++i) mxp[i] = s[i];
+#pragma unroll
+      for (int i = 8; i < kKTile; ++i) mxp[i & 7] = fmaxf(mxp[i & 7], s[i]);
+      const float mx = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])),
+                             fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7])));
       const float m_new = mx * kLog2e;
       if (j == 0) {
         m_used = (m_new == -INFINITY) ? 0.f : m_new;
@@ -272,13 +277,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
           }
         }
       }
-      float psum = 0.f;
+      float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < kKTile; ++i) {
         s[i] = fast_exp2(fmaf(s[i], kLog2e, -m_used));
-        psum += s[i];
+        ps[i & 7] += s[i];
       }
-      l_run += psum;
+      l_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
       // P (bf16) -> smem once P V(j-1) has finished reading the buffer
       mbar_wait(&bars->p_empty, (j & 1) ^ 1);
 #pragma unroll
