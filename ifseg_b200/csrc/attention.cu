@@ -13,7 +13,7 @@
 //                        more than 2^8), exp2, row sum; P(j) -> smem as bf16 in the swizzled K-major
 //                        layout the tensor core reads
 //   O += P(j) V(j)       tcgen05.mma M128 N64 K64 accumulating in TMEM (V tile is the MN-major B operand)
-// K/V tiles are triple-buffered TMA loads.  112 KB of shared memory and 256 TMEM columns per CTA
+// K/V tiles and P are double-buffered.  112 KB of shared memory and 256 TMEM columns per CTA
 // keep two CTAs per SM, so the eight softmax warps of an SM cover each other's waits.
 #include <string.h>
 
@@ -25,7 +25,7 @@ static constexpr int kQTile = 128;
 static constexpr int kKTile = 64;
 static constexpr int kHeadDim = 64;
 static constexpr int kAttnThreads = 160;
-static constexpr int kKvStages = 3;
+static constexpr int kKvStages = 2;
 static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr float kRescaleThreshold = 8.0f;  // log2 domain: probabilities stay below 2^8
 
@@ -46,15 +46,15 @@ struct AttnSmem {
   static constexpr int offQ = 0;
   static constexpr int offK = offQ + kQ;
   static constexpr int offV = offK + kKvStages * kKV;
-  static constexpr int offP = offV + kKvStages * kKV;
-  static constexpr int offBias = offP + kP;
+  static constexpr int offP = offV + kKvStages * kKV;  // two P buffers (ping-pong)
+  static constexpr int offBias = offP + 2 * kP;
   static constexpr int offBar = offBias + kBias;
   static constexpr int kTotal = offBar + 256;
 };
 
 struct AttnBars {
   uint64_t q_full, k_full[kKvStages], k_empty[kKvStages], v_full[kKvStages], v_empty[kKvStages];
-  uint64_t s_full[2], s_empty[2], p_full, p_empty, b_full, b_empty, o_done;
+  uint64_t s_full[2], s_empty[2], p_full[2], b_empty, o_done;  // s_full also carries the bias-tile bytes
   uint32_t tmem_slot;
 };
 static_assert(sizeof(AttnBars) <= 256, "barrier block");
@@ -87,12 +87,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       mbar_init(&bars->v_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->s_full[i], p.bias ? 2 : 1);  // tcgen05.commit of S(j) (+ the expect_tx arrive of bias(j))
       mbar_init(&bars->s_empty[i], 128);
     }
-    mbar_init(&bars->p_full, 128);
-    mbar_init(&bars->p_empty, 1);
-    mbar_init(&bars->b_full, 1);
+    // one "P published" barrier per P buffer: the softmax warps may run one tile ahead of the P V issue,
+    // so a single barrier could advance two phases before the control lane looks at it
+    mbar_init(&bars->p_full[0], 128);
+    mbar_init(&bars->p_full[1], 128);
     mbar_init(&bars->b_empty, 128);
     mbar_init(&bars->o_done, 1);
     fence_mbar_init();
@@ -129,10 +130,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         mbar_expect_tx(&bars->v_full[st], AttnSmem::kKV);
         tma_load_4d(smem + AttnSmem::offV + st * AttnSmem::kKV, &tmV, &bars->v_full[st], 0, h, t * kKTile, b);
       };
-      auto load_bias = [&](int t) {
-        mbar_expect_tx(&bars->b_full, AttnSmem::kBias);
-        tma_load_3d(smem + AttnSmem::offBias, &tmB, &bars->b_full, t * kKTile, q0, h);
-        tma_load_3d(smem + AttnSmem::offBias + AttnSmem::kBias / 2, &tmB, &bars->b_full, t * kKTile + 32, q0, h);
+      auto load_bias = [&](int t) {  // completes on the same barrier as S(t): one wait per tile for the softmax warps
+        mbar_expect_tx(&bars->s_full[t & 1], AttnSmem::kBias);
+        tma_load_3d(smem + AttnSmem::offBias, &tmB, &bars->s_full[t & 1], t * kKTile, q0, h);
+        tma_load_3d(smem + AttnSmem::offBias + AttnSmem::kBias / 2, &tmB, &bars->s_full[t & 1], t * kKTile + 32, q0, h);
       };
       mbar_expect_tx(&bars->q_full, AttnSmem::kQ);
       tma_load_4d(smem + AttnSmem::offQ, &tmQ, &bars->q_full, 0, h, q0, b);
@@ -140,7 +141,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       if (p.bias) load_bias(0);
       for (int t = 0; t < kKvStages && t < n_kt; ++t) load_v(t);
       const uint64_t dq = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offQ));
-      const uint64_t dp = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offP));
 
 #pragma unroll 1
       for (int j = 0; j <= n_kt; ++j) {
@@ -157,15 +157,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
             umma_f16(tmem_s + (j & 1) * 64, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
           umma_commit(&bars->s_full[j & 1]);
           umma_commit(&bars->k_empty[st]);
-          // K(j-1)'s stage is free (S(j-1) retired long ago): prefetch K(j+2) into it
-          if (j >= 1 && j + 2 < n_kt) {
+          // K(j-1)'s stage is free (S(j-1) retired long ago): prefetch K(j+1) into it
+          if (j >= 1 && j + 1 < n_kt) {
             mbar_wait(&bars->k_empty[(j - 1) % kKvStages], ((j - 1) / kKvStages) & 1);
-            load_k(j + 2);
+            load_k(j + 1);
           }
-          // V(j-2)'s stage is free once PV(j-2) retired: prefetch V(j+1) into it
-          if (j >= 2 && j + 1 < n_kt) {
+          // V(j-2)'s stage is free once PV(j-2) retired: prefetch V(j) into it
+          if (j >= 2) {
             mbar_wait(&bars->v_empty[(j - 2) % kKvStages], ((j - 2) / kKvStages) & 1);
-            load_v(j + 1);
+            load_v(j);
           }
         }
         if (j >= 1) {
@@ -173,13 +173,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
           const int t = j - 1;
           const int st = t % kKvStages;
           mbar_wait(&bars->v_full[st], (t / kKvStages) & 1);
-          mbar_wait(&bars->p_full, t & 1);
+          mbar_wait(&bars->p_full[t & 1], (t >> 1) & 1);
           tc_fence_after();
           const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offV + st * AttnSmem::kKV));
+          const uint64_t dp = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offP + (t & 1) * AttnSmem::kP));
 #pragma unroll
           for (int k = 0; k < kKTile / 16; ++k)  // V: 16 key rows = 2048 B per K step -> +128 in the address field
             umma_f16(tmem_o, dp + 2 * k, dv + 128 * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
-          umma_commit(&bars->p_empty);
           umma_commit(&bars->v_empty[st]);
           umma_commit(&bars->o_done);
         }
@@ -195,43 +195,53 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
     const uint8_t* bias_row = smem + AttnSmem::offBias + tid * 128;  // this thread's row inside each bias box
     const uint8_t* kpm_row = p.kpm ? p.kpm + static_cast<int64_t>(b) * p.Tk : nullptr;
-    uint8_t* p_row = smem + AttnSmem::offP + tid * 128;
+    uint8_t* p_row0 = smem + AttnSmem::offP + tid * 128;
     float m_used = 0.f;  // log2-domain reference max the probabilities are expressed against
     float l_run = 0.f;
 
 #pragma unroll 1
     for (int j = 0; j < n_kt; ++j) {
       const int k0 = j * kKTile;
-      mbar_wait(&bars->s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(&bars->s_full[j & 1], (j >> 1) & 1);  // S(j) retired and bias(j) landed (P V(j-2) retired too)
       tc_fence_after();
       float s[kKTile];
       {
         uint32_t r0[32], r1[32];
         tmem_ld_32x32(tmem_s + (j & 1) * 64 + lane_addr, r0);
         tmem_ld_32x32(tmem_s + (j & 1) * 64 + lane_addr + 32, r1);
-        tmem_ld_wait();
+        if (p.bias) {  // the swizzled smem reads of the bias tile overlap the TMEM load latency
+          float4 bb[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          s[i] = __uint_as_float(r0[i]);
-          s[32 + i] = __uint_as_float(r1[i]);
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              bb[half * 8 + c] =
+                  *reinterpret_cast<const float4*>(bias_row + half * (AttnSmem::kBias / 2) + ((c ^ (tid & 7)) << 4));
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            s[4 * c + 0] = __uint_as_float(r0[4 * c + 0]) + bb[c].x;
+            s[4 * c + 1] = __uint_as_float(r0[4 * c + 1]) + bb[c].y;
+            s[4 * c + 2] = __uint_as_float(r0[4 * c + 2]) + bb[c].z;
+            s[4 * c + 3] = __uint_as_float(r0[4 * c + 3]) + bb[c].w;
+            s[32 + 4 * c + 0] = __uint_as_float(r1[4 * c + 0]) + bb[8 + c].x;
+            s[32 + 4 * c + 1] = __uint_as_float(r1[4 * c + 1]) + bb[8 + c].y;
+            s[32 + 4 * c + 2] = __uint_as_float(r1[4 * c + 2]) + bb[8 + c].z;
+            s[32 + 4 * c + 3] = __uint_as_float(r1[4 * c + 3]) + bb[8 + c].w;
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            s[i] = __uint_as_float(r0[i]);
+            s[32 + i] = __uint_as_float(r1[i]);
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(&bars->s_empty[j & 1]);
-      if (p.bias) {  // bias tile staged by TMA (128B swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7))
-        mbar_wait(&bars->b_full, j & 1);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 b4 =
-                *reinterpret_cast<const float4*>(bias_row + half * (AttnSmem::kBias / 2) + ((c ^ (tid & 7)) << 4));
-            const int i = half * 32 + c * 4;
-            s[i] += b4.x; s[i + 1] += b4.y; s[i + 2] += b4.z; s[i + 3] += b4.w;
-          }
-        }
-        mbar_arrive(&bars->b_empty);
-      }
+      if (p.bias) mbar_arrive(&bars->b_empty);
       const bool need_mask = (k0 + kKTile > p.Tk) || (p.causal && (k0 + kKTile - 1 > q0)) || (kpm_row != nullptr);
       if (need_mask) {
 #pragma unroll
@@ -284,8 +294,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         ps[i & 7] += s[i];
       }
       l_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
-      // P (bf16) -> smem once P V(j-1) has finished reading the buffer
-      mbar_wait(&bars->p_empty, (j & 1) ^ 1);
+      // P (bf16) -> smem buffer j&1: its previous reader P V(j-2) retired before S(j) did (in-order tensor pipe)
+      uint8_t* p_row = p_row0 + (j & 1) * AttnSmem::kP;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         uint4 u;
@@ -296,7 +306,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         *reinterpret_cast<uint4*>(p_row + ((c ^ (tid & 7)) << 4)) = u;
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&bars->p_full);
+      mbar_arrive(&bars->p_full[j & 1]);
     }
 
     if (n_kt > 0) {

@@ -334,3 +334,28 @@ def test_gemm_folded_layernorm(ops):
                    out_dtype=torch.float32)
     ref = F.layer_norm(ff, (Fd,), gam, bet, 1e-5) @ w2.t() + b2 + res
     assert _rel(out, ref) < 3e-3, _rel(out, ref)
+
+
+def test_attention_full_size_repeatable(ops):
+    """BASELINE cfg-2 encoder shape (B=8, H=12, T=936, bias): many co-resident CTAs exercise the
+    mbarrier hand-offs under load; results must be identical across launches and match fp32."""
+    g = torch.Generator(device="cuda").manual_seed(2024)
+    B, H, T, dh = 8, 12, 936, 64
+    D = H * dh
+    qkv = (torch.randn(B, T, 3 * D, device="cuda", generator=g) * 0.5).bfloat16()
+    bias = torch.zeros(H, T, 960, device="cuda")
+    bias[:, :, :T] = torch.randn(H, T, T, device="cuda", generator=g)
+    hs = torch.rand(H, device="cuda", generator=g) + 0.5
+    outs = []
+    for _ in range(6):
+        out = torch.empty(B, T, D, device="cuda", dtype=torch.bfloat16)
+        ops.attention(qkv, qkv[:, :, D:], qkv[:, :, 2 * D:], out, B=B, H=H, Tq=T, Tk=T, q_strides=(3 * D, T * 3 * D),
+                      k_strides=(3 * D, T * 3 * D), v_strides=(3 * D, T * 3 * D), o_strides=(D, T * D), bias=bias,
+                      head_scale=hs)
+        outs.append(out)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    q, k, v = (t.reshape(B, T, H, dh) for t in qkv.split(D, dim=-1))
+    ref = _attn_ref(q[:2], k[:2], v[:2], bias, False, None, hs).reshape(2, T, D)
+    assert _rel(outs[0][:2], ref) < 8e-3
