@@ -12,6 +12,7 @@
 // zero fill is the convolution padding, so no im2col matrix ever exists.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -71,13 +72,247 @@ SGF_DEVICE bool epi_has(bool runtime_value) {
   else return (kEpi & kFlag) != 0;
 }
 
+// Epilogue shared by the 1-CTA and the 2-CTA kernels.  Executed by the kEpiWarps epilogue warps
+// (warp index 2..): `stage_bytes_avail` bytes at `smem` (the retired pipeline stages) hold the staging tiles.
+template <int BN, int kEpiWarps, int kStageBytesAvail, bool kConv, int kEpi>
+SGF_DEVICE void gemm_epilogue(uint8_t* smem, uint32_t tmem_base, uint64_t* accum_bar, const GemmShape& shp,
+                              const GemmEpilogue& ep, int m0, int n0, int z, int img, int h0, int w0, int warp,
+                              int lane) {
+  constexpr bool kRt = (kEpi & kEpiRuntime) != 0;
+  // ------------------------------ epilogue warps ------------------------------
+  // kEpiWarps warps; warp (quarter, part) owns TMEM lanes [32*quarter, +32) and columns
+  // [part*kCols, +kCols) of the tile.
+  // Phase 1: TMEM -> registers (thread = row), column-wise ops (row-norm, scale, bias, q-scale, GELU),
+  //          row parked in a per-warp smem staging tile (the pipeline stages are dead by then).
+  // Phase 2: the tile is re-read with lanes along the columns, so the residual add and the output
+  //          stores are fully coalesced 16/32-byte-per-lane row segments.
+  constexpr int kSplit = kEpiWarps / 4;
+  constexpr int kCols = BN / kSplit;
+  constexpr int kRowPitch = kCols * 4 + 16;  // bytes; +16 keeps the thread-per-row float4 writes conflict-free
+  constexpr int kLanesPerRow = kCols / 8;
+  constexpr int kRowsPerIter = 32 / kLanesPerRow;
+  constexpr int kIters = 32 / kRowsPerIter;
+  static_assert(kEpiWarps * 32 * kRowPitch <= kStageBytesAvail, "epilogue staging must fit in the pipeline smem");
+  const int ew = warp - 2;
+  const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+  const int part = ew >> 2;
+  uint8_t* stage = smem + ew * (32 * kRowPitch);
+  const int col = part * kCols + (lane % kLanesPerRow) * 8;
+  const int c = n0 + col;
+  // specialised kernels are only dispatched for N % 32 == 0: a lane's 8 columns are all in or all out
+  const bool vec_ok = kRt ? ((shp.N % 8) == 0 && (c + 8 <= shp.N)) : (c < shp.N);
+  const bool out_f32 = epi_has<kEpi, kEpiOutF32>(ep.c_dtype == SGF_F32);
+  const bool res_f32 = epi_has<kEpi, kEpiResF32>(ep.residual && ep.r_dtype == SGF_F32);
+  const bool res_b16 = epi_has<kEpi, kEpiResBf16>(ep.residual && ep.r_dtype != SGF_F32);
+  const bool do_relu = epi_has<kEpi, kEpiRelu>(ep.act == SGF_ACT_RELU);
+  const int csz = out_f32 ? 4 : 2;
+  const int rsz = res_f32 ? 4 : 2;
+
+  // folded-LayerNorm row statistics of this thread's row: summed (fixed order -> deterministic) while the
+  // main loop is still running
+  float rn_mean = 0.f, rn_rstd = 1.f;
+  const bool rn_on = !kConv && epi_has<kEpi, kEpiRowNorm>(ep.rownorm_stats != nullptr);
+  if (rn_on) {
+    const int mrow = min(m0 + quarter * 32 + lane, shp.M - 1);
+    const float4* sp = reinterpret_cast<const float4*>(ep.rownorm_stats) +
+                       (static_cast<int64_t>(z) * shp.M + mrow) * (ep.rownorm_parts / 2);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+    for (int q = 0; q < ep.rownorm_parts / 2; ++q) {
+      const float4 t = __ldg(sp + q);
+      s0 += t.x; s1 += t.y; s0 += t.z; s1 += t.w;
+    }
+    rn_mean = s0 * ep.rownorm_inv_dim;
+    rn_rstd = rsqrtf(fmaxf(s1 * ep.rownorm_inv_dim - rn_mean * rn_mean, 0.f) + 1e-5f);
+  }
+
+  mbar_wait(accum_bar, 0);
+  tc_fence_after();
+
+  // ---- phase 1 ----
+#pragma unroll 1
+  for (int ch = 0; ch < kCols / 32; ++ch) {
+    const int c0 = n0 + part * kCols + ch * 32;
+    if (c0 >= shp.N) break;  // warp-uniform
+    uint32_t acc[32];
+    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + part * kCols + ch * 32, acc);
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+    const bool full32 = kRt ? (c0 + 32 <= shp.N && (shp.N % 4) == 0) : true;
+    if (full32) {
+      if (rn_on) {  // folded LayerNorm of the A operand: v = rstd * (v - mean * u[n])
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 u4 = __ldg(reinterpret_cast<const float4*>(ep.rownorm_u + c0 + j));
+          v[j] = rn_rstd * (v[j] - rn_mean * u4.x); v[j + 1] = rn_rstd * (v[j + 1] - rn_mean * u4.y);
+          v[j + 2] = rn_rstd * (v[j + 2] - rn_mean * u4.z); v[j + 3] = rn_rstd * (v[j + 3] - rn_mean * u4.w);
+        }
+      }
+      if (epi_has<kEpi, kEpiScale>(ep.col_scale != nullptr)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + c0 + j));
+          v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+        }
+      }
+      if (epi_has<kEpi, kEpiBias>(ep.col_bias != nullptr)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.col_bias + c0 + j));
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+      }
+    } else if constexpr (kRt) {
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        if (c0 + j < shp.N) {
+          if (rn_on) v[j] = rn_rstd * (v[j] - rn_mean * ep.rownorm_u[c0 + j]);
+          if (ep.col_scale) v[j] *= ep.col_scale[c0 + j];
+          if (ep.col_bias) v[j] += ep.col_bias[c0 + j];
+        }
+      }
+    }
+    if (epi_has<kEpi, kEpiAlpha>(ep.alpha_cols > 0)) {
+      if (ep.alpha_cols >= c0 + 32) {  // warp-uniform: the whole chunk is scaled (q columns)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+      } else if (ep.alpha_cols > c0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < ep.alpha_cols) v[j] *= ep.alpha;
+      }
+    }
+    if (epi_has<kEpi, kEpiGelu>(ep.act == SGF_ACT_GELU)) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    }
+    float4* dst = reinterpret_cast<float4*>(stage + lane * kRowPitch + ch * 128);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  __syncwarp();
+
+  // ---- phase 2a: row map + all residual loads of this warp issued back to back (one exposed latency) ----
+  int out_rows[kIters];
+  uint4 res_lo[kIters], res_hi[kIters];
+#pragma unroll
+  for (int it = 0; it < kIters; ++it) {
+    const int r = quarter * 32 + it * kRowsPerIter + lane / kLanesPerRow;
+    int64_t out_row;
+    bool row_ok;
+    if constexpr (kConv) {
+      const int hh = h0 + r / shp.bw, ww = w0 + r % shp.bw;
+      row_ok = (hh < shp.H) && (ww < shp.W);
+      out_row = (static_cast<int64_t>(img) * shp.H + hh) * shp.W + ww;
+    } else {
+      row_ok = (m0 + r) < shp.M;
+      out_row = m0 + r;
+    }
+    out_rows[it] = (row_ok && c < shp.N) ? static_cast<int>(out_row) : -1;
+    res_lo[it] = make_uint4(0, 0, 0, 0);
+    res_hi[it] = make_uint4(0, 0, 0, 0);
+    if ((res_f32 || res_b16) && vec_ok && out_rows[it] >= 0) {
+      const uint8_t* rptr = reinterpret_cast<const uint8_t*>(ep.residual) +
+                            (static_cast<int64_t>(z) * ep.r_batch_stride + out_row * ep.ldr + c) * rsz;
+      res_lo[it] = *reinterpret_cast<const uint4*>(rptr);
+      if (res_f32) res_hi[it] = *reinterpret_cast<const uint4*>(rptr + 16);
+    }
+  }
+  // ---- phase 2b ----
+  const int scol = (lane % kLanesPerRow) * 8;  // column inside this warp's staging tile
+  const bool want_stats = epi_has<kEpi, kEpiRowStats>(ep.rowstats_out != nullptr);
+#pragma unroll
+  for (int it = 0; it < kIters; ++it) {
+    float st_sum = 0.f, st_sq = 0.f;
+    if (out_rows[it] >= 0) {
+      const int rl = it * kRowsPerIter + lane / kLanesPerRow;
+      float v[8];
+      {
+        const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + scol * 4);
+        const float4 b4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + scol * 4 + 16);
+        v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+      }
+      uint8_t* cptr = reinterpret_cast<uint8_t*>(ep.c) +
+                      (static_cast<int64_t>(z) * ep.c_batch_stride + static_cast<int64_t>(out_rows[it]) * ep.ldc + c) * csz;
+      if (vec_ok) {
+        if (res_f32) {
+          v[0] += __uint_as_float(res_lo[it].x); v[1] += __uint_as_float(res_lo[it].y);
+          v[2] += __uint_as_float(res_lo[it].z); v[3] += __uint_as_float(res_lo[it].w);
+          v[4] += __uint_as_float(res_hi[it].x); v[5] += __uint_as_float(res_hi[it].y);
+          v[6] += __uint_as_float(res_hi[it].z); v[7] += __uint_as_float(res_hi[it].w);
+        } else if (res_b16) {
+          const float2 a = unpack_bf16x2(res_lo[it].x), b2 = unpack_bf16x2(res_lo[it].y),
+                       c2 = unpack_bf16x2(res_lo[it].z), d = unpack_bf16x2(res_lo[it].w);
+          v[0] += a.x; v[1] += a.y; v[2] += b2.x; v[3] += b2.y; v[4] += c2.x; v[5] += c2.y; v[6] += d.x; v[7] += d.y;
+        }
+        if (do_relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (out_f32) {
+          *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(cptr + 16) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(cptr) = o;
+          if (want_stats) {  // statistics of exactly what was stored
+            const float2 a = unpack_bf16x2(o.x), b2 = unpack_bf16x2(o.y), c2 = unpack_bf16x2(o.z), d = unpack_bf16x2(o.w);
+            const float w[8] = {a.x, a.y, b2.x, b2.y, c2.x, c2.y, d.x, d.y};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              st_sum += w[j];
+              st_sq = fmaf(w[j], w[j], st_sq);
+            }
+          }
+        }
+      } else if constexpr (kRt) {
+        const uint8_t* rptr = ep.residual ? reinterpret_cast<const uint8_t*>(ep.residual) +
+                                                (static_cast<int64_t>(z) * ep.r_batch_stride +
+                                                 static_cast<int64_t>(out_rows[it]) * ep.ldr + c) * rsz
+                                          : nullptr;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          if (c + j < shp.N) {
+            float t = v[j];
+            if (rptr)
+              t += res_f32 ? reinterpret_cast<const float*>(rptr)[j]
+                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rptr)[j]);
+            if (do_relu) t = fmaxf(t, 0.0f);
+            if (out_f32)
+              reinterpret_cast<float*>(cptr)[j] = t;
+            else
+              reinterpret_cast<__nv_bfloat16*>(cptr)[j] = __float2bfloat16_rn(t);
+          }
+        }
+      }
+    }  // valid row
+    if (want_stats) {  // warp-uniform: reduce over the lanes that share a row, one slot per row segment
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {  // 8 lanes = one 64-column block of a row
+        st_sum += __shfl_xor_sync(0xffffffffu, st_sum, o);
+        st_sq += __shfl_xor_sync(0xffffffffu, st_sq, o);
+      }
+      if ((lane & 7) == 0 && out_rows[it] >= 0) {
+        // deterministic: one (sum, sumsq) slot per 64-column block of the row, summed in order by the consumer
+        const int nparts = (shp.N + 63) / 64;
+        float2* sp = reinterpret_cast<float2*>(ep.rowstats_out) +
+                     (static_cast<int64_t>(z) * shp.M + out_rows[it]) * nparts + c / 64;
+        *sp = make_float2(st_sum, st_sq);
+      }
+    }
+  }
+}
+
 template <int BN, int kStages, bool kConv, int kEpi>
 __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const GemmShape shp, const GemmEpilogue ep) {
   using S = GemmSmem<BN>;
   constexpr int kEpiWarps = gemm_epi_warps<BN>();
-  constexpr bool kRt = (kEpi & kEpiRuntime) != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16B aligned: round up to the 1024B the 128B swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -166,232 +401,8 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
       umma_commit(accum_bar);  // accumulator complete
     }
   } else {
-    // ------------------------------ epilogue warps ------------------------------
-    // kEpiWarps warps; warp (quarter, part) owns TMEM lanes [32*quarter, +32) and columns
-    // [part*kCols, +kCols) of the tile.
-    // Phase 1: TMEM -> registers (thread = row), column-wise ops (row-norm, scale, bias, q-scale, GELU),
-    //          row parked in a per-warp smem staging tile (the pipeline stages are dead by then).
-    // Phase 2: the tile is re-read with lanes along the columns, so the residual add and the output
-    //          stores are fully coalesced 16/32-byte-per-lane row segments.
-    constexpr int kSplit = kEpiWarps / 4;
-    constexpr int kCols = BN / kSplit;
-    constexpr int kRowPitch = kCols * 4 + 16;  // bytes; +16 keeps the thread-per-row float4 writes conflict-free
-    constexpr int kLanesPerRow = kCols / 8;
-    constexpr int kRowsPerIter = 32 / kLanesPerRow;
-    constexpr int kIters = 32 / kRowsPerIter;
-    static_assert(kEpiWarps * 32 * kRowPitch <= kStages * S::kStageBytes, "epilogue staging must fit in the pipeline smem");
-    const int ew = warp - 2;
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int part = ew >> 2;
-    uint8_t* stage = smem + ew * (32 * kRowPitch);
-    const int col = part * kCols + (lane % kLanesPerRow) * 8;
-    const int c = n0 + col;
-    // specialised kernels are only dispatched for N % 32 == 0: a lane's 8 columns are all in or all out
-    const bool vec_ok = kRt ? ((shp.N % 8) == 0 && (c + 8 <= shp.N)) : (c < shp.N);
-    const bool out_f32 = epi_has<kEpi, kEpiOutF32>(ep.c_dtype == SGF_F32);
-    const bool res_f32 = epi_has<kEpi, kEpiResF32>(ep.residual && ep.r_dtype == SGF_F32);
-    const bool res_b16 = epi_has<kEpi, kEpiResBf16>(ep.residual && ep.r_dtype != SGF_F32);
-    const bool do_relu = epi_has<kEpi, kEpiRelu>(ep.act == SGF_ACT_RELU);
-    const int csz = out_f32 ? 4 : 2;
-    const int rsz = res_f32 ? 4 : 2;
-
-    // folded-LayerNorm row statistics of this thread's row: summed (fixed order -> deterministic) while the
-    // main loop is still running
-    float rn_mean = 0.f, rn_rstd = 1.f;
-    const bool rn_on = !kConv && epi_has<kEpi, kEpiRowNorm>(ep.rownorm_stats != nullptr);
-    if (rn_on) {
-      const int mrow = min(m0 + quarter * 32 + lane, shp.M - 1);
-      const float4* sp = reinterpret_cast<const float4*>(ep.rownorm_stats) +
-                         (static_cast<int64_t>(z) * shp.M + mrow) * (ep.rownorm_parts / 2);
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll 4
-      for (int q = 0; q < ep.rownorm_parts / 2; ++q) {
-        const float4 t = __ldg(sp + q);
-        s0 += t.x; s1 += t.y; s0 += t.z; s1 += t.w;
-      }
-      rn_mean = s0 * ep.rownorm_inv_dim;
-      rn_rstd = rsqrtf(fmaxf(s1 * ep.rownorm_inv_dim - rn_mean * rn_mean, 0.f) + 1e-5f);
-    }
-
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-
-    // ---- phase 1 ----
-#pragma unroll 1
-    for (int ch = 0; ch < kCols / 32; ++ch) {
-      const int c0 = n0 + part * kCols + ch * 32;
-      if (c0 >= shp.N) break;  // warp-uniform
-      uint32_t acc[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + part * kCols + ch * 32, acc);
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-      const bool full32 = kRt ? (c0 + 32 <= shp.N && (shp.N % 4) == 0) : true;
-      if (full32) {
-        if (rn_on) {  // folded LayerNorm of the A operand: v = rstd * (v - mean * u[n])
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 u4 = __ldg(reinterpret_cast<const float4*>(ep.rownorm_u + c0 + j));
-            v[j] = rn_rstd * (v[j] - rn_mean * u4.x); v[j + 1] = rn_rstd * (v[j + 1] - rn_mean * u4.y);
-            v[j + 2] = rn_rstd * (v[j + 2] - rn_mean * u4.z); v[j + 3] = rn_rstd * (v[j + 3] - rn_mean * u4.w);
-          }
-        }
-        if (epi_has<kEpi, kEpiScale>(ep.col_scale != nullptr)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + c0 + j));
-            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-          }
-        }
-        if (epi_has<kEpi, kEpiBias>(ep.col_bias != nullptr)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.col_bias + c0 + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
-        }
-      } else if constexpr (kRt) {
-#pragma unroll 4
-        for (int j = 0; j < 32; ++j) {
-          if (c0 + j < shp.N) {
-            if (rn_on) v[j] = rn_rstd * (v[j] - rn_mean * ep.rownorm_u[c0 + j]);
-            if (ep.col_scale) v[j] *= ep.col_scale[c0 + j];
-            if (ep.col_bias) v[j] += ep.col_bias[c0 + j];
-          }
-        }
-      }
-      if (epi_has<kEpi, kEpiAlpha>(ep.alpha_cols > 0)) {
-        if (ep.alpha_cols >= c0 + 32) {  // warp-uniform: the whole chunk is scaled (q columns)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
-        } else if (ep.alpha_cols > c0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < ep.alpha_cols) v[j] *= ep.alpha;
-        }
-      }
-      if (epi_has<kEpi, kEpiGelu>(ep.act == SGF_ACT_GELU)) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-      }
-      float4* dst = reinterpret_cast<float4*>(stage + lane * kRowPitch + ch * 128);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
-    __syncwarp();
-
-    // ---- phase 2a: row map + all residual loads of this warp issued back to back (one exposed latency) ----
-    int out_rows[kIters];
-    uint4 res_lo[kIters], res_hi[kIters];
-#pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int r = quarter * 32 + it * kRowsPerIter + lane / kLanesPerRow;
-      int64_t out_row;
-      bool row_ok;
-      if constexpr (kConv) {
-        const int hh = h0 + r / shp.bw, ww = w0 + r % shp.bw;
-        row_ok = (hh < shp.H) && (ww < shp.W);
-        out_row = (static_cast<int64_t>(img) * shp.H + hh) * shp.W + ww;
-      } else {
-        row_ok = (m0 + r) < shp.M;
-        out_row = m0 + r;
-      }
-      out_rows[it] = (row_ok && c < shp.N) ? static_cast<int>(out_row) : -1;
-      res_lo[it] = make_uint4(0, 0, 0, 0);
-      res_hi[it] = make_uint4(0, 0, 0, 0);
-      if ((res_f32 || res_b16) && vec_ok && out_rows[it] >= 0) {
-        const uint8_t* rptr = reinterpret_cast<const uint8_t*>(ep.residual) +
-                              (static_cast<int64_t>(z) * ep.r_batch_stride + out_row * ep.ldr + c) * rsz;
-        res_lo[it] = *reinterpret_cast<const uint4*>(rptr);
-        if (res_f32) res_hi[it] = *reinterpret_cast<const uint4*>(rptr + 16);
-      }
-    }
-    // ---- phase 2b ----
-    const int scol = (lane % kLanesPerRow) * 8;  // column inside this warp's staging tile
-    const bool want_stats = (kCols == 64) && epi_has<kEpi, kEpiRowStats>(ep.rowstats_out != nullptr);
-#pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      float st_sum = 0.f, st_sq = 0.f;
-      if (out_rows[it] >= 0) {
-        const int rl = it * kRowsPerIter + lane / kLanesPerRow;
-        float v[8];
-        {
-          const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + scol * 4);
-          const float4 b4 = *reinterpret_cast<const float4*>(stage + rl * kRowPitch + scol * 4 + 16);
-          v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
-        }
-        uint8_t* cptr = reinterpret_cast<uint8_t*>(ep.c) +
-                        (static_cast<int64_t>(z) * ep.c_batch_stride + static_cast<int64_t>(out_rows[it]) * ep.ldc + c) * csz;
-        if (vec_ok) {
-          if (res_f32) {
-            v[0] += __uint_as_float(res_lo[it].x); v[1] += __uint_as_float(res_lo[it].y);
-            v[2] += __uint_as_float(res_lo[it].z); v[3] += __uint_as_float(res_lo[it].w);
-            v[4] += __uint_as_float(res_hi[it].x); v[5] += __uint_as_float(res_hi[it].y);
-            v[6] += __uint_as_float(res_hi[it].z); v[7] += __uint_as_float(res_hi[it].w);
-          } else if (res_b16) {
-            const float2 a = unpack_bf16x2(res_lo[it].x), b2 = unpack_bf16x2(res_lo[it].y),
-                         c2 = unpack_bf16x2(res_lo[it].z), d = unpack_bf16x2(res_lo[it].w);
-            v[0] += a.x; v[1] += a.y; v[2] += b2.x; v[3] += b2.y; v[4] += c2.x; v[5] += c2.y; v[6] += d.x; v[7] += d.y;
-          }
-          if (do_relu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
-          }
-          if (out_f32) {
-            *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(cptr + 16) = make_float4(v[4], v[5], v[6], v[7]);
-          } else {
-            uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(cptr) = o;
-            if (want_stats) {  // statistics of exactly what was stored
-              const float2 a = unpack_bf16x2(o.x), b2 = unpack_bf16x2(o.y), c2 = unpack_bf16x2(o.z), d = unpack_bf16x2(o.w);
-              const float w[8] = {a.x, a.y, b2.x, b2.y, c2.x, c2.y, d.x, d.y};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                st_sum += w[j];
-                st_sq = fmaf(w[j], w[j], st_sq);
-              }
-            }
-          }
-        } else if constexpr (kRt) {
-          const uint8_t* rptr = ep.residual ? reinterpret_cast<const uint8_t*>(ep.residual) +
-                                                  (static_cast<int64_t>(z) * ep.r_batch_stride +
-                                                   static_cast<int64_t>(out_rows[it]) * ep.ldr + c) * rsz
-                                            : nullptr;
-#pragma unroll 1
-          for (int j = 0; j < 8; ++j) {
-            if (c + j < shp.N) {
-              float t = v[j];
-              if (rptr)
-                t += res_f32 ? reinterpret_cast<const float*>(rptr)[j]
-                             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rptr)[j]);
-              if (do_relu) t = fmaxf(t, 0.0f);
-              if (out_f32)
-                reinterpret_cast<float*>(cptr)[j] = t;
-              else
-                reinterpret_cast<__nv_bfloat16*>(cptr)[j] = __float2bfloat16_rn(t);
-            }
-          }
-        }
-      }  // valid row
-      if (want_stats) {  // warp-uniform: reduce over the lanes that share a row, one slot per row segment
-#pragma unroll
-        for (int o = kLanesPerRow / 2; o > 0; o >>= 1) {
-          st_sum += __shfl_xor_sync(0xffffffffu, st_sum, o);
-          st_sq += __shfl_xor_sync(0xffffffffu, st_sq, o);
-        }
-        if ((lane % kLanesPerRow) == 0 && out_rows[it] >= 0) {
-          // deterministic: one (sum, sumsq) slot per 64-column block of the row, summed in order by the consumer
-          const int nparts = (shp.N + 63) / 64;
-          float2* sp = reinterpret_cast<float2*>(ep.rowstats_out) +
-                       (static_cast<int64_t>(z) * shp.M + out_rows[it]) * nparts + (n0 + part * kCols) / 64;
-          *sp = make_float2(st_sum, st_sq);
-        }
-      }
-    }
+    gemm_epilogue<BN, kEpiWarps, kStages * S::kStageBytes, kConv, kEpi>(smem, tmem_base, accum_bar, shp, ep, m0, n0, z,
+                                                                        img, h0, w0, warp, lane);
   }
 
   tc_fence_before();
@@ -399,6 +410,361 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// CTA-pair kernel: a cluster of two CTAs (two SMs of a TPC) computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2.  Each CTA stages its own 128 rows of A and only HALF of the B tile
+// (BN/2 rows), so the shared-memory fill traffic per MMA cycle -- the limiter of the 1-CTA kernel --
+// is halved; the leader CTA's single MMA thread drives both tensor cores.
+//   full[s]   (leader only): 1 arrival (leader's expect_tx of both CTAs' bytes) + TMA bytes of both CTAs
+//   empty[s]  (per CTA)    : multicast tcgen05.commit from the leader
+//   accum     (per CTA)    : multicast tcgen05.commit from the leader
+// ----------------------------------------------------------------------------------------
+template <int BN>
+struct Gemm2Smem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = (BN / 2) * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+};
+template <int BN>
+static constexpr int gemm2_stages() { return BN >= 256 ? 6 : 4; }
+
+template <int BN, int kEpi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1))
+    gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmShape shp, const GemmEpilogue ep) {
+  using S = Gemm2Smem<BN>;
+  constexpr int kStages = gemm2_stages<BN>();
+  constexpr int kEpiWarps = gemm_epi_warps<BN>();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* accum_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int n0 = blockIdx.y * BN;
+  const int m0 = (blockIdx.x >> 1) * (2 * BM) + static_cast<int>(rank) * BM;  // this CTA's 128 rows
+  const int z = blockIdx.z;
+  const int num_kb = (shp.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<BN>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+#pragma unroll 1
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);  // own copy: the leader's commit is multicast to both CTAs
+        uint8_t* sa = smem + s * S::kStageBytes;
+        uint8_t* sb = sa + S::kABytes;
+        if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
+        tma_load_3d_2cta(sa, &tmA, &full_bar[s], kb * BK, m0, z);
+        tma_load_3d_2cta(sb, &tmB, &full_bar[s], kb * BK, n0 + static_cast<int>(rank) * (BN / 2), z);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+#pragma unroll 1
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+        const uint32_t sb = sa + S::kABytes;
+        const uint64_t da = make_smem_desc_sw128(sa);
+        const uint64_t db = make_smem_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_2cta(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit_2cta(&empty_bar[s], 0b11);
+      }
+      umma_commit_2cta(accum_bar, 0b11);
+    }
+  } else {
+    gemm_epilogue<BN, kEpiWarps, kStages * S::kStageBytes, false, kEpi>(smem, tmem_base, accum_bar, shp, ep, m0, n0, z, 0,
+                                                                        0, 0, warp, lane);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may release TMEM / exit while the pair's MMAs or TMA signals can still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<BN>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// Persistent CTA-pair kernel: one cluster of two CTAs per SM pair loops over 256 x 256 output tiles.
+// The 512 TMEM columns hold TWO accumulators, so the epilogue of tile i (8 warps per CTA, thread =
+// row, straight from TMEM to global memory) runs while the tensor cores already work on tile i+1;
+// barrier set-up, TMEM allocation and descriptor fetches are paid once per SM instead of once per tile.
+//   full[s]/empty[s]        : smem ring, as in the non-persistent pair kernel, running across tiles
+//   tmem_full[2]  (per CTA) : multicast tcgen05.commit when an accumulator is complete
+//   tmem_empty[2] (leader)  : 2 x 8 epilogue-warp arrivals (both CTAs) once an accumulator is drained
+// ----------------------------------------------------------------------------------------
+static constexpr int kP2BN = 256;
+static constexpr int kP2Stages = 6;
+static constexpr int kP2EpiWarps = 8;
+static constexpr int kP2Threads = 64 + 32 * kP2EpiWarps;
+
+template <int kEpi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1)
+    gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const GemmShape shp, const GemmEpilogue ep, const int num_m_pairs, const int num_tiles) {
+  using S = Gemm2Smem<kP2BN>;
+  constexpr int BN = kP2BN;
+  constexpr int kStages = kP2Stages;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int z = blockIdx.z;
+  const int num_kb = (shp.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * kP2EpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;  // running k-block counter across tiles
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int m0 = (t % num_m_pairs) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = (t / num_m_pairs) * BN;
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % kStages;
+          mbar_wait(&empty_bar[s], ((g / kStages) & 1) ^ 1);
+          uint8_t* sa = smem + s * S::kStageBytes;
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
+          tma_load_3d_2cta(sa, &tmA, &full_bar[s], kb * BK, m0, z);
+          tma_load_3d_2cta(sa + S::kABytes, &tmB, &full_bar[s], kb * BK, n0 + static_cast<int>(rank) * (BN / 2), z);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      uint32_t g = 0;
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const int ab = it & 1;
+        mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);  // both CTAs drained this accumulator
+        tc_fence_after();
+#pragma unroll 1
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % kStages;
+          mbar_wait(&full_bar[s], (g / kStages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+          const uint64_t da = make_smem_desc_sw128(sa);
+          const uint64_t db = make_smem_desc_sw128(sa + S::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16_2cta(tmem_base + ab * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta(&empty_bar[s], 0b11);
+        }
+        umma_commit_2cta(&tmem_full[ab], 0b11);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps: thread = row, straight from TMEM to global memory ----------------
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;  // columns [half*128, +128) of the tile
+    const bool out_f32 = (kEpi & kEpiOutF32) != 0;
+    const int csz = out_f32 ? 4 : 2;
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      const int ab = it & 1;
+      const int m0 = (t % num_m_pairs) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = (t / num_m_pairs) * BN;
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < shp.M;
+      const int rrow = row_ok ? row : shp.M - 1;
+      float rn_mean = 0.f, rn_rstd = 1.f;
+      if constexpr ((kEpi & kEpiRowNorm) != 0) {
+        const float4* sp = reinterpret_cast<const float4*>(ep.rownorm_stats) +
+                           (static_cast<int64_t>(z) * shp.M + rrow) * (ep.rownorm_parts / 2);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+        for (int q = 0; q < ep.rownorm_parts / 2; ++q) {
+          const float4 u = __ldg(sp + q);
+          s0 += u.x; s1 += u.y; s0 += u.z; s1 += u.w;
+        }
+        rn_mean = s0 * ep.rownorm_inv_dim;
+        rn_rstd = rsqrtf(fmaxf(s1 * ep.rownorm_inv_dim - rn_mean * rn_mean, 0.f) + 1e-5f);
+      }
+      mbar_wait(&tmem_full[ab], (it >> 1) & 1);
+      tc_fence_after();
+      uint8_t* crow = reinterpret_cast<uint8_t*>(ep.c) + (static_cast<int64_t>(z) * ep.c_batch_stride + static_cast<int64_t>(rrow) * ep.ldc) * csz;
+      float st_sum = 0.f, st_sq = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        const int c0 = n0 + half * 128 + ch * 32;
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + ab * BN + (static_cast<uint32_t>(quarter * 32) << 16) + half * 128 + ch * 32, acc);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+        if constexpr ((kEpi & kEpiRowNorm) != 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 u4 = __ldg(reinterpret_cast<const float4*>(ep.rownorm_u + c0 + j));
+            v[j] = rn_rstd * (v[j] - rn_mean * u4.x); v[j + 1] = rn_rstd * (v[j + 1] - rn_mean * u4.y);
+            v[j + 2] = rn_rstd * (v[j + 2] - rn_mean * u4.z); v[j + 3] = rn_rstd * (v[j + 3] - rn_mean * u4.w);
+          }
+        }
+        if constexpr ((kEpi & kEpiScale) != 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + c0 + j));
+            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
+          }
+        }
+        if constexpr ((kEpi & kEpiBias) != 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.col_bias + c0 + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+        if constexpr ((kEpi & kEpiAlpha) != 0) {
+          if (ep.alpha_cols >= c0 + 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+          } else if (ep.alpha_cols > c0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < ep.alpha_cols) v[j] *= ep.alpha;
+          }
+        }
+        if constexpr ((kEpi & kEpiGelu) != 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if constexpr ((kEpi & kEpiResF32) != 0) {
+          const float4* rp = reinterpret_cast<const float4*>(
+              reinterpret_cast<const float*>(ep.residual) + static_cast<int64_t>(z) * ep.r_batch_stride +
+              static_cast<int64_t>(rrow) * ep.ldr + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r4 = rp[j];
+            v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+          }
+        }
+        if constexpr ((kEpi & kEpiResBf16) != 0) {
+          const uint4* rp = reinterpret_cast<const uint4*>(
+              reinterpret_cast<const __nv_bfloat16*>(ep.residual) + static_cast<int64_t>(z) * ep.r_batch_stride +
+              static_cast<int64_t>(rrow) * ep.ldr + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 r4 = rp[j];
+            const float2 a = unpack_bf16x2(r4.x), b2 = unpack_bf16x2(r4.y), c2 = unpack_bf16x2(r4.z), d = unpack_bf16x2(r4.w);
+            v[8 * j] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += b2.x; v[8 * j + 3] += b2.y;
+            v[8 * j + 4] += c2.x; v[8 * j + 5] += c2.y; v[8 * j + 6] += d.x; v[8 * j + 7] += d.y;
+          }
+        }
+        if constexpr ((kEpi & kEpiRelu) != 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (row_ok) {
+          if (out_f32) {
+            float4* cp = reinterpret_cast<float4*>(crow + static_cast<int64_t>(c0) * 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* cp = reinterpret_cast<uint4*>(crow + static_cast<int64_t>(c0) * 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              cp[j] = o;
+              if constexpr ((kEpi & kEpiRowStats) != 0) {
+                const float2 a = unpack_bf16x2(o.x), b2 = unpack_bf16x2(o.y), c2 = unpack_bf16x2(o.z), d = unpack_bf16x2(o.w);
+                st_sum += ((a.x + a.y) + (b2.x + b2.y)) + ((c2.x + c2.y) + (d.x + d.y));
+                st_sq += ((a.x * a.x + a.y * a.y) + (b2.x * b2.x + b2.y * b2.y)) +
+                         ((c2.x * c2.x + c2.y * c2.y) + (d.x * d.x + d.y * d.y));
+              }
+            }
+          }
+        }
+        if constexpr ((kEpi & kEpiRowStats) != 0) {
+          if (ch & 1) {  // one deterministic (sum, sumsq) slot per 64-column block of the row
+            if (row_ok) {
+              const int nparts = (shp.N + 63) / 64;
+              reinterpret_cast<float2*>(ep.rowstats_out)[(static_cast<int64_t>(z) * shp.M + row) * nparts + (c0 - 32) / 64] =
+                  make_float2(st_sum, st_sq);
+            }
+            st_sum = 0.f;
+            st_sq = 0.f;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[ab]);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<512>(tmem_base);
   }
 }
 
@@ -415,6 +781,21 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                        dim3 grid, cudaStream_t st) {
   auto kern = gemm_tcgen05_kernel<BN, kStages, kConv, kEpi>;
   constexpr int smem = gemm_smem_bytes<BN, kStages>();
+  static bool configured = false;
+  if (!configured) {
+    SGF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  SGF_CHECK_CUDA(launch_pdl(kern, grid, dim3(gemm_threads<BN>()), smem, st, tmA, tmB, shp, ep));
+  count_launch();
+  return SGF_OK;
+}
+
+template <int BN, int kEpi>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
+                        dim3 grid, cudaStream_t st) {
+  auto kern = gemm2_tcgen05_kernel<BN, kEpi>;
+  constexpr int smem = gemm2_stages<BN>() * Gemm2Smem<BN>::kStageBytes + (2 * gemm2_stages<BN>() + 1) * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
     SGF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -470,6 +851,69 @@ static int dispatch_epilogue(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   return launch_gemm<BN, kStages, kConv, kEpiRuntime>(tmA, tmB, shp, ep, grid, st);
 }
 
+template <int kEpi>
+static int launch_gemm2p(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
+                         int batch, cudaStream_t st) {
+  auto kern = gemm2p_tcgen05_kernel<kEpi>;
+  constexpr int smem = kP2Stages * Gemm2Smem<kP2BN>::kStageBytes + (2 * kP2Stages + 4) * 8 + 16 + 1024;
+  static bool configured = false;
+  static int num_sms = 0;
+  if (!configured) {
+    SGF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int dev = 0;
+    SGF_CHECK_CUDA(cudaGetDevice(&dev));
+    SGF_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    configured = true;
+  }
+  const int num_m_pairs = (shp.M + 2 * BM - 1) / (2 * BM);
+  const int num_tiles = num_m_pairs * (shp.N / kP2BN);
+  int clusters = num_sms / 2;
+  if (batch > 1) clusters = clusters / batch > 0 ? clusters / batch : 1;
+  if (clusters > num_tiles) clusters = num_tiles;
+  dim3 grid(2 * clusters, 1, batch);
+  SGF_CHECK_CUDA(launch_pdl(kern, grid, dim3(kP2Threads), smem, st, tmA, tmB, shp, ep, num_m_pairs, num_tiles));
+  count_launch();
+  return SGF_OK;
+}
+
+#define SGF_EPI2P_CASE(MASK)                                                                           \
+  case (MASK):                                                                                          \
+    return launch_gemm2p<(MASK)>(tmA, tmB, shp, ep, batch, st);
+
+static int dispatch_epilogue2p(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
+                               int batch, cudaStream_t st) {
+  switch (epilogue_mask(ep)) {
+    SGF_EPI2P_CASE(kEpiBias | kEpiAlpha)
+    SGF_EPI2P_CASE(kEpiBias | kEpiOutF32)
+    SGF_EPI2P_CASE(kEpiBias)
+    SGF_EPI2P_CASE(kEpiBias | kEpiGelu | kEpiRowStats)
+    SGF_EPI2P_CASE(kEpiBias | kEpiRowNorm | kEpiResF32 | kEpiOutF32)
+    SGF_EPI2P_CASE(kEpiScale | kEpiBias | kEpiRelu)
+    SGF_EPI2P_CASE(kEpiScale | kEpiBias | kEpiRelu | kEpiResBf16)
+    SGF_EPI2P_CASE(kEpiScale | kEpiBias)
+    SGF_EPI2P_CASE(0)
+    default: return -1;
+  }
+}
+
+#define SGF_EPI2_CASE(MASK)                                                                            \
+  case (MASK):                                                                                          \
+    return launch_gemm2<BN, (MASK)>(tmA, tmB, shp, ep, grid, st);
+
+template <int BN>
+static int dispatch_epilogue2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
+                              dim3 grid, cudaStream_t st) {
+  switch (epilogue_mask(ep)) {
+    SGF_EPI2_CASE(kEpiBias | kEpiAlpha)
+    SGF_EPI2_CASE(kEpiBias | kEpiOutF32)
+    SGF_EPI2_CASE(kEpiBias)
+    SGF_EPI2_CASE(kEpiBias | kEpiGelu | kEpiRowStats)
+    SGF_EPI2_CASE(kEpiBias | kEpiRowNorm | kEpiResF32 | kEpiOutF32)
+    SGF_EPI2_CASE(0)
+    default: return -1;  // no CTA-pair specialisation: caller falls back to the 1-CTA kernel
+  }
+}
+
 static int check_epilogue_alignment(const GemmEpilogue& ep, int N) {
   if (N % 8 == 0) {
     const int cs = ep.c_dtype == SGF_F32 ? 4 : 2;
@@ -491,7 +935,7 @@ static int check_epilogue_alignment(const GemmEpilogue& ep, int N) {
 static int g_force_bn = 0, g_force_stages = 0;  // tuning hook (sgf_gemm_force_variant)
 
 static int pick_bn(int M_tiles, int N, int batch) {
-  if (g_force_bn) return g_force_bn;
+  if (g_force_bn && g_force_bn < 1000) return g_force_bn;
   // prefer the widest tile that still gives >= 1 wave of CTAs on 148 SMs
   if (N <= 32) return 32;
   if (N <= 64) return 64;
@@ -530,6 +974,42 @@ extern "C" int sgf_gemm_bf16(const sgf_gemm_args* a, void* stream) {
 
   const int m_tiles = (a->M + BM - 1) / BM;
   int bn = pick_bn(m_tiles, a->N, a->batch);
+  // CTA-pair kernel for the large transformer GEMMs (tile 256 x BN2): full N tiles only
+  int bn2 = 0;
+  if (g_force_bn == 0 || g_force_bn >= 1000) {
+    const int want = g_force_bn >= 1000 ? g_force_bn - 1000 : 0;
+    if (want) bn2 = want;
+    else {
+      static const int mode = [] { const char* e = getenv("SGF_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+      const int tiles = ((a->M + 255) / 256) * (a->N / 256);
+      if (mode == 1 && a->M >= 2048 && a->N % 256 == 0 && a->N >= 2048 && a->K >= 256) bn2 = 256;
+      if (mode == 2 && a->M >= 1024 && a->N % 256 == 0 && tiles >= 48) bn2 = 256;
+    }
+    if (bn2 && (a->N % bn2 != 0 || a->N % 32 != 0)) bn2 = 0;
+  }
+  if (bn2) {
+    CUtensorMap tmA2, tmB2;
+    uint64_t dimsA[3] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M), static_cast<uint64_t>(a->batch)};
+    uint64_t strA[2] = {static_cast<uint64_t>(a->lda) * 2,
+                        static_cast<uint64_t>(a->batch > 1 ? a->a_batch_stride : a->lda * (int64_t)a->M) * 2};
+    uint32_t boxA[3] = {BK, BM, 1};
+    uint64_t dimsB[3] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->batch)};
+    uint64_t strB[2] = {static_cast<uint64_t>(a->ldb) * 2,
+                        static_cast<uint64_t>(a->batch > 1 ? a->b_batch_stride : a->ldb * (int64_t)a->N) * 2};
+    uint32_t boxB[3] = {BK, static_cast<uint32_t>(bn2 / 2), 1};
+    if (int rc = encode_tmap(&tmA2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dimsA, strA, boxA, CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+    if (int rc = encode_tmap(&tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->b, dimsB, strB, boxB, CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+    dim3 grid2(2 * ((a->M + 2 * BM - 1) / (2 * BM)), a->N / bn2, a->batch);
+    int rc = -1;
+    if (bn2 == 256 && g_force_stages != 1) rc = dispatch_epilogue2p(tmA2, tmB2, shp, ep, a->batch, st);  // persistent
+    if (rc < 0)
+      rc = bn2 == 256 ? dispatch_epilogue2<256>(tmA2, tmB2, shp, ep, grid2, st)
+                      : dispatch_epilogue2<128>(tmA2, tmB2, shp, ep, grid2, st);
+    if (rc >= 0) return rc;
+  }
+  if (g_force_bn >= 1000) bn = 128;
   if (a->rowstats_out && bn != 64 && bn != 128) bn = 128;  // statistics are kept per 64-column block
 
   CUtensorMap tmA, tmB;
