@@ -183,3 +183,44 @@ def test_criterion_eval_branch(case15):
     ocfg = R.SegOFAConfig(num_seg=C, patch_image_size=S)
     ref_val = R.imfree_loss(extra["aux_output"][0].cpu(), t2s, ocfg)
     assert abs(val.item() - ref_val.item()) < 1e-3
+
+
+@pytest.mark.parametrize("arch,num_seg,size,batch", [("segofa_large", 150, 96, 2), ("segofa_tiny", 15, 64, 3),
+                                                     ("segofa_medium", 171, 80, 1)])
+def test_other_architectures_vs_oracle(cuda_device, arch, num_seg, size, batch):
+    """Every registered architecture (ResNet-50/101/152 stems, D in {256,512,1024}, 4..16 heads) against the
+    CPU oracle on fresh seeded weights."""
+    from oracle import restated as R
+    from ifseg_b200.synthetic import synthetic_inputs
+
+    model, sd = build_cuda_model(arch, num_seg, size, seed=11)
+    inp = synthetic_inputs(model.cfg, batch, size, seed=13)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        ref, _ = R.segofa_forward(sd, oracle_cfg(model.cfg), inp["src_tokens"], inp["patch_images"], inp["patch_masks"])
+        x, _ = model(**{k: v.cuda() for k, v in inp.items()})
+    err = rel_l2(x, ref)
+    print(f"{arch}: rel-L2 vs oracle {err:.3e}")
+    assert x.shape == ref.shape and err <= 1.5e-2
+
+
+def test_serving_session_matches_eager(case15):
+    """SegmentationSession (CUDA graph + pinned pipelined I/O) returns the same masks as the eager API."""
+    from ifseg_b200.serving import SegmentationSession
+    from ifseg_b200.synthetic import synthetic_inputs
+
+    g, model, _ = case15
+    S = g["image_size"]
+    sess = SegmentationSession(model, 2, S, g["src_tokens"][0])
+    batches = [synthetic_inputs(model.cfg, 2, S, seed=100 + i)["patch_images"] for i in range(5)]
+    outs = [m.clone() for m in sess.infer_stream(batches)]
+    assert len(outs) == 5
+    eng = model.engine()
+    for imgs, m in zip(batches, outs):
+        with torch.no_grad():
+            x, extra = model(src_tokens=g["src_tokens"][:1].repeat(2, 1).cuda(), patch_images=imgs.cuda(),
+                             patch_masks=torch.ones(2, dtype=torch.bool).cuda(),
+                             prev_output_tokens=torch.zeros(2, 1, dtype=torch.long).cuda())
+            ref = eng.predict_mask(x, extra["encoder_returns"]["image_embed_shape"][0], (S, S))
+        assert torch.equal(m, ref.cpu())
+    assert torch.equal(sess.infer(batches[0]), outs[0])
