@@ -50,6 +50,7 @@ class RowLnArgs(C.Structure):
         ("rows", _i32), ("D", _i32),
         ("seg_len", _i32), ("seg_stride", _i32), ("seg_off", _i32),
         ("clear_rowstats", _vp),
+        ("x_act", _i32),
     ]
 
 
@@ -73,6 +74,7 @@ class AttentionArgs(C.Structure):
         ("bias", _vp), ("bias_head_stride", _i64), ("bias_row_stride", _i64),
         ("head_scale", _vp), ("key_padding_mask", _vp),
         ("B", _i32), ("H", _i32), ("Tq", _i32), ("Tk", _i32), ("causal", _i32),
+        ("lse", _vp),
     ]
 
 
@@ -89,7 +91,55 @@ class SeglossArgs(C.Structure):
     _fields_ = [
         ("logits", _vp), ("batch_stride", _i64), ("tok_stride", _i64),
         ("B", _i32), ("C", _i32), ("hp", _i32), ("wp", _i32), ("h", _i32), ("w", _i32),
-        ("target", _vp), ("label_smoothing", _f32), ("out", _vp),
+        ("target", _vp), ("label_smoothing", _f32), ("out", _vp), ("lse_out", _vp),
+    ]
+
+
+class SeglossBwdArgs(C.Structure):
+    _fields_ = [
+        ("logits", _vp), ("batch_stride", _i64), ("tok_stride", _i64),
+        ("B", _i32), ("C", _i32), ("hp", _i32), ("wp", _i32), ("h", _i32), ("w", _i32),
+        ("target", _vp), ("lse", _vp), ("count", _vp),
+        ("label_smoothing", _f32), ("grad_scale", _f32),
+        ("dlogits", _vp), ("d_batch_stride", _i64), ("d_tok_stride", _i64), ("d_tokens", _i32),
+    ]
+
+
+class RowLnBwdArgs(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("ldx", _i64), ("x_dtype", _i32),
+        ("gather_idx", _vp),
+        ("x_act", _i32),
+        ("pre_add", _vp),
+        ("g1", _vp),
+        ("v", _vp), ("ldv", _i64), ("v_dtype", _i32),
+        ("g2", _vp),
+        ("dy2", _vp), ("ldy2", _i64), ("dy2_dtype", _i32),
+        ("dv_in", _vp), ("lddv", _i64),
+        ("d_res", _vp), ("ldres", _i64),
+        ("dx", _vp), ("lddx", _i64), ("dx_dtype", _i32), ("dx_accumulate", _i32),
+        ("dg1", _vp), ("db1", _vp), ("dg2", _vp), ("db2", _vp), ("d_pre_add", _vp),
+        ("rows", _i32), ("D", _i32),
+        ("seg_len", _i32), ("seg_stride", _i32), ("seg_off", _i32),
+    ]
+
+
+class AttentionBwdArgs(C.Structure):
+    _fields_ = [
+        ("q", _vp), ("q_row_stride", _i64), ("q_batch_stride", _i64),
+        ("k", _vp), ("k_row_stride", _i64), ("k_batch_stride", _i64),
+        ("v", _vp), ("v_row_stride", _i64), ("v_batch_stride", _i64),
+        ("out", _vp), ("o_row_stride", _i64), ("o_batch_stride", _i64),
+        ("dout", _vp), ("do_row_stride", _i64), ("do_batch_stride", _i64),
+        ("dq", _vp), ("dq_row_stride", _i64), ("dq_batch_stride", _i64),
+        ("dk", _vp), ("dk_row_stride", _i64), ("dk_batch_stride", _i64),
+        ("dv", _vp), ("dv_row_stride", _i64), ("dv_batch_stride", _i64),
+        ("bias", _vp), ("bias_head_stride", _i64), ("bias_row_stride", _i64),
+        ("head_scale", _vp), ("d_head_scale", _vp),
+        ("key_padding_mask", _vp),
+        ("lse", _vp), ("delta", _vp),
+        ("dq_scale", _f32),
+        ("B", _i32), ("H", _i32), ("Tq", _i32), ("Tk", _i32), ("causal", _i32),
     ]
 
 
@@ -111,6 +161,12 @@ EXPORTS = [
     ("sgf_upsample_argmax", C.c_int, [C.POINTER(SegmaskArgs), _vp]),
     ("sgf_embedding_bag_mean", C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp]),
     ("sgf_upsample_ce_loss", C.c_int, [C.POINTER(SeglossArgs), _vp]),
+    ("sgf_upsample_ce_loss_bwd", C.c_int, [C.POINTER(SeglossBwdArgs), _vp]),
+    ("sgf_row_layernorm_bwd", C.c_int, [C.POINTER(RowLnBwdArgs), _vp]),
+    ("sgf_transpose_cast", C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp]),
+    ("sgf_attention_bwd_bf16", C.c_int, [C.POINTER(AttentionBwdArgs), _vp]),
+    ("sgf_adam_step", C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
+    ("sgf_sumsq", C.c_int, [_vp, _i64, _vp, _vp]),
 ]
 
 _lib = None
@@ -132,7 +188,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError -> missing export
         fn.restype = res
         fn.argtypes = args
-    if lib.sgf_abi_version() != 2:
+    if lib.sgf_abi_version() != 3:
         raise RuntimeError("libsegofa_b200.so ABI version mismatch")
     _lib = lib
     return lib

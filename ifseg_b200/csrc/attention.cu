@@ -36,6 +36,7 @@ struct AttnParams {
   const float* head_scale;
   const uint8_t* kpm;
   int B, H, Tq, Tk, causal;
+  float* lse;
 };
 
 struct AttnSmem {
@@ -316,6 +317,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
     {
       // the TMEM loads are warp-collective: every lane executes them, rows >= Tq only skip the stores
       const float inv = (1.0f / l_run) * (p.head_scale ? p.head_scale[h] : 1.0f);
+      if (p.lse && row < p.Tq)  // log2-domain log-sum-exp of the (biased, masked) score row, for the backward
+        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Tq + row] = m_used + __log2f(l_run);
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(b) * p.o_batch_stride +
                            static_cast<int64_t>(row) * p.o_row_stride + h * kHeadDim;
 #pragma unroll
@@ -386,7 +389,7 @@ extern "C" int sgf_attention_bf16(const sgf_attention_args* a, void* stream) {
       return rc;
   }
   AttnParams p{a->out, a->o_row_stride, a->o_batch_stride, a->bias, a->head_scale, a->key_padding_mask,
-               a->B, a->H, a->Tq, a->Tk, a->causal};
+               a->B, a->H, a->Tq, a->Tk, a->causal, a->lse};
   constexpr int smem = AttnSmem::kTotal;
   static bool configured = false;
   if (!configured) {

@@ -21,6 +21,7 @@ struct RowLnParams {
   int rows, D;
   int seg_len, seg_stride, seg_off;
   float* clear_rowstats;
+  int x_act;
 };
 
 SGF_DEVICE void load8(const void* base, int dtype, int64_t elem_off, float (&v)[8]) {
@@ -117,6 +118,10 @@ __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const Ro
     for (int c = lane; c < nchunk; c += 32) {
       float v[8];
       smem_load8(xr, p.x_dtype, c * 8, v);
+      if (p.x_act == SGF_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+      }
       if (p.pre_add) {
         float a[8];
         load8(p.pre_add, SGF_F32, c * 8, a);
@@ -131,6 +136,10 @@ __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const Ro
     for (int c = lane; c < nchunk; c += 32) {
       float v[8];
       smem_load8(xr, p.x_dtype, c * 8, v);
+      if (p.x_act == SGF_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+      }
       if (p.pre_add) {
         float a[8];
         load8(p.pre_add, SGF_F32, c * 8, a);
@@ -146,12 +155,16 @@ __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const Ro
     rstd1 = rsqrtf(warp_sum(q) * invD + 1e-5f);
   }
   // ---- v = LN1(t) + residual ; out1 ; stash for LN2 ----
-  const bool two_stage = p.out2 && (p.g1 || p.residual || p.pre_add || p.out1);
+  const bool two_stage = p.out2 && (p.g1 || p.residual || p.pre_add || p.out1 || p.x_act);
   float s2 = 0.f;
   if (two_stage || p.out1) {
     for (int c = lane; c < nchunk; c += 32) {
       float v[8];
       smem_load8(xr, p.x_dtype, c * 8, v);
+      if (p.x_act == SGF_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+      }
       if (p.pre_add) {
         float a[8];
         load8(p.pre_add, SGF_F32, c * 8, a);
@@ -432,12 +445,12 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
               "row_layernorm: row strides must be multiples of 8 elements");
   RowLnParams p{a->x, a->ldx, a->x_dtype, a->gather_idx, a->pre_add, a->g1, a->b1, a->residual, a->ldr, a->r_dtype,
                 a->out1, a->ld1, a->out1_dtype, a->g2, a->b2, a->out2, a->ld2, a->zero_row, a->rows, a->D,
-                a->seg_len, a->seg_stride, a->seg_off, a->clear_rowstats};
+                a->seg_len, a->seg_stride, a->seg_off, a->clear_rowstats, a->x_act};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int xs = a->x_dtype == SGF_F32 ? 4 : 2, rs = a->r_dtype == SGF_F32 ? 4 : 2;
   const int x_row_bytes = a->D * xs;
   const int r_row_bytes = a->residual ? a->D * rs : 0;
-  const bool two_stage = a->out2 && (a->g1 || a->residual || a->pre_add || a->out1);
+  const bool two_stage = a->out2 && (a->g1 || a->residual || a->pre_add || a->out1 || a->x_act);
   const int s_row_bytes = two_stage ? a->D * 4 : 0;
   int kLnRows = kLnMaxRows;
   while (kLnRows > 1 && kLnRows * (x_row_bytes + r_row_bytes + s_row_bytes) > 96 * 1024) kLnRows >>= 1;

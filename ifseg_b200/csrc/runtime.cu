@@ -71,6 +71,6 @@ int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* 
 }  // namespace sgf
 
 extern "C" const char* sgf_last_error(void) { return sgf::g_err; }
-extern "C" int sgf_abi_version(void) { return 2; }
+extern "C" int sgf_abi_version(void) { return 3; }
 extern "C" int64_t sgf_launch_count(void) { return sgf::g_launches.load(); }
 extern "C" void sgf_reset_launch_count(void) { sgf::g_launches.store(0); }

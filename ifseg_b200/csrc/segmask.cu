@@ -99,6 +99,7 @@ struct SeglossParams {
   float eps;
   float* out;
   float scale_h, scale_w;
+  float* lse_out;
 };
 
 __global__ void __launch_bounds__(256) upsample_ce_loss_kernel(const SeglossParams p) {
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(256) upsample_ce_loss_kernel(const SeglossPara
         m = mn;
       }
       const float lse = m + __logf(ssum);
+      if (p.lse_out) p.lse_out[pix] = lse;
       loss = (1.f - p.eps) * (lse - vt) + p.eps * (lse - vsum / static_cast<float>(p.C));
       cnt = 1.f;
     }
@@ -157,16 +159,134 @@ __global__ void __launch_bounds__(256) upsample_ce_loss_kernel(const SeglossPara
   }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// adjoint of upsample + pixel cross-entropy w.r.t. the low-resolution logits (gather form)
+// ----------------------------------------------------------------------------------------
+struct SeglossBwdParams {
+  const float* logits;
+  int64_t batch_stride, tok_stride;
+  int B, C, hp, wp, h, w;
+  const int64_t* target;
+  const float* lse;
+  const float* count;
+  float eps, grad_scale;
+  __nv_bfloat16* dlogits;
+  int64_t d_batch_stride, d_tok_stride;
+  int d_tokens;
+  float scale_h, scale_w;
+};
+
+// weight with which low-res index `want` enters output index `dst` (0 when it does not)
+SGF_DEVICE float tap_weight(float scale, int dst, int in_size, int want, int& i0, int& i1, float& l0, float& l1) {
+  src_index(scale, dst, in_size, i0, i1, l0, l1);
+  return (i0 == want ? l0 : 0.f) + (i1 == want ? l1 : 0.f);
+}
+
+__global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const SeglossBwdParams p) {
+  const int tok = blockIdx.x;
+  const int b = blockIdx.y;
+  __nv_bfloat16* drow = p.dlogits + static_cast<int64_t>(b) * p.d_batch_stride + static_cast<int64_t>(tok) * p.d_tok_stride;
+  if (tok >= p.hp * p.wp) {  // eos slot / padding rows receive no gradient (seg_criterion.py:238)
+    for (int c = threadIdx.x; c < p.d_tok_stride; c += blockDim.x) drow[c] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const int py = tok / p.wp, px = tok - py * p.wp;
+  // conservative pixel footprint of the patch: src = scale*(dst+0.5)-0.5 in (p-1, p+1)
+  const float inv_h = static_cast<float>(p.h) / static_cast<float>(p.hp), inv_w = static_cast<float>(p.w) / static_cast<float>(p.wp);
+  int ylo = static_cast<int>(floorf((py - 0.5f) * inv_h - 0.5f)) - 1, yhi = static_cast<int>(ceilf((py + 1.5f) * inv_h - 0.5f)) + 1;
+  int xlo = static_cast<int>(floorf((px - 0.5f) * inv_w - 0.5f)) - 1, xhi = static_cast<int>(ceilf((px + 1.5f) * inv_w - 0.5f)) + 1;
+  ylo = max(ylo, 0); xlo = max(xlo, 0); yhi = min(yhi, p.h - 1); xhi = min(xhi, p.w - 1);
+  if (py == 0) ylo = 0;  // clamped border rows/columns all map onto the first / last patch
+  if (px == 0) xlo = 0;
+  if (py == p.hp - 1) yhi = p.h - 1;
+  if (px == p.wp - 1) xhi = p.w - 1;
+  const float inv_cnt = p.grad_scale / fmaxf(p.count[0], 1.0f);
+  const float* base = p.logits + static_cast<int64_t>(b) * p.batch_stride;
+  const float uni = p.eps / static_cast<float>(p.C);
+  for (int c = threadIdx.x; c < p.d_tok_stride; c += blockDim.x) {
+    if (c >= p.C) {
+      drow[c] = __float2bfloat16_rn(0.f);
+      continue;
+    }
+    float nb[3][3];  // this class's logits on the 3x3 patch neighbourhood (clamped)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int yy = min(max(py - 1 + dy, 0), p.hp - 1), xx = min(max(px - 1 + dx, 0), p.wp - 1);
+        nb[dy][dx] = __ldg(base + static_cast<int64_t>(yy * p.wp + xx) * p.tok_stride + c);
+      }
+    float g = 0.f;
+    for (int y = ylo; y <= yhi; ++y) {
+      int y0, y1;
+      float hl0, hl1;
+      const float wy = tap_weight(p.scale_h, y, p.hp, py, y0, y1, hl0, hl1);
+      if (wy == 0.f) continue;
+      const int r0 = y0 - (py - 1), r1 = y1 - (py - 1);
+      for (int x = xlo; x <= xhi; ++x) {
+        int x0, x1;
+        float wl0, wl1;
+        const float wx = tap_weight(p.scale_w, x, p.wp, px, x0, x1, wl0, wl1);
+        if (wx == 0.f) continue;
+        const int64_t pix = (static_cast<int64_t>(b) * p.h + y) * p.w + x;
+        const int64_t t = p.target[pix];
+        if (t < 0 || t >= p.C) continue;
+        const int q0 = x0 - (px - 1), q1 = x1 - (px - 1);
+        // r*, q* are in [0,2] whenever the weight is non-zero; select without dynamic register indexing
+        float v00, v01, v10, v11;
+        {
+          const float a0 = r0 == 0 ? nb[0][0] : (r0 == 1 ? nb[1][0] : nb[2][0]);
+          const float a1 = r0 == 0 ? nb[0][1] : (r0 == 1 ? nb[1][1] : nb[2][1]);
+          const float a2 = r0 == 0 ? nb[0][2] : (r0 == 1 ? nb[1][2] : nb[2][2]);
+          const float c0 = r1 == 0 ? nb[0][0] : (r1 == 1 ? nb[1][0] : nb[2][0]);
+          const float c1 = r1 == 0 ? nb[0][1] : (r1 == 1 ? nb[1][1] : nb[2][1]);
+          const float c2 = r1 == 0 ? nb[0][2] : (r1 == 1 ? nb[1][2] : nb[2][2]);
+          v00 = q0 == 0 ? a0 : (q0 == 1 ? a1 : a2);
+          v01 = q1 == 0 ? a0 : (q1 == 1 ? a1 : a2);
+          v10 = q0 == 0 ? c0 : (q0 == 1 ? c1 : c2);
+          v11 = q1 == 0 ? c0 : (q1 == 1 ? c1 : c2);
+        }
+        const float top = __fadd_rn(__fmul_rn(wl0, v00), __fmul_rn(wl1, v01));
+        const float bot = __fadd_rn(__fmul_rn(wl0, v10), __fmul_rn(wl1, v11));
+        const float v = __fadd_rn(__fmul_rn(hl0, top), __fmul_rn(hl1, bot));
+        const float prob = __expf(v - p.lse[pix]);
+        g += wy * wx * (prob - (t == c ? 1.f - p.eps : 0.f) - uni);
+      }
+    }
+    drow[c] = __float2bfloat16_rn(g * inv_cnt);
+  }
+}
+
 }  // namespace sgf
 
 using namespace sgf;
+
+extern "C" int sgf_upsample_ce_loss_bwd(const sgf_segloss_bwd_args* a, void* stream) {
+  SGF_REQUIRE(a != nullptr && a->logits && a->target && a->lse && a->count && a->dlogits, "upsample_ce_loss_bwd: null pointer");
+  SGF_REQUIRE(a->B > 0 && a->C > 0 && a->hp > 0 && a->wp > 0 && a->h > 0 && a->w > 0, "upsample_ce_loss_bwd: bad shape");
+  SGF_REQUIRE(a->d_tok_stride >= a->C && a->d_tokens >= a->hp * a->wp, "upsample_ce_loss_bwd: dlogits too small");
+  SeglossBwdParams p{a->logits, a->batch_stride, a->tok_stride, a->B, a->C, a->hp, a->wp, a->h, a->w, a->target,
+                     a->lse, a->count, a->label_smoothing, a->grad_scale, reinterpret_cast<__nv_bfloat16*>(a->dlogits),
+                     a->d_batch_stride, a->d_tok_stride, a->d_tokens,
+                     static_cast<float>(a->hp) / static_cast<float>(a->h),
+                     static_cast<float>(a->wp) / static_cast<float>(a->w)};
+  int threads = static_cast<int>((a->d_tok_stride + 31) / 32 * 32);
+  if (threads > 256) threads = 256;
+  dim3 grid(a->d_tokens, a->B);
+  upsample_ce_bwd_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
+
 
 extern "C" int sgf_upsample_ce_loss(const sgf_segloss_args* a, void* stream) {
   SGF_REQUIRE(a != nullptr && a->logits && a->target && a->out, "upsample_ce_loss: null pointer");
   SGF_REQUIRE(a->B > 0 && a->C > 0 && a->hp > 0 && a->wp > 0 && a->h > 0 && a->w > 0, "upsample_ce_loss: bad shape");
   SeglossParams p{a->logits, a->batch_stride, a->tok_stride, a->B, a->C, a->hp, a->wp, a->h, a->w, a->target,
                   a->label_smoothing, a->out, static_cast<float>(a->hp) / static_cast<float>(a->h),
-                  static_cast<float>(a->wp) / static_cast<float>(a->w)};
+                  static_cast<float>(a->wp) / static_cast<float>(a->w), a->lse_out};
   dim3 block(256), grid((a->w + 255) / 256, a->h, a->B);
   upsample_ce_loss_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   SGF_CHECK_CUDA(cudaGetLastError());

@@ -1,0 +1,545 @@
+// Training-path row kernels (HBM-bound): adjoint of the fused LayerNorm row kernel, the
+// transpose/cast that produces the operands of the dense adjoints, fused Adam, sum of squares.
+// Same conventions as rowops.cu: one warp per row, rows staged through shared memory with 1-D
+// bulk async copies, 128-bit accesses, warp-shuffle reductions.
+#include "common.cuh"
+
+namespace sgf {
+
+SGF_DEVICE void ld8g(const void* base, int dtype, int64_t elem_off, float (&v)[8]) {
+  if (dtype == SGF_F32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
+    const float4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+}
+SGF_DEVICE void st8g(void* base, int dtype, int64_t elem_off, const float (&v)[8]) {
+  if (dtype == SGF_F32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = u;
+  }
+}
+SGF_DEVICE void ld8s(const uint8_t* row, int dtype, int e, float (&v)[8]) {
+  if (dtype == SGF_F32) {
+    const float4 a = *reinterpret_cast<const float4*>(row + e * 4);
+    const float4 b = *reinterpret_cast<const float4*>(row + e * 4 + 16);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + e * 2);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+}
+
+// d/dx of the erf-GELU (same rational erf as gelu_erf): Phi(x) + x * phi(x)
+SGF_DEVICE float gelu_erf_grad(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = fast_exp2(-1.4426950408889634f * z * z);  // exp(-x^2/2)
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
+struct RowLnBwdParams {
+  const void* x; int64_t ldx; int x_dtype;
+  const int64_t* gather_idx;
+  int x_act;
+  const float* pre_add;
+  const float* g1;
+  const void* v; int64_t ldv; int v_dtype;
+  const float* g2;
+  const void* dy2; int64_t ldy2; int dy2_dtype;
+  const float* dv_in; int64_t lddv;
+  float* d_res; int64_t ldres;
+  void* dx; int64_t lddx; int dx_dtype; int dx_accumulate;
+  float* dg1; float* db1; float* dg2; float* db2; float* d_pre_add;
+  int rows, D;
+  int seg_len, seg_stride, seg_off;
+};
+
+__global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdParams p, const int x_bytes,
+                                                                const int v_bytes, const int dy_bytes,
+                                                                const int dv_bytes, const int n_acc) {
+  pdl_trigger();
+  const int kRows = blockDim.x >> 5;
+  extern __shared__ __align__(128) uint8_t bsm[];
+  uint8_t* xbuf = bsm;
+  uint8_t* vbuf = xbuf + kRows * x_bytes;
+  uint8_t* dybuf = vbuf + kRows * v_bytes;
+  uint8_t* dvbuf = dybuf + kRows * dy_bytes;
+  float* acc = reinterpret_cast<float*>(dvbuf + kRows * dv_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(acc + static_cast<size_t>(n_acc) * p.D);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int D = p.D;
+
+  int na = 0;
+  float* a_g2 = p.dg2 ? acc + (na++) * D : nullptr;
+  float* a_b2 = p.db2 ? acc + (na++) * D : nullptr;
+  float* a_g1 = p.dg1 ? acc + (na++) * D : nullptr;
+  float* a_b1 = p.db1 ? acc + (na++) * D : nullptr;
+  float* a_pa = p.d_pre_add ? acc + (na++) * D : nullptr;
+  for (int i = threadIdx.x; i < n_acc * D; i += blockDim.x) acc[i] = 0.f;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+
+  const int xs = p.x_dtype == SGF_F32 ? 4 : 2, vs = p.v_dtype == SGF_F32 ? 4 : 2, ys = p.dy2_dtype == SGF_F32 ? 4 : 2;
+  const float invD = 1.0f / static_cast<float>(D);
+  const int nchunk = D >> 3;
+  const int ngroups = (p.rows + kRows - 1) / kRows;
+  uint32_t phase = 0;
+
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x, phase ^= 1u) {
+    const int row0 = g * kRows;
+    const int nrows = min(kRows, p.rows - row0);
+    const int row = row0 + warp;
+    const bool live = warp < nrows;
+    int64_t dst_row = row;
+    if (p.seg_len > 0) dst_row = static_cast<int64_t>(row / p.seg_len) * p.seg_stride + p.seg_off + row % p.seg_len;
+    const int64_t src_row = (live && p.gather_idx) ? p.gather_idx[row] : row;
+    if (threadIdx.x == 0)
+      mbar_expect_tx(bar, nrows * (x_bytes + v_bytes + dy_bytes + (p.dv_in ? dv_bytes : 0)));
+    __syncthreads();
+    if (live && lane == 0) {
+      if (x_bytes)
+        bulk_load_1d(xbuf + warp * x_bytes, reinterpret_cast<const uint8_t*>(p.x) + src_row * p.ldx * xs, x_bytes, bar);
+      if (v_bytes)
+        bulk_load_1d(vbuf + warp * v_bytes, reinterpret_cast<const uint8_t*>(p.v) + dst_row * p.ldv * vs, v_bytes, bar);
+      if (dy_bytes)
+        bulk_load_1d(dybuf + warp * dy_bytes, reinterpret_cast<const uint8_t*>(p.dy2) + dst_row * p.ldy2 * ys, dy_bytes,
+                     bar);
+      if (p.dv_in)
+        bulk_load_1d(dvbuf + warp * dv_bytes, reinterpret_cast<const uint8_t*>(p.dv_in) + dst_row * p.lddv * 4, dv_bytes,
+                     bar);
+    }
+    mbar_wait(bar, phase);
+    if (live) {
+      const uint8_t* xr = xbuf + warp * x_bytes;
+      const uint8_t* vr = vbuf + warp * v_bytes;
+      const uint8_t* dyr = dybuf + warp * dy_bytes;
+      float* dvr = reinterpret_cast<float*>(dvbuf + warp * dv_bytes);
+
+      auto load_t = [&](int c, float (&t)[8]) {
+        ld8s(xr, p.x_dtype, c * 8, t);
+        if (p.x_act == SGF_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = gelu_erf(t[j]);
+        }
+        if (p.pre_add) {
+          float a[8];
+          ld8g(p.pre_add, SGF_F32, c * 8, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] += a[j];
+        }
+      };
+      auto load_v = [&](int c, float (&v)[8]) {
+        if (v_bytes) ld8s(vr, p.v_dtype, c * 8, v);
+        else load_t(c, v);
+      };
+      auto finalize = [&](int c, float (&dt)[8]) {
+        if (a_pa) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(a_pa + c * 8 + j, dt[j]);
+        }
+        if (p.dx) {
+          if (p.x_act == SGF_ACT_GELU) {
+            float xv[8];
+            ld8s(xr, p.x_dtype, c * 8, xv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dt[j] *= gelu_erf_grad(xv[j]);
+          }
+          const int64_t off = src_row * p.lddx + c * 8;
+          if (p.dx_accumulate) {
+            float o[8];
+            ld8g(p.dx, p.dx_dtype, off, o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dt[j] += o[j];
+          }
+          st8g(p.dx, p.dx_dtype, off, dt);
+        }
+      };
+
+      // ---- LayerNorm 2 adjoint: statistics of v, then the two row means ----
+      float mean2 = 0.f, rstd2 = 1.f, c1 = 0.f, c2 = 0.f;
+      if (p.g2 && dy_bytes) {
+        float s = 0.f;
+        for (int c = lane; c < nchunk; c += 32) {
+          float v[8];
+          load_v(c, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s += v[j];
+        }
+        mean2 = warp_sum(s) * invD;
+        float q = 0.f;
+        for (int c = lane; c < nchunk; c += 32) {
+          float v[8];
+          load_v(c, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = v[j] - mean2;
+            q += d * d;
+          }
+        }
+        rstd2 = rsqrtf(warp_sum(q) * invD + 1e-5f);
+        float a = 0.f, b = 0.f;
+        for (int c = lane; c < nchunk; c += 32) {
+          float v[8], dy[8], gm[8];
+          load_v(c, v);
+          ld8s(dyr, p.dy2_dtype, c * 8, dy);
+          ld8g(p.g2, SGF_F32, c * 8, gm);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float gy = dy[j] * gm[j];
+            a += gy;
+            b += gy * (v[j] - mean2) * rstd2;
+          }
+        }
+        c1 = warp_sum(a) * invD;
+        c2 = warp_sum(b) * invD;
+      }
+      // ---- dv = dv_in + LN2'(dy2) ----
+      for (int c = lane; c < nchunk; c += 32) {
+        float dv[8];
+        if (p.dv_in) {
+          ld8s(reinterpret_cast<const uint8_t*>(dvr), SGF_F32, c * 8, dv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dv[j] = 0.f;
+        }
+        if (dy_bytes) {
+          float dy[8];
+          ld8s(dyr, p.dy2_dtype, c * 8, dy);
+          if (p.g2) {
+            float v[8], gm[8];
+            load_v(c, v);
+            ld8g(p.g2, SGF_F32, c * 8, gm);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float xh = (v[j] - mean2) * rstd2;
+              dv[j] += rstd2 * (dy[j] * gm[j] - c1 - xh * c2);
+              if (a_g2) atomicAdd(a_g2 + c * 8 + j, dy[j] * xh);
+              if (a_b2) atomicAdd(a_b2 + c * 8 + j, dy[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dv[j] += dy[j];
+          }
+        }
+        if (p.d_res) st8g(p.d_res, SGF_F32, dst_row * p.ldres + c * 8, dv);
+        if (!p.g1) {
+          finalize(c, dv);
+        } else {
+          *reinterpret_cast<float4*>(dvr + c * 8) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+          *reinterpret_cast<float4*>(dvr + c * 8 + 4) = make_float4(dv[4], dv[5], dv[6], dv[7]);
+        }
+      }
+      // ---- LayerNorm 1 adjoint ----
+      if (p.g1) {
+        float s = 0.f;
+        for (int c = lane; c < nchunk; c += 32) {
+          float t[8];
+          load_t(c, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s += t[j];
+        }
+        const float mean1 = warp_sum(s) * invD;
+        float q = 0.f;
+        for (int c = lane; c < nchunk; c += 32) {
+          float t[8];
+          load_t(c, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = t[j] - mean1;
+            q += d * d;
+          }
+        }
+        const float rstd1 = rsqrtf(warp_sum(q) * invD + 1e-5f);
+        float a = 0.f, b = 0.f;
+        for (int c = lane; c < nchunk; c += 32) {
+          float t[8], dv[8], gm[8];
+          load_t(c, t);
+          ld8s(reinterpret_cast<const uint8_t*>(dvr), SGF_F32, c * 8, dv);
+          ld8g(p.g1, SGF_F32, c * 8, gm);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float gy = dv[j] * gm[j];
+            a += gy;
+            b += gy * (t[j] - mean1) * rstd1;
+          }
+        }
+        const float d1 = warp_sum(a) * invD, d2 = warp_sum(b) * invD;
+        for (int c = lane; c < nchunk; c += 32) {
+          float t[8], dv[8], gm[8], dt[8];
+          load_t(c, t);
+          ld8s(reinterpret_cast<const uint8_t*>(dvr), SGF_F32, c * 8, dv);
+          ld8g(p.g1, SGF_F32, c * 8, gm);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float th = (t[j] - mean1) * rstd1;
+            dt[j] = rstd1 * (dv[j] * gm[j] - d1 - th * d2);
+            if (a_g1) atomicAdd(a_g1 + c * 8 + j, dv[j] * th);
+            if (a_b1) atomicAdd(a_b1 + c * 8 + j, dv[j]);
+          }
+          finalize(c, dt);
+        }
+      }
+    }
+    fence_proxy_async();  // generic-proxy accesses to the staging rows are ordered before the next bulk loads
+    __syncthreads();
+  }
+  // ---- flush the per-CTA parameter-gradient partials ----
+  na = 0;
+  float* outs[5];
+  if (p.dg2) outs[na++] = p.dg2;
+  if (p.db2) outs[na++] = p.db2;
+  if (p.dg1) outs[na++] = p.dg1;
+  if (p.db1) outs[na++] = p.db1;
+  if (p.d_pre_add) outs[na++] = p.d_pre_add;
+  for (int a = 0; a < na; ++a)
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      const float v = acc[a * D + i];
+      if (v != 0.f) atomicAdd(outs[a] + i, v);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// transpose + cast (+ column sums)
+// ----------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const TIn* __restrict__ in, int64_t ld_in, int M, int N,
+                                                             __nv_bfloat16* __restrict__ out_t, int64_t ld_t,
+                                                             __nv_bfloat16* __restrict__ out_c, int64_t ld_c,
+                                                             float* __restrict__ colsum) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64][72];  // [n][m]
+  __shared__ float csum[64];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  if (colsum && tid < 64) csum[tid] = 0.f;
+  if (colsum) __syncthreads();
+  const int cg = tid & 7, rr = tid >> 3;
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int ml = rr + 32 * i;
+    const int m = m0 + ml, n = n0 + cg * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (m < M && n < N) {
+      const TIn* src = in + static_cast<int64_t>(m) * ld_in + n;
+      if (n + 8 <= N) {
+        ld8g(in, sizeof(TIn) == 4 ? SGF_F32 : SGF_BF16, static_cast<int64_t>(m) * ld_in + n, v);
+      } else {
+        for (int j = 0; j < N - n; ++j) v[j] = static_cast<float>(src[j]);
+      }
+      if (out_c) {
+        if (n + 8 <= N) st8g(out_c, SGF_BF16, static_cast<int64_t>(m) * ld_c + n, v);
+        else
+          for (int j = 0; j < N - n; ++j) out_c[static_cast<int64_t>(m) * ld_c + n + j] = __float2bfloat16_rn(v[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      tile[cg * 8 + j][ml] = __float2bfloat16_rn(v[j]);
+      cs[j] += v[j];
+    }
+  }
+  if (colsum) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&csum[cg * 8 + j], cs[j]);
+  }
+  __syncthreads();
+  if (out_t) {
+    const int m_end = (M + 7) & ~7;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int nl = rr + 32 * i;
+      const int n = n0 + nl, m = m0 + cg * 8;
+      if (n < N && m < m_end)
+        *reinterpret_cast<uint4*>(out_t + static_cast<int64_t>(n) * ld_t + m) = *reinterpret_cast<const uint4*>(&tile[nl][cg * 8]);
+    }
+  }
+  if (colsum && tid < 64 && n0 + tid < N) atomicAdd(colsum + n0 + tid, csum[tid]);
+}
+
+// ----------------------------------------------------------------------------------------
+// fused Adam(W) over a flat fp32 buffer; sum of squares
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                                                        float b1, float b2, float eps, float wd, float bc1, float bc2,
+                                                        const float* __restrict__ grad_scale) {
+  const float gs = grad_scale ? grad_scale[0] : 1.0f;
+  const int64_t i0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
+  if (i0 >= n) return;
+  if (i0 + 4 <= n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i0);
+    const float4 gg = *reinterpret_cast<const float4*>(g + i0);
+    float4 mm = *reinterpret_cast<float4*>(m + i0), vv = *reinterpret_cast<float4*>(v + i0);
+    float* P = &pp.x; const float* G = &gg.x; float* Mo = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = G[j] * gs;
+      Mo[j] = b1 * Mo[j] + (1.f - b1) * gr;
+      V[j] = b2 * V[j] + (1.f - b2) * gr * gr;
+      const float den = sqrtf(V[j]) / bc2 + eps;  // bc2 = sqrt(1 - beta2^t)
+      P[j] = P[j] - lr * wd * P[j] - (lr / bc1) * (Mo[j] / den);
+    }
+    *reinterpret_cast<float4*>(p + i0) = pp;
+    *reinterpret_cast<float4*>(m + i0) = mm;
+    *reinterpret_cast<float4*>(v + i0) = vv;
+  } else {
+    for (int64_t i = i0; i < n; ++i) {
+      const float gr = g[i] * gs;
+      m[i] = b1 * m[i] + (1.f - b1) * gr;
+      v[i] = b2 * v[i] + (1.f - b2) * gr * gr;
+      const float den = sqrtf(v[i]) / bc2 + eps;
+      p[i] = p[i] - lr * wd * p[i] - (lr / bc1) * (m[i] / den);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int64_t i = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x * 4) {
+    if (i + 4 <= n) {
+      const float4 a = *reinterpret_cast<const float4*>(x + i);
+      s += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    } else {
+      for (int64_t j = i; j < n; ++j) s += x[j] * x[j];
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+
+}  // namespace sgf
+
+using namespace sgf;
+
+extern "C" int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* a, void* stream) {
+  SGF_REQUIRE(a != nullptr, "row_layernorm_bwd: null args");
+  SGF_REQUIRE(a->rows > 0 && a->D > 0 && a->D % 8 == 0 && a->D <= 8192, "row_layernorm_bwd: bad D=%d rows=%d", a->D,
+              a->rows);
+  SGF_REQUIRE(a->dy2 || a->dv_in, "row_layernorm_bwd: no incoming gradient");
+  SGF_REQUIRE(!a->g2 || a->dy2, "row_layernorm_bwd: g2 without dy2");
+  SGF_REQUIRE(a->v || (!a->g1), "row_layernorm_bwd: v == NULL requires no LN1 (v = t)");
+  const bool x_used = a->g1 || a->x_act || (a->g2 && !a->v);
+  SGF_REQUIRE(!x_used || a->x, "row_layernorm_bwd: x is required for this operand combination");
+  SGF_REQUIRE(!a->dx || a->lddx % 8 == 0, "row_layernorm_bwd: lddx must be a multiple of 8");
+  const int xs = a->x_dtype == SGF_F32 ? 4 : 2, vs = a->v_dtype == SGF_F32 ? 4 : 2, ys = a->dy2_dtype == SGF_F32 ? 4 : 2;
+  const int x_bytes = x_used ? a->D * xs : 0;
+  const int v_bytes = (a->v && a->g2) ? a->D * vs : 0;
+  const int dy_bytes = a->dy2 ? a->D * ys : 0;
+  const int dv_bytes = (a->dv_in || a->g1) ? a->D * 4 : 0;
+  if (x_bytes)
+    SGF_REQUIRE(reinterpret_cast<uintptr_t>(a->x) % 16 == 0 && (a->ldx * xs) % 16 == 0, "row_layernorm_bwd: x alignment");
+  if (v_bytes)
+    SGF_REQUIRE(reinterpret_cast<uintptr_t>(a->v) % 16 == 0 && (a->ldv * vs) % 16 == 0, "row_layernorm_bwd: v alignment");
+  if (dy_bytes)
+    SGF_REQUIRE(reinterpret_cast<uintptr_t>(a->dy2) % 16 == 0 && (a->ldy2 * ys) % 16 == 0,
+                "row_layernorm_bwd: dy2 alignment");
+  if (a->dv_in)
+    SGF_REQUIRE(reinterpret_cast<uintptr_t>(a->dv_in) % 16 == 0 && (a->lddv * 4) % 16 == 0,
+                "row_layernorm_bwd: dv_in alignment");
+  const int n_acc = (a->dg2 ? 1 : 0) + (a->db2 ? 1 : 0) + (a->dg1 ? 1 : 0) + (a->db1 ? 1 : 0) + (a->d_pre_add ? 1 : 0);
+  const int per_row = x_bytes + v_bytes + dy_bytes + dv_bytes;
+  const int fixed = n_acc * a->D * 4 + 16;
+  int kRows = 8;
+  while (kRows > 1 && kRows * per_row + fixed > 100 * 1024) kRows >>= 1;
+  const int smem = kRows * per_row + fixed;
+  SGF_REQUIRE(smem <= 200 * 1024, "row_layernorm_bwd: D=%d needs %d B of shared memory", a->D, smem);
+  RowLnBwdParams p{a->x, a->ldx, a->x_dtype, a->gather_idx, a->x_act, a->pre_add, a->g1, a->v, a->ldv, a->v_dtype,
+                   a->g2, a->dy2, a->ldy2, a->dy2_dtype, a->dv_in, a->lddv, a->d_res, a->ldres, a->dx, a->lddx,
+                   a->dx_dtype, a->dx_accumulate, a->dg1, a->db1, a->dg2, a->db2, a->d_pre_add, a->rows, a->D,
+                   a->seg_len, a->seg_stride, a->seg_off};
+  static bool configured = false;
+  if (!configured) {
+    SGF_CHECK_CUDA(cudaFuncSetAttribute(row_layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  const int ngroups = (a->rows + kRows - 1) / kRows;
+  const int per_sm = smem > 110 * 1024 ? 1 : 2;
+  const int grid = ngroups < 148 * per_sm ? ngroups : 148 * per_sm;
+  SGF_CHECK_CUDA(launch_pdl(row_layernorm_bwd_kernel, dim3(grid), dim3(kRows * 32), static_cast<size_t>(smem),
+                            reinterpret_cast<cudaStream_t>(stream), p, x_bytes, v_bytes, dy_bytes, dv_bytes, n_acc));
+  count_launch();
+  return SGF_OK;
+}
+
+extern "C" int sgf_transpose_cast(const void* in, int32_t in_dtype, int64_t ld_in, int32_t M, int32_t N, void* out_t,
+                                  int64_t ld_t, void* out_c, int64_t ld_c, float* colsum, void* stream) {
+  SGF_REQUIRE(in && M > 0 && N > 0 && (out_t || out_c || colsum), "transpose_cast: bad arguments");
+  const int es = in_dtype == SGF_F32 ? 4 : 2;
+  SGF_REQUIRE(reinterpret_cast<uintptr_t>(in) % 16 == 0 && (ld_in * es) % 16 == 0, "transpose_cast: input alignment");
+  SGF_REQUIRE(!out_t || (ld_t % 8 == 0 && ld_t >= ((M + 7) & ~7) && reinterpret_cast<uintptr_t>(out_t) % 16 == 0),
+              "transpose_cast: ld_t must be a multiple of 8 and >= M rounded up to 8");
+  SGF_REQUIRE(!out_c || (ld_c % 8 == 0 && ld_c >= N && reinterpret_cast<uintptr_t>(out_c) % 16 == 0),
+              "transpose_cast: ld_c must be a multiple of 8 and >= N");
+  dim3 grid((N + 63) / 64, (M + 63) / 64), block(256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (in_dtype == SGF_F32)
+    transpose_cast_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(in), ld_in, M, N,
+                                                         reinterpret_cast<__nv_bfloat16*>(out_t), ld_t,
+                                                         reinterpret_cast<__nv_bfloat16*>(out_c), ld_c, colsum);
+  else
+    transpose_cast_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld_in, M, N,
+                                                                 reinterpret_cast<__nv_bfloat16*>(out_t), ld_t,
+                                                                 reinterpret_cast<__nv_bfloat16*>(out_c), ld_c, colsum);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
+
+extern "C" int sgf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                             const float* grad_scale, void* stream) {
+  SGF_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step > 0, "adam_step: bad arguments");
+  SGF_REQUIRE((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+               reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) % 16 == 0,
+              "adam_step: buffers must be 16-byte aligned");
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  const float bc2 = sqrtf(1.0f - powf(beta2, static_cast<float>(step)));
+  const int64_t threads = (n + 3) / 4;
+  adam_step_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
+
+extern "C" int sgf_sumsq(const float* x, int64_t n, float* out, void* stream) {
+  SGF_REQUIRE(x && out && n > 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0, "sumsq: bad arguments");
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n, out);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}

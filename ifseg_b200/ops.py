@@ -179,7 +179,7 @@ def maxpool3x3s2(x):
 
 def row_layernorm(x, *, rows=None, D=None, ldx=None, gather_idx=None, pre_add=None, ln1=None, residual=None,
                   ldr=None, out1=None, ld1=None, ln2=None, out2=None, ld2=None, zero_row=None, seg=None,
-                  clear_rowstats=None):
+                  clear_rowstats=None, x_act=ACT_NONE):
     """See sgf_row_layernorm in include/segofa_b200.h.  ln1/ln2 = (gamma, beta) fp32 tensors."""
     lib = _lib.load()
     _req(x, None, "x")
@@ -195,7 +195,7 @@ def row_layernorm(x, *, rows=None, D=None, ldx=None, gather_idx=None, pre_add=No
         _DT[out1.dtype] if out1 is not None else SGF_BF16,
         _p(ln2[0]) if ln2 else None, _p(ln2[1]) if ln2 else None,
         _p(out2), (out2.stride(-2) if ld2 is None else ld2) if out2 is not None else 0,
-        _p(zero_row), rows, D, seg_len, seg_stride, seg_off, _p(clear_rowstats))
+        _p(zero_row), rows, D, seg_len, seg_stride, seg_off, _p(clear_rowstats), int(x_act))
     nb = rows * D * (x.element_size() + (residual.element_size() if residual is not None else 0)
                      + (out1.element_size() if out1 is not None else 0) + (2 if out2 is not None else 0))
     with _timed("row_layernorm", nbytes=float(nb)):
@@ -227,7 +227,7 @@ def build_attn_bias(abs_bias, Tk, blocks=(), out=None, dense_add=None):
 
 
 def attention(q, k, v, out, *, B, H, Tq, Tk, q_strides, k_strides, v_strides, o_strides, bias=None,
-              head_scale=None, key_padding_mask=None, causal=False):
+              head_scale=None, key_padding_mask=None, causal=False, lse=None):
     """q/k/v/out: bf16 tensors used as base pointers; *_strides = (row_stride, batch_stride) in elements."""
     lib = _lib.load()
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
@@ -238,7 +238,7 @@ def attention(q, k, v, out, *, B, H, Tq, Tk, q_strides, k_strides, v_strides, o_
         _p(q), q_strides[0], q_strides[1], _p(k), k_strides[0], k_strides[1], _p(v), v_strides[0], v_strides[1],
         _p(out), o_strides[0], o_strides[1],
         _p(bias), bias.stride(0) if bias is not None else 0, bias.stride(1) if bias is not None else 0,
-        _p(head_scale), _p(key_padding_mask), B, H, Tq, Tk, 1 if causal else 0)
+        _p(head_scale), _p(key_padding_mask), B, H, Tq, Tk, 1 if causal else 0, _p(lse))
     pairs = Tq * Tk if not causal else Tq * (Tq + 1) / 2.0
     with _timed("attention_tcgen05", 4.0 * B * H * pairs * 64):
         _lib.check(lib.sgf_attention_bf16(C.byref(args), _stream()), "sgf_attention_bf16")
@@ -281,7 +281,7 @@ def embedding_bag_mean(tokens, ends, table, P):
     return out
 
 
-def upsample_ce_loss(logits, target, hp, wp, label_smoothing=0.0):
+def upsample_ce_loss(logits, target, hp, wp, label_smoothing=0.0, lse_out=None, raw=False):
     """mean pixel cross-entropy of the bilinearly upsampled logits (fp32 [B,>=hp*wp,C]) against
     target int64 [B,h,w] class ids (ids outside [0,C) are ignored).  Returns (loss 0-dim, count 0-dim)."""
     lib = _lib.load()
@@ -290,7 +290,106 @@ def upsample_ce_loss(logits, target, hp, wp, label_smoothing=0.0):
     B, h, w = target.shape
     acc = torch.zeros(2, dtype=torch.float32, device=logits.device)
     args = _lib.SeglossArgs(_p(logits), logits.stride(0), logits.stride(1), B, logits.shape[2], hp, wp, h, w,
-                            _p(target), float(label_smoothing), _p(acc))
+                            _p(target), float(label_smoothing), _p(acc), _p(lse_out))
     with _timed("upsample_ce", nbytes=float(target.numel() * 8)):
         _lib.check(lib.sgf_upsample_ce_loss(C.byref(args), _stream()), "sgf_upsample_ce_loss")
+    if raw:
+        return acc
     return acc[0] / acc[1], acc[1]
+
+
+# ----------------------------------------------------------------------------------------
+# training path (adjoint kernels)
+# ----------------------------------------------------------------------------------------
+def upsample_ce_loss_bwd(logits, target, lse, count, hp, wp, dlogits, label_smoothing=0.0, grad_scale=1.0):
+    """dlogits bf16 [B, tokens, ld] <- d(mean pixel CE)/d(low-res logits) * grad_scale; count = device scalar."""
+    lib = _lib.load()
+    _req(logits, torch.float32, "logits")
+    _req(target, torch.int64, "target")
+    _req(lse, torch.float32, "lse")
+    _req(dlogits, torch.bfloat16, "dlogits")
+    B, h, w = target.shape
+    args = _lib.SeglossBwdArgs(_p(logits), logits.stride(0), logits.stride(1), B, logits.shape[2], hp, wp, h, w,
+                               _p(target), _p(lse), _p(count), float(label_smoothing), float(grad_scale),
+                               _p(dlogits), dlogits.stride(0), dlogits.stride(1), dlogits.shape[1])
+    with _timed("upsample_ce_bwd", nbytes=float(target.numel() * 12)):
+        _lib.check(lib.sgf_upsample_ce_loss_bwd(C.byref(args), _stream()), "sgf_upsample_ce_loss_bwd")
+    return dlogits
+
+
+def row_layernorm_bwd(*, rows, D, x=None, ldx=None, gather_idx=None, x_act=ACT_NONE, pre_add=None, g1=None, v=None,
+                      g2=None, dy2=None, dv_in=None, d_res=None, dx=None, dx_accumulate=False, dg1=None, db1=None,
+                      dg2=None, db2=None, d_pre_add=None, seg=None):
+    """Adjoint of row_layernorm (see sgf_row_layernorm_bwd in include/segofa_b200.h)."""
+    lib = _lib.load()
+    seg_len, seg_stride, seg_off = seg if seg is not None else (0, 0, 0)
+
+    def ld(t):
+        return t.stride(-2) if t is not None else 0
+
+    def dt(t):
+        return _DT[t.dtype] if t is not None else SGF_BF16
+
+    args = _lib.RowLnBwdArgs(
+        _p(x), ld(x) if ldx is None else ldx, dt(x), _p(gather_idx), int(x_act), _p(pre_add), _p(g1),
+        _p(v), ld(v), dt(v), _p(g2), _p(dy2), ld(dy2), dt(dy2), _p(dv_in), ld(dv_in), _p(d_res), ld(d_res),
+        _p(dx), ld(dx), dt(dx), 1 if dx_accumulate else 0, _p(dg1), _p(db1), _p(dg2), _p(db2), _p(d_pre_add),
+        rows, D, seg_len, seg_stride, seg_off)
+    nb = rows * D * sum(t.element_size() for t in (x, v, dy2, dv_in, d_res, dx) if t is not None)
+    with _timed("row_layernorm_bwd", nbytes=float(nb)):
+        _lib.check(lib.sgf_row_layernorm_bwd(C.byref(args), _stream()), "sgf_row_layernorm_bwd")
+
+
+def transpose_cast(x, M=None, N=None, out_t=None, out_c=None, colsum=None, want_t=True):
+    """x [M,N] fp32/bf16 (row stride x.stride(0)) -> out_t bf16 [N, pad8(M)] (and/or out_c bf16 [M,N], colsum fp32 [N] +=)."""
+    lib = _lib.load()
+    _req(x, None, "x")
+    M = x.shape[0] if M is None else M
+    N = x.shape[1] if N is None else N
+    if out_t is None and want_t:
+        out_t = torch.empty((N, (M + 7) // 8 * 8), dtype=torch.bfloat16, device=x.device)
+    with _timed("transpose_cast", nbytes=float(M * N * (x.element_size() + 2))):
+        _lib.check(lib.sgf_transpose_cast(_p(x), _DT[x.dtype], x.stride(0), M, N, _p(out_t),
+                                          out_t.stride(0) if out_t is not None else 0, _p(out_c),
+                                          out_c.stride(0) if out_c is not None else 0, _p(colsum), _stream()),
+                   "sgf_transpose_cast")
+    return out_t
+
+
+def attention_bwd(q, k, v, out, dout, dq, dk, dv, *, B, H, Tq, Tk, q_strides, k_strides, v_strides, o_strides,
+                  do_strides, dq_strides, dk_strides, dv_strides, lse, delta, bias=None, head_scale=None,
+                  d_head_scale=None, key_padding_mask=None, causal=False, dq_scale=1.0):
+    lib = _lib.load()
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (dout, "dout"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
+        _req(t, torch.bfloat16, n)
+    _req(lse, torch.float32, "lse")
+    _req(delta, torch.float32, "delta")
+    args = _lib.AttentionBwdArgs(
+        _p(q), q_strides[0], q_strides[1], _p(k), k_strides[0], k_strides[1], _p(v), v_strides[0], v_strides[1],
+        _p(out), o_strides[0], o_strides[1], _p(dout), do_strides[0], do_strides[1],
+        _p(dq), dq_strides[0], dq_strides[1], _p(dk), dk_strides[0], dk_strides[1], _p(dv), dv_strides[0], dv_strides[1],
+        _p(bias), bias.stride(0) if bias is not None else 0, bias.stride(1) if bias is not None else 0,
+        _p(head_scale), _p(d_head_scale), _p(key_padding_mask), _p(lse), _p(delta), float(dq_scale),
+        B, H, Tq, Tk, 1 if causal else 0)
+    pairs = Tq * Tk if not causal else Tq * (Tq + 1) / 2.0
+    with _timed("attention_bwd_tcgen05", 10.0 * B * H * pairs * 64):  # 5 algorithmic tile GEMMs
+        _lib.check(lib.sgf_attention_bwd_bf16(C.byref(args), _stream()), "sgf_attention_bwd_bf16")
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1,
+              grad_scale=None):
+    lib = _lib.load()
+    for t, n in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _req(t, torch.float32, n)
+    with _timed("adam", nbytes=float(param.numel() * 28)):
+        _lib.check(lib.sgf_adam_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr),
+                                     float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                     _p(grad_scale), _stream()), "sgf_adam_step")
+
+
+def sumsq(x, out):
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    with _timed("sumsq", nbytes=float(x.numel() * 4)):
+        _lib.check(lib.sgf_sumsq(_p(x), x.numel(), _p(out), _stream()), "sgf_sumsq")
+    return out

@@ -132,6 +132,7 @@ typedef struct {
   int32_t rows, D;
   int32_t seg_len, seg_stride, seg_off;
   float* clear_rowstats; /* optional [rows,2] fp32 scratch zeroed as a side effect (row-stats of a following GEMM) */
+  int32_t x_act;         /* SGF_ACT_GELU: t = gelu(x[r]) (the FFN's gelu -> ffn_layernorm pair of the training path) */
 } sgf_rowln_args;
 int sgf_row_layernorm(const sgf_rowln_args* args, void* stream);
 
@@ -181,6 +182,7 @@ typedef struct {
   const float* head_scale;
   const uint8_t* key_padding_mask;
   int32_t B, H, Tq, Tk, causal;
+  float* lse; /* optional fp32 [B,H,Tq]: log2-domain log-sum-exp of every score row (saved for the backward) */
 } sgf_attention_args;
 int sgf_attention_bf16(const sgf_attention_args* args, void* stream);
 
@@ -230,8 +232,105 @@ typedef struct {
   const int64_t* target;
   float label_smoothing;
   float* out; /* [2] */
+  float* lse_out; /* optional fp32 [B,h,w]: per-pixel logsumexp saved for sgf_upsample_ce_loss_bwd */
 } sgf_segloss_args;
 int sgf_upsample_ce_loss(const sgf_segloss_args* args, void* stream);
+
+/* =======================================================================================
+ * Training path (image-free branch, segofa.py:136-151 + seg_criterion.py:246-267): the
+ * reference gets its backward from autograd over the ATen ops above; the entry points below are
+ * the hand-written adjoint kernels.  Dense adjoints (dX = dY W, dW = dY^T X) reuse sgf_gemm_bf16
+ * on operands transposed by sgf_transpose_cast.
+ * ===================================================================================== */
+
+/* Backward of sgf_upsample_ce_loss w.r.t. the low-resolution logits, gather form (no atomics,
+ * deterministic): one CTA per (sample, patch), one thread per class; the thread walks the pixel
+ * footprint of its patch, re-evaluates its class's interpolated logit, p = exp(v - lse[pixel]),
+ * and accumulates weight * (p - (1-eps)[c == target] - eps/C).  The result is scaled by
+ * grad_scale / count[0] (count = out[1] of the forward, read on the device: no host sync) and
+ * written as bf16 dlogits[b, tok, c] (ld = ld_tok elements per token, batch stride in elements);
+ * columns C..ld_tok-1 and token rows >= hp*wp (the eos slot) are zeroed by the kernel.
+ * Adjoint of seg_criterion.py:237-244 (resize) + :263-267 (F.cross_entropy). */
+typedef struct {
+  const float* logits; int64_t batch_stride; int64_t tok_stride;
+  int32_t B, C, hp, wp, h, w;
+  const int64_t* target;
+  const float* lse;      /* [B,h,w] from the forward */
+  const float* count;    /* device pointer to the number of counted pixels */
+  float label_smoothing; float grad_scale;
+  void* dlogits; int64_t d_batch_stride; int64_t d_tok_stride; int32_t d_tokens; /* bf16 [B, d_tokens, d_tok_stride] */
+} sgf_segloss_bwd_args;
+int sgf_upsample_ce_loss_bwd(const sgf_segloss_bwd_args* args, void* stream);
+
+/* Adjoint of sgf_row_layernorm.  Forward:  t = act(x[src]) (+ pre_add); u = g1 ? LN1(t) : t;
+ * v = u (+ residual) = out1;  out2 = LN2(v).  Given dy2 = dL/d out2 (optional) and dv_in = dL/d out1
+ * flowing in on the residual stream (optional):
+ *     dv   = dv_in + LN2'(dy2; v)            -> d_res (fp32, optional; may alias dv_in)
+ *     dt   = g1 ? LN1'(dv; t) : dv
+ *     dx   = dt * act'(x)                     -> written (or accumulated) at the x row (src)
+ *     dg1,db1,dg2,db2,d_pre_add (fp32 [D]) accumulated with atomics (per-CTA shared partials first).
+ * LayerNorm statistics are recomputed from the saved rows (the row is staged in shared memory
+ * anyway), so the forward saves no (mean, rstd).  v == NULL means v = t (no LN1, no residual).
+ * Replaces autograd of LayerNorm / residual add / GELU at unify_transformer_layer.py:256-291,
+ * 463-568 and the embedding LayerNorms of encoder_module.py:571-602, decoder_module.py:575-576. */
+typedef struct {
+  const void* x; int64_t ldx; int32_t x_dtype;
+  const int64_t* gather_idx;
+  int32_t x_act;
+  const float* pre_add;
+  const float* g1;
+  const void* v; int64_t ldv; int32_t v_dtype;
+  const float* g2;
+  const void* dy2; int64_t ldy2; int32_t dy2_dtype;
+  const float* dv_in; int64_t lddv;
+  float* d_res; int64_t ldres;
+  void* dx; int64_t lddx; int32_t dx_dtype; int32_t dx_accumulate;
+  float* dg1; float* db1; float* dg2; float* db2; float* d_pre_add;
+  int32_t rows, D;
+  int32_t seg_len, seg_stride, seg_off;
+} sgf_rowln_bwd_args;
+int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* args, void* stream);
+
+/* in [M,N] (fp32 or bf16, row stride ld_in) -> out_t bf16 [N, ld_t >= M] (transposed; columns
+ * M..ld_t-1 zero-filled up to the next multiple of 8), optional out_c bf16 [M, ld_c] (plain cast
+ * copy), optional colsum fp32 [N] += sum_m in[m,n] (bias gradients).  Produces the operands of
+ * the dense adjoints: W^T for dX = dY W, and dY^T / X^T for dW = dY^T X. */
+int sgf_transpose_cast(const void* in, int32_t in_dtype, int64_t ld_in, int32_t M, int32_t N, void* out_t,
+                       int64_t ld_t, void* out_c, int64_t ld_c, float* colsum, void* stream);
+
+/* Backward of sgf_attention_bf16 (same operand addressing).  Three kernels:
+ *   delta[b,h,i] = sum_d dout[b,i,h,d] * out[b,i,h,d]   (+ d_head_scale[h] += delta / head_scale[h])
+ *   dQ  : CTA per (128 queries, head, batch): S = Q K^T and dP = dO V^T on tcgen05 into TMEM,
+ *         P = exp2(S + bias - lse), dS = P (head_scale dP - delta) -> bf16 smem, dQ += dS K (TMEM)
+ *   dKdV: CTA per (128 keys, head, batch): S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q
+ * dq is multiplied by dq_scale (the q pre-scaling of the QKV epilogue).  The gradient w.r.t. the
+ * additive position bias is NOT produced.  delta: fp32 scratch [B,H,Tq]. */
+typedef struct {
+  const void* q; int64_t q_row_stride; int64_t q_batch_stride;
+  const void* k; int64_t k_row_stride; int64_t k_batch_stride;
+  const void* v; int64_t v_row_stride; int64_t v_batch_stride;
+  const void* out; int64_t o_row_stride; int64_t o_batch_stride;
+  const void* dout; int64_t do_row_stride; int64_t do_batch_stride;
+  void* dq; int64_t dq_row_stride; int64_t dq_batch_stride;
+  void* dk; int64_t dk_row_stride; int64_t dk_batch_stride;
+  void* dv; int64_t dv_row_stride; int64_t dv_batch_stride;
+  const float* bias; int64_t bias_head_stride; int64_t bias_row_stride;
+  const float* head_scale; float* d_head_scale;
+  const uint8_t* key_padding_mask;
+  const float* lse; float* delta;
+  float dq_scale;
+  int32_t B, H, Tq, Tk, causal;
+} sgf_attention_bwd_args;
+int sgf_attention_bwd_bf16(const sgf_attention_bwd_args* args, void* stream);
+
+/* Multi-tensor-free fused Adam(W) step over one flat fp32 master buffer (cf/optim/adam.py, fp32
+ * master weights of cf/optim/fp16_optimizer.py:108-222): p -= lr*(m_hat/(sqrt(v_hat)+eps) + wd*p)
+ * with grads scaled by grad_scale[0] (device scalar: 1/sample_size * clip coefficient). */
+int sgf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int32_t step, const float* grad_scale,
+                  void* stream);
+/* out[0] += sum of squares of x[0..n) (gradient-norm for clip_grad_norm, trainer.py:886) */
+int sgf_sumsq(const float* x, int64_t n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == bound, declared ^ bound
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.sgf_abi_version() == 2
+    assert lib.sgf_abi_version() == 3
     assert lib.sgf_launch_count() == 0
 
 
@@ -42,7 +42,9 @@ def test_struct_layouts_match_the_header(tmp_path):
 
     structs = {"sgf_gemm_args": _lib.GemmArgs, "sgf_conv3x3_args": _lib.Conv3x3Args, "sgf_rowln_args": _lib.RowLnArgs,
                "sgf_relblock": _lib.RelBlock, "sgf_bias_args": _lib.BiasArgs, "sgf_attention_args": _lib.AttentionArgs,
-               "sgf_segmask_args": _lib.SegmaskArgs}
+               "sgf_segmask_args": _lib.SegmaskArgs, "sgf_segloss_args": _lib.SeglossArgs,
+               "sgf_segloss_bwd_args": _lib.SeglossBwdArgs, "sgf_rowln_bwd_args": _lib.RowLnBwdArgs,
+               "sgf_attention_bwd_args": _lib.AttentionBwdArgs}
     src = open(HEADER).read()
     prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     expect = {}
