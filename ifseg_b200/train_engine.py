@@ -1,0 +1,540 @@
+"""Training step of the image-free branch on one B200: forward with saved activations + hand-written
+backward, as a flat sequence of C-ABI kernel launches (no autograd graph).
+
+Reference call stack: SegCriterion.forward (criterions/seg_criterion.py:165-193) ->
+SegOFAModel.forward aux branch (models/segofa/segofa.py:136-151) -> encode_with_artificial_image
+(encoder_module.py:499-675) -> surrogate decoder (decoder_module.py:486-677) -> compute_imfree_loss
+(seg_criterion.py:246-267) -> optimizer.backward (autograd).  Here:
+
+  * every trainable parameter lives in ONE flat fp32 master buffer (`arena.flat32`; the nn.Parameters are
+    views into it, so state_dict / checkpoints / external optimizers keep working) with a parallel flat fp32
+    gradient buffer (`param.grad` are views into it: a DDP-style all-reduce is one collective over a
+    contiguous range) and flat Adam moments;
+  * q/k/v weights of an attention (and the k/v weights of ALL decoder cross-attentions) are adjacent in the
+    arena, so the fused [3D,D] / [L*2D,D] GEMM operands and their gradients are plain views;
+  * per step every weight matrix is cast to bf16 and transposed once (`sgf_transpose_cast`): W for the forward
+    GEMM and dW = dY^T X, W^T for dX = dY W;
+  * activations needed by the adjoints are kept (4-5 GB at cfg 3: nothing is recomputed except LayerNorm
+    statistics, GELU and the attention probabilities); the residual-stream gradient is one fp32 buffer per
+    stack updated in place.
+
+Round-1 limits: dropout / DropPath are off (deterministic, eval-mode numerics -- the gradient-parity
+configuration of SURVEY.md s8d); no gradient is produced for the parameters that only feed the additive
+position bias (pos/rel-pos tables, pos_q/k projections, pos LayerNorms) -- their .grad
+stays None and they are not updated.
+"""
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .engine import SegOFAEngine
+
+_BF16 = torch.bfloat16
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+class ParamArena:
+    """Flat fp32 master / gradient / Adam-moment buffers holding every trainable parameter."""
+
+    def __init__(self, groups: List[List[torch.nn.Parameter]], device):
+        self.slots: Dict[int, tuple] = {}  # id(param) -> (offset, numel)
+        off = 0
+        seen = set()
+        for grp in groups:
+            for p in grp:
+                if id(p) in seen:
+                    raise ValueError("parameter listed twice in the arena")
+                seen.add(id(p))
+                self.slots[id(p)] = (off, p.numel())
+                off += p.numel()
+            off = _pad8(off)
+        self.numel = off
+        self.flat32 = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad32 = torch.zeros(off, dtype=torch.float32, device=device)
+        self.exp_avg = None
+        self.exp_avg_sq = None
+        self.params = [p for grp in groups for p in grp]
+        with torch.no_grad():
+            for p in self.params:
+                o, n = self.slots[id(p)]
+                self.flat32[o:o + n].copy_(p.detach().reshape(-1).float())
+                p.data = self.flat32[o:o + n].view(p.shape)
+                p.grad = self.grad32[o:o + n].view(p.shape)
+
+    def has(self, p):
+        return p is not None and id(p) in self.slots
+
+    def view(self, buf, params, shape):
+        """view of `buf` covering the adjacent parameters `params` with the given shape."""
+        o0, _ = self.slots[id(params[0])]
+        o = o0
+        for p in params:
+            po, n = self.slots[id(p)]
+            if po != o:
+                raise ValueError("parameters are not adjacent in the arena")
+            o += n
+        return buf[o0:o].view(shape)
+
+    def ensure_moments(self):
+        if self.exp_avg is None:
+            self.exp_avg = torch.zeros_like(self.flat32)
+            self.exp_avg_sq = torch.zeros_like(self.flat32)
+
+
+class _Dense:
+    """One GEMM operand set: fp32 master view(s), bf16 W [N,K], bf16 W^T [K,pad8(N)], grads."""
+    __slots__ = ("src", "w16", "w16t", "b32", "gw", "gb", "N", "K")
+
+
+class SegOFATrainEngine:
+    def __init__(self, model):
+        p0 = next(model.parameters())
+        if not p0.is_cuda:
+            raise RuntimeError("segofa_b200: training runs on a B200 only (no CPU fallback) -- call model.cuda() first")
+        if any(p.dtype != torch.float32 for p in model.parameters() if p.requires_grad):
+            raise RuntimeError("segofa_b200 training keeps fp32 master parameters and makes its own bf16 operand "
+                               "copies (cf. fp16_optimizer.py:108-222); keep the model in fp32")
+        self.model = model
+        self.cfg = model.cfg
+        self.device = p0.device
+        if self.cfg.decoder_input_type != "encoder_output":
+            raise NotImplementedError("training implements --decoder-input-type=encoder_output (the shipped recipe)")
+        self._build_arena()
+        # the inference engine provides the (batch-invariant) position bias and the real-image no-grad pass
+        self.inf: Optional[SegOFAEngine] = None
+        self.accumulate = False
+        self.step_count = 0
+        self._scratch: Dict = {}
+        self.refresh_weights()
+
+    # ------------------------------------------------------------------------------------
+    # parameters
+    # ------------------------------------------------------------------------------------
+    def _build_arena(self):
+        m = self.model
+        enc, dec = m.encoder, m.decoder
+        groups: List[List[torch.nn.Parameter]] = []
+        taken = set()
+
+        def add(ps):
+            ps = [p for p in ps if p is not None]
+            if not ps:
+                return
+            req = [p.requires_grad for p in ps]
+            if not any(req):
+                return
+            if not all(req):
+                raise NotImplementedError("a fused parameter group is only partially trainable")
+            groups.append(ps)
+            taken.update(id(p) for p in ps)
+
+        def attn(a, cross):
+            if cross:
+                add([a.q_proj.weight]); add([a.q_proj.bias])
+            else:
+                add([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight])
+                add([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias])
+            add([a.out_proj.weight]); add([a.out_proj.bias]); add([a.c_attn])
+
+        for l in enc.layers:
+            attn(l.self_attn, False)
+        add([w for l in dec.layers for w in (l.encoder_attn.k_proj.weight, l.encoder_attn.v_proj.weight)])
+        add([b for l in dec.layers for b in (l.encoder_attn.k_proj.bias, l.encoder_attn.v_proj.bias)])
+        for l in dec.layers:
+            attn(l.self_attn, False)
+            attn(l.encoder_attn, True)
+        # everything else that is trainable AND receives a gradient from this engine
+        self._no_grad_names = []
+        for name, p in m.named_parameters():
+            if not p.requires_grad or id(p) in taken:
+                continue
+            if self._is_bias_path(name):
+                self._no_grad_names.append(name)
+                continue
+            add([p])
+        self.arena = ParamArena(groups, self.device)
+        for name, p in m.named_parameters():
+            if name in self._no_grad_names:
+                p.grad = None
+
+    @staticmethod
+    def _is_bias_path(name):
+        keys = ("embed_positions", "embed_image_positions", "embed_seg_positions", "pos_ln.", "image_pos_ln.",
+                "seg_pos_ln.", "pos_q_linear", "pos_k_linear", "rel_pos_table_list", "code_layernorm_embedding")
+        return any(k in name for k in keys)
+
+    def _dense(self, weights, biases):
+        """weights/biases: lists of nn.Parameter fused along the output dimension."""
+        d = _Dense()
+        N = sum(w.shape[0] for w in weights)
+        K = weights[0].shape[1]
+        d.N, d.K = N, K
+        ar = self.arena
+        if ar.has(weights[0]):
+            d.src = ar.view(ar.flat32, weights, (N, K))
+            d.gw = ar.view(ar.grad32, weights, (N, K))
+        else:
+            d.src = torch.cat([w.detach().float() for w in weights], 0).contiguous()
+            d.gw = None
+        d.w16 = torch.empty((N, K), dtype=_BF16, device=self.device)
+        d.w16t = torch.empty((K, _pad8(N)), dtype=_BF16, device=self.device)
+        d.b32, d.gb = None, None
+        if biases and biases[0] is not None:
+            if ar.has(biases[0]):
+                d.b32 = ar.view(ar.flat32, biases, (N,))
+                d.gb = ar.view(ar.grad32, biases, (N,))
+            else:
+                d.b32 = torch.cat([b.detach().float() for b in biases], 0).contiguous()
+        return d
+
+    def _ln(self, mod):
+        ar = self.arena
+        if ar.has(mod.weight):
+            return (mod.weight.data, mod.bias.data, mod.weight.grad, mod.bias.grad)
+        return (mod.weight.detach().float().contiguous(), mod.bias.detach().float().contiguous(), None, None)
+
+    def _vec(self, p):
+        if p is None:
+            return None, None
+        if self.arena.has(p):
+            return p.data, p.grad
+        return p.detach().float().contiguous(), None
+
+    def refresh_weights(self):
+        """(Re)derive the bf16 operands from the fp32 masters: once at construction and after every optimizer
+        step.  One transpose-cast launch per weight matrix."""
+        m = self.model
+        enc, dec = m.encoder, m.decoder
+        first = not hasattr(self, "dense")
+        if first:
+            self.dense: List[_Dense] = []
+
+            def mk(ws, bs):
+                d = self._dense(ws, bs)
+                self.dense.append(d)
+                return d
+
+            def attn(a):
+                return dict(qkv=mk([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight],
+                                   [a.q_proj.bias, a.k_proj.bias, a.v_proj.bias]),
+                            out=mk([a.out_proj.weight], [a.out_proj.bias]), c_attn=self._vec(a.c_attn))
+
+            self.enc_layers = []
+            for l in enc.layers:
+                self.enc_layers.append(dict(
+                    attn=attn(l.self_attn), ln_self=self._ln(l.self_attn_layer_norm), ln_attn=self._ln(l.attn_ln),
+                    ln_final=self._ln(l.final_layer_norm), ln_ffn=self._ln(l.ffn_layernorm),
+                    fc1=mk([l.fc1.weight], [l.fc1.bias]), fc2=mk([l.fc2.weight], [l.fc2.bias])))
+            self.cross_kv = mk([w for l in dec.layers for w in (l.encoder_attn.k_proj.weight, l.encoder_attn.v_proj.weight)],
+                               [b for l in dec.layers for b in (l.encoder_attn.k_proj.bias, l.encoder_attn.v_proj.bias)])
+            self.dec_layers = []
+            for l in dec.layers:
+                ca = l.encoder_attn
+                self.dec_layers.append(dict(
+                    attn=attn(l.self_attn),
+                    cross=dict(q=mk([ca.q_proj.weight], [ca.q_proj.bias]), out=mk([ca.out_proj.weight], [ca.out_proj.bias]),
+                               c_attn=self._vec(ca.c_attn)),
+                    ln_self=self._ln(l.self_attn_layer_norm), ln_self_attn=self._ln(l.self_attn_ln),
+                    ln_enc_attn=self._ln(l.encoder_attn_layer_norm), ln_cross_attn=self._ln(l.cross_attn_ln),
+                    ln_final=self._ln(l.final_layer_norm), ln_ffn=self._ln(l.ffn_layernorm),
+                    fc1=mk([l.fc1.weight], [l.fc1.bias]), fc2=mk([l.fc2.weight], [l.fc2.bias])))
+            self.seg_proj = mk([dec.seg_projection.weight], [None])
+            self.ln_emb, self.ln_patch = self._ln(enc.layernorm_embedding), self._ln(enc.patch_layernorm_embedding)
+            self.ln_enc_out, self.ln_dec_out = self._ln(enc.layer_norm), self._ln(dec.layer_norm)
+            self.dec_ln_emb = self._ln(dec.layernorm_embedding)
+            te, self.g_type = self._vec(enc.type_embedding.weight)
+            self.type_txt, self.type_img = te[0], te[1]
+            self.embed_tokens = enc.embed_tokens.weight.detach()
+            if enc.embed_tokens.weight.requires_grad:
+                raise NotImplementedError("training requires --freeze-encoder-embedding/--freeze-decoder-embedding "
+                                          "(the shipped recipe); token-embedding gradients are not implemented")
+        for d in self.dense:
+            if first or d.gw is not None:
+                ops.transpose_cast(d.src, out_t=d.w16t, out_c=d.w16)
+        if self.inf is None:
+            self.inf = SegOFAEngine(self.model)
+            self.inf.fold_ffn_layernorm = True
+
+    # ------------------------------------------------------------------------------------
+    # helpers
+    # ------------------------------------------------------------------------------------
+    def _buf(self, key, shape, dtype):
+        t = self._scratch.get(key)
+        if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._scratch[key] = t
+        return t
+
+    def _lin_fwd(self, a, L: _Dense, tag, **kw):
+        return ops.gemm(a, L.w16, bias=L.b32, tag=tag, **kw)
+
+    def _lin_bwd(self, dy, x, L: _Dense, M, tag, need_dx=True, dx_dtype=_BF16, dx_out=None):
+        """dy bf16 [M,N] (row stride may exceed N), x bf16 [M,K] saved input.  Writes dW / db into the arena
+        gradient views, returns dX = dY W."""
+        N, K = L.N, L.K
+        Mp = _pad8(M)
+        if L.gw is not None:
+            dyt = self._buf("dyt", (max(d.N for d in self.dense), Mp), _BF16)
+            xt = self._buf("xt", (max(d.K for d in self.dense), Mp), _BF16)
+            ops.transpose_cast(dy, M=M, N=N, out_t=dyt, colsum=L.gb)
+            ops.transpose_cast(x, M=M, N=K, out_t=xt)
+            ops.gemm(dyt, xt, L.gw, M=N, N=K, K=M, lda=Mp, ldb=Mp, residual=L.gw if self.accumulate else None,
+                     tag="wgrad_" + tag)
+        if not need_dx:
+            return None
+        return ops.gemm(dy, L.w16t, dx_out, M=M, N=K, K=N, lda=dy.stride(0), ldb=L.w16t.stride(0), out_dtype=dx_dtype,
+                        tag="dgrad_" + tag)
+
+    # ------------------------------------------------------------------------------------
+    # forward + backward of the image-free branch
+    # ------------------------------------------------------------------------------------
+    def forward_backward(self, aux_input, target_classes, label_smoothing=0.0, grad_scale=1.0, backward=True):
+        """aux_input: the dict segofa.py:136-151 receives (src_tokens, patch_images = bag tokens, patch_masks = bag
+        end offsets, prev_output_tokens); target_classes int64 [B,S,S] class ids (<0 or >=C ignored).
+        Returns (loss 0-dim tensor = mean pixel CE, logits fp32 [B,Td,C]); gradients of the mean loss times
+        grad_scale are left in param.grad (views of arena.grad32)."""
+        cfg, dev = self.cfg, self.device
+        D, H, Fd, C = cfg.embed_dim, cfg.heads, cfg.ffn_dim, cfg.num_seg
+        src_tokens = aux_input["src_tokens"].to(dev)
+        B, T_txt = src_tokens.shape
+        if bool(src_tokens.eq(cfg.padding_idx).any()):
+            raise NotImplementedError("training with padded prompts is not implemented (every IFSeg batch shares one prompt)")
+        h = w = cfg.patch_image_size // 16
+        P = h * w
+        T, Td = P + T_txt, P + 1
+        M, Md = B * T, B * Td
+        f32 = torch.float32
+        new = lambda shape, dt=_BF16: torch.empty(shape, dtype=dt, device=dev)  # noqa: E731
+
+        enc_biases, pos = self.inf._encoder_bias(h, w, T_txt, True)
+        self_biases, cross_abs = self.inf._decoder_bias(h, w, pos)
+        if not self.accumulate:
+            self.arena.grad32.zero_()
+
+        # ------------------------------ encoder forward ------------------------------
+        bag = ops.embedding_bag_mean(aux_input["patch_images"].to(dev).contiguous(),
+                                     aux_input["patch_masks"].to(dev).contiguous(), self.embed_tokens, P)
+        tok_idx = src_tokens.reshape(-1).contiguous()
+        x = new((M, D), f32)
+        a = new((M, D))
+        L0 = self.enc_layers[0]
+        ops.row_layernorm(bag, pre_add=self.type_img, ln1=self.ln_patch[:2], out1=x, ln2=L0["ln_self"][:2], out2=a,
+                          seg=(P, T, 0))
+        ops.row_layernorm(self.embed_tokens, rows=B * T_txt, D=D, gather_idx=tok_idx, pre_add=self.type_txt,
+                          ln1=self.ln_emb[:2], out1=x, ln2=L0["ln_self"][:2], out2=a, seg=(T_txt, T, P))
+        x_emb = x
+        enc_saved = []
+        s3 = (3 * D, T * 3 * D)
+        for li, L in enumerate(self.enc_layers):
+            S = dict(a=a)
+            S["qkv"] = self._lin_fwd(a, L["attn"]["qkv"], "qkv", alpha=cfg.attn_scaling, alpha_cols=D)
+            S["o"], S["lse"] = new((M, D)), new((B, H, T), f32)
+            ops.attention(S["qkv"], S["qkv"][:, D:], S["qkv"][:, 2 * D:], S["o"], B=B, H=H, Tq=T, Tk=T, q_strides=s3,
+                          k_strides=s3, v_strides=s3, o_strides=(D, T * D), bias=enc_biases[li],
+                          head_scale=L["attn"]["c_attn"][0], lse=S["lse"])
+            S["y"] = self._lin_fwd(S["o"], L["attn"]["out"], "out_proj", out_dtype=f32)
+            S["x1"], S["a2"] = new((M, D), f32), new((M, D))
+            ops.row_layernorm(S["y"], ln1=L["ln_attn"][:2], residual=x, out1=S["x1"], ln2=L["ln_final"][:2], out2=S["a2"])
+            S["h"] = self._lin_fwd(S["a2"], L["fc1"], "fc1")
+            S["z"] = new((M, Fd))
+            ops.row_layernorm(S["h"], ln2=L["ln_ffn"][:2], out2=S["z"], x_act=ops.ACT_GELU)
+            S["x2"] = new((M, D), f32)
+            ops.gemm(S["z"], L["fc2"].w16, S["x2"], bias=L["fc2"].b32, residual=S["x1"], tag="fc2")
+            nxt = self.enc_layers[li + 1]["ln_self"] if li + 1 < len(self.enc_layers) else self.ln_enc_out
+            S["ln_next"] = nxt
+            a = new((M, D))
+            ops.row_layernorm(S["x2"], ln2=nxt[:2], out2=a)
+            x = S["x2"]
+            enc_saved.append(S)
+        enc_out = a  # [B*T, D] bf16
+
+        # ------------------------------ decoder forward ------------------------------
+        nL = len(self.dec_layers)
+        bos = aux_input["prev_output_tokens"].to(dev)[:, 0].contiguous()
+        xd = new((Md, D), f32)
+        ad = new((Md, D))
+        D0 = self.dec_layers[0]
+        ops.row_layernorm(self.embed_tokens, rows=B, D=D, gather_idx=bos, ln1=self.dec_ln_emb[:2], out1=xd,
+                          ln2=D0["ln_self"][:2], out2=ad, seg=(1, Td, 0))
+        dec_in_idx = self.inf._cached(("dec_in_idx", B, T, P), lambda: (
+            torch.arange(B).unsqueeze(1) * T + torch.arange(P).unsqueeze(0)).reshape(-1))
+        ops.row_layernorm(enc_out, rows=B * P, gather_idx=dec_in_idx, ln1=self.dec_ln_emb[:2], out1=xd,
+                          ln2=D0["ln_self"][:2], out2=ad, seg=(P, Td, 1))
+        xd_emb = xd
+        kv_all = self._lin_fwd(enc_out, self.cross_kv, "cross_kv")  # [M, nL*2D]
+        kvs = (nL * 2 * D, T * nL * 2 * D)
+        sd3 = (3 * D, Td * 3 * D)
+        dec_saved = []
+        a, x = ad, xd
+        for li, L in enumerate(self.dec_layers):
+            S = dict(a=a)
+            S["qkv"] = self._lin_fwd(a, L["attn"]["qkv"], "qkv", alpha=cfg.attn_scaling, alpha_cols=D)
+            S["o"], S["lse"] = new((Md, D)), new((B, H, Td), f32)
+            ops.attention(S["qkv"], S["qkv"][:, D:], S["qkv"][:, 2 * D:], S["o"], B=B, H=H, Tq=Td, Tk=Td, q_strides=sd3,
+                          k_strides=sd3, v_strides=sd3, o_strides=(D, Td * D), bias=self_biases[li],
+                          head_scale=L["attn"]["c_attn"][0], causal=True, lse=S["lse"])
+            S["y"] = self._lin_fwd(S["o"], L["attn"]["out"], "out_proj", out_dtype=f32)
+            S["x1"], S["a2"] = new((Md, D), f32), new((Md, D))
+            ops.row_layernorm(S["y"], ln1=L["ln_self_attn"][:2], residual=x, out1=S["x1"], ln2=L["ln_enc_attn"][:2],
+                              out2=S["a2"])
+            Cx = L["cross"]
+            S["qc"] = self._lin_fwd(S["a2"], Cx["q"], "cross_q", alpha=cfg.attn_scaling, alpha_cols=D)
+            S["oc"], S["lse_c"] = new((Md, D)), new((B, H, Td), f32)
+            kbase = kv_all[:, li * 2 * D:]
+            ops.attention(S["qc"], kbase, kbase[:, D:], S["oc"], B=B, H=H, Tq=Td, Tk=T, q_strides=(D, Td * D),
+                          k_strides=kvs, v_strides=kvs, o_strides=(D, Td * D), bias=cross_abs,
+                          head_scale=Cx["c_attn"][0], lse=S["lse_c"])
+            S["yc"] = self._lin_fwd(S["oc"], Cx["out"], "out_proj", out_dtype=f32)
+            S["x2"], S["a3"] = new((Md, D), f32), new((Md, D))
+            ops.row_layernorm(S["yc"], ln1=L["ln_cross_attn"][:2], residual=S["x1"], out1=S["x2"], ln2=L["ln_final"][:2],
+                              out2=S["a3"])
+            S["h"] = self._lin_fwd(S["a3"], L["fc1"], "fc1")
+            S["z"] = new((Md, Fd))
+            ops.row_layernorm(S["h"], ln2=L["ln_ffn"][:2], out2=S["z"], x_act=ops.ACT_GELU)
+            S["x3"] = new((Md, D), f32)
+            ops.gemm(S["z"], L["fc2"].w16, S["x3"], bias=L["fc2"].b32, residual=S["x2"], tag="fc2")
+            nxt = self.dec_layers[li + 1]["ln_self"] if li + 1 < nL else self.ln_dec_out
+            S["ln_next"] = nxt
+            a = new((Md, D))
+            ops.row_layernorm(S["x3"], ln2=nxt[:2], out2=a)
+            x = S["x3"]
+            dec_saved.append(S)
+        feats = a
+        logits = ops.gemm(feats, self.seg_proj.w16, out_dtype=f32, tag="seg_proj").view(B, Td, C)
+
+        # ------------------------------ loss ------------------------------
+        tgt = target_classes.to(dev).contiguous()
+        pix_lse = new(tuple(tgt.shape), f32)
+        acc = ops.upsample_ce_loss(logits, tgt, h, w, label_smoothing, lse_out=pix_lse, raw=True)
+        loss = acc[0] / acc[1]
+        if not backward:
+            return loss, logits
+        Cp = _pad8(C)
+        dlogits = new((B, Td, Cp))
+        ops.upsample_ce_loss_bwd(logits, tgt, pix_lse, acc[1:], h, w, dlogits, label_smoothing, grad_scale)
+
+        # ------------------------------ decoder backward ------------------------------
+        da = self._lin_bwd(dlogits.view(Md, Cp), feats, self.seg_proj, Md, "seg_proj")  # [Md, D] bf16
+        dxs = None  # fp32 residual-stream gradient
+        dkv_all = new((M, nL * 2 * D))
+        for li in reversed(range(nL)):
+            L, S = self.dec_layers[li], dec_saved[li]
+            nxt = S["ln_next"]
+            dx_new = dxs if dxs is not None else new((Md, D), f32)
+            dy = new((Md, D))
+            ops.row_layernorm_bwd(rows=Md, D=D, v=S["x3"], g2=nxt[0], dy2=da, dv_in=dxs, d_res=dx_new, dx=dy,
+                                  dg2=nxt[2], db2=nxt[3])
+            dxs = dx_new
+            dz = self._lin_bwd(dy, S["z"], L["fc2"], Md, "fc2")
+            dh = new((Md, Fd))
+            ops.row_layernorm_bwd(rows=Md, D=Fd, x=S["h"], x_act=ops.ACT_GELU, g2=L["ln_ffn"][0], dy2=dz, dx=dh,
+                                  dg2=L["ln_ffn"][2], db2=L["ln_ffn"][3])
+            da3 = self._lin_bwd(dh, S["a3"], L["fc1"], Md, "fc1")
+            # cross-attention block
+            dyc = new((Md, D))
+            ops.row_layernorm_bwd(rows=Md, D=D, x=S["yc"], g1=L["ln_cross_attn"][0], v=S["x2"], g2=L["ln_final"][0],
+                                  dy2=da3, dv_in=dxs, d_res=dxs, dx=dyc, dg1=L["ln_cross_attn"][2],
+                                  db1=L["ln_cross_attn"][3], dg2=L["ln_final"][2], db2=L["ln_final"][3])
+            Cx = L["cross"]
+            doc = self._lin_bwd(dyc, S["oc"], Cx["out"], Md, "out_proj")
+            dqc = new((Md, D))
+            kbase, dkbase = kv_all[:, li * 2 * D:], dkv_all[:, li * 2 * D:]
+            delta = self._buf("delta", (B, H, max(T, Td)), f32)
+            ops.attention_bwd(S["qc"], kbase, kbase[:, D:], S["oc"], doc, dqc, dkbase, dkbase[:, D:], B=B, H=H, Tq=Td,
+                              Tk=T, q_strides=(D, Td * D), k_strides=kvs, v_strides=kvs, o_strides=(D, Td * D),
+                              do_strides=(D, Td * D), dq_strides=(D, Td * D), dk_strides=kvs, dv_strides=kvs,
+                              lse=S["lse_c"], delta=delta, bias=cross_abs, head_scale=Cx["c_attn"][0],
+                              d_head_scale=Cx["c_attn"][1], dq_scale=cfg.attn_scaling)
+            da2 = self._lin_bwd(dqc, S["a2"], Cx["q"], Md, "cross_q")
+            # self-attention block
+            dy = new((Md, D))
+            ops.row_layernorm_bwd(rows=Md, D=D, x=S["y"], g1=L["ln_self_attn"][0], v=S["x1"], g2=L["ln_enc_attn"][0],
+                                  dy2=da2, dv_in=dxs, d_res=dxs, dx=dy, dg1=L["ln_self_attn"][2],
+                                  db1=L["ln_self_attn"][3], dg2=L["ln_enc_attn"][2], db2=L["ln_enc_attn"][3])
+            do = self._lin_bwd(dy, S["o"], L["attn"]["out"], Md, "out_proj")
+            dqkv = new((Md, 3 * D))
+            ops.attention_bwd(S["qkv"], S["qkv"][:, D:], S["qkv"][:, 2 * D:], S["o"], do, dqkv, dqkv[:, D:],
+                              dqkv[:, 2 * D:], B=B, H=H, Tq=Td, Tk=Td, q_strides=sd3, k_strides=sd3, v_strides=sd3,
+                              o_strides=(D, Td * D), do_strides=(D, Td * D), dq_strides=sd3, dk_strides=sd3,
+                              dv_strides=sd3, lse=S["lse"], delta=delta, bias=self_biases[li],
+                              head_scale=L["attn"]["c_attn"][0], d_head_scale=L["attn"]["c_attn"][1], causal=True,
+                              dq_scale=cfg.attn_scaling)
+            da = self._lin_bwd(dqkv, S["a"], L["attn"]["qkv"], Md, "qkv")
+            dec_saved[li] = None
+        # decoder input embedding: rows 0 = bos (frozen embedding), rows 1..P = encoder_out rows
+        d_enc_out = self._lin_bwd(dkv_all, enc_out, self.cross_kv, M, "cross_kv", dx_dtype=f32)  # [M, D] fp32
+        g_emb, g_l0 = self.dec_ln_emb, self.dec_layers[0]["ln_self"]
+        ops.row_layernorm_bwd(rows=B, D=D, x=self.embed_tokens, gather_idx=bos, g1=g_emb[0], v=xd_emb, g2=g_l0[0],
+                              dy2=da, dv_in=dxs, dg1=g_emb[2], db1=g_emb[3], dg2=g_l0[2], db2=g_l0[3], seg=(1, Td, 0))
+        ops.row_layernorm_bwd(rows=B * P, D=D, x=enc_out, gather_idx=dec_in_idx, g1=g_emb[0], v=xd_emb, g2=g_l0[0],
+                              dy2=da, dv_in=dxs, dx=d_enc_out, dx_accumulate=True, dg1=g_emb[2], db1=g_emb[3],
+                              dg2=g_l0[2], db2=g_l0[3], seg=(P, Td, 1))
+
+        # ------------------------------ encoder backward ------------------------------
+        da = d_enc_out  # fp32 gradient w.r.t. encoder_out (= LN_enc_out(x))
+        dxs = None
+        for li in reversed(range(len(self.enc_layers))):
+            L, S = self.enc_layers[li], enc_saved[li]
+            nxt = S["ln_next"]
+            dx_new = dxs if dxs is not None else new((M, D), f32)
+            dy = new((M, D))
+            ops.row_layernorm_bwd(rows=M, D=D, v=S["x2"], g2=nxt[0], dy2=da, dv_in=dxs, d_res=dx_new, dx=dy,
+                                  dg2=nxt[2], db2=nxt[3])
+            dxs = dx_new
+            dz = self._lin_bwd(dy, S["z"], L["fc2"], M, "fc2")
+            dh = new((M, Fd))
+            ops.row_layernorm_bwd(rows=M, D=Fd, x=S["h"], x_act=ops.ACT_GELU, g2=L["ln_ffn"][0], dy2=dz, dx=dh,
+                                  dg2=L["ln_ffn"][2], db2=L["ln_ffn"][3])
+            da2 = self._lin_bwd(dh, S["a2"], L["fc1"], M, "fc1")
+            dy = new((M, D))
+            ops.row_layernorm_bwd(rows=M, D=D, x=S["y"], g1=L["ln_attn"][0], v=S["x1"], g2=L["ln_final"][0], dy2=da2,
+                                  dv_in=dxs, d_res=dxs, dx=dy, dg1=L["ln_attn"][2], db1=L["ln_attn"][3],
+                                  dg2=L["ln_final"][2], db2=L["ln_final"][3])
+            do = self._lin_bwd(dy, S["o"], L["attn"]["out"], M, "out_proj")
+            dqkv = new((M, 3 * D))
+            delta = self._buf("delta", (B, H, max(T, Td)), f32)
+            ops.attention_bwd(S["qkv"], S["qkv"][:, D:], S["qkv"][:, 2 * D:], S["o"], do, dqkv, dqkv[:, D:],
+                              dqkv[:, 2 * D:], B=B, H=H, Tq=T, Tk=T, q_strides=s3, k_strides=s3, v_strides=s3,
+                              o_strides=(D, T * D), do_strides=(D, T * D), dq_strides=s3, dk_strides=s3, dv_strides=s3,
+                              lse=S["lse"], delta=delta, bias=enc_biases[li], head_scale=L["attn"]["c_attn"][0],
+                              d_head_scale=L["attn"]["c_attn"][1], dq_scale=cfg.attn_scaling)
+            da = self._lin_bwd(dqkv, S["a"], L["attn"]["qkv"], M, "qkv")
+            enc_saved[li] = None
+        # encoder input embeddings (token embeddings frozen): type embedding + the two embedding LayerNorms
+        g_l0 = self.enc_layers[0]["ln_self"]
+        gt = self.g_type
+        ops.row_layernorm_bwd(rows=B * P, D=D, x=bag, pre_add=self.type_img, g1=self.ln_patch[0], v=x_emb, g2=g_l0[0],
+                              dy2=da, dv_in=dxs, dg1=self.ln_patch[2], db1=self.ln_patch[3], dg2=g_l0[2], db2=g_l0[3],
+                              d_pre_add=gt[1] if gt is not None else None, seg=(P, T, 0))
+        ops.row_layernorm_bwd(rows=B * T_txt, D=D, x=self.embed_tokens, gather_idx=tok_idx, pre_add=self.type_txt,
+                              g1=self.ln_emb[0], v=x_emb, g2=g_l0[0], dy2=da, dv_in=dxs, dg1=self.ln_emb[2],
+                              db1=self.ln_emb[3], dg2=g_l0[2], db2=g_l0[3], d_pre_add=gt[0] if gt is not None else None,
+                              seg=(T_txt, T, P))
+        return loss, logits
+
+    # ------------------------------------------------------------------------------------
+    # optimizer: clip_grad_norm (trainer.py:886) + fused Adam on the flat buffers (fp16_optimizer/adam.py)
+    # ------------------------------------------------------------------------------------
+    def grad_norm(self):
+        out = torch.zeros(1, dtype=torch.float32, device=self.device)
+        ops.sumsq(self.arena.grad32, out)
+        return out.sqrt()
+
+    def optimizer_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, clip_norm=0.0, grad_mult=1.0):
+        """grads *= grad_mult; clip to clip_norm (global L2 over the arena); AdamW; refresh the bf16 operands.
+        Everything stays on the device (no host sync).  Returns the pre-clip gradient norm (device tensor)."""
+        ar = self.arena
+        ar.ensure_moments()
+        self.step_count += 1
+        gnorm = self.grad_norm() * grad_mult
+        scale = torch.full((1,), float(grad_mult), dtype=torch.float32, device=self.device)
+        if clip_norm > 0:
+            scale = scale * (clip_norm / (gnorm + 1e-6)).clamp(max=1.0)
+        ops.adam_step(ar.flat32, ar.grad32, ar.exp_avg, ar.exp_avg_sq, lr=lr, beta1=betas[0], beta2=betas[1], eps=eps,
+                      weight_decay=weight_decay, step=self.step_count, grad_scale=scale)
+        self.refresh_weights()
+        return gnorm

@@ -169,9 +169,71 @@ def main():
     # cfg 1 of BASELINE.json (Base, 128x128, 15 classes, B=1) + a 2-image batch at 150 classes
     run_case("base_c15_s128", "segofa_base", 15, 128, 1, prompts)
     run_case("base_c150_s64_b2", "segofa_base", 150, 64, 2, prompts)
+    run_grad_case("base_c150_s64_b2")
     if "--full" in sys.argv:  # cfg 2 shape (not saved: 8x901x15 logits only) -- minutes of CPU
         run_case("base_c15_s480", "segofa_base", 15, 480, 2, prompts, save=False)
 
 
 if __name__ == "__main__":
     main()
+
+
+def run_grad_case(name="base_c150_s64_b2"):
+    """Gradient fixture of the image-free training branch, generated by the UNMODIFIED reference model
+    (eval mode: dropout / DropPath off -- the deterministic gradient-parity configuration of SURVEY.md s8d)
+    + compute_imfree_loss (seg_criterion.py:246-267 with 32/512 generalised), autograd backward.
+    Saves the per-parameter gradient norms of every tensor that receives a gradient, a few small gradients
+    in full, the loss and the target; asserts that the restated oracle's autograd reproduces all of it."""
+    g = torch.load(os.path.join(GOLD, f"golden_{name}.pt"))
+    arch, num_seg, size, batch = g["arch"], g["num_seg"], g["image_size"], g["batch"]
+    cfg = preset(arch, num_seg=num_seg, patch_image_size=size, orig_patch_image_size=size)
+    ocfg = oracle_cfg(cfg)
+    ref, _ = build_reference_model(arch, num_seg, size)
+    sd = generate_state_dict(cfg, seed=0)
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    gen = torch.Generator().manual_seed(5)
+    # dictionary-id targets on the full-resolution grid (+ trailing eos), incl. the ignored "unknown" id
+    t2s = torch.cat([torch.randint(0, num_seg + 1, (batch, size * size), generator=gen) + 59457,
+                     torch.full((batch, 1), 2)], 1)
+    aux = g["aux_input"]
+    _, extra = ref(aux_input=aux)
+    loss_ref = R.imfree_loss(extra["aux_output"][0], t2s, ocfg)
+    ref.zero_grad()
+    loss_ref.backward()
+    grads_ref = {k: p.grad.clone() for k, p in ref.named_parameters() if p.grad is not None}
+    # the restated oracle under autograd
+    sd_g = {k: (v.clone().requires_grad_() if v.is_floating_point() and k in grads_ref else v) for k, v in sd.items()}
+    x_or, _ = R.segofa_forward_aux(sd_g, ocfg, aux)
+    loss_or = R.imfree_loss(x_or, t2s, ocfg)
+    loss_or.backward()
+    worst = 0.0
+    for k, gr in grads_ref.items():
+        go = sd_g[k].grad
+        if go is None or gr.norm().item() < 1e-8:  # k_proj / pos_k biases: exactly zero in exact arithmetic
+            continue                                 # (softmax is invariant to a per-row constant): fp noise only
+        worst = max(worst, ((go - gr).norm() / gr.norm().clamp_min(1e-30)).item())
+    print(f"[grads {name}] loss ref {loss_ref.item():.6f} oracle {loss_or.item():.6f}; {len(grads_ref)} tensors with "
+          f"gradients; worst rel-L2(oracle autograd, reference autograd) = {worst:.3e}")
+    assert abs(loss_ref.item() - loss_or.item()) < 1e-5 and worst < 2e-4
+    # noise floor: the reference's own bf16 run (model.to(bf16), trainer.py:95-101) against its fp32 run
+    ref16 = ref.to(torch.bfloat16)
+    ref16.zero_grad()
+    _, extra16 = ref16(aux_input=aux)
+    loss16 = R.imfree_loss(extra16["aux_output"][0], t2s, ocfg)
+    loss16.backward()
+    g16 = {k: p.grad.float() for k, p in ref16.named_parameters() if p.grad is not None}
+    floor = {k: ((g16[k] - v).norm() / v.norm().clamp_min(1e-30)).item() for k, v in grads_ref.items() if k in g16}
+    num = sum(((g16[k] - v) ** 2).sum().item() for k, v in grads_ref.items() if k in g16)
+    den = sum((v ** 2).sum().item() for k, v in grads_ref.items() if k in g16)
+    floor_global = (num / den) ** 0.5
+    fl = sorted(v for k, v in floor.items() if grads_ref[k].norm().item() > 1e-8)
+    print(f"[grads {name}] reference bf16-vs-fp32: loss {loss16.item():.4f}; global grad rel-L2 {floor_global:.3e}; "
+          f"per-tensor median {fl[len(fl) // 2]:.3e} max {fl[-1]:.3e}")
+    small = {k: v for k, v in grads_ref.items() if v.numel() <= 4096 and ("layers.0." in k or "layers.5." in k or ".layers." not in k)}
+    torch.save(dict(name=name, loss=loss_ref.item(), text2seg_target=t2s.to(torch.int32),
+                    grad_norms={k: v.norm().item() for k, v in grads_ref.items()},
+                    grad_numel={k: v.numel() for k, v in grads_ref.items()}, small_grads=small,
+                    ref_bf16_grad_rel_l2=floor_global, ref_bf16_grad_rel_l2_per_tensor=floor, ref_bf16_loss=loss16.item()),
+               os.path.join(GOLD, f"golden_grads_{name}.pt"))
+    return grads_ref

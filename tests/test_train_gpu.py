@@ -1,0 +1,108 @@
+"""-m gpu: the training step of the image-free branch (forward with saved activations + hand-written
+backward, ifseg_b200/train_engine.py) against the oracle's autograd and the gradient fixture generated
+from the unmodified reference (tests/golden/golden_grads_*.pt, oracle/make_golden.py:run_grad_case).
+
+Tolerance (written here, as north_star asks): the reference's own bf16 run differs from its fp32 run by
+4.8e-2 global gradient rel-L2 (per tensor: median 1.5e-2, max 1.4e-1; stored in the fixture).  Gate: our
+global gradient rel-L2 against the fp32 oracle is below that noise floor, the loss agrees to 1e-2 relative."""
+import pytest
+import torch
+
+from helpers import load_golden, oracle_cfg, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(name="base_c150_s64_b2"):
+    import os
+
+    from helpers import GOLD
+    from ifseg_b200.seg_criterion import class_targets
+    from ifseg_b200.segofa import SegOFAModel
+    from ifseg_b200.synthetic import generate_state_dict
+    from ifseg_b200.train_engine import SegOFATrainEngine
+
+    g = load_golden(name)
+    gg = torch.load(os.path.join(GOLD, f"golden_grads_{name}.pt"), map_location="cpu")
+    C, S, B = g["num_seg"], g["image_size"], g["batch"]
+    model = SegOFAModel.from_config(g["arch"], C, S)
+    sd = generate_state_dict(model.cfg, 0)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    eng = SegOFATrainEngine(model)
+    t2s = gg["text2seg_target"].long()
+    tgt = class_targets(t2s[:, :-1].reshape(B, S, S), 59457, C).cuda()
+    aux = {k: v.cuda() for k, v in g["aux_input"].items()}
+    return g, gg, model, sd, eng, aux, tgt, t2s
+
+
+def test_imfree_train_step_gradients_vs_oracle(cuda_device):
+    from oracle import restated as R
+
+    g, gg, model, sd, eng, aux, tgt, t2s = _setup()
+    loss, logits = eng.forward_backward(aux, tgt)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - gg["loss"]) < 1e-2 * gg["loss"], (loss.item(), gg["loss"])
+    assert rel_l2(logits, g["aux_logits"]) <= 0.75 * g["ref_bf16_rel_l2"]
+
+    ours = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    # golden norms from the reference itself
+    ratios = []
+    for k, gr in ours.items():
+        assert k in gg["grad_norms"], f"{k}: the reference produces no gradient here"
+        n_ref = gg["grad_norms"][k]
+        if n_ref > 1e-8:
+            ratios.append((gr.norm().item() / n_ref, k))
+    lo, hi = min(ratios), max(ratios)
+    assert 0.8 < lo[0] and hi[0] < 1.25, (lo, hi)
+    for k, ref in gg["small_grads"].items():
+        if k in ours and gg["grad_norms"][k] > 1e-8:
+            assert rel_l2(ours[k], ref) < 0.2, (k, rel_l2(ours[k], ref))
+    # full comparison against the oracle's autograd (fp32, CPU)
+    torch.set_num_threads(8)
+    ocfg = oracle_cfg(model.cfg)
+    sd_g = {k: (v.clone().requires_grad_() if k in ours else v) for k, v in sd.items()}
+    x_or, _ = R.segofa_forward_aux(sd_g, ocfg, g["aux_input"])
+    R.imfree_loss(x_or, t2s, ocfg).backward()
+    num = den = 0.0
+    worst = (0.0, None)
+    per = []
+    for k, gr in ours.items():
+        go = sd_g[k].grad
+        if go is None or go.norm().item() < 1e-8:
+            assert gr.norm().item() < 1e-5, (k, gr.norm().item())  # k_proj biases: exactly zero in exact arithmetic
+            continue
+        num += ((gr - go) ** 2).sum().item()
+        den += (go ** 2).sum().item()
+        e = rel_l2(gr, go)
+        per.append(e)
+        if e > worst[0]:
+            worst = (e, k)
+    glob = (num / den) ** 0.5
+    per.sort()
+    print(f"\ngradient parity: {len(per)} tensors, global rel-L2 {glob:.3e} (reference bf16 floor "
+          f"{gg['ref_bf16_grad_rel_l2']:.3e}), per-tensor median {per[len(per) // 2]:.3e}, worst {worst[0]:.3e} {worst[1]}")
+    assert glob <= gg["ref_bf16_grad_rel_l2"], glob
+    assert worst[0] < 0.25, worst
+    # every tensor the reference gives a gradient to is either produced or on the documented bias-path list
+    missing = [k for k in gg["grad_norms"] if k not in ours and not eng._is_bias_path(k)]
+    assert not missing, missing
+
+
+def test_train_loop_decreases_loss_and_keeps_views(cuda_device):
+    g, gg, model, sd, eng, aux, tgt, t2s = _setup()
+    first = None
+    for it in range(6):
+        loss, _ = eng.forward_backward(aux, tgt)
+        gn = eng.optimizer_step(lr=2e-4, weight_decay=0.01, clip_norm=1.0)
+        if first is None:
+            first = loss.item()
+            assert abs(gn.item() - sum(v ** 2 for k, v in gg["grad_norms"].items() if not eng._is_bias_path(k)) ** 0.5) \
+                < 0.08 * gn.item()
+    last, _ = eng.forward_backward(aux, tgt, backward=False)
+    assert last.item() < first - 0.05, (first, last.item())
+    # the nn.Parameters are views of the flat master buffer: state_dict sees the updated weights
+    p = model.encoder.layers[0].fc1.weight
+    assert p.data_ptr() >= eng.arena.flat32.data_ptr()
+    assert not torch.equal(p.detach().cpu(), sd["encoder.layers.0.fc1.weight"])
+    assert torch.isfinite(eng.arena.flat32).all()
