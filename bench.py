@@ -38,13 +38,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOPS_PER_IMG = {2: 286.8e9, 4: 364.6e9}  # SURVEY.md s8d (forward, algorithmic)
+FLOPS_PER_IMG = {2: 286.8e9, 4: 364.6e9, 3: 1061.2e9}  # SURVEY.md s8d (forward / train step, algorithmic)
 CONFIGS = {
     # id: (arch, image, classes, batch, description)
     1: ("segofa_base", 128, 15, 1, "OFA-Base segofa 128x128, 15 COCO-unseen classes, batch 1"),
     2: ("segofa_base", 480, 15, 8, "OFA-Base segofa 480x480 inference, 15 COCO-unseen classes, batch 8"),
     4: ("segofa_base", 512, 171, 8, "OFA-Base segofa 512x512 inference, 171 COCO-Stuff classes, batch 8"),
+    3: ("segofa_base", 480, 150, 8, "OFA-Base segofa 480x480 image-free finetune step, 150 ADE classes, per-GPU batch 8 "
+                                    "(aux fwd+bwd + no-grad real-image fwd + metrics + grad all-reduce + Adam)"),
 }
+TRAIN_CONFIGS = {3}
 
 
 def load_peaks():
@@ -139,6 +142,162 @@ def cpu_reference_run(cfg_id, steps, warmup, sample_batch=None):
                        f"fp32 torch CPU, {cores} threads; oracle/restated.py pinned on the reference"), dt
 
 
+def cpu_reference_train_run(cfg_id, steps, warmup):
+    """One image-free train step of the oracle port on the host cores (fp32 torch CPU autograd):
+    aux forward + imfree loss + backward, no-grad real-image forward + mask.  Batch 1."""
+    import torch
+
+    from ifseg_b200.config import preset
+    from ifseg_b200.synthetic import generate_state_dict, synthetic_train_sample
+    from oracle import restated as R
+
+    arch, size, nseg, batch, _ = CONFIGS[cfg_id]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = preset(arch, num_seg=nseg, patch_image_size=size, orig_patch_image_size=size)
+    sd = generate_state_dict(cfg, 0)
+    train_keys = [k for k, v in sd.items() if v.is_floating_point() and (".layers." in k or "layer_norm" in k)
+                  and "embed_images" not in k]
+    sd_g = {k: (v.clone().requires_grad_() if k in train_keys else v) for k, v in sd.items()}
+    ocfg = R.SegOFAConfig(**{k: getattr(cfg, k) for k in R.SegOFAConfig.__dataclass_fields__ if hasattr(cfg, k)})
+    smp = synthetic_train_sample(cfg, 1, size, seed=1, src_tokens=prompt_tokens(nseg))
+    hp = size // 16
+
+    def step():
+        for v in sd_g.values():
+            if v.requires_grad:
+                v.grad = None
+        x, _ = R.segofa_forward_aux(sd_g, ocfg, smp["aux_input"])
+        R.imfree_loss(x, smp["text2seg_target"], ocfg).backward()
+        ni = smp["net_input"]
+        with torch.no_grad():
+            lg, _ = R.segofa_forward(sd_g, ocfg, ni["src_tokens"], ni["patch_images"], ni["patch_masks"])
+            R.predict_mask(lg, hp, hp, size, size)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=1 / dt, unit="images/s", cores=cores, kind="port",
+                sample=f"{steps} timed + {warmup} warm-up train steps of batch 1 (of {batch}) at {size}x{size}: aux fwd+bwd "
+                       f"(autograd) + no-grad real-image fwd, fp32 torch CPU, {cores} threads, no optimizer; "
+                       f"oracle/restated.py pinned on the reference"), dt
+
+
+def bench_train(args, rank, world, local_rank, config):
+    import torch
+    import torch.distributed as dist
+
+    from ifseg_b200 import ops
+    from ifseg_b200.segofa import SegOFAModel
+    from ifseg_b200.synthetic import generate_state_dict, synthetic_train_sample
+    from ifseg_b200.trainer import SegOFATrainer, TrainSession
+
+    arch, size, nseg, batch, desc = CONFIGS[args.config]
+    peaks = load_peaks()
+    model = SegOFAModel.from_config(arch, nseg, size)
+    model.load_state_dict(generate_state_dict(model.cfg, 0), strict=True)
+    model = model.cuda()
+    trainer = SegOFATrainer(model)  # shipped recipe: Adam lr 5e-5, wd 0.1, clip 1.0 (Appendix B)
+    smp = synthetic_train_sample(model.cfg, batch, size, seed=1 + rank, src_tokens=prompt_tokens(nseg))
+    pinned = {k: ({kk: vv.pin_memory() for kk, vv in v.items()} if isinstance(v, dict) else
+                  (v.pin_memory() if torch.is_tensor(v) else v)) for k, v in smp.items()}
+    sess = TrainSession(trainer, smp, use_cuda_graph=not args.no_graph)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        sess.step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    with torch.cuda.stream(sess.stream):
+        for _ in range(args.steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(sess.stream)
+            sess.step()
+            e.record(sess.stream)
+            evs.append((s, e))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs) / args.steps
+    # end to end: pinned host sample -> device buffers -> step -> loss back on the host, every step
+    def e2e_step():
+        sess.load(pinned)
+        out = sess.step()
+        with torch.cuda.stream(sess.stream):
+            return float(out["loss"])  # D2H of the loss on the session stream (host sync)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    h2d = sum(v.numel() * v.element_size() for d in (pinned["net_input"], pinned["aux_input"]) for v in d.values()) + \
+        pinned["target"].numel() * 8 + pinned["text2seg_target"].numel() * 8
+    # per-kernel attribution (eager)
+    timer = ops.KernelTimer(fine=args.kernel_breakdown)
+    ops.set_timer(timer)
+    with torch.cuda.stream(sess.stream):
+        trainer.train_step(sess.static, check_pads=False)
+    fam_fine = timer.summary()
+    ops.set_timer(None)
+    fam = {}
+    for k, v in fam_fine.items():
+        d = fam.setdefault(k.split(":")[0], dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        for kk in d:
+            d[kk] += v[kk]
+    total_k_ms = sum(v["ms"] for v in fam.values())
+    if args.kernel_breakdown and rank == 0:
+        for k, v in sorted(fam_fine.items(), key=lambda kv: -kv[1]["ms"]):
+            sys.stderr.write(f"{k:34s} launches {v['launches']:4d}  {v['ms']:8.3f} ms  {100 * v['ms'] / total_k_ms:5.1f}%  "
+                             f"{v['flops'] / max(v['ms'], 1e-9) / 1e9:8.1f} TFLOP/s  {v['bytes'] / max(v['ms'], 1e-9) / 1e6:8.1f} GB/s\n")
+    t = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = t[0].item(), t[1].item()
+    n = max(world, 1)
+    if rank == 0:
+        d = fam["gemm_tcgen05"]
+        achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
+        step_tflops = FLOPS_PER_IMG[args.config] * batch / (dev_ms / 1e3) / 1e12
+        out = {
+            "metric": "images/sec (train step)", "value": n * batch / (dev_ms / 1e3), "unit": "images/s", "n_gpus": n,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+            "e2e": {"value": n * batch * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": sess.launches_per_step * args.steps, "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05", "achieved": achieved,
+                         "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                         "traffic": None, "peak_source": peaks["source"] + " (bf16 sustained)",
+                         "launches_per_step": d["launches"], "share_of_step_kernel_time": d["ms"] / total_k_ms,
+                         "step": {"achieved": step_tflops, "frac": step_tflops / peaks["bf16_sustained"],
+                                  "flops_per_image": FLOPS_PER_IMG[args.config]}},
+            "kernel_families": {k: {"launches": v["launches"], "ms": round(v["ms"], 4)} for k, v in fam.items()},
+            "cuda_graph": sess.graph is not None,
+            "train": {"dropout": 0.0, "note": "dropout/DropPath off; position-bias parameters frozen (DESIGN.md)"},
+        }
+        if not args.no_cpu_baseline:
+            cb, _ = cpu_reference_train_run(args.config, 1, 0)
+            out["cpu_baseline"] = cb
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,9 +323,13 @@ def main():
         if rank != 0:
             return
         steps = max(1, min(args.steps, 3))
-        cb, dt = cpu_reference_run(args.config, steps, min(args.warmup, 1))
+        if args.config in TRAIN_CONFIGS:
+            cb, dt = cpu_reference_train_run(args.config, min(steps, 2), min(args.warmup, 1))
+        else:
+            cb, dt = cpu_reference_run(args.config, steps, min(args.warmup, 1))
         print(json.dumps({
-            "impl": "reference", "metric": "images/sec", "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
+            "impl": "reference", "metric": "images/sec (train step)" if args.config in TRAIN_CONFIGS else "images/sec",
+            "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0,
@@ -183,6 +346,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl")
+    if args.config in TRAIN_CONFIGS:
+        config["l2_policy"] = "256 MB memset between timed steps (not timed); a step streams > 4 GB of activations"
+        return bench_train(args, rank, world, local_rank, config)
     from ifseg_b200 import ops
     from ifseg_b200.segofa import SegOFAModel
     from ifseg_b200.serving import SegmentationSession

@@ -121,6 +121,7 @@ class RowLnBwdArgs(C.Structure):
         ("dg1", _vp), ("db1", _vp), ("dg2", _vp), ("db2", _vp), ("d_pre_add", _vp),
         ("rows", _i32), ("D", _i32),
         ("seg_len", _i32), ("seg_stride", _i32), ("seg_off", _i32),
+        ("dx_colsum", _vp),
     ]
 
 
@@ -150,6 +151,7 @@ EXPORTS = [
     ("sgf_launch_count", _i64, []),
     ("sgf_reset_launch_count", None, []),
     ("sgf_gemm_bf16", C.c_int, [C.POINTER(GemmArgs), _vp]),
+    ("sgf_gemm_bf16_ex", C.c_int, [C.POINTER(GemmArgs), _i32, _i32, _i32, _vp]),
     ("sgf_gemm_force_variant", None, [C.c_int, C.c_int]),
     ("sgf_conv3x3_s1_nhwc", C.c_int, [C.POINTER(Conv3x3Args), _vp]),
     ("sgf_nchw_f32_to_nhwc_bf16", C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
@@ -165,7 +167,7 @@ EXPORTS = [
     ("sgf_row_layernorm_bwd", C.c_int, [C.POINTER(RowLnBwdArgs), _vp]),
     ("sgf_transpose_cast", C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp]),
     ("sgf_attention_bwd_bf16", C.c_int, [C.POINTER(AttentionBwdArgs), _vp]),
-    ("sgf_adam_step", C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
+    ("sgf_adam_step", C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp, _vp]),
     ("sgf_sumsq", C.c_int, [_vp, _i64, _vp, _vp]),
 ]
 

@@ -64,8 +64,12 @@ struct GemmSmem {
 // fully general path for odd shapes (N not a multiple of 32, rare operand combinations).
 enum : int {
   kEpiScale = 1, kEpiBias = 2, kEpiAlpha = 4, kEpiGelu = 8, kEpiRelu = 16, kEpiResBf16 = 32, kEpiResF32 = 64,
-  kEpiOutF32 = 128, kEpiRowStats = 256, kEpiRowNorm = 512, kEpiRuntime = 1 << 15
+  kEpiOutF32 = 128, kEpiRowStats = 256, kEpiRowNorm = 512, kEpiAtomic = 1024, kEpiRuntime = 1 << 15
 };
+SGF_DEVICE void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 template <int kEpi, int kFlag>
 SGF_DEVICE bool epi_has(bool runtime_value) {
   if constexpr ((kEpi & kEpiRuntime) != 0) return runtime_value;
@@ -251,7 +255,10 @@ SGF_DEVICE void gemm_epilogue(uint8_t* smem, uint32_t tmem_base, uint64_t* accum
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
         }
-        if (out_f32) {
+        if constexpr (!kRt && (kEpi & kEpiAtomic) != 0) {  // split-K partial: fp32 reduction into C
+          red_add_f32x4(reinterpret_cast<float*>(cptr), v[0], v[1], v[2], v[3]);
+          red_add_f32x4(reinterpret_cast<float*>(cptr) + 4, v[4], v[5], v[6], v[7]);
+        } else if (out_f32) {
           *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(cptr + 16) = make_float4(v[4], v[5], v[6], v[7]);
         } else {
@@ -405,6 +412,124 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
                                                                         img, h0, w0, warp, lane);
   }
 
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// Mixed-major kernel for the dense adjoints: either operand may be MN-major, i.e. stored with the
+// CONTRACTION index as the row index (A[k][m] / B[k][n]), which is how the saved activations and
+// output gradients lie in HBM for dW[n,k] = sum_t dY[t,n] X[t,k] (contraction over tokens) and how
+// W[n,k] lies for dX = dY W (contraction over n).  No transposed copies are materialised: an
+// MN-major tile is staged as 64-column TMA boxes ([64 contraction rows] x [64 MN elements], 128B
+// swizzle) and consumed through an MN-major UMMA descriptor (LBO = distance between the 64-wide
+// column blocks, SBO = 8-row group stride).  blockIdx.z = split-K slice; slices reduce into C with
+// vector fp32 atomics (kEpiAtomic).
+// ----------------------------------------------------------------------------------------
+SGF_DEVICE uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t block_stride_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(block_stride_bytes >> 4) << 16;  // LBO: next 64-element block along M/N
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                // SBO: next group of 8 contraction rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int BN, int kStages, bool kAmn, bool kBmn, int kEpi>
+__global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_mm_tcgen05_kernel(
+    const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape shp,
+    const GemmEpilogue ep, const int kb_per_split) {
+  using S = GemmSmem<BN>;
+  constexpr int kEpiWarps = gemm_epi_warps<BN>();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* accum_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int num_kb_all = (shp.K + BK - 1) / BK;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int num_kb = min(kb_per_split, num_kb_all - kb0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+#pragma unroll 1
+      for (int i = 0; i < num_kb; ++i) {
+        const int kb = kb0 + i;
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::kStageBytes;
+        uint8_t* sb = sa + S::kABytes;
+        mbar_expect_tx(&full_bar[s], S::kStageBytes);
+        if constexpr (kAmn) {
+#pragma unroll
+          for (int blk = 0; blk < BM / 64; ++blk) tma_load_2d(sa + blk * 8192, &tmA, &full_bar[s], m0 + blk * 64, kb * BK);
+        } else {
+          tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
+        }
+        if constexpr (kBmn) {
+#pragma unroll
+          for (int blk = 0; blk < BN / 64; ++blk) tma_load_2d(sb + blk * 8192, &tmB, &full_bar[s], n0 + blk * 64, kb * BK);
+        } else {
+          tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, kAmn ? 1 : 0, kBmn ? 1 : 0);
+#pragma unroll 1
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (i / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+        const uint32_t sb = sa + S::kABytes;
+        const uint64_t da = kAmn ? make_smem_desc_sw128_mn(sa, 8192) : make_smem_desc_sw128(sa);
+        const uint64_t db = kBmn ? make_smem_desc_sw128_mn(sb, 8192) : make_smem_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // K-major: 16 contraction elements = 32 B inside the swizzle row (+2); MN-major: 16 rows of 128 B (+128)
+          umma_f16(tmem_base, da + (kAmn ? 128 : 2) * k, db + (kBmn ? 128 : 2) * k, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    gemm_epilogue<BN, kEpiWarps, kStages * S::kStageBytes, false, kEpi>(smem, tmem_base, accum_bar, shp, ep, m0, n0, 0, 0,
+                                                                        0, 0, warp, lane);
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -844,6 +969,9 @@ static int dispatch_epilogue(const CUtensorMap& tmA, const CUtensorMap& tmB, con
         SGF_EPI_CASE(kEpiBias | kEpiGelu)                           // fc1
         SGF_EPI_CASE(kEpiBias | kEpiRowNorm | kEpiResF32 | kEpiOutF32)  // fc2 with folded ffn_layernorm
         SGF_EPI_CASE(kEpiBias | kEpiResF32 | kEpiOutF32)            // fc2
+        SGF_EPI_CASE(0)                                             // dX = dY W (bf16)
+        SGF_EPI_CASE(kEpiOutF32)                                    // dW = dY^T X (fp32), d(encoder_out)
+        SGF_EPI_CASE(kEpiOutF32 | kEpiResF32)                       // dW += (gradient accumulation)
         default: break;
       }
     }
@@ -892,6 +1020,7 @@ static int dispatch_epilogue2p(const CUtensorMap& tmA, const CUtensorMap& tmB, c
     SGF_EPI2P_CASE(kEpiScale | kEpiBias | kEpiRelu | kEpiResBf16)
     SGF_EPI2P_CASE(kEpiScale | kEpiBias)
     SGF_EPI2P_CASE(0)
+    SGF_EPI2P_CASE(kEpiOutF32)
     default: return -1;
   }
 }
@@ -1038,6 +1167,85 @@ extern "C" int sgf_gemm_bf16(const sgf_gemm_args* a, void* stream) {
     case 256: return dispatch_epilogue<256, 4, false>(tmA, tmB, shp, ep, grid, st);
     default: return dispatch_epilogue<128, 3, false>(tmA, tmB, shp, ep, grid, st);
   }
+}
+
+
+template <int BN, bool kAmn, bool kBmn, int kEpi>
+static int launch_gemm_mm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
+                          dim3 grid, int kb_per_split, cudaStream_t st) {
+  constexpr int kStages = BN <= 64 ? 4 : 3;
+  auto kern = gemm_mm_tcgen05_kernel<BN, kStages, kAmn, kBmn, kEpi>;
+  constexpr int smem = gemm_smem_bytes<BN, kStages>();
+  static bool configured = false;
+  if (!configured) {
+    SGF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  SGF_CHECK_CUDA(launch_pdl(kern, grid, dim3(gemm_threads<BN>()), smem, st, tmA, tmB, shp, ep, kb_per_split));
+  count_launch();
+  return SGF_OK;
+}
+
+template <int BN, bool kAmn, bool kBmn>
+static int dispatch_gemm_mm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
+                            dim3 grid, int kb_per_split, bool atomic, cudaStream_t st) {
+  if (atomic) return launch_gemm_mm<BN, kAmn, kBmn, kEpiOutF32 | kEpiAtomic>(tmA, tmB, shp, ep, grid, kb_per_split, st);
+  if (ep.c_dtype == SGF_F32) return launch_gemm_mm<BN, kAmn, kBmn, kEpiOutF32>(tmA, tmB, shp, ep, grid, kb_per_split, st);
+  return launch_gemm_mm<BN, kAmn, kBmn, 0>(tmA, tmB, shp, ep, grid, kb_per_split, st);
+}
+
+extern "C" int sgf_gemm_bf16_ex(const sgf_gemm_args* a, int32_t a_mn_major, int32_t b_mn_major, int32_t split_k,
+                                void* stream) {
+  SGF_REQUIRE(a != nullptr && a->a && a->b && a->c, "gemm_ex: null pointer");
+  SGF_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->batch == 1, "gemm_ex: bad shape (batch must be 1)");
+  SGF_REQUIRE(!a->col_scale && !a->col_bias && !a->residual && a->act == SGF_ACT_NONE && a->alpha_cols == 0 &&
+                  !a->rowstats_out && !a->rownorm_stats,
+              "gemm_ex: the mixed-major kernel has a plain epilogue (store or fp32 accumulate)");
+  SGF_REQUIRE(a->N % 32 == 0, "gemm_ex: N must be a multiple of 32 (N=%d)", a->N);
+  SGF_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(a->a) % 16) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->b) % 16) == 0,
+              "gemm_ex: operand alignment");
+  SGF_REQUIRE(a->lda >= (a_mn_major ? a->M : a->K) && a->ldb >= (b_mn_major ? a->N : a->K), "gemm_ex: leading dimension");
+  if (split_k < 1) split_k = 1;
+  SGF_REQUIRE(split_k == 1 || a->c_dtype == SGF_F32, "gemm_ex: split-K needs an fp32 output (accumulated in place)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GemmShape shp{};
+  shp.M = a->M; shp.N = a->N; shp.K = a->K;
+  GemmEpilogue ep{a->c, a->ldc, 0, a->c_dtype, nullptr, nullptr, nullptr, 0, 0, SGF_BF16, SGF_ACT_NONE, 1.0f, 0,
+                  nullptr, nullptr, nullptr, 0.f, 0};
+  if (int rc = check_epilogue_alignment(ep, a->N)) return rc;
+  const int m_tiles = (a->M + BM - 1) / BM;
+  const int bn = (a->N % 128 == 0 || a->N > 128) && (static_cast<long>(m_tiles) * ((a->N + 127) / 128) * split_k >= 96) ? 128 : 64;
+  auto make_map = [&](CUtensorMap* tm, const void* base, int64_t ld, int rows_mn, bool mn_major, int box_mn) -> int {
+    if (mn_major) {  // [K rows][MN contiguous]: box = 64 MN elements x 64 contraction rows
+      uint64_t dims[2] = {static_cast<uint64_t>(rows_mn), static_cast<uint64_t>(a->K)};
+      uint64_t strides[1] = {static_cast<uint64_t>(ld) * 2};
+      uint32_t box[2] = {64, BK};
+      return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
+    uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(rows_mn)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ld) * 2};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(box_mn)};
+    return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  CUtensorMap tmA, tmB;
+  if (int rc = make_map(&tmA, a->a, a->lda, a->M, a_mn_major != 0, BM)) return rc;
+  if (int rc = make_map(&tmB, a->b, a->ldb, a->N, b_mn_major != 0, bn)) return rc;
+  const int num_kb = (a->K + BK - 1) / BK;
+  if (split_k > num_kb) split_k = num_kb;
+  const int kb_per_split = (num_kb + split_k - 1) / split_k;
+  split_k = (num_kb + kb_per_split - 1) / kb_per_split;
+  dim3 grid((a->N + bn - 1) / bn, m_tiles, split_k);
+  const bool atomic = split_k > 1;
+#define SGF_MM_CASE(AMN, BMN)                                                                                   \
+  if ((a_mn_major != 0) == AMN && (b_mn_major != 0) == BMN)                                                      \
+    return bn == 128 ? dispatch_gemm_mm<128, AMN, BMN>(tmA, tmB, shp, ep, grid, kb_per_split, atomic, st)        \
+                     : dispatch_gemm_mm<64, AMN, BMN>(tmA, tmB, shp, ep, grid, kb_per_split, atomic, st);
+  SGF_MM_CASE(true, true)
+  SGF_MM_CASE(false, true)
+#undef SGF_MM_CASE
+  set_last_error("gemm_ex: only (A MN-major, B MN-major) and (A K-major, B MN-major) are built");
+  return SGF_ERR_UNSUPPORTED;
 }
 
 extern "C" void sgf_gemm_force_variant(int bn, int stages) {

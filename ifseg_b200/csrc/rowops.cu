@@ -433,8 +433,19 @@ extern "C" int sgf_embedding_bag_mean(const int64_t* tokens, int64_t ld_tokens, 
   return SGF_OK;
 }
 
+namespace sgf {
+int launch_gelu_ln_fwd_wide(const void* h, int64_t ldh, const float* g, const float* b, void* z, int64_t ldz, int rows,
+                            int F, cudaStream_t st);  // train.cu
+}
+
 extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
   SGF_REQUIRE(a != nullptr, "row_layernorm: null args");
+  if (a->x_act == SGF_ACT_GELU && a->x_dtype == SGF_BF16 && !a->gather_idx && !a->pre_add && !a->g1 && !a->residual &&
+      !a->out1 && a->out2 && a->g2 && a->b2 && !a->zero_row && a->seg_len == 0 && !a->clear_rowstats && a->D >= 1024 &&
+      a->D <= 4096 && a->D % 8 == 0 && a->rows > 0 && a->ldx % 8 == 0 && a->ld2 % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(a->x) % 16 == 0 && reinterpret_cast<uintptr_t>(a->out2) % 16 == 0)
+    return launch_gelu_ln_fwd_wide(a->x, a->ldx, a->g2, a->b2, a->out2, a->ld2, a->rows, a->D,
+                                   reinterpret_cast<cudaStream_t>(stream));
   SGF_REQUIRE(a->rows > 0 && a->D > 0 && a->D % 8 == 0, "row_layernorm: D must be a positive multiple of 8 (D=%d)", a->D);
   SGF_REQUIRE(a->D <= 5120, "row_layernorm: D=%d exceeds the 5120 register-resident limit", a->D);
   SGF_REQUIRE((a->g1 == nullptr) == (a->b1 == nullptr), "row_layernorm: g1/b1 must both be set or both null");

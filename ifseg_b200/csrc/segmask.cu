@@ -177,13 +177,22 @@ struct SeglossBwdParams {
   float scale_h, scale_w;
 };
 
-// weight with which low-res index `want` enters output index `dst` (0 when it does not)
-SGF_DEVICE float tap_weight(float scale, int dst, int in_size, int want, int& i0, int& i1, float& l0, float& l1) {
-  src_index(scale, dst, in_size, i0, i1, l0, l1);
-  return (i0 == want ? l0 : 0.f) + (i1 == want ? l1 : 0.f);
-}
+// Stage 1 (whole CTA): everything that does not depend on the class -- per footprint row / column the two taps and
+// their weights, per footprint pixel the weight w = wy*wx (0 for ignored pixels), log2e * logsumexp and the target --
+// goes to shared memory once.  Stage 2 (thread = class): per footprint row the two row taps are blended once
+// (3 values), columns are walked in runs of constant tap pair, so a pixel costs ~10 instructions
+// (2 FMA interpolation, ex2, accumulate).  Gather form: no atomics, deterministic.
+struct FootTap {
+  float l0, l1, w;
+  int i0, i1;  // tap indices relative to (p - 1): 0..2
+};
 
-__global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const SeglossBwdParams p) {
+__global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const SeglossBwdParams p, const int fy_max, const int fx_max) {
+  extern __shared__ __align__(16) uint8_t ce_smem[];
+  float2* pixv = reinterpret_cast<float2*>(ce_smem);              // (w, log2e * lse) per footprint pixel
+  int* pixt = reinterpret_cast<int*>(pixv + fy_max * fx_max);      // target class (or -1)
+  FootTap* rowp = reinterpret_cast<FootTap*>(pixt + fy_max * fx_max);
+  FootTap* colp = rowp + fy_max;
   const int tok = blockIdx.x;
   const int b = blockIdx.y;
   __nv_bfloat16* drow = p.dlogits + static_cast<int64_t>(b) * p.d_batch_stride + static_cast<int64_t>(tok) * p.d_tok_stride;
@@ -201,9 +210,36 @@ __global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const SeglossBwdPa
   if (px == 0) xlo = 0;
   if (py == p.hp - 1) yhi = p.h - 1;
   if (px == p.wp - 1) xhi = p.w - 1;
+  const int nY = min(yhi - ylo + 1, fy_max), nX = min(xhi - xlo + 1, fx_max);
+  for (int i = threadIdx.x; i < nY + nX; i += blockDim.x) {
+    const bool is_row = i < nY;
+    const int d = is_row ? ylo + i : xlo + (i - nY);
+    int i0, i1;
+    float l0, l1;
+    src_index(is_row ? p.scale_h : p.scale_w, d, is_row ? p.hp : p.wp, i0, i1, l0, l1);
+    const int want = is_row ? py : px;
+    FootTap t;
+    t.l0 = l0; t.l1 = l1;
+    t.w = (i0 == want ? l0 : 0.f) + (i1 == want ? l1 : 0.f);
+    t.i0 = min(max(i0 - (want - 1), 0), 2);
+    t.i1 = min(max(i1 - (want - 1), 0), 2);
+    (is_row ? rowp[i] : colp[i - nY]) = t;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nY * nX; i += blockDim.x) {
+    const int iy = i / nX, ix = i - iy * nX;
+    const float w = rowp[iy].w * colp[ix].w;
+    const int64_t pix = (static_cast<int64_t>(b) * p.h + (ylo + iy)) * p.w + (xlo + ix);
+    const int64_t t = p.target[pix];
+    const bool ok = w != 0.f && t >= 0 && t < p.C;
+    pixv[i] = ok ? make_float2(w, p.lse[pix] * 1.4426950408889634f) : make_float2(0.f, INFINITY);
+    pixt[i] = ok ? static_cast<int>(t) : -1;
+  }
+  __syncthreads();
   const float inv_cnt = p.grad_scale / fmaxf(p.count[0], 1.0f);
   const float* base = p.logits + static_cast<int64_t>(b) * p.batch_stride;
   const float uni = p.eps / static_cast<float>(p.C);
+  const float hit = 1.f - p.eps;
   for (int c = threadIdx.x; c < p.d_tok_stride; c += blockDim.x) {
     if (c >= p.C) {
       drow[c] = __float2bfloat16_rn(0.f);
@@ -217,43 +253,36 @@ __global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const SeglossBwdPa
         const int yy = min(max(py - 1 + dy, 0), p.hp - 1), xx = min(max(px - 1 + dx, 0), p.wp - 1);
         nb[dy][dx] = __ldg(base + static_cast<int64_t>(yy * p.wp + xx) * p.tok_stride + c);
       }
-    float g = 0.f;
-    for (int y = ylo; y <= yhi; ++y) {
-      int y0, y1;
-      float hl0, hl1;
-      const float wy = tap_weight(p.scale_h, y, p.hp, py, y0, y1, hl0, hl1);
-      if (wy == 0.f) continue;
-      const int r0 = y0 - (py - 1), r1 = y1 - (py - 1);
-      for (int x = xlo; x <= xhi; ++x) {
-        int x0, x1;
-        float wl0, wl1;
-        const float wx = tap_weight(p.scale_w, x, p.wp, px, x0, x1, wl0, wl1);
-        if (wx == 0.f) continue;
-        const int64_t pix = (static_cast<int64_t>(b) * p.h + y) * p.w + x;
-        const int64_t t = p.target[pix];
-        if (t < 0 || t >= p.C) continue;
-        const int q0 = x0 - (px - 1), q1 = x1 - (px - 1);
-        // r*, q* are in [0,2] whenever the weight is non-zero; select without dynamic register indexing
-        float v00, v01, v10, v11;
-        {
-          const float a0 = r0 == 0 ? nb[0][0] : (r0 == 1 ? nb[1][0] : nb[2][0]);
-          const float a1 = r0 == 0 ? nb[0][1] : (r0 == 1 ? nb[1][1] : nb[2][1]);
-          const float a2 = r0 == 0 ? nb[0][2] : (r0 == 1 ? nb[1][2] : nb[2][2]);
-          const float c0 = r1 == 0 ? nb[0][0] : (r1 == 1 ? nb[1][0] : nb[2][0]);
-          const float c1 = r1 == 0 ? nb[0][1] : (r1 == 1 ? nb[1][1] : nb[2][1]);
-          const float c2 = r1 == 0 ? nb[0][2] : (r1 == 1 ? nb[1][2] : nb[2][2]);
-          v00 = q0 == 0 ? a0 : (q0 == 1 ? a1 : a2);
-          v01 = q1 == 0 ? a0 : (q1 == 1 ? a1 : a2);
-          v10 = q0 == 0 ? c0 : (q0 == 1 ? c1 : c2);
-          v11 = q1 == 0 ? c0 : (q1 == 1 ? c1 : c2);
+    float g = 0.f, sw = 0.f;
+    for (int iy = 0; iy < nY; ++iy) {
+      const FootTap rp = rowp[iy];
+      if (rp.w == 0.f) continue;  // CTA-uniform
+      float a[3];  // the two row taps blended, per neighbourhood column
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float top = rp.i0 == 0 ? nb[0][dx] : (rp.i0 == 1 ? nb[1][dx] : nb[2][dx]);
+        const float bot = rp.i1 == 0 ? nb[0][dx] : (rp.i1 == 1 ? nb[1][dx] : nb[2][dx]);
+        a[dx] = rp.l0 * top + rp.l1 * bot;
+      }
+      const float2* pv = pixv + iy * nX;
+      const int* pt = pixt + iy * nX;
+      int ix = 0;
+      while (ix < nX) {  // run of columns sharing one tap pair
+        const int q0 = colp[ix].i0, q1 = colp[ix].i1;
+        const float vL = (q0 == 0 ? a[0] : (q0 == 1 ? a[1] : a[2])) * 1.4426950408889634f;
+        const float vR = (q1 == 0 ? a[0] : (q1 == 1 ? a[1] : a[2])) * 1.4426950408889634f;
+        for (; ix < nX && colp[ix].i0 == q0 && colp[ix].i1 == q1; ++ix) {
+          const float2 wl = pv[ix];
+          if (wl.x == 0.f) continue;  // CTA-uniform: ignored pixel or zero weight
+          const float v2 = fmaf(colp[ix].l0, vL, colp[ix].l1 * vR);  // log2e * interpolated logit
+          const float prob = fast_exp2(v2 - wl.y);
+          g = fmaf(wl.x, prob, g);
+          sw += wl.x;
+          if (pt[ix] == c) g = fmaf(-wl.x, hit, g);
         }
-        const float top = __fadd_rn(__fmul_rn(wl0, v00), __fmul_rn(wl1, v01));
-        const float bot = __fadd_rn(__fmul_rn(wl0, v10), __fmul_rn(wl1, v11));
-        const float v = __fadd_rn(__fmul_rn(hl0, top), __fmul_rn(hl1, bot));
-        const float prob = __expf(v - p.lse[pix]);
-        g += wy * wx * (prob - (t == c ? 1.f - p.eps : 0.f) - uni);
       }
     }
+    g = fmaf(-uni, sw, g);
     drow[c] = __float2bfloat16_rn(g * inv_cnt);
   }
 }
@@ -273,8 +302,18 @@ extern "C" int sgf_upsample_ce_loss_bwd(const sgf_segloss_bwd_args* a, void* str
                      static_cast<float>(a->wp) / static_cast<float>(a->w)};
   int threads = static_cast<int>((a->d_tok_stride + 31) / 32 * 32);
   if (threads > 256) threads = 256;
+  // footprint bound: 2 patches of pixels plus the conservative margins; border patches take the clamped rows too
+  const int fy_max = 2 * ((a->h + a->hp - 1) / a->hp) + 6 + (a->h + a->hp - 1) / a->hp;
+  const int fx_max = 2 * ((a->w + a->wp - 1) / a->wp) + 6 + (a->w + a->wp - 1) / a->wp;
+  const size_t smem = static_cast<size_t>(fy_max + fx_max) * sizeof(FootTap) + static_cast<size_t>(fy_max) * fx_max * 12;
+  SGF_REQUIRE(smem <= 160 * 1024, "upsample_ce_loss_bwd: up-sampling factor too large (%zu B of shared memory)", smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    SGF_CHECK_CUDA(cudaFuncSetAttribute(upsample_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = 160 * 1024;
+  }
   dim3 grid(a->d_tokens, a->B);
-  upsample_ce_bwd_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  upsample_ce_bwd_kernel<<<grid, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p, fy_max, fx_max);
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return SGF_OK;

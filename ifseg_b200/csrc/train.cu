@@ -70,11 +70,17 @@ struct RowLnBwdParams {
   float* dg1; float* db1; float* dg2; float* db2; float* d_pre_add;
   int rows, D;
   int seg_len, seg_stride, seg_off;
+  float* dx_colsum;
 };
 
+// Parameter-gradient partials are kept in PER-WARP private shared-memory accumulators (lane l of every warp
+// always owns the same columns, so plain vector read-modify-writes suffice: no atomics, no bank conflicts) and
+// are summed over the warps and flushed with one global atomic per column per CTA at the end.  LayerNorm
+// statistics cost two passes over the staged row (mean; then centred sum of squares together with the two
+// dot products the adjoint needs), GELU is evaluated once per element into an fp32 stash.
 __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdParams p, const int x_bytes,
                                                                 const int v_bytes, const int dy_bytes,
-                                                                const int dv_bytes, const int n_acc) {
+                                                                const int dv_bytes, const int t_bytes, const int n_acc) {
   pdl_trigger();
   const int kRows = blockDim.x >> 5;
   extern __shared__ __align__(128) uint8_t bsm[];
@@ -82,19 +88,22 @@ __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdPa
   uint8_t* vbuf = xbuf + kRows * x_bytes;
   uint8_t* dybuf = vbuf + kRows * v_bytes;
   uint8_t* dvbuf = dybuf + kRows * dy_bytes;
-  float* acc = reinterpret_cast<float*>(dvbuf + kRows * dv_bytes);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(acc + static_cast<size_t>(n_acc) * p.D);
+  uint8_t* tbuf = dvbuf + kRows * dv_bytes;  // fp32 stash of t = act(x) (+ pre_add) when an activation is applied
+  float* acc = reinterpret_cast<float*>(tbuf + kRows * t_bytes);  // [kRows][n_acc][D]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(acc + static_cast<size_t>(kRows) * n_acc * p.D);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int D = p.D;
 
+  float* wacc = acc + static_cast<size_t>(warp) * n_acc * D;
   int na = 0;
-  float* a_g2 = p.dg2 ? acc + (na++) * D : nullptr;
-  float* a_b2 = p.db2 ? acc + (na++) * D : nullptr;
-  float* a_g1 = p.dg1 ? acc + (na++) * D : nullptr;
-  float* a_b1 = p.db1 ? acc + (na++) * D : nullptr;
-  float* a_pa = p.d_pre_add ? acc + (na++) * D : nullptr;
-  for (int i = threadIdx.x; i < n_acc * D; i += blockDim.x) acc[i] = 0.f;
+  float* a_g2 = p.dg2 ? wacc + (na++) * D : nullptr;
+  float* a_b2 = p.db2 ? wacc + (na++) * D : nullptr;
+  float* a_g1 = p.dg1 ? wacc + (na++) * D : nullptr;
+  float* a_b1 = p.db1 ? wacc + (na++) * D : nullptr;
+  float* a_pa = p.d_pre_add ? wacc + (na++) * D : nullptr;
+  float* a_cs = p.dx_colsum ? wacc + (na++) * D : nullptr;
+  for (int i = threadIdx.x; i < kRows * n_acc * D; i += blockDim.x) acc[i] = 0.f;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -107,6 +116,13 @@ __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdPa
   const int nchunk = D >> 3;
   const int ngroups = (p.rows + kRows - 1) / kRows;
   uint32_t phase = 0;
+  auto acc8 = [](float* a, int c, const float (&v)[8]) {
+    float4* q = reinterpret_cast<float4*>(a + c * 8);
+    float4 u0 = q[0], u1 = q[1];
+    u0.x += v[0]; u0.y += v[1]; u0.z += v[2]; u0.w += v[3];
+    u1.x += v[4]; u1.y += v[5]; u1.z += v[6]; u1.w += v[7];
+    q[0] = u0; q[1] = u1;
+  };
 
   for (int g = blockIdx.x; g < ngroups; g += gridDim.x, phase ^= 1u) {
     const int row0 = g * kRows;
@@ -137,8 +153,14 @@ __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdPa
       const uint8_t* vr = vbuf + warp * v_bytes;
       const uint8_t* dyr = dybuf + warp * dy_bytes;
       float* dvr = reinterpret_cast<float*>(dvbuf + warp * dv_bytes);
+      float* tr = reinterpret_cast<float*>(tbuf + warp * t_bytes);
 
-      auto load_t = [&](int c, float (&t)[8]) {
+      // t = act(x) + pre_add; with an activation it is evaluated once (first sweep) and re-read from the stash
+      auto load_t = [&](int c, float (&t)[8], bool first) {
+        if (t_bytes && !first) {
+          ld8s(reinterpret_cast<const uint8_t*>(tr), SGF_F32, c * 8, t);
+          return;
+        }
         ld8s(xr, p.x_dtype, c * 8, t);
         if (p.x_act == SGF_ACT_GELU) {
 #pragma unroll
@@ -150,16 +172,17 @@ __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdPa
 #pragma unroll
           for (int j = 0; j < 8; ++j) t[j] += a[j];
         }
+        if (t_bytes) {
+          *reinterpret_cast<float4*>(tr + c * 8) = make_float4(t[0], t[1], t[2], t[3]);
+          *reinterpret_cast<float4*>(tr + c * 8 + 4) = make_float4(t[4], t[5], t[6], t[7]);
+        }
       };
-      auto load_v = [&](int c, float (&v)[8]) {
+      auto load_v = [&](int c, float (&v)[8], bool first) {
         if (v_bytes) ld8s(vr, p.v_dtype, c * 8, v);
-        else load_t(c, v);
+        else load_t(c, v, first);
       };
       auto finalize = [&](int c, float (&dt)[8]) {
-        if (a_pa) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) atomicAdd(a_pa + c * 8 + j, dt[j]);
-        }
+        if (a_pa) acc8(a_pa, c, dt);
         if (p.dx) {
           if (p.x_act == SGF_ACT_GELU) {
             float xv[8];
@@ -167,6 +190,7 @@ __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdPa
 #pragma unroll
             for (int j = 0; j < 8; ++j) dt[j] *= gelu_erf_grad(xv[j]);
           }
+          if (a_cs) acc8(a_cs, c, dt);
           const int64_t off = src_row * p.lddx + c * 8;
           if (p.dx_accumulate) {
             float o[8];
@@ -178,45 +202,39 @@ __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdPa
         }
       };
 
-      // ---- LayerNorm 2 adjoint: statistics of v, then the two row means ----
+      // ---- LayerNorm 2 adjoint: mean, then centred sums (variance + the two adjoint dot products) ----
       float mean2 = 0.f, rstd2 = 1.f, c1 = 0.f, c2 = 0.f;
-      if (p.g2 && dy_bytes) {
+      const bool ln2 = p.g2 && dy_bytes;
+      if (ln2) {
         float s = 0.f;
         for (int c = lane; c < nchunk; c += 32) {
           float v[8];
-          load_v(c, v);
+          load_v(c, v, true);
 #pragma unroll
           for (int j = 0; j < 8; ++j) s += v[j];
         }
         mean2 = warp_sum(s) * invD;
-        float q = 0.f;
-        for (int c = lane; c < nchunk; c += 32) {
-          float v[8];
-          load_v(c, v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float d = v[j] - mean2;
-            q += d * d;
-          }
-        }
-        rstd2 = rsqrtf(warp_sum(q) * invD + 1e-5f);
-        float a = 0.f, b = 0.f;
+        float q = 0.f, a = 0.f, b = 0.f;
         for (int c = lane; c < nchunk; c += 32) {
           float v[8], dy[8], gm[8];
-          load_v(c, v);
+          load_v(c, v, false);
           ld8s(dyr, p.dy2_dtype, c * 8, dy);
           ld8g(p.g2, SGF_F32, c * 8, gm);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            const float d = v[j] - mean2;
             const float gy = dy[j] * gm[j];
+            q += d * d;
             a += gy;
-            b += gy * (v[j] - mean2) * rstd2;
+            b += gy * d;
           }
         }
+        rstd2 = rsqrtf(warp_sum(q) * invD + 1e-5f);
         c1 = warp_sum(a) * invD;
-        c2 = warp_sum(b) * invD;
+        c2 = warp_sum(b) * invD * rstd2;
       }
-      // ---- dv = dv_in + LN2'(dy2) ----
+      // ---- dv = dv_in + LN2'(dy2) ; with LN1: also the mean of t ----
+      float s1 = 0.f;
       for (int c = lane; c < nchunk; c += 32) {
         float dv[8];
         if (p.dv_in) {
@@ -229,16 +247,17 @@ __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdPa
           float dy[8];
           ld8s(dyr, p.dy2_dtype, c * 8, dy);
           if (p.g2) {
-            float v[8], gm[8];
-            load_v(c, v);
+            float v[8], gm[8], gx[8];
+            load_v(c, v, false);
             ld8g(p.g2, SGF_F32, c * 8, gm);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float xh = (v[j] - mean2) * rstd2;
               dv[j] += rstd2 * (dy[j] * gm[j] - c1 - xh * c2);
-              if (a_g2) atomicAdd(a_g2 + c * 8 + j, dy[j] * xh);
-              if (a_b2) atomicAdd(a_b2 + c * 8 + j, dy[j]);
+              gx[j] = dy[j] * xh;
             }
+            if (a_g2) acc8(a_g2, c, gx);
+            if (a_b2) acc8(a_b2, c, dy);
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) dv[j] += dy[j];
@@ -250,55 +269,45 @@ __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdPa
         } else {
           *reinterpret_cast<float4*>(dvr + c * 8) = make_float4(dv[0], dv[1], dv[2], dv[3]);
           *reinterpret_cast<float4*>(dvr + c * 8 + 4) = make_float4(dv[4], dv[5], dv[6], dv[7]);
+          float t[8];
+          load_t(c, t, true);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s1 += t[j];
         }
       }
       // ---- LayerNorm 1 adjoint ----
       if (p.g1) {
-        float s = 0.f;
-        for (int c = lane; c < nchunk; c += 32) {
-          float t[8];
-          load_t(c, t);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) s += t[j];
-        }
-        const float mean1 = warp_sum(s) * invD;
-        float q = 0.f;
-        for (int c = lane; c < nchunk; c += 32) {
-          float t[8];
-          load_t(c, t);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float d = t[j] - mean1;
-            q += d * d;
-          }
-        }
-        const float rstd1 = rsqrtf(warp_sum(q) * invD + 1e-5f);
-        float a = 0.f, b = 0.f;
+        const float mean1 = warp_sum(s1) * invD;
+        float q = 0.f, a = 0.f, b = 0.f;
         for (int c = lane; c < nchunk; c += 32) {
           float t[8], dv[8], gm[8];
-          load_t(c, t);
+          load_t(c, t, false);
           ld8s(reinterpret_cast<const uint8_t*>(dvr), SGF_F32, c * 8, dv);
           ld8g(p.g1, SGF_F32, c * 8, gm);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            const float d = t[j] - mean1;
             const float gy = dv[j] * gm[j];
+            q += d * d;
             a += gy;
-            b += gy * (t[j] - mean1) * rstd1;
+            b += gy * d;
           }
         }
-        const float d1 = warp_sum(a) * invD, d2 = warp_sum(b) * invD;
+        const float rstd1 = rsqrtf(warp_sum(q) * invD + 1e-5f);
+        const float d1 = warp_sum(a) * invD, d2 = warp_sum(b) * invD * rstd1;
         for (int c = lane; c < nchunk; c += 32) {
-          float t[8], dv[8], gm[8], dt[8];
-          load_t(c, t);
+          float t[8], dv[8], gm[8], dt[8], gx[8];
+          load_t(c, t, false);
           ld8s(reinterpret_cast<const uint8_t*>(dvr), SGF_F32, c * 8, dv);
           ld8g(p.g1, SGF_F32, c * 8, gm);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float th = (t[j] - mean1) * rstd1;
             dt[j] = rstd1 * (dv[j] * gm[j] - d1 - th * d2);
-            if (a_g1) atomicAdd(a_g1 + c * 8 + j, dv[j] * th);
-            if (a_b1) atomicAdd(a_b1 + c * 8 + j, dv[j]);
+            gx[j] = dv[j] * th;
           }
+          if (a_g1) acc8(a_g1, c, gx);
+          if (a_b1) acc8(a_b1, c, dv);
           finalize(c, dt);
         }
       }
@@ -306,17 +315,19 @@ __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdPa
     fence_proxy_async();  // generic-proxy accesses to the staging rows are ordered before the next bulk loads
     __syncthreads();
   }
-  // ---- flush the per-CTA parameter-gradient partials ----
+  // ---- sum the per-warp partials and flush: one global atomic per column per CTA ----
   na = 0;
-  float* outs[5];
+  float* outs[6];
   if (p.dg2) outs[na++] = p.dg2;
   if (p.db2) outs[na++] = p.db2;
   if (p.dg1) outs[na++] = p.dg1;
   if (p.db1) outs[na++] = p.db1;
   if (p.d_pre_add) outs[na++] = p.d_pre_add;
+  if (p.dx_colsum) outs[na++] = p.dx_colsum;
   for (int a = 0; a < na; ++a)
     for (int i = threadIdx.x; i < D; i += blockDim.x) {
-      const float v = acc[a * D + i];
+      float v = 0.f;
+      for (int w = 0; w < kRows; ++w) v += acc[(static_cast<size_t>(w) * n_acc + a) * D + i];
       if (v != 0.f) atomicAdd(outs[a] + i, v);
     }
 }
@@ -380,13 +391,245 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const TIn* __restri
 }
 
 // ----------------------------------------------------------------------------------------
+// Wide rows (the FFN's z = LN(gelu(h)), F = 1024..4096): one CTA of 128 threads per row, the row lives in
+// REGISTERS (thread t owns the 8-column chunks t, t+128, ...), statistics by warp shuffles + one shared-memory
+// exchange, parameter-gradient partials in registers across all the rows a CTA walks (one global atomic per
+// column per CTA at the end).  No shared-memory staging, 4-5 CTAs per SM.
+// ----------------------------------------------------------------------------------------
+template <int NV>
+SGF_DEVICE void block_sum4(float (&v)[NV], float* red /* [4*NV] */) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[(threadIdx.x >> 5) * NV + i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = (red[i] + red[NV + i]) + (red[2 * NV + i] + red[3 * NV + i]);
+}
+
+SGF_DEVICE void unpack8(const uint4& u, float (&v)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+// Phi(x) (normal CDF) with the same rational erf as gelu_erf; gelu(x) = x * Phi(x)
+SGF_DEVICE float gelu_cdf(float x, float& e_out) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = fast_exp2(-1.4426950408889634f * z * z);
+  e_out = e;
+  return 0.5f * (1.0f + copysignf(fmaf(-p * t, e, 1.0f), x));
+}
+
+template <int NC>
+__global__ void __launch_bounds__(128) gelu_ln_fwd_wide_kernel(const __nv_bfloat16* __restrict__ h, int64_t ldh,
+                                                               const float* __restrict__ gam, const float* __restrict__ bet,
+                                                               __nv_bfloat16* __restrict__ z, int64_t ldz, int rows, int F) {
+  __shared__ float red[2][4];
+  pdl_trigger();
+  pdl_wait();
+  const float invF = 1.0f / static_cast<float>(F);
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    float t[NC][8];
+    float s[1] = {0.f};
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int col = (k * 128 + threadIdx.x) * 8;
+      if (col < F) {
+        const uint4 u = *reinterpret_cast<const uint4*>(h + static_cast<int64_t>(row) * ldh + col);
+        unpack8(u, t[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          t[k][j] = gelu_erf(t[k][j]);
+          s[0] += t[k][j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[k][j] = 0.f;
+      }
+    }
+    block_sum4<1>(s, red[0]);
+    const float mean = s[0] * invF;
+    float q[1] = {0.f};
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      if ((k * 128 + threadIdx.x) * 8 < F) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = t[k][j] - mean;
+          q[0] += d * d;
+        }
+      }
+    }
+    block_sum4<1>(q, red[1]);
+    const float rstd = rsqrtf(q[0] * invF + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int col = (k * 128 + threadIdx.x) * 8;
+      if (col < F) {
+        float g[8], b[8], o[8];
+        ld8g(gam, SGF_F32, col, g);
+        ld8g(bet, SGF_F32, col, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (t[k][j] - mean) * rstd * g[j] + b[j];
+        st8g(z, SGF_BF16, static_cast<int64_t>(row) * ldz + col, o);
+      }
+    }
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(128) gelu_ln_bwd_wide_kernel(const __nv_bfloat16* __restrict__ h, int64_t ldh,
+                                                               const __nv_bfloat16* __restrict__ dz, int64_t lddz,
+                                                               const float* __restrict__ gam,
+                                                               __nv_bfloat16* __restrict__ dh, int64_t lddh,
+                                                               float* __restrict__ dgam, float* __restrict__ dbet,
+                                                               float* __restrict__ dh_colsum, int rows, int F) {
+  __shared__ float red[2][12];
+  pdl_trigger();
+  pdl_wait();
+  const float invF = 1.0f / static_cast<float>(F);
+  float ag[NC][8], ab[NC][8], ac[NC][8];
+#pragma unroll
+  for (int k = 0; k < NC; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[k][j] = ab[k][j] = ac[k][j] = 0.f;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    uint4 hx[NC];
+    float cdf[NC][8], dzv[NC][8];  // Phi(h) and dz
+    float s[1] = {0.f};
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int col = (k * 128 + threadIdx.x) * 8;
+      if (col < F) {
+        hx[k] = *reinterpret_cast<const uint4*>(h + static_cast<int64_t>(row) * ldh + col);
+        const uint4 ud = *reinterpret_cast<const uint4*>(dz + static_cast<int64_t>(row) * lddz + col);
+        unpack8(ud, dzv[k]);
+        float x[8];
+        unpack8(hx[k], x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float e;
+          cdf[k][j] = gelu_cdf(x[j], e);
+          s[0] += x[j] * cdf[k][j];
+        }
+      } else {
+        hx[k] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cdf[k][j] = dzv[k][j] = 0.f;
+      }
+    }
+    block_sum4<1>(s, red[0]);
+    const float mean = s[0] * invF;
+    float r3[3] = {0.f, 0.f, 0.f};  // sum (t-mean)^2, sum dz*gamma, sum dz*gamma*(t-mean)
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int col = (k * 128 + threadIdx.x) * 8;
+      if (col < F) {
+        float x[8], g[8];
+        unpack8(hx[k], x);
+        ld8g(gam, SGF_F32, col, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = x[j] * cdf[k][j] - mean;
+          const float gy = dzv[k][j] * g[j];
+          r3[0] += d * d;
+          r3[1] += gy;
+          r3[2] += gy * d;
+        }
+      }
+    }
+    block_sum4<3>(r3, red[1]);
+    const float rstd = rsqrtf(r3[0] * invF + 1e-5f);
+    const float c1 = r3[1] * invF, c2 = r3[2] * invF * rstd;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int col = (k * 128 + threadIdx.x) * 8;
+      if (col < F) {
+        float x[8], g[8], o[8];
+        unpack8(hx[k], x);
+        ld8g(gam, SGF_F32, col, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (x[j] * cdf[k][j] - mean) * rstd;
+          const float dt = rstd * (dzv[k][j] * g[j] - c1 - xh * c2);
+          const float e = fast_exp2(-0.72134752044448170368f * x[j] * x[j]);  // exp(-x^2/2)
+          o[j] = dt * fmaf(x[j] * 0.3989422804014327f, e, cdf[k][j]);          // * gelu'(x) = Phi + x phi
+          ag[k][j] = fmaf(dzv[k][j], xh, ag[k][j]);
+          ab[k][j] += dzv[k][j];
+          ac[k][j] += o[j];
+        }
+        st8g(dh, SGF_BF16, static_cast<int64_t>(row) * lddh + col, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int col = (k * 128 + threadIdx.x) * 8;
+    if (col < F) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (dgam) atomicAdd(dgam + col + j, ag[k][j]);
+        if (dbet) atomicAdd(dbet + col + j, ab[k][j]);
+        if (dh_colsum) atomicAdd(dh_colsum + col + j, ac[k][j]);
+      }
+    }
+  }
+}
+
+// column sums of a bf16 [M,N] matrix (bias gradients): block = 256 columns x 256 rows, warp w walks rows w, w+8, ...
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int M, int N,
+                                                          float* __restrict__ out) {
+  __shared__ float part[8][256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * 256;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < N) {
+    const int r1 = min(r0 + 256, M);
+#pragma unroll 4
+    for (int r = r0 + warp; r < r1; r += 8) {
+      float v[8];
+      if (c + 8 <= N) {
+        ld8g(x, SGF_BF16, static_cast<int64_t>(r) * ld + c, v);
+      } else {
+        for (int j = 0; j < 8; ++j) v[j] = c + j < N ? __bfloat162float(x[static_cast<int64_t>(r) * ld + c + j]) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w][threadIdx.x];
+    atomicAdd(out + col, s);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // fused Adam(W) over a flat fp32 buffer; sum of squares
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                                                         float b1, float b2, float eps, float wd, float bc1, float bc2,
+                                                        const int32_t* __restrict__ step_dev,
                                                         const float* __restrict__ grad_scale) {
   const float gs = grad_scale ? grad_scale[0] : 1.0f;
+  if (step_dev) {
+    const float t = static_cast<float>(step_dev[0]);
+    bc1 = 1.0f - powf(b1, t);
+    bc2 = sqrtf(1.0f - powf(b2, t));
+  }
   const int64_t i0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) * 4;
   if (i0 >= n) return;
   if (i0 + 4 <= n) {
@@ -467,17 +710,42 @@ extern "C" int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* a, void* stream) 
   if (a->dv_in)
     SGF_REQUIRE(reinterpret_cast<uintptr_t>(a->dv_in) % 16 == 0 && (a->lddv * 4) % 16 == 0,
                 "row_layernorm_bwd: dv_in alignment");
-  const int n_acc = (a->dg2 ? 1 : 0) + (a->db2 ? 1 : 0) + (a->dg1 ? 1 : 0) + (a->db1 ? 1 : 0) + (a->d_pre_add ? 1 : 0);
-  const int per_row = x_bytes + v_bytes + dy_bytes + dv_bytes;
-  const int fixed = n_acc * a->D * 4 + 16;
+  // wide FFN rows: register-resident specialisation
+  if (a->x_act == SGF_ACT_GELU && !a->g1 && !a->v && !a->dv_in && !a->d_res && !a->gather_idx && !a->pre_add && a->g2 &&
+      a->dy2 && a->dy2_dtype == SGF_BF16 && a->x_dtype == SGF_BF16 && a->dx && a->dx_dtype == SGF_BF16 &&
+      !a->dx_accumulate && a->seg_len == 0 && a->D >= 1024 && a->D <= 4096 && !a->dg1 && !a->db1 && !a->d_pre_add) {
+    const int nc = (a->D + 1023) / 1024;
+    int grid = a->rows < 148 * 5 ? a->rows : 148 * 5;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    auto h = reinterpret_cast<const __nv_bfloat16*>(a->x);
+    auto dz = reinterpret_cast<const __nv_bfloat16*>(a->dy2);
+    auto dh = reinterpret_cast<__nv_bfloat16*>(a->dx);
+#define SGF_WIDE_BWD(NC)                                                                                          \
+  SGF_CHECK_CUDA(launch_pdl(gelu_ln_bwd_wide_kernel<NC>, dim3(grid), dim3(128), size_t(0), st, h, a->ldx, dz, a->ldy2,   \
+                            a->g2, dh, a->lddx, a->dg2, a->db2, a->dx_colsum, a->rows, a->D))
+    if (nc == 1) SGF_WIDE_BWD(1);
+    else if (nc == 2) SGF_WIDE_BWD(2);
+    else if (nc == 3) SGF_WIDE_BWD(3);
+    else SGF_WIDE_BWD(4);
+#undef SGF_WIDE_BWD
+    count_launch();
+    return SGF_OK;
+  }
+  const int n_acc = (a->dg2 ? 1 : 0) + (a->db2 ? 1 : 0) + (a->dg1 ? 1 : 0) + (a->db1 ? 1 : 0) + (a->d_pre_add ? 1 : 0) +
+                    (a->dx_colsum ? 1 : 0);
+  const int t_bytes = (a->x_act != SGF_ACT_NONE && x_used) ? a->D * 4 : 0;
+  const int per_row = x_bytes + v_bytes + dy_bytes + dv_bytes + t_bytes + n_acc * a->D * 4;
+  const int fixed = 16;
   int kRows = 8;
-  while (kRows > 1 && kRows * per_row + fixed > 100 * 1024) kRows >>= 1;
+  while (kRows > 1 && kRows * per_row + fixed > 110 * 1024) kRows >>= 1;  // two CTAs per SM when possible
+  if (kRows < 4 && 4 * per_row + fixed <= 200 * 1024) kRows = 4;         // wide rows: one CTA of 4 warps
+  else if (kRows < 2 && 2 * per_row + fixed <= 200 * 1024) kRows = 2;
   const int smem = kRows * per_row + fixed;
   SGF_REQUIRE(smem <= 200 * 1024, "row_layernorm_bwd: D=%d needs %d B of shared memory", a->D, smem);
   RowLnBwdParams p{a->x, a->ldx, a->x_dtype, a->gather_idx, a->x_act, a->pre_add, a->g1, a->v, a->ldv, a->v_dtype,
                    a->g2, a->dy2, a->ldy2, a->dy2_dtype, a->dv_in, a->lddv, a->d_res, a->ldres, a->dx, a->lddx,
                    a->dx_dtype, a->dx_accumulate, a->dg1, a->db1, a->dg2, a->db2, a->d_pre_add, a->rows, a->D,
-                   a->seg_len, a->seg_stride, a->seg_off};
+                   a->seg_len, a->seg_stride, a->seg_off, a->dx_colsum};
   static bool configured = false;
   if (!configured) {
     SGF_CHECK_CUDA(cudaFuncSetAttribute(row_layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -487,10 +755,30 @@ extern "C" int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* a, void* stream) 
   const int per_sm = smem > 110 * 1024 ? 1 : 2;
   const int grid = ngroups < 148 * per_sm ? ngroups : 148 * per_sm;
   SGF_CHECK_CUDA(launch_pdl(row_layernorm_bwd_kernel, dim3(grid), dim3(kRows * 32), static_cast<size_t>(smem),
-                            reinterpret_cast<cudaStream_t>(stream), p, x_bytes, v_bytes, dy_bytes, dv_bytes, n_acc));
+                            reinterpret_cast<cudaStream_t>(stream), p, x_bytes, v_bytes, dy_bytes, dv_bytes, t_bytes, n_acc));
   count_launch();
   return SGF_OK;
 }
+
+namespace sgf {
+// called by sgf_row_layernorm (rowops.cu) for the x_act == GELU, F-wide, plain LN2 pattern
+int launch_gelu_ln_fwd_wide(const void* h, int64_t ldh, const float* g, const float* b, void* z, int64_t ldz, int rows,
+                            int F, cudaStream_t st) {
+  const int nc = (F + 1023) / 1024;
+  const int grid = rows < 148 * 6 ? rows : 148 * 6;
+  auto hp = reinterpret_cast<const __nv_bfloat16*>(h);
+  auto zp = reinterpret_cast<__nv_bfloat16*>(z);
+#define SGF_WIDE_FWD(NC) \
+  SGF_CHECK_CUDA(launch_pdl(gelu_ln_fwd_wide_kernel<NC>, dim3(grid), dim3(128), size_t(0), st, hp, ldh, g, b, zp, ldz, rows, F))
+  if (nc == 1) SGF_WIDE_FWD(1);
+  else if (nc == 2) SGF_WIDE_FWD(2);
+  else if (nc == 3) SGF_WIDE_FWD(3);
+  else SGF_WIDE_FWD(4);
+#undef SGF_WIDE_FWD
+  count_launch();
+  return SGF_OK;
+}
+}  // namespace sgf
 
 extern "C" int sgf_transpose_cast(const void* in, int32_t in_dtype, int64_t ld_in, int32_t M, int32_t N, void* out_t,
                                   int64_t ld_t, void* out_c, int64_t ld_c, float* colsum, void* stream) {
@@ -501,8 +789,15 @@ extern "C" int sgf_transpose_cast(const void* in, int32_t in_dtype, int64_t ld_i
               "transpose_cast: ld_t must be a multiple of 8 and >= M rounded up to 8");
   SGF_REQUIRE(!out_c || (ld_c % 8 == 0 && ld_c >= N && reinterpret_cast<uintptr_t>(out_c) % 16 == 0),
               "transpose_cast: ld_c must be a multiple of 8 and >= N");
-  dim3 grid((N + 63) / 64, (M + 63) / 64), block(256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!out_t && !out_c && in_dtype == SGF_BF16) {  // column sums only: dedicated streaming kernel
+    dim3 cgrid((N + 255) / 256, (M + 255) / 256);
+    colsum_bf16_kernel<<<cgrid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld_in, M, N, colsum);
+    SGF_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return SGF_OK;
+  }
+  dim3 grid((N + 63) / 64, (M + 63) / 64), block(256);
   if (in_dtype == SGF_F32)
     transpose_cast_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(in), ld_in, M, N,
                                                          reinterpret_cast<__nv_bfloat16*>(out_t), ld_t,
@@ -518,8 +813,8 @@ extern "C" int sgf_transpose_cast(const void* in, int32_t in_dtype, int64_t ld_i
 
 extern "C" int sgf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                              float beta1, float beta2, float eps, float weight_decay, int32_t step,
-                             const float* grad_scale, void* stream) {
-  SGF_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step > 0, "adam_step: bad arguments");
+                             const int32_t* step_dev, const float* grad_scale, void* stream) {
+  SGF_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && (step > 0 || step_dev), "adam_step: bad arguments");
   SGF_REQUIRE((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) % 16 == 0,
               "adam_step: buffers must be 16-byte aligned");
@@ -527,7 +822,7 @@ extern "C" int sgf_adam_step(float* param, const float* grad, float* exp_avg, fl
   const float bc2 = sqrtf(1.0f - powf(beta2, static_cast<float>(step)));
   const int64_t threads = (n + 3) / 4;
   adam_step_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, step_dev, grad_scale);
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return SGF_OK;

@@ -40,7 +40,11 @@ class _ConvW:
 
 
 class SegOFAEngine:
-    def __init__(self, model):
+    def __init__(self, model, live=None):
+        # live = a SegOFATrainEngine: trainable operands are then VIEWS of its bf16 operand buffers / fp32 master
+        # arena, so this engine follows every optimizer step without being rebuilt (the trainer's no-grad
+        # real-image pass, seg_criterion.py:185).  ffn_layernorm is not folded in that mode (derived weights).
+        self.live = live
         self.cfg: SegOFAConfig = model.cfg
         p = next(model.parameters())
         if not p.is_cuda:
@@ -59,7 +63,7 @@ class SegOFAEngine:
         # dropped with the engine whenever the model's parameters may change (SegOFAModel.invalidate_engine).
         self.cache_position_bias = True
         # ffn_layernorm folded into the fc1/fc2 epilogues (default) or run as a separate row kernel
-        self.fold_ffn_layernorm = os.environ.get("SGF_FOLD_FFN_LN", "1") != "0"
+        self.fold_ffn_layernorm = os.environ.get("SGF_FOLD_FFN_LN", "1") != "0" and live is None
         self._bias_cache: Dict = {}
         with torch.no_grad():
             self._prepare(model)
@@ -68,10 +72,25 @@ class SegOFAEngine:
     # parameter preparation (derived device tensors; rebuilt whenever the model invalidates)
     # ------------------------------------------------------------------------------------
     def _f32(self, t):
+        if self.live is not None and self.live.arena.has(t):
+            return t.data  # live view of the fp32 master
         return t.detach().to(device=self.device, dtype=torch.float32).contiguous()
 
     def _b16(self, t):
+        if self.live is not None:
+            d = self.live.dense_index.get((id(t),))
+            if d is not None:
+                return d.w16
         return t.detach().to(device=self.device, dtype=_BF16).contiguous()
+
+    def _fused(self, weights, biases):
+        """bf16 [sum N, K] weight and fp32 bias of several nn.Linear fused along the output dimension."""
+        if self.live is not None:
+            d = self.live.dense_index.get(tuple(id(w) for w in weights))
+            if d is not None:
+                return d.w16, d.b32
+        return (self._b16(torch.cat([w.detach() for w in weights], 0)),
+                self._f32(torch.cat([b.detach() for b in biases], 0)))
 
     def _ln(self, m):
         return (self._f32(m.weight), self._f32(m.bias))
@@ -97,11 +116,11 @@ class SegOFAEngine:
         d = {}
         if cross:
             d["wq"], d["bq"] = self._b16(m.q_proj.weight), self._f32(m.q_proj.bias)
-            d["wkv"] = self._b16(torch.cat([m.k_proj.weight, m.v_proj.weight], 0))
-            d["bkv"] = self._f32(torch.cat([m.k_proj.bias, m.v_proj.bias], 0))
+            if self.live is None:  # (live: only the all-layer fused operand w_cross_kv_all exists)
+                d["wkv"], d["bkv"] = self._fused([m.k_proj.weight, m.v_proj.weight], [m.k_proj.bias, m.v_proj.bias])
         else:
-            d["wqkv"] = self._b16(torch.cat([m.q_proj.weight, m.k_proj.weight, m.v_proj.weight], 0))
-            d["bqkv"] = self._f32(torch.cat([m.q_proj.bias, m.k_proj.bias, m.v_proj.bias], 0))
+            d["wqkv"], d["bqkv"] = self._fused([m.q_proj.weight, m.k_proj.weight, m.v_proj.weight],
+                                               [m.q_proj.bias, m.k_proj.bias, m.v_proj.bias])
         d["wo"], d["bo"] = self._b16(m.out_proj.weight), self._f32(m.out_proj.bias)
         d["c_attn"] = self._f32(m.c_attn) if m.c_attn is not None else None
         return d
@@ -109,6 +128,8 @@ class SegOFAEngine:
     def _ffn_fold(self, layer):
         """ffn_layernorm folded into fc2 (see sgf_gemm_args row-norm): W2' = W2 * gamma, u = rowsum(W2'),
         c = b2 + W2 beta."""
+        if self.live is not None:
+            return dict(w2=self._b16(layer.fc2.weight), b2=self._f32(layer.fc2.bias), ln_ffn=self._ln(layer.ffn_layernorm))
         w2 = layer.fc2.weight.detach().float().to(self.device)
         g, b = layer.ffn_layernorm.weight.detach().float().to(self.device), layer.ffn_layernorm.bias.detach().float().to(self.device)
         w2f = (w2 * g.unsqueeze(0)).to(_BF16).contiguous()
@@ -169,8 +190,13 @@ class SegOFAEngine:
                 ln_final=self._ln(l.final_layer_norm),
                 w1=self._b16(l.fc1.weight), b1=self._f32(l.fc1.bias), **self._ffn_fold(l)))
         # all decoder layers' cross-attention K/V projections of encoder_out as ONE GEMM (N = L*2D)
-        self.w_cross_kv_all = torch.cat([d["cross"]["wkv"] for d in self.dec_layers], 0).contiguous()
-        self.b_cross_kv_all = torch.cat([d["cross"]["bkv"] for d in self.dec_layers], 0).contiguous()
+        if self.live is not None:
+            self.w_cross_kv_all, self.b_cross_kv_all = self._fused(
+                [w for l in dec.layers for w in (l.encoder_attn.k_proj.weight, l.encoder_attn.v_proj.weight)],
+                [b for l in dec.layers for b in (l.encoder_attn.k_proj.bias, l.encoder_attn.v_proj.bias)])
+        else:
+            self.w_cross_kv_all = torch.cat([d["cross"]["wkv"] for d in self.dec_layers], 0).contiguous()
+            self.b_cross_kv_all = torch.cat([d["cross"]["bkv"] for d in self.dec_layers], 0).contiguous()
         self.ln_dec_out = self._ln(dec.layer_norm)
         self.dec_seg_rel = [self._f32(t.weight) for t in dec.seg_rel_pos_table_list]
         self.seg_rp_bucket = dec.seg_rp_bucket.to(self.device)

@@ -117,6 +117,23 @@ def gemm(a, b, out=None, *, bias=None, scale=None, residual=None, act=ACT_NONE, 
     return out
 
 
+def gemm_ex(a, b, out, *, M, N, K, a_mn, b_mn, lda=None, ldb=None, ldc=None, split_k=1, tag=None):
+    """out[M,N] (+)= A_eff @ B_eff^T with MN-major operands (see sgf_gemm_bf16_ex): a is [K,M] when a_mn else [M,K];
+    b is [K,N] when b_mn else [N,K].  split_k > 1 accumulates into the fp32 `out`."""
+    lib = _lib.load()
+    _req(a, torch.bfloat16, "a")
+    _req(b, torch.bfloat16, "b")
+    lda = a.stride(-2) if lda is None else lda
+    ldb = b.stride(-2) if ldb is None else ldb
+    ldc = out.stride(-2) if ldc is None else ldc
+    args = _lib.GemmArgs(_p(a), lda, 0, _p(b), ldb, 0, _p(out), ldc, 0, _DT[out.dtype], M, N, K, 1, None, None, None, 0, 0,
+                         SGF_BF16, ACT_NONE, 1.0, 0, None, None, None, 0)
+    with _timed("gemm_tcgen05" + (":" + tag if tag and _TIMER is not None and _TIMER.fine else ""), 2.0 * M * N * K):
+        _lib.check(lib.sgf_gemm_bf16_ex(C.byref(args), 1 if a_mn else 0, 1 if b_mn else 0, int(split_k), _stream()),
+                   "sgf_gemm_bf16_ex")
+    return out
+
+
 def conv3x3_s1(x, w, scale, bias, act=ACT_RELU, out=None, tag=None):
     """x [N,H,W,Cin] bf16 NHWC, w [Cout,3,3,Cin] bf16 -> [N,H,W,Cout] bf16."""
     lib = _lib.load()
@@ -319,7 +336,7 @@ def upsample_ce_loss_bwd(logits, target, lse, count, hp, wp, dlogits, label_smoo
 
 def row_layernorm_bwd(*, rows, D, x=None, ldx=None, gather_idx=None, x_act=ACT_NONE, pre_add=None, g1=None, v=None,
                       g2=None, dy2=None, dv_in=None, d_res=None, dx=None, dx_accumulate=False, dg1=None, db1=None,
-                      dg2=None, db2=None, d_pre_add=None, seg=None):
+                      dg2=None, db2=None, d_pre_add=None, seg=None, dx_colsum=None):
     """Adjoint of row_layernorm (see sgf_row_layernorm_bwd in include/segofa_b200.h)."""
     lib = _lib.load()
     seg_len, seg_stride, seg_off = seg if seg is not None else (0, 0, 0)
@@ -334,7 +351,7 @@ def row_layernorm_bwd(*, rows, D, x=None, ldx=None, gather_idx=None, x_act=ACT_N
         _p(x), ld(x) if ldx is None else ldx, dt(x), _p(gather_idx), int(x_act), _p(pre_add), _p(g1),
         _p(v), ld(v), dt(v), _p(g2), _p(dy2), ld(dy2), dt(dy2), _p(dv_in), ld(dv_in), _p(d_res), ld(d_res),
         _p(dx), ld(dx), dt(dx), 1 if dx_accumulate else 0, _p(dg1), _p(db1), _p(dg2), _p(db2), _p(d_pre_add),
-        rows, D, seg_len, seg_stride, seg_off)
+        rows, D, seg_len, seg_stride, seg_off, _p(dx_colsum))
     nb = rows * D * sum(t.element_size() for t in (x, v, dy2, dv_in, d_res, dx) if t is not None)
     with _timed("row_layernorm_bwd", nbytes=float(nb)):
         _lib.check(lib.sgf_row_layernorm_bwd(C.byref(args), _stream()), "sgf_row_layernorm_bwd")
@@ -377,14 +394,14 @@ def attention_bwd(q, k, v, out, dout, dq, dk, dv, *, B, H, Tq, Tk, q_strides, k_
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1,
-              grad_scale=None):
+              step_dev=None, grad_scale=None):
     lib = _lib.load()
     for t, n in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
         _req(t, torch.float32, n)
     with _timed("adam", nbytes=float(param.numel() * 28)):
         _lib.check(lib.sgf_adam_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr),
                                      float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
-                                     _p(grad_scale), _stream()), "sgf_adam_step")
+                                     _p(step_dev), _p(grad_scale), _stream()), "sgf_adam_step")
 
 
 def sumsq(x, out):

@@ -250,3 +250,39 @@ def synthetic_inputs(cfg: SegOFAConfig, batch: int, image_size: int, seed: int =
         patch_images=images,
         patch_masks=torch.ones(batch, dtype=torch.bool),
     )
+
+
+def synthetic_train_sample(cfg: SegOFAConfig, batch: int, image_size: int, seed: int = 1, src_tokens=None,
+                           seg_id_offset: int = 59457):
+    """Seeded host sample of one image-free training step in the layout SegmentationDataset.collate produces
+    (data/mm_data/segmentation_dataset.py:303-347, artificial_image_type='rand_k-1-33'): per sample a random
+    sh x sw label grid (sh, sw ~ U{1..32}, labels ~ U{0..C-1}) nearest-resized to the (S/16)^2 patch grid (ragged
+    bags of the class-name BPE tokens -> aux_input.patch_images / patch_masks = cumulative bag ends) and to the
+    S^2 pixel grid (text2seg_target, dictionary ids + eos); plus the real-image net_input and a random target
+    for the no-grad metric pass.  Class-name tokens: stand-in slices of the prompt (1-3 tokens per class)."""
+    inp = synthetic_inputs(cfg, batch, image_size, seed, src_tokens)
+    g = torch.Generator().manual_seed(seed + 1000)
+    C, S = cfg.num_seg, image_size
+    hp = S // 16
+    tok = inp["src_tokens"][0]
+    names = [tok[(13 + n) % (len(tok) - 3): (13 + n) % (len(tok) - 3) + 1 + n % 3] for n in range(C)]
+    bags, ends, t2s = [], [], []
+    for _ in range(batch):
+        sh, sw = (int(torch.randint(1, 33, (1,), generator=g)) for _ in range(2))
+        grid = torch.randint(0, C, (1, 1, sh, sw), generator=g).float()
+        low = torch.nn.functional.interpolate(grid, size=(hp, hp), mode="nearest").long().reshape(-1)
+        full = torch.nn.functional.interpolate(grid, size=(S, S), mode="nearest").long().reshape(-1)
+        toks = [names[int(c)] for c in low]
+        bags.append(torch.cat(toks))
+        ends.append(torch.tensor([len(t) for t in toks]).cumsum(0))
+        t2s.append(torch.cat([full + seg_id_offset, torch.tensor([2])]))
+    L = max(len(b) for b in bags)
+    bag_tokens = torch.full((batch, L), cfg.padding_idx, dtype=torch.long)
+    for b in range(batch):
+        bag_tokens[b, : len(bags[b])] = bags[b]
+    aux = dict(src_tokens=inp["src_tokens"], src_lengths=inp["src_lengths"], patch_images=bag_tokens,
+               patch_masks=torch.cat(ends), prev_output_tokens=inp["prev_output_tokens"])
+    target = torch.cat([torch.randint(0, C + 1, (batch, S * S), generator=g) + seg_id_offset,
+                        torch.full((batch, 1), 2)], 1)
+    return dict(net_input=inp, aux_input=aux, target=target, text2seg_target=torch.stack(t2s),
+                ntokens=batch * (hp * hp + 1), nsentences=batch)

@@ -107,7 +107,9 @@ class SegOFATrainEngine:
         # the inference engine provides the (batch-invariant) position bias and the real-image no-grad pass
         self.inf: Optional[SegOFAEngine] = None
         self.accumulate = False
+        self.grad_sync = None  # callable(lo, hi): gradient range [lo,hi) of arena.grad32 is final (DDP bucket)
         self.step_count = 0
+        self._step_dev = None
         self._scratch: Dict = {}
         self.refresh_weights()
 
@@ -115,13 +117,20 @@ class SegOFATrainEngine:
     # parameters
     # ------------------------------------------------------------------------------------
     def _build_arena(self):
+        """Arena order = forward order (encoder embeddings, encoder layers, encoder.layer_norm, fused cross k/v,
+        decoder embeddings, decoder layers, decoder.layer_norm): the backward finalises gradients from the top of
+        the arena downwards, so every all-reduce bucket is one contiguous range (`_sync_down`)."""
         m = self.model
         enc, dec = m.encoder, m.decoder
         groups: List[List[torch.nn.Parameter]] = []
+        marks: Dict = {}
         taken = set()
+        self._no_grad_names = []
+        cross_kv_ids = {id(p) for l in dec.layers for p in (l.encoder_attn.k_proj.weight, l.encoder_attn.v_proj.weight,
+                                                            l.encoder_attn.k_proj.bias, l.encoder_attn.v_proj.bias)}
 
         def add(ps):
-            ps = [p for p in ps if p is not None]
+            ps = [p for p in ps if p is not None and id(p) not in taken]
             if not ps:
                 return
             req = [p.requires_grad for p in ps]
@@ -140,26 +149,51 @@ class SegOFATrainEngine:
                 add([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias])
             add([a.out_proj.weight]); add([a.out_proj.bias]); add([a.c_attn])
 
-        for l in enc.layers:
+        def rest(module, prefix, skip_children=()):
+            for name, p in module.named_parameters():
+                if any(name.startswith(c + ".") for c in skip_children) or id(p) in cross_kv_ids:
+                    continue
+                if not p.requires_grad or id(p) in taken:
+                    continue
+                if self._is_bias_path(prefix + name):
+                    self._no_grad_names.append(prefix + name)
+                    continue
+                add([p])
+
+        rest(enc, "encoder.", skip_children=("layers", "layer_norm", "embed_images"))
+        for i, l in enumerate(enc.layers):
+            marks[("enc", i)] = len(groups)
             attn(l.self_attn, False)
+            rest(l, f"encoder.layers.{i}.")
+        marks[("enc", len(enc.layers))] = len(groups)
+        rest(enc.layer_norm, "encoder.layer_norm.")
+        marks["cross_kv"] = len(groups)
         add([w for l in dec.layers for w in (l.encoder_attn.k_proj.weight, l.encoder_attn.v_proj.weight)])
         add([b for l in dec.layers for b in (l.encoder_attn.k_proj.bias, l.encoder_attn.v_proj.bias)])
-        for l in dec.layers:
+        rest(dec, "decoder.", skip_children=("layers", "layer_norm"))
+        for i, l in enumerate(dec.layers):
+            marks[("dec", i)] = len(groups)
             attn(l.self_attn, False)
             attn(l.encoder_attn, True)
-        # everything else that is trainable AND receives a gradient from this engine
-        self._no_grad_names = []
-        for name, p in m.named_parameters():
-            if not p.requires_grad or id(p) in taken:
-                continue
-            if self._is_bias_path(name):
-                self._no_grad_names.append(name)
-                continue
-            add([p])
+            rest(l, f"decoder.layers.{i}.")
+        marks[("dec", len(dec.layers))] = len(groups)
+        rest(dec.layer_norm, "decoder.layer_norm.")
         self.arena = ParamArena(groups, self.device)
+        self.marks = {k: (self.arena.slots[id(groups[gi][0])][0] if gi < len(groups) else self.arena.numel)
+                      for k, gi in marks.items()}
+        covered = {id(p) for p in self.arena.params}
         for name, p in m.named_parameters():
             if name in self._no_grad_names:
                 p.grad = None
+            elif p.requires_grad and id(p) not in covered:
+                raise RuntimeError(f"trainable parameter {name} is not covered by the training engine")
+
+    def _sync_down(self, key):
+        """Gradients of arena[marks[key]:] are final: hand the not-yet-synchronised part to the DDP callback."""
+        lo = self.marks[key] if key is not None else 0
+        if self.grad_sync is not None and lo < self._sync_hi:
+            self.grad_sync(lo, self._sync_hi)
+        self._sync_hi = min(self._sync_hi, lo)
 
     @staticmethod
     def _is_bias_path(name):
@@ -212,10 +246,12 @@ class SegOFATrainEngine:
         first = not hasattr(self, "dense")
         if first:
             self.dense: List[_Dense] = []
+            self.dense_index: Dict[tuple, _Dense] = {}
 
             def mk(ws, bs):
                 d = self._dense(ws, bs)
                 self.dense.append(d)
+                self.dense_index[tuple(id(w) for w in ws)] = d
                 return d
 
             def attn(a):
@@ -256,8 +292,7 @@ class SegOFATrainEngine:
             if first or d.gw is not None:
                 ops.transpose_cast(d.src, out_t=d.w16t, out_c=d.w16)
         if self.inf is None:
-            self.inf = SegOFAEngine(self.model)
-            self.inf.fold_ffn_layernorm = True
+            self.inf = SegOFAEngine(self.model, live=self)
 
     # ------------------------------------------------------------------------------------
     # helpers
@@ -278,12 +313,21 @@ class SegOFATrainEngine:
         N, K = L.N, L.K
         Mp = _pad8(M)
         if L.gw is not None:
-            dyt = self._buf("dyt", (max(d.N for d in self.dense), Mp), _BF16)
-            xt = self._buf("xt", (max(d.K for d in self.dense), Mp), _BF16)
-            ops.transpose_cast(dy, M=M, N=N, out_t=dyt, colsum=L.gb)
-            ops.transpose_cast(x, M=M, N=K, out_t=xt)
-            ops.gemm(dyt, xt, L.gw, M=N, N=K, K=M, lda=Mp, ldb=Mp, residual=L.gw if self.accumulate else None,
-                     tag="wgrad_" + tag)
+            if L.gb is not None:
+                ops.transpose_cast(dy, M=M, N=N, want_t=False, colsum=L.gb)  # db = column sums of dY
+            if K % 32 == 0:
+                # dW[n,k] (+)= sum_t dY[t,n] X[t,k]: both operands are read as they lie (MN-major TMA tiles), the token
+                # dimension is split over CTAs and reduced with fp32 atomics into the (zeroed / accumulating) gradient
+                tiles = ((N + 127) // 128) * ((K + 127) // 128)
+                split = max(1, min(8, (296 + tiles - 1) // tiles, (M + 1023) // 1024))
+                ops.gemm_ex(dy, x, L.gw, M=N, N=K, K=M, a_mn=True, b_mn=True, lda=dy.stride(0), ldb=x.stride(0),
+                            split_k=split, tag="wgrad_" + tag)
+            else:
+                dyt = self._buf(("dyt", Mp), (max(d.N for d in self.dense), Mp), _BF16)
+                xt = self._buf(("xt", Mp), (max(d.K for d in self.dense), Mp), _BF16)
+                ops.transpose_cast(dy, M=M, N=N, out_t=dyt)
+                ops.transpose_cast(x, M=M, N=K, out_t=xt)
+                ops.gemm(dyt, xt, L.gw, M=N, N=K, K=M, lda=Mp, ldb=Mp, residual=L.gw, tag="wgrad_" + tag)
         if not need_dx:
             return None
         return ops.gemm(dy, L.w16t, dx_out, M=M, N=K, K=N, lda=dy.stride(0), ldb=L.w16t.stride(0), out_dtype=dx_dtype,
@@ -292,7 +336,8 @@ class SegOFATrainEngine:
     # ------------------------------------------------------------------------------------
     # forward + backward of the image-free branch
     # ------------------------------------------------------------------------------------
-    def forward_backward(self, aux_input, target_classes, label_smoothing=0.0, grad_scale=1.0, backward=True):
+    def forward_backward(self, aux_input, target_classes, label_smoothing=0.0, grad_scale=1.0, backward=True,
+                         check_pads=True):
         """aux_input: the dict segofa.py:136-151 receives (src_tokens, patch_images = bag tokens, patch_masks = bag
         end offsets, prev_output_tokens); target_classes int64 [B,S,S] class ids (<0 or >=C ignored).
         Returns (loss 0-dim tensor = mean pixel CE, logits fp32 [B,Td,C]); gradients of the mean loss times
@@ -301,7 +346,7 @@ class SegOFATrainEngine:
         D, H, Fd, C = cfg.embed_dim, cfg.heads, cfg.ffn_dim, cfg.num_seg
         src_tokens = aux_input["src_tokens"].to(dev)
         B, T_txt = src_tokens.shape
-        if bool(src_tokens.eq(cfg.padding_idx).any()):
+        if check_pads and bool(src_tokens.eq(cfg.padding_idx).any()):  # host sync (skipped under graph capture)
             raise NotImplementedError("training with padded prompts is not implemented (every IFSeg batch shares one prompt)")
         h = w = cfg.patch_image_size // 16
         P = h * w
@@ -314,6 +359,7 @@ class SegOFATrainEngine:
         self_biases, cross_abs = self.inf._decoder_bias(h, w, pos)
         if not self.accumulate:
             self.arena.grad32.zero_()
+        self._sync_hi = self.arena.numel
 
         # ------------------------------ encoder forward ------------------------------
         bag = ops.embedding_bag_mean(aux_input["patch_images"].to(dev).contiguous(),
@@ -465,6 +511,7 @@ class SegOFATrainEngine:
                               dq_scale=cfg.attn_scaling)
             da = self._lin_bwd(dqkv, S["a"], L["attn"]["qkv"], Md, "qkv")
             dec_saved[li] = None
+            self._sync_down(("dec", li + 1))
         # decoder input embedding: rows 0 = bos (frozen embedding), rows 1..P = encoder_out rows
         d_enc_out = self._lin_bwd(dkv_all, enc_out, self.cross_kv, M, "cross_kv", dx_dtype=f32)  # [M, D] fp32
         g_emb, g_l0 = self.dec_ln_emb, self.dec_layers[0]["ln_self"]
@@ -474,6 +521,7 @@ class SegOFATrainEngine:
                               dy2=da, dv_in=dxs, dx=d_enc_out, dx_accumulate=True, dg1=g_emb[2], db1=g_emb[3],
                               dg2=g_l0[2], db2=g_l0[3], seg=(P, Td, 1))
 
+        self._sync_down("cross_kv")
         # ------------------------------ encoder backward ------------------------------
         da = d_enc_out  # fp32 gradient w.r.t. encoder_out (= LN_enc_out(x))
         dxs = None
@@ -504,6 +552,7 @@ class SegOFATrainEngine:
                               d_head_scale=L["attn"]["c_attn"][1], dq_scale=cfg.attn_scaling)
             da = self._lin_bwd(dqkv, S["a"], L["attn"]["qkv"], M, "qkv")
             enc_saved[li] = None
+            self._sync_down(("enc", li + 1))
         # encoder input embeddings (token embeddings frozen): type embedding + the two embedding LayerNorms
         g_l0 = self.enc_layers[0]["ln_self"]
         gt = self.g_type
@@ -514,6 +563,7 @@ class SegOFATrainEngine:
                               g1=self.ln_emb[0], v=x_emb, g2=g_l0[0], dy2=da, dv_in=dxs, dg1=self.ln_emb[2],
                               db1=self.ln_emb[3], dg2=g_l0[2], db2=g_l0[3], d_pre_add=gt[0] if gt is not None else None,
                               seg=(T_txt, T, P))
+        self._sync_down(None)
         return loss, logits
 
     # ------------------------------------------------------------------------------------
@@ -530,11 +580,14 @@ class SegOFATrainEngine:
         ar = self.arena
         ar.ensure_moments()
         self.step_count += 1
+        if self._step_dev is None:
+            self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._step_dev += 1  # device-resident update counter: the whole step can be replayed from a CUDA graph
         gnorm = self.grad_norm() * grad_mult
         scale = torch.full((1,), float(grad_mult), dtype=torch.float32, device=self.device)
         if clip_norm > 0:
             scale = scale * (clip_norm / (gnorm + 1e-6)).clamp(max=1.0)
         ops.adam_step(ar.flat32, ar.grad32, ar.exp_avg, ar.exp_avg_sq, lr=lr, beta1=betas[0], beta2=betas[1], eps=eps,
-                      weight_decay=weight_decay, step=self.step_count, grad_scale=scale)
+                      weight_decay=weight_decay, step=self.step_count, step_dev=self._step_dev, grad_scale=scale)
         self.refresh_weights()
         return gnorm

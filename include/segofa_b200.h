@@ -70,6 +70,14 @@ typedef struct {
   int32_t rownorm_dim;
 } sgf_gemm_args;
 int sgf_gemm_bf16(const sgf_gemm_args* args, void* stream);
+/* Mixed-major variant for the dense adjoints of the training path (no transposed copies):
+ *   C[M,N] (+)= A_eff[M,K] * B_eff[N,K]^T   with  A_eff[m,k] = a_mn_major ? a[k*lda + m] : a[m*lda + k]
+ *                                                B_eff[n,k] = b_mn_major ? b[k*ldb + n] : b[n*ldb + k]
+ * (a_mn, b_mn) = (1,1): dW = dY^T X over the token dimension;  (0,1): dX = dY W with W as stored [N_out,K_in].
+ * Plain epilogue only (no bias/activation/residual; batch = 1).  split_k > 1 splits the contraction over
+ * blockIdx.z and REDUCES the partial tiles into C with vector fp32 atomics: C must be fp32 and hold the value to
+ * accumulate onto (zeros, or a running gradient for gradient accumulation).  N % 32 == 0. */
+int sgf_gemm_bf16_ex(const sgf_gemm_args* args, int32_t a_mn_major, int32_t b_mn_major, int32_t split_k, void* stream);
 /* tuning hook: force the N-tile (32/64/128/256, 0 = heuristic) and pipeline depth of sgf_gemm_bf16 */
 void sgf_gemm_force_variant(int bn, int stages);
 
@@ -288,6 +296,7 @@ typedef struct {
   float* dg1; float* db1; float* dg2; float* db2; float* d_pre_add;
   int32_t rows, D;
   int32_t seg_len, seg_stride, seg_off;
+  float* dx_colsum; /* optional fp32 [D] += column sums of dx (= bias gradient of the linear that produced x) */
 } sgf_rowln_bwd_args;
 int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* args, void* stream);
 
@@ -325,10 +334,12 @@ int sgf_attention_bwd_bf16(const sgf_attention_bwd_args* args, void* stream);
 
 /* Multi-tensor-free fused Adam(W) step over one flat fp32 master buffer (cf/optim/adam.py, fp32
  * master weights of cf/optim/fp16_optimizer.py:108-222): p -= lr*(m_hat/(sqrt(v_hat)+eps) + wd*p)
- * with grads scaled by grad_scale[0] (device scalar: 1/sample_size * clip coefficient). */
+ * with grads scaled by grad_scale[0] (device scalar: 1/sample_size * clip coefficient).  The update
+ * number is `step`, or step_dev[0] when step_dev != NULL (device-resident counter: the launch can then be
+ * replayed from a CUDA graph). */
 int sgf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                  float beta1, float beta2, float eps, float weight_decay, int32_t step, const float* grad_scale,
-                  void* stream);
+                  float beta1, float beta2, float eps, float weight_decay, int32_t step, const int32_t* step_dev,
+                  const float* grad_scale, void* stream);
 /* out[0] += sum of squares of x[0..n) (gradient-norm for clip_grad_norm, trainer.py:886) */
 int sgf_sumsq(const float* x, int64_t n, float* out, void* stream);
 

@@ -24,7 +24,7 @@ def _gen(seed):
 # ----------------------------------------------------------------------------------------
 # row kernel: forward x_act, and the adjoint in the three site shapes the engine uses
 # ----------------------------------------------------------------------------------------
-@pytest.mark.parametrize("D", [3072, 4096, 256])
+@pytest.mark.parametrize("D", [3072, 4096, 256, 1024, 2048])
 def test_row_layernorm_gelu_forward(ops, D):
     g = _gen(D)
     rows = 77
@@ -52,8 +52,10 @@ def test_row_layernorm_bwd_residual_site(ops, D, rows):
     d_res = torch.empty(rows, D, device="cuda")
     dx = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
     pg = [torch.zeros(D, device="cuda") for _ in range(4)]
+    cs = torch.zeros(D, device="cuda")
     ops.row_layernorm_bwd(rows=rows, D=D, x=y.detach(), g1=g1.detach(), v=v.detach(), g2=g2.detach(), dy2=dy2,
-                          dv_in=dv_in, d_res=d_res, dx=dx, dg1=pg[0], db1=pg[1], dg2=pg[2], db2=pg[3])
+                          dv_in=dv_in, d_res=d_res, dx=dx, dg1=pg[0], db1=pg[1], dg2=pg[2], db2=pg[3], dx_colsum=cs)
+    assert _rel(cs, y.grad.sum(0)) < 1e-4
     assert _rel(d_res, res.grad) < 1e-5
     assert _rel(dx, y.grad) < 4e-3
     for got, ref in zip(pg, (g1.grad, b1.grad, g2.grad, b2.grad)):
@@ -80,7 +82,7 @@ def test_row_layernorm_bwd_in_place_and_plain_residual(ops):
     assert _rel(dg2, g2.grad) < 1e-4 and _rel(db2, b2.grad) < 1e-4
 
 
-@pytest.mark.parametrize("F_", [3072, 4096])
+@pytest.mark.parametrize("F_", [3072, 4096, 1024, 2048, 512])
 def test_row_layernorm_bwd_gelu_site(ops, F_):
     """z = LN(gelu(h)): dh from dz (FFN site, no saved v: recomputed from h)."""
     g = _gen(F_)
@@ -91,10 +93,12 @@ def test_row_layernorm_bwd_gelu_site(ops, F_):
     dz = (torch.randn(rows, F_, device="cuda", generator=g) * 0.1).bfloat16()
     (F.layer_norm(F.gelu(h), (F_,), g2, b2, 1e-5) * dz.float()).sum().backward()
     dh = torch.empty(rows, F_, device="cuda", dtype=torch.bfloat16)
-    dg2, db2 = torch.zeros(F_, device="cuda"), torch.zeros(F_, device="cuda")
-    ops.row_layernorm_bwd(rows=rows, D=F_, x=h16, x_act=ops.ACT_GELU, g2=g2.detach(), dy2=dz, dx=dh, dg2=dg2, db2=db2)
+    dg2, db2, cs = torch.zeros(F_, device="cuda"), torch.zeros(F_, device="cuda"), torch.zeros(F_, device="cuda")
+    ops.row_layernorm_bwd(rows=rows, D=F_, x=h16, x_act=ops.ACT_GELU, g2=g2.detach(), dy2=dz, dx=dh, dg2=dg2, db2=db2,
+                          dx_colsum=cs)
     assert _rel(dh, h.grad) < 5e-3, _rel(dh, h.grad)
     assert _rel(dg2, g2.grad) < 1e-4 and _rel(db2, b2.grad) < 1e-4
+    assert _rel(cs, h.grad.sum(0)) < 2e-3, _rel(cs, h.grad.sum(0))
 
 
 def test_row_layernorm_bwd_embedding_site_scatter(ops):
@@ -165,6 +169,37 @@ def test_dense_adjoints_through_gemm(ops):
     acc = torch.randn(N, K, device="cuda", generator=g)
     dw2 = ops.gemm(dyt, xt, acc.clone(), M=N, N=K, K=M, residual=acc)
     assert _rel(dw2, acc + dy.float().t() @ x.float()) < 2e-5
+
+
+@pytest.mark.parametrize("T,N,K,split", [(8920, 768, 768, 8), (1115, 3072, 768, 2), (462, 2304, 768, 1), (901, 768, 3072, 3),
+                                         (130, 64, 96, 1)])
+def test_gemm_mixed_major_wgrad(ops, T, N, K, split):
+    """dW[n,k] = sum_t dY[t,n] X[t,k] straight from the row-major dY / X (MN-major TMA operands), split-K atomics."""
+    g = _gen(T + N + K)
+    dy = (torch.randn(T, N, device="cuda", generator=g) * 0.1).bfloat16()
+    x = torch.randn(T, K, device="cuda", generator=g).bfloat16()
+    base = torch.randn(N, K, device="cuda", generator=g)
+    out = base.clone()
+    ops.gemm_ex(dy, x, out, M=N, N=K, K=T, a_mn=True, b_mn=True, split_k=split)
+    if split == 1:
+        ref = dy.float().t() @ x.float()
+    else:
+        ref = base + dy.float().t() @ x.float()
+    assert _rel(out, ref) < 2e-5, _rel(out, ref)
+    out16 = torch.empty(N, K, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_ex(dy, x, out16, M=N, N=K, K=T, a_mn=True, b_mn=True)
+    assert _rel(out16, dy.float().t() @ x.float()) < 4e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(8920, 768, 3072), (462, 768, 2304), (901, 3072, 768)])
+def test_gemm_mixed_major_dgrad(ops, M, N, K):
+    """dX[m,n] = sum_k dY[m,k] W[k,n] with W as stored ([out=k, in=n], B MN-major)."""
+    g = _gen(M + N + K)
+    dy = (torch.randn(M, K, device="cuda", generator=g) * 0.1).bfloat16()
+    w = (torch.randn(K, N, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_ex(dy, w, out, M=M, N=N, K=K, a_mn=False, b_mn=True)
+    assert _rel(out, dy.float() @ w.float()) < 4e-3
 
 
 # ----------------------------------------------------------------------------------------
