@@ -347,7 +347,8 @@ struct DkvSmem {
   static constexpr int offDO = offQ + 2 * kQ;
   static constexpr int offP = offDO + 2 * kQ;
   static constexpr int offDS = offP + kP;
-  static constexpr int offBar = offDS + kP;
+  static constexpr int offStat = offDS + kP;       // [2 stages][lse 64 | delta 64] fp32
+  static constexpr int offBar = offStat + 2 * 128 * 4;
   static constexpr int kTotal = offBar + 256;
 };
 struct DkvBars {
@@ -474,9 +475,19 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dkv_kernel(const __gr
     const float* dl_bh = p.delta + (static_cast<int64_t>(b) * p.H + h) * p.Tq;
     const float* bias_h = p.bias ? p.bias + static_cast<int64_t>(h) * p.bias_head_stride + min(key, p.Tk - 1) : nullptr;
 
+    float* stat = reinterpret_cast<float*>(smem + DkvSmem::offStat);
 #pragma unroll 1
     for (int j = 0; j < n_t; ++j) {
       const int qb = (t_first + j) * kBS;
+      // per-query statistics of this tile -> shared memory (one element per thread), read back as broadcast float4
+      {
+        const int q = qb + (tid & 63);
+        const float* src = tid < 64 ? lse_bh : dl_bh;
+        stat[(j & 1) * 128 + tid] = q < p.Tq ? __ldg(src + q) : (tid < 64 ? INFINITY : 0.f);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const float4* st_l = reinterpret_cast<const float4*>(stat + (j & 1) * 128);
+      const float4* st_d = st_l + 16;
       mbar_wait(&bars->sdp_full, j & 1);
       tc_fence_after();
       uint32_t pk_p[32], pk_ds[32];
@@ -495,17 +506,23 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dkv_kernel(const __gr
         }
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int q = qb + half * 32 + i;
-          const bool live = key_ok && q < p.Tq && !(p.causal && key > q);
-          const int qc = min(q, p.Tq - 1);
-          float s = __uint_as_float(rs[i]);
-          if (p.bias) s += bv[i];
-          float pr = fast_exp2(fmaf(s, kLog2eB, -__ldg(lse_bh + qc)));
-          if (!live) pr = 0.f;
-          const float ds = pr * fmaf(hs, __uint_as_float(rp[i]), -__ldg(dl_bh + qc));
-          rs[i] = __float_as_uint(pr);
-          rp[i] = __float_as_uint(ds);
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 l4 = st_l[half * 8 + i4];
+          const float4 d4 = st_d[half * 8 + i4];
+          const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+          const float dv4[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i4 * 4 + u;
+            const int q = qb + half * 32 + i;
+            float s = __uint_as_float(rs[i]);
+            if (p.bias) s += bv[i];
+            float pr = fast_exp2(fmaf(s, kLog2eB, -lv[u]));  // queries >= Tq carry lse = +inf -> 0
+            if (!key_ok || (p.causal && key > q)) pr = 0.f;
+            const float ds = pr * fmaf(hs, __uint_as_float(rp[i]), -dv4[u]);
+            rs[i] = __float_as_uint(pr);
+            rp[i] = __float_as_uint(ds);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {

@@ -1198,9 +1198,9 @@ extern "C" int sgf_gemm_bf16_ex(const sgf_gemm_args* a, int32_t a_mn_major, int3
                                 void* stream) {
   SGF_REQUIRE(a != nullptr && a->a && a->b && a->c, "gemm_ex: null pointer");
   SGF_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->batch == 1, "gemm_ex: bad shape (batch must be 1)");
-  SGF_REQUIRE(!a->col_scale && !a->col_bias && !a->residual && a->act == SGF_ACT_NONE && a->alpha_cols == 0 &&
-                  !a->rowstats_out && !a->rownorm_stats,
-              "gemm_ex: the mixed-major kernel has a plain epilogue (store or fp32 accumulate)");
+  SGF_REQUIRE(!a->col_scale && !a->col_bias && a->act == SGF_ACT_NONE && a->alpha_cols == 0 && !a->rowstats_out &&
+                  !a->rownorm_stats && (!a->residual || (a->residual == a->c && a->r_dtype == SGF_F32 && a->c_dtype == SGF_F32)),
+              "gemm_ex: the mixed-major kernel has a plain epilogue (store, or fp32 accumulate in place: residual == c)");
   SGF_REQUIRE(a->N % 32 == 0, "gemm_ex: N must be a multiple of 32 (N=%d)", a->N);
   SGF_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(a->a) % 16) == 0 &&
                   (reinterpret_cast<uintptr_t>(a->b) % 16) == 0,
@@ -1236,7 +1236,7 @@ extern "C" int sgf_gemm_bf16_ex(const sgf_gemm_args* a, int32_t a_mn_major, int3
   const int kb_per_split = (num_kb + split_k - 1) / split_k;
   split_k = (num_kb + kb_per_split - 1) / kb_per_split;
   dim3 grid((a->N + bn - 1) / bn, m_tiles, split_k);
-  const bool atomic = split_k > 1;
+  const bool atomic = split_k > 1 || a->residual != nullptr;  // residual == c: accumulate in place
 #define SGF_MM_CASE(AMN, BMN)                                                                                   \
   if ((a_mn_major != 0) == AMN && (b_mn_major != 0) == BMN)                                                      \
     return bn == 128 ? dispatch_gemm_mm<128, AMN, BMN>(tmA, tmB, shp, ep, grid, kb_per_split, atomic, st)        \

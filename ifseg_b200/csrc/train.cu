@@ -484,21 +484,28 @@ __global__ void __launch_bounds__(128) gelu_ln_fwd_wide_kernel(const __nv_bfloat
 }
 
 template <int NC>
-__global__ void __launch_bounds__(128) gelu_ln_bwd_wide_kernel(const __nv_bfloat16* __restrict__ h, int64_t ldh,
-                                                               const __nv_bfloat16* __restrict__ dz, int64_t lddz,
-                                                               const float* __restrict__ gam,
-                                                               __nv_bfloat16* __restrict__ dh, int64_t lddh,
-                                                               float* __restrict__ dgam, float* __restrict__ dbet,
-                                                               float* __restrict__ dh_colsum, int rows, int F) {
+__global__ void __launch_bounds__(128, 4) gelu_ln_bwd_wide_kernel(const __nv_bfloat16* __restrict__ h, int64_t ldh,
+                                                                  const __nv_bfloat16* __restrict__ dz, int64_t lddz,
+                                                                  const float* __restrict__ gam,
+                                                                  __nv_bfloat16* __restrict__ dh, int64_t lddh,
+                                                                  float* __restrict__ dgam, float* __restrict__ dbet,
+                                                                  float* __restrict__ dh_colsum, int rows, int F) {
+  // per-CTA partials of (dgamma, dbeta, column sums of dh): thread t owns its columns in all three arrays, so plain
+  // shared-memory read-modify-writes suffice (keeps the register count low enough for 4-5 CTAs per SM)
+  extern __shared__ __align__(16) float wacc[];  // [3][F]
   __shared__ float red[2][12];
   pdl_trigger();
+  for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) wacc[i] = 0.f;
+  __syncthreads();
   pdl_wait();
   const float invF = 1.0f / static_cast<float>(F);
-  float ag[NC][8], ab[NC][8], ac[NC][8];
-#pragma unroll
-  for (int k = 0; k < NC; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ag[k][j] = ab[k][j] = ac[k][j] = 0.f;
+  auto rmw8 = [](float* a, const float (&v)[8]) {
+    float4* q = reinterpret_cast<float4*>(a);
+    float4 u0 = q[0], u1 = q[1];
+    u0.x += v[0]; u0.y += v[1]; u0.z += v[2]; u0.w += v[3];
+    u1.x += v[4]; u1.y += v[5]; u1.z += v[6]; u1.w += v[7];
+    q[0] = u0; q[1] = u1;
+  };
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     uint4 hx[NC];
     float cdf[NC][8], dzv[NC][8];  // Phi(h) and dz
@@ -551,7 +558,7 @@ __global__ void __launch_bounds__(128) gelu_ln_bwd_wide_kernel(const __nv_bfloat
     for (int k = 0; k < NC; ++k) {
       const int col = (k * 128 + threadIdx.x) * 8;
       if (col < F) {
-        float x[8], g[8], o[8];
+        float x[8], g[8], o[8], gx[8];
         unpack8(hx[k], x);
         ld8g(gam, SGF_F32, col, g);
 #pragma unroll
@@ -560,11 +567,12 @@ __global__ void __launch_bounds__(128) gelu_ln_bwd_wide_kernel(const __nv_bfloat
           const float dt = rstd * (dzv[k][j] * g[j] - c1 - xh * c2);
           const float e = fast_exp2(-0.72134752044448170368f * x[j] * x[j]);  // exp(-x^2/2)
           o[j] = dt * fmaf(x[j] * 0.3989422804014327f, e, cdf[k][j]);          // * gelu'(x) = Phi + x phi
-          ag[k][j] = fmaf(dzv[k][j], xh, ag[k][j]);
-          ab[k][j] += dzv[k][j];
-          ac[k][j] += o[j];
+          gx[j] = dzv[k][j] * xh;
         }
         st8g(dh, SGF_BF16, static_cast<int64_t>(row) * lddh + col, o);
+        rmw8(wacc + col, gx);
+        rmw8(wacc + F + col, dzv[k]);
+        rmw8(wacc + 2 * F + col, o);
       }
     }
   }
@@ -574,9 +582,9 @@ __global__ void __launch_bounds__(128) gelu_ln_bwd_wide_kernel(const __nv_bfloat
     if (col < F) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (dgam) atomicAdd(dgam + col + j, ag[k][j]);
-        if (dbet) atomicAdd(dbet + col + j, ab[k][j]);
-        if (dh_colsum) atomicAdd(dh_colsum + col + j, ac[k][j]);
+        if (dgam) atomicAdd(dgam + col + j, wacc[col + j]);
+        if (dbet) atomicAdd(dbet + col + j, wacc[F + col + j]);
+        if (dh_colsum) atomicAdd(dh_colsum + col + j, wacc[2 * F + col + j]);
       }
     }
   }
@@ -715,18 +723,29 @@ extern "C" int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* a, void* stream) 
       a->dy2 && a->dy2_dtype == SGF_BF16 && a->x_dtype == SGF_BF16 && a->dx && a->dx_dtype == SGF_BF16 &&
       !a->dx_accumulate && a->seg_len == 0 && a->D >= 1024 && a->D <= 4096 && !a->dg1 && !a->db1 && !a->d_pre_add) {
     const int nc = (a->D + 1023) / 1024;
-    int grid = a->rows < 148 * 5 ? a->rows : 148 * 5;
+    int grid = a->rows < 148 * 4 ? a->rows : 148 * 4;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     auto h = reinterpret_cast<const __nv_bfloat16*>(a->x);
     auto dz = reinterpret_cast<const __nv_bfloat16*>(a->dy2);
     auto dh = reinterpret_cast<__nv_bfloat16*>(a->dx);
+    const size_t wsm = static_cast<size_t>(3) * a->D * sizeof(float);
 #define SGF_WIDE_BWD(NC)                                                                                          \
-  SGF_CHECK_CUDA(launch_pdl(gelu_ln_bwd_wide_kernel<NC>, dim3(grid), dim3(128), size_t(0), st, h, a->ldx, dz, a->ldy2,   \
-                            a->g2, dh, a->lddx, a->dg2, a->db2, a->dx_colsum, a->rows, a->D))
-    if (nc == 1) SGF_WIDE_BWD(1);
-    else if (nc == 2) SGF_WIDE_BWD(2);
-    else if (nc == 3) SGF_WIDE_BWD(3);
-    else SGF_WIDE_BWD(4);
+  {                                                                                                               \
+    static bool cfgd = false;                                                                                     \
+    if (!cfgd) {                                                                                                  \
+      SGF_CHECK_CUDA(cudaFuncSetAttribute(gelu_ln_bwd_wide_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          3 * 4096 * 4));                                                         \
+      cfgd = true;                                                                                                \
+    }                                                                                                             \
+    SGF_CHECK_CUDA(launch_pdl(gelu_ln_bwd_wide_kernel<NC>, dim3(grid), dim3(128), wsm, st, h, a->ldx, dz, a->ldy2, \
+                              a->g2, dh, a->lddx, a->dg2, a->db2, a->dx_colsum, a->rows, a->D));                  \
+  }
+    switch (nc) {
+      case 1: SGF_WIDE_BWD(1) break;
+      case 2: SGF_WIDE_BWD(2) break;
+      case 3: SGF_WIDE_BWD(3) break;
+      default: SGF_WIDE_BWD(4) break;
+    }
 #undef SGF_WIDE_BWD
     count_launch();
     return SGF_OK;

@@ -117,7 +117,7 @@ def gemm(a, b, out=None, *, bias=None, scale=None, residual=None, act=ACT_NONE, 
     return out
 
 
-def gemm_ex(a, b, out, *, M, N, K, a_mn, b_mn, lda=None, ldb=None, ldc=None, split_k=1, tag=None):
+def gemm_ex(a, b, out, *, M, N, K, a_mn, b_mn, lda=None, ldb=None, ldc=None, split_k=1, accumulate=False, tag=None):
     """out[M,N] (+)= A_eff @ B_eff^T with MN-major operands (see sgf_gemm_bf16_ex): a is [K,M] when a_mn else [M,K];
     b is [K,N] when b_mn else [N,K].  split_k > 1 accumulates into the fp32 `out`."""
     lib = _lib.load()
@@ -126,8 +126,10 @@ def gemm_ex(a, b, out, *, M, N, K, a_mn, b_mn, lda=None, ldb=None, ldc=None, spl
     lda = a.stride(-2) if lda is None else lda
     ldb = b.stride(-2) if ldb is None else ldb
     ldc = out.stride(-2) if ldc is None else ldc
-    args = _lib.GemmArgs(_p(a), lda, 0, _p(b), ldb, 0, _p(out), ldc, 0, _DT[out.dtype], M, N, K, 1, None, None, None, 0, 0,
-                         SGF_BF16, ACT_NONE, 1.0, 0, None, None, None, 0)
+    acc = accumulate or split_k > 1
+    args = _lib.GemmArgs(_p(a), lda, 0, _p(b), ldb, 0, _p(out), ldc, 0, _DT[out.dtype], M, N, K, 1, None, None,
+                         _p(out) if acc else None, ldc if acc else 0, 0, SGF_F32 if acc else SGF_BF16, ACT_NONE, 1.0, 0,
+                         None, None, None, 0)
     with _timed("gemm_tcgen05" + (":" + tag if tag and _TIMER is not None and _TIMER.fine else ""), 2.0 * M * N * K):
         _lib.check(lib.sgf_gemm_bf16_ex(C.byref(args), 1 if a_mn else 0, 1 if b_mn else 0, int(split_k), _stream()),
                    "sgf_gemm_bf16_ex")
@@ -215,7 +217,7 @@ def row_layernorm(x, *, rows=None, D=None, ldx=None, gather_idx=None, pre_add=No
         _p(zero_row), rows, D, seg_len, seg_stride, seg_off, _p(clear_rowstats), int(x_act))
     nb = rows * D * (x.element_size() + (residual.element_size() if residual is not None else 0)
                      + (out1.element_size() if out1 is not None else 0) + (2 if out2 is not None else 0))
-    with _timed("row_layernorm", nbytes=float(nb)):
+    with _timed("row_layernorm" + (f":D{D}{'g1' if ln1 else ''}" if _TIMER is not None and _TIMER.fine else ""), nbytes=float(nb)):
         _lib.check(lib.sgf_row_layernorm(C.byref(args), _stream()), "sgf_row_layernorm")
 
 
@@ -353,7 +355,7 @@ def row_layernorm_bwd(*, rows, D, x=None, ldx=None, gather_idx=None, x_act=ACT_N
         _p(dx), ld(dx), dt(dx), 1 if dx_accumulate else 0, _p(dg1), _p(db1), _p(dg2), _p(db2), _p(d_pre_add),
         rows, D, seg_len, seg_stride, seg_off, _p(dx_colsum))
     nb = rows * D * sum(t.element_size() for t in (x, v, dy2, dv_in, d_res, dx) if t is not None)
-    with _timed("row_layernorm_bwd", nbytes=float(nb)):
+    with _timed("row_layernorm_bwd" + (f":D{D}{'g1' if g1 is not None else ''}" if _TIMER is not None and _TIMER.fine else ""), nbytes=float(nb)):
         _lib.check(lib.sgf_row_layernorm_bwd(C.byref(args), _stream()), "sgf_row_layernorm_bwd")
 
 

@@ -8,7 +8,8 @@
 
 Round-1 state: the evaluation branch (model.eval()) is complete except the ResNet-feature label
 propagation (`resnet_iters > 0`, seg_criterion.py:197-213 -- SURVEY.md s8f-2); the training branch
-computes the image-free loss VALUE but raises for backward (the autograd path is a later round).
+(unsupervised_segmentation: image-free loss + no-grad real-image metrics) returns a loss whose .backward()
+runs the hand-written adjoint kernels (PixelCrossEntropyFunction -> train_engine.ImFreeBranchFunction).
 """
 import math
 
@@ -37,6 +38,29 @@ def pixel_cross_entropy(logits, target_classes, hp, wp, label_smoothing=0.0):
     """F.cross_entropy(upsample(logits), target) over the non-ignored pixels, fused."""
     loss, _ = ops.upsample_ce_loss(logits.float().contiguous(), target_classes.contiguous(), hp, wp, label_smoothing)
     return loss
+
+
+class PixelCrossEntropyFunction(torch.autograd.Function):
+    """compute_imfree_loss (seg_criterion.py:246-267) as one autograd node: forward = sgf_upsample_ce_loss (the
+    up-sampled logits never exist), backward = sgf_upsample_ce_loss_bwd (gradient w.r.t. the patch-grid logits)."""
+
+    @staticmethod
+    def forward(ctx, logits, target_classes, hp, wp, eps):
+        logits = logits.float().contiguous()
+        tgt = target_classes.contiguous()
+        lse = torch.empty(tuple(tgt.shape), dtype=torch.float32, device=logits.device)
+        acc = ops.upsample_ce_loss(logits, tgt, hp, wp, eps, lse_out=lse, raw=True)
+        ctx.save_for_backward(logits, tgt, lse, acc)
+        ctx.hw, ctx.eps = (hp, wp), eps
+        return acc[0] / acc[1]
+
+    @staticmethod
+    def backward(ctx, gout):
+        logits, tgt, lse, acc = ctx.saved_tensors
+        B, T, C = logits.shape
+        dl = torch.empty((B, T, (C + 7) // 8 * 8), dtype=torch.bfloat16, device=logits.device)
+        ops.upsample_ce_loss_bwd(logits, tgt, lse, acc[1:], ctx.hw[0], ctx.hw[1], dl, ctx.eps, 1.0)
+        return dl[..., :C].float() * gout, None, None, None, None
 
 
 def derive_metrics(area_intersect, area_pred_label, area_label, area_union):
@@ -93,10 +117,25 @@ class SegCriterion:
     def forward(self, model, sample, update_num=0, reduce=True, ema_model=None):
         self.iter += 1
         self.effective_iter = self.iter // self.criterion_update_freq
-        if model.training:
-            raise NotImplementedError(
-                "segofa_b200 round 1: the training branch (image-free loss backward) is not built; "
-                "imfree_loss_value() gives the forward value")
+        if model.training and not self.unsupervised_segmentation:
+            raise NotImplementedError("segofa_b200 trains the image-free branch only (--unsupervised-segmentation=true, "
+                                      "every shipped recipe); the supervised real-image loss has no backward")
+        if model.training:  # seg_criterion.py:178-186
+            S = model.cfg.patch_image_size
+            net_output = model(full_context_alignment=self.full_context_alignment, aux_input=sample["aux_input"])
+            logits = net_output[1]["aux_output"][0]
+            ids = sample["text2seg_target"][:, :-1].reshape(-1, S, S).to(logits.device)
+            tgt = class_targets(ids, self.seg_id_offset, self.num_seg, self.padding_idx)
+            imfree_loss = PixelCrossEntropyFunction.apply(logits, tgt, S // 16, S // 16, self.eps)
+            loss = imfree_loss
+            with torch.no_grad():
+                seg_logits, seg_extra = model(**sample["net_input"], full_context_alignment=self.full_context_alignment)
+                seg_loss, metrics = self.compute_loss(seg_logits, seg_extra, sample)
+            sample_size = sample["target"].size(0) if self.sentence_avg else 1
+            logging_output = {"loss": loss.data, "imfree_loss": imfree_loss.data, "seg_loss": seg_loss.data,
+                              "ntokens": sample["ntokens"], "nsentences": sample["nsentences"], "sample_size": sample_size}
+            logging_output.update(metrics)
+            return loss, sample_size, logging_output
         if self.resnet_iters > 0:
             raise NotImplementedError("ResNet-feature label propagation (resnet_iters > 0) is a 'next' row (SURVEY s8f-2)")
         with torch.no_grad():

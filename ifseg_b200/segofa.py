@@ -448,6 +448,15 @@ class SegOFAModel(FairseqEncoderDecoderModel):
         """Drop device-side derived weights (bf16 copies, folded BN, fused QKV).  Called on
         anything that may change parameters."""
         self._engine = None
+        self._train_engine = None
+
+    def train_engine(self):
+        """The training engine (flat fp32 master arena + hand-written backward); created on first use."""
+        if self._train_engine is None:
+            from .train_engine import SegOFATrainEngine
+
+            self._train_engine = SegOFATrainEngine(self)
+        return self._train_engine
 
     def train(self, mode: bool = True):
         self.invalidate_engine()
@@ -455,6 +464,7 @@ class SegOFAModel(FairseqEncoderDecoderModel):
 
     def _apply(self, fn, *a, **k):
         self.invalidate_engine()
+        self._train_engine = None  # the arena views are replaced by .to()/.cuda()/.float()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict=True, model_cfg=None, args=None, **kw):
@@ -525,13 +535,14 @@ class SegOFAModel(FairseqEncoderDecoderModel):
                 raise NotImplementedError(f"segofa_b200: `{nm}` is not on the IFSeg hot path (SURVEY.md s8)")
         if return_all_hiddens:
             raise NotImplementedError("segofa_b200: return_all_hiddens is not implemented")
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+        grad_mode = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
+        if grad_mode and src_tokens is not None:
             raise NotImplementedError(
-                "segofa_b200 round 1 implements the no-grad forward (inference / the trainer's inference_mode "
-                "pass); the autograd path of the image-free branch is not built yet -- wrap the call in "
-                "torch.no_grad()/inference_mode() or model.eval()"
-            )
-        eng = self.engine()
+                "segofa_b200: the real-image branch has no backward (every shipped recipe trains the image-free "
+                "branch and runs this one under torch.inference_mode(), seg_criterion.py:185) -- wrap the call in "
+                "torch.no_grad()/inference_mode() or use model.eval()")
+        # while a training engine exists its live-operand inference engine follows every optimizer update
+        eng = self._train_engine.inf if (self._train_engine is not None and self.training) else self.engine()
         x, extra = None, {}
         if src_tokens is not None:
             enc = eng.encode(src_tokens, patch_images=patch_images, patch_masks=patch_masks)
@@ -540,7 +551,12 @@ class SegOFAModel(FairseqEncoderDecoderModel):
             x, extra = eng.decode(enc, prev_output_tokens, full_context_alignment=full_context_alignment,
                                   features_only=features_only)
             extra["encoder_returns"] = eng.encoder_out_dict(enc)
-        if aux_input is not None:
+        if aux_input is not None and grad_mode:
+            # image-free branch with gradients: forward keeps the activations, backward is the hand-written adjoint
+            # chain (train_engine.py); always causal (full_context_alignment is not forwarded, segofa.py:145-149)
+            ax = self.train_engine().imfree_logits(aux_input)
+            extra["aux_output"] = (ax, {"attn": [None], "inner_states": []})
+        elif aux_input is not None:
             aenc = eng.encode(aux_input.get("src_tokens"), bag_tokens=aux_input.get("patch_images"),
                               bag_offsets=aux_input.get("patch_masks"))
             ax, aextra = eng.decode(aenc, aux_input.get("prev_output_tokens"), full_context_alignment=False)

@@ -85,6 +85,35 @@ class ParamArena:
             self.exp_avg_sq = torch.zeros_like(self.flat32)
 
 
+class ImFreeBranchFunction(torch.autograd.Function):
+    """autograd bridge for drop-in callers (optimizer.backward(loss), fp16_optimizer.py:96-106): the forward runs
+    SegOFATrainEngine.forward_train, the backward runs the hand-written adjoint chain and ACCUMULATES the parameter
+    gradients straight into param.grad (views of the flat gradient arena) -- so fairseq's legacy_ddp / our own
+    bucketed all-reduce, which reduce whatever .grad holds after backward, work unchanged.  (`hook` is a dummy
+    leaf that makes the output require grad; parameters are not autograd inputs.)"""
+
+    @staticmethod
+    def forward(ctx, hook, engine, aux_input):
+        c = engine.forward_train(aux_input)
+        ctx.engine, ctx.c = engine, c
+        return c["logits"]
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        eng, c = ctx.engine, ctx.c
+        C = eng.cfg.num_seg
+        dl = torch.zeros((c["B"], c["Td"], _pad8(C)), dtype=_BF16, device=dlogits.device)
+        dl[..., :C] = dlogits
+        eng.attach_grads()
+        prev, eng.accumulate = eng.accumulate, True
+        try:
+            eng.backward_from(c, dl)
+        finally:
+            eng.accumulate = prev
+        ctx.c = None
+        return None, None, None
+
+
 class _Dense:
     """One GEMM operand set: fp32 master view(s), bf16 W [N,K], bf16 W^T [K,pad8(N)], grads."""
     __slots__ = ("src", "w16", "w16t", "b32", "gw", "gb", "N", "K")
@@ -109,6 +138,8 @@ class SegOFATrainEngine:
         self.accumulate = False
         self.grad_sync = None  # callable(lo, hi): gradient range [lo,hi) of arena.grad32 is final (DDP bucket)
         self.step_count = 0
+        self._fresh = False
+        self._hook = None
         self._step_dev = None
         self._scratch: Dict = {}
         self.refresh_weights()
@@ -187,6 +218,23 @@ class SegOFATrainEngine:
                 p.grad = None
             elif p.requires_grad and id(p) not in covered:
                 raise RuntimeError(f"trainable parameter {name} is not covered by the training engine")
+
+    def attach_grads(self):
+        """param.grad <- views of arena.grad32 (again).  zero_grad(set_to_none=True) drops them: the arena is then
+        cleared, which is exactly what the caller asked for."""
+        ar = self.arena
+        missing = [p for p in ar.params if p.grad is None]
+        if missing:
+            ar.grad32.zero_()
+            for p in ar.params:
+                o, n = ar.slots[id(p)]
+                p.grad = ar.grad32[o:o + n].view(p.shape)
+
+    def imfree_logits(self, aux_input):
+        """logits [B,Td,C] of the image-free branch, attached to autograd (see ImFreeBranchFunction)."""
+        if self._hook is None:
+            self._hook = torch.zeros((), device=self.device, requires_grad=True)
+        return ImFreeBranchFunction.apply(self._hook, self, aux_input)
 
     def _sync_down(self, key):
         """Gradients of arena[marks[key]:] are final: hand the not-yet-synchronised part to the DDP callback."""
@@ -291,6 +339,7 @@ class SegOFATrainEngine:
         for d in self.dense:
             if first or d.gw is not None:
                 ops.transpose_cast(d.src, out_t=d.w16t, out_c=d.w16)
+        self._fresh = True
         if self.inf is None:
             self.inf = SegOFAEngine(self.model, live=self)
 
@@ -307,13 +356,13 @@ class SegOFATrainEngine:
     def _lin_fwd(self, a, L: _Dense, tag, **kw):
         return ops.gemm(a, L.w16, bias=L.b32, tag=tag, **kw)
 
-    def _lin_bwd(self, dy, x, L: _Dense, M, tag, need_dx=True, dx_dtype=_BF16, dx_out=None):
+    def _lin_bwd(self, dy, x, L: _Dense, M, tag, need_dx=True, dx_dtype=_BF16, dx_out=None, bias_done=False):
         """dy bf16 [M,N] (row stride may exceed N), x bf16 [M,K] saved input.  Writes dW / db into the arena
         gradient views, returns dX = dY W."""
         N, K = L.N, L.K
         Mp = _pad8(M)
         if L.gw is not None:
-            if L.gb is not None:
+            if L.gb is not None and not bias_done:
                 ops.transpose_cast(dy, M=M, N=N, want_t=False, colsum=L.gb)  # db = column sums of dY
             if K % 32 == 0:
                 # dW[n,k] (+)= sum_t dY[t,n] X[t,k]: both operands are read as they lie (MN-major TMA tiles), the token
@@ -321,7 +370,7 @@ class SegOFATrainEngine:
                 tiles = ((N + 127) // 128) * ((K + 127) // 128)
                 split = max(1, min(8, (296 + tiles - 1) // tiles, (M + 1023) // 1024))
                 ops.gemm_ex(dy, x, L.gw, M=N, N=K, K=M, a_mn=True, b_mn=True, lda=dy.stride(0), ldb=x.stride(0),
-                            split_k=split, tag="wgrad_" + tag)
+                            split_k=split, accumulate=True, tag="wgrad_" + tag)
             else:
                 dyt = self._buf(("dyt", Mp), (max(d.N for d in self.dense), Mp), _BF16)
                 xt = self._buf(("xt", Mp), (max(d.K for d in self.dense), Mp), _BF16)
@@ -342,6 +391,25 @@ class SegOFATrainEngine:
         end offsets, prev_output_tokens); target_classes int64 [B,S,S] class ids (<0 or >=C ignored).
         Returns (loss 0-dim tensor = mean pixel CE, logits fp32 [B,Td,C]); gradients of the mean loss times
         grad_scale are left in param.grad (views of arena.grad32)."""
+        c = self.forward_train(aux_input, check_pads=check_pads)
+        logits, h, w = c["logits"], c["h"], c["w"]
+        tgt = target_classes.to(self.device).contiguous()
+        pix_lse = torch.empty(tuple(tgt.shape), dtype=torch.float32, device=self.device)
+        acc = ops.upsample_ce_loss(logits, tgt, h, w, label_smoothing, lse_out=pix_lse, raw=True)
+        loss = acc[0] / acc[1]
+        if not backward:
+            return loss, logits
+        dlogits = torch.empty((c["B"], c["Td"], _pad8(self.cfg.num_seg)), dtype=_BF16, device=self.device)
+        ops.upsample_ce_loss_bwd(logits, tgt, pix_lse, acc[1:], h, w, dlogits, label_smoothing, grad_scale)
+        self.backward_from(c, dlogits)
+        return loss, logits
+
+    def forward_train(self, aux_input, check_pads=True):
+        """Forward of the image-free branch keeping what the adjoints need; returns the context dict
+        (`logits` fp32 [B,Td,C] among it) that backward_from consumes."""
+        if not self._fresh:
+            self.refresh_weights()  # an external optimizer may have updated the fp32 masters in place
+        self._fresh = False
         cfg, dev = self.cfg, self.device
         D, H, Fd, C = cfg.embed_dim, cfg.heads, cfg.ffn_dim, cfg.num_seg
         src_tokens = aux_input["src_tokens"].to(dev)
@@ -357,9 +425,6 @@ class SegOFATrainEngine:
 
         enc_biases, pos = self.inf._encoder_bias(h, w, T_txt, True)
         self_biases, cross_abs = self.inf._decoder_bias(h, w, pos)
-        if not self.accumulate:
-            self.arena.grad32.zero_()
-        self._sync_hi = self.arena.numel
 
         # ------------------------------ encoder forward ------------------------------
         bag = ops.embedding_bag_mean(aux_input["patch_images"].to(dev).contiguous(),
@@ -452,16 +517,30 @@ class SegOFATrainEngine:
         feats = a
         logits = ops.gemm(feats, self.seg_proj.w16, out_dtype=f32, tag="seg_proj").view(B, Td, C)
 
-        # ------------------------------ loss ------------------------------
-        tgt = target_classes.to(dev).contiguous()
-        pix_lse = new(tuple(tgt.shape), f32)
-        acc = ops.upsample_ce_loss(logits, tgt, h, w, label_smoothing, lse_out=pix_lse, raw=True)
-        loss = acc[0] / acc[1]
-        if not backward:
-            return loss, logits
-        Cp = _pad8(C)
-        dlogits = new((B, Td, Cp))
-        ops.upsample_ce_loss_bwd(logits, tgt, pix_lse, acc[1:], h, w, dlogits, label_smoothing, grad_scale)
+        return dict(logits=logits, h=h, w=w, B=B, T_txt=T_txt, P=P, T=T, Td=Td, M=M, Md=Md, bag=bag, tok_idx=tok_idx,
+                    x_emb=x_emb, xd_emb=xd_emb, enc_out=enc_out, kv_all=kv_all, feats=feats, dec_in_idx=dec_in_idx, bos=bos,
+                    enc_saved=enc_saved, dec_saved=dec_saved, enc_biases=enc_biases, self_biases=self_biases,
+                    cross_abs=cross_abs)
+
+    def backward_from(self, c, dlogits):
+        """Adjoint of forward_train: dlogits bf16 [B,Td,pad8(C)] = dL/dlogits.  Parameter gradients are written
+        (accumulated when self.accumulate) into arena.grad32, i.e. into param.grad."""
+        cfg, dev = self.cfg, self.device
+        D, H, Fd, C = cfg.embed_dim, cfg.heads, cfg.ffn_dim, cfg.num_seg
+        f32 = torch.float32
+        new = lambda shape, dt=_BF16: torch.empty(shape, dtype=dt, device=dev)  # noqa: E731
+        B, T_txt, P, T, Td, M, Md = (c[k] for k in ("B", "T_txt", "P", "T", "Td", "M", "Md"))
+        bag, tok_idx, x_emb, xd_emb, enc_out, kv_all, feats = (c[k] for k in (
+            "bag", "tok_idx", "x_emb", "xd_emb", "enc_out", "kv_all", "feats"))
+        dec_in_idx, bos, enc_saved, dec_saved = c["dec_in_idx"], c["bos"], c["enc_saved"], c["dec_saved"]
+        enc_biases, self_biases, cross_abs = c["enc_biases"], c["self_biases"], c["cross_abs"]
+        nL = len(self.dec_layers)
+        s3, sd3 = (3 * D, T * 3 * D), (3 * D, Td * 3 * D)
+        kvs = (nL * 2 * D, T * nL * 2 * D)
+        Cp = dlogits.shape[-1]
+        if not self.accumulate:
+            self.arena.grad32.zero_()
+        self._sync_hi = self.arena.numel
 
         # ------------------------------ decoder backward ------------------------------
         da = self._lin_bwd(dlogits.view(Md, Cp), feats, self.seg_proj, Md, "seg_proj")  # [Md, D] bf16
@@ -473,20 +552,21 @@ class SegOFATrainEngine:
             dx_new = dxs if dxs is not None else new((Md, D), f32)
             dy = new((Md, D))
             ops.row_layernorm_bwd(rows=Md, D=D, v=S["x3"], g2=nxt[0], dy2=da, dv_in=dxs, d_res=dx_new, dx=dy,
-                                  dg2=nxt[2], db2=nxt[3])
+                                  dg2=nxt[2], db2=nxt[3], dx_colsum=L["fc2"].gb)
             dxs = dx_new
-            dz = self._lin_bwd(dy, S["z"], L["fc2"], Md, "fc2")
+            dz = self._lin_bwd(dy, S["z"], L["fc2"], Md, "fc2", bias_done=True)
             dh = new((Md, Fd))
             ops.row_layernorm_bwd(rows=Md, D=Fd, x=S["h"], x_act=ops.ACT_GELU, g2=L["ln_ffn"][0], dy2=dz, dx=dh,
-                                  dg2=L["ln_ffn"][2], db2=L["ln_ffn"][3])
-            da3 = self._lin_bwd(dh, S["a3"], L["fc1"], Md, "fc1")
+                                  dg2=L["ln_ffn"][2], db2=L["ln_ffn"][3], dx_colsum=L["fc1"].gb)
+            da3 = self._lin_bwd(dh, S["a3"], L["fc1"], Md, "fc1", bias_done=True)
             # cross-attention block
             dyc = new((Md, D))
             ops.row_layernorm_bwd(rows=Md, D=D, x=S["yc"], g1=L["ln_cross_attn"][0], v=S["x2"], g2=L["ln_final"][0],
                                   dy2=da3, dv_in=dxs, d_res=dxs, dx=dyc, dg1=L["ln_cross_attn"][2],
-                                  db1=L["ln_cross_attn"][3], dg2=L["ln_final"][2], db2=L["ln_final"][3])
+                                  db1=L["ln_cross_attn"][3], dg2=L["ln_final"][2], db2=L["ln_final"][3],
+                                  dx_colsum=L["cross"]["out"].gb)
             Cx = L["cross"]
-            doc = self._lin_bwd(dyc, S["oc"], Cx["out"], Md, "out_proj")
+            doc = self._lin_bwd(dyc, S["oc"], Cx["out"], Md, "out_proj", bias_done=True)
             dqc = new((Md, D))
             kbase, dkbase = kv_all[:, li * 2 * D:], dkv_all[:, li * 2 * D:]
             delta = self._buf("delta", (B, H, max(T, Td)), f32)
@@ -500,8 +580,9 @@ class SegOFATrainEngine:
             dy = new((Md, D))
             ops.row_layernorm_bwd(rows=Md, D=D, x=S["y"], g1=L["ln_self_attn"][0], v=S["x1"], g2=L["ln_enc_attn"][0],
                                   dy2=da2, dv_in=dxs, d_res=dxs, dx=dy, dg1=L["ln_self_attn"][2],
-                                  db1=L["ln_self_attn"][3], dg2=L["ln_enc_attn"][2], db2=L["ln_enc_attn"][3])
-            do = self._lin_bwd(dy, S["o"], L["attn"]["out"], Md, "out_proj")
+                                  db1=L["ln_self_attn"][3], dg2=L["ln_enc_attn"][2], db2=L["ln_enc_attn"][3],
+                                  dx_colsum=L["attn"]["out"].gb)
+            do = self._lin_bwd(dy, S["o"], L["attn"]["out"], Md, "out_proj", bias_done=True)
             dqkv = new((Md, 3 * D))
             ops.attention_bwd(S["qkv"], S["qkv"][:, D:], S["qkv"][:, 2 * D:], S["o"], do, dqkv, dqkv[:, D:],
                               dqkv[:, 2 * D:], B=B, H=H, Tq=Td, Tk=Td, q_strides=sd3, k_strides=sd3, v_strides=sd3,
@@ -531,18 +612,18 @@ class SegOFATrainEngine:
             dx_new = dxs if dxs is not None else new((M, D), f32)
             dy = new((M, D))
             ops.row_layernorm_bwd(rows=M, D=D, v=S["x2"], g2=nxt[0], dy2=da, dv_in=dxs, d_res=dx_new, dx=dy,
-                                  dg2=nxt[2], db2=nxt[3])
+                                  dg2=nxt[2], db2=nxt[3], dx_colsum=L["fc2"].gb)
             dxs = dx_new
-            dz = self._lin_bwd(dy, S["z"], L["fc2"], M, "fc2")
+            dz = self._lin_bwd(dy, S["z"], L["fc2"], M, "fc2", bias_done=True)
             dh = new((M, Fd))
             ops.row_layernorm_bwd(rows=M, D=Fd, x=S["h"], x_act=ops.ACT_GELU, g2=L["ln_ffn"][0], dy2=dz, dx=dh,
-                                  dg2=L["ln_ffn"][2], db2=L["ln_ffn"][3])
-            da2 = self._lin_bwd(dh, S["a2"], L["fc1"], M, "fc1")
+                                  dg2=L["ln_ffn"][2], db2=L["ln_ffn"][3], dx_colsum=L["fc1"].gb)
+            da2 = self._lin_bwd(dh, S["a2"], L["fc1"], M, "fc1", bias_done=True)
             dy = new((M, D))
             ops.row_layernorm_bwd(rows=M, D=D, x=S["y"], g1=L["ln_attn"][0], v=S["x1"], g2=L["ln_final"][0], dy2=da2,
                                   dv_in=dxs, d_res=dxs, dx=dy, dg1=L["ln_attn"][2], db1=L["ln_attn"][3],
-                                  dg2=L["ln_final"][2], db2=L["ln_final"][3])
-            do = self._lin_bwd(dy, S["o"], L["attn"]["out"], M, "out_proj")
+                                  dg2=L["ln_final"][2], db2=L["ln_final"][3], dx_colsum=L["attn"]["out"].gb)
+            do = self._lin_bwd(dy, S["o"], L["attn"]["out"], M, "out_proj", bias_done=True)
             dqkv = new((M, 3 * D))
             delta = self._buf("delta", (B, H, max(T, Td)), f32)
             ops.attention_bwd(S["qkv"], S["qkv"][:, D:], S["qkv"][:, 2 * D:], S["o"], do, dqkv, dqkv[:, D:],
@@ -564,7 +645,6 @@ class SegOFATrainEngine:
                               db1=self.ln_emb[3], dg2=g_l0[2], db2=g_l0[3], d_pre_add=gt[0] if gt is not None else None,
                               seg=(T_txt, T, P))
         self._sync_down(None)
-        return loss, logits
 
     # ------------------------------------------------------------------------------------
     # optimizer: clip_grad_norm (trainer.py:886) + fused Adam on the flat buffers (fp16_optimizer/adam.py)

@@ -74,7 +74,7 @@ int sgf_gemm_bf16(const sgf_gemm_args* args, void* stream);
  *   C[M,N] (+)= A_eff[M,K] * B_eff[N,K]^T   with  A_eff[m,k] = a_mn_major ? a[k*lda + m] : a[m*lda + k]
  *                                                B_eff[n,k] = b_mn_major ? b[k*ldb + n] : b[n*ldb + k]
  * (a_mn, b_mn) = (1,1): dW = dY^T X over the token dimension;  (0,1): dX = dY W with W as stored [N_out,K_in].
- * Plain epilogue only (no bias/activation/residual; batch = 1).  split_k > 1 splits the contraction over
+ * Plain epilogue only (no bias/activation; batch = 1; residual == c requests in-place accumulation).  split_k > 1 splits the contraction over
  * blockIdx.z and REDUCES the partial tiles into C with vector fp32 atomics: C must be fp32 and hold the value to
  * accumulate onto (zeros, or a running gradient for gradient accumulation).  N % 32 == 0. */
 int sgf_gemm_bf16_ex(const sgf_gemm_args* args, int32_t a_mn_major, int32_t b_mn_major, int32_t split_k, void* stream);

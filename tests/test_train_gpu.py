@@ -106,3 +106,54 @@ def test_train_loop_decreases_loss_and_keeps_views(cuda_device):
     assert p.data_ptr() >= eng.arena.flat32.data_ptr()
     assert not torch.equal(p.detach().cpu(), sd["encoder.layers.0.fc1.weight"])
     assert torch.isfinite(eng.arena.flat32).all()
+
+
+def test_criterion_training_branch_through_autograd(cuda_device):
+    """The drop-in call sequence of task.train_step (segmentation.py:190-222): model.train();
+    loss, sample_size, log = criterion(model, sample); optimizer.backward(loss) -> loss.backward().
+    Gradients arrive in param.grad (views of the arena) and equal the fused forward_backward path."""
+    import types
+
+    from ifseg_b200.fairseq_compat import StubDictionary
+    from ifseg_b200.seg_criterion import SegCriterion
+    from ifseg_b200.synthetic import synthetic_inputs
+
+    g, gg, model, sd, eng0, aux, tgt, t2s = _setup()
+    # reference gradients of the fused path (own engine instance of the same model)
+    loss0, _ = eng0.forward_backward(aux, tgt)
+    ref = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    model._train_engine = eng0
+    model.train()
+    C, S, B = g["num_seg"], g["image_size"], g["batch"]
+    task = types.SimpleNamespace(target_dictionary=StubDictionary(C),
+                                 cfg=types.SimpleNamespace(num_seg_tokens=C, category_list=",".join(f"c{i}" for i in range(C))))
+    crit = SegCriterion(task)
+    inp = {k: v.cuda() for k, v in synthetic_inputs(model.cfg, B, S, seed=1, src_tokens=g["src_tokens"][0]).items()}
+    gen = torch.Generator().manual_seed(9)
+    target = torch.cat([torch.randint(0, C + 1, (B, S * S), generator=gen) + 59457, torch.full((B, 1), 2)], 1)
+    sample = {"net_input": inp, "aux_input": aux, "target": target, "text2seg_target": t2s, "ntokens": 1, "nsentences": B}
+    model.zero_grad(set_to_none=True)
+    loss, sample_size, log = crit(model, sample)
+    assert loss.requires_grad and sample_size == 1
+    for k in ("loss", "imfree_loss", "seg_loss", "area_intersect", "area_union", "nll_loss"):
+        assert k in log
+    assert abs(loss.item() - loss0.item()) < 1e-5
+    loss.backward()
+    torch.cuda.synchronize()
+    n = 0
+    for k, p in model.named_parameters():
+        if k in ref:
+            assert p.grad is not None and p.grad.data_ptr() >= eng0.arena.grad32.data_ptr()
+            assert rel_l2(p.grad, ref[k]) < 2e-3 or ref[k].norm().item() < 1e-6, (k, rel_l2(p.grad, ref[k]))
+            n += 1
+    assert n == len(ref) and n >= 323
+    # autograd semantics: a second backward accumulates
+    loss2, _, _ = crit(model, sample)
+    loss2.backward()
+    k = "encoder.layers.0.fc1.weight"
+    assert rel_l2(dict(model.named_parameters())[k].grad, 2 * ref[k]) < 2e-3
+    # eval after training uses the updated parameters through a fresh inference engine
+    model.eval()
+    with torch.no_grad():
+        x, _ = model(**inp)
+    assert torch.isfinite(x).all()

@@ -1,8 +1,6 @@
 set -x
-timeout 900 python -m pytest tests/test_train_ops_gpu.py -q > gpurun_out/train_ops_c.log 2>&1
-tail -15 gpurun_out/train_ops_c.log
-timeout 900 python -m pytest tests/test_train_gpu.py -q -x -s > gpurun_out/train_gpu.log 2>&1
-tail -8 gpurun_out/train_gpu.log
+timeout 900 python -m pytest tests/test_train_gpu.py tests/test_train_ops_gpu.py -q -x > gpurun_out/train_gpu.log 2>&1
+tail -5 gpurun_out/train_gpu.log
 timeout 900 python bench.py --config 3 --steps 10 --warmup 3 --no-cpu-baseline --kernel-breakdown > gpurun_out/bench_train_graph.json 2> gpurun_out/bench_train_graph.err
 python - <<'PY'
 import json
@@ -10,4 +8,4 @@ d=json.load(open('gpurun_out/bench_train_graph.json'))
 print(d['ms_per_step'], d['value'], d['e2e'], d['roofline']['step'])
 print(d['kernel_families'])
 PY
-head -12 gpurun_out/bench_train_graph.err
+grep -E "row_layernorm|transpose|attention" gpurun_out/bench_train_graph.err
