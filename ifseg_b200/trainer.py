@@ -107,10 +107,25 @@ class TrainSession:
                 self.out = trainer.train_step(self.static, check_pads=False)
                 self.launches_per_step = ops.launch_count() - n0
         self.stream.synchronize()
-        if use_cuda_graph and trainer.world == 1:
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=self.stream):
-                self.out = trainer.train_step(self.static, check_pads=False)
+        import os
+
+        # world > 1: capturing the bucketed NCCL all-reduces works (c10d records them as cross-stream dependencies, so
+        # they still overlap the backward: 31.1 vs 31.7 ms eager at 2 GPUs) but process-group teardown then hangs
+        # with this torch/NCCL build, so multi-GPU sessions run eagerly unless SGF_GRAPH_NCCL=1
+        if use_cuda_graph and (trainer.world == 1 or os.environ.get("SGF_GRAPH_NCCL") == "1"):
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=self.stream):
+                    self.out = trainer.train_step(self.static, check_pads=False)
+                self.graph = graph
+            except Exception as e:  # noqa: BLE001 -- e.g. a c10d build that refuses capture: stay eager
+                if trainer.world == 1:
+                    raise
+                import warnings
+
+                warnings.warn(f"CUDA-graph capture of the multi-GPU train step failed ({e}); running eagerly")
+                torch.cuda.synchronize()
+                self.graph = None
 
     def load(self, sample_host):
         """host (pinned) sample -> the static device buffers (async on the session stream)."""
