@@ -141,6 +141,15 @@ class AttentionBwdArgs(C.Structure):
         ("lse", _vp), ("delta", _vp),
         ("dq_scale", _f32),
         ("B", _i32), ("H", _i32), ("Tq", _i32), ("Tk", _i32), ("causal", _i32),
+        ("dbias", _vp),
+    ]
+
+
+class BiasBwdArgs(C.Structure):
+    _fields_ = [
+        ("dbias", _vp), ("dabs_acc", _vp), ("head_stride", _i64), ("row_stride", _i64),
+        ("H", _i32), ("Tq", _i32),
+        ("num_blocks", _i32), ("order", _vp * 2), ("offsets", _vp * 2), ("dtable", _vp * 2), ("num_rel", _i32 * 2),
     ]
 
 
@@ -167,6 +176,7 @@ EXPORTS = [
     ("sgf_row_layernorm_bwd", C.c_int, [C.POINTER(RowLnBwdArgs), _vp]),
     ("sgf_transpose_cast", C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp]),
     ("sgf_attention_bwd_bf16", C.c_int, [C.POINTER(AttentionBwdArgs), _vp]),
+    ("sgf_attn_bias_bwd", C.c_int, [C.POINTER(BiasBwdArgs), _vp]),
     ("sgf_adam_step", C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp, _vp]),
     ("sgf_sumsq", C.c_int, [_vp, _i64, _vp, _vp]),
 ]

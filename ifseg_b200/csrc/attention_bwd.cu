@@ -37,6 +37,7 @@ struct AttnBwdParams {
   void* dk; int64_t dk_row_stride, dk_batch_stride;
   void* dv; int64_t dv_row_stride, dv_batch_stride;
   int B, H, Tq, Tk, causal;
+  float* dbias;  // optional fp32 [H,Tq,bias_row_stride]: += dS summed over the batch (vector atomics)
 };
 
 // ----------------------------------------------------------------------------------------
@@ -280,6 +281,14 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dq_kernel(const __gri
           }
           const float ds = pr * fmaf(hs, __uint_as_float(rp[i]), -dl);
           rs[i] = __float_as_uint(ds);
+        }
+        if (p.dbias && row_ok) {  // d(bias)[h,i,j] += dS: the bias is shared by the batch (and, for abs, by the layers)
+          float* db = p.dbias + static_cast<int64_t>(h) * p.bias_head_stride + static_cast<int64_t>(row) * p.bias_row_stride +
+                      k0 + half * 32;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            red_add_f32x4(db + 4 * c, __uint_as_float(rs[4 * c]), __uint_as_float(rs[4 * c + 1]),
+                          __uint_as_float(rs[4 * c + 2]), __uint_as_float(rs[4 * c + 3]));
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i)
@@ -628,7 +637,10 @@ extern "C" int sgf_attention_bwd_bf16(const sgf_attention_bwd_args* a, void* str
   }
   AttnBwdParams p{a->bias, a->bias_head_stride, a->bias_row_stride, a->head_scale, a->key_padding_mask, a->lse,
                   a->delta, a->dq, a->dq_row_stride, a->dq_batch_stride, a->dq_scale, a->dk, a->dk_row_stride,
-                  a->dk_batch_stride, a->dv, a->dv_row_stride, a->dv_batch_stride, a->B, a->H, a->Tq, a->Tk, a->causal};
+                  a->dk_batch_stride, a->dv, a->dv_row_stride, a->dv_batch_stride, a->B, a->H, a->Tq, a->Tk, a->causal,
+                  a->dbias};
+  SGF_REQUIRE(!a->dbias || (a->bias && reinterpret_cast<uintptr_t>(a->dbias) % 16 == 0 && a->bias_row_stride % 64 == 0),
+              "attention_bwd: dbias needs bias (same strides), 16-byte alignment and a row stride padded to 64");
   static bool configured = false;
   if (!configured) {
     SGF_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::kTotal));

@@ -306,6 +306,10 @@ SGF_DEVICE float gelu_erf(float x) {
   const float erf_abs = fmaf(-p * t, e, 1.0f);  // erf(|x|/sqrt2)
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
+// vector fp32 reduction into global memory (no return value): one 16-byte L2 atomic
+SGF_DEVICE void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 SGF_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -66,10 +66,6 @@ enum : int {
   kEpiScale = 1, kEpiBias = 2, kEpiAlpha = 4, kEpiGelu = 8, kEpiRelu = 16, kEpiResBf16 = 32, kEpiResF32 = 64,
   kEpiOutF32 = 128, kEpiRowStats = 256, kEpiRowNorm = 512, kEpiAtomic = 1024, kEpiRuntime = 1 << 15
 };
-SGF_DEVICE void red_add_f32x4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 template <int kEpi, int kFlag>
 SGF_DEVICE bool epi_has(bool runtime_value) {
   if constexpr ((kEpi & kEpiRuntime) != 0) return runtime_value;

@@ -265,6 +265,41 @@ __global__ void __launch_bounds__(256) build_attn_bias_kernel(const BiasParams p
   }
 }
 
+// adjoint of build_attn_bias_kernel.  Shared-memory fp32 atomics are CAS loops on this architecture, so the
+// relative-position table gradient is a GATHER: the (i,j) positions of every bucket are a static CSR list (built
+// once per shape on the host); one warp sums the positions of one (bucket, head) and adds the result to the table
+// gradient (unique owner: no atomics, deterministic).  A second elementwise kernel folds the layer's gradient into
+// the abs-term accumulator and clears the per-layer buffer.
+__global__ void __launch_bounds__(256) bias_table_gather_kernel(const float* __restrict__ dbias, int64_t head_stride,
+                                                                const int32_t* __restrict__ order,
+                                                                const int32_t* __restrict__ offsets, int num_rel, int H,
+                                                                float* __restrict__ dtable) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int h = blockIdx.y;
+  if (r >= num_rel) return;
+  const int lane = threadIdx.x & 31;
+  const int lo = offsets[r], hi = offsets[r + 1];
+  if (lo == hi) return;
+  const float* src = dbias + h * head_stride;
+  float s = 0.f;
+  for (int t = lo + lane; t < hi; t += 32) s += __ldg(src + order[t]);
+  s = warp_sum(s);
+  if (lane == 0) dtable[static_cast<int64_t>(r) * H + h] += s;
+}
+
+__global__ void __launch_bounds__(256) bias_fold_clear_kernel(float4* __restrict__ dbias, float4* __restrict__ dabs,
+                                                              int64_t n4) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = dbias[i];
+  if (dabs) {
+    float4 a = dabs[i];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    dabs[i] = a;
+  }
+  dbias[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // ----------------------------------------------------------------------------------------
 // stem helpers
 // ----------------------------------------------------------------------------------------
@@ -495,6 +530,29 @@ extern "C" int sgf_build_attn_bias(const sgf_bias_args* a, void* stream) {
   }
   dim3 grid((a->Tk + 255) / 256, a->Tq), block(256);
   build_attn_bias_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
+
+extern "C" int sgf_attn_bias_bwd(const sgf_bias_bwd_args* a, void* stream) {
+  SGF_REQUIRE(a != nullptr && a->dbias, "attn_bias_bwd: null pointer");
+  SGF_REQUIRE(a->H > 0 && a->Tq > 0 && a->row_stride % 4 == 0 && a->head_stride == static_cast<int64_t>(a->Tq) * a->row_stride &&
+                  reinterpret_cast<uintptr_t>(a->dbias) % 16 == 0,
+              "attn_bias_bwd: dbias must be a dense [H,Tq,row_stride] buffer with row_stride %% 4 == 0");
+  SGF_REQUIRE(a->num_blocks >= 0 && a->num_blocks <= 2, "attn_bias_bwd: at most 2 blocks");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int b = 0; b < a->num_blocks; ++b) {
+    SGF_REQUIRE(a->order[b] && a->offsets[b] && a->dtable[b] && a->num_rel[b] > 0, "attn_bias_bwd: bad block %d", b);
+    dim3 grid((a->num_rel[b] + 7) / 8, a->H);
+    bias_table_gather_kernel<<<grid, 256, 0, st>>>(a->dbias, a->head_stride, a->order[b], a->offsets[b], a->num_rel[b],
+                                                   a->H, a->dtable[b]);
+    SGF_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  const int64_t n4 = static_cast<int64_t>(a->H) * a->head_stride / 4;
+  bias_fold_clear_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<float4*>(a->dbias), reinterpret_cast<float4*>(a->dabs_acc), n4);
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return SGF_OK;

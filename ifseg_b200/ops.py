@@ -377,7 +377,7 @@ def transpose_cast(x, M=None, N=None, out_t=None, out_c=None, colsum=None, want_
 
 def attention_bwd(q, k, v, out, dout, dq, dk, dv, *, B, H, Tq, Tk, q_strides, k_strides, v_strides, o_strides,
                   do_strides, dq_strides, dk_strides, dv_strides, lse, delta, bias=None, head_scale=None,
-                  d_head_scale=None, key_padding_mask=None, causal=False, dq_scale=1.0):
+                  d_head_scale=None, key_padding_mask=None, causal=False, dq_scale=1.0, dbias=None):
     lib = _lib.load()
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (dout, "dout"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
         _req(t, torch.bfloat16, n)
@@ -389,10 +389,45 @@ def attention_bwd(q, k, v, out, dout, dq, dk, dv, *, B, H, Tq, Tk, q_strides, k_
         _p(dq), dq_strides[0], dq_strides[1], _p(dk), dk_strides[0], dk_strides[1], _p(dv), dv_strides[0], dv_strides[1],
         _p(bias), bias.stride(0) if bias is not None else 0, bias.stride(1) if bias is not None else 0,
         _p(head_scale), _p(d_head_scale), _p(key_padding_mask), _p(lse), _p(delta), float(dq_scale),
-        B, H, Tq, Tk, 1 if causal else 0)
+        B, H, Tq, Tk, 1 if causal else 0, _p(dbias))
     pairs = Tq * Tk if not causal else Tq * (Tq + 1) / 2.0
     with _timed("attention_bwd_tcgen05", 10.0 * B * H * pairs * 64):  # 5 algorithmic tile GEMMs
         _lib.check(lib.sgf_attention_bwd_bf16(C.byref(args), _stream()), "sgf_attention_bwd_bf16")
+
+
+def bias_block_csr(bucket, ids, lo, row_stride):
+    """Static CSR grouping of the positions of one relative-position block by bucket (host-side, once per shape):
+    returns (order int32 [n*n] of flat positions i*row_stride + j, offsets int32 [num_rel+1] -- sized by the caller's
+    table) as device tensors.  bucket int64 [*,*], ids int64 [n]."""
+    b = bucket[ids][:, ids]  # [n, n] bucket of (i, j)
+    n = ids.numel()
+    flat = b.reshape(-1)
+    perm = torch.argsort(flat, stable=True)
+    ii, jj = perm // n, perm % n
+    order = ((ii + lo) * row_stride + (jj + lo)).to(torch.int32)
+    return order.contiguous(), flat
+
+
+def attn_bias_bwd(dbias, blocks=(), dabs_acc=None):
+    """Adjoint of build_attn_bias for one layer (see sgf_attn_bias_bwd): dbias fp32 [H,Tq,row_stride] is consumed and
+    cleared; blocks: iterable of (order int32, offsets int32 [num_rel+1], dtable fp32 [num_rel,H])."""
+    lib = _lib.load()
+    _req(dbias, torch.float32, "dbias")
+    H, Tq, _ = dbias.shape
+    args = _lib.BiasBwdArgs()
+    args.dbias = dbias.data_ptr()
+    args.dabs_acc = dabs_acc.data_ptr() if dabs_acc is not None else None
+    args.head_stride, args.row_stride = dbias.stride(0), dbias.stride(1)
+    args.H, args.Tq, args.num_blocks = H, Tq, len(blocks)
+    for i, (order, offsets, dtable) in enumerate(blocks):
+        _req(dtable, torch.float32, "dtable")
+        _req(order, torch.int32, "order")
+        _req(offsets, torch.int32, "offsets")
+        assert dtable.is_contiguous() and dtable.shape[1] == H and offsets.numel() == dtable.shape[0] + 1
+        args.order[i], args.offsets[i], args.dtable[i] = order.data_ptr(), offsets.data_ptr(), dtable.data_ptr()
+        args.num_rel[i] = dtable.shape[0]
+    with _timed("attn_bias_bwd", nbytes=20.0 * H * Tq * dbias.stride(1)):
+        _lib.check(lib.sgf_attn_bias_bwd(C.byref(args), _stream()), "sgf_attn_bias_bwd")
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1,

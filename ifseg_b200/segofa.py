@@ -377,6 +377,7 @@ class SegOFAModel(FairseqEncoderDecoderModel):
         if hasattr(self.encoder, "dictionary"):
             self.eos = self.encoder.dictionary.eos()
         self._engine = None
+        self._train_engine = None
 
     # -- CLI / construction ---------------------------------------------------------------
     @staticmethod
@@ -448,7 +449,6 @@ class SegOFAModel(FairseqEncoderDecoderModel):
         """Drop device-side derived weights (bf16 copies, folded BN, fused QKV).  Called on
         anything that may change parameters."""
         self._engine = None
-        self._train_engine = None
 
     def train_engine(self):
         """The training engine (flat fp32 master arena + hand-written backward); created on first use."""
@@ -469,6 +469,8 @@ class SegOFAModel(FairseqEncoderDecoderModel):
 
     def load_state_dict(self, state_dict, strict=True, model_cfg=None, args=None, **kw):
         self.invalidate_engine()
+        if self._train_engine is not None:  # parameters are copied in place into the arena: re-derive the bf16 operands
+            self._train_engine._fresh = False
         self.upgrade_state_dict_named(state_dict, "")
         return super().load_state_dict(state_dict, strict, **kw)
 

@@ -18,10 +18,14 @@ SegOFAModel.forward aux branch (models/segofa/segofa.py:136-151) -> encode_with_
     statistics, GELU and the attention probabilities); the residual-stream gradient is one fp32 buffer per
     stack updated in place.
 
-Round-1 limits: dropout / DropPath are off (deterministic, eval-mode numerics -- the gradient-parity
-configuration of SURVEY.md s8d); no gradient is produced for the parameters that only feed the additive
-position bias (pos/rel-pos tables, pos_q/k projections, pos LayerNorms) -- their .grad
-stays None and they are not updated.
+  * the additive position bias is differentiated too: the dQ kernel reduces dS over the batch into a
+    per-layer fp32 buffer (vector atomics), `sgf_attn_bias_bwd` scatters it into the relative-position tables and sums
+    the layers' abs terms, and the abs term is pulled back through the head-batched pq pk^T GEMM, the position
+    projections, the position LayerNorms and the (gathered) position tables.  All 380 tensors the reference gives a
+    gradient to receive one; the 20 trainable tensors it never reaches stay without (.grad None), as there.
+
+Round-1 limit: dropout / DropPath are off (deterministic, eval-mode numerics -- the gradient-parity
+configuration of SURVEY.md s8d).
 """
 from typing import Dict, List, Optional
 
@@ -245,8 +249,10 @@ class SegOFATrainEngine:
 
     @staticmethod
     def _is_bias_path(name):
-        keys = ("embed_positions", "embed_image_positions", "embed_seg_positions", "pos_ln.", "image_pos_ln.",
-                "seg_pos_ln.", "pos_q_linear", "pos_k_linear", "rel_pos_table_list", "code_layernorm_embedding")
+        """Trainable tensors that no path of the surrogate decoder reaches (the reference leaves their .grad None
+        too: SURVEY.md s8a, 20 tensors -- the reason the recipes need --find-unused-parameters)."""
+        keys = ("decoder.embed_positions", "decoder.embed_image_positions", "decoder.pos_ln.", "decoder.image_pos_ln.",
+                "decoder.token_rel_pos_table_list", "decoder.image_rel_pos_table_list", "code_layernorm_embedding")
         return any(k in name for k in keys)
 
     def _dense(self, weights, biases):
@@ -327,6 +333,19 @@ class SegOFATrainEngine:
                     ln_final=self._ln(l.final_layer_norm), ln_ffn=self._ln(l.ffn_layernorm),
                     fc1=mk([l.fc1.weight], [l.fc1.bias]), fc2=mk([l.fc2.weight], [l.fc2.bias])))
             self.seg_proj = mk([dec.seg_projection.weight], [None])
+            # additive position bias (encoder_module.py:757-809, decoder_module.py:541-629): projections, LayerNorms,
+            # absolute and relative position tables -- all trainable, all rebuilt every step
+            self.pos_q, self.pos_k = (mk([m_.weight], [m_.bias]) for m_ in (enc.pos_q_linear, enc.pos_k_linear))
+            self.self_pos_q, self.self_pos_k = (mk([m_.weight], [m_.bias]) for m_ in (dec.self_pos_q_linear, dec.self_pos_k_linear))
+            self.cross_pos_q, self.cross_pos_k = (mk([m_.weight], [m_.bias]) for m_ in (dec.cross_pos_q_linear, dec.cross_pos_k_linear))
+            self.ln_pos, self.ln_img_pos, self.ln_seg_pos = self._ln(enc.pos_ln), self._ln(enc.image_pos_ln), self._ln(dec.seg_pos_ln)
+            self.tab_pos, self.tab_img_pos = self._vec(enc.embed_positions.weight), self._vec(enc.embed_image_positions.weight)
+            self.tab_seg_pos = self._vec(dec.embed_seg_positions.weight)
+            self.rel_tok = [self._vec(t.weight) for t in enc.token_rel_pos_table_list]
+            self.rel_img = [self._vec(t.weight) for t in enc.image_rel_pos_table_list]
+            self.rel_seg = [self._vec(t.weight) for t in dec.seg_rel_pos_table_list]
+            self.token_rp_bucket, self.image_rp_bucket = enc.token_rp_bucket.to(self.device), enc.image_rp_bucket.to(self.device)
+            self.seg_rp_bucket = dec.seg_rp_bucket.to(self.device)
             self.ln_emb, self.ln_patch = self._ln(enc.layernorm_embedding), self._ln(enc.patch_layernorm_embedding)
             self.ln_enc_out, self.ln_dec_out = self._ln(enc.layer_norm), self._ln(dec.layer_norm)
             self.dec_ln_emb = self._ln(dec.layernorm_embedding)
@@ -342,6 +361,7 @@ class SegOFATrainEngine:
         self._fresh = True
         if self.inf is None:
             self.inf = SegOFAEngine(self.model, live=self)
+            self.inf.cache_position_bias = False  # the position parameters are trained: rebuilt on every call
 
     # ------------------------------------------------------------------------------------
     # helpers
@@ -353,10 +373,93 @@ class SegOFATrainEngine:
             self._scratch[key] = t
         return t
 
+    def _csr(self, name, bucket, ids, lo, row_stride, dtable):
+        """(order, offsets, dtable) of one relative-position block: static per shape, cached."""
+        key = ("csr", name, ids.numel(), lo, row_stride, dtable.shape[0])
+        hit = self._scratch.get(key)
+        if hit is None:
+            order, flat = ops.bias_block_csr(bucket, ids, lo, row_stride)
+            counts = torch.bincount(flat, minlength=dtable.shape[0])
+            offsets = torch.zeros(dtable.shape[0] + 1, dtype=torch.int32, device=self.device)
+            offsets[1:] = counts.cumsum(0).to(torch.int32)
+            hit = (order, offsets)
+            self._scratch[key] = hit
+        return hit[0], hit[1], dtable
+
+    def _abs_bias(self, pq, pk, Tq, Tk):
+        """fp32 [H, Tq, pad64(Tk)] = per-head pq pk^T (one head-batched GEMM)."""
+        cfg = self.cfg
+        D, H, dh = cfg.embed_dim, cfg.heads, cfg.head_dim
+        Tkp = (Tk + 63) // 64 * 64
+        out = torch.zeros((H, Tq, Tkp), dtype=torch.float32, device=self.device)
+        ops.gemm(pq, pk, out, M=Tq, N=Tk, K=dh, batch=H, lda=D, ldb=D, a_batch_stride=dh, b_batch_stride=dh,
+                 ldc=Tkp, c_batch_stride=Tq * Tkp)
+        return out
+
+    def _position_bias(self, h, w, T_txt):
+        """Additive attention biases of both stacks from the CURRENT position parameters, keeping what their adjoint
+        needs (post-LN position embeddings and the projected q/k positions)."""
+        cfg, dev = self.cfg, self.device
+        P, D = h * w, cfg.embed_dim
+        T, Td = P + T_txt, P + 1
+        oh = cfg.orig_patch_image_size // 16
+        if (h, w) != (oh, oh) or (h, w) != (self.model.decoder.seg_bucket_size,) * 2:
+            raise NotImplementedError("training on a patch grid different from the orig/seg grid (interpolated position "
+                                      "tables) is a 'next' row (SURVEY.md s8f-2)")
+        ids = self.inf._image_position_ids(h, w)
+        tok_ids = self.inf._cached(("arange", T_txt), lambda: torch.arange(T_txt))
+        seg_ids = self.inf._cached(("arange", Td), lambda: torch.arange(Td))
+        pos = torch.empty((T, D), dtype=_BF16, device=dev)
+        ops.row_layernorm(self.tab_img_pos[0], rows=P, gather_idx=ids, ln2=self.ln_img_pos[:2], out2=pos)
+        ops.row_layernorm(self.tab_pos[0], rows=T_txt, ln2=self.ln_pos[:2], out2=pos[P:])
+        sc = cfg.pos_scaling
+        pq = ops.gemm(pos, self.pos_q.w16, bias=self.pos_q.b32, alpha=sc, alpha_cols=D)
+        pk = ops.gemm(pos, self.pos_k.w16, bias=self.pos_k.b32)
+        absb = self._abs_bias(pq, pk, T, T)
+        enc_biases = []
+        for l in range(cfg.enc_layers):
+            blocks = [(self.image_rp_bucket, ids, self.rel_img[l][0], 0, P), (self.token_rp_bucket, tok_ids, self.rel_tok[l][0], P, T)]
+            enc_biases.append(ops.build_attn_bias(absb, T, blocks))
+        tgt_pos = torch.empty((Td, D), dtype=_BF16, device=dev)
+        ops.row_layernorm(self.tab_seg_pos[0], rows=Td, ln2=self.ln_seg_pos[:2], out2=tgt_pos)
+        spq = ops.gemm(tgt_pos, self.self_pos_q.w16, bias=self.self_pos_q.b32, alpha=sc, alpha_cols=D)
+        spk = ops.gemm(tgt_pos, self.self_pos_k.w16, bias=self.self_pos_k.b32)
+        cpq = ops.gemm(tgt_pos, self.cross_pos_q.w16, bias=self.cross_pos_q.b32, alpha=sc, alpha_cols=D)
+        cpk = ops.gemm(pos, self.cross_pos_k.w16, bias=self.cross_pos_k.b32)
+        self_abs = self._abs_bias(spq, spk, Td, Td)
+        cross_abs = self._abs_bias(cpq, cpk, Td, T)
+        self_biases = [ops.build_attn_bias(self_abs, Td, [(self.seg_rp_bucket, seg_ids, self.rel_seg[l][0], 0, Td)])
+                       for l in range(cfg.dec_layers)]
+        return dict(enc_biases=enc_biases, self_biases=self_biases, cross_abs=cross_abs, pos=pos, pq=pq, pk=pk,
+                    tgt_pos=tgt_pos, spq=spq, spk=spk, cpq=cpq, cpk=cpk, ids=ids, tok_ids=tok_ids, seg_ids=seg_ids)
+
+    def _abs_bias_bwd(self, dabs, pq, pk, Lq: _Dense, Lk: _Dense, xq, xk, Tq, Tk, dxq, dxk):
+        """Adjoint of abs = pq pk^T (per head) and of the two position projections.  dabs fp32 [H,Tq,pad64(Tk)];
+        pq/pk bf16 [T*,D] (pq already carries pos_scaling); xq/xk the bf16 projection inputs.  Accumulates the input
+        gradients into the fp32 buffers dxq [Tq,D] / dxk [Tk,D] and the parameter gradients into the arena."""
+        cfg = self.cfg
+        D, H, dh = cfg.embed_dim, cfg.heads, cfg.head_dim
+        Tkp = dabs.shape[2]
+        d16 = torch.empty((H, Tq, Tkp), dtype=_BF16, device=self.device)
+        ops.transpose_cast(dabs.view(H * Tq, Tkp), out_c=d16.view(H * Tq, Tkp), want_t=False)  # fp32 -> bf16
+        pkt = ops.transpose_cast(pk)  # [D, pad8(Tk)]
+        dpq = torch.empty((Tq, D), dtype=_BF16, device=self.device)
+        dpk = torch.empty((Tk, D), dtype=_BF16, device=self.device)
+        # d(pos_q W^T + b)_h = pos_scaling * dabs_h pk_h   (one head-batched GEMM)
+        ops.gemm(d16, pkt, dpq, M=Tq, N=dh, K=Tk, batch=H, lda=Tkp, ldb=pkt.stride(0), ldc=D, a_batch_stride=Tq * Tkp,
+                 b_batch_stride=dh * pkt.stride(0), c_batch_stride=dh, alpha=cfg.pos_scaling, alpha_cols=dh)
+        # d(pk)_h = dabs_h^T pq_h: contraction over the query index, both operands read as they lie (MN-major)
+        for hh in range(H):
+            ops.gemm_ex(d16[hh], pq[:, hh * dh:], dpk[:, hh * dh:], M=Tk, N=dh, K=Tq, a_mn=True, b_mn=True, lda=Tkp,
+                        ldb=D, ldc=D, tag="pos_bias")
+        self._lin_bwd(dpq, xq, Lq, Tq, "pos_q", dx_out=dxq, dx_residual=dxq)
+        self._lin_bwd(dpk, xk, Lk, Tk, "pos_k", dx_out=dxk, dx_residual=dxk)
+
     def _lin_fwd(self, a, L: _Dense, tag, **kw):
         return ops.gemm(a, L.w16, bias=L.b32, tag=tag, **kw)
 
-    def _lin_bwd(self, dy, x, L: _Dense, M, tag, need_dx=True, dx_dtype=_BF16, dx_out=None, bias_done=False):
+    def _lin_bwd(self, dy, x, L: _Dense, M, tag, need_dx=True, dx_dtype=_BF16, dx_out=None, bias_done=False,
+                 dx_residual=None):
         """dy bf16 [M,N] (row stride may exceed N), x bf16 [M,K] saved input.  Writes dW / db into the arena
         gradient views, returns dX = dY W."""
         N, K = L.N, L.K
@@ -380,7 +483,7 @@ class SegOFATrainEngine:
         if not need_dx:
             return None
         return ops.gemm(dy, L.w16t, dx_out, M=M, N=K, K=N, lda=dy.stride(0), ldb=L.w16t.stride(0), out_dtype=dx_dtype,
-                        tag="dgrad_" + tag)
+                        residual=dx_residual, tag="dgrad_" + tag)
 
     # ------------------------------------------------------------------------------------
     # forward + backward of the image-free branch
@@ -423,8 +526,8 @@ class SegOFATrainEngine:
         f32 = torch.float32
         new = lambda shape, dt=_BF16: torch.empty(shape, dtype=dt, device=dev)  # noqa: E731
 
-        enc_biases, pos = self.inf._encoder_bias(h, w, T_txt, True)
-        self_biases, cross_abs = self.inf._decoder_bias(h, w, pos)
+        pb = self._position_bias(h, w, T_txt)
+        enc_biases, self_biases, cross_abs = pb["enc_biases"], pb["self_biases"], pb["cross_abs"]
 
         # ------------------------------ encoder forward ------------------------------
         bag = ops.embedding_bag_mean(aux_input["patch_images"].to(dev).contiguous(),
@@ -520,7 +623,7 @@ class SegOFATrainEngine:
         return dict(logits=logits, h=h, w=w, B=B, T_txt=T_txt, P=P, T=T, Td=Td, M=M, Md=Md, bag=bag, tok_idx=tok_idx,
                     x_emb=x_emb, xd_emb=xd_emb, enc_out=enc_out, kv_all=kv_all, feats=feats, dec_in_idx=dec_in_idx, bos=bos,
                     enc_saved=enc_saved, dec_saved=dec_saved, enc_biases=enc_biases, self_biases=self_biases,
-                    cross_abs=cross_abs)
+                    cross_abs=cross_abs, pb=pb)
 
     def backward_from(self, c, dlogits):
         """Adjoint of forward_train: dlogits bf16 [B,Td,pad8(C)] = dL/dlogits.  Parameter gradients are written
@@ -546,6 +649,12 @@ class SegOFATrainEngine:
         da = self._lin_bwd(dlogits.view(Md, Cp), feats, self.seg_proj, Md, "seg_proj")  # [Md, D] bf16
         dxs = None  # fp32 residual-stream gradient
         dkv_all = new((M, nL * 2 * D))
+        pb = c["pb"]
+        # gradients w.r.t. the additive position biases: per-layer scratch (consumed + cleared by sgf_attn_bias_bwd),
+        # and the layer-summed gradients of the abs terms
+        d_self_l = torch.zeros_like(self_biases[0])
+        d_self_abs = torch.zeros_like(self_biases[0])
+        d_cross_abs = torch.zeros_like(cross_abs)  # no rel term: all layers accumulate straight into it
         for li in reversed(range(nL)):
             L, S = self.dec_layers[li], dec_saved[li]
             nxt = S["ln_next"]
@@ -574,7 +683,7 @@ class SegOFATrainEngine:
                               Tk=T, q_strides=(D, Td * D), k_strides=kvs, v_strides=kvs, o_strides=(D, Td * D),
                               do_strides=(D, Td * D), dq_strides=(D, Td * D), dk_strides=kvs, dv_strides=kvs,
                               lse=S["lse_c"], delta=delta, bias=cross_abs, head_scale=Cx["c_attn"][0],
-                              d_head_scale=Cx["c_attn"][1], dq_scale=cfg.attn_scaling)
+                              d_head_scale=Cx["c_attn"][1], dq_scale=cfg.attn_scaling, dbias=d_cross_abs)
             da2 = self._lin_bwd(dqc, S["a2"], Cx["q"], Md, "cross_q")
             # self-attention block
             dy = new((Md, D))
@@ -589,7 +698,9 @@ class SegOFATrainEngine:
                               o_strides=(D, Td * D), do_strides=(D, Td * D), dq_strides=sd3, dk_strides=sd3,
                               dv_strides=sd3, lse=S["lse"], delta=delta, bias=self_biases[li],
                               head_scale=L["attn"]["c_attn"][0], d_head_scale=L["attn"]["c_attn"][1], causal=True,
-                              dq_scale=cfg.attn_scaling)
+                              dq_scale=cfg.attn_scaling, dbias=d_self_l)
+            ops.attn_bias_bwd(d_self_l, [self._csr("seg", self.seg_rp_bucket, pb["seg_ids"], 0, d_self_l.stride(1),
+                                                   self.rel_seg[li][1])], dabs_acc=d_self_abs)
             da = self._lin_bwd(dqkv, S["a"], L["attn"]["qkv"], Md, "qkv")
             dec_saved[li] = None
             self._sync_down(("dec", li + 1))
@@ -602,8 +713,20 @@ class SegOFATrainEngine:
                               dy2=da, dv_in=dxs, dx=d_enc_out, dx_accumulate=True, dg1=g_emb[2], db1=g_emb[3],
                               dg2=g_l0[2], db2=g_l0[3], seg=(P, Td, 1))
 
+        # decoder position bias: abs terms -> projections -> seg_pos_ln -> embed_seg_positions; the key side of the
+        # cross bias reaches the ENCODER's position embeddings (d_pos, continued after the encoder layers)
+        d_tgt_pos = torch.zeros((Td, D), dtype=f32, device=dev)
+        d_pos = torch.zeros((T, D), dtype=f32, device=dev)
+        self._abs_bias_bwd(d_self_abs, pb["spq"], pb["spk"], self.self_pos_q, self.self_pos_k, pb["tgt_pos"], pb["tgt_pos"],
+                           Td, Td, d_tgt_pos, d_tgt_pos)
+        self._abs_bias_bwd(d_cross_abs, pb["cpq"], pb["cpk"], self.cross_pos_q, self.cross_pos_k, pb["tgt_pos"], pb["pos"],
+                           Td, T, d_tgt_pos, d_pos)
+        ops.row_layernorm_bwd(rows=Td, D=D, x=self.tab_seg_pos[0], g2=self.ln_seg_pos[0], dy2=d_tgt_pos,
+                              dx=self.tab_seg_pos[1], dx_accumulate=True, dg2=self.ln_seg_pos[2], db2=self.ln_seg_pos[3])
         self._sync_down("cross_kv")
         # ------------------------------ encoder backward ------------------------------
+        d_enc_l = torch.zeros_like(enc_biases[0])
+        d_enc_abs = torch.zeros_like(enc_biases[0])
         da = d_enc_out  # fp32 gradient w.r.t. encoder_out (= LN_enc_out(x))
         dxs = None
         for li in reversed(range(len(self.enc_layers))):
@@ -630,7 +753,11 @@ class SegOFATrainEngine:
                               dqkv[:, 2 * D:], B=B, H=H, Tq=T, Tk=T, q_strides=s3, k_strides=s3, v_strides=s3,
                               o_strides=(D, T * D), do_strides=(D, T * D), dq_strides=s3, dk_strides=s3, dv_strides=s3,
                               lse=S["lse"], delta=delta, bias=enc_biases[li], head_scale=L["attn"]["c_attn"][0],
-                              d_head_scale=L["attn"]["c_attn"][1], dq_scale=cfg.attn_scaling)
+                              d_head_scale=L["attn"]["c_attn"][1], dq_scale=cfg.attn_scaling, dbias=d_enc_l)
+            rs = d_enc_l.stride(1)
+            ops.attn_bias_bwd(d_enc_l, [self._csr("img", self.image_rp_bucket, pb["ids"], 0, rs, self.rel_img[li][1]),
+                                        self._csr("tok", self.token_rp_bucket, pb["tok_ids"], P, rs, self.rel_tok[li][1])],
+                              dabs_acc=d_enc_abs)
             da = self._lin_bwd(dqkv, S["a"], L["attn"]["qkv"], M, "qkv")
             enc_saved[li] = None
             self._sync_down(("enc", li + 1))
@@ -644,6 +771,12 @@ class SegOFATrainEngine:
                               g1=self.ln_emb[0], v=x_emb, g2=g_l0[0], dy2=da, dv_in=dxs, dg1=self.ln_emb[2],
                               db1=self.ln_emb[3], dg2=g_l0[2], db2=g_l0[3], d_pre_add=gt[0] if gt is not None else None,
                               seg=(T_txt, T, P))
+        # encoder position bias: abs term -> pos_q/pos_k -> pos_ln / image_pos_ln -> the two position tables
+        self._abs_bias_bwd(d_enc_abs, pb["pq"], pb["pk"], self.pos_q, self.pos_k, pb["pos"], pb["pos"], T, T, d_pos, d_pos)
+        ops.row_layernorm_bwd(rows=P, D=D, x=self.tab_img_pos[0], gather_idx=pb["ids"], g2=self.ln_img_pos[0], dy2=d_pos,
+                              dx=self.tab_img_pos[1], dx_accumulate=True, dg2=self.ln_img_pos[2], db2=self.ln_img_pos[3])
+        ops.row_layernorm_bwd(rows=T_txt, D=D, x=self.tab_pos[0], g2=self.ln_pos[0], dy2=d_pos[P:],
+                              dx=self.tab_pos[1], dx_accumulate=True, dg2=self.ln_pos[2], db2=self.ln_pos[3])
         self._sync_down(None)
 
     # ------------------------------------------------------------------------------------

@@ -313,7 +313,8 @@ int sgf_transpose_cast(const void* in, int32_t in_dtype, int64_t ld_in, int32_t 
  *         P = exp2(S + bias - lse), dS = P (head_scale dP - delta) -> bf16 smem, dQ += dS K (TMEM)
  *   dKdV: CTA per (128 keys, head, batch): S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q
  * dq is multiplied by dq_scale (the q pre-scaling of the QKV epilogue).  The gradient w.r.t. the
- * additive position bias is NOT produced.  delta: fp32 scratch [B,H,Tq]. */
+ * additive position bias is accumulated into `dbias` when given (vector fp32 atomics from the dQ kernel).
+ * delta: fp32 scratch [B,H,Tq]. */
 typedef struct {
   const void* q; int64_t q_row_stride; int64_t q_batch_stride;
   const void* k; int64_t k_row_stride; int64_t k_batch_stride;
@@ -329,8 +330,24 @@ typedef struct {
   const float* lse; float* delta;
   float dq_scale;
   int32_t B, H, Tq, Tk, causal;
+  float* dbias; /* optional fp32 [H,Tq,bias_row_stride] (bias strides; row stride a multiple of 64): += dS summed over
+                   the batch, i.e. the gradient w.r.t. the additive position bias */
 } sgf_attention_bwd_args;
 int sgf_attention_bwd_bf16(const sgf_attention_bwd_args* args, void* stream);
+
+/* Adjoint of sgf_build_attn_bias for one layer.  dbias[h,i,j] is the batch-summed dS of that layer's attention
+ * (written by sgf_attention_bwd_bf16).  For every block b the table gradient is a gather over a static CSR list of
+ * the block's positions grouped by bucket (built once per shape by the caller from the same bucket/ids tensors the
+ * forward uses): dtable_b[r,h] += sum_{t in [offsets_b[r], offsets_b[r+1])} dbias[h].flat[order_b[t]], with
+ * order_b[t] = i*row_stride + j -- one warp per (r,h), no atomics, deterministic.  Then dabs_acc += dbias (the
+ * gradient of the layer-independent abs term; optional) and dbias is cleared for the next layer.
+ * Adjoint of encoder_module.py:313-331,790-809 / decoder_module.py:327-333,601-627 (identity-interpolation case). */
+typedef struct {
+  float* dbias; float* dabs_acc; int64_t head_stride; int64_t row_stride;
+  int32_t H, Tq;
+  int32_t num_blocks; const int32_t* order[2]; const int32_t* offsets[2]; float* dtable[2]; int32_t num_rel[2];
+} sgf_bias_bwd_args;
+int sgf_attn_bias_bwd(const sgf_bias_bwd_args* args, void* stream);
 
 /* Multi-tensor-free fused Adam(W) step over one flat fp32 master buffer (cf/optim/adam.py, fp32
  * master weights of cf/optim/fp16_optimizer.py:108-222): p -= lr*(m_hat/(sqrt(v_hat)+eps) + wd*p)

@@ -85,8 +85,9 @@ def test_imfree_train_step_gradients_vs_oracle(cuda_device):
     assert glob <= gg["ref_bf16_grad_rel_l2"], glob
     assert worst[0] < 0.25, worst
     # every tensor the reference gives a gradient to is either produced or on the documented bias-path list
-    missing = [k for k in gg["grad_norms"] if k not in ours and not eng._is_bias_path(k)]
+    missing = [k for k in gg["grad_norms"] if k not in ours]
     assert not missing, missing
+    assert len(ours) == len(gg["grad_norms"]) == 380  # exactly the tensors the reference gives a gradient to
 
 
 def test_train_loop_decreases_loss_and_keeps_views(cuda_device):
@@ -97,8 +98,7 @@ def test_train_loop_decreases_loss_and_keeps_views(cuda_device):
         gn = eng.optimizer_step(lr=2e-4, weight_decay=0.01, clip_norm=1.0)
         if first is None:
             first = loss.item()
-            assert abs(gn.item() - sum(v ** 2 for k, v in gg["grad_norms"].items() if not eng._is_bias_path(k)) ** 0.5) \
-                < 0.08 * gn.item()
+            assert abs(gn.item() - sum(v ** 2 for v in gg["grad_norms"].values()) ** 0.5) < 0.08 * gn.item()
     last, _ = eng.forward_backward(aux, tgt, backward=False)
     assert last.item() < first - 0.05, (first, last.item())
     # the nn.Parameters are views of the flat master buffer: state_dict sees the updated weights
