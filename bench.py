@@ -288,7 +288,9 @@ def bench_train(args, rank, world, local_rank, config):
                                   "flops_per_image": FLOPS_PER_IMG[args.config]}},
             "kernel_families": {k: {"launches": v["launches"], "ms": round(v["ms"], 4)} for k, v in fam.items()},
             "cuda_graph": sess.graph is not None,
-            "train": {"dropout": 0.0, "note": "dropout/DropPath off; position-bias parameters frozen (DESIGN.md)"},
+            "train": {"dropout": trainer.engine.drop_p if trainer.engine.stochastic else 0.0,
+                      "drop_path_max": max(trainer.engine.enc_dpr) if trainer.engine.stochastic else 0.0,
+                      "note": "shipped recipe noise (dropout 0.1, DropPath 0..0.1) on; all 380 gradient tensors; Adam + clip"},
         }
         if not args.no_cpu_baseline:
             cb, _ = cpu_reference_train_run(args.config, 1, 0)

@@ -51,6 +51,8 @@ class RowLnArgs(C.Structure):
         ("seg_len", _i32), ("seg_stride", _i32), ("seg_off", _i32),
         ("clear_rowstats", _vp),
         ("x_act", _i32),
+        ("drop_p", _f32), ("droppath_p", _f32), ("drop_seed", C.c_uint32), ("drop_site", C.c_uint32),
+        ("rows_per_sample", _i32), ("drop_step", _vp),
     ]
 
 
@@ -122,6 +124,8 @@ class RowLnBwdArgs(C.Structure):
         ("rows", _i32), ("D", _i32),
         ("seg_len", _i32), ("seg_stride", _i32), ("seg_off", _i32),
         ("dx_colsum", _vp),
+        ("drop_p", _f32), ("droppath_p", _f32), ("drop_seed", C.c_uint32), ("drop_site", C.c_uint32),
+        ("rows_per_sample", _i32), ("drop_step", _vp),
     ]
 
 

@@ -306,6 +306,58 @@ SGF_DEVICE float gelu_erf(float x) {
   const float erf_abs = fmaf(-p * t, e, 1.0f);  // erf(|x|/sqrt2)
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
+// ----------------------------------------------------------------------------------------
+// counter-based dropout / DropPath masks: a pure function of (seed, step, site, row, column), so the forward and
+// the adjoint kernels regenerate identical masks and a CUDA-graph replay draws new ones (step lives on the device)
+// ----------------------------------------------------------------------------------------
+SGF_DEVICE uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+struct DropCtx {
+  uint64_t key;
+  uint32_t thresh16;   // element dropped when its 16 random bits < thresh16
+  uint32_t thresh24;   // sample's path dropped when its 24 random bits < thresh24
+  float inv_keep, inv_keep_path;
+  int rows_per_sample;
+  bool on;
+};
+SGF_DEVICE DropCtx make_drop_ctx(float drop_p, float droppath_p, uint32_t seed, uint32_t site, const int32_t* step_dev,
+                                 int rows_per_sample) {
+  DropCtx c;
+  c.on = drop_p > 0.f || droppath_p > 0.f;
+  const uint64_t step = step_dev ? static_cast<uint64_t>(step_dev[0]) : 0ull;
+  c.key = mix64((static_cast<uint64_t>(seed) << 32) ^ (step * 0x632BE59BD9B4E019ull) ^ (static_cast<uint64_t>(site) << 8));
+  c.thresh16 = static_cast<uint32_t>(drop_p * 65536.0f + 0.5f);
+  c.thresh24 = static_cast<uint32_t>(droppath_p * 16777216.0f + 0.5f);
+  c.inv_keep = drop_p > 0.f ? 1.0f / (1.0f - static_cast<float>(c.thresh16) * (1.0f / 65536.0f)) : 1.0f;
+  c.inv_keep_path = droppath_p > 0.f ? 1.0f / (1.0f - static_cast<float>(c.thresh24) * (1.0f / 16777216.0f)) : 1.0f;
+  c.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
+  return c;
+}
+// multipliers of the 8 elements of chunk `chunk` of (output) row `row`: element keep / (1-p) times path keep / (1-dp)
+SGF_DEVICE void drop_mult8(const DropCtx& c, int64_t row, int chunk, float (&m)[8]) {
+  float path = 1.0f;
+  if (c.thresh24) {
+    const uint64_t b = static_cast<uint64_t>(row / c.rows_per_sample);
+    path = (static_cast<uint32_t>(mix64(c.key ^ 0xD1B54A32D192ED03ull ^ (b << 1)) >> 40) >= c.thresh24) ? c.inv_keep_path : 0.f;
+  }
+  if (c.thresh16) {
+    const uint64_t base = c.key ^ (static_cast<uint64_t>(row) << 22) ^ (static_cast<uint64_t>(chunk) << 1);
+    const uint64_t a = mix64(base), b2 = mix64(base | 1ull);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      m[j] = (static_cast<uint32_t>(a >> (16 * j)) & 0xFFFFu) >= c.thresh16 ? c.inv_keep * path : 0.f;
+      m[4 + j] = (static_cast<uint32_t>(b2 >> (16 * j)) & 0xFFFFu) >= c.thresh16 ? c.inv_keep * path : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = path;
+  }
+}
+
 // vector fp32 reduction into global memory (no return value): one 16-byte L2 atomic
 SGF_DEVICE void red_add_f32x4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

@@ -22,6 +22,7 @@ struct RowLnParams {
   int seg_len, seg_stride, seg_off;
   float* clear_rowstats;
   int x_act;
+  float drop_p, droppath_p; uint32_t drop_seed, drop_site; int rows_per_sample; const int32_t* drop_step;
 };
 
 SGF_DEVICE void load8(const void* base, int dtype, int64_t elem_off, float (&v)[8]) {
@@ -155,7 +156,8 @@ __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const Ro
     rstd1 = rsqrtf(warp_sum(q) * invD + 1e-5f);
   }
   // ---- v = LN1(t) + residual ; out1 ; stash for LN2 ----
-  const bool two_stage = p.out2 && (p.g1 || p.residual || p.pre_add || p.out1 || p.x_act);
+  const DropCtx drop = make_drop_ctx(p.drop_p, p.droppath_p, p.drop_seed, p.drop_site, p.drop_step, p.rows_per_sample);
+  const bool two_stage = p.out2 && (p.g1 || p.residual || p.pre_add || p.out1 || p.x_act || drop.on);
   float s2 = 0.f;
   if (two_stage || p.out1) {
     for (int c = lane; c < nchunk; c += 32) {
@@ -177,6 +179,12 @@ __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const Ro
         load8(p.b1, SGF_F32, c * 8, b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean1) * rstd1 * g[j] + b[j];
+      }
+      if (drop.on) {
+        float m[8];
+        drop_mult8(drop, dst_row, c, m);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= m[j];
       }
       if (p.residual) {
         float r[8];
@@ -477,6 +485,7 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
   SGF_REQUIRE(a != nullptr, "row_layernorm: null args");
   if (a->x_act == SGF_ACT_GELU && a->x_dtype == SGF_BF16 && !a->gather_idx && !a->pre_add && !a->g1 && !a->residual &&
       !a->out1 && a->out2 && a->g2 && a->b2 && !a->zero_row && a->seg_len == 0 && !a->clear_rowstats && a->D >= 1024 &&
+      a->drop_p == 0.f && a->droppath_p == 0.f &&
       a->D <= 4096 && a->D % 8 == 0 && a->rows > 0 && a->ldx % 8 == 0 && a->ld2 % 8 == 0 &&
       reinterpret_cast<uintptr_t>(a->x) % 16 == 0 && reinterpret_cast<uintptr_t>(a->out2) % 16 == 0)
     return launch_gelu_ln_fwd_wide(a->x, a->ldx, a->g2, a->b2, a->out2, a->ld2, a->rows, a->D,
@@ -491,12 +500,14 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
               "row_layernorm: row strides must be multiples of 8 elements");
   RowLnParams p{a->x, a->ldx, a->x_dtype, a->gather_idx, a->pre_add, a->g1, a->b1, a->residual, a->ldr, a->r_dtype,
                 a->out1, a->ld1, a->out1_dtype, a->g2, a->b2, a->out2, a->ld2, a->zero_row, a->rows, a->D,
-                a->seg_len, a->seg_stride, a->seg_off, a->clear_rowstats, a->x_act};
+                a->seg_len, a->seg_stride, a->seg_off, a->clear_rowstats, a->x_act, a->drop_p, a->droppath_p,
+                a->drop_seed, a->drop_site, a->rows_per_sample, a->drop_step};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int xs = a->x_dtype == SGF_F32 ? 4 : 2, rs = a->r_dtype == SGF_F32 ? 4 : 2;
   const int x_row_bytes = a->D * xs;
   const int r_row_bytes = a->residual ? a->D * rs : 0;
-  const bool two_stage = a->out2 && (a->g1 || a->residual || a->pre_add || a->out1 || a->x_act);
+  const bool two_stage = a->out2 && (a->g1 || a->residual || a->pre_add || a->out1 || a->x_act || a->drop_p > 0.f ||
+                                     a->droppath_p > 0.f);
   const int s_row_bytes = two_stage ? a->D * 4 : 0;
   int kLnRows = kLnMaxRows;
   while (kLnRows > 1 && kLnRows * (x_row_bytes + r_row_bytes + s_row_bytes) > 96 * 1024) kLnRows >>= 1;

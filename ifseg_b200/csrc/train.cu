@@ -71,6 +71,7 @@ struct RowLnBwdParams {
   int rows, D;
   int seg_len, seg_stride, seg_off;
   float* dx_colsum;
+  float drop_p, droppath_p; uint32_t drop_seed, drop_site; int rows_per_sample; const int32_t* drop_step;
 };
 
 // Parameter-gradient partials are kept in PER-WARP private shared-memory accumulators (lane l of every warp
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdPa
   const int nchunk = D >> 3;
   const int ngroups = (p.rows + kRows - 1) / kRows;
   uint32_t phase = 0;
+  const DropCtx drop = make_drop_ctx(p.drop_p, p.droppath_p, p.drop_seed, p.drop_site, p.drop_step, p.rows_per_sample);
   auto acc8 = [](float* a, int c, const float (&v)[8]) {
     float4* q = reinterpret_cast<float4*>(a + c * 8);
     float4 u0 = q[0], u1 = q[1];
@@ -264,6 +266,12 @@ __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdPa
           }
         }
         if (p.d_res) st8g(p.d_res, SGF_F32, dst_row * p.ldres + c * 8, dv);
+        if (drop.on) {  // du = dv * (dropout / DropPath multiplier of the forward)
+          float m[8];
+          drop_mult8(drop, dst_row, c, m);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dv[j] *= m[j];
+        }
         if (!p.g1) {
           finalize(c, dv);
         } else {
@@ -721,7 +729,8 @@ extern "C" int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* a, void* stream) 
   // wide FFN rows: register-resident specialisation
   if (a->x_act == SGF_ACT_GELU && !a->g1 && !a->v && !a->dv_in && !a->d_res && !a->gather_idx && !a->pre_add && a->g2 &&
       a->dy2 && a->dy2_dtype == SGF_BF16 && a->x_dtype == SGF_BF16 && a->dx && a->dx_dtype == SGF_BF16 &&
-      !a->dx_accumulate && a->seg_len == 0 && a->D >= 1024 && a->D <= 4096 && !a->dg1 && !a->db1 && !a->d_pre_add) {
+      !a->dx_accumulate && a->seg_len == 0 && a->D >= 1024 && a->D <= 4096 && !a->dg1 && !a->db1 && !a->d_pre_add &&
+      a->drop_p == 0.f && a->droppath_p == 0.f) {
     const int nc = (a->D + 1023) / 1024;
     int grid = a->rows < 148 * 4 ? a->rows : 148 * 4;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -764,7 +773,8 @@ extern "C" int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* a, void* stream) 
   RowLnBwdParams p{a->x, a->ldx, a->x_dtype, a->gather_idx, a->x_act, a->pre_add, a->g1, a->v, a->ldv, a->v_dtype,
                    a->g2, a->dy2, a->ldy2, a->dy2_dtype, a->dv_in, a->lddv, a->d_res, a->ldres, a->dx, a->lddx,
                    a->dx_dtype, a->dx_accumulate, a->dg1, a->db1, a->dg2, a->db2, a->d_pre_add, a->rows, a->D,
-                   a->seg_len, a->seg_stride, a->seg_off, a->dx_colsum};
+                   a->seg_len, a->seg_stride, a->seg_off, a->dx_colsum, a->drop_p, a->droppath_p, a->drop_seed,
+                   a->drop_site, a->rows_per_sample, a->drop_step};
   static bool configured = false;
   if (!configured) {
     SGF_CHECK_CUDA(cudaFuncSetAttribute(row_layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -196,9 +196,17 @@ def maxpool3x3s2(x):
     return y
 
 
+def _drop_fields(drop):
+    """drop = None | dict(p, path_p, seed, site, rows_per_sample, step (int32 device tensor or None))."""
+    if not drop:
+        return 0.0, 0.0, 0, 0, 0, None
+    return (float(drop.get("p", 0.0)), float(drop.get("path_p", 0.0)), int(drop.get("seed", 0)) & 0xFFFFFFFF,
+            int(drop.get("site", 0)), int(drop.get("rows_per_sample", 0)), _p(drop.get("step")))
+
+
 def row_layernorm(x, *, rows=None, D=None, ldx=None, gather_idx=None, pre_add=None, ln1=None, residual=None,
                   ldr=None, out1=None, ld1=None, ln2=None, out2=None, ld2=None, zero_row=None, seg=None,
-                  clear_rowstats=None, x_act=ACT_NONE):
+                  clear_rowstats=None, x_act=ACT_NONE, drop=None):
     """See sgf_row_layernorm in include/segofa_b200.h.  ln1/ln2 = (gamma, beta) fp32 tensors."""
     lib = _lib.load()
     _req(x, None, "x")
@@ -214,7 +222,7 @@ def row_layernorm(x, *, rows=None, D=None, ldx=None, gather_idx=None, pre_add=No
         _DT[out1.dtype] if out1 is not None else SGF_BF16,
         _p(ln2[0]) if ln2 else None, _p(ln2[1]) if ln2 else None,
         _p(out2), (out2.stride(-2) if ld2 is None else ld2) if out2 is not None else 0,
-        _p(zero_row), rows, D, seg_len, seg_stride, seg_off, _p(clear_rowstats), int(x_act))
+        _p(zero_row), rows, D, seg_len, seg_stride, seg_off, _p(clear_rowstats), int(x_act), *_drop_fields(drop))
     nb = rows * D * (x.element_size() + (residual.element_size() if residual is not None else 0)
                      + (out1.element_size() if out1 is not None else 0) + (2 if out2 is not None else 0))
     with _timed("row_layernorm" + (f":D{D}{'g1' if ln1 else ''}" if _TIMER is not None and _TIMER.fine else ""), nbytes=float(nb)):
@@ -338,7 +346,7 @@ def upsample_ce_loss_bwd(logits, target, lse, count, hp, wp, dlogits, label_smoo
 
 def row_layernorm_bwd(*, rows, D, x=None, ldx=None, gather_idx=None, x_act=ACT_NONE, pre_add=None, g1=None, v=None,
                       g2=None, dy2=None, dv_in=None, d_res=None, dx=None, dx_accumulate=False, dg1=None, db1=None,
-                      dg2=None, db2=None, d_pre_add=None, seg=None, dx_colsum=None):
+                      dg2=None, db2=None, d_pre_add=None, seg=None, dx_colsum=None, drop=None):
     """Adjoint of row_layernorm (see sgf_row_layernorm_bwd in include/segofa_b200.h)."""
     lib = _lib.load()
     seg_len, seg_stride, seg_off = seg if seg is not None else (0, 0, 0)
@@ -353,7 +361,7 @@ def row_layernorm_bwd(*, rows, D, x=None, ldx=None, gather_idx=None, x_act=ACT_N
         _p(x), ld(x) if ldx is None else ldx, dt(x), _p(gather_idx), int(x_act), _p(pre_add), _p(g1),
         _p(v), ld(v), dt(v), _p(g2), _p(dy2), ld(dy2), dt(dy2), _p(dv_in), ld(dv_in), _p(d_res), ld(d_res),
         _p(dx), ld(dx), dt(dx), 1 if dx_accumulate else 0, _p(dg1), _p(db1), _p(dg2), _p(db2), _p(d_pre_add),
-        rows, D, seg_len, seg_stride, seg_off, _p(dx_colsum))
+        rows, D, seg_len, seg_stride, seg_off, _p(dx_colsum), *_drop_fields(drop))
     nb = rows * D * sum(t.element_size() for t in (x, v, dy2, dv_in, d_res, dx) if t is not None)
     with _timed("row_layernorm_bwd" + (f":D{D}{'g1' if g1 is not None else ''}" if _TIMER is not None and _TIMER.fine else ""), nbytes=float(nb)):
         _lib.check(lib.sgf_row_layernorm_bwd(C.byref(args), _stream()), "sgf_row_layernorm_bwd")

@@ -124,7 +124,7 @@ class _Dense:
 
 
 class SegOFATrainEngine:
-    def __init__(self, model):
+    def __init__(self, model, stochastic=True, seed=1):
         p0 = next(model.parameters())
         if not p0.is_cuda:
             raise RuntimeError("segofa_b200: training runs on a B200 only (no CPU fallback) -- call model.cuda() first")
@@ -142,6 +142,21 @@ class SegOFATrainEngine:
         self.accumulate = False
         self.grad_sync = None  # callable(lo, hi): gradient range [lo,hi) of arena.grad32 is final (DDP bucket)
         self.step_count = 0
+        # training-mode noise of the shipped recipe (--dropout, --encoder/decoder-drop-path-rate; attention and activation
+        # dropout are 0 there): counter-based masks regenerated by the adjoint kernels.  stochastic=False gives the
+        # deterministic (eval-mode) numerics the gradient-parity tests use.
+        a = getattr(model, "args", None)
+        self.stochastic = stochastic
+        self.seed = seed
+        self.drop_p = float(getattr(a, "dropout", 0.0) or 0.0)
+        if float(getattr(a, "attention_dropout", 0.0) or 0.0) > 0 or float(getattr(a, "activation_dropout", 0.0) or 0.0) > 0:
+            raise NotImplementedError("attention / activation dropout > 0 is not implemented (0 in every shipped recipe)")
+        ne, nd = self.cfg.enc_layers, self.cfg.dec_layers
+        e_rate = float(getattr(a, "encoder_drop_path_rate", 0.0) or 0.0)
+        d_rate = float(getattr(a, "decoder_drop_path_rate", 0.0) or 0.0)
+        self.enc_dpr = [e_rate * i / max(ne - 1, 1) for i in range(ne)]  # torch.linspace(0, rate, layers)
+        self.dec_dpr = [d_rate * i / max(nd - 1, 1) for i in range(nd)]
+        self._fwd_dev = torch.zeros(1, dtype=torch.int32, device=self.device)  # forward counter = mask "step"
         self._fresh = False
         self._hook = None
         self._step_dev = None
@@ -455,6 +470,12 @@ class SegOFATrainEngine:
         self._lin_bwd(dpq, xq, Lq, Tq, "pos_q", dx_out=dxq, dx_residual=dxq)
         self._lin_bwd(dpk, xk, Lk, Tk, "pos_k", dx_out=dxk, dx_residual=dxk)
 
+    def _drop(self, site, rows_per_sample, path_p=0.0):
+        if not self.stochastic or (self.drop_p <= 0.0 and path_p <= 0.0):
+            return None
+        return dict(p=self.drop_p, path_p=path_p, seed=self.seed, site=site, rows_per_sample=rows_per_sample,
+                    step=self._fwd_dev)
+
     def _lin_fwd(self, a, L: _Dense, tag, **kw):
         return ops.gemm(a, L.w16, bias=L.b32, tag=tag, **kw)
 
@@ -513,6 +534,7 @@ class SegOFATrainEngine:
         if not self._fresh:
             self.refresh_weights()  # an external optimizer may have updated the fp32 masters in place
         self._fresh = False
+        self._fwd_dev += 1
         cfg, dev = self.cfg, self.device
         D, H, Fd, C = cfg.embed_dim, cfg.heads, cfg.ffn_dim, cfg.num_seg
         src_tokens = aux_input["src_tokens"].to(dev)
@@ -537,9 +559,10 @@ class SegOFATrainEngine:
         a = new((M, D))
         L0 = self.enc_layers[0]
         ops.row_layernorm(bag, pre_add=self.type_img, ln1=self.ln_patch[:2], out1=x, ln2=L0["ln_self"][:2], out2=a,
-                          seg=(P, T, 0))
+                          seg=(P, T, 0), drop=self._drop(1, T))
         ops.row_layernorm(self.embed_tokens, rows=B * T_txt, D=D, gather_idx=tok_idx, pre_add=self.type_txt,
-                          ln1=self.ln_emb[:2], out1=x, ln2=L0["ln_self"][:2], out2=a, seg=(T_txt, T, P))
+                          ln1=self.ln_emb[:2], out1=x, ln2=L0["ln_self"][:2], out2=a, seg=(T_txt, T, P),
+                          drop=self._drop(2, T))
         x_emb = x
         enc_saved = []
         s3 = (3 * D, T * 3 * D)
@@ -552,16 +575,19 @@ class SegOFATrainEngine:
                           head_scale=L["attn"]["c_attn"][0], lse=S["lse"])
             S["y"] = self._lin_fwd(S["o"], L["attn"]["out"], "out_proj", out_dtype=f32)
             S["x1"], S["a2"] = new((M, D), f32), new((M, D))
-            ops.row_layernorm(S["y"], ln1=L["ln_attn"][:2], residual=x, out1=S["x1"], ln2=L["ln_final"][:2], out2=S["a2"])
+            S["dA"], S["dB"] = self._drop(10 + 2 * li, T, self.enc_dpr[li]), self._drop(11 + 2 * li, T, self.enc_dpr[li])
+            ops.row_layernorm(S["y"], ln1=L["ln_attn"][:2], residual=x, out1=S["x1"], ln2=L["ln_final"][:2], out2=S["a2"],
+                              drop=S["dA"])
             S["h"] = self._lin_fwd(S["a2"], L["fc1"], "fc1")
             S["z"] = new((M, Fd))
             ops.row_layernorm(S["h"], ln2=L["ln_ffn"][:2], out2=S["z"], x_act=ops.ACT_GELU)
             S["x2"] = new((M, D), f32)
-            ops.gemm(S["z"], L["fc2"].w16, S["x2"], bias=L["fc2"].b32, residual=S["x1"], tag="fc2")
+            y2 = self._lin_fwd(S["z"], L["fc2"], "fc2", out_dtype=f32)
             nxt = self.enc_layers[li + 1]["ln_self"] if li + 1 < len(self.enc_layers) else self.ln_enc_out
             S["ln_next"] = nxt
             a = new((M, D))
-            ops.row_layernorm(S["x2"], ln2=nxt[:2], out2=a)
+            # x2 = x1 + drop_path(dropout(fc2(...))) and the next block's pre-LayerNorm in one row kernel
+            ops.row_layernorm(y2, residual=S["x1"], out1=S["x2"], ln2=nxt[:2], out2=a, drop=S["dB"])
             x = S["x2"]
             enc_saved.append(S)
         enc_out = a  # [B*T, D] bf16
@@ -573,11 +599,11 @@ class SegOFATrainEngine:
         ad = new((Md, D))
         D0 = self.dec_layers[0]
         ops.row_layernorm(self.embed_tokens, rows=B, D=D, gather_idx=bos, ln1=self.dec_ln_emb[:2], out1=xd,
-                          ln2=D0["ln_self"][:2], out2=ad, seg=(1, Td, 0))
+                          ln2=D0["ln_self"][:2], out2=ad, seg=(1, Td, 0), drop=self._drop(100, Td))
         dec_in_idx = self.inf._cached(("dec_in_idx", B, T, P), lambda: (
             torch.arange(B).unsqueeze(1) * T + torch.arange(P).unsqueeze(0)).reshape(-1))
         ops.row_layernorm(enc_out, rows=B * P, gather_idx=dec_in_idx, ln1=self.dec_ln_emb[:2], out1=xd,
-                          ln2=D0["ln_self"][:2], out2=ad, seg=(P, Td, 1))
+                          ln2=D0["ln_self"][:2], out2=ad, seg=(P, Td, 1), drop=self._drop(101, Td))
         xd_emb = xd
         kv_all = self._lin_fwd(enc_out, self.cross_kv, "cross_kv")  # [M, nL*2D]
         kvs = (nL * 2 * D, T * nL * 2 * D)
@@ -593,8 +619,9 @@ class SegOFATrainEngine:
                           head_scale=L["attn"]["c_attn"][0], causal=True, lse=S["lse"])
             S["y"] = self._lin_fwd(S["o"], L["attn"]["out"], "out_proj", out_dtype=f32)
             S["x1"], S["a2"] = new((Md, D), f32), new((Md, D))
+            S["dS"], S["dC"], S["dB"] = (self._drop(110 + 3 * li + k, Td, self.dec_dpr[li]) for k in range(3))
             ops.row_layernorm(S["y"], ln1=L["ln_self_attn"][:2], residual=x, out1=S["x1"], ln2=L["ln_enc_attn"][:2],
-                              out2=S["a2"])
+                              out2=S["a2"], drop=S["dS"])
             Cx = L["cross"]
             S["qc"] = self._lin_fwd(S["a2"], Cx["q"], "cross_q", alpha=cfg.attn_scaling, alpha_cols=D)
             S["oc"], S["lse_c"] = new((Md, D)), new((B, H, Td), f32)
@@ -605,16 +632,16 @@ class SegOFATrainEngine:
             S["yc"] = self._lin_fwd(S["oc"], Cx["out"], "out_proj", out_dtype=f32)
             S["x2"], S["a3"] = new((Md, D), f32), new((Md, D))
             ops.row_layernorm(S["yc"], ln1=L["ln_cross_attn"][:2], residual=S["x1"], out1=S["x2"], ln2=L["ln_final"][:2],
-                              out2=S["a3"])
+                              out2=S["a3"], drop=S["dC"])
             S["h"] = self._lin_fwd(S["a3"], L["fc1"], "fc1")
             S["z"] = new((Md, Fd))
             ops.row_layernorm(S["h"], ln2=L["ln_ffn"][:2], out2=S["z"], x_act=ops.ACT_GELU)
             S["x3"] = new((Md, D), f32)
-            ops.gemm(S["z"], L["fc2"].w16, S["x3"], bias=L["fc2"].b32, residual=S["x2"], tag="fc2")
+            y2 = self._lin_fwd(S["z"], L["fc2"], "fc2", out_dtype=f32)
             nxt = self.dec_layers[li + 1]["ln_self"] if li + 1 < nL else self.ln_dec_out
             S["ln_next"] = nxt
             a = new((Md, D))
-            ops.row_layernorm(S["x3"], ln2=nxt[:2], out2=a)
+            ops.row_layernorm(y2, residual=S["x2"], out1=S["x3"], ln2=nxt[:2], out2=a, drop=S["dB"])
             x = S["x3"]
             dec_saved.append(S)
         feats = a
@@ -661,7 +688,7 @@ class SegOFATrainEngine:
             dx_new = dxs if dxs is not None else new((Md, D), f32)
             dy = new((Md, D))
             ops.row_layernorm_bwd(rows=Md, D=D, v=S["x3"], g2=nxt[0], dy2=da, dv_in=dxs, d_res=dx_new, dx=dy,
-                                  dg2=nxt[2], db2=nxt[3], dx_colsum=L["fc2"].gb)
+                                  dg2=nxt[2], db2=nxt[3], dx_colsum=L["fc2"].gb, drop=S["dB"])
             dxs = dx_new
             dz = self._lin_bwd(dy, S["z"], L["fc2"], Md, "fc2", bias_done=True)
             dh = new((Md, Fd))
@@ -673,7 +700,7 @@ class SegOFATrainEngine:
             ops.row_layernorm_bwd(rows=Md, D=D, x=S["yc"], g1=L["ln_cross_attn"][0], v=S["x2"], g2=L["ln_final"][0],
                                   dy2=da3, dv_in=dxs, d_res=dxs, dx=dyc, dg1=L["ln_cross_attn"][2],
                                   db1=L["ln_cross_attn"][3], dg2=L["ln_final"][2], db2=L["ln_final"][3],
-                                  dx_colsum=L["cross"]["out"].gb)
+                                  dx_colsum=L["cross"]["out"].gb, drop=S["dC"])
             Cx = L["cross"]
             doc = self._lin_bwd(dyc, S["oc"], Cx["out"], Md, "out_proj", bias_done=True)
             dqc = new((Md, D))
@@ -690,7 +717,7 @@ class SegOFATrainEngine:
             ops.row_layernorm_bwd(rows=Md, D=D, x=S["y"], g1=L["ln_self_attn"][0], v=S["x1"], g2=L["ln_enc_attn"][0],
                                   dy2=da2, dv_in=dxs, d_res=dxs, dx=dy, dg1=L["ln_self_attn"][2],
                                   db1=L["ln_self_attn"][3], dg2=L["ln_enc_attn"][2], db2=L["ln_enc_attn"][3],
-                                  dx_colsum=L["attn"]["out"].gb)
+                                  dx_colsum=L["attn"]["out"].gb, drop=S["dS"])
             do = self._lin_bwd(dy, S["o"], L["attn"]["out"], Md, "out_proj", bias_done=True)
             dqkv = new((Md, 3 * D))
             ops.attention_bwd(S["qkv"], S["qkv"][:, D:], S["qkv"][:, 2 * D:], S["o"], do, dqkv, dqkv[:, D:],
@@ -708,10 +735,11 @@ class SegOFATrainEngine:
         d_enc_out = self._lin_bwd(dkv_all, enc_out, self.cross_kv, M, "cross_kv", dx_dtype=f32)  # [M, D] fp32
         g_emb, g_l0 = self.dec_ln_emb, self.dec_layers[0]["ln_self"]
         ops.row_layernorm_bwd(rows=B, D=D, x=self.embed_tokens, gather_idx=bos, g1=g_emb[0], v=xd_emb, g2=g_l0[0],
-                              dy2=da, dv_in=dxs, dg1=g_emb[2], db1=g_emb[3], dg2=g_l0[2], db2=g_l0[3], seg=(1, Td, 0))
+                              dy2=da, dv_in=dxs, dg1=g_emb[2], db1=g_emb[3], dg2=g_l0[2], db2=g_l0[3], seg=(1, Td, 0),
+                              drop=self._drop(100, Td))
         ops.row_layernorm_bwd(rows=B * P, D=D, x=enc_out, gather_idx=dec_in_idx, g1=g_emb[0], v=xd_emb, g2=g_l0[0],
                               dy2=da, dv_in=dxs, dx=d_enc_out, dx_accumulate=True, dg1=g_emb[2], db1=g_emb[3],
-                              dg2=g_l0[2], db2=g_l0[3], seg=(P, Td, 1))
+                              dg2=g_l0[2], db2=g_l0[3], seg=(P, Td, 1), drop=self._drop(101, Td))
 
         # decoder position bias: abs terms -> projections -> seg_pos_ln -> embed_seg_positions; the key side of the
         # cross bias reaches the ENCODER's position embeddings (d_pos, continued after the encoder layers)
@@ -735,7 +763,7 @@ class SegOFATrainEngine:
             dx_new = dxs if dxs is not None else new((M, D), f32)
             dy = new((M, D))
             ops.row_layernorm_bwd(rows=M, D=D, v=S["x2"], g2=nxt[0], dy2=da, dv_in=dxs, d_res=dx_new, dx=dy,
-                                  dg2=nxt[2], db2=nxt[3], dx_colsum=L["fc2"].gb)
+                                  dg2=nxt[2], db2=nxt[3], dx_colsum=L["fc2"].gb, drop=S["dB"])
             dxs = dx_new
             dz = self._lin_bwd(dy, S["z"], L["fc2"], M, "fc2", bias_done=True)
             dh = new((M, Fd))
@@ -745,7 +773,8 @@ class SegOFATrainEngine:
             dy = new((M, D))
             ops.row_layernorm_bwd(rows=M, D=D, x=S["y"], g1=L["ln_attn"][0], v=S["x1"], g2=L["ln_final"][0], dy2=da2,
                                   dv_in=dxs, d_res=dxs, dx=dy, dg1=L["ln_attn"][2], db1=L["ln_attn"][3],
-                                  dg2=L["ln_final"][2], db2=L["ln_final"][3], dx_colsum=L["attn"]["out"].gb)
+                                  dg2=L["ln_final"][2], db2=L["ln_final"][3], dx_colsum=L["attn"]["out"].gb,
+                                  drop=S["dA"])
             do = self._lin_bwd(dy, S["o"], L["attn"]["out"], M, "out_proj", bias_done=True)
             dqkv = new((M, 3 * D))
             delta = self._buf("delta", (B, H, max(T, Td)), f32)
@@ -766,11 +795,11 @@ class SegOFATrainEngine:
         gt = self.g_type
         ops.row_layernorm_bwd(rows=B * P, D=D, x=bag, pre_add=self.type_img, g1=self.ln_patch[0], v=x_emb, g2=g_l0[0],
                               dy2=da, dv_in=dxs, dg1=self.ln_patch[2], db1=self.ln_patch[3], dg2=g_l0[2], db2=g_l0[3],
-                              d_pre_add=gt[1] if gt is not None else None, seg=(P, T, 0))
+                              d_pre_add=gt[1] if gt is not None else None, seg=(P, T, 0), drop=self._drop(1, T))
         ops.row_layernorm_bwd(rows=B * T_txt, D=D, x=self.embed_tokens, gather_idx=tok_idx, pre_add=self.type_txt,
                               g1=self.ln_emb[0], v=x_emb, g2=g_l0[0], dy2=da, dv_in=dxs, dg1=self.ln_emb[2],
                               db1=self.ln_emb[3], dg2=g_l0[2], db2=g_l0[3], d_pre_add=gt[0] if gt is not None else None,
-                              seg=(T_txt, T, P))
+                              seg=(T_txt, T, P), drop=self._drop(2, T))
         # encoder position bias: abs term -> pos_q/pos_k -> pos_ln / image_pos_ln -> the two position tables
         self._abs_bias_bwd(d_enc_abs, pb["pq"], pb["pk"], self.pos_q, self.pos_k, pb["pos"], pb["pos"], T, T, d_pos, d_pos)
         ops.row_layernorm_bwd(rows=P, D=D, x=self.tab_img_pos[0], gather_idx=pb["ids"], g2=self.ln_img_pos[0], dy2=d_pos,

@@ -23,9 +23,10 @@ from .train_engine import SegOFATrainEngine
 
 class SegOFATrainer:
     def __init__(self, model, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1, clip_norm=1.0,
-                 label_smoothing=0.0, seg_id_offset=59457, process_group=None, eval_real_image=True):
+                 label_smoothing=0.0, seg_id_offset=59457, process_group=None, eval_real_image=True, stochastic=True,
+                 seed=1):
         self.model = model
-        self.engine = SegOFATrainEngine(model)
+        self.engine = SegOFATrainEngine(model, stochastic=stochastic, seed=seed)  # dropout / DropPath of the recipe
         self.lr, self.betas, self.eps, self.weight_decay, self.clip_norm = lr, betas, eps, weight_decay, clip_norm
         self.label_smoothing = label_smoothing
         self.seg_id_offset = seg_id_offset

@@ -141,6 +141,12 @@ typedef struct {
   int32_t seg_len, seg_stride, seg_off;
   float* clear_rowstats; /* optional [rows,2] fp32 scratch zeroed as a side effect (row-stats of a following GEMM) */
   int32_t x_act;         /* SGF_ACT_GELU: t = gelu(x[r]) (the FFN's gelu -> ffn_layernorm pair of the training path) */
+  /* training-mode dropout (fairseq_dropout.py) and DropPath (unify_transformer_layer.py:19-35) applied to u before the
+   * residual add: v = u * keep_elem/(1-drop_p) * keep_path[sample]/(1-droppath_p) + residual.  Masks are a counter-based
+   * hash of (drop_seed, drop_step[0], drop_site, output row, column): the adjoint kernel regenerates them, a CUDA-graph
+   * replay with an incremented device-side step draws new ones.  sample = output row / rows_per_sample. */
+  float drop_p; float droppath_p; uint32_t drop_seed; uint32_t drop_site; int32_t rows_per_sample;
+  const int32_t* drop_step;
 } sgf_rowln_args;
 int sgf_row_layernorm(const sgf_rowln_args* args, void* stream);
 
@@ -297,6 +303,9 @@ typedef struct {
   int32_t rows, D;
   int32_t seg_len, seg_stride, seg_off;
   float* dx_colsum; /* optional fp32 [D] += column sums of dx (= bias gradient of the linear that produced x) */
+  /* same dropout / DropPath description as the forward call: du = dv * mask (d_res = dv is not masked) */
+  float drop_p; float droppath_p; uint32_t drop_seed; uint32_t drop_site; int32_t rows_per_sample;
+  const int32_t* drop_step;
 } sgf_rowln_bwd_args;
 int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* args, void* stream);
 

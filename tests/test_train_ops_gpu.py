@@ -326,3 +326,42 @@ def test_adam_and_sumsq(ops):
     out = torch.zeros(1, device="cuda")
     ops.sumsq(grad[:n], out)
     assert abs(out.item() - grad[:n].double().pow(2).sum().item()) < 1e-3 * out.item()
+
+
+def test_row_dropout_droppath_masks_forward_backward(ops):
+    """Counter-based dropout / DropPath: mask values and rates, per-sample path masks, the adjoint regenerates the
+    forward's mask exactly, and a different device-side step draws a different mask."""
+    g = _gen(21)
+    Bn, rps, D = 16, 64, 768
+    rows = Bn * rps
+    x = torch.ones(rows, D, device="cuda")
+    res = torch.zeros(rows, D, device="cuda")
+    one, zero = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
+    step = torch.tensor([3], dtype=torch.int32, device="cuda")
+    drop = dict(p=0.25, path_p=0.5, seed=7, site=5, rows_per_sample=rps, step=step)
+    out1 = torch.empty(rows, D, device="cuda")
+    out2 = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    ops.row_layernorm(x, residual=res, out1=out1, ln2=(one, zero), out2=out2, drop=drop)
+    m = out1.clone()
+    scale = 1.0 / (0.75 * 0.5)
+    assert ((m == 0) | ((m - scale).abs() < 1e-3)).all()
+    per_sample = m.view(Bn, rps * D)
+    alive = per_sample.abs().sum(1) > 0
+    assert 2 <= int(alive.sum()) <= 14                                    # DropPath: whole samples, p = 0.5
+    assert (per_sample[~alive] == 0).all()
+    keep = (per_sample[alive] > 0).float().mean().item()
+    assert abs(keep - 0.75) < 0.01, keep                                  # element dropout inside surviving samples
+    dy = torch.randn(rows, D, device="cuda", generator=g)
+    dx = torch.empty(rows, D, device="cuda")
+    ops.row_layernorm_bwd(rows=rows, D=D, dy2=dy, dx=dx, drop=drop)
+    assert torch.equal(dx, dy * m)
+    step += 1
+    ops.row_layernorm(x, residual=res, out1=out1, ln2=(one, zero), out2=out2, drop=drop)
+    assert not torch.equal(out1, m) and abs((out1 > 0).float().mean().item() - (m > 0).float().mean().item()) < 0.3
+    # p = 0: bit-identical to the call without a drop description
+    o_a, o_b = torch.empty_like(out1), torch.empty_like(out1)
+    y = torch.randn(rows, D, device="cuda", generator=g)
+    ops.row_layernorm(y, ln1=(one, zero), residual=res, out1=o_a, ln2=(one, zero), out2=out2)
+    ops.row_layernorm(y, ln1=(one, zero), residual=res, out1=o_b, ln2=(one, zero), out2=out2,
+                      drop=dict(p=0.0, path_p=0.0, seed=1, site=1, rows_per_sample=rps, step=step))
+    assert torch.equal(o_a, o_b)
