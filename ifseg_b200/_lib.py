@@ -176,6 +176,9 @@ EXPORTS = [
     ("sgf_upsample_argmax", C.c_int, [C.POINTER(SegmaskArgs), _vp]),
     ("sgf_embedding_bag_mean", C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i64, _i32, _vp, _vp]),
     ("sgf_upsample_ce_loss", C.c_int, [C.POINTER(SeglossArgs), _vp]),
+    ("sgf_l2_normalize_rows", C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _vp]),
+    ("sgf_row_topk", C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    ("sgf_label_propagation", C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _f32, _vp, _i32, _i32, _vp, _vp, _vp]),
     ("sgf_upsample_ce_loss_bwd", C.c_int, [C.POINTER(SeglossBwdArgs), _vp]),
     ("sgf_row_layernorm_bwd", C.c_int, [C.POINTER(RowLnBwdArgs), _vp]),
     ("sgf_transpose_cast", C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp]),

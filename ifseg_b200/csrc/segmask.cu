@@ -287,9 +287,163 @@ __global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const SeglossBwdPa
   }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// Validation post-processing (seg_criterion.py:197-213): label propagation over the ResNet-feature
+// nearest neighbours.  L2-normalised features -> cosine similarity (batched tcgen05 GEMM, gemm.cu) ->
+// top-k neighbours per patch -> resnet_iters rounds of prob[p] = mean_k prob[nbr_k(p)].
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2_normalize_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                                __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane * 8; c < D; c += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx + c);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    s += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + cc.x * cc.x + cc.y * cc.y + d.x * d.x + d.y * d.y;
+  }
+  s = warp_sum(s);
+  const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);  // F.normalize eps
+  for (int c = lane * 8; c < D; c += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx + c);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    uint4 o;
+    o.x = pack_bf16x2(a.x * inv, a.y * inv); o.y = pack_bf16x2(b.x * inv, b.y * inv);
+    o.z = pack_bf16x2(cc.x * inv, cc.y * inv); o.w = pack_bf16x2(d.x * inv, d.y * inv);
+    *reinterpret_cast<uint4*>(y + static_cast<int64_t>(row) * ldy + c) = o;
+  }
+}
+
+// top-k (k <= 8) column indices of every row, largest first, lowest index first among equals; one warp per row
+template <int K>
+__global__ void __launch_bounds__(256) row_topk_kernel(const float* __restrict__ x, int64_t ldx, int rows, int n,
+                                                       int32_t* __restrict__ idx_out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float bv[K];
+  int bi[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { bv[k] = -INFINITY; bi[k] = 0x7fffffff; }
+  const float* r = x + static_cast<int64_t>(row) * ldx;
+  for (int j = lane; j < n; j += 32) {
+    float v = r[j];
+    int id = j;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {  // insertion into the lane-local sorted list
+      const bool better = v > bv[k] || (v == bv[k] && id < bi[k]);
+      if (better) {
+        const float tv = bv[k]; const int ti = bi[k];
+        bv[k] = v; bi[k] = id; v = tv; id = ti;
+      }
+    }
+  }
+  // K rounds: the warp-wide best head is emitted, its owner pops it
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float v = bv[0];
+    int id = bi[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, id, o);
+      if (ov > v || (ov == v && oi < id)) { v = ov; id = oi; }
+    }
+    if (lane == 0) idx_out[static_cast<int64_t>(row) * K + k] = id;
+    if (bi[0] == id) {
+#pragma unroll
+      for (int q = 0; q + 1 < K; ++q) { bv[q] = bv[q + 1]; bi[q] = bi[q + 1]; }
+      bv[K - 1] = -INFINITY; bi[K - 1] = 0x7fffffff;
+    }
+  }
+}
+
+// out[b,p,:] = softmax(x[b,p,:] * inv_temp)   (one warp per row)
+__global__ void __launch_bounds__(256) row_softmax_kernel(const float* __restrict__ x, int64_t batch_stride, int64_t tok_stride,
+                                                          int P, int C, float inv_temp, float* __restrict__ out, int rows) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* r = x + static_cast<int64_t>(row / P) * batch_stride + static_cast<int64_t>(row % P) * tok_stride;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, r[c] * inv_temp);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += __expf(r[c] * inv_temp - m);
+  s = warp_sum(s);
+  const float inv = 1.0f / s;
+  for (int c = lane; c < C; c += 32) out[static_cast<int64_t>(row) * C + c] = __expf(r[c] * inv_temp - m) * inv;
+}
+
+// out[b,p,c] = mean_k in[b, nbr[b,p,k], c]
+__global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restrict__ in, const int32_t* __restrict__ nbr, int K,
+                                                          int P, int C, int64_t total, float* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int c = i % C;
+  const int64_t bp = i / C;
+  const int64_t b = bp / P;
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) s += in[(b * P + nbr[bp * K + k]) * C + c];
+  out[i] = s / static_cast<float>(K);
+}
+
 }  // namespace sgf
 
 using namespace sgf;
+
+extern "C" int sgf_l2_normalize_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t D, void* stream) {
+  SGF_REQUIRE(x && y && rows > 0 && D > 0 && D % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "l2_normalize_rows: bad arguments");
+  l2_normalize_rows_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, D);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
+
+extern "C" int sgf_row_topk(const float* x, int64_t ldx, int32_t rows, int32_t n, int32_t k, int32_t* idx_out, void* stream) {
+  SGF_REQUIRE(x && idx_out && rows > 0 && n > 0 && k >= 1 && k <= 8 && k <= n, "row_topk: bad arguments (1 <= k <= 8)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((rows + 7) / 8);
+  switch (k) {
+    case 1: row_topk_kernel<1><<<grid, 256, 0, st>>>(x, ldx, rows, n, idx_out); break;
+    case 2: row_topk_kernel<2><<<grid, 256, 0, st>>>(x, ldx, rows, n, idx_out); break;
+    case 3: row_topk_kernel<3><<<grid, 256, 0, st>>>(x, ldx, rows, n, idx_out); break;
+    case 4: row_topk_kernel<4><<<grid, 256, 0, st>>>(x, ldx, rows, n, idx_out); break;
+    case 5: row_topk_kernel<5><<<grid, 256, 0, st>>>(x, ldx, rows, n, idx_out); break;
+    case 6: row_topk_kernel<6><<<grid, 256, 0, st>>>(x, ldx, rows, n, idx_out); break;
+    case 7: row_topk_kernel<7><<<grid, 256, 0, st>>>(x, ldx, rows, n, idx_out); break;
+    default: row_topk_kernel<8><<<grid, 256, 0, st>>>(x, ldx, rows, n, idx_out); break;
+  }
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
+
+extern "C" int sgf_label_propagation(const float* logits, int64_t batch_stride, int64_t tok_stride, int32_t B, int32_t P,
+                                     int32_t C, float temperature, const int32_t* nbr, int32_t k, int32_t iters,
+                                     float* prob_a, float* prob_b, void* stream) {
+  SGF_REQUIRE(logits && nbr && prob_a && prob_b && B > 0 && P > 0 && C > 0 && k >= 1 && iters >= 0 && temperature > 0.f,
+              "label_propagation: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rows = B * P;
+  row_softmax_kernel<<<(rows + 7) / 8, 256, 0, st>>>(logits, batch_stride, tok_stride, P, C, 1.0f / temperature, prob_a, rows);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  const int64_t total = static_cast<int64_t>(rows) * C;
+  float* src = prob_a;
+  float* dst = prob_b;
+  for (int it = 0; it < iters; ++it) {
+    gather_mean_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, nbr, k, P, C, total, dst);
+    SGF_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    float* t = src; src = dst; dst = t;
+  }
+  return SGF_OK;  // result in prob_a when iters is even, prob_b when odd
+}
+
 
 extern "C" int sgf_upsample_ce_loss_bwd(const sgf_segloss_bwd_args* a, void* stream) {
   SGF_REQUIRE(a != nullptr && a->logits && a->target && a->lse && a->count && a->dlogits, "upsample_ce_loss_bwd: null pointer");

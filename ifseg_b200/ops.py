@@ -325,6 +325,33 @@ def upsample_ce_loss(logits, target, hp, wp, label_smoothing=0.0, lse_out=None, 
     return acc[0] / acc[1], acc[1]
 
 
+def label_propagation(features, logits, topk=3, iters=25, temperature=1.0):
+    """seg_criterion.py:197-213.  features bf16 [B,P,Df] (ResNet patch features), logits fp32 [B,>=P,C] ->
+    propagated class probabilities fp32 [B,P,C] and the neighbour indices int32 [B,P,topk]."""
+    lib = _lib.load()
+    _req(features, torch.bfloat16, "features")
+    _req(logits, torch.float32, "logits")
+    B, P, Df = features.shape
+    Cn = logits.shape[2]
+    f = features.reshape(B * P, Df)
+    fn = torch.empty_like(f)
+    with _timed("label_prop", nbytes=float(f.numel() * 4)):
+        _lib.check(lib.sgf_l2_normalize_rows(_p(f), f.stride(0), _p(fn), fn.stride(0), B * P, Df, _stream()),
+                   "sgf_l2_normalize_rows")
+    Pp = (P + 3) // 4 * 4
+    sim = torch.empty((B, P, Pp), dtype=torch.float32, device=f.device)
+    gemm(fn, fn, sim, M=P, N=P, K=Df, batch=B, lda=Df, ldb=Df, ldc=Pp, a_batch_stride=P * Df, b_batch_stride=P * Df,
+         c_batch_stride=P * Pp, tag="cosine_sim")
+    nbr = torch.empty((B, P, topk), dtype=torch.int32, device=f.device)
+    pa = torch.empty((B, P, Cn), dtype=torch.float32, device=f.device)
+    pb = torch.empty_like(pa)
+    with _timed("label_prop", nbytes=float(sim.numel() * 4 + iters * pa.numel() * 8)):
+        _lib.check(lib.sgf_row_topk(_p(sim), Pp, B * P, P, topk, _p(nbr), _stream()), "sgf_row_topk")
+        _lib.check(lib.sgf_label_propagation(_p(logits), logits.stride(0), logits.stride(1), B, P, Cn, float(temperature),
+                                             _p(nbr), topk, iters, _p(pa), _p(pb), _stream()), "sgf_label_propagation")
+    return (pa if iters % 2 == 0 else pb), nbr
+
+
 # ----------------------------------------------------------------------------------------
 # training path (adjoint kernels)
 # ----------------------------------------------------------------------------------------

@@ -6,8 +6,8 @@
   _lazy_initialization (:373-407)                       -> sgf_embedding_bag_mean;
   SegCriterion.forward (:165-235)                       -> same signature and logging_output keys.
 
-Round-1 state: the evaluation branch (model.eval()) is complete except the ResNet-feature label
-propagation (`resnet_iters > 0`, seg_criterion.py:197-213 -- SURVEY.md s8f-2); the training branch
+Round-1 state: the evaluation branch (model.eval()) incl. the ResNet-feature label propagation
+(`resnet_iters > 0`, seg_criterion.py:197-213 -> ops.label_propagation); the training branch
 (unsupervised_segmentation: image-free loss + no-grad real-image metrics) returns a loss whose .backward()
 runs the hand-written adjoint kernels (PixelCrossEntropyFunction -> train_engine.ImFreeBranchFunction).
 """
@@ -136,10 +136,14 @@ class SegCriterion:
                               "ntokens": sample["ntokens"], "nsentences": sample["nsentences"], "sample_size": sample_size}
             logging_output.update(metrics)
             return loss, sample_size, logging_output
-        if self.resnet_iters > 0:
-            raise NotImplementedError("ResNet-feature label propagation (resnet_iters > 0) is a 'next' row (SURVEY s8f-2)")
         with torch.no_grad():
             logits, extra = model(**sample["net_input"], full_context_alignment=self.full_context_alignment)
+            if self.resnet_iters > 0:  # seg_criterion.py:197-213: label propagation over ResNet-feature neighbours
+                feats = extra["encoder_returns"]["image_embed_before_proj"][0]
+                prob, _ = ops.label_propagation(feats.contiguous(), logits.float().contiguous(), self.resnet_topk,
+                                                self.resnet_iters, self.resnet_prob_temperature)
+                eos = prob.new_zeros((prob.shape[0], 1, prob.shape[2]))  # fake eos row (:211)
+                extra["resnet_postprocess_probability"] = torch.cat([prob, eos], dim=1)
             seg_loss, metrics = self.compute_loss(logits, extra, sample)
         imfree_loss = torch.zeros(1, device=logits.device)
         loss = seg_loss
@@ -163,6 +167,11 @@ class SegCriterion:
             tgt = class_targets(ids, self.seg_id_offset, self.num_seg, self.padding_idx)
         _, ai, ap, al, au = segmentation_metrics(logits, tgt, hp, wp)
         metrics = {"area_intersect": ai, "area_pred_label": ap, "area_label": al, "area_union": au}
+        post = extra.get("resnet_postprocess_probability")
+        if post is not None:  # seg_criterion.py:329-336: the same metric on the propagated probabilities
+            _, ai2, ap2, al2, au2 = segmentation_metrics(post, tgt, hp, wp)
+            metrics.update(area_intersect_resnet_postprocess=ai2, area_pred_label_resnet_postprocess=ap2,
+                           area_label_resnet_postprocess=al2, area_union_resnet_postprocess=au2)
         loss = pixel_cross_entropy(logits, tgt, hp, wp, self.eps)  # "just for display" (:340)
         metrics["nll_loss"] = loss
         return loss, metrics

@@ -250,6 +250,22 @@ typedef struct {
 } sgf_segloss_args;
 int sgf_upsample_ce_loss(const sgf_segloss_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Validation post-processing (seg_criterion.py:197-213, resnet_iters > 0): label propagation over the nearest
+ * neighbours of the ResNet patch features.
+ *   sgf_l2_normalize_rows : y[r] = x[r] / max(||x[r]||, 1e-12)        (F.normalize; bf16 rows)
+ *   (cosine similarity = batched sgf_gemm_bf16 of the normalised features with themselves)
+ *   sgf_row_topk          : the k (<= 8) largest columns of every fp32 row, largest first (torch.topk)
+ *   sgf_label_propagation : prob = softmax(logits / temperature) over C, then `iters` rounds of
+ *                           prob[b,p,:] = mean_k prob[b, nbr[b,p,k], :]; ping-pong buffers prob_a / prob_b
+ *                           ([B,P,C] fp32): the result is in prob_a for even iters, prob_b for odd.
+ * ------------------------------------------------------------------------------------- */
+int sgf_l2_normalize_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t D, void* stream);
+int sgf_row_topk(const float* x, int64_t ldx, int32_t rows, int32_t n, int32_t k, int32_t* idx_out, void* stream);
+int sgf_label_propagation(const float* logits, int64_t batch_stride, int64_t tok_stride, int32_t B, int32_t P, int32_t C,
+                          float temperature, const int32_t* nbr, int32_t k, int32_t iters, float* prob_a, float* prob_b,
+                          void* stream);
+
 /* =======================================================================================
  * Training path (image-free branch, segofa.py:136-151 + seg_criterion.py:246-267): the
  * reference gets its backward from autograd over the ATen ops above; the entry points below are

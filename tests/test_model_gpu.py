@@ -173,6 +173,14 @@ def test_criterion_eval_branch(case15):
     assert abs(loss.item() - ref_loss.item()) < 1e-3
     m = derive_metrics(ai, ap, al, au)
     assert 0 <= m["mIoU"] <= 1 and 0 <= m["aAcc"] <= 1
+    # validation post-processing (resnet_iters > 0): the propagated probabilities give a second set of areas
+    crit_pp = SegCriterion(task, resnet_iters=5, resnet_topk=3)
+    _, _, log_pp = crit_pp(model, sample)
+    for k in ("area_intersect_resnet_postprocess", "area_pred_label_resnet_postprocess", "area_label_resnet_postprocess",
+              "area_union_resnet_postprocess"):
+        assert k in log_pp and log_pp[k].shape == (C,)
+    assert torch.equal(log_pp["area_label_resnet_postprocess"], log_pp["area_label"])
+    assert log_pp["area_pred_label_resnet_postprocess"].sum() == log_pp["area_pred_label"].sum()
     # image-free loss value (training forward) against the oracle's imfree_loss on OUR aux logits
     aux = {k: v.cuda() for k, v in g["aux_input"].items()}
     t2s = torch.cat([torch.randint(0, C + 1, (g["batch"], S * S), generator=gen) + 59457,

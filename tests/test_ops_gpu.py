@@ -359,3 +359,39 @@ def test_attention_full_size_repeatable(ops):
     q, k, v = (t.reshape(B, T, H, dh) for t in qkv.split(D, dim=-1))
     ref = _attn_ref(q[:2], k[:2], v[:2], bias, False, None, hs).reshape(2, T, D)
     assert _rel(outs[0][:2], ref) < 8e-3
+
+
+@pytest.mark.parametrize("B,P,C,k,iters", [(2, 900, 150, 3, 25), (1, 64, 15, 3, 4), (3, 100, 171, 5, 1), (1, 16, 15, 1, 0)])
+def test_label_propagation(ops, B, P, C, k, iters):
+    """seg_criterion.py:197-213: normalise -> cosine similarity -> top-k -> iters x gather-mean."""
+    g = torch.Generator(device="cuda").manual_seed(P + C)
+    feats = torch.randn(B, P, 1024, device="cuda", generator=g).relu().bfloat16()
+    logits = torch.randn(B, P + 1, C, device="cuda", generator=g) * 2
+    prob, nbr = ops.label_propagation(feats, logits, topk=k, iters=iters, temperature=0.7)
+    fn = F.normalize(feats.float(), dim=-1)
+    sim = fn @ fn.transpose(-1, -2)
+    # every chosen neighbour is within bf16 rounding of the true k-th best similarity; self is the best
+    vals = sim.gather(-1, nbr.long())
+    kth = sim.topk(k, dim=-1).values
+    assert (vals >= kth[..., -1:] - 2e-2).all()
+    assert (nbr[..., 0].long() == torch.arange(P, device="cuda")).float().mean() > 0.99
+    assert (vals[..., :-1] >= vals[..., 1:] - 2e-2).all()  # largest first
+    # the propagation itself, on OUR neighbours, against the reference's indexing loop
+    ref = (logits[:, :P] / 0.7).softmax(-1)
+    bi = torch.arange(B, device="cuda").view(B, 1, 1).expand(B, P, k)
+    for _ in range(iters):
+        ref = ref[bi, nbr.long()].mean(dim=-2)
+    assert prob.shape == (B, P, C)
+    assert torch.allclose(prob, ref, atol=2e-6, rtol=1e-4)
+
+
+def test_row_topk_ties_and_order(ops):
+    from ifseg_b200 import _lib
+    import ctypes as C
+
+    x = torch.tensor([[1.0, 5.0, 5.0, 3.0, 5.0, -1.0, 2.0], [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 9.0]], device="cuda")
+    out = torch.empty(2, 3, dtype=torch.int32, device="cuda")
+    lib = _lib.load()
+    _lib.check(lib.sgf_row_topk(C.c_void_p(x.data_ptr()), 7, 2, 7, 3, C.c_void_p(out.data_ptr()),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream)), "sgf_row_topk")
+    assert out.tolist() == [[1, 2, 4], [6, 0, 1]]
