@@ -64,6 +64,7 @@ class BiasArgs(C.Structure):
     _fields_ = [
         ("out", _vp), ("abs", _vp), ("head_stride", _i64), ("row_stride", _i64), ("dense_add", _vp),
         ("H", _i32), ("Tq", _i32), ("Tk", _i32), ("num_blocks", _i32), ("blocks", RelBlock * 2),
+        ("out_f16", _vp),
     ]
 
 

@@ -13,9 +13,14 @@
 //                        more than 2^8), exp2, row sum; P(j) -> smem as bf16 in the swizzled K-major
 //                        layout the tensor core reads
 //   O += P(j) V(j)       tcgen05.mma M128 N64 K64 accumulating in TMEM (V tile is the MN-major B operand)
-// K/V tiles and P are double-buffered.  112 KB of shared memory and 256 TMEM columns per CTA
-// keep two CTAs per SM, so the eight softmax warps of an SM cover each other's waits.
+// The loop is TMA-latency bound unless every stream is prefetched at least two tiles ahead (a tile costs ~2000
+// cycles of softmax work, an L2->smem TMA round trip under load ~3500): K and V tiles are triple-buffered, the bias
+// tile is FP16 (half the bytes of the dominant L2 stream) and double-buffered, P is single-buffered (its reader
+// P V(j-1) retires long before softmax(j) has its probabilities).  112 KB of shared memory and 256 TMEM columns per
+// CTA keep two CTAs per SM, so the eight softmax warps of an SM cover each other's waits.
 #include <string.h>
+
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -25,14 +30,14 @@ static constexpr int kQTile = 128;
 static constexpr int kKTile = 64;
 static constexpr int kHeadDim = 64;
 static constexpr int kAttnThreads = 160;
-static constexpr int kKvStages = 2;
+static constexpr int kKvStages = 3;
 static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr float kRescaleThreshold = 8.0f;  // log2 domain: probabilities stay below 2^8
 
 struct AttnParams {
   void* out;
   int64_t o_row_stride, o_batch_stride;
-  const float* bias;
+  const void* bias;
   const float* head_scale;
   const uint8_t* kpm;
   int B, H, Tq, Tk, causal;
@@ -43,19 +48,19 @@ struct AttnSmem {
   static constexpr int kQ = kQTile * kHeadDim * 2;     // 16 KB
   static constexpr int kKV = kKTile * kHeadDim * 2;    // 8 KB
   static constexpr int kP = kQTile * kKTile * 2;       // 16 KB
-  static constexpr int kBias = kQTile * kKTile * 4;    // 32 KB fp32 bias tile: two 128B-swizzled [128 x 32] boxes
+  static constexpr int kBias = kQTile * kKTile * 2;    // 16 KB fp16 bias tile: one 128B-swizzled [128 x 64] box
   static constexpr int offQ = 0;
   static constexpr int offK = offQ + kQ;
   static constexpr int offV = offK + kKvStages * kKV;
-  static constexpr int offP = offV + kKvStages * kKV;  // two P buffers (ping-pong)
-  static constexpr int offBias = offP + 2 * kP;
-  static constexpr int offBar = offBias + kBias;
+  static constexpr int offP = offV + kKvStages * kKV;  // one P buffer
+  static constexpr int offBias = offP + kP;            // two bias buffers
+  static constexpr int offBar = offBias + 2 * kBias;
   static constexpr int kTotal = offBar + 256;
 };
 
 struct AttnBars {
   uint64_t q_full, k_full[kKvStages], k_empty[kKvStages], v_full[kKvStages], v_empty[kKvStages];
-  uint64_t s_full[2], s_empty[2], p_full[2], b_empty, o_done;  // s_full also carries the bias-tile bytes
+  uint64_t s_full[2], s_empty[2], p_full, b_empty[2], o_done;  // s_full also carries the bias-tile bytes
   uint32_t tmem_slot;
 };
 static_assert(sizeof(AttnBars) <= 256, "barrier block");
@@ -91,11 +96,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       mbar_init(&bars->s_full[i], p.bias ? 2 : 1);  // tcgen05.commit of S(j) (+ the expect_tx arrive of bias(j))
       mbar_init(&bars->s_empty[i], 128);
     }
-    // one "P published" barrier per P buffer: the softmax warps may run one tile ahead of the P V issue,
-    // so a single barrier could advance two phases before the control lane looks at it
-    mbar_init(&bars->p_full[0], 128);
-    mbar_init(&bars->p_full[1], 128);
-    mbar_init(&bars->b_empty, 128);
+    mbar_init(&bars->p_full, 128);
+    mbar_init(&bars->b_empty[0], 128);
+    mbar_init(&bars->b_empty[1], 128);
     mbar_init(&bars->o_done, 1);
     fence_mbar_init();
   }
@@ -133,14 +136,16 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       };
       auto load_bias = [&](int t) {  // completes on the same barrier as S(t): one wait per tile for the softmax warps
         mbar_expect_tx(&bars->s_full[t & 1], AttnSmem::kBias);
-        tma_load_3d(smem + AttnSmem::offBias, &tmB, &bars->s_full[t & 1], t * kKTile, q0, h);
-        tma_load_3d(smem + AttnSmem::offBias + AttnSmem::kBias / 2, &tmB, &bars->s_full[t & 1], t * kKTile + 32, q0, h);
+        tma_load_3d(smem + AttnSmem::offBias + (t & 1) * AttnSmem::kBias, &tmB, &bars->s_full[t & 1], t * kKTile, q0, h);
       };
       mbar_expect_tx(&bars->q_full, AttnSmem::kQ);
       tma_load_4d(smem + AttnSmem::offQ, &tmQ, &bars->q_full, 0, h, q0, b);
       for (int t = 0; t < kKvStages && t < n_kt; ++t) load_k(t);
-      if (p.bias) load_bias(0);
-      for (int t = 0; t < kKvStages && t < n_kt; ++t) load_v(t);
+      if (p.bias) {
+        load_bias(0);
+        if (n_kt > 1) load_bias(1);
+      }
+      for (int t = 0; t < 2 && t < n_kt; ++t) load_v(t);
       const uint64_t dq = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offQ));
 
 #pragma unroll 1
@@ -158,15 +163,20 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
             umma_f16(tmem_s + (j & 1) * 64, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
           umma_commit(&bars->s_full[j & 1]);
           umma_commit(&bars->k_empty[st]);
-          // K(j-1)'s stage is free (S(j-1) retired long ago): prefetch K(j+1) into it
-          if (j >= 1 && j + 1 < n_kt) {
+          // K(j-1)'s stage is free (S(j-1) retired a tile ago): prefetch K(j+2) into it
+          if (j >= 1 && j + 2 < n_kt) {
             mbar_wait(&bars->k_empty[(j - 1) % kKvStages], ((j - 1) / kKvStages) & 1);
-            load_k(j + 1);
+            load_k(j + 2);
           }
-          // V(j-2)'s stage is free once PV(j-2) retired: prefetch V(j) into it
-          if (j >= 2) {
-            mbar_wait(&bars->v_empty[(j - 2) % kKvStages], ((j - 2) / kKvStages) & 1);
-            load_v(j);
+          // V(j+1) goes into the stage of V(j-2) (P V(j-2) was issued a tile ago); V(0), V(1) were loaded up front
+          if (j >= 1 && j + 1 < n_kt) {
+            if (j >= 2) mbar_wait(&bars->v_empty[(j - 2) % kKvStages], ((j - 2) / kKvStages) & 1);
+            load_v(j + 1);
+          }
+          // bias(j+1) goes into the buffer softmax(j-1) has read
+          if (p.bias && j >= 1 && j + 1 < n_kt) {
+            mbar_wait(&bars->b_empty[(j + 1) & 1], ((j - 1) >> 1) & 1);
+            load_bias(j + 1);
           }
         }
         if (j >= 1) {
@@ -174,19 +184,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
           const int t = j - 1;
           const int st = t % kKvStages;
           mbar_wait(&bars->v_full[st], (t / kKvStages) & 1);
-          mbar_wait(&bars->p_full[t & 1], (t >> 1) & 1);
+          mbar_wait(&bars->p_full, t & 1);
           tc_fence_after();
           const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offV + st * AttnSmem::kKV));
-          const uint64_t dp = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offP + (t & 1) * AttnSmem::kP));
+          const uint64_t dp = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offP));
 #pragma unroll
           for (int k = 0; k < kKTile / 16; ++k)  // V: 16 key rows = 2048 B per K step -> +128 in the address field
             umma_f16(tmem_o, dp + 2 * k, dv + 128 * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
           umma_commit(&bars->v_empty[st]);
           umma_commit(&bars->o_done);
-        }
-        if (p.bias && j + 1 < n_kt) {  // bias(j+1) as soon as every softmax thread has consumed bias(j)
-          mbar_wait(&bars->b_empty, j & 1);
-          load_bias(j + 1);
         }
       }
     }
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
     // =================================== softmax warps ===================================
     const int row = q0 + tid;
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    const uint8_t* bias_row = smem + AttnSmem::offBias + tid * 128;  // this thread's row inside each bias box
+    const uint8_t* bias_row = smem + AttnSmem::offBias + tid * 128;  // this thread's 64-half row inside a bias buffer
     const uint8_t* kpm_row = p.kpm ? p.kpm + static_cast<int64_t>(b) * p.Tk : nullptr;
     uint8_t* p_row0 = smem + AttnSmem::offP + tid * 128;
     float m_used = 0.f;  // log2-domain reference max the probabilities are expressed against
@@ -210,26 +216,22 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         uint32_t r0[32], r1[32];
         tmem_ld_32x32(tmem_s + (j & 1) * 64 + lane_addr, r0);
         tmem_ld_32x32(tmem_s + (j & 1) * 64 + lane_addr + 32, r1);
-        if (p.bias) {  // the swizzled smem reads of the bias tile overlap the TMEM load latency
-          float4 bb[16];
+        if (p.bias) {  // the swizzled smem reads of the fp16 bias tile overlap the TMEM load latency
+          uint4 bb[8];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              bb[half * 8 + c] =
-                  *reinterpret_cast<const float4*>(bias_row + half * (AttnSmem::kBias / 2) + ((c ^ (tid & 7)) << 4));
-          }
+          for (int c = 0; c < 8; ++c)
+            bb[c] = *reinterpret_cast<const uint4*>(bias_row + (j & 1) * AttnSmem::kBias + ((c ^ (tid & 7)) << 4));
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            s[4 * c + 0] = __uint_as_float(r0[4 * c + 0]) + bb[c].x;
-            s[4 * c + 1] = __uint_as_float(r0[4 * c + 1]) + bb[c].y;
-            s[4 * c + 2] = __uint_as_float(r0[4 * c + 2]) + bb[c].z;
-            s[4 * c + 3] = __uint_as_float(r0[4 * c + 3]) + bb[c].w;
-            s[32 + 4 * c + 0] = __uint_as_float(r1[4 * c + 0]) + bb[8 + c].x;
-            s[32 + 4 * c + 1] = __uint_as_float(r1[4 * c + 1]) + bb[8 + c].y;
-            s[32 + 4 * c + 2] = __uint_as_float(r1[4 * c + 2]) + bb[8 + c].z;
-            s[32 + 4 * c + 3] = __uint_as_float(r1[4 * c + 3]) + bb[8 + c].w;
+          for (int c = 0; c < 8; ++c) {  // chunk c = columns 8c .. 8c+7
+            const uint32_t w[4] = {bb[c].x, bb[c].y, bb[c].z, bb[c].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+              const int col = 8 * c + 2 * q;
+              s[col] = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + f.x;
+              s[col + 1] = __uint_as_float(col < 32 ? r0[col + 1] : r1[col - 31]) + f.y;
+            }
           }
         } else {
           tmem_ld_wait();
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       }
       tc_fence_before();
       mbar_arrive(&bars->s_empty[j & 1]);
-      if (p.bias) mbar_arrive(&bars->b_empty);
+      if (p.bias) mbar_arrive(&bars->b_empty[j & 1]);
       const bool need_mask = (k0 + kKTile > p.Tk) || (p.causal && (k0 + kKTile - 1 > q0)) || (kpm_row != nullptr);
       if (need_mask) {
 #pragma unroll
@@ -295,8 +297,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         ps[i & 7] += s[i];
       }
       l_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
-      // P (bf16) -> smem buffer j&1: its previous reader P V(j-2) retired before S(j) did (in-order tensor pipe)
-      uint8_t* p_row = p_row0 + (j & 1) * AttnSmem::kP;
+      // P (bf16) -> the single smem buffer once its previous reader P V(j-1) has retired (issued a tile ago)
+      if (j >= 1) mbar_wait(&bars->o_done, (j - 1) & 1);
+      uint8_t* p_row = p_row0;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         uint4 u;
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         *reinterpret_cast<uint4*>(p_row + ((c ^ (tid & 7)) << 4)) = u;
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&bars->p_full[j & 1]);
+      mbar_arrive(&bars->p_full);
     }
 
     if (n_kt > 0) {
@@ -372,9 +375,9 @@ extern "C" int sgf_attention_bf16(const sgf_attention_args* a, void* stream) {
                reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->out)) % 16 == 0,
               "attention: q/k/v/out must be 16-byte aligned");
   if (a->bias)
-    SGF_REQUIRE(a->bias_row_stride % 4 == 0 && a->bias_head_stride % 4 == 0 &&
+    SGF_REQUIRE(a->bias_row_stride % 8 == 0 && a->bias_head_stride % 8 == 0 &&
                     reinterpret_cast<uintptr_t>(a->bias) % 16 == 0 && a->bias_row_stride >= a->Tk,
-                "attention: bias must be 16-byte aligned with row/head strides multiples of 4 floats");
+                "attention: the fp16 bias must be 16-byte aligned with row/head strides multiples of 8 elements");
   CUtensorMap tmQ, tmK, tmV;
   if (int rc = make_qkv_map(&tmQ, a->q, a->q_row_stride, a->q_batch_stride, a->H, a->Tq, a->B, kQTile)) return rc;
   if (int rc = make_qkv_map(&tmK, a->k, a->k_row_stride, a->k_batch_stride, a->H, a->Tk, a->B, kKTile)) return rc;
@@ -383,9 +386,9 @@ extern "C" int sgf_attention_bf16(const sgf_attention_args* a, void* stream) {
   memset(&tmB, 0, sizeof(tmB));
   if (a->bias) {
     uint64_t dims[3] = {static_cast<uint64_t>(a->bias_row_stride), static_cast<uint64_t>(a->Tq), static_cast<uint64_t>(a->H)};
-    uint64_t strides[2] = {static_cast<uint64_t>(a->bias_row_stride) * 4, static_cast<uint64_t>(a->bias_head_stride) * 4};
-    uint32_t box[3] = {32, kQTile, 1};
-    if (int rc = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a->bias, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+    uint64_t strides[2] = {static_cast<uint64_t>(a->bias_row_stride) * 2, static_cast<uint64_t>(a->bias_head_stride) * 2};
+    uint32_t box[3] = {kKTile, kQTile, 1};
+    if (int rc = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a->bias, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
   }
   AttnParams p{a->out, a->o_row_stride, a->o_batch_stride, a->bias, a->head_scale, a->key_padding_mask,

@@ -649,7 +649,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<BN>(), 
 // ----------------------------------------------------------------------------------------
 static constexpr int kP2BN = 256;
 static constexpr int kP2Stages = 6;
-static constexpr int kP2EpiWarps = 8;
+static constexpr int kP2EpiWarps = 16;  // 4 per TMEM lane quarter, 64 columns each: the epilogue (GELU, bias, packing) is
+                                         // issue-bound and must keep up with a 12-k-block main loop
 static constexpr int kP2Threads = 64 + 32 * kP2EpiWarps;
 
 template <int kEpi>
@@ -742,7 +743,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1)
     // ---------------- epilogue warps: thread = row, straight from TMEM to global memory ----------------
     const int ew = warp - 2;
     const int quarter = warp & 3;
-    const int half = ew >> 2;  // columns [half*128, +128) of the tile
+    constexpr int kParts = kP2EpiWarps / 4;
+    constexpr int kColsPerWarp = BN / kParts;
+    const int half = ew >> 2;  // columns [half*kColsPerWarp, +kColsPerWarp) of the tile
     const bool out_f32 = (kEpi & kEpiOutF32) != 0;
     const int csz = out_f32 ? 4 : 2;
     int it = 0;
@@ -771,10 +774,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1)
       uint8_t* crow = reinterpret_cast<uint8_t*>(ep.c) + (static_cast<int64_t>(z) * ep.c_batch_stride + static_cast<int64_t>(rrow) * ep.ldc) * csz;
       float st_sum = 0.f, st_sq = 0.f;
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        const int c0 = n0 + half * 128 + ch * 32;
+      for (int ch = 0; ch < kColsPerWarp / 32; ++ch) {
+        const int c0 = n0 + half * kColsPerWarp + ch * 32;
         uint32_t acc[32];
-        tmem_ld_32x32(tmem_base + ab * BN + (static_cast<uint32_t>(quarter * 32) << 16) + half * 128 + ch * 32, acc);
+        tmem_ld_32x32(tmem_base + ab * BN + (static_cast<uint32_t>(quarter * 32) << 16) + half * kColsPerWarp + ch * 32, acc);
         tmem_ld_wait();
         float v[32];
 #pragma unroll

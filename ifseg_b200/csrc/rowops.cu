@@ -1,6 +1,8 @@
 // HBM-bound row / layout kernels: fused LayerNorm(+gather, +residual, +second LayerNorm),
 // attention rel-pos bias assembly, stem layout helpers (NCHW->NHWC, im2col for the few strided
 // convolutions, max-pool).  Warp-shuffle reductions, 128-bit global accesses.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sgf {
@@ -253,6 +255,7 @@ struct BiasParams {
   float* out; const float* abs; int64_t head_stride, row_stride; const float* dense_add;
   int H, Tq, Tk, num_blocks;
   sgf_relblock blk[2];
+  __half* out16;
 };
 __global__ void __launch_bounds__(256) build_attn_bias_kernel(const BiasParams p) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -269,7 +272,12 @@ __global__ void __launch_bounds__(256) build_attn_bias_kernel(const BiasParams p
     float v = p.abs[h * p.head_stride + off];
     if (p.dense_add) v += p.dense_add[h * p.head_stride + off];
     if (t) v += t[h];
-    p.out[h * p.head_stride + off] = v;
+    if (p.out16) {  // the attention kernels read fp16; an fp32 copy, when asked for, holds exactly the same values
+      const __half hv = __float2half_rn(v);
+      p.out16[h * p.head_stride + off] = hv;
+      v = __half2float(hv);
+    }
+    if (p.out) p.out[h * p.head_stride + off] = v;
   }
 }
 
@@ -529,10 +537,11 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
 }
 
 extern "C" int sgf_build_attn_bias(const sgf_bias_args* a, void* stream) {
-  SGF_REQUIRE(a != nullptr && a->out && a->abs, "build_attn_bias: null pointer");
+  SGF_REQUIRE(a != nullptr && (a->out || a->out_f16) && a->abs, "build_attn_bias: null pointer");
   SGF_REQUIRE(a->H > 0 && a->Tq > 0 && a->Tk > 0 && a->row_stride >= a->Tk, "build_attn_bias: bad shape");
   SGF_REQUIRE(a->num_blocks >= 0 && a->num_blocks <= 2, "build_attn_bias: at most 2 blocks");
-  BiasParams p{a->out, a->abs, a->head_stride, a->row_stride, a->dense_add, a->H, a->Tq, a->Tk, a->num_blocks, {}};
+  BiasParams p{a->out, a->abs, a->head_stride, a->row_stride, a->dense_add, a->H, a->Tq, a->Tk, a->num_blocks, {},
+               reinterpret_cast<__half*>(a->out_f16)};
   for (int b = 0; b < a->num_blocks; ++b) {
     const sgf_relblock& k = a->blocks[b];
     SGF_REQUIRE(k.bucket && k.ids && k.table && k.lo >= 0 && k.hi > k.lo && k.hi <= a->Tq && k.hi <= a->Tk,

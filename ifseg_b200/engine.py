@@ -10,7 +10,7 @@ Data layout in HBM
   * the stem runs NHWC bf16; FrozenBatchNorm is folded to a per-channel (scale, bias) applied in
     the convolution epilogue together with ReLU and the residual add;
   * the additive attention bias is batch-invariant and parameter-only: it is built once per
-    forward as fp32 [H, Tq, Tk_pad] per layer (abs-pos q_pos k_pos^T by a head-batched GEMM +
+    forward as fp16 [H, Tq, Tk_pad] per layer (abs-pos q_pos k_pos^T by a head-batched GEMM +
     rel-pos table lookups), never per batch element and never through clone/cat/interpolate
     chains (those are 55-60% of the reference's forward time).
 
@@ -289,7 +289,7 @@ class SegOFAEngine:
         for l in range(cfg.enc_layers):
             blocks = [(self.image_rp_bucket, ids, self.enc_img_rel[l], 0, P),
                       (self.token_rp_bucket, tok_ids, self.enc_tok_rel[l], P, T)]
-            biases.append(ops.build_attn_bias(absb, T, blocks))
+            biases.append(ops.build_attn_bias(absb, T, blocks, f16=True))  # fp16: what the attention kernel streams
         res = (biases, pos)
         if self.cache_position_bias:
             self._bias_cache[key] = res
@@ -311,8 +311,9 @@ class SegOFAEngine:
         self_abs = self._abs_bias(tgt_pos, tgt_pos, self.w_self_pq, self.b_self_pq, self.w_self_pk, self.b_self_pk)
         cross_abs = self._abs_bias(tgt_pos, enc_pos, self.w_cross_pq, self.b_cross_pq, self.w_cross_pk, self.b_cross_pk)
         seg_ids = self._cached(("arange", Td), lambda: torch.arange(Td))
-        self_biases = [ops.build_attn_bias(self_abs, Td, [(self.seg_rp_bucket, seg_ids, self.dec_seg_rel[l], 0, Td)])
+        self_biases = [ops.build_attn_bias(self_abs, Td, [(self.seg_rp_bucket, seg_ids, self.dec_seg_rel[l], 0, Td)], f16=True)
                        for l in range(cfg.dec_layers)]
+        cross_abs = ops.build_attn_bias(cross_abs, enc_pos.shape[0], (), f16=True)
         res = (self_biases, cross_abs)
         if self.cache_position_bias:
             self._bias_cache[key] = res

@@ -229,16 +229,24 @@ def row_layernorm(x, *, rows=None, D=None, ldx=None, gather_idx=None, pre_add=No
         _lib.check(lib.sgf_row_layernorm(C.byref(args), _stream()), "sgf_row_layernorm")
 
 
-def build_attn_bias(abs_bias, Tk, blocks=(), out=None, dense_add=None):
+def build_attn_bias(abs_bias, Tk, blocks=(), out=None, dense_add=None, f16=False, keep_f32=False):
     """out[h,i,j] = abs[h,i,j] (+ dense_add) + rel-pos lookups.  abs_bias fp32 [H,Tq,row_stride>=Tk];
-    blocks: iterable of (bucket int64 2-D, ids int64 [hi-lo], table fp32 [num_rel,H], lo, hi)."""
+    blocks: iterable of (bucket int64 2-D, ids int64 [hi-lo], table fp32 [num_rel,H], lo, hi).
+    f16=True returns the fp16 tensor the attention kernel reads (zero padding columns); with keep_f32 also the fp32
+    tensor holding exactly the same values (for the adjoint kernels): (b16, b32)."""
     lib = _lib.load()
     _req(abs_bias, torch.float32, "abs_bias")
-    out = torch.empty_like(abs_bias) if out is None else out
-    assert out.stride() == abs_bias.stride() and abs_bias.stride(2) == 1
+    out16 = torch.zeros(abs_bias.shape, dtype=torch.float16, device=abs_bias.device) if f16 else None
+    if f16 and not keep_f32:
+        out = None
+    else:
+        out = torch.empty_like(abs_bias) if out is None else out
+        assert out.stride() == abs_bias.stride()
+    assert abs_bias.stride(2) == 1
     H, Tq, _ = abs_bias.shape
     args = _lib.BiasArgs()
-    args.out, args.abs = out.data_ptr(), abs_bias.data_ptr()
+    args.out, args.abs = (out.data_ptr() if out is not None else None), abs_bias.data_ptr()
+    args.out_f16 = out16.data_ptr() if out16 is not None else None
     args.head_stride, args.row_stride = abs_bias.stride(0), abs_bias.stride(1)
     args.dense_add = dense_add.data_ptr() if dense_add is not None else None
     args.H, args.Tq, args.Tk, args.num_blocks = H, Tq, Tk, len(blocks)
@@ -250,6 +258,8 @@ def build_attn_bias(abs_bias, Tk, blocks=(), out=None, dense_add=None):
         args.blocks[i] = _lib.RelBlock(bucket.data_ptr(), bucket.stride(0), ids.data_ptr(), table.data_ptr(), lo, hi)
     with _timed("attn_bias", nbytes=8.0 * H * Tq * Tk):
         _lib.check(lib.sgf_build_attn_bias(C.byref(args), _stream()), "sgf_build_attn_bias")
+    if f16:
+        return (out16, out) if keep_f32 else out16
     return out
 
 
@@ -260,7 +270,7 @@ def attention(q, k, v, out, *, B, H, Tq, Tk, q_strides, k_strides, v_strides, o_
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         _req(t, torch.bfloat16, n)
     if bias is not None:
-        _req(bias, torch.float32, "bias")
+        _req(bias, torch.float16, "bias")
     args = _lib.AttentionArgs(
         _p(q), q_strides[0], q_strides[1], _p(k), k_strides[0], k_strides[1], _p(v), v_strides[0], v_strides[1],
         _p(out), o_strides[0], o_strides[1],

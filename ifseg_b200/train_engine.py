@@ -434,7 +434,7 @@ class SegOFATrainEngine:
         enc_biases = []
         for l in range(cfg.enc_layers):
             blocks = [(self.image_rp_bucket, ids, self.rel_img[l][0], 0, P), (self.token_rp_bucket, tok_ids, self.rel_tok[l][0], P, T)]
-            enc_biases.append(ops.build_attn_bias(absb, T, blocks))
+            enc_biases.append(ops.build_attn_bias(absb, T, blocks, f16=True, keep_f32=True))
         tgt_pos = torch.empty((Td, D), dtype=_BF16, device=dev)
         ops.row_layernorm(self.tab_seg_pos[0], rows=Td, ln2=self.ln_seg_pos[:2], out2=tgt_pos)
         spq = ops.gemm(tgt_pos, self.self_pos_q.w16, bias=self.self_pos_q.b32, alpha=sc, alpha_cols=D)
@@ -443,9 +443,13 @@ class SegOFATrainEngine:
         cpk = ops.gemm(pos, self.cross_pos_k.w16, bias=self.cross_pos_k.b32)
         self_abs = self._abs_bias(spq, spk, Td, Td)
         cross_abs = self._abs_bias(cpq, cpk, Td, T)
-        self_biases = [ops.build_attn_bias(self_abs, Td, [(self.seg_rp_bucket, seg_ids, self.rel_seg[l][0], 0, Td)])
-                       for l in range(cfg.dec_layers)]
-        return dict(enc_biases=enc_biases, self_biases=self_biases, cross_abs=cross_abs, pos=pos, pq=pq, pk=pk,
+        self_biases = [ops.build_attn_bias(self_abs, Td, [(self.seg_rp_bucket, seg_ids, self.rel_seg[l][0], 0, Td)],
+                                           f16=True, keep_f32=True) for l in range(cfg.dec_layers)]
+        cross16, cross32 = ops.build_attn_bias(cross_abs, T, (), f16=True, keep_f32=True)
+        # (fp16 for the forward kernel, fp32 with bit-identical values for the adjoint kernels)
+        return dict(enc_biases=[b[0] for b in enc_biases], self_biases=[b[0] for b in self_biases], cross_abs=cross16,
+                    enc_biases32=[b[1] for b in enc_biases], self_biases32=[b[1] for b in self_biases], cross_abs32=cross32,
+                    pos=pos, pq=pq, pk=pk,
                     tgt_pos=tgt_pos, spq=spq, spk=spk, cpq=cpq, cpk=cpk, ids=ids, tok_ids=tok_ids, seg_ids=seg_ids)
 
     def _abs_bias_bwd(self, dabs, pq, pk, Lq: _Dense, Lk: _Dense, xq, xk, Tq, Tk, dxq, dxk):
@@ -663,7 +667,8 @@ class SegOFATrainEngine:
         bag, tok_idx, x_emb, xd_emb, enc_out, kv_all, feats = (c[k] for k in (
             "bag", "tok_idx", "x_emb", "xd_emb", "enc_out", "kv_all", "feats"))
         dec_in_idx, bos, enc_saved, dec_saved = c["dec_in_idx"], c["bos"], c["enc_saved"], c["dec_saved"]
-        enc_biases, self_biases, cross_abs = c["enc_biases"], c["self_biases"], c["cross_abs"]
+        pb = c["pb"]
+        enc_biases, self_biases, cross_abs = pb["enc_biases32"], pb["self_biases32"], pb["cross_abs32"]
         nL = len(self.dec_layers)
         s3, sd3 = (3 * D, T * 3 * D), (3 * D, Td * 3 * D)
         kvs = (nL * 2 * D, T * nL * 2 * D)

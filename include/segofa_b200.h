@@ -173,6 +173,9 @@ typedef struct {
   const float* dense_add;                                                /* optional */
   int32_t H, Tq, Tk;
   int32_t num_blocks; sgf_relblock blocks[2];
+  void* out_f16; /* optional fp16 [H,Tq,row_stride] (same strides): what sgf_attention_bf16 reads.  When given, `out` may
+                    be NULL, and if not NULL it receives float(half(value)) -- bit-identical to the fp16 copy (the
+                    adjoint kernels read fp32) */
 } sgf_bias_args;
 int sgf_build_attn_bias(const sgf_bias_args* args, void* stream);
 
@@ -182,7 +185,8 @@ int sgf_build_attn_bias(const sgf_bias_args* args, void* stream);
  *   row-owning threads, probabilities re-staged to shared memory as the bf16 A operand of PV.
  *   q is expected pre-scaled (the QKV GEMM epilogue applies (2*d_h)^-1/2 to the q columns).
  *   Element (b,t,h,d) of q/k/v/out lives at base + b*batch_stride + t*row_stride + h*64 + d.
- *   bias fp32 [H,Tq,Tk] (batch-invariant) or NULL; key_padding_mask uint8 [B,Tk] (1 = masked) or
+ *   bias FP16 [H,Tq,row_stride] (batch-invariant; row stride a multiple of 8, streamed through double-buffered TMA
+ *   tiles: half the L2 traffic of fp32 and room for a deeper K/V prefetch) or NULL; key_padding_mask uint8 [B,Tk] (1 = masked) or
  *   NULL; causal != 0 masks j > i (decoder_module.py:878-890).
  * Replaces unify_multihead_attention.py:459-512 (bmm, bias add, masks, fp32 softmax, bmm,
  * c_attn scale).
@@ -192,7 +196,7 @@ typedef struct {
   const void* k; int64_t k_row_stride; int64_t k_batch_stride;
   const void* v; int64_t v_row_stride; int64_t v_batch_stride;
   void* out; int64_t o_row_stride; int64_t o_batch_stride;
-  const float* bias; int64_t bias_head_stride; int64_t bias_row_stride;
+  const void* bias; int64_t bias_head_stride; int64_t bias_row_stride; /* fp16, strides in elements */
   const float* head_scale;
   const uint8_t* key_padding_mask;
   int32_t B, H, Tq, Tk, causal;

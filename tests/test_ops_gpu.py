@@ -197,6 +197,7 @@ def test_attention(ops, B, H, Tq, Tk, causal, use_bias, use_kpm):
     if use_bias:
         bias = torch.zeros(H, Tq, Tkp, device="cuda")
         bias[:, :, :Tk] = torch.randn(H, Tq, Tk, device="cuda", generator=g)
+        bias = bias.half()  # the kernel streams the bias as fp16
     kpm = None
     if use_kpm:
         kpm = torch.zeros(B, Tk, dtype=torch.uint8, device="cuda")
@@ -207,7 +208,7 @@ def test_attention(ops, B, H, Tq, Tk, causal, use_bias, use_kpm):
     ops.attention(q, k, v, out, B=B, H=H, Tq=Tq, Tk=Tk, q_strides=(D, Tq * D), k_strides=(D, Tk * D),
                   v_strides=(D, Tk * D), o_strides=(D, Tq * D), bias=bias, head_scale=hs, key_padding_mask=kpm,
                   causal=causal)
-    ref = _attn_ref(q, k, v, bias, causal, kpm, hs).reshape(B, Tq, D)
+    ref = _attn_ref(q, k, v, bias.float() if bias is not None else None, causal, kpm, hs).reshape(B, Tq, D)
     err = _rel(out, ref)
     assert err < 8e-3, err
 
@@ -267,6 +268,10 @@ def test_build_attn_bias(ops):
     ref[:, 0:64, 0:64] += tab_a[bucket[ids_a][:, ids_a]].permute(2, 0, 1)
     ref[:, 74:100, 74:100] += tab_b[bucket[ids_b][:, ids_b]].permute(2, 0, 1)
     assert torch.allclose(out[:, :, :T], ref, atol=1e-6)
+    b16, b32 = ops.build_attn_bias(absb, T, [(bucket, ids_a, tab_a, 0, 64), (bucket, ids_b, tab_b, 74, 100)],
+                                   dense_add=dense, f16=True, keep_f32=True)
+    assert b16.dtype == torch.float16 and torch.equal(b16[:, :, :T], ref.half()) and (b16[:, :, T:] == 0).all()
+    assert torch.equal(b32[:, :, :T], b16[:, :, :T].float())  # the adjoint kernels see exactly the forward's values
 
 
 def test_embedding_bag_mean(ops):
@@ -345,6 +350,7 @@ def test_attention_full_size_repeatable(ops):
     qkv = (torch.randn(B, T, 3 * D, device="cuda", generator=g) * 0.5).bfloat16()
     bias = torch.zeros(H, T, 960, device="cuda")
     bias[:, :, :T] = torch.randn(H, T, T, device="cuda", generator=g)
+    bias = bias.half()
     hs = torch.rand(H, device="cuda", generator=g) + 0.5
     outs = []
     for _ in range(6):
@@ -357,7 +363,7 @@ def test_attention_full_size_repeatable(ops):
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
     q, k, v = (t.reshape(B, T, H, dh) for t in qkv.split(D, dim=-1))
-    ref = _attn_ref(q[:2], k[:2], v[:2], bias, False, None, hs).reshape(2, T, D)
+    ref = _attn_ref(q[:2], k[:2], v[:2], bias.float(), False, None, hs).reshape(2, T, D)
     assert _rel(outs[0][:2], ref) < 8e-3
 
 

@@ -249,6 +249,7 @@ def test_attention_backward(ops, B, H, Tq, Tk, causal, use_bias, use_kpm):
     if use_bias:
         bias = torch.zeros(H, Tq, Tkp, device="cuda")
         bias[:, :, :Tk] = torch.randn(H, Tq, Tk, device="cuda", generator=g)
+        bias = bias.half().float()  # fp16-representable: the forward streams fp16, the adjoint kernels read fp32
     kpm = None
     if use_kpm:
         kpm = torch.zeros(B, Tk, dtype=torch.uint8, device="cuda")
@@ -264,8 +265,8 @@ def test_attention_backward(ops, B, H, Tq, Tk, causal, use_bias, use_kpm):
     out = torch.empty(B, Tq, D, device="cuda", dtype=torch.bfloat16)
     lse = torch.empty(B, H, Tq, device="cuda")
     ops.attention(q, k, v, out, B=B, H=H, Tq=Tq, Tk=Tk, q_strides=(D, Tq * D), k_strides=(D, Tk * D),
-                  v_strides=(D, Tk * D), o_strides=(D, Tq * D), bias=bias, head_scale=hs, key_padding_mask=kpm,
-                  causal=causal, lse=lse)
+                  v_strides=(D, Tk * D), o_strides=(D, Tq * D), bias=bias.half() if bias is not None else None,
+                  head_scale=hs, key_padding_mask=kpm, causal=causal, lse=lse)
     assert _rel(out, ref) < 8e-3
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     delta = torch.empty(B, H, Tq, device="cuda")

@@ -53,7 +53,7 @@ def main():
         k = torch.randn(B, Tk, D, device="cuda").bfloat16()
         v = torch.randn(B, Tk, D, device="cuda").bfloat16()
         Tkp = (Tk + 63) // 64 * 64
-        bias = torch.randn(H, Tq, Tkp, device="cuda")
+        bias = torch.randn(H, Tq, Tkp, device="cuda").half()
         out = torch.empty(B, Tq, D, device="cuda", dtype=torch.bfloat16)
         f = lambda: ops.attention(q, k, v, out, B=B, H=H, Tq=Tq, Tk=Tk, q_strides=(D, Tq * D), k_strides=(D, Tk * D),
                                   v_strides=(D, Tk * D), o_strides=(D, Tq * D), bias=bias, causal=causal)
