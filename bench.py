@@ -38,7 +38,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOPS_PER_IMG = {2: 286.8e9, 4: 364.6e9, 3: 1061.2e9}  # SURVEY.md s8d (forward / train step, algorithmic)
+FLOPS_PER_IMG = {2: 286.8e9, 4: 364.6e9, 3: 1061.2e9, 5: 6465.3e9}  # SURVEY.md s8d (forward / train step, algorithmic)
 CONFIGS = {
     # id: (arch, image, classes, batch, description)
     1: ("segofa_base", 128, 15, 1, "OFA-Base segofa 128x128, 15 COCO-unseen classes, batch 1"),
@@ -46,8 +46,10 @@ CONFIGS = {
     4: ("segofa_base", 512, 171, 8, "OFA-Base segofa 512x512 inference, 171 COCO-Stuff classes, batch 8"),
     3: ("segofa_base", 480, 150, 8, "OFA-Base segofa 480x480 image-free finetune step, 150 ADE classes, per-GPU batch 8 "
                                     "(aux fwd+bwd + no-grad real-image fwd + metrics + grad all-reduce + Adam)"),
+    5: ("segofa_large", 640, 150, 4, "OFA-Large segofa 640x640 image-free finetune step, 150 ADE classes, per-GPU batch 4 "
+                                     "(aux fwd+bwd + no-grad real-image fwd + metrics + grad all-reduce + Adam)"),
 }
-TRAIN_CONFIGS = {3}
+TRAIN_CONFIGS = {3, 5}
 
 
 def load_peaks():

@@ -255,10 +255,12 @@ class SegOFAEngine:
         D, H, dh = cfg.embed_dim, cfg.heads, cfg.head_dim
         Tq, Tk = pos_q_in.shape[0], pos_k_in.shape[0]
         pq = ops.gemm(pos_q_in, wq, bias=bq, alpha=cfg.pos_scaling, alpha_cols=D)
-        pk = ops.gemm(pos_k_in, wk, bias=bk)
         Tkp = _pad64(Tk)
-        out = torch.zeros((H, Tq, Tkp), dtype=torch.float32, device=self.device)
-        ops.gemm(pq, pk, out, M=Tq, N=Tk, K=dh, batch=H, lda=D, ldb=D, a_batch_stride=dh, b_batch_stride=dh,
+        pk = torch.zeros((Tkp, D), dtype=_BF16, device=self.device)  # zero rows beyond Tk: the GEMM below runs at width Tkp
+        ops.gemm(pos_k_in, wk, pk[:Tk], bias=bk)
+        out = torch.empty((H, Tq, Tkp), dtype=torch.float32, device=self.device)
+        # N = padded width: key rows >= Tk are TMA zero-fill -> zero padding columns, vectorised epilogue (N % 32 == 0)
+        ops.gemm(pq, pk, out, M=Tq, N=Tkp, K=dh, batch=H, lda=D, ldb=D, a_batch_stride=dh, b_batch_stride=dh,
                  ldc=Tkp, c_batch_stride=Tq * Tkp)
         return out
 

@@ -376,7 +376,7 @@ class SegOFATrainEngine:
         self._fresh = True
         if self.inf is None:
             self.inf = SegOFAEngine(self.model, live=self)
-            self.inf.cache_position_bias = False  # the position parameters are trained: rebuilt on every call
+            self.inf.cache_position_bias = False  # the position parameters are trained: never reuse across steps
 
     # ------------------------------------------------------------------------------------
     # helpers
@@ -406,10 +406,21 @@ class SegOFATrainEngine:
         cfg = self.cfg
         D, H, dh = cfg.embed_dim, cfg.heads, cfg.head_dim
         Tkp = (Tk + 63) // 64 * 64
-        out = torch.zeros((H, Tq, Tkp), dtype=torch.float32, device=self.device)
-        ops.gemm(pq, pk, out, M=Tq, N=Tk, K=dh, batch=H, lda=D, ldb=D, a_batch_stride=dh, b_batch_stride=dh,
+        out = torch.empty((H, Tq, Tkp), dtype=torch.float32, device=self.device)
+        # N = the padded width: key rows >= Tk are TMA zero-fill, so the padding columns come out 0 and the vectorised
+        # (N % 32 == 0) epilogue applies
+        assert pk.shape[0] >= Tkp  # _key_proj pads the key-side projection with zero rows
+        ops.gemm(pq, pk, out, M=Tq, N=Tkp, K=dh, batch=H, lda=D, ldb=D, a_batch_stride=dh, b_batch_stride=dh,
                  ldc=Tkp, c_batch_stride=Tq * Tkp)
         return out
+
+    def _key_proj(self, x, L: _Dense):
+        """key-side position projection [Tk, D] inside a zero buffer of pad64(Tk) rows (so that the abs-bias GEMM can run
+        at the padded width); returns (padded buffer, [Tk, D] view)."""
+        Tk = x.shape[0]
+        full = torch.zeros(((Tk + 63) // 64 * 64, L.N), dtype=_BF16, device=self.device)
+        ops.gemm(x, L.w16, full[:Tk], bias=L.b32)
+        return full, full[:Tk]
 
     def _position_bias(self, h, w, T_txt):
         """Additive attention biases of both stacks from the CURRENT position parameters, keeping what their adjoint
@@ -429,8 +440,8 @@ class SegOFATrainEngine:
         ops.row_layernorm(self.tab_pos[0], rows=T_txt, ln2=self.ln_pos[:2], out2=pos[P:])
         sc = cfg.pos_scaling
         pq = ops.gemm(pos, self.pos_q.w16, bias=self.pos_q.b32, alpha=sc, alpha_cols=D)
-        pk = ops.gemm(pos, self.pos_k.w16, bias=self.pos_k.b32)
-        absb = self._abs_bias(pq, pk, T, T)
+        pk_full, pk = self._key_proj(pos, self.pos_k)
+        absb = self._abs_bias(pq, pk_full, T, T)
         enc_biases = []
         for l in range(cfg.enc_layers):
             blocks = [(self.image_rp_bucket, ids, self.rel_img[l][0], 0, P), (self.token_rp_bucket, tok_ids, self.rel_tok[l][0], P, T)]
@@ -438,14 +449,19 @@ class SegOFATrainEngine:
         tgt_pos = torch.empty((Td, D), dtype=_BF16, device=dev)
         ops.row_layernorm(self.tab_seg_pos[0], rows=Td, ln2=self.ln_seg_pos[:2], out2=tgt_pos)
         spq = ops.gemm(tgt_pos, self.self_pos_q.w16, bias=self.self_pos_q.b32, alpha=sc, alpha_cols=D)
-        spk = ops.gemm(tgt_pos, self.self_pos_k.w16, bias=self.self_pos_k.b32)
+        spk_full, spk = self._key_proj(tgt_pos, self.self_pos_k)
         cpq = ops.gemm(tgt_pos, self.cross_pos_q.w16, bias=self.cross_pos_q.b32, alpha=sc, alpha_cols=D)
-        cpk = ops.gemm(pos, self.cross_pos_k.w16, bias=self.cross_pos_k.b32)
-        self_abs = self._abs_bias(spq, spk, Td, Td)
-        cross_abs = self._abs_bias(cpq, cpk, Td, T)
+        cpk_full, cpk = self._key_proj(pos, self.cross_pos_k)
+        self_abs = self._abs_bias(spq, spk_full, Td, Td)
+        cross_abs = self._abs_bias(cpq, cpk_full, Td, T)
         self_biases = [ops.build_attn_bias(self_abs, Td, [(self.seg_rp_bucket, seg_ids, self.rel_seg[l][0], 0, Td)],
                                            f16=True, keep_f32=True) for l in range(cfg.dec_layers)]
         cross16, cross32 = ops.build_attn_bias(cross_abs, T, (), f16=True, keep_f32=True)
+        # the no-grad real-image pass of the same step (seg_criterion.py:185) sees the same grid and prompt: hand it
+        # these biases instead of letting the inference engine rebuild them
+        self.inf.cache_position_bias = True
+        self.inf._bias_cache = {("enc", h, w, T_txt, False): ([b[0] for b in enc_biases], pos),
+                                ("dec", h, w, T): ([b[0] for b in self_biases], cross16)}
         # (fp16 for the forward kernel, fp32 with bit-identical values for the adjoint kernels)
         return dict(enc_biases=[b[0] for b in enc_biases], self_biases=[b[0] for b in self_biases], cross_abs=cross16,
                     enc_biases32=[b[1] for b in enc_biases], self_biases32=[b[1] for b in self_biases], cross_abs32=cross32,
