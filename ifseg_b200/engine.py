@@ -24,6 +24,7 @@ import os
 from typing import Dict, Optional
 
 import torch
+import torch.nn.functional as F
 
 from . import ops
 from .config import SegOFAConfig
@@ -268,6 +269,32 @@ class SegOFAEngine:
         oh = self.cfg.orig_patch_image_size // 16
         return (h, w) != (oh, oh)
 
+    # General patch grids (validation keeps the image aspect ratio).  The relative-position bias of the image block is
+    # defined on the orig grid and resized with two separable bilinear passes; this is a batch-invariant, parameter-only
+    # precompute (cached per grid like every other bias), so it is expressed with torch on the device and handed to
+    # sgf_build_attn_bias as `dense_add` -- the per-image hot path is unchanged.
+    def _interp_image_rel(self, table, oh, h, w):
+        """encoder_module.py:321-331, 782-808 -> fp32 [H, h*w, h*w]: key axis first, then query axis."""
+        H = self.cfg.heads
+        oids = self._image_position_ids(oh, oh)
+        v = table[self.image_rp_bucket[oids][:, oids]].permute(2, 0, 1)            # [H, q(oh*oh), k(oh*oh)]
+        v = v.reshape(H, oh * oh, oh, oh).permute(1, 0, 2, 3)                       # [(q), H, kh, kw]
+        v = F.interpolate(v, size=(h, w), mode="bilinear")                          # keys -> (h, w)
+        v = v.reshape(oh, oh, H, h * w).permute(3, 2, 0, 1)                         # [(k'), H, qh, qw]
+        v = F.interpolate(v, size=(h, w), mode="bilinear")                          # queries -> (h, w)
+        return v.reshape(h * w, H, h * w).permute(1, 2, 0)                          # [H, q', k']
+
+    def _interp_seg_rel(self, table, sb, h, w):
+        """decoder_module.py:601-625 -> fp32 [H, Td, Td]: query axis first, then key axis; bos row/column exempt."""
+        H = self.cfg.heads
+        n, Td = sb * sb, h * w + 1
+        v = table[self.seg_rp_bucket].permute(2, 0, 1)                              # [H, q(n+1), k(n+1)]
+        t = v.permute(2, 0, 1)                                                      # [k, H, q]
+        seg = F.interpolate(t[..., 1:].reshape(n + 1, H, sb, sb), size=(h, w), mode="bilinear").reshape(n + 1, H, h * w)
+        t = torch.cat([t[..., :1], seg], dim=-1).permute(2, 1, 0)                   # [q'(Td), H, k(n+1)]
+        seg = F.interpolate(t[..., 1:].reshape(Td, H, sb, sb), size=(h, w), mode="bilinear").reshape(Td, H, h * w)
+        return torch.cat([t[..., :1], seg], dim=-1).permute(1, 0, 2)               # [H, q', k'(Td)]
+
     def _encoder_bias(self, h, w, T_txt, artificial):
         """list of fp32 [H,T_e,pad64(T_e)] per layer + the post-LN position embeddings [T_e,D] bf16."""
         key = ("enc", h, w, T_txt, artificial)
@@ -277,21 +304,33 @@ class SegOFAEngine:
         P, D = h * w, cfg.embed_dim
         T = P + T_txt
         oh = cfg.orig_patch_image_size // 16
-        if P > oh * oh or (not artificial and self._interp_needed(h, w)):
-            raise NotImplementedError(
-                f"segofa_b200: patch grid {h}x{w} differs from the orig_patch_image_size grid {oh}x{oh}; the "
-                "interpolated position tables (encoder_module.py:358-370, 802-808) are a 'next' row (SURVEY.md s8f-2)")
-        ids = self._image_position_ids(h, w)
+        if artificial and P > oh * oh:
+            raise NotImplementedError("segofa_b200: the image-free branch runs on the patch_image_size grid only")
+        interp = (not artificial) and self._interp_needed(h, w)  # validation keeps the aspect ratio: general grids
         pos = torch.empty((T, D), dtype=_BF16, device=self.device)
-        ops.row_layernorm(self.enc_img_pos_table, rows=P, gather_idx=ids, ln2=self.ln_img_pos, out2=pos)
+        if P > oh * oh:
+            # encoder_module.py:358-370: the orig-grid absolute position embeddings, bilinearly resized to (h, w)
+            oids = self._image_position_ids(oh, oh)
+            old = self.enc_img_pos_table[oids].reshape(1, oh, oh, D).permute(0, 3, 1, 2)
+            new = F.interpolate(old, size=(h, w), mode="bilinear").permute(0, 2, 3, 1).reshape(P, D).contiguous()
+            ops.row_layernorm(new, rows=P, ln2=self.ln_img_pos, out2=pos)
+        else:
+            ops.row_layernorm(self.enc_img_pos_table, rows=P, gather_idx=self._image_position_ids(h, w),
+                              ln2=self.ln_img_pos, out2=pos)
         ops.row_layernorm(self.enc_pos_table, rows=T_txt, ln2=self.ln_pos, out2=pos[P:])
         absb = self._abs_bias(pos, pos, self.w_pos_q, self.b_pos_q, self.w_pos_k, self.b_pos_k)
         tok_ids = self._cached(("arange", T_txt), lambda: torch.arange(T_txt))
+        ids = self._image_position_ids(h, w) if not interp else None
         biases = []
         for l in range(cfg.enc_layers):
-            blocks = [(self.image_rp_bucket, ids, self.enc_img_rel[l], 0, P),
-                      (self.token_rp_bucket, tok_ids, self.enc_tok_rel[l], P, T)]
-            biases.append(ops.build_attn_bias(absb, T, blocks, f16=True))  # fp16: what the attention kernel streams
+            tok_block = (self.token_rp_bucket, tok_ids, self.enc_tok_rel[l], P, T)
+            if not interp:
+                blocks = [(self.image_rp_bucket, ids, self.enc_img_rel[l], 0, P), tok_block]
+                biases.append(ops.build_attn_bias(absb, T, blocks, f16=True))  # fp16: what the attention kernel streams
+            else:
+                dense = torch.zeros_like(absb)
+                dense[:, :P, :P] = self._interp_image_rel(self.enc_img_rel[l], oh, h, w)
+                biases.append(ops.build_attn_bias(absb, T, [tok_block], dense_add=dense, f16=True))
         res = (biases, pos)
         if self.cache_position_bias:
             self._bias_cache[key] = res
@@ -303,18 +342,29 @@ class SegOFAEngine:
             return self._bias_cache[key]
         cfg = self.cfg
         sb = self.seg_bucket_size
-        if (h, w) != (sb, sb):
-            raise NotImplementedError(
-                f"segofa_b200: patch grid {h}x{w} differs from the seg_bucket grid {sb}x{sb}; interpolated seg "
-                "position tables (decoder_module.py:541-548, 603-625) are a 'next' row (SURVEY.md s8f-2)")
+        interp = (h, w) != (sb, sb)
         Td, D = h * w + 1, cfg.embed_dim
         tgt_pos = torch.empty((Td, D), dtype=_BF16, device=self.device)
-        ops.row_layernorm(self.seg_pos_table, rows=Td, ln2=self.ln_seg_pos, out2=tgt_pos)  # ids 0..n == table rows
+        if not interp:
+            ops.row_layernorm(self.seg_pos_table, rows=Td, ln2=self.ln_seg_pos, out2=tgt_pos)  # ids 0..n == table rows
+        else:
+            # decoder_module.py:541-550: the seg_bucket-grid embeddings resized to (h, w); slot 0 (bos) carried through
+            old = self.seg_pos_table[1: sb * sb + 1].reshape(1, sb, sb, D).permute(0, 3, 1, 2)
+            new = F.interpolate(old, size=(h, w), mode="bilinear").permute(0, 2, 3, 1).reshape(h * w, D)
+            ops.row_layernorm(torch.cat([self.seg_pos_table[0:1], new], 0).contiguous(), rows=Td, ln2=self.ln_seg_pos,
+                              out2=tgt_pos)
         self_abs = self._abs_bias(tgt_pos, tgt_pos, self.w_self_pq, self.b_self_pq, self.w_self_pk, self.b_self_pk)
         cross_abs = self._abs_bias(tgt_pos, enc_pos, self.w_cross_pq, self.b_cross_pq, self.w_cross_pk, self.b_cross_pk)
         seg_ids = self._cached(("arange", Td), lambda: torch.arange(Td))
-        self_biases = [ops.build_attn_bias(self_abs, Td, [(self.seg_rp_bucket, seg_ids, self.dec_seg_rel[l], 0, Td)], f16=True)
-                       for l in range(cfg.dec_layers)]
+        if not interp:
+            self_biases = [ops.build_attn_bias(self_abs, Td, [(self.seg_rp_bucket, seg_ids, self.dec_seg_rel[l], 0, Td)],
+                                               f16=True) for l in range(cfg.dec_layers)]
+        else:
+            self_biases = []
+            for l in range(cfg.dec_layers):
+                dense = torch.zeros_like(self_abs)
+                dense[:, :, :Td] = self._interp_seg_rel(self.dec_seg_rel[l], sb, h, w)
+                self_biases.append(ops.build_attn_bias(self_abs, Td, (), dense_add=dense, f16=True))
         cross_abs = ops.build_attn_bias(cross_abs, enc_pos.shape[0], (), f16=True)
         res = (self_biases, cross_abs)
         if self.cache_position_bias:

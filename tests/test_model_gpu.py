@@ -232,3 +232,29 @@ def test_serving_session_matches_eager(case15):
             ref = eng.predict_mask(x, extra["encoder_returns"]["image_embed_shape"][0], (S, S))
         assert torch.equal(m, ref.cpu())
     assert torch.equal(sess.infer(batches[0]), outs[0])
+
+
+@pytest.mark.parametrize("Hi,Wi", [(128, 192), (96, 160), (160, 128)])
+def test_general_patch_grids_vs_oracle(cuda_device, Hi, Wi):
+    """Validation keeps the image aspect ratio: patch grids that differ from the orig / seg_bucket
+    grid go through the interpolated position tables (encoder_module.py:358-370, 782-808; decoder_module.py:541-550,
+    601-625).  8x12 (more patches than the 8x8 orig grid), 6x10 (fewer, other shape), 10x8."""
+    from oracle import restated as R
+    from ifseg_b200.synthetic import synthetic_inputs
+
+    model, sd = build_cuda_model("segofa_base", 15, 128, seed=3)
+    inp = synthetic_inputs(model.cfg, 2, 128, seed=5)
+    g = torch.Generator().manual_seed(Hi + Wi)
+    images = torch.randn(2, 3, Hi, Wi, generator=g)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        ref, _ = R.segofa_forward(sd, oracle_cfg(model.cfg), inp["src_tokens"], images, inp["patch_masks"])
+        x, extra = model(src_tokens=inp["src_tokens"].cuda(), src_lengths=inp["src_lengths"].cuda(),
+                         prev_output_tokens=inp["prev_output_tokens"].cuda(), patch_images=images.cuda(),
+                         patch_masks=inp["patch_masks"].cuda())
+    hp, wp = extra["encoder_returns"]["image_embed_shape"][0]
+    assert (hp, wp) == (Hi // 16, Wi // 16) and x.shape == ref.shape == (2, hp * wp + 1, 15)
+    err = rel_l2(x, ref)
+    assert err < 1.2e-2, err
+    mask = model.engine().predict_mask(x, (hp, wp), (Hi, Wi))
+    assert torch.equal(mask.cpu().view(2, -1), R.predict_mask(x.cpu(), hp, wp, Hi, Wi))
