@@ -71,48 +71,66 @@ SGF_DEVICE void smem_load8(const uint8_t* row, int dtype, int e, float (&v)[8]) 
 
 __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const RowLnParams p, const int x_row_bytes,
                                                                         const int r_row_bytes, const int s_row_bytes) {
+  // Persistent CTAs; every warp owns one row slot and runs its own two-deep pipeline: while it works on the row of
+  // group g it has the bulk copies of its row of group g + gridDim.x in flight (per-warp mbarriers: no CTA-wide
+  // synchronisation anywhere in the loop).
   pdl_trigger();
   const int kLnRows = blockDim.x >> 5;
   extern __shared__ __align__(128) uint8_t ln_smem[];
-  uint8_t* xbuf = ln_smem;                                   // [kLnRows][x_row_bytes]
-  uint8_t* rbuf = xbuf + kLnRows * x_row_bytes;              // [kLnRows][r_row_bytes]   (residual)
-  uint8_t* sbuf = rbuf + kLnRows * r_row_bytes;              // [kLnRows][s_row_bytes]   (fp32 stash for LN2)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sbuf + kLnRows * s_row_bytes);
+  const int in_bytes = x_row_bytes + r_row_bytes;
+  uint8_t* inbuf = ln_smem;                                              // [2][kLnRows][x | residual]
+  uint8_t* sbuf = inbuf + 2 * kLnRows * in_bytes;                        // [kLnRows][s_row_bytes] (fp32 stash for LN2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbuf + kLnRows * s_row_bytes);  // [2][kLnRows]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int row0 = blockIdx.x * kLnRows;
-  const int nrows = min(kLnRows, p.rows - row0);
   const int xs = p.x_dtype == SGF_F32 ? 4 : 2, rs = p.r_dtype == SGF_F32 ? 4 : 2;
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+  const int ngroups = (p.rows + kLnRows - 1) / kLnRows;
+  if (lane == 0) {
+    mbar_init(&bars[warp], 1);
+    mbar_init(&bars[kLnRows + warp], 1);
     fence_mbar_init();
   }
-  __syncthreads();
+  __syncwarp();
   pdl_wait();
-  const int row = row0 + warp;
-  const bool live = warp < nrows;
-  int64_t dst_row = row;
-  if (p.seg_len > 0) dst_row = static_cast<int64_t>(row / p.seg_len) * p.seg_stride + p.seg_off + row % p.seg_len;
-  if (threadIdx.x == 0) mbar_expect_tx(bar, nrows * (x_row_bytes + r_row_bytes));
-  __syncthreads();  // expect_tx is posted before any complete_tx can arrive
-  if (live && lane == 0) {
-    const int64_t src_row = p.gather_idx ? p.gather_idx[row] : row;
-    bulk_load_1d(xbuf + warp * x_row_bytes, reinterpret_cast<const uint8_t*>(p.x) + src_row * p.ldx * xs, x_row_bytes, bar);
-    if (p.residual)
-      bulk_load_1d(rbuf + warp * r_row_bytes, reinterpret_cast<const uint8_t*>(p.residual) + dst_row * p.ldr * rs,
-                   r_row_bytes, bar);
-  }
-  if (live && p.clear_rowstats && lane < 2) p.clear_rowstats[static_cast<int64_t>(row) * 2 + lane] = 0.f;
-  mbar_wait(bar, 0);
-  if (!live) return;
-
-  const uint8_t* xr = xbuf + warp * x_row_bytes;
-  const uint8_t* rr = rbuf + warp * r_row_bytes;
-  float* sr = reinterpret_cast<float*>(sbuf + warp * s_row_bytes);
-  const bool zero = p.zero_row && p.zero_row[row];
   const float invD = 1.0f / static_cast<float>(p.D);
   const int nchunk = p.D >> 3;
+  const DropCtx drop = make_drop_ctx(p.drop_p, p.droppath_p, p.drop_seed, p.drop_site, p.drop_step, p.rows_per_sample);
+  const bool two_stage = p.out2 && (p.g1 || p.residual || p.pre_add || p.out1 || p.x_act || drop.on);
+  float* sr = reinterpret_cast<float*>(sbuf + warp * s_row_bytes);
+
+  auto dst_of = [&](int row) -> int64_t {
+    return p.seg_len > 0 ? static_cast<int64_t>(row / p.seg_len) * p.seg_stride + p.seg_off + row % p.seg_len : row;
+  };
+  auto issue = [&](int g, int buf) {  // lane 0: bulk copies of this warp's row of group g into buffer `buf`
+    const int row = g * kLnRows + warp;
+    if (row >= p.rows) return;
+    uint8_t* dst = inbuf + (buf * kLnRows + warp) * in_bytes;
+    uint64_t* bar = &bars[buf * kLnRows + warp];
+    mbar_expect_tx(bar, in_bytes);
+    const int64_t src_row = p.gather_idx ? p.gather_idx[row] : row;
+    bulk_load_1d(dst, reinterpret_cast<const uint8_t*>(p.x) + src_row * p.ldx * xs, x_row_bytes, bar);
+    if (p.residual)
+      bulk_load_1d(dst + x_row_bytes, reinterpret_cast<const uint8_t*>(p.residual) + dst_of(row) * p.ldr * rs, r_row_bytes,
+                   bar);
+  };
+  if (lane == 0 && static_cast<int>(blockIdx.x) < ngroups) issue(blockIdx.x, 0);
+
+  int it = 0;
+  for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++it) {
+    const int buf = it & 1;
+    __syncwarp();  // every lane is done with the other buffer (previous group) before lane 0 refills it
+    if (lane == 0 && g + static_cast<int>(gridDim.x) < ngroups) {
+      fence_proxy_async();  // generic-proxy reads of that buffer are ordered before the async-proxy bulk writes
+      issue(g + gridDim.x, buf ^ 1);
+    }
+    const int row = g * kLnRows + warp;
+    if (row >= p.rows) continue;  // (only in the last group)
+    const int64_t dst_row = dst_of(row);
+    if (p.clear_rowstats && lane < 2) p.clear_rowstats[static_cast<int64_t>(row) * 2 + lane] = 0.f;
+    mbar_wait(&bars[buf * kLnRows + warp], (it >> 1) & 1);
+    const uint8_t* xr = inbuf + (buf * kLnRows + warp) * in_bytes;
+    const uint8_t* rr = xr + x_row_bytes;
+    const bool zero = p.zero_row && p.zero_row[row];
 
   // ---- first LayerNorm statistics (over t = x + pre_add) ----
   float mean1 = 0.f, rstd1 = 1.f;
@@ -158,8 +176,6 @@ __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const Ro
     rstd1 = rsqrtf(warp_sum(q) * invD + 1e-5f);
   }
   // ---- v = LN1(t) + residual ; out1 ; stash for LN2 ----
-  const DropCtx drop = make_drop_ctx(p.drop_p, p.droppath_p, p.drop_seed, p.drop_site, p.drop_step, p.rows_per_sample);
-  const bool two_stage = p.out2 && (p.g1 || p.residual || p.pre_add || p.out1 || p.x_act || drop.on);
   float s2 = 0.f;
   if (two_stage || p.out1) {
     for (int c = lane; c < nchunk; c += 32) {
@@ -213,7 +229,7 @@ __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const Ro
       }
     }
   }
-  if (!p.out2) return;
+  if (!p.out2) continue;
   // ---- second LayerNorm (over the stash, or directly over x for the plain x -> LN -> out2 form) ----
   const uint8_t* vrow = two_stage ? reinterpret_cast<const uint8_t*>(sr) : xr;
   const int vdt = two_stage ? SGF_F32 : p.x_dtype;
@@ -246,6 +262,7 @@ __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const Ro
     for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean2) * rstd2 * g[j] + b[j];
     store8(p.out2, SGF_BF16, dst_row * p.ld2 + c * 8, v);
   }
+  }  // persistent loop over row groups
 }
 
 // ----------------------------------------------------------------------------------------
@@ -517,9 +534,11 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
   const bool two_stage = a->out2 && (a->g1 || a->residual || a->pre_add || a->out1 || a->x_act || a->drop_p > 0.f ||
                                      a->droppath_p > 0.f);
   const int s_row_bytes = two_stage ? a->D * 4 : 0;
+  // per row: two staging buffers (double-buffered bulk copies) + the fp32 stash; three CTAs per SM when the rows allow
+  const int per_row = 2 * (x_row_bytes + r_row_bytes) + s_row_bytes + 16;
   int kLnRows = kLnMaxRows;
-  while (kLnRows > 1 && kLnRows * (x_row_bytes + r_row_bytes + s_row_bytes) > 96 * 1024) kLnRows >>= 1;
-  const int smem = kLnRows * (x_row_bytes + r_row_bytes + s_row_bytes) + 16;
+  while (kLnRows > 1 && kLnRows * per_row > 72 * 1024) kLnRows >>= 1;
+  const int smem = kLnRows * per_row;
   SGF_REQUIRE(smem <= 200 * 1024, "row_layernorm: D=%d too wide for this operand combination (%d B smem)", a->D, smem);
   SGF_REQUIRE(reinterpret_cast<uintptr_t>(a->x) % 16 == 0 && (a->ldx * xs) % 16 == 0 &&
                   (!a->residual || (reinterpret_cast<uintptr_t>(a->residual) % 16 == 0 && (a->ldr * rs) % 16 == 0)),
@@ -529,7 +548,11 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
     SGF_CHECK_CUDA(cudaFuncSetAttribute(row_layernorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured_smem = 200 * 1024;
   }
-  dim3 block(kLnRows * 32), grid((a->rows + kLnRows - 1) / kLnRows);
+  const int ngroups = (a->rows + kLnRows - 1) / kLnRows;
+  int per_sm = (220 * 1024) / (smem + 1024);
+  per_sm = per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm);
+  const int resident = 148 * per_sm;
+  dim3 block(kLnRows * 32), grid(ngroups < resident ? ngroups : resident);
   SGF_CHECK_CUDA(launch_pdl(row_layernorm_kernel, grid, block, smem, st, p, x_row_bytes, r_row_bytes, s_row_bytes));
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
