@@ -158,6 +158,16 @@ class BiasBwdArgs(C.Structure):
     ]
 
 
+class ArtSampleArgs(C.Structure):
+    _fields_ = [
+        ("name_tokens", _vp), ("name_ld", _i32), ("name_lens", _vp),
+        ("C", _i32), ("B", _i32), ("hp", _i32), ("S", _i32), ("lo", _i32), ("hi", _i32),
+        ("seed", C.c_uint32), ("step", _vp),
+        ("seg_id_offset", _i64), ("eos_id", _i64), ("pad_id", _i64),
+        ("bag_tokens", _vp), ("bag_ld", _i64), ("bag_ends", _vp), ("target", _vp), ("grid_out", _vp),
+    ]
+
+
 # every symbol include/segofa_b200.h declares: (name, restype, argtypes)
 EXPORTS = [
     ("sgf_last_error", C.c_char_p, []),
@@ -185,6 +195,7 @@ EXPORTS = [
     ("sgf_transpose_cast", C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp]),
     ("sgf_attention_bwd_bf16", C.c_int, [C.POINTER(AttentionBwdArgs), _vp]),
     ("sgf_attn_bias_bwd", C.c_int, [C.POINTER(BiasBwdArgs), _vp]),
+    ("sgf_artificial_sample", C.c_int, [C.POINTER(ArtSampleArgs), _vp]),
     ("sgf_adam_step", C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp, _vp]),
     ("sgf_sumsq", C.c_int, [_vp, _i64, _vp, _vp]),
 ]

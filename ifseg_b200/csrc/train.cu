@@ -697,9 +697,133 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
   }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// Device-side generation of the image-free training sample (data/mm_data/segmentation_dataset.py:303-329,
+// artificial_image_type = 'rand_k-l-r'): per sample a random sh x sw label grid (sh, sw ~ U{l..r-1}, labels ~
+// U{0..C-1}) nearest-resized (torchvision Resize(NEAREST) == F.interpolate(mode='nearest'): src = min(floor(dst *
+// float(in)/out), in-1)) to the patch grid -- ragged bags of the class-name tokens + cumulative bag ends -- and to the
+// pixel grid -- text2seg_target.  Counter-based RNG keyed by (seed, step[0], sample): nothing crosses PCIe.
+// ----------------------------------------------------------------------------------------
+struct ArtSampleParams {
+  const int64_t* name_tokens; int name_ld; const int32_t* name_lens;
+  int C, B, hp, S, lo, hi;
+  uint32_t seed; const int32_t* step;
+  int64_t seg_id_offset, eos_id, pad_id;
+  int64_t* bag_tokens; int64_t bag_ld; int64_t* bag_ends; int64_t* target; int32_t* grid_out;  // grid_out [B, 2 + 32*32] optional
+};
+SGF_DEVICE uint64_t art_key(const ArtSampleParams& p, int b) {
+  const uint64_t step = p.step ? static_cast<uint64_t>(p.step[0]) : 0ull;
+  return mix64((static_cast<uint64_t>(p.seed) << 32) ^ (step * 0x9E3779B97F4A7C15ull) ^ (static_cast<uint64_t>(b) << 12) ^ 0xA57ull);
+}
+SGF_DEVICE void art_dims(const ArtSampleParams& p, uint64_t key, int& sh, int& sw) {
+  const uint32_t span = static_cast<uint32_t>(p.hi - p.lo);
+  sh = p.lo + static_cast<int>((mix64(key ^ 0x1111ull) >> 33) % span);
+  sw = p.lo + static_cast<int>((mix64(key ^ 0x2222ull) >> 33) % span);
+}
+SGF_DEVICE int art_label(const ArtSampleParams& p, uint64_t key, int y, int x) {
+  return static_cast<int>((mix64(key ^ (static_cast<uint64_t>(y * 64 + x + 1) << 16)) >> 33) % static_cast<uint32_t>(p.C));
+}
+SGF_DEVICE int nearest_src(int dst, int in_size, int out_size) {
+  const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+  return min(static_cast<int>(floorf(static_cast<float>(dst) * scale)), in_size - 1);
+}
+
+__global__ void __launch_bounds__(1024) art_bags_kernel(const ArtSampleParams p) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int b = blockIdx.x;
+  const int P = p.hp * p.hp;
+  const uint64_t key = art_key(p, b);
+  int sh, sw;
+  art_dims(p, key, sh, sw);
+  if (p.grid_out && threadIdx.x == 0) {
+    p.grid_out[b * 1026] = sh;
+    p.grid_out[b * 1026 + 1] = sw;
+  }
+  if (p.grid_out)
+    for (int i = threadIdx.x; i < sh * sw; i += blockDim.x) p.grid_out[b * 1026 + 2 + i] = art_label(p, key, i / sw, i % sw);
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t* row = p.bag_tokens + static_cast<int64_t>(b) * p.bag_ld;
+  for (int base = 0; base < P; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    int label = 0, len = 0;
+    if (i < P) {
+      label = art_label(p, key, nearest_src(i / p.hp, sh, p.hp), nearest_src(i % p.hp, sw, p.hp));
+      len = p.name_lens[label];
+    }
+    int incl = len;  // inclusive scan over the block
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += n;
+      }
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int end = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + incl;
+    if (i < P) {
+      p.bag_ends[static_cast<int64_t>(b) * P + i] = end;
+      for (int k = 0; k < len; ++k) row[end - len + k] = p.name_tokens[static_cast<int64_t>(label) * p.name_ld + k];
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = end;  // total so far (last thread holds the block's inclusive end)
+    __syncthreads();
+  }
+  for (int64_t k = carry_s + threadIdx.x; k < p.bag_ld; k += blockDim.x) row[k] = p.pad_id;
+}
+
+__global__ void __launch_bounds__(256) art_target_kernel(const ArtSampleParams p) {
+  const int b = blockIdx.y;
+  const int64_t n = static_cast<int64_t>(p.S) * p.S;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i > n) return;
+  int64_t* out = p.target + static_cast<int64_t>(b) * (n + 1);
+  if (i == n) {
+    out[i] = p.eos_id;
+    return;
+  }
+  const uint64_t key = art_key(p, b);
+  int sh, sw;
+  art_dims(p, key, sh, sw);
+  const int y = static_cast<int>(i / p.S), x = static_cast<int>(i % p.S);
+  out[i] = p.seg_id_offset + art_label(p, key, nearest_src(y, sh, p.S), nearest_src(x, sw, p.S));
+}
+
 }  // namespace sgf
 
 using namespace sgf;
+
+extern "C" int sgf_artificial_sample(const sgf_artsample_args* a, void* stream) {
+  SGF_REQUIRE(a != nullptr && a->name_tokens && a->name_lens && a->bag_tokens && a->bag_ends && a->target,
+              "artificial_sample: null pointer");
+  SGF_REQUIRE(a->C > 0 && a->B > 0 && a->hp > 0 && a->S > 0 && a->lo >= 1 && a->hi > a->lo && a->hi <= 33,
+              "artificial_sample: bad arguments (1 <= lo < hi <= 33)");
+  ArtSampleParams p{a->name_tokens, a->name_ld, a->name_lens, a->C, a->B, a->hp, a->S, a->lo, a->hi, a->seed, a->step,
+                    a->seg_id_offset, a->eos_id, a->pad_id, a->bag_tokens, a->bag_ld, a->bag_ends, a->target, a->grid_out};
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  art_bags_kernel<<<a->B, 1024, 0, st>>>(p);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  const int64_t n = static_cast<int64_t>(a->S) * a->S + 1;
+  art_target_kernel<<<dim3(static_cast<unsigned>((n + 255) / 256), a->B), 256, 0, st>>>(p);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
+
 
 extern "C" int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* a, void* stream) {
   SGF_REQUIRE(a != nullptr, "row_layernorm_bwd: null args");

@@ -475,6 +475,28 @@ def attn_bias_bwd(dbias, blocks=(), dabs_acc=None):
         _lib.check(lib.sgf_attn_bias_bwd(C.byref(args), _stream()), "sgf_attn_bias_bwd")
 
 
+def artificial_sample(name_tokens, name_lens, B, hp, S, *, lo=1, hi=33, seed=1, step=None, seg_id_offset=59457, eos_id=2,
+                      pad_id=1, want_grid=False):
+    """Image-free training sample generated on the device (segmentation_dataset.py:303-329, 'rand_k-lo-hi').
+    name_tokens int64 [C, Lmax] / name_lens int32 [C]: BPE ids of the class names.  Returns (bag_tokens int64
+    [B, hp*hp*Lmax], bag_ends int64 [B*hp*hp], text2seg_target int64 [B, S*S+1]) (+ the label grids when want_grid)."""
+    lib = _lib.load()
+    _req(name_tokens, torch.int64, "name_tokens")
+    _req(name_lens, torch.int32, "name_lens")
+    Cn, Lmax = name_tokens.shape
+    P = hp * hp
+    dev = name_tokens.device
+    bag = torch.empty((B, P * Lmax), dtype=torch.int64, device=dev)
+    ends = torch.empty((B * P,), dtype=torch.int64, device=dev)
+    target = torch.empty((B, S * S + 1), dtype=torch.int64, device=dev)
+    grid = torch.zeros((B, 1026), dtype=torch.int32, device=dev) if want_grid else None
+    args = _lib.ArtSampleArgs(_p(name_tokens), name_tokens.stride(0), _p(name_lens), Cn, B, hp, S, lo, hi, int(seed) & 0xFFFFFFFF,
+                              _p(step), seg_id_offset, eos_id, pad_id, _p(bag), bag.stride(0), _p(ends), _p(target), _p(grid))
+    with _timed("artificial_sample", nbytes=float(target.numel() * 8 + bag.numel() * 8)):
+        _lib.check(lib.sgf_artificial_sample(C.byref(args), _stream()), "sgf_artificial_sample")
+    return (bag, ends, target, grid) if want_grid else (bag, ends, target)
+
+
 def adam_step(param, grad, exp_avg, exp_avg_sq, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1,
               step_dev=None, grad_scale=None):
     lib = _lib.load()

@@ -378,6 +378,23 @@ typedef struct {
 } sgf_bias_bwd_args;
 int sgf_attn_bias_bwd(const sgf_bias_bwd_args* args, void* stream);
 
+/* Device-side generation of the image-free training sample (data/mm_data/segmentation_dataset.py:303-329,
+ * artificial_image_type 'rand_k-lo-hi'): per sample a random sh x sw label grid (sh, sw in
+ * [lo, hi), labels in [0, C)) nearest-resized to the hp x hp patch grid -> bag_tokens int64 [B, bag_ld] (the
+ * class-name tokens of every patch, back to back, tail = pad_id; bag_ld >= hp*hp*max name length) and bag_ends int64
+ * [B, hp*hp] (cumulative bag lengths) = aux_input["patch_images"] / ["patch_masks"]; and to the S x S pixel grid ->
+ * target int64 [B, S*S+1] (seg_id_offset + label, then eos_id) = sample["text2seg_target"].  name_tokens int64
+ * [C, name_ld] / name_lens int32 [C] are the BPE ids of the class names.  Counter-based RNG keyed by (seed, step[0]).
+ * grid_out (optional int32 [B, 2 + 32*32]) receives (sh, sw, labels) for inspection. */
+typedef struct {
+  const int64_t* name_tokens; int32_t name_ld; const int32_t* name_lens;
+  int32_t C, B, hp, S, lo, hi;
+  uint32_t seed; const int32_t* step;
+  int64_t seg_id_offset, eos_id, pad_id;
+  int64_t* bag_tokens; int64_t bag_ld; int64_t* bag_ends; int64_t* target; int32_t* grid_out;
+} sgf_artsample_args;
+int sgf_artificial_sample(const sgf_artsample_args* args, void* stream);
+
 /* Multi-tensor-free fused Adam(W) step over one flat fp32 master buffer (cf/optim/adam.py, fp32
  * master weights of cf/optim/fp16_optimizer.py:108-222): p -= lr*(m_hat/(sqrt(v_hat)+eps) + wd*p)
  * with grads scaled by grad_scale[0] (device scalar: 1/sample_size * clip coefficient).  The update

@@ -44,7 +44,7 @@ def test_struct_layouts_match_the_header(tmp_path):
                "sgf_relblock": _lib.RelBlock, "sgf_bias_args": _lib.BiasArgs, "sgf_attention_args": _lib.AttentionArgs,
                "sgf_segmask_args": _lib.SegmaskArgs, "sgf_segloss_args": _lib.SeglossArgs,
                "sgf_segloss_bwd_args": _lib.SeglossBwdArgs, "sgf_rowln_bwd_args": _lib.RowLnBwdArgs,
-               "sgf_attention_bwd_args": _lib.AttentionBwdArgs, "sgf_bias_bwd_args": _lib.BiasBwdArgs}
+               "sgf_attention_bwd_args": _lib.AttentionBwdArgs, "sgf_bias_bwd_args": _lib.BiasBwdArgs, "sgf_artsample_args": _lib.ArtSampleArgs}
     src = open(HEADER).read()
     prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     expect = {}

@@ -366,3 +366,61 @@ def test_row_dropout_droppath_masks_forward_backward(ops):
     ops.row_layernorm(y, ln1=(one, zero), residual=res, out1=o_b, ln2=(one, zero), out2=out2,
                       drop=dict(p=0.0, path_p=0.0, seed=1, site=1, rows_per_sample=rps, step=step))
     assert torch.equal(o_a, o_b)
+
+
+@pytest.mark.parametrize("B,C,hp,S", [(8, 150, 30, 480), (3, 15, 8, 128), (2, 171, 40, 640)])
+def test_artificial_sample_generated_on_device(ops, B, C, hp, S):
+    """segmentation_dataset.py:303-329 on the GPU: rebuild the expected bags / targets with torch from the label grids
+    the kernel reports (nearest resize == F.interpolate(mode='nearest'), the torchvision Resize(NEAREST) the dataset uses)."""
+    g = _gen(C + hp)
+    Lmax = 4
+    lens = torch.randint(1, Lmax + 1, (C,), device="cuda", generator=g).int()
+    names = torch.randint(4, 50000, (C, Lmax), device="cuda", generator=g)
+    step = torch.tensor([11], dtype=torch.int32, device="cuda")
+    bag, ends, target, grid = ops.artificial_sample(names, lens, B, hp, S, seed=3, step=step, want_grid=True)
+    P = hp * hp
+    assert bag.shape == (B, P * Lmax) and ends.shape == (B * P,) and target.shape == (B, S * S + 1)
+    shs = set()
+    for b in range(B):
+        sh, sw = int(grid[b, 0]), int(grid[b, 1])
+        assert 1 <= sh <= 32 and 1 <= sw <= 32
+        shs.add((sh, sw))
+        lab = grid[b, 2: 2 + sh * sw].reshape(1, 1, sh, sw).float()
+        assert lab.min() >= 0 and lab.max() < C
+        low = F.interpolate(lab, size=(hp, hp), mode="nearest").long().reshape(-1)
+        full = F.interpolate(lab, size=(S, S), mode="nearest").long().reshape(-1)
+        assert torch.equal(target[b, :-1], full + 59457) and int(target[b, -1]) == 2
+        l = lens[low].long()
+        assert torch.equal(ends[b * P:(b + 1) * P], l.cumsum(0))
+        exp = torch.cat([names[c, : int(n)] for c, n in zip(low.tolist(), l.tolist())])
+        assert torch.equal(bag[b, : exp.numel()], exp) and (bag[b, exp.numel():] == 1).all()
+    assert len(shs) > 1  # samples differ
+    step += 1
+    _, _, target2 = ops.artificial_sample(names, lens, B, hp, S, seed=3, step=step)
+    assert not torch.equal(target, target2)  # a new step draws a new sample
+
+
+def test_generated_sample_feeds_the_training_engine(cuda_device):
+    """The generated tensors are exactly what aux_input / text2seg_target carry: one train step runs on them."""
+    from ifseg_b200 import ops as o
+    from ifseg_b200.seg_criterion import class_targets
+    from ifseg_b200.segofa import SegOFAModel
+    from ifseg_b200.synthetic import generate_state_dict, synthetic_inputs
+    from ifseg_b200.train_engine import SegOFATrainEngine
+
+    C, S, B = 15, 64, 2
+    model = SegOFAModel.from_config("segofa_tiny", C, S)
+    model.load_state_dict(generate_state_dict(model.cfg, 0), strict=True)
+    model = model.cuda()
+    eng = SegOFATrainEngine(model, stochastic=False)
+    inp = synthetic_inputs(model.cfg, B, S, seed=1)
+    g = _gen(5)
+    lens = torch.randint(1, 4, (C,), device="cuda", generator=g).int()
+    names = torch.randint(4, 50000, (C, 3), device="cuda", generator=g)
+    bag, ends, t2s = o.artificial_sample(names, lens, B, S // 16, S, seed=9)
+    aux = dict(src_tokens=inp["src_tokens"].cuda(), src_lengths=inp["src_lengths"].cuda(), patch_images=bag,
+               patch_masks=ends, prev_output_tokens=inp["prev_output_tokens"].cuda())
+    tgt = class_targets(t2s[:, :-1].reshape(B, S, S), 59457, C)
+    loss, logits = eng.forward_backward(aux, tgt)
+    assert torch.isfinite(loss) and logits.shape == (B, (S // 16) ** 2 + 1, C)
+    assert torch.isfinite(eng.arena.grad32).all() and eng.arena.grad32.abs().sum() > 0

@@ -1,19 +1,3 @@
 set -x
-timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_train_ops_gpu.py -q -k "row_layernorm or gelu or dropout" > gpurun_out/row_ops.log 2>&1
-tail -8 gpurun_out/row_ops.log
-timeout 900 python -m pytest tests/test_model_gpu.py tests/test_train_gpu.py -q -x > gpurun_out/model_gpu.log 2>&1
-tail -5 gpurun_out/model_gpu.log
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --kernel-breakdown > gpurun_out/bench_inf.json 2> gpurun_out/bench_inf.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_inf.json'))
-print('INF', d['ms_per_step'], d['value'], d['e2e']['value'], d['kernel_families'])
-PY
-grep row_layernorm gpurun_out/bench_inf.err
-timeout 600 python bench.py --config 3 --steps 10 --warmup 3 --no-cpu-baseline --kernel-breakdown > gpurun_out/bench_train_graph.json 2> gpurun_out/bench_train_graph.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_train_graph.json'))
-print('TRAIN', d['ms_per_step'], d['value'], d['e2e']['value'])
-PY
-grep row_layernorm gpurun_out/bench_train_graph.err
+timeout 900 python -m pytest tests/test_train_ops_gpu.py -q -k "artificial or generated" > gpurun_out/art.log 2>&1
+tail -25 gpurun_out/art.log
