@@ -112,3 +112,57 @@ def test_bucketed_gradient_allreduce_gloo_world2():
         assert p.exitcode == 0
     for r in range(2):
         assert torch.equal(res[r], torch.full((1000,), 3.0))  # sum over ranks; the optimizer applies 1/world
+
+
+def test_bias_block_csr_groups_positions_by_bucket():
+    """The static CSR the relative-position-table adjoint gathers over: every (i, j) of the block appears exactly once,
+    grouped by bucket, with flat offsets into the padded [Tq, row_stride] bias layout."""
+    from ifseg_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    bucket = torch.randint(0, 13, (40, 40), generator=g)
+    ids = torch.randperm(40, generator=g)[:9]
+    lo, row_stride, num_rel = 5, 64, 13
+    order, flat = ops.bias_block_csr(bucket, ids, lo, row_stride)
+    counts = torch.bincount(flat, minlength=num_rel)
+    offsets = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+    assert order.numel() == 81 and order.unique().numel() == 81
+    dbias = torch.randn(lo + 9 + 3, row_stride, generator=g)
+    want = torch.zeros(num_rel)
+    for a in range(9):
+        for b in range(9):
+            want[bucket[ids[a], ids[b]]] += dbias[lo + a, lo + b]
+    got = torch.stack([dbias.reshape(-1)[order[offsets[r]:offsets[r + 1]].long()].sum() for r in range(num_rel)])
+    assert torch.allclose(got, want, atol=1e-5)
+
+
+def test_synthetic_train_sample_layout():
+    """Same layout as SegmentationDataset.collate for artificial_image_type='rand_k-1-33' (segmentation_dataset.py:303-347)."""
+    from ifseg_b200.config import preset
+    from ifseg_b200.synthetic import synthetic_train_sample
+
+    cfg = preset("segofa_base", num_seg=15, patch_image_size=64, orig_patch_image_size=64)
+    s = synthetic_train_sample(cfg, 3, 64, seed=4)
+    P = 16
+    aux = s["aux_input"]
+    assert set(aux) == {"src_tokens", "src_lengths", "patch_images", "patch_masks", "prev_output_tokens"}
+    assert aux["patch_masks"].shape == (3 * P,) and s["text2seg_target"].shape == (3, 64 * 64 + 1)
+    ends = aux["patch_masks"].view(3, P)
+    assert (ends[:, 1:] > ends[:, :-1]).all() and (ends[:, 0] >= 1).all()  # every bag holds at least one token
+    for b in range(3):
+        n = int(ends[b, -1])
+        assert (aux["patch_images"][b, :n] != cfg.padding_idx).all() and (aux["patch_images"][b, n:] == cfg.padding_idx).all()
+    t = s["text2seg_target"]
+    assert (t[:, -1] == 2).all() and (t[:, :-1] >= 59457).all() and (t[:, :-1] < 59457 + 15).all()
+    assert s["net_input"]["patch_images"].shape == (3, 3, 64, 64) and s["target"].shape == (3, 64 * 64 + 1)
+
+
+def test_training_engine_fails_loudly_without_cuda():
+    from ifseg_b200.train_engine import SegOFATrainEngine
+    from ifseg_b200.trainer import SegOFATrainer
+
+    m = _model()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        SegOFATrainEngine(m)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        SegOFATrainer(m)
