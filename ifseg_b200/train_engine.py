@@ -536,17 +536,23 @@ class SegOFATrainEngine:
         Returns (loss 0-dim tensor = mean pixel CE, logits fp32 [B,Td,C]); gradients of the mean loss times
         grad_scale are left in param.grad (views of arena.grad32)."""
         c = self.forward_train(aux_input, check_pads=check_pads)
+        loss, dlogits = self.loss_and_dlogits(c, target_classes, label_smoothing, grad_scale, backward)
+        if backward:
+            self.backward_from(c, dlogits)
+        return loss, c["logits"]
+
+    def loss_and_dlogits(self, c, target_classes, label_smoothing=0.0, grad_scale=1.0, backward=True):
+        """compute_imfree_loss on the context of forward_train: (mean pixel CE, bf16 dL/dlogits [B,Td,pad8(C)] or None)."""
         logits, h, w = c["logits"], c["h"], c["w"]
         tgt = target_classes.to(self.device).contiguous()
         pix_lse = torch.empty(tuple(tgt.shape), dtype=torch.float32, device=self.device)
         acc = ops.upsample_ce_loss(logits, tgt, h, w, label_smoothing, lse_out=pix_lse, raw=True)
         loss = acc[0] / acc[1]
         if not backward:
-            return loss, logits
+            return loss, None
         dlogits = torch.empty((c["B"], c["Td"], _pad8(self.cfg.num_seg)), dtype=_BF16, device=self.device)
         ops.upsample_ce_loss_bwd(logits, tgt, pix_lse, acc[1:], h, w, dlogits, label_smoothing, grad_scale)
-        self.backward_from(c, dlogits)
-        return loss, logits
+        return loss, dlogits
 
     def forward_train(self, aux_input, check_pads=True):
         """Forward of the image-free branch keeping what the adjoints need; returns the context dict

@@ -37,6 +37,7 @@ class SegOFATrainer:
             self.world = torch.distributed.get_world_size(process_group)
         self.engine.grad_sync = self._sync_bucket if self.world > 1 else None
         self._works = []
+        self._side = None
         self.num_updates = 0
 
     # gradient exchange: called by the engine as soon as a contiguous gradient range is final
@@ -67,11 +68,19 @@ class SegOFATrainer:
         ids = sample["text2seg_target"][:, :-1].reshape(B, S, S).to(dev)
         tgt = class_targets(ids, self.seg_id_offset, C, cfg.padding_idx)
         self._works = []
-        imfree_loss, _ = eng.forward_backward(sample["aux_input"], tgt, self.label_smoothing, check_pads=check_pads)
+        c = eng.forward_train(sample["aux_input"], check_pads=check_pads)
+        imfree_loss, dlogits = eng.loss_and_dlogits(c, tgt, self.label_smoothing)
         log = {"loss": imfree_loss, "imfree_loss": imfree_loss}
-        if self.eval_real_image:  # `with torch.inference_mode(): model(**net_input)` + compute_loss (display metrics)
+        main = torch.cuda.current_stream()
+        if self.eval_real_image:
+            # `with torch.inference_mode(): model(**net_input)` + compute_loss (display metrics, seg_criterion.py:185):
+            # independent of the backward, so it runs on a side stream underneath it (its small stem kernels fill
+            # the SMs the backward's wave tails leave idle); joined before the optimizer touches the weights
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(main)
             ni = sample["net_input"]
-            with torch.no_grad():
+            with torch.cuda.stream(self._side), torch.no_grad():
                 enc = eng.inf.encode(ni["src_tokens"], patch_images=ni["patch_images"], patch_masks=ni["patch_masks"],
                                      has_pads=False)
                 logits, _ = eng.inf.decode(enc, ni["prev_output_tokens"])
@@ -80,8 +89,14 @@ class SegOFATrainer:
                 rt = class_targets(sample["target"][:, :-1].reshape(B, h, w).to(dev), self.seg_id_offset, C, cfg.padding_idx)
                 _, areas = ops.upsample_argmax(logits, hp, wp, h, w, target=rt)
                 seg_loss, _ = ops.upsample_ce_loss(logits, rt, hp, wp, self.label_smoothing)
+                union = areas[1] + areas[2] - areas[0]
+                for t in (seg_loss, areas, union):
+                    t.record_stream(main)
             log.update(seg_loss=seg_loss, area_intersect=areas[0], area_pred_label=areas[1], area_label=areas[2],
-                       area_union=areas[1] + areas[2] - areas[0])
+                       area_union=union)
+        eng.backward_from(c, dlogits)
+        if self.eval_real_image:
+            main.wait_stream(self._side)
         for wk in self._works:
             wk.wait()
         gnorm = eng.optimizer_step(self.lr, self.betas, self.eps, self.weight_decay, self.clip_norm,
