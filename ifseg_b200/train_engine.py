@@ -158,6 +158,7 @@ class SegOFATrainEngine:
         self.dec_dpr = [d_rate * i / max(nd - 1, 1) for i in range(nd)]
         self._fwd_dev = torch.zeros(1, dtype=torch.int32, device=self.device)  # forward counter = mask "step"
         self._fresh = False
+        self._wstream = None
         self._hook = None
         self._step_dev = None
         self._scratch: Dict = {}
@@ -255,9 +256,16 @@ class SegOFATrainEngine:
             self._hook = torch.zeros((), device=self.device, requires_grad=True)
         return ImFreeBranchFunction.apply(self._hook, self, aux_input)
 
+    def _wgrad_stream(self):
+        if self._wstream is None:
+            self._wstream = torch.cuda.Stream()
+        return self._wstream
+
     def _sync_down(self, key):
         """Gradients of arena[marks[key]:] are final: hand the not-yet-synchronised part to the DDP callback."""
         lo = self.marks[key] if key is not None else 0
+        if self._wstream is not None and (self.grad_sync is not None or key is None):
+            torch.cuda.current_stream().wait_stream(self._wstream)  # the side-stream weight gradients of this range
         if self.grad_sync is not None and lo < self._sync_hi:
             self.grad_sync(lo, self._sync_hi)
         self._sync_hi = min(self._sync_hi, lo)
@@ -505,17 +513,27 @@ class SegOFATrainEngine:
         gradient views, returns dX = dY W."""
         N, K = L.N, L.K
         Mp = _pad8(M)
-        if L.gw is not None:
-            if L.gb is not None and not bias_done:
-                ops.transpose_cast(dy, M=M, N=N, want_t=False, colsum=L.gb)  # db = column sums of dY
-            if K % 32 == 0:
+        if L.gw is not None and K % 32 == 0:
+            # Weight / bias gradients feed nothing downstream: they run on a side stream underneath the dX chain (their
+            # CTAs fill the SMs that the chain's wave tails and small row kernels leave idle).
+            cur = torch.cuda.current_stream()
+            ws = self._wgrad_stream()
+            ws.wait_stream(cur)
+            with torch.cuda.stream(ws):
+                if L.gb is not None and not bias_done:
+                    ops.transpose_cast(dy, M=M, N=N, want_t=False, colsum=L.gb)  # db = column sums of dY
                 # dW[n,k] (+)= sum_t dY[t,n] X[t,k]: both operands are read as they lie (MN-major TMA tiles), the token
                 # dimension is split over CTAs and reduced with fp32 atomics into the (zeroed / accumulating) gradient
                 tiles = ((N + 127) // 128) * ((K + 127) // 128)
                 split = max(1, min(8, (296 + tiles - 1) // tiles, (M + 1023) // 1024))
                 ops.gemm_ex(dy, x, L.gw, M=N, N=K, K=M, a_mn=True, b_mn=True, lda=dy.stride(0), ldb=x.stride(0),
                             split_k=split, accumulate=True, tag="wgrad_" + tag)
-            else:
+            dy.record_stream(ws)
+            x.record_stream(ws)
+        elif L.gw is not None:
+            if L.gb is not None and not bias_done:
+                ops.transpose_cast(dy, M=M, N=N, want_t=False, colsum=L.gb)
+            if True:
                 dyt = self._buf(("dyt", Mp), (max(d.N for d in self.dense), Mp), _BF16)
                 xt = self._buf(("xt", Mp), (max(d.K for d in self.dense), Mp), _BF16)
                 ops.transpose_cast(dy, M=M, N=N, out_t=dyt)
