@@ -293,11 +293,42 @@ SGF_DEVICE float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+SGF_DEVICE float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Packed fp32x2 arithmetic (sm_100: FFMA2/FMUL2/FADD2 — two lanes per FMA-pipe issue slot).  The row kernels are
+// issue-bound on their elementwise chains, so everything that is not a MUFU or a sign trick goes through these.
+SGF_DEVICE float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)),
+        "l"(reinterpret_cast<const uint64_t&>(c)));
+  return d;
+}
+SGF_DEVICE float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return d;
+}
+SGF_DEVICE float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return d;
+}
+SGF_DEVICE float2 splat2(float a) { return make_float2(a, a); }
+
 // erf-GELU with the Abramowitz-Stegun 7.1.26 rational approximation of erf (|error| <= 1.5e-7,
 // far below the bf16 rounding of the result): 2 MUFU (rcp, ex2) + ~12 FMA-pipe ops, no branches.
 SGF_DEVICE float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
@@ -305,6 +336,26 @@ SGF_DEVICE float gelu_erf(float x) {
   const float e = fast_exp2(-1.4426950408889634f * z * z);
   const float erf_abs = fmaf(-p * t, e, 1.0f);  // erf(|x|/sqrt2)
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+// Two elements at a time.  Returns Phi(x) (the normal CDF: gelu(x) = x * Phi(x)) and e = exp(-x^2/2)
+// (gelu'(x) = Phi(x) + x * e / sqrt(2 pi)).  Per pair: 10 packed FMA-pipe ops, 4 MUFU, 4 sign/abs ALU ops.
+SGF_DEVICE float2 gelu_cdf2(float2 x, float2& e) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 den = fma2(splat2(0.3275911f * 0.70710678118654752440f), ax, splat2(1.0f));
+  const float2 t = make_float2(fast_rcp(den.x), fast_rcp(den.y));
+  float2 p = fma2(splat2(-1.061405429f), t, splat2(1.453152027f));  // -(A&S polynomial): erf = 1 + (p t) e
+  p = fma2(p, t, splat2(-1.421413741f));
+  p = fma2(p, t, splat2(0.284496736f));
+  p = fma2(p, t, splat2(-0.254829592f));
+  const float2 arg = mul2(mul2(x, x), splat2(-0.72134752044448170368f));  // -x^2/2 * log2(e)
+  e = make_float2(fast_exp2(arg.x), fast_exp2(arg.y));
+  const float2 erf_abs = fma2(mul2(p, t), e, splat2(1.0f));
+  const float2 s = make_float2(copysignf(erf_abs.x, x.x), copysignf(erf_abs.y, x.y));
+  return fma2(splat2(0.5f), s, splat2(0.5f));
+}
+SGF_DEVICE float2 gelu_erf2(float2 x) {
+  float2 e;
+  return mul2(x, gelu_cdf2(x, e));
 }
 // ----------------------------------------------------------------------------------------
 // counter-based dropout / DropPath masks: a pure function of (seed, step, site, row, column), so the forward and
@@ -361,6 +412,9 @@ SGF_DEVICE void drop_mult8(const DropCtx& c, int64_t row, int chunk, float (&m)[
 // vector fp32 reduction into global memory (no return value): one 16-byte L2 atomic
 SGF_DEVICE void red_add_f32x4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+SGF_DEVICE void red_add_f32(float* addr, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
 SGF_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

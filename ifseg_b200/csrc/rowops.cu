@@ -266,6 +266,169 @@ __global__ void __launch_bounds__(kLnMaxRows * 32) row_layernorm_kernel(const Ro
 }
 
 // ----------------------------------------------------------------------------------------
+// Register-resident variant for model-width rows (D <= 1280, no activation): one warp per row, lane l owns the
+// 8-column chunks l, l+32, ...; x and the residual row arrive through direct 128-bit global loads issued back to
+// back, both LayerNorms run on registers (packed fp32x2 arithmetic), nothing is staged in shared memory, so the
+// SM holds 24-32 warps of independent rows.
+// ----------------------------------------------------------------------------------------
+SGF_DEVICE void load8p(const void* base, int dtype, int64_t off, float2 (&v)[4]) {
+  if (dtype == SGF_F32) {
+    const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    const float4 a = q[0], b = q[1];
+    v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w); v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+    v[0] = unpack_bf16x2(u.x); v[1] = unpack_bf16x2(u.y); v[2] = unpack_bf16x2(u.z); v[3] = unpack_bf16x2(u.w);
+  }
+}
+SGF_DEVICE void store8p(void* base, int dtype, int64_t off, const float2 (&v)[4]) {
+  if (dtype == SGF_F32) {
+    float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+    q[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    q[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+  } else {
+    uint4 u;
+    u.x = pack_bf16x2(v[0].x, v[0].y); u.y = pack_bf16x2(v[1].x, v[1].y);
+    u.z = pack_bf16x2(v[2].x, v[2].y); u.w = pack_bf16x2(v[3].x, v[3].y);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = u;
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(128, NC <= 3 ? 4 : 3) row_layernorm_reg_kernel(const RowLnParams p) {
+  pdl_trigger();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float invD = 1.0f / static_cast<float>(p.D);
+  const int nchunk = p.D >> 3;
+  const DropCtx drop = make_drop_ctx(p.drop_p, p.droppath_p, p.drop_seed, p.drop_site, p.drop_step, p.rows_per_sample);
+  const float2 zero2 = splat2(0.f);
+  pdl_wait();
+  for (int row = blockIdx.x * 4 + warp; row < p.rows; row += gridDim.x * 4) {
+    const int64_t dst_row =
+        p.seg_len > 0 ? static_cast<int64_t>(row / p.seg_len) * p.seg_stride + p.seg_off + row % p.seg_len : row;
+    const int64_t src_row = p.gather_idx ? p.gather_idx[row] : row;
+    if (p.clear_rowstats && lane < 2) p.clear_rowstats[static_cast<int64_t>(row) * 2 + lane] = 0.f;
+    const bool zero = p.zero_row && p.zero_row[row];
+    float2 y[NC][4], r[NC][4];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nchunk) {
+        load8p(p.x, p.x_dtype, src_row * p.ldx + c * 8, y[k]);
+        if (p.residual) load8p(p.residual, p.r_dtype, dst_row * p.ldr + c * 8, r[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      const bool ok = c < nchunk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!ok) y[k][j] = zero2;
+        if (!ok || !p.residual) r[k][j] = zero2;
+      }
+      if (ok && p.pre_add) {
+        float2 a[4];
+        load8p(p.pre_add, SGF_F32, c * 8, a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[k][j] = add2(y[k][j], a[j]);
+      }
+    }
+    // ---- first LayerNorm ----
+    if (p.g1) {
+      float2 s2 = zero2;
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s2 = add2(s2, y[k][j]);
+      const float mean = warp_sum(s2.x + s2.y) * invD;
+      const float2 nm = splat2(-mean);
+      float2 q = zero2;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        if (lane + 32 * k < nchunk) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            y[k][j] = add2(y[k][j], nm);
+            q = fma2(y[k][j], y[k][j], q);
+          }
+        }
+      }
+      const float2 rs = splat2(rsqrtf(warp_sum(q.x + q.y) * invD + 1e-5f));
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const int c = lane + 32 * k;
+        if (c < nchunk) {
+          float2 g[4], b[4];
+          load8p(p.g1, SGF_F32, c * 8, g);
+          load8p(p.b1, SGF_F32, c * 8, b);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) y[k][j] = fma2(mul2(y[k][j], rs), g[j], b[j]);
+        }
+      }
+    }
+    // ---- dropout / DropPath, residual, padding rows, first output ----
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nchunk) {
+        if (drop.on) {
+          float m[8];
+          drop_mult8(drop, dst_row, c, m);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) y[k][j] = mul2(y[k][j], make_float2(m[2 * j], m[2 * j + 1]));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          y[k][j] = add2(y[k][j], r[k][j]);
+          if (zero) y[k][j] = zero2;
+        }
+        if (p.out1) {
+          store8p(p.out1, p.out1_dtype, dst_row * p.ld1 + c * 8, y[k]);
+          if (p.out1_dtype == SGF_BF16) {  // second LN sees exactly what was stored
+#pragma unroll
+            for (int j = 0; j < 4; ++j) y[k][j] = unpack_bf16x2(pack_bf16x2(y[k][j].x, y[k][j].y));
+          }
+        }
+      }
+    }
+    if (!p.out2) continue;
+    // ---- second LayerNorm ----
+    float2 s2 = zero2;
+#pragma unroll
+    for (int k = 0; k < NC; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s2 = add2(s2, y[k][j]);
+    const float mean2 = warp_sum(s2.x + s2.y) * invD;
+    const float2 nm2 = splat2(-mean2);
+    float2 q2 = zero2;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      if (lane + 32 * k < nchunk) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          y[k][j] = add2(y[k][j], nm2);
+          q2 = fma2(y[k][j], y[k][j], q2);
+        }
+      }
+    }
+    const float2 rs2 = splat2(rsqrtf(warp_sum(q2.x + q2.y) * invD + 1e-5f));
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nchunk) {
+        float2 g[4], b[4];
+        load8p(p.g2, SGF_F32, c * 8, g);
+        load8p(p.b2, SGF_F32, c * 8, b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[k][j] = fma2(mul2(y[k][j], rs2), g[j], b[j]);
+        store8p(p.out2, SGF_BF16, dst_row * p.ld2 + c * 8, y[k]);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // attention bias: out = abs (+ dense_add) + rel-pos table lookups on up to two square blocks
 // ----------------------------------------------------------------------------------------
 struct BiasParams {
@@ -529,6 +692,26 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
                 a->drop_seed, a->drop_site, a->rows_per_sample, a->drop_step};
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int xs = a->x_dtype == SGF_F32 ? 4 : 2, rs = a->r_dtype == SGF_F32 ? 4 : 2;
+  SGF_REQUIRE(reinterpret_cast<uintptr_t>(a->x) % 16 == 0 && (a->ldx * xs) % 16 == 0 &&
+                  (!a->residual || (reinterpret_cast<uintptr_t>(a->residual) % 16 == 0 && (a->ldr * rs) % 16 == 0)),
+              "row_layernorm: x/residual rows must be 16-byte aligned");
+  const bool out_ok = (!a->out1 || reinterpret_cast<uintptr_t>(a->out1) % 16 == 0) &&
+                      (!a->out2 || reinterpret_cast<uintptr_t>(a->out2) % 16 == 0);
+  if (a->x_act == SGF_ACT_NONE && a->D <= 1280 && out_ok) {  // model-width rows: register-resident kernel
+    const int nc = (a->D + 255) / 256;
+    const int ngrp = (a->rows + 3) / 4;
+    const int resident = 148 * (nc <= 3 ? 4 : 3);
+    const dim3 grid(ngrp < resident ? ngrp : resident), block(128);
+    switch (nc) {
+      case 1: SGF_CHECK_CUDA(launch_pdl(row_layernorm_reg_kernel<1>, grid, block, size_t(0), st, p)); break;
+      case 2: SGF_CHECK_CUDA(launch_pdl(row_layernorm_reg_kernel<2>, grid, block, size_t(0), st, p)); break;
+      case 3: SGF_CHECK_CUDA(launch_pdl(row_layernorm_reg_kernel<3>, grid, block, size_t(0), st, p)); break;
+      case 4: SGF_CHECK_CUDA(launch_pdl(row_layernorm_reg_kernel<4>, grid, block, size_t(0), st, p)); break;
+      default: SGF_CHECK_CUDA(launch_pdl(row_layernorm_reg_kernel<5>, grid, block, size_t(0), st, p)); break;
+    }
+    count_launch();
+    return SGF_OK;
+  }
   const int x_row_bytes = a->D * xs;
   const int r_row_bytes = a->residual ? a->D * rs : 0;
   const bool two_stage = a->out2 && (a->g1 || a->residual || a->pre_add || a->out1 || a->x_act || a->drop_p > 0.f ||

@@ -2,6 +2,8 @@
 // transpose/cast that produces the operands of the dense adjoints, fused Adam, sum of squares.
 // Same conventions as rowops.cu: one warp per row, rows staged through shared memory with 1-D
 // bulk async copies, 128-bit accesses, warp-shuffle reductions.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sgf {
@@ -44,7 +46,7 @@ SGF_DEVICE void ld8s(const uint8_t* row, int dtype, int e, float (&v)[8]) {
 // d/dx of the erf-GELU (same rational erf as gelu_erf): Phi(x) + x * phi(x)
 SGF_DEVICE float gelu_erf_grad(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
@@ -341,6 +343,279 @@ __global__ void __launch_bounds__(256) row_layernorm_bwd_kernel(const RowLnBwdPa
 }
 
 // ----------------------------------------------------------------------------------------
+// Register-resident variant of the row adjoint for model-width rows (D <= 1280, no activation): one warp per row,
+// lane l owns the 8-column chunks l, l+32, ...; every operand of the row is fetched with direct 128-bit global loads
+// issued up front (12+ independent loads in flight per lane instead of a staged bulk copy the whole CTA waits for),
+// statistics come from registers (no re-reads), the arithmetic is packed fp32x2.  Parameter-gradient partials stay in
+// per-warp private shared-memory accumulators (plain vector read-modify-writes).  3 CTAs x 4 warps per SM.
+// ----------------------------------------------------------------------------------------
+SGF_DEVICE void ld8gp2(const void* base, int dtype, int64_t off, float2 (&v)[4]) {
+  if (dtype == SGF_F32) {
+    const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    const float4 a = q[0], b = q[1];
+    v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w); v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + off);
+    v[0] = unpack_bf16x2(u.x); v[1] = unpack_bf16x2(u.y); v[2] = unpack_bf16x2(u.z); v[3] = unpack_bf16x2(u.w);
+  }
+}
+SGF_DEVICE void st8gp2(void* base, int dtype, int64_t off, const float2 (&v)[4]) {
+  if (dtype == SGF_F32) {
+    float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+    q[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    q[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+  } else {
+    uint4 u;
+    u.x = pack_bf16x2(v[0].x, v[0].y); u.y = pack_bf16x2(v[1].x, v[1].y);
+    u.z = pack_bf16x2(v[2].x, v[2].y); u.w = pack_bf16x2(v[3].x, v[3].y);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = u;
+  }
+}
+SGF_DEVICE void acc8p(float* a, int col, const float2 (&v)[4]) {
+  float4* q = reinterpret_cast<float4*>(a + col);
+  const float4 u0 = q[0], u1 = q[1];
+  const float2 r0 = add2(make_float2(u0.x, u0.y), v[0]), r1 = add2(make_float2(u0.z, u0.w), v[1]);
+  const float2 r2 = add2(make_float2(u1.x, u1.y), v[2]), r3 = add2(make_float2(u1.z, u1.w), v[3]);
+  q[0] = make_float4(r0.x, r0.y, r1.x, r1.y);
+  q[1] = make_float4(r2.x, r2.y, r3.x, r3.y);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(128, NC <= 3 ? 3 : 2) row_layernorm_bwd_reg_kernel(const RowLnBwdParams p, const int n_acc) {
+  pdl_trigger();
+  extern __shared__ __align__(16) float racc[];  // [4 warps][n_acc][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int D = p.D;
+  float* wacc = racc + static_cast<size_t>(warp) * n_acc * D;
+  int na = 0;
+  float* a_g2 = p.dg2 ? wacc + (na++) * D : nullptr;
+  float* a_b2 = p.db2 ? wacc + (na++) * D : nullptr;
+  float* a_g1 = p.dg1 ? wacc + (na++) * D : nullptr;
+  float* a_b1 = p.db1 ? wacc + (na++) * D : nullptr;
+  float* a_pa = p.d_pre_add ? wacc + (na++) * D : nullptr;
+  float* a_cs = p.dx_colsum ? wacc + (na++) * D : nullptr;
+  for (int i = lane * 4; i < n_acc * D; i += 128) *reinterpret_cast<float4*>(wacc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  pdl_wait();
+
+  const float invD = 1.0f / static_cast<float>(D);
+  const int nchunk = D >> 3;
+  const bool ln2 = p.g2 && p.dy2;
+  const bool has_v = p.v && ln2;
+  const bool x_used = p.g1 || (ln2 && !p.v);
+  const DropCtx drop = make_drop_ctx(p.drop_p, p.droppath_p, p.drop_seed, p.drop_site, p.drop_step, p.rows_per_sample);
+  const float2 zero2 = splat2(0.f);
+
+  for (int row = blockIdx.x * 4 + warp; row < p.rows; row += gridDim.x * 4) {
+    int64_t dst_row = row;
+    if (p.seg_len > 0) dst_row = static_cast<int64_t>(row / p.seg_len) * p.seg_stride + p.seg_off + row % p.seg_len;
+    const int64_t src_row = p.gather_idx ? p.gather_idx[row] : row;
+
+    float2 dv[NC][4], dy[NC][4], t[NC][4], w[NC][4];
+    // ---- every operand of the row, issued back to back ----
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nchunk) {
+        if (p.dv_in) ld8gp2(p.dv_in, SGF_F32, dst_row * p.lddv + c * 8, dv[k]);
+        if (p.dy2) ld8gp2(p.dy2, p.dy2_dtype, dst_row * p.ldy2 + c * 8, dy[k]);
+        if (has_v) ld8gp2(p.v, p.v_dtype, dst_row * p.ldv + c * 8, w[k]);
+        if (x_used) ld8gp2(p.x, p.x_dtype, src_row * p.ldx + c * 8, t[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      const bool ok = c < nchunk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!ok || !p.dv_in) dv[k][j] = zero2;
+        if (!ok || !p.dy2) dy[k][j] = zero2;
+        if (!ok || !x_used) t[k][j] = zero2;
+      }
+      if (ok && x_used && p.pre_add) {
+        float2 a[4];
+        ld8gp2(p.pre_add, SGF_F32, c * 8, a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[k][j] = add2(t[k][j], a[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (!ok || !has_v) w[k][j] = t[k][j];  // LN2 acts on t itself when no separate v was saved
+    }
+
+    // ---- dv = dv_in + LN2'(dy2) ----
+    if (ln2) {
+      float2 s2 = zero2;
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s2 = add2(s2, w[k][j]);
+      const float mean2 = warp_sum(s2.x + s2.y) * invD;
+      const float2 nm = splat2(-mean2);
+      float2 q = zero2, a = zero2, b = zero2;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const int c = lane + 32 * k;
+        if (c < nchunk) {
+          float2 gm[4];
+          ld8gp2(p.g2, SGF_F32, c * 8, gm);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 d = add2(w[k][j], nm);
+            const float2 gy = mul2(dy[k][j], gm[j]);
+            w[k][j] = d;  // centred
+            q = fma2(d, d, q);
+            a = add2(a, gy);
+            b = fma2(gy, d, b);
+          }
+        }
+      }
+      const float rstd2 = rsqrtf(warp_sum(q.x + q.y) * invD + 1e-5f);
+      const float c1 = warp_sum(a.x + a.y) * invD;
+      const float c2 = warp_sum(b.x + b.y) * invD * rstd2;
+      const float2 rs = splat2(rstd2), nc1r = splat2(-c1 * rstd2), nc2r = splat2(-c2 * rstd2);
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const int c = lane + 32 * k;
+        if (c < nchunk) {
+          float2 gm[4], gx[4];
+          ld8gp2(p.g2, SGF_F32, c * 8, gm);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 xh = mul2(w[k][j], rs);
+            const float2 lin = fma2(mul2(dy[k][j], gm[j]), rs, nc1r);  // rstd (dy g - c1)
+            dv[k][j] = add2(dv[k][j], fma2(xh, nc2r, lin));
+            gx[j] = mul2(dy[k][j], xh);
+          }
+          if (a_g2) acc8p(a_g2, c * 8, gx);
+          if (a_b2) acc8p(a_b2, c * 8, dy[k]);
+        }
+      }
+    } else if (p.dy2) {
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dv[k][j] = add2(dv[k][j], dy[k][j]);
+    }
+    // ---- residual-stream gradient out; dropout / DropPath multiplier of the forward ----
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nchunk) {
+        if (p.d_res) st8gp2(p.d_res, SGF_F32, dst_row * p.ldres + c * 8, dv[k]);
+        if (drop.on) {
+          float m[8];
+          drop_mult8(drop, dst_row, c, m);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dv[k][j] = mul2(dv[k][j], make_float2(m[2 * j], m[2 * j + 1]));
+        }
+      }
+    }
+    // ---- LayerNorm 1 adjoint ----
+    if (p.g1) {
+      float2 s2 = zero2;
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s2 = add2(s2, t[k][j]);
+      const float mean1 = warp_sum(s2.x + s2.y) * invD;
+      const float2 nm = splat2(-mean1);
+      float2 q = zero2, a = zero2, b = zero2;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const int c = lane + 32 * k;
+        if (c < nchunk) {
+          float2 gm[4];
+          ld8gp2(p.g1, SGF_F32, c * 8, gm);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 d = add2(t[k][j], nm);
+            const float2 gy = mul2(dv[k][j], gm[j]);
+            t[k][j] = d;
+            q = fma2(d, d, q);
+            a = add2(a, gy);
+            b = fma2(gy, d, b);
+          }
+        }
+      }
+      const float rstd1 = rsqrtf(warp_sum(q.x + q.y) * invD + 1e-5f);
+      const float d1 = warp_sum(a.x + a.y) * invD;
+      const float d2 = warp_sum(b.x + b.y) * invD * rstd1;
+      const float2 rs = splat2(rstd1), nd1r = splat2(-d1 * rstd1), nd2r = splat2(-d2 * rstd1);
+#pragma unroll
+      for (int k = 0; k < NC; ++k) {
+        const int c = lane + 32 * k;
+        if (c < nchunk) {
+          float2 gm[4], gx[4];
+          ld8gp2(p.g1, SGF_F32, c * 8, gm);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 th = mul2(t[k][j], rs);
+            const float2 lin = fma2(mul2(dv[k][j], gm[j]), rs, nd1r);
+            gx[j] = mul2(dv[k][j], th);
+            t[k][j] = fma2(th, nd2r, lin);  // dt
+          }
+          if (a_g1) acc8p(a_g1, c * 8, gx);
+          if (a_b1) acc8p(a_b1, c * 8, dv[k]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[k][j] = dv[k][j];
+    }
+    // ---- dt out ----
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nchunk) {
+        if (a_pa) acc8p(a_pa, c * 8, t[k]);
+        if (p.dx) {
+          if (a_cs) acc8p(a_cs, c * 8, t[k]);
+          const int64_t off = src_row * p.lddx + c * 8;
+          if (p.dx_accumulate) {
+            float2 o[4];
+            ld8gp2(p.dx, p.dx_dtype, off, o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[k][j] = add2(t[k][j], o[j]);
+          }
+          st8gp2(p.dx, p.dx_dtype, off, t[k]);
+        }
+      }
+    }
+  }
+  // ---- sum the four per-warp partials and flush ----
+  __syncthreads();
+  float* outs[6];
+  na = 0;
+  if (p.dg2) outs[na++] = p.dg2;
+  if (p.db2) outs[na++] = p.db2;
+  if (p.dg1) outs[na++] = p.dg1;
+  if (p.db1) outs[na++] = p.db1;
+  if (p.d_pre_add) outs[na++] = p.d_pre_add;
+  if (p.dx_colsum) outs[na++] = p.dx_colsum;
+  for (int a = 0; a < na; ++a) {
+    float* dst = outs[a];
+    const bool al = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    for (int i = threadIdx.x * 4; i < D; i += 128 * 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int wq = 0; wq < 4; ++wq) {
+        const float4 u = *reinterpret_cast<const float4*>(racc + (static_cast<size_t>(wq) * n_acc + a) * D + i);
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+      }
+      if (al) {
+        red_add_f32x4(dst + i, v.x, v.y, v.z, v.w);
+      } else {
+        red_add_f32(dst + i, v.x); red_add_f32(dst + i + 1, v.y); red_add_f32(dst + i + 2, v.z); red_add_f32(dst + i + 3, v.w);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // transpose + cast (+ column sums)
 // ----------------------------------------------------------------------------------------
 template <typename TIn>
@@ -424,7 +699,7 @@ SGF_DEVICE void unpack8(const uint4& u, float (&v)[8]) {
 // Phi(x) (normal CDF) with the same rational erf as gelu_erf; gelu(x) = x * Phi(x)
 SGF_DEVICE float gelu_cdf(float x, float& e_out) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
@@ -432,6 +707,14 @@ SGF_DEVICE float gelu_cdf(float x, float& e_out) {
   const float e = fast_exp2(-1.4426950408889634f * z * z);
   e_out = e;
   return 0.5f * (1.0f + copysignf(fmaf(-p * t, e, 1.0f), x));
+}
+
+SGF_DEVICE void unpack8p(const uint4& u, float2 (&v)[4]) {
+  v[0] = unpack_bf16x2(u.x); v[1] = unpack_bf16x2(u.y); v[2] = unpack_bf16x2(u.z); v[3] = unpack_bf16x2(u.w);
+}
+SGF_DEVICE void ld8gp(const float* base, int col, float2 (&v)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(base + col), b = *reinterpret_cast<const float4*>(base + col + 4);
+  v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w); v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
 }
 
 template <int NC>
@@ -443,51 +726,76 @@ __global__ void __launch_bounds__(128) gelu_ln_fwd_wide_kernel(const __nv_bfloat
   pdl_wait();
   const float invF = 1.0f / static_cast<float>(F);
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    float t[NC][8];
-    float s[1] = {0.f};
+    float2 t[NC][4];
+    float2 s2 = splat2(0.f);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       const int col = (k * 128 + threadIdx.x) * 8;
       if (col < F) {
         const uint4 u = *reinterpret_cast<const uint4*>(h + static_cast<int64_t>(row) * ldh + col);
-        unpack8(u, t[k]);
+        float2 x[4];
+        unpack8p(u, x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          t[k][j] = gelu_erf(t[k][j]);
-          s[0] += t[k][j];
+        for (int j = 0; j < 4; ++j) {
+          t[k][j] = gelu_erf2(x[j]);
+          s2 = add2(s2, t[k][j]);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t[k][j] = 0.f;
+        for (int j = 0; j < 4; ++j) t[k][j] = splat2(0.f);
       }
     }
+    float s[1] = {s2.x + s2.y};
     block_sum4<1>(s, red[0]);
     const float mean = s[0] * invF;
-    float q[1] = {0.f};
+    const float2 nmean = splat2(-mean);
+    float2 q2 = splat2(0.f);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       if ((k * 128 + threadIdx.x) * 8 < F) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = t[k][j] - mean;
-          q[0] += d * d;
+        for (int j = 0; j < 4; ++j) {
+          const float2 d = add2(t[k][j], nmean);
+          q2 = fma2(d, d, q2);
         }
       }
     }
+    float q[1] = {q2.x + q2.y};
     block_sum4<1>(q, red[1]);
     const float rstd = rsqrtf(q[0] * invF + 1e-5f);
+    const float2 rs2 = splat2(rstd), nmr = splat2(-mean * rstd);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       const int col = (k * 128 + threadIdx.x) * 8;
       if (col < F) {
-        float g[8], b[8], o[8];
-        ld8g(gam, SGF_F32, col, g);
-        ld8g(bet, SGF_F32, col, b);
+        float2 g[4], b[4];
+        ld8gp(gam, col, g);
+        ld8gp(bet, col, b);
+        uint4 o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (t[k][j] - mean) * rstd * g[j] + b[j];
-        st8g(z, SGF_BF16, static_cast<int64_t>(row) * ldz + col, o);
+        for (int j = 0; j < 4; ++j) {
+          const float2 y = fma2(fma2(t[k][j], rs2, nmr), g[j], b[j]);
+          ow[j] = pack_bf16x2(y.x, y.y);
+        }
+        *reinterpret_cast<uint4*>(z + static_cast<int64_t>(row) * ldz + col) = o;
       }
     }
+  }
+}
+
+// adds 8 consecutive shared-memory partials to a global fp32 vector: two 128-bit reductions when the destination is
+// 16-byte aligned (parameter-gradient arena views normally are), scalar atomics otherwise
+SGF_DEVICE void flush8(float* __restrict__ dst, const float* __restrict__ part, int col) {
+  if (!dst) return;
+  const float4 a = *reinterpret_cast<const float4*>(part + col), b = *reinterpret_cast<const float4*>(part + col + 4);
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    red_add_f32x4(dst + col, a.x, a.y, a.z, a.w);
+    red_add_f32x4(dst + col + 4, b.x, b.y, b.z, b.w);
+  } else {
+    red_add_f32(dst + col, a.x); red_add_f32(dst + col + 1, a.y); red_add_f32(dst + col + 2, a.z);
+    red_add_f32(dst + col + 3, a.w); red_add_f32(dst + col + 4, b.x); red_add_f32(dst + col + 5, b.y);
+    red_add_f32(dst + col + 6, b.z); red_add_f32(dst + col + 7, b.w);
   }
 }
 
@@ -499,7 +807,8 @@ __global__ void __launch_bounds__(128, 4) gelu_ln_bwd_wide_kernel(const __nv_bfl
                                                                   float* __restrict__ dgam, float* __restrict__ dbet,
                                                                   float* __restrict__ dh_colsum, int rows, int F) {
   // per-CTA partials of (dgamma, dbeta, column sums of dh): thread t owns its columns in all three arrays, so plain
-  // shared-memory read-modify-writes suffice (keeps the register count low enough for 4-5 CTAs per SM)
+  // shared-memory read-modify-writes suffice (keeps the register count low enough for 4 CTAs per SM).  All
+  // elementwise arithmetic is packed fp32x2: the kernel is bound by instruction issue, not by HBM.
   extern __shared__ __align__(16) float wacc[];  // [3][F]
   __shared__ float red[2][12];
   pdl_trigger();
@@ -507,79 +816,87 @@ __global__ void __launch_bounds__(128, 4) gelu_ln_bwd_wide_kernel(const __nv_bfl
   __syncthreads();
   pdl_wait();
   const float invF = 1.0f / static_cast<float>(F);
-  auto rmw8 = [](float* a, const float (&v)[8]) {
+  auto rmw8 = [](float* a, const float2 (&v)[4]) {
     float4* q = reinterpret_cast<float4*>(a);
-    float4 u0 = q[0], u1 = q[1];
-    u0.x += v[0]; u0.y += v[1]; u0.z += v[2]; u0.w += v[3];
-    u1.x += v[4]; u1.y += v[5]; u1.z += v[6]; u1.w += v[7];
-    q[0] = u0; q[1] = u1;
+    const float4 u0 = q[0], u1 = q[1];
+    const float2 r0 = add2(make_float2(u0.x, u0.y), v[0]), r1 = add2(make_float2(u0.z, u0.w), v[1]);
+    const float2 r2 = add2(make_float2(u1.x, u1.y), v[2]), r3 = add2(make_float2(u1.z, u1.w), v[3]);
+    q[0] = make_float4(r0.x, r0.y, r1.x, r1.y);
+    q[1] = make_float4(r2.x, r2.y, r3.x, r3.y);
   };
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    uint4 hx[NC];
-    float cdf[NC][8], dzv[NC][8];  // Phi(h) and dz
-    float s[1] = {0.f};
+    uint4 dzp[NC];                  // dz, still packed
+    float2 t[NC][4], gp[NC][4];     // t = gelu(h), gp = gelu'(h)
+    float2 s2 = splat2(0.f);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       const int col = (k * 128 + threadIdx.x) * 8;
       if (col < F) {
-        hx[k] = *reinterpret_cast<const uint4*>(h + static_cast<int64_t>(row) * ldh + col);
-        const uint4 ud = *reinterpret_cast<const uint4*>(dz + static_cast<int64_t>(row) * lddz + col);
-        unpack8(ud, dzv[k]);
-        float x[8];
-        unpack8(hx[k], x);
+        const uint4 hx = *reinterpret_cast<const uint4*>(h + static_cast<int64_t>(row) * ldh + col);
+        dzp[k] = *reinterpret_cast<const uint4*>(dz + static_cast<int64_t>(row) * lddz + col);
+        float2 x[4];
+        unpack8p(hx, x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float e;
-          cdf[k][j] = gelu_cdf(x[j], e);
-          s[0] += x[j] * cdf[k][j];
+        for (int j = 0; j < 4; ++j) {
+          float2 e;
+          const float2 cdf = gelu_cdf2(x[j], e);
+          t[k][j] = mul2(x[j], cdf);
+          gp[k][j] = fma2(mul2(x[j], splat2(0.3989422804014327f)), e, cdf);  // Phi + x phi
+          s2 = add2(s2, t[k][j]);
         }
       } else {
-        hx[k] = make_uint4(0, 0, 0, 0);
+        dzp[k] = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cdf[k][j] = dzv[k][j] = 0.f;
+        for (int j = 0; j < 4; ++j) t[k][j] = gp[k][j] = splat2(0.f);
       }
     }
+    float s[1] = {s2.x + s2.y};
     block_sum4<1>(s, red[0]);
     const float mean = s[0] * invF;
-    float r3[3] = {0.f, 0.f, 0.f};  // sum (t-mean)^2, sum dz*gamma, sum dz*gamma*(t-mean)
+    const float2 nmean = splat2(-mean);
+    float2 q0 = splat2(0.f), q1 = splat2(0.f), q2 = splat2(0.f);  // sum (t-mean)^2, sum dz*gamma, sum dz*gamma*(t-mean)
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       const int col = (k * 128 + threadIdx.x) * 8;
       if (col < F) {
-        float x[8], g[8];
-        unpack8(hx[k], x);
-        ld8g(gam, SGF_F32, col, g);
+        float2 g[4], dzv[4];
+        ld8gp(gam, col, g);
+        unpack8p(dzp[k], dzv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = x[j] * cdf[k][j] - mean;
-          const float gy = dzv[k][j] * g[j];
-          r3[0] += d * d;
-          r3[1] += gy;
-          r3[2] += gy * d;
+        for (int j = 0; j < 4; ++j) {
+          const float2 d = add2(t[k][j], nmean);
+          const float2 gy = mul2(dzv[j], g[j]);
+          q0 = fma2(d, d, q0);
+          q1 = add2(q1, gy);
+          q2 = fma2(gy, d, q2);
         }
       }
     }
+    float r3[3] = {q0.x + q0.y, q1.x + q1.y, q2.x + q2.y};
     block_sum4<3>(r3, red[1]);
     const float rstd = rsqrtf(r3[0] * invF + 1e-5f);
     const float c1 = r3[1] * invF, c2 = r3[2] * invF * rstd;
+    const float2 rs2 = splat2(rstd), nmr = splat2(-mean * rstd), nc1r = splat2(-c1 * rstd), nc2r = splat2(-c2 * rstd);
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       const int col = (k * 128 + threadIdx.x) * 8;
       if (col < F) {
-        float x[8], g[8], o[8], gx[8];
-        unpack8(hx[k], x);
-        ld8g(gam, SGF_F32, col, g);
+        float2 g[4], dzv[4], o[4], gx[4];
+        ld8gp(gam, col, g);
+        unpack8p(dzp[k], dzv);
+        uint4 ou;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&ou);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (x[j] * cdf[k][j] - mean) * rstd;
-          const float dt = rstd * (dzv[k][j] * g[j] - c1 - xh * c2);
-          const float e = fast_exp2(-0.72134752044448170368f * x[j] * x[j]);  // exp(-x^2/2)
-          o[j] = dt * fmaf(x[j] * 0.3989422804014327f, e, cdf[k][j]);          // * gelu'(x) = Phi + x phi
-          gx[j] = dzv[k][j] * xh;
+        for (int j = 0; j < 4; ++j) {
+          const float2 xh = fma2(t[k][j], rs2, nmr);
+          const float2 dt = fma2(xh, nc2r, fma2(mul2(dzv[j], g[j]), rs2, nc1r));  // rstd (dz g - c1 - xh c2)
+          o[j] = mul2(dt, gp[k][j]);
+          gx[j] = mul2(dzv[j], xh);
+          ow[j] = pack_bf16x2(o[j].x, o[j].y);
         }
-        st8g(dh, SGF_BF16, static_cast<int64_t>(row) * lddh + col, o);
+        *reinterpret_cast<uint4*>(dh + static_cast<int64_t>(row) * lddh + col) = ou;
         rmw8(wacc + col, gx);
-        rmw8(wacc + F + col, dzv[k]);
+        rmw8(wacc + F + col, dzv);
         rmw8(wacc + 2 * F + col, o);
       }
     }
@@ -588,12 +905,9 @@ __global__ void __launch_bounds__(128, 4) gelu_ln_bwd_wide_kernel(const __nv_bfl
   for (int k = 0; k < NC; ++k) {
     const int col = (k * 128 + threadIdx.x) * 8;
     if (col < F) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (dgam) atomicAdd(dgam + col + j, wacc[col + j]);
-        if (dbet) atomicAdd(dbet + col + j, wacc[F + col + j]);
-        if (dh_colsum) atomicAdd(dh_colsum + col + j, wacc[2 * F + col + j]);
-      }
+      flush8(dgam, wacc, col);
+      flush8(dbet, wacc + F, col);
+      flush8(dh_colsum, wacc + 2 * F, col);
     }
   }
 }
@@ -885,6 +1199,43 @@ extern "C" int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* a, void* stream) 
   }
   const int n_acc = (a->dg2 ? 1 : 0) + (a->db2 ? 1 : 0) + (a->dg1 ? 1 : 0) + (a->db1 ? 1 : 0) + (a->d_pre_add ? 1 : 0) +
                     (a->dx_colsum ? 1 : 0);
+  RowLnBwdParams p{a->x, a->ldx, a->x_dtype, a->gather_idx, a->x_act, a->pre_add, a->g1, a->v, a->ldv, a->v_dtype,
+                   a->g2, a->dy2, a->ldy2, a->dy2_dtype, a->dv_in, a->lddv, a->d_res, a->ldres, a->dx, a->lddx,
+                   a->dx_dtype, a->dx_accumulate, a->dg1, a->db1, a->dg2, a->db2, a->d_pre_add, a->rows, a->D,
+                   a->seg_len, a->seg_stride, a->seg_off, a->dx_colsum, a->drop_p, a->droppath_p, a->drop_seed,
+                   a->drop_site, a->rows_per_sample, a->drop_step};
+  // model-width rows without an activation: register-resident kernel
+  const bool dx_ok = !a->dx || reinterpret_cast<uintptr_t>(a->dx) % 16 == 0;
+  const bool res_ok = !a->d_res || (reinterpret_cast<uintptr_t>(a->d_res) % 16 == 0 && a->ldres % 4 == 0);
+  if (a->x_act == SGF_ACT_NONE && a->D <= 1280 && dx_ok && res_ok) {
+    const int nc = (a->D + 255) / 256;
+    const size_t rsm = static_cast<size_t>(4) * n_acc * a->D * sizeof(float);
+    const int max_cta = nc <= 3 ? 3 : 2;
+    const int per_sm = rsm == 0 ? max_cta : static_cast<int>(std::min<size_t>(max_cta, (200 * 1024) / rsm));
+    const int ngrp = (a->rows + 3) / 4;
+    const int grid = ngrp < 148 * per_sm ? ngrp : 148 * per_sm;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define SGF_ROW_BWD_REG(NC)                                                                                        \
+  {                                                                                                                \
+    static bool cfgd = false;                                                                                      \
+    if (!cfgd) {                                                                                                   \
+      SGF_CHECK_CUDA(cudaFuncSetAttribute(row_layernorm_bwd_reg_kernel<NC>,                                        \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 6 * 1280 * 4));         \
+      cfgd = true;                                                                                                 \
+    }                                                                                                              \
+    SGF_CHECK_CUDA(launch_pdl(row_layernorm_bwd_reg_kernel<NC>, dim3(grid), dim3(128), rsm, st, p, n_acc));        \
+  }
+    switch (nc) {
+      case 1: SGF_ROW_BWD_REG(1) break;
+      case 2: SGF_ROW_BWD_REG(2) break;
+      case 3: SGF_ROW_BWD_REG(3) break;
+      case 4: SGF_ROW_BWD_REG(4) break;
+      default: SGF_ROW_BWD_REG(5) break;
+    }
+#undef SGF_ROW_BWD_REG
+    count_launch();
+    return SGF_OK;
+  }
   const int t_bytes = (a->x_act != SGF_ACT_NONE && x_used) ? a->D * 4 : 0;
   const int per_row = x_bytes + v_bytes + dy_bytes + dv_bytes + t_bytes + n_acc * a->D * 4;
   const int fixed = 16;
@@ -894,11 +1245,6 @@ extern "C" int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* a, void* stream) 
   else if (kRows < 2 && 2 * per_row + fixed <= 200 * 1024) kRows = 2;
   const int smem = kRows * per_row + fixed;
   SGF_REQUIRE(smem <= 200 * 1024, "row_layernorm_bwd: D=%d needs %d B of shared memory", a->D, smem);
-  RowLnBwdParams p{a->x, a->ldx, a->x_dtype, a->gather_idx, a->x_act, a->pre_add, a->g1, a->v, a->ldv, a->v_dtype,
-                   a->g2, a->dy2, a->ldy2, a->dy2_dtype, a->dv_in, a->lddv, a->d_res, a->ldres, a->dx, a->lddx,
-                   a->dx_dtype, a->dx_accumulate, a->dg1, a->db1, a->dg2, a->db2, a->d_pre_add, a->rows, a->D,
-                   a->seg_len, a->seg_stride, a->seg_off, a->dx_colsum, a->drop_p, a->droppath_p, a->drop_seed,
-                   a->drop_site, a->rows_per_sample, a->drop_step};
   static bool configured = false;
   if (!configured) {
     SGF_CHECK_CUDA(cudaFuncSetAttribute(row_layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -124,6 +124,9 @@ class _Dense:
 
 
 class SegOFATrainEngine:
+    _wstream = None  # side stream of the weight-gradient GEMMs (created on first use)
+    grad_sync = None
+
     def __init__(self, model, stochastic=True, seed=1):
         p0 = next(model.parameters())
         if not p0.is_cuda:
