@@ -7,6 +7,8 @@
 // Arithmetic mirrors ATen's upsample_bilinear2d(align_corners=False): source index
 // s = max(0, scale*(d+0.5)-0.5), i0 = (int)s, i1 = i0 + (i0 < in-1), l1 = s - i0, l0 = 1 - l1,
 // value = h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11), evaluated without FMA contraction.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sgf {
@@ -177,22 +179,33 @@ struct SeglossBwdParams {
   float scale_h, scale_w;
 };
 
-// Stage 1 (whole CTA): everything that does not depend on the class -- per footprint row / column the two taps and
-// their weights, per footprint pixel the weight w = wy*wx (0 for ignored pixels), log2e * logsumexp and the target --
-// goes to shared memory once.  Stage 2 (thread = class): per footprint row the two row taps are blended once
-// (3 values), columns are walked in runs of constant tap pair, so a pixel costs ~10 instructions
-// (2 FMA interpolation, ex2, accumulate).  Gather form: no atomics, deterministic.
+// Stage 1 (whole CTA): everything that does not depend on the class goes to shared memory once -- per footprint row
+// the two taps and their weights; the footprint columns re-laid out as RUNS of constant tap pair, each run padded to a
+// multiple of four columns (padding carries weight 0 / logsumexp +inf, i.e. contributes exactly 0); per footprint
+// pixel the weight w = wy*wx (0 for ignored pixels) and -log2e * logsumexp; and the class-dependent one-hot term
+// sum_{pixels with target c} w as a fixed-point histogram (native integer shared-memory atomics).
+// Stage 2 (thread = class): per footprint row the two row taps are blended once (3 values); inside a run four
+// pixels cost four 128-bit shared loads, six packed-fp32x2 FMAs and four ex2 -- the kernel runs at the MUFU rate.
+// Gather form: no global atomics, deterministic.
 struct FootTap {
   float l0, l1, w;
   int i0, i1;  // tap indices relative to (p - 1): 0..2
 };
+static constexpr int kCeMaxRuns = 64;
 
-__global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const SeglossBwdParams p, const int fy_max, const int fx_max) {
+__global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const SeglossBwdParams p, const int fy_max, const int fx_max,
+                                                              const int nxp_max, const float qscale) {
   extern __shared__ __align__(16) uint8_t ce_smem[];
-  float2* pixv = reinterpret_cast<float2*>(ce_smem);              // (w, log2e * lse) per footprint pixel
-  int* pixt = reinterpret_cast<int*>(pixv + fy_max * fx_max);      // target class (or -1)
-  FootTap* rowp = reinterpret_cast<FootTap*>(pixt + fy_max * fx_max);
+  float* pw = reinterpret_cast<float*>(ce_smem);                  // [nY][nXp] pixel weight
+  float* pl = pw + fy_max * nxp_max;                               // [nY][nXp] -log2e * lse
+  float* cl0 = pl + fy_max * nxp_max;                              // [nXp] column tap weights (run-padded layout)
+  float* cl1 = cl0 + nxp_max;
+  int4* runs = reinterpret_cast<int4*>(cl1 + nxp_max);             // (base, padded length, q0, q1)
+  FootTap* rowp = reinterpret_cast<FootTap*>(runs + kCeMaxRuns);
   FootTap* colp = rowp + fy_max;
+  int* colpos = reinterpret_cast<int*>(colp + fx_max);             // footprint column -> run-padded position
+  int* hitq = colpos + fx_max;                                     // [C] fixed-point one-hot weights; [C] = total
+  __shared__ int s_nruns, s_nxp;
   const int tok = blockIdx.x;
   const int b = blockIdx.y;
   __nv_bfloat16* drow = p.dlogits + static_cast<int64_t>(b) * p.d_batch_stride + static_cast<int64_t>(tok) * p.d_tok_stride;
@@ -225,18 +238,60 @@ __global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const SeglossBwdPa
     t.i1 = min(max(i1 - (want - 1), 0), 2);
     (is_row ? rowp[i] : colp[i - nY]) = t;
   }
+  for (int i = threadIdx.x; i <= p.C; i += blockDim.x) hitq[i] = 0;
   __syncthreads();
+  if (threadIdx.x == 0) {  // run layout (a handful of runs: the tap pair changes once per source column)
+    int nr = 0, pos = 0;
+    for (int ix = 0; ix < nX; ++ix) {
+      const bool fresh = ix == 0 || colp[ix].i0 != colp[ix - 1].i0 || colp[ix].i1 != colp[ix - 1].i1;
+      if (fresh && nr < kCeMaxRuns) {
+        if (nr > 0) runs[nr - 1].y = ((pos + 3) & ~3) - runs[nr - 1].x;
+        pos = (pos + 3) & ~3;
+        runs[nr++] = make_int4(pos, 0, colp[ix].i0, colp[ix].i1);
+      }
+      colpos[ix] = pos;
+      ++pos;
+    }
+    pos = (pos + 3) & ~3;
+    if (nr > 0) runs[nr - 1].y = pos - runs[nr - 1].x;
+    s_nruns = nr;
+    s_nxp = min(pos, nxp_max);
+  }
+  __syncthreads();
+  const int nXp = s_nxp, nruns = s_nruns;
+  for (int i = threadIdx.x; i < nXp; i += blockDim.x) cl0[i] = cl1[i] = 0.f;
+  for (int i = threadIdx.x; i < nY * nXp; i += blockDim.x) {
+    pw[i] = 0.f;
+    pl[i] = -INFINITY;
+  }
+  __syncthreads();
+  for (int ix = threadIdx.x; ix < nX; ix += blockDim.x) {
+    const int pos = colpos[ix];
+    if (pos < nXp) {
+      cl0[pos] = colp[ix].l0;
+      cl1[pos] = colp[ix].l1;
+    }
+  }
+  int swq = 0;
   for (int i = threadIdx.x; i < nY * nX; i += blockDim.x) {
     const int iy = i / nX, ix = i - iy * nX;
     const float w = rowp[iy].w * colp[ix].w;
     const int64_t pix = (static_cast<int64_t>(b) * p.h + (ylo + iy)) * p.w + (xlo + ix);
     const int64_t t = p.target[pix];
-    const bool ok = w != 0.f && t >= 0 && t < p.C;
-    pixv[i] = ok ? make_float2(w, p.lse[pix] * 1.4426950408889634f) : make_float2(0.f, INFINITY);
-    pixt[i] = ok ? static_cast<int>(t) : -1;
+    const int pos = colpos[ix];
+    if (w != 0.f && t >= 0 && t < p.C && pos < nXp) {
+      pw[iy * nXp + pos] = w;
+      pl[iy * nXp + pos] = p.lse[pix] * -1.4426950408889634f;
+      const int q = __float2int_rn(w * qscale);
+      atomicAdd(&hitq[static_cast<int>(t)], q);
+      swq += q;
+    }
   }
+  swq = __reduce_add_sync(0xffffffffu, swq);
+  if ((threadIdx.x & 31) == 0 && swq != 0) atomicAdd(&hitq[p.C], swq);
   __syncthreads();
   const float inv_cnt = p.grad_scale / fmaxf(p.count[0], 1.0f);
+  const float inv_q = 1.0f / qscale;
   const float* base = p.logits + static_cast<int64_t>(b) * p.batch_stride;
   const float uni = p.eps / static_cast<float>(p.C);
   const float hit = 1.f - p.eps;
@@ -253,36 +308,39 @@ __global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const SeglossBwdPa
         const int yy = min(max(py - 1 + dy, 0), p.hp - 1), xx = min(max(px - 1 + dx, 0), p.wp - 1);
         nb[dy][dx] = __ldg(base + static_cast<int64_t>(yy * p.wp + xx) * p.tok_stride + c);
       }
-    float g = 0.f, sw = 0.f;
+    float2 g2 = make_float2(0.f, 0.f);
     for (int iy = 0; iy < nY; ++iy) {
       const FootTap rp = rowp[iy];
       if (rp.w == 0.f) continue;  // CTA-uniform
-      float a[3];  // the two row taps blended, per neighbourhood column
+      float a[3];  // log2e * (the two row taps blended), per neighbourhood column
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
         const float top = rp.i0 == 0 ? nb[0][dx] : (rp.i0 == 1 ? nb[1][dx] : nb[2][dx]);
         const float bot = rp.i1 == 0 ? nb[0][dx] : (rp.i1 == 1 ? nb[1][dx] : nb[2][dx]);
-        a[dx] = rp.l0 * top + rp.l1 * bot;
+        a[dx] = (rp.l0 * top + rp.l1 * bot) * 1.4426950408889634f;
       }
-      const float2* pv = pixv + iy * nX;
-      const int* pt = pixt + iy * nX;
-      int ix = 0;
-      while (ix < nX) {  // run of columns sharing one tap pair
-        const int q0 = colp[ix].i0, q1 = colp[ix].i1;
-        const float vL = (q0 == 0 ? a[0] : (q0 == 1 ? a[1] : a[2])) * 1.4426950408889634f;
-        const float vR = (q1 == 0 ? a[0] : (q1 == 1 ? a[1] : a[2])) * 1.4426950408889634f;
-        for (; ix < nX && colp[ix].i0 == q0 && colp[ix].i1 == q1; ++ix) {
-          const float2 wl = pv[ix];
-          if (wl.x == 0.f) continue;  // CTA-uniform: ignored pixel or zero weight
-          const float v2 = fmaf(colp[ix].l0, vL, colp[ix].l1 * vR);  // log2e * interpolated logit
-          const float prob = fast_exp2(v2 - wl.y);
-          g = fmaf(wl.x, prob, g);
-          sw += wl.x;
-          if (pt[ix] == c) g = fmaf(-wl.x, hit, g);
+      for (int r = 0; r < nruns; ++r) {
+        const int4 run = runs[r];
+        const float2 vL = splat2(run.z == 0 ? a[0] : (run.z == 1 ? a[1] : a[2]));
+        const float2 vR = splat2(run.w == 0 ? a[0] : (run.w == 1 ? a[1] : a[2]));
+        const float4* c0 = reinterpret_cast<const float4*>(cl0 + run.x);
+        const float4* c1 = reinterpret_cast<const float4*>(cl1 + run.x);
+        const float4* wr = reinterpret_cast<const float4*>(pw + iy * nXp + run.x);
+        const float4* lr = reinterpret_cast<const float4*>(pl + iy * nXp + run.x);
+        const int n4 = run.y >> 2;
+#pragma unroll 2
+        for (int i = 0; i < n4; ++i) {
+          const float4 A = c0[i], Bc = c1[i], W = wr[i], L = lr[i];
+          const float2 v0 = fma2(make_float2(A.x, A.y), vL, fma2(make_float2(Bc.x, Bc.y), vR, make_float2(L.x, L.y)));
+          const float2 v1 = fma2(make_float2(A.z, A.w), vL, fma2(make_float2(Bc.z, Bc.w), vR, make_float2(L.z, L.w)));
+          g2 = fma2(make_float2(W.x, W.y), make_float2(fast_exp2(v0.x), fast_exp2(v0.y)), g2);
+          g2 = fma2(make_float2(W.z, W.w), make_float2(fast_exp2(v1.x), fast_exp2(v1.y)), g2);
         }
       }
     }
-    g = fmaf(-uni, sw, g);
+    float g = g2.x + g2.y;
+    g = fmaf(-hit * inv_q, static_cast<float>(hitq[c]), g);
+    g = fmaf(-uni * inv_q, static_cast<float>(hitq[p.C]), g);
     drow[c] = __float2bfloat16_rn(g * inv_cnt);
   }
 }
@@ -459,7 +517,17 @@ extern "C" int sgf_upsample_ce_loss_bwd(const sgf_segloss_bwd_args* a, void* str
   // footprint bound: 2 patches of pixels plus the conservative margins; border patches take the clamped rows too
   const int fy_max = 2 * ((a->h + a->hp - 1) / a->hp) + 6 + (a->h + a->hp - 1) / a->hp;
   const int fx_max = 2 * ((a->w + a->wp - 1) / a->wp) + 6 + (a->w + a->wp - 1) / a->wp;
-  const size_t smem = static_cast<size_t>(fy_max + fx_max) * sizeof(FootTap) + static_cast<size_t>(fy_max) * fx_max * 12;
+  // run-padded row length: every run of constant tap pair is padded to a multiple of 4 columns; when up-sampling the
+  // tap pair changes at most every (w/wp) columns, when down-sampling it may change at every column
+  const int max_runs = a->w >= a->wp ? std::min(kCeMaxRuns, fx_max / std::max(1, a->w / a->wp) + 3) : std::min(kCeMaxRuns, fx_max);
+  const int nxp_max = (fx_max + 3 * max_runs + 7) & ~3;
+  // fixed-point scale of the one-hot histogram: the weights of one footprint sum to < 4 (h/hp)(w/wp)
+  const double wsum_bound = 4.0 * ((a->h + a->hp - 1) / a->hp) * ((a->w + a->wp - 1) / a->wp);
+  float qscale = 1.0f;
+  while (static_cast<double>(qscale) * 2.0 * wsum_bound < 1073741824.0) qscale *= 2.0f;
+  const size_t smem = static_cast<size_t>(2) * fy_max * nxp_max * 4 + static_cast<size_t>(2) * nxp_max * 4 +
+                      kCeMaxRuns * sizeof(int4) + static_cast<size_t>(fy_max + fx_max) * sizeof(FootTap) +
+                      static_cast<size_t>(fx_max) * 4 + static_cast<size_t>(a->C + 1) * 4 + 16;
   SGF_REQUIRE(smem <= 160 * 1024, "upsample_ce_loss_bwd: up-sampling factor too large (%zu B of shared memory)", smem);
   static size_t configured = 0;
   if (smem > configured) {
@@ -467,7 +535,7 @@ extern "C" int sgf_upsample_ce_loss_bwd(const sgf_segloss_bwd_args* a, void* str
     configured = 160 * 1024;
   }
   dim3 grid(a->d_tokens, a->B);
-  upsample_ce_bwd_kernel<<<grid, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p, fy_max, fx_max);
+  upsample_ce_bwd_kernel<<<grid, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p, fy_max, fx_max, nxp_max, qscale);
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return SGF_OK;

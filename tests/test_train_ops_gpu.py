@@ -204,7 +204,9 @@ def test_gemm_mixed_major_dgrad(ops, M, N, K):
 
 # ----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,C,hp,wp,h,w,eps", [(2, 15, 8, 8, 128, 128, 0.0), (1, 150, 4, 4, 64, 64, 0.1),
-                                                (2, 171, 30, 30, 480, 480, 0.0), (1, 15, 6, 5, 100, 75, 0.0)])
+                                                (2, 171, 30, 30, 480, 480, 0.0), (1, 15, 6, 5, 100, 75, 0.0),
+                                                (1, 15, 16, 12, 10, 9, 0.1), (1, 40, 5, 7, 83, 101, 0.0),
+                                                (1, 8, 4, 4, 128, 128, 0.0)])
 def test_upsample_ce_backward(ops, B, C, hp, wp, h, w, eps):
     g = _gen(C + hp)
     Td = hp * wp + 1
