@@ -38,6 +38,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline family's largest kernel, from the
+# committed `ncu --set full` captures (the roofline is tensor-bound; traffic is reported to show there are no wasted
+# re-reads: it is below the algorithmic operand bytes because C tiles stay in the 126 MB L2)
+NCU_TRAFFIC = {
+    2: (15.79e6, "gemm2p_tcgen05_kernel<6> (fc1: M=7208 N=3072 K=768; algorithmic operand bytes 60.1 MB), "
+                 "profiles/r01_gemm2p_final_full.txt"),
+    3: (68.95e6, "gemm_mm_tcgen05_kernel<128,3,1,1,1152> (split-K weight gradient, fp32 accumulate; "
+                 "algorithmic 77.9 MB for the fc weight gradient), profiles/r01_trainmisc_final_full.txt"),
+}
 FLOPS_PER_IMG = {2: 286.8e9, 4: 364.6e9, 3: 1061.2e9, 5: 6465.3e9}  # SURVEY.md s8d (forward / train step, algorithmic)
 CONFIGS = {
     # id: (arch, image, classes, batch, description)
@@ -284,7 +293,9 @@ def bench_train(args, rank, world, local_rank, config):
             "gpu_launches": sess.launches_per_step * args.steps, "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05", "achieved": achieved,
                          "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                         "traffic": None, "peak_source": peaks["source"] + " (bf16 sustained)",
+                         "traffic": NCU_TRAFFIC.get(args.config, (None, None))[0],
+                         "traffic_source": NCU_TRAFFIC.get(args.config, (None, None))[1],
+                         "peak_source": peaks["source"] + " (bf16 sustained)",
                          "launches_per_step": d["launches"], "share_of_step_kernel_time": d["ms"] / total_k_ms,
                          "step": {"achieved": step_tflops, "frac": step_tflops / peaks["bf16_sustained"],
                                   "flops_per_image": FLOPS_PER_IMG[args.config]}},
@@ -461,7 +472,9 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peaks["bf16_sustained"],
-                         "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                         "traffic": NCU_TRAFFIC.get(args.config, (None, None))[0],
+                         "traffic_source": NCU_TRAFFIC.get(args.config, (None, None))[1],
                          "peak_source": peaks["source"] + " (bf16 sustained: kernel timed inside a long step)",
                          "launches_per_step": d["launches"], "share_of_step_kernel_time": d["ms"] / total_k_ms,
                          "step": {"achieved": step_tflops, "frac": step_tflops / peaks["bf16_sustained"],
