@@ -295,7 +295,7 @@ SGF_DEVICE void store8p(void* base, int dtype, int64_t off, const float2 (&v)[4]
 }
 
 template <int NC>
-__global__ void __launch_bounds__(128, NC <= 3 ? 4 : 3) row_layernorm_reg_kernel(const RowLnParams p) {
+__global__ void __launch_bounds__(128, NC <= 3 ? 5 : 3) row_layernorm_reg_kernel(const RowLnParams p) {
   pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float invD = 1.0f / static_cast<float>(p.D);
@@ -667,6 +667,8 @@ extern "C" int sgf_embedding_bag_mean(const int64_t* tokens, int64_t ld_tokens, 
 namespace sgf {
 int launch_gelu_ln_fwd_wide(const void* h, int64_t ldh, const float* g, const float* b, void* z, int64_t ldz, int rows,
                             int F, cudaStream_t st);  // train.cu
+int launch_ln_fwd_wide_plain(const void* h, int64_t ldh, const float* g, const float* b, void* z, int64_t ldz, int rows,
+                             int F, cudaStream_t st);  // train.cu
 }
 
 extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
@@ -678,6 +680,13 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
       reinterpret_cast<uintptr_t>(a->x) % 16 == 0 && reinterpret_cast<uintptr_t>(a->out2) % 16 == 0)
     return launch_gelu_ln_fwd_wide(a->x, a->ldx, a->g2, a->b2, a->out2, a->ld2, a->rows, a->D,
                                    reinterpret_cast<cudaStream_t>(stream));
+  // plain wide LayerNorm (the inference FFN: GELU already applied by the GEMM epilogue)
+  if (a->x_act == SGF_ACT_NONE && a->x_dtype == SGF_BF16 && !a->gather_idx && !a->pre_add && !a->g1 && !a->residual &&
+      !a->out1 && a->out2 && a->g2 && a->b2 && !a->zero_row && a->seg_len == 0 && !a->clear_rowstats && a->D >= 1536 &&
+      a->drop_p == 0.f && a->droppath_p == 0.f && a->D <= 8192 && a->D % 512 == 0 && a->rows > 0 && a->ldx % 8 == 0 &&
+      a->ld2 % 8 == 0 && reinterpret_cast<uintptr_t>(a->x) % 16 == 0 && reinterpret_cast<uintptr_t>(a->out2) % 16 == 0)
+    return launch_ln_fwd_wide_plain(a->x, a->ldx, a->g2, a->b2, a->out2, a->ld2, a->rows, a->D,
+                                    reinterpret_cast<cudaStream_t>(stream));
   SGF_REQUIRE(a->rows > 0 && a->D > 0 && a->D % 8 == 0, "row_layernorm: D must be a positive multiple of 8 (D=%d)", a->D);
   SGF_REQUIRE(a->D <= 5120, "row_layernorm: D=%d exceeds the 5120 register-resident limit", a->D);
   SGF_REQUIRE((a->g1 == nullptr) == (a->b1 == nullptr), "row_layernorm: g1/b1 must both be set or both null");
@@ -700,7 +709,7 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
   if (a->x_act == SGF_ACT_NONE && a->D <= 1280 && out_ok) {  // model-width rows: register-resident kernel
     const int nc = (a->D + 255) / 256;
     const int ngrp = (a->rows + 3) / 4;
-    const int resident = 148 * (nc <= 3 ? 4 : 3);
+    const int resident = 148 * (nc <= 3 ? 5 : 3);
     const dim3 grid(ngrp < resident ? ngrp : resident), block(128);
     switch (nc) {
       case 1: SGF_CHECK_CUDA(launch_pdl(row_layernorm_reg_kernel<1>, grid, block, size_t(0), st, p)); break;

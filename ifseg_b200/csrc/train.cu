@@ -912,6 +912,195 @@ __global__ void __launch_bounds__(128, 4) gelu_ln_bwd_wide_kernel(const __nv_bfl
   }
 }
 
+// ----------------------------------------------------------------------------------------
+// Wide rows, second generation (F a multiple of 512): CTA = F/16 threads per row, thread t owns the two 8-column
+// chunks t and t + F/16 -- for EVERY row the CTA walks, so gamma/beta live in registers and the parameter-gradient
+// partials are thread-private.  One pass computes every row statistic the (adjoint) LayerNorm needs
+// (sum t, sum t^2, sum dz g, sum dz g t), so a row costs ONE block reduction; the next row's loads are issued
+// before the current row is processed.
+// ----------------------------------------------------------------------------------------
+template <int NV>
+SGF_DEVICE void block_sum_nw(float (&v)[NV], float* red /* [NV][16] */, int nw) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[i * 16 + (threadIdx.x >> 5)] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float a = 0.f;
+    for (int w = 0; w < nw; ++w) a += red[i * 16 + w];
+    v[i] = a;
+  }
+}
+
+template <bool kGelu>
+__global__ void __launch_bounds__(512) ln_fwd_wide2_kernel(const __nv_bfloat16* __restrict__ h, int64_t ldh,
+                                                           const float* __restrict__ gam, const float* __restrict__ bet,
+                                                           __nv_bfloat16* __restrict__ z, int64_t ldz, int rows, int F) {
+  __shared__ float red[2][2 * 16];
+  pdl_trigger();
+  const int NT = blockDim.x, nw = NT >> 5;
+  const int col[2] = {static_cast<int>(threadIdx.x) * 8, (static_cast<int>(threadIdx.x) + NT) * 8};
+  float2 g[2][4], b[2][4];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    ld8gp(gam, col[k], g[k]);
+    ld8gp(bet, col[k], b[k]);
+  }
+  pdl_wait();
+  const float invF = 1.0f / static_cast<float>(F);
+  int row = blockIdx.x;
+  uint4 nx[2];
+  if (row < rows) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) nx[k] = *reinterpret_cast<const uint4*>(h + static_cast<int64_t>(row) * ldh + col[k]);
+  }
+  for (int par = 0; row < rows; row += gridDim.x, par ^= 1) {
+    const uint4 cur[2] = {nx[0], nx[1]};
+    const int nrow = row + gridDim.x;
+    if (nrow < rows) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) nx[k] = *reinterpret_cast<const uint4*>(h + static_cast<int64_t>(nrow) * ldh + col[k]);
+    }
+    float2 t[2][4];
+    float2 s2 = splat2(0.f), q2 = splat2(0.f);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      unpack8p(cur[k], t[k]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (kGelu) t[k][j] = gelu_erf2(t[k][j]);
+        s2 = add2(s2, t[k][j]);
+        q2 = fma2(t[k][j], t[k][j], q2);
+      }
+    }
+    float st[2] = {s2.x + s2.y, q2.x + q2.y};
+    block_sum_nw<2>(st, red[par], nw);
+    const float mean = st[0] * invF;
+    const float rstd = rsqrtf(fmaxf(st[1] * invF - mean * mean, 0.f) + 1e-5f);
+    const float2 rs2 = splat2(rstd), nmr = splat2(-mean * rstd);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 y = fma2(fma2(t[k][j], rs2, nmr), g[k][j], b[k][j]);
+        ow[j] = pack_bf16x2(y.x, y.y);
+      }
+      *reinterpret_cast<uint4*>(z + static_cast<int64_t>(row) * ldz + col[k]) = o;
+    }
+  }
+}
+
+template <int NT>
+__global__ void __maxnreg__(NT == 192 ? 112 : 128) gelu_ln_bwd_wide2_kernel(const __nv_bfloat16* __restrict__ h, int64_t ldh,
+                                                                const __nv_bfloat16* __restrict__ dz, int64_t lddz,
+                                                                const float* __restrict__ gam,
+                                                                __nv_bfloat16* __restrict__ dh, int64_t lddh,
+                                                                float* __restrict__ dgam, float* __restrict__ dbet,
+                                                                float* __restrict__ dh_colsum, int rows, int F) {
+  extern __shared__ __align__(16) float wacc[];  // [3][F]: (dgamma, dbeta, column sums of dh); thread-private columns
+  __shared__ float red[2][4 * 16];
+  pdl_trigger();
+  constexpr int nw = NT >> 5;
+  const int col[2] = {static_cast<int>(threadIdx.x) * 8, (static_cast<int>(threadIdx.x) + NT) * 8};
+  float2 g[2][4];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    ld8gp(gam, col[k], g[k]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      *reinterpret_cast<float4*>(wacc + a * F + col[k]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(wacc + a * F + col[k] + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  pdl_wait();
+  const float invF = 1.0f / static_cast<float>(F);
+  auto rmw8 = [](float* a, const float2 (&v)[4]) {
+    float4* q = reinterpret_cast<float4*>(a);
+    const float4 u0 = q[0], u1 = q[1];
+    const float2 r0 = add2(make_float2(u0.x, u0.y), v[0]), r1 = add2(make_float2(u0.z, u0.w), v[1]);
+    const float2 r2 = add2(make_float2(u1.x, u1.y), v[2]), r3 = add2(make_float2(u1.z, u1.w), v[3]);
+    q[0] = make_float4(r0.x, r0.y, r1.x, r1.y);
+    q[1] = make_float4(r2.x, r2.y, r3.x, r3.y);
+  };
+  int row = blockIdx.x;
+  uint4 nh[2], nd[2];
+  if (row < rows) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      nh[k] = *reinterpret_cast<const uint4*>(h + static_cast<int64_t>(row) * ldh + col[k]);
+      nd[k] = *reinterpret_cast<const uint4*>(dz + static_cast<int64_t>(row) * lddz + col[k]);
+    }
+  }
+  for (int par = 0; row < rows; row += gridDim.x, par ^= 1) {
+    const uint4 ch[2] = {nh[0], nh[1]}, cd[2] = {nd[0], nd[1]};
+    const int nrow = row + gridDim.x;
+    if (nrow < rows) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        nh[k] = *reinterpret_cast<const uint4*>(h + static_cast<int64_t>(nrow) * ldh + col[k]);
+        nd[k] = *reinterpret_cast<const uint4*>(dz + static_cast<int64_t>(nrow) * lddz + col[k]);
+      }
+    }
+    float2 t[2][4], gp[2][4];  // t = gelu(h), gp = gelu'(h)
+    float2 a0 = splat2(0.f), a1 = splat2(0.f), a2 = splat2(0.f), a3 = splat2(0.f);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float2 x[4], dzv[4];
+      unpack8p(ch[k], x);
+      unpack8p(cd[k], dzv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 e;
+        const float2 cdf = gelu_cdf2(x[j], e);
+        t[k][j] = mul2(x[j], cdf);
+        gp[k][j] = fma2(mul2(x[j], splat2(0.3989422804014327f)), e, cdf);  // Phi + x phi
+        const float2 gy = mul2(dzv[j], g[k][j]);
+        a0 = add2(a0, t[k][j]);
+        a1 = fma2(t[k][j], t[k][j], a1);
+        a2 = add2(a2, gy);
+        a3 = fma2(gy, t[k][j], a3);
+      }
+    }
+    float st[4] = {a0.x + a0.y, a1.x + a1.y, a2.x + a2.y, a3.x + a3.y};
+    block_sum_nw<4>(st, red[par], nw);
+    const float mean = st[0] * invF;
+    const float rstd = rsqrtf(fmaxf(st[1] * invF - mean * mean, 0.f) + 1e-5f);
+    const float c1 = st[2] * invF, c2 = (st[3] - mean * st[2]) * invF * rstd;
+    const float2 rs2 = splat2(rstd), nmr = splat2(-mean * rstd), nc1r = splat2(-c1 * rstd), nc2r = splat2(-c2 * rstd);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float2 dzv[4], o[4], gx[4];
+      unpack8p(cd[k], dzv);
+      uint4 ou;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&ou);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xh = fma2(t[k][j], rs2, nmr);
+        const float2 dt = fma2(xh, nc2r, fma2(mul2(dzv[j], g[k][j]), rs2, nc1r));  // rstd (dz g - c1 - xh c2)
+        o[j] = mul2(dt, gp[k][j]);
+        gx[j] = mul2(dzv[j], xh);
+        ow[j] = pack_bf16x2(o[j].x, o[j].y);
+      }
+      *reinterpret_cast<uint4*>(dh + static_cast<int64_t>(row) * lddh + col[k]) = ou;
+      rmw8(wacc + col[k], gx);
+      rmw8(wacc + F + col[k], dzv);
+      rmw8(wacc + 2 * F + col[k], o);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    flush8(dgam, wacc, col[k]);
+    flush8(dbet, wacc + F, col[k]);
+    flush8(dh_colsum, wacc + 2 * F, col[k]);
+  }
+}
+
 // column sums of a bf16 [M,N] matrix (bias gradients): block = 256 columns x 256 rows, warp w walks rows w, w+8, ...
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int M, int N,
                                                           float* __restrict__ out) {
@@ -1176,6 +1365,31 @@ extern "C" int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* a, void* stream) 
     auto dz = reinterpret_cast<const __nv_bfloat16*>(a->dy2);
     auto dh = reinterpret_cast<__nv_bfloat16*>(a->dx);
     const size_t wsm = static_cast<size_t>(3) * a->D * sizeof(float);
+    if (a->D % 1024 == 0 || a->D == 3072 || a->D == 5120) {  // second-generation kernel: F/16 threads per row
+      const int nt = a->D / 16;
+#define SGF_WIDE2_BWD(NT)                                                                                            \
+  if (nt == NT) {                                                                                                    \
+    static int per_sm = 0;                                                                                           \
+    if (!per_sm) {                                                                                                   \
+      SGF_CHECK_CUDA(cudaFuncSetAttribute(gelu_ln_bwd_wide2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          3 * 16 * NT * 4));                                                         \
+      int n = 0;                                                                                                     \
+      SGF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gelu_ln_bwd_wide2_kernel<NT>, NT, wsm));      \
+      per_sm = n > 0 ? n : 1;                                                                                        \
+    }                                                                                                                \
+    const int g2 = a->rows < 148 * per_sm ? a->rows : 148 * per_sm;                                                  \
+    SGF_CHECK_CUDA(launch_pdl(gelu_ln_bwd_wide2_kernel<NT>, dim3(g2), dim3(NT), wsm, st, h, a->ldx, dz, a->ldy2,     \
+                              a->g2, dh, a->lddx, a->dg2, a->db2, a->dx_colsum, a->rows, a->D));                     \
+    count_launch();                                                                                                  \
+    return SGF_OK;                                                                                                   \
+  }
+      SGF_WIDE2_BWD(64)
+      SGF_WIDE2_BWD(128)
+      SGF_WIDE2_BWD(192)
+      SGF_WIDE2_BWD(256)
+      SGF_WIDE2_BWD(320)
+#undef SGF_WIDE2_BWD
+    }
 #define SGF_WIDE_BWD(NC)                                                                                          \
   {                                                                                                               \
     static bool cfgd = false;                                                                                     \
@@ -1261,8 +1475,32 @@ extern "C" int sgf_row_layernorm_bwd(const sgf_rowln_bwd_args* a, void* stream) 
 
 namespace sgf {
 // called by sgf_row_layernorm (rowops.cu) for the x_act == GELU, F-wide, plain LN2 pattern
+template <bool kGelu>
+static int launch_ln_fwd_wide2(const __nv_bfloat16* hp, int64_t ldh, const float* g, const float* b, __nv_bfloat16* zp,
+                               int64_t ldz, int rows, int F, cudaStream_t st) {
+  const int nt = F / 16;
+  static int per_sm[17] = {0};
+  if (!per_sm[nt / 32]) {
+    int n = 0;
+    SGF_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ln_fwd_wide2_kernel<kGelu>, nt, 0));
+    per_sm[nt / 32] = n > 0 ? n : 1;
+  }
+  const int grid = rows < 148 * per_sm[nt / 32] ? rows : 148 * per_sm[nt / 32];
+  SGF_CHECK_CUDA(launch_pdl(ln_fwd_wide2_kernel<kGelu>, dim3(grid), dim3(nt), size_t(0), st, hp, ldh, g, b, zp, ldz, rows, F));
+  count_launch();
+  return SGF_OK;
+}
+// plain wide LayerNorm (no activation): bf16 in, bf16 out
+int launch_ln_fwd_wide_plain(const void* h, int64_t ldh, const float* g, const float* b, void* z, int64_t ldz, int rows,
+                             int F, cudaStream_t st) {
+  return launch_ln_fwd_wide2<false>(reinterpret_cast<const __nv_bfloat16*>(h), ldh, g, b,
+                                    reinterpret_cast<__nv_bfloat16*>(z), ldz, rows, F, st);
+}
 int launch_gelu_ln_fwd_wide(const void* h, int64_t ldh, const float* g, const float* b, void* z, int64_t ldz, int rows,
                             int F, cudaStream_t st) {
+  if (F % 512 == 0 && F <= 8192)
+    return launch_ln_fwd_wide2<true>(reinterpret_cast<const __nv_bfloat16*>(h), ldh, g, b,
+                                     reinterpret_cast<__nv_bfloat16*>(z), ldz, rows, F, st);
   const int nc = (F + 1023) / 1024;
   const int grid = rows < 148 * 6 ? rows : 148 * 6;
   auto hp = reinterpret_cast<const __nv_bfloat16*>(h);
