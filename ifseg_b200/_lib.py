@@ -147,6 +147,7 @@ class AttentionBwdArgs(C.Structure):
         ("dq_scale", _f32),
         ("B", _i32), ("H", _i32), ("Tq", _i32), ("Tk", _i32), ("causal", _i32),
         ("dbias", _vp),
+        ("bias_t", _vp), ("bias_t_head_stride", _i64), ("bias_t_row_stride", _i64),
     ]
 
 
@@ -194,6 +195,7 @@ EXPORTS = [
     ("sgf_row_layernorm_bwd", C.c_int, [C.POINTER(RowLnBwdArgs), _vp]),
     ("sgf_transpose_cast", C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp]),
     ("sgf_attention_bwd_bf16", C.c_int, [C.POINTER(AttentionBwdArgs), _vp]),
+    ("sgf_transpose16_batched", C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _i64, _vp]),
     ("sgf_attn_bias_bwd", C.c_int, [C.POINTER(BiasBwdArgs), _vp]),
     ("sgf_artificial_sample", C.c_int, [C.POINTER(ArtSampleArgs), _vp]),
     ("sgf_adam_step", C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp, _vp]),

@@ -17,6 +17,8 @@
 // free of atomics and deterministic.
 #include <string.h>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sgf {
@@ -28,7 +30,7 @@ static constexpr int kBwdThreads = 160;
 static constexpr float kLog2eB = 1.4426950408889634f;
 
 struct AttnBwdParams {
-  const float* bias; int64_t bias_head_stride, bias_row_stride;
+  const __half* bias; int64_t bias_head_stride, bias_row_stride;  // fp16, the tensor the forward kernel streamed
   const float* head_scale;
   const uint8_t* kpm;
   const float* lse;
@@ -38,6 +40,7 @@ struct AttnBwdParams {
   void* dv; int64_t dv_row_stride, dv_batch_stride;
   int B, H, Tq, Tk, causal;
   float* dbias;  // optional fp32 [H,Tq,bias_row_stride]: += dS summed over the batch (vector atomics)
+  const __half* bias_t; int64_t bias_t_head_stride, bias_t_row_stride;  // optional transposed copy [H,Tk,>=roundup(Tq,64)]
 };
 
 // ----------------------------------------------------------------------------------------
@@ -90,19 +93,19 @@ struct DqSmem {
   static constexpr int kQ = kBT * kHd * 2;       // 16 KB (Q, dO)
   static constexpr int kKV = kBS * kHd * 2;      // 8 KB
   static constexpr int kDS = kBT * kBS * 2;      // 16 KB
-  static constexpr int kBias = kBT * kBS * 4;    // 32 KB
+  static constexpr int kBias = kBT * kBS * 2;    // 16 KB fp16 tile (one 128B-swizzled [128 x 64] box), two buffers
   static constexpr int offQ = 0;
   static constexpr int offDO = offQ + kQ;
   static constexpr int offK = offDO + kQ;
   static constexpr int offV = offK + 2 * kKV;
   static constexpr int offDS = offV + 2 * kKV;
   static constexpr int offBias = offDS + kDS;
-  static constexpr int offBar = offBias + kBias;
+  static constexpr int offBar = offBias + 2 * kBias;
   static constexpr int kTotal = offBar + 256;
 };
 struct DqBars {
   uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2];
-  uint64_t sdp_full, sdp_empty, b_empty, ds_full, ds_empty, dq_done;
+  uint64_t sdp_full, sdp_empty, b_full[2], b_empty[2], ds_full, ds_empty, dq_done;
   uint32_t tmem_slot;
 };
 static_assert(sizeof(DqBars) <= 256, "barrier block");
@@ -133,9 +136,12 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dq_kernel(const __gri
       mbar_init(&bars->v_full[i], 1);
       mbar_init(&bars->v_empty[i], 1);
     }
-    mbar_init(&bars->sdp_full, p.bias ? 2 : 1);
+    mbar_init(&bars->sdp_full, 1);
     mbar_init(&bars->sdp_empty, 128);
-    mbar_init(&bars->b_empty, 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->b_full[i], 1);
+      mbar_init(&bars->b_empty[i], 128);
+    }
     mbar_init(&bars->ds_full, 128);
     mbar_init(&bars->ds_empty, 1);
     mbar_init(&bars->dq_done, 1);
@@ -174,10 +180,10 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dq_kernel(const __gri
         mbar_expect_tx(&bars->v_full[st], DqSmem::kKV);
         tma_load_4d(smem + DqSmem::offV + st * DqSmem::kKV, &tmV, &bars->v_full[st], 0, h, t * kBS, b);
       };
-      auto load_bias = [&](int t) {
-        mbar_expect_tx(&bars->sdp_full, DqSmem::kBias);
-        tma_load_3d(smem + DqSmem::offBias, &tmB, &bars->sdp_full, t * kBS, q0, h);
-        tma_load_3d(smem + DqSmem::offBias + DqSmem::kBias / 2, &tmB, &bars->sdp_full, t * kBS + 32, q0, h);
+      auto load_bias = [&](int t) {  // two tiles ahead of the softmax warps
+        const int st = t & 1;
+        mbar_expect_tx(&bars->b_full[st], DqSmem::kBias);
+        tma_load_3d(smem + DqSmem::offBias + st * DqSmem::kBias, &tmB, &bars->b_full[st], t * kBS, q0, h);
       };
       mbar_expect_tx(&bars->q_full, 2 * DqSmem::kQ);
       tma_load_4d(smem + DqSmem::offQ, &tmQ, &bars->q_full, 0, h, q0, b);
@@ -186,7 +192,10 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dq_kernel(const __gri
         load_k(t);
         load_v(t);
       }
-      if (p.bias) load_bias(0);
+      if (p.bias) {
+        load_bias(0);
+        if (n_kt > 1) load_bias(1);
+      }
       const uint64_t dq_ = make_smem_desc_sw128(smem_u32(smem + DqSmem::offQ));
       const uint64_t ddo = make_smem_desc_sw128(smem_u32(smem + DqSmem::offDO));
       const uint64_t dds = make_smem_desc_sw128(smem_u32(smem + DqSmem::offDS));
@@ -231,9 +240,9 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dq_kernel(const __gri
             load_k(j + 1);
           }
         }
-        if (p.bias && j + 1 < n_kt) {
-          mbar_wait(&bars->b_empty, j & 1);
-          load_bias(j + 1);
+        if (p.bias && j + 2 < n_kt) {  // bias(j+2) reuses the buffer softmax(j) is reading
+          mbar_wait(&bars->b_empty[j & 1], (j >> 1) & 1);
+          load_bias(j + 2);
         }
       }
     }
@@ -241,7 +250,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dq_kernel(const __gri
     const int row = q0 + tid;
     const bool row_ok = row < p.Tq;
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    const uint8_t* bias_row = smem + DqSmem::offBias + tid * 128;
+    const uint8_t* bias_row0 = smem + DqSmem::offBias + tid * 128;  // this thread's 64-half row inside a bias buffer
     const uint8_t* kpm_row = p.kpm ? p.kpm + static_cast<int64_t>(b) * p.Tk : nullptr;
     uint8_t* ds_row = smem + DqSmem::offDS + tid * 128;
     const int64_t stat_idx = (static_cast<int64_t>(b) * p.H + h) * p.Tq + row;
@@ -253,7 +262,9 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dq_kernel(const __gri
     for (int j = 0; j < n_kt; ++j) {
       const int k0 = j * kBS;
       mbar_wait(&bars->sdp_full, j & 1);
+      if (p.bias) mbar_wait(&bars->b_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      const uint8_t* bias_row = bias_row0 + (j & 1) * DqSmem::kBias;
       const bool need_mask = (k0 + kBS > p.Tk) || (p.causal && (k0 + kBS - 1 > q0)) || (kpm_row != nullptr);
       uint32_t packed[32];  // dS row as bf16 pairs
 #pragma unroll
@@ -261,26 +272,39 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dq_kernel(const __gri
         uint32_t rs[32], rp[32];
         tmem_ld_32x32(tmem_s + lane_addr + half * 32, rs);
         tmem_ld_32x32(tmem_dp + lane_addr + half * 32, rp);
-        float4 bb[8];
+        uint4 bu[4];  // fp16 bias of columns half*32 .. half*32+31 (chunks 4*half .. 4*half+3 of the swizzled row)
         if (p.bias) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            bb[c] = *reinterpret_cast<const float4*>(bias_row + half * (DqSmem::kBias / 2) + ((c ^ (tid & 7)) << 4));
+          for (int c = 0; c < 4; ++c)
+            bu[c] = *reinterpret_cast<const uint4*>(bias_row + (((half * 4 + c) ^ (tid & 7)) << 4));
         }
         tmem_ld_wait();
+        const float2 l2e = splat2(kLog2eB), nL2 = splat2(-L2), ndl = splat2(-dl), hs2 = splat2(hs);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(rs[i]);
-          if (p.bias) s += reinterpret_cast<const float*>(bb)[i];
-          float pr = fast_exp2(fmaf(s, kLog2eB, -L2));
-          if (need_mask) {
-            const int col = k0 + half * 32 + i;
-            bool dead = col >= p.Tk || (p.causal && col > row);
-            if (!dead && kpm_row) dead = kpm_row[col] != 0;
-            if (dead) pr = 0.f;
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t w[4] = {bu[c].x, bu[c].y, bu[c].z, bu[c].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int i = 8 * c + 2 * q;
+            float2 sv = make_float2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1]));
+            if (p.bias) sv = add2(sv, __half22float2(*reinterpret_cast<const __half2*>(&w[q])));
+            const float2 e = fma2(sv, l2e, nL2);
+            float2 pr = make_float2(fast_exp2(e.x), fast_exp2(e.y));
+            if (need_mask) {  // CTA-uniform: boundary / causal-diagonal / padded tiles only
+              const int col = k0 + half * 32 + i;
+              bool dead0 = col >= p.Tk || (p.causal && col > row);
+              bool dead1 = col + 1 >= p.Tk || (p.causal && col + 1 > row);
+              if (kpm_row) {
+                if (!dead0) dead0 = kpm_row[col] != 0;
+                if (!dead1) dead1 = kpm_row[col + 1] != 0;
+              }
+              if (dead0) pr.x = 0.f;
+              if (dead1) pr.y = 0.f;
+            }
+            const float2 ds = mul2(pr, fma2(hs2, make_float2(__uint_as_float(rp[i]), __uint_as_float(rp[i + 1])), ndl));
+            rs[i] = __float_as_uint(ds.x);
+            rs[i + 1] = __float_as_uint(ds.y);
           }
-          const float ds = pr * fmaf(hs, __uint_as_float(rp[i]), -dl);
-          rs[i] = __float_as_uint(ds);
         }
         if (p.dbias && row_ok) {  // d(bias)[h,i,j] += dS: the bias is shared by the batch (and, for abs, by the layers)
           float* db = p.dbias + static_cast<int64_t>(h) * p.bias_head_stride + static_cast<int64_t>(row) * p.bias_row_stride +
@@ -296,7 +320,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dq_kernel(const __gri
       }
       tc_fence_before();
       mbar_arrive(&bars->sdp_empty);
-      if (p.bias) mbar_arrive(&bars->b_empty);
+      if (p.bias) mbar_arrive(&bars->b_empty[j & 1]);
       if (j >= 1) mbar_wait(&bars->ds_empty, (j - 1) & 1);  // dQ(j-1) has consumed the dS buffer
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -482,62 +506,88 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dkv_kernel(const __gr
     const float hs = p.head_scale ? p.head_scale[h] : 1.0f;
     const float* lse_bh = p.lse + (static_cast<int64_t>(b) * p.H + h) * p.Tq;
     const float* dl_bh = p.delta + (static_cast<int64_t>(b) * p.H + h) * p.Tq;
-    const float* bias_h = p.bias ? p.bias + static_cast<int64_t>(h) * p.bias_head_stride + min(key, p.Tk - 1) : nullptr;
+    // key-major copy of the bias: this thread's 64 query values of a tile are 128 contiguous bytes
+    const __half* bias_tk = p.bias_t ? p.bias_t + static_cast<int64_t>(h) * p.bias_t_head_stride +
+                                           static_cast<int64_t>(min(key, p.Tk - 1)) * p.bias_t_row_stride
+                                     : nullptr;
 
     float* stat = reinterpret_cast<float*>(smem + DkvSmem::offStat);
 #pragma unroll 1
     for (int j = 0; j < n_t; ++j) {
       const int qb = (t_first + j) * kBS;
+      // this key's 64 bias values of the tile: the first 32 are requested before the wait for S / dP, the other 32
+      // while the first half is being processed
+      uint4 cbias[2][4];
+      if (bias_tk) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cbias[0][c] = __ldg(reinterpret_cast<const uint4*>(bias_tk + qb + 8 * c));
+      }
       // per-query statistics of this tile -> shared memory (one element per thread), read back as broadcast float4
       {
         const int q = qb + (tid & 63);
         const float* src = tid < 64 ? lse_bh : dl_bh;
-        stat[(j & 1) * 128 + tid] = q < p.Tq ? __ldg(src + q) : (tid < 64 ? INFINITY : 0.f);
+        stat[(j & 1) * 128 + tid] = q < p.Tq ? -__ldg(src + q) : (tid < 64 ? -INFINITY : 0.f);  // negated: FMA addends
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       const float4* st_l = reinterpret_cast<const float4*>(stat + (j & 1) * 128);
       const float4* st_d = st_l + 16;
       mbar_wait(&bars->sdp_full, j & 1);
       tc_fence_after();
+      const bool mask_tile = p.causal && (k0 + kBT - 1 > qb);
       uint32_t pk_p[32], pk_ds[32];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t rs[32], rp[32];
         tmem_ld_32x32(tmem_s + lane_addr + half * 32, rs);
         tmem_ld_32x32(tmem_dp + lane_addr + half * 32, rp);
-        float bv[32];
-        if (p.bias) {
+        if (bias_tk && half == 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int q = min(qb + half * 32 + i, p.Tq - 1);
-            bv[i] = __ldg(bias_h + static_cast<int64_t>(q) * p.bias_row_stride);
-          }
+          for (int c = 0; c < 4; ++c) cbias[1][c] = __ldg(reinterpret_cast<const uint4*>(bias_tk + qb + 32 + 8 * c));
         }
         tmem_ld_wait();
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 l4 = st_l[half * 8 + i4];
-          const float4 d4 = st_d[half * 8 + i4];
-          const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
-          const float dv4[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i4 * 4 + u;
-            const int q = qb + half * 32 + i;
-            float s = __uint_as_float(rs[i]);
-            if (p.bias) s += bv[i];
-            float pr = fast_exp2(fmaf(s, kLog2eB, -lv[u]));  // queries >= Tq carry lse = +inf -> 0
-            if (!key_ok || (p.causal && key > q)) pr = 0.f;
-            const float ds = pr * fmaf(hs, __uint_as_float(rp[i]), -dv4[u]);
-            rs[i] = __float_as_uint(pr);
-            rp[i] = __float_as_uint(ds);
+          const float4 l4 = st_l[half * 8 + i4];  // -lse (log2 domain) of the four queries
+          const float4 d4 = st_d[half * 8 + i4];  // -delta
+          float2 b01 = splat2(0.f), b23 = splat2(0.f);
+          if (bias_tk) {
+            const uint4 ub = cbias[half][i4 >> 1];
+            const uint32_t w0 = (i4 & 1) ? ub.z : ub.x, w1 = (i4 & 1) ? ub.w : ub.y;
+            b01 = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+            b23 = __half22float2(*reinterpret_cast<const __half2*>(&w1));
           }
+          const int i = i4 * 4;
+          const float2 e01 = fma2(add2(make_float2(__uint_as_float(rs[i]), __uint_as_float(rs[i + 1])), b01),
+                                  splat2(kLog2eB), make_float2(l4.x, l4.y));
+          const float2 e23 = fma2(add2(make_float2(__uint_as_float(rs[i + 2]), __uint_as_float(rs[i + 3])), b23),
+                                  splat2(kLog2eB), make_float2(l4.z, l4.w));
+          float2 p01 = make_float2(fast_exp2(e01.x), fast_exp2(e01.y));  // queries >= Tq carry -lse = -inf -> 0
+          float2 p23 = make_float2(fast_exp2(e23.x), fast_exp2(e23.y));
+          if (mask_tile) {  // the causal diagonal crosses this tile
+            const int q = qb + half * 32 + i;
+            if (key > q) p01.x = 0.f;
+            if (key > q + 1) p01.y = 0.f;
+            if (key > q + 2) p23.x = 0.f;
+            if (key > q + 3) p23.y = 0.f;
+          }
+          const float2 s01 = mul2(p01, fma2(splat2(hs), make_float2(__uint_as_float(rp[i]), __uint_as_float(rp[i + 1])),
+                                            make_float2(d4.x, d4.y)));
+          const float2 s23 = mul2(p23, fma2(splat2(hs), make_float2(__uint_as_float(rp[i + 2]), __uint_as_float(rp[i + 3])),
+                                            make_float2(d4.z, d4.w)));
+          rs[i] = __float_as_uint(p01.x); rs[i + 1] = __float_as_uint(p01.y);
+          rs[i + 2] = __float_as_uint(p23.x); rs[i + 3] = __float_as_uint(p23.y);
+          rp[i] = __float_as_uint(s01.x); rp[i + 1] = __float_as_uint(s01.y);
+          rp[i + 2] = __float_as_uint(s23.x); rp[i + 3] = __float_as_uint(s23.y);
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           pk_p[half * 16 + i] = pack_bf16x2(__uint_as_float(rs[2 * i]), __uint_as_float(rs[2 * i + 1]));
           pk_ds[half * 16 + i] = pack_bf16x2(__uint_as_float(rp[2 * i]), __uint_as_float(rp[2 * i + 1]));
         }
+      }
+      if (!key_ok) {  // padded / out-of-range key: its whole row of P^T and dS^T is zero
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pk_p[i] = pk_ds[i] = 0u;
       }
       tc_fence_before();
       mbar_arrive(&bars->sdp_empty);
@@ -596,6 +646,39 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dkv_kernel(const __gr
   }
 }
 
+// out[h][c][r] = in[h][r][c] for 16-bit elements (the key-major copy of an fp16 bias for the dK/dV kernel); rows of
+// `out` beyond R (up to the padded row length) are zero-filled.  64x64 tiles through shared memory, 128-bit accesses.
+__global__ void __launch_bounds__(256) transpose16_batched_kernel(const uint16_t* __restrict__ in, int64_t in_hs,
+                                                                 int64_t in_rs, int R, int C, uint16_t* __restrict__ out,
+                                                                 int64_t out_hs, int64_t out_rs) {
+  __shared__ uint16_t tile[64][72];
+  const uint16_t* ih = in + static_cast<int64_t>(blockIdx.z) * in_hs;
+  uint16_t* oh = out + static_cast<int64_t>(blockIdx.z) * out_hs;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tr = threadIdx.x >> 2, seg = (threadIdx.x & 3) * 16;
+  {
+    const int r = r0 + tr;
+    uint4 a = make_uint4(0, 0, 0, 0), b = a;
+    if (r < R) {
+      if (c0 + seg + 8 <= C) a = *reinterpret_cast<const uint4*>(ih + static_cast<int64_t>(r) * in_rs + c0 + seg);
+      if (c0 + seg + 16 <= C) b = *reinterpret_cast<const uint4*>(ih + static_cast<int64_t>(r) * in_rs + c0 + seg + 8);
+    }
+    *reinterpret_cast<uint4*>(&tile[tr][seg]) = a;
+    *reinterpret_cast<uint4*>(&tile[tr][seg + 8]) = b;
+  }
+  __syncthreads();
+  const int c = c0 + tr;
+  if (c < C) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      w[i] = static_cast<uint32_t>(tile[seg + 2 * i][tr]) | (static_cast<uint32_t>(tile[seg + 2 * i + 1][tr]) << 16);
+    uint16_t* dst = oh + static_cast<int64_t>(c) * out_rs + r0 + seg;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
 static int make_hd_map(CUtensorMap* m, const void* base, int64_t row_stride, int64_t batch_stride, int H, int T, int B,
                        int box_rows) {
   uint64_t dims[4] = {kHd, static_cast<uint64_t>(H), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
@@ -620,10 +703,15 @@ extern "C" int sgf_attention_bwd_bf16(const sgf_attention_bwd_args* a, void* str
   const void* ptrs[] = {a->q, a->k, a->v, a->out, a->dout, a->dq, a->dk, a->dv};
   for (const void* ptr : ptrs) SGF_REQUIRE(reinterpret_cast<uintptr_t>(ptr) % 16 == 0, "attention_bwd: 16-byte alignment");
   if (a->bias)
-    SGF_REQUIRE(a->bias_row_stride % 4 == 0 && a->bias_head_stride % 4 == 0 &&
+    SGF_REQUIRE(a->bias_row_stride % 8 == 0 && a->bias_head_stride % 8 == 0 &&
                     reinterpret_cast<uintptr_t>(a->bias) % 16 == 0 && a->bias_row_stride >= a->Tk,
-                "attention_bwd: bias alignment");
+                "attention_bwd: the fp16 bias must be 16-byte aligned with row/head strides multiples of 8 elements");
   SGF_REQUIRE(!a->d_head_scale || a->head_scale, "attention_bwd: d_head_scale needs head_scale");
+  SGF_REQUIRE(!a->bias || a->bias_t, "attention_bwd: a bias needs its key-major copy bias_t (sgf_transpose16_batched)");
+  if (a->bias_t)
+    SGF_REQUIRE(a->bias && a->bias_t_row_stride % 8 == 0 && a->bias_t_head_stride % 8 == 0 &&
+                    reinterpret_cast<uintptr_t>(a->bias_t) % 16 == 0 && a->bias_t_row_stride >= (a->Tq + 63) / 64 * 64,
+                "attention_bwd: bias_t must be the 16-byte aligned [H,Tk,>=roundup(Tq,64)] transpose of bias");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   {
@@ -635,10 +723,10 @@ extern "C" int sgf_attention_bwd_bf16(const sgf_attention_bwd_args* a, void* str
     SGF_CHECK_CUDA(cudaGetLastError());
     count_launch();
   }
-  AttnBwdParams p{a->bias, a->bias_head_stride, a->bias_row_stride, a->head_scale, a->key_padding_mask, a->lse,
+  AttnBwdParams p{reinterpret_cast<const __half*>(a->bias), a->bias_head_stride, a->bias_row_stride, a->head_scale, a->key_padding_mask, a->lse,
                   a->delta, a->dq, a->dq_row_stride, a->dq_batch_stride, a->dq_scale, a->dk, a->dk_row_stride,
                   a->dk_batch_stride, a->dv, a->dv_row_stride, a->dv_batch_stride, a->B, a->H, a->Tq, a->Tk, a->causal,
-                  a->dbias};
+                  a->dbias, reinterpret_cast<const __half*>(a->bias_t), a->bias_t_head_stride, a->bias_t_row_stride};
   SGF_REQUIRE(!a->dbias || (a->bias && reinterpret_cast<uintptr_t>(a->dbias) % 16 == 0 && a->bias_row_stride % 64 == 0),
               "attention_bwd: dbias needs bias (same strides), 16-byte alignment and a row stride padded to 64");
   static bool configured = false;
@@ -656,9 +744,9 @@ extern "C" int sgf_attention_bwd_bf16(const sgf_attention_bwd_args* a, void* str
     memset(&tmB, 0, sizeof(tmB));
     if (a->bias) {
       uint64_t dims[3] = {static_cast<uint64_t>(a->bias_row_stride), static_cast<uint64_t>(a->Tq), static_cast<uint64_t>(a->H)};
-      uint64_t strides[2] = {static_cast<uint64_t>(a->bias_row_stride) * 4, static_cast<uint64_t>(a->bias_head_stride) * 4};
-      uint32_t box[3] = {32, kBT, 1};
-      if (int rc = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a->bias, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+      uint64_t strides[2] = {static_cast<uint64_t>(a->bias_row_stride) * 2, static_cast<uint64_t>(a->bias_head_stride) * 2};
+      uint32_t box[3] = {kBS, kBT, 1};
+      if (int rc = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a->bias, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
         return rc;
     }
     dim3 grid((a->Tq + kBT - 1) / kBT, a->H, a->B);
@@ -677,5 +765,22 @@ extern "C" int sgf_attention_bwd_bf16(const sgf_attention_bwd_args* a, void* str
                               tmQ, tmDO, tmK, tmV, p));
     count_launch();
   }
+  return SGF_OK;
+}
+
+extern "C" int sgf_transpose16_batched(const void* in, int64_t in_head_stride, int64_t in_row_stride, int32_t H, int32_t R,
+                                       int32_t C_, void* out, int64_t out_head_stride, int64_t out_row_stride,
+                                       void* stream) {
+  SGF_REQUIRE(in && out && H > 0 && R > 0 && C_ > 0, "transpose16_batched: bad arguments");
+  SGF_REQUIRE(C_ % 8 == 0 && in_row_stride % 8 == 0 && in_row_stride >= C_ && in_head_stride % 8 == 0 &&
+                  out_row_stride % 8 == 0 && out_row_stride >= (R + 63) / 64 * 64 && out_head_stride % 8 == 0 &&
+                  reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
+              "transpose16_batched: 16-byte alignment; C a multiple of 8; out rows padded to a multiple of 64");
+  dim3 grid((C_ + 63) / 64, (R + 63) / 64, H);
+  transpose16_batched_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint16_t*>(in), in_head_stride, in_row_stride, R, C_, reinterpret_cast<uint16_t*>(out),
+      out_head_stride, out_row_stride);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return SGF_OK;
 }

@@ -422,22 +422,44 @@ def transpose_cast(x, M=None, N=None, out_t=None, out_c=None, colsum=None, want_
 
 def attention_bwd(q, k, v, out, dout, dq, dk, dv, *, B, H, Tq, Tk, q_strides, k_strides, v_strides, o_strides,
                   do_strides, dq_strides, dk_strides, dv_strides, lse, delta, bias=None, head_scale=None,
-                  d_head_scale=None, key_padding_mask=None, causal=False, dq_scale=1.0, dbias=None):
+                  d_head_scale=None, key_padding_mask=None, causal=False, dq_scale=1.0, dbias=None, bias_t=None):
+    """bias: the fp16 tensor the forward streamed; bias_t: optional key-major copy (transpose_bias) for the dK/dV kernel."""
     lib = _lib.load()
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (dout, "dout"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
         _req(t, torch.bfloat16, n)
     _req(lse, torch.float32, "lse")
     _req(delta, torch.float32, "delta")
+    if bias is not None:
+        _req(bias, torch.float16, "bias")  # the tensor the forward kernel streamed
+        if bias_t is None:
+            bias_t = transpose_bias(bias, Tk)
     args = _lib.AttentionBwdArgs(
         _p(q), q_strides[0], q_strides[1], _p(k), k_strides[0], k_strides[1], _p(v), v_strides[0], v_strides[1],
         _p(out), o_strides[0], o_strides[1], _p(dout), do_strides[0], do_strides[1],
         _p(dq), dq_strides[0], dq_strides[1], _p(dk), dk_strides[0], dk_strides[1], _p(dv), dv_strides[0], dv_strides[1],
         _p(bias), bias.stride(0) if bias is not None else 0, bias.stride(1) if bias is not None else 0,
         _p(head_scale), _p(d_head_scale), _p(key_padding_mask), _p(lse), _p(delta), float(dq_scale),
-        B, H, Tq, Tk, 1 if causal else 0, _p(dbias))
+        B, H, Tq, Tk, 1 if causal else 0, _p(dbias),
+        _p(bias_t), bias_t.stride(0) if bias_t is not None else 0, bias_t.stride(1) if bias_t is not None else 0)
+    if bias_t is not None:
+        _req(bias_t, torch.float16, "bias_t")
     pairs = Tq * Tk if not causal else Tq * (Tq + 1) / 2.0
     with _timed("attention_bwd_tcgen05", 10.0 * B * H * pairs * 64):  # 5 algorithmic tile GEMMs
         _lib.check(lib.sgf_attention_bwd_bf16(C.byref(args), _stream()), "sgf_attention_bwd_bf16")
+
+
+def transpose_bias(bias, Tk):
+    """key-major copy [H, Tk_pad, roundup(Tq, 64)] of an fp16 bias [H, Tq, row_stride] (for attention_bwd's bias_t)."""
+    lib = _lib.load()
+    _req(bias, torch.float16, "bias")
+    H, Tq, ld = bias.shape
+    assert bias.stride(2) == 1 and ld % 8 == 0
+    cols = (Tk + 7) // 8 * 8
+    out = torch.empty((H, cols, (Tq + 63) // 64 * 64), dtype=torch.float16, device=bias.device)
+    with _timed("attn_bias", nbytes=4.0 * H * Tq * cols):
+        _lib.check(lib.sgf_transpose16_batched(_p(bias), bias.stride(0), bias.stride(1), H, Tq, cols, _p(out),
+                                               out.stride(0), out.stride(1), _stream()), "sgf_transpose16_batched")
+    return out
 
 
 def bias_block_csr(bucket, ids, lo, row_stride):

@@ -343,6 +343,7 @@ int sgf_transpose_cast(const void* in, int32_t in_dtype, int64_t ld_in, int32_t 
  *   dKdV: CTA per (128 keys, head, batch): S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q
  * dq is multiplied by dq_scale (the q pre-scaling of the QKV epilogue).  The gradient w.r.t. the
  * additive position bias is accumulated into `dbias` when given (vector fp32 atomics from the dQ kernel).
+ * The bias is the forward's FP16 tensor: the dQ kernel streams it as double-buffered 128B-swizzled TMA tiles.
  * delta: fp32 scratch [B,H,Tq]. */
 typedef struct {
   const void* q; int64_t q_row_stride; int64_t q_batch_stride;
@@ -353,7 +354,7 @@ typedef struct {
   void* dq; int64_t dq_row_stride; int64_t dq_batch_stride;
   void* dk; int64_t dk_row_stride; int64_t dk_batch_stride;
   void* dv; int64_t dv_row_stride; int64_t dv_batch_stride;
-  const float* bias; int64_t bias_head_stride; int64_t bias_row_stride;
+  const void* bias; int64_t bias_head_stride; int64_t bias_row_stride; /* FP16 (the tensor the forward streamed), strides in elements, multiples of 8 */
   const float* head_scale; float* d_head_scale;
   const uint8_t* key_padding_mask;
   const float* lse; float* delta;
@@ -361,8 +362,16 @@ typedef struct {
   int32_t B, H, Tq, Tk, causal;
   float* dbias; /* optional fp32 [H,Tq,bias_row_stride] (bias strides; row stride a multiple of 64): += dS summed over
                    the batch, i.e. the gradient w.r.t. the additive position bias */
+  const void* bias_t; int64_t bias_t_head_stride; int64_t bias_t_row_stride; /* FP16 key-major copy of bias, required with bias
+                   [H,Tk,>=roundup(Tq,64)] (sgf_transpose16_batched): the dK/dV kernel, whose threads own keys, then reads
+                   128 contiguous bytes per tile instead of 64 strided elements */
 } sgf_attention_bwd_args;
 int sgf_attention_bwd_bf16(const sgf_attention_bwd_args* args, void* stream);
+
+/* out[h][c][r] = in[h][r][c] for 16-bit elements, H matrices of R x C (C a multiple of 8); the rows of `out` are padded
+ * to a multiple of 64 elements (zero-filled beyond R).  Strides in elements, multiples of 8; 16-byte aligned pointers. */
+int sgf_transpose16_batched(const void* in, int64_t in_head_stride, int64_t in_row_stride, int32_t H, int32_t R, int32_t C,
+                            void* out, int64_t out_head_stride, int64_t out_row_stride, void* stream);
 
 /* Adjoint of sgf_build_attn_bias for one layer.  dbias[h,i,j] is the batch-summed dS of that layer's attention
  * (written by sgf_attention_bwd_bf16).  For every block b the table gradient is a gather over a static CSR list of

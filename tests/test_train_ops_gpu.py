@@ -276,7 +276,18 @@ def test_attention_backward(ops, B, H, Tq, Tk, causal, use_bias, use_kpm):
     ops.attention_bwd(q, k, v, out, dout, dq, dk, dv, B=B, H=H, Tq=Tq, Tk=Tk, q_strides=(D, Tq * D),
                       k_strides=(D, Tk * D), v_strides=(D, Tk * D), o_strides=(D, Tq * D), do_strides=(D, Tq * D),
                       dq_strides=(D, Tq * D), dk_strides=(D, Tk * D), dv_strides=(D, Tk * D), lse=lse, delta=delta,
-                      bias=bias, head_scale=hs, d_head_scale=dhs, key_padding_mask=kpm, causal=causal, dq_scale=1.0)
+                      bias=bias.half() if bias is not None else None, head_scale=hs, d_head_scale=dhs,
+                      key_padding_mask=kpm, causal=causal, dq_scale=1.0)
+    if bias is not None:  # same adjoint through the key-major bias copy the dK/dV kernel prefers
+        bt = ops.transpose_bias(bias.half(), Tk)
+        assert torch.equal(bt[:, :Tk, :Tq], bias.half()[:, :, :Tk].transpose(1, 2)) and (bt[:, :, Tq:] == 0).all()
+        dq2, dk2, dv2 = torch.empty_like(dq), torch.empty_like(dk), torch.empty_like(dv)
+        ops.attention_bwd(q, k, v, out, dout, dq2, dk2, dv2, B=B, H=H, Tq=Tq, Tk=Tk, q_strides=(D, Tq * D),
+                          k_strides=(D, Tk * D), v_strides=(D, Tk * D), o_strides=(D, Tq * D), do_strides=(D, Tq * D),
+                          dq_strides=(D, Tq * D), dk_strides=(D, Tk * D), dv_strides=(D, Tk * D), lse=lse,
+                          delta=torch.empty_like(delta), bias=bias.half(), bias_t=bt, head_scale=hs,
+                          key_padding_mask=kpm, causal=causal, dq_scale=1.0)
+        assert torch.equal(dk2, dk) and torch.equal(dv2, dv) and torch.equal(dq2, dq)
     torch.cuda.synchronize()
     assert _rel(dv, vf.grad) < 1.2e-2, ("dv", _rel(dv, vf.grad))
     assert _rel(dq, qf.grad) < 1.5e-2, ("dq", _rel(dq, qf.grad))
