@@ -229,8 +229,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
             for (int q = 0; q < 4; ++q) {
               const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
               const int col = 8 * c + 2 * q;
-              s[col] = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]) + f.x;
-              s[col + 1] = __uint_as_float(col < 32 ? r0[col + 1] : r1[col - 31]) + f.y;
+              const float2 sv = add2(make_float2(__uint_as_float(col < 32 ? r0[col] : r1[col - 32]),
+                                                 __uint_as_float(col < 32 ? r0[col + 1] : r1[col - 31])), f);
+              s[col] = sv.x;
+              s[col + 1] = sv.y;
             }
           }
         } else {
@@ -290,13 +292,17 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
           }
         }
       }
-      float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float2 ps[4] = {splat2(0.f), splat2(0.f), splat2(0.f), splat2(0.f)};
+      const float2 l2e = splat2(kLog2e), nm = splat2(-m_used);
 #pragma unroll
-      for (int i = 0; i < kKTile; ++i) {
-        s[i] = fast_exp2(fmaf(s[i], kLog2e, -m_used));
-        ps[i & 7] += s[i];
+      for (int i = 0; i < kKTile; i += 2) {
+        const float2 e = fma2(make_float2(s[i], s[i + 1]), l2e, nm);
+        s[i] = fast_exp2(e.x);
+        s[i + 1] = fast_exp2(e.y);
+        ps[(i >> 1) & 3] = add2(ps[(i >> 1) & 3], make_float2(s[i], s[i + 1]));
       }
-      l_run += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
+      const float2 pt = add2(add2(ps[0], ps[1]), add2(ps[2], ps[3]));
+      l_run += pt.x + pt.y;
       // P (bf16) -> the single smem buffer once its previous reader P V(j-1) has retired (issued a tile ago)
       if (j >= 1) mbar_wait(&bars->o_done, (j - 1) & 1);
       uint8_t* p_row = p_row0;
