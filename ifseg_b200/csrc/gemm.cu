@@ -186,7 +186,11 @@ SGF_DEVICE void gemm_epilogue(uint8_t* smem, uint32_t tmem_base, uint64_t* accum
     }
     if (epi_has<kEpi, kEpiGelu>(ep.act == SGF_ACT_GELU)) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      for (int j = 0; j < 32; j += 2) {
+        const float2 y = gelu_erf2(make_float2(v[j], v[j + 1]));
+        v[j] = y.x;
+        v[j + 1] = y.y;
+      }
     }
     float4* dst = reinterpret_cast<float4*>(stage + lane * kRowPitch + ch * 128);
 #pragma unroll
@@ -816,7 +820,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1)
         }
         if constexpr ((kEpi & kEpiGelu) != 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 32; j += 2) {
+            const float2 y = gelu_erf2(make_float2(v[j], v[j + 1]));
+            v[j] = y.x;
+            v[j + 1] = y.y;
+          }
         }
         if constexpr ((kEpi & kEpiResF32) != 0) {
           const float4* rp = reinterpret_cast<const float4*>(
