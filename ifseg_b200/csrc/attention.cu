@@ -76,9 +76,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
   pdl_trigger();
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int q0 = blockIdx.x * kQTile;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
+  const int b = blockIdx.x;  // batch fastest: the CTAs streaming the same (batch-invariant) bias tiles run together
+  const int q0 = blockIdx.y * kQTile;
+  const int h = blockIdx.z;
 
   int n_kt = (p.Tk + kKTile - 1) / kKTile;
   if (p.causal) n_kt = min(n_kt, (min(q0 + kQTile, p.Tq) + kKTile - 1) / kKTile);  // keys j <= max row of the tile
@@ -406,7 +406,7 @@ extern "C" int sgf_attention_bf16(const sgf_attention_args* a, void* stream) {
         cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((a->Tq + kQTile - 1) / kQTile, a->H, a->B);
+  dim3 grid(a->B, (a->Tq + kQTile - 1) / kQTile, a->H);
   SGF_CHECK_CUDA(launch_pdl(attention_tcgen05_kernel, grid, dim3(kAttnThreads), smem,
                             reinterpret_cast<cudaStream_t>(stream), tmQ, tmK, tmV, tmB, p));
   count_launch();

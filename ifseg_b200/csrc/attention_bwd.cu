@@ -121,9 +121,10 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dq_kernel(const __gri
   pdl_trigger();
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int q0 = blockIdx.x * kBT;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
+  // batch fastest: the CTAs that share a bias tile and add into the same dbias lines run together (L2-resident)
+  const int b = blockIdx.x;
+  const int q0 = blockIdx.y * kBT;
+  const int h = blockIdx.z;
   int n_kt = (p.Tk + kBS - 1) / kBS;
   if (p.causal) n_kt = min(n_kt, (min(q0 + kBT, p.Tq) + kBS - 1) / kBS);
 
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_dkv_kernel(const __gr
   pdl_trigger();
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int k0 = blockIdx.x * kBT;
+  const int k0 = blockIdx.x * kBT;  // (key-tile fastest: batch-fastest ordering measured slower for this kernel)
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int n_qt_all = (p.Tq + kBS - 1) / kBS;
@@ -749,7 +750,7 @@ extern "C" int sgf_attention_bwd_bf16(const sgf_attention_bwd_args* a, void* str
       if (int rc = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a->bias, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
         return rc;
     }
-    dim3 grid((a->Tq + kBT - 1) / kBT, a->H, a->B);
+    dim3 grid(a->B, (a->Tq + kBT - 1) / kBT, a->H);
     SGF_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel, grid, dim3(kBwdThreads), static_cast<size_t>(DqSmem::kTotal), st, tmQ,
                               tmDO, tmK, tmV, tmB, p));
     count_launch();
