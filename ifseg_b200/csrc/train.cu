@@ -977,10 +977,29 @@ __global__ void __launch_bounds__(512) ln_fwd_wide2_kernel(const __nv_bfloat16* 
         q2 = fma2(t[k][j], t[k][j], q2);
       }
     }
-    float st[2] = {s2.x + s2.y, q2.x + q2.y};
-    block_sum_nw<2>(st, red[par], nw);
-    const float mean = st[0] * invF;
-    const float rstd = rsqrtf(fmaxf(st[1] * invF - mean * mean, 0.f) + 1e-5f);
+    float mean, rstd;
+    if (kGelu) {  // one reduction: GELU outputs are O(1) with a spread of the same order, E[t^2] - mean^2 is safe
+      float st[2] = {s2.x + s2.y, q2.x + q2.y};
+      block_sum_nw<2>(st, red[par], nw);
+      mean = st[0] * invF;
+      rstd = rsqrtf(fmaxf(st[1] * invF - mean * mean, 0.f) + 1e-5f);
+    } else {  // arbitrary inputs: mean first, then the centred sum of squares (two reductions)
+      float s1[1] = {s2.x + s2.y};
+      block_sum_nw<1>(s1, red[par], nw);
+      mean = s1[0] * invF;
+      const float2 nm = splat2(-mean);
+      float2 c2 = splat2(0.f);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 d = add2(t[k][j], nm);
+          c2 = fma2(d, d, c2);
+        }
+      float s3[1] = {c2.x + c2.y};
+      block_sum_nw<1>(s3, red[par] + 16, nw);
+      rstd = rsqrtf(s3[0] * invF + 1e-5f);
+    }
     const float2 rs2 = splat2(rstd), nmr = splat2(-mean * rstd);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {

@@ -120,7 +120,7 @@ def test_stem_helpers(ops):
     assert torch.equal(mp, ref)
 
 
-@pytest.mark.parametrize("D", [768, 3072, 1024, 256, 4096])
+@pytest.mark.parametrize("D", [768, 3072, 1024, 256, 4096, 1280, 512, 5120, 1536])
 def test_row_layernorm(ops, D):
     g = torch.Generator(device="cuda").manual_seed(D)
     rows = 301
@@ -140,6 +140,10 @@ def test_row_layernorm(ops, D):
     r1 = res + F.layer_norm(x.float(), (D,), g1, b1, 1e-5)
     assert _rel(o1, r1) < 1e-5
     assert _rel(o2, F.layer_norm(r1, (D,), g2, b2, 1e-5)) < 4e-3
+    # a large common offset must not cost precision (centred variance)
+    xo = (torch.randn(rows, D, device="cuda", generator=g) * 0.5 + 30).bfloat16()
+    ops.row_layernorm(xo, ln2=(g1, b1), out2=out)
+    assert _rel(out, F.layer_norm(xo.float(), (D,), g1, b1, 1e-5)) < 4e-3
 
 
 def test_row_layernorm_gather_segments(ops):

@@ -24,7 +24,7 @@ def _gen(seed):
 # ----------------------------------------------------------------------------------------
 # row kernel: forward x_act, and the adjoint in the three site shapes the engine uses
 # ----------------------------------------------------------------------------------------
-@pytest.mark.parametrize("D", [3072, 4096, 256, 1024, 2048])
+@pytest.mark.parametrize("D", [3072, 4096, 256, 1024, 2048, 5120, 1536])
 def test_row_layernorm_gelu_forward(ops, D):
     g = _gen(D)
     rows = 77
@@ -36,7 +36,7 @@ def test_row_layernorm_gelu_forward(ops, D):
     assert _rel(out, ref) < 4e-3
 
 
-@pytest.mark.parametrize("D,rows", [(768, 901), (1024, 130), (256, 9)])
+@pytest.mark.parametrize("D,rows", [(768, 901), (1024, 130), (256, 9), (1280, 33), (512, 70)])
 def test_row_layernorm_bwd_residual_site(ops, D, rows):
     """y -> LN1 -> + residual -> out1 ; out2 = LN2(out1)   (attn_ln / final_layer_norm site)."""
     g = _gen(D + rows)
@@ -82,7 +82,7 @@ def test_row_layernorm_bwd_in_place_and_plain_residual(ops):
     assert _rel(dg2, g2.grad) < 1e-4 and _rel(db2, b2.grad) < 1e-4
 
 
-@pytest.mark.parametrize("F_", [3072, 4096, 1024, 2048, 512])
+@pytest.mark.parametrize("F_", [3072, 4096, 1024, 2048, 512, 5120, 1536])
 def test_row_layernorm_bwd_gelu_site(ops, F_):
     """z = LN(gelu(h)): dh from dz (FFN site, no saved v: recomputed from h)."""
     g = _gen(F_)
