@@ -61,6 +61,18 @@ CONFIGS = {
 TRAIN_CONFIGS = {3, 5}
 
 
+_OUT_FD = None  # set in __main__: the real stdout, which carries exactly ONE JSON line
+
+
+def emit(obj):
+    line = json.dumps(obj) + "\n"
+    if _OUT_FD is None:
+        sys.stdout.write(line)
+        sys.stdout.flush()
+    else:
+        os.write(_OUT_FD, line.encode())
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -308,7 +320,7 @@ def bench_train(args, rank, world, local_rank, config):
         if not args.no_cpu_baseline:
             cb, _ = cpu_reference_train_run(args.config, 1, 0)
             out["cpu_baseline"] = cb
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -342,14 +354,14 @@ def main():
             cb, dt = cpu_reference_train_run(args.config, min(steps, 2), min(args.warmup, 1))
         else:
             cb, dt = cpu_reference_run(args.config, steps, min(args.warmup, 1))
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "images/sec (train step)" if args.config in TRAIN_CONFIGS else "images/sec",
             "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0,
                                         "d2h_bytes_per_step": 0},
-        }))
+        })
         return
 
     import torch
@@ -485,10 +497,15 @@ def main():
         if not args.no_cpu_baseline:
             cb, _ = cpu_reference_run(args.config, 1, 1, sample_batch=1 if size >= 256 else None)
             out["cpu_baseline"] = cb
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
+    # anything a library prints to fd 1 while we run (NCCL's version banner under NCCL_DEBUG, for instance) goes to
+    # stderr, so that stdout is the one JSON line the contract asks for
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)
     main()
