@@ -233,7 +233,7 @@ def build_attn_bias(abs_bias, Tk, blocks=(), out=None, dense_add=None, f16=False
     """out[h,i,j] = abs[h,i,j] (+ dense_add) + rel-pos lookups.  abs_bias fp32 [H,Tq,row_stride>=Tk];
     blocks: iterable of (bucket int64 2-D, ids int64 [hi-lo], table fp32 [num_rel,H], lo, hi).
     f16=True returns the fp16 tensor the attention kernel reads (zero padding columns); with keep_f32 also the fp32
-    tensor holding exactly the same values (for the adjoint kernels): (b16, b32)."""
+    tensor holding exactly the same values (debugging / tests; the adjoint kernels read the fp16 tensor): (b16, b32)."""
     lib = _lib.load()
     _req(abs_bias, torch.float32, "abs_bias")
     out16 = torch.zeros(abs_bias.shape, dtype=torch.float16, device=abs_bias.device) if f16 else None
