@@ -1022,6 +1022,7 @@ static int dispatch_epilogue2p(const CUtensorMap& tmA, const CUtensorMap& tmB, c
     SGF_EPI2P_CASE(kEpiBias | kEpiOutF32)
     SGF_EPI2P_CASE(kEpiBias)
     SGF_EPI2P_CASE(kEpiBias | kEpiGelu | kEpiRowStats)
+    SGF_EPI2P_CASE(kEpiBias | kEpiGelu)
     SGF_EPI2P_CASE(kEpiBias | kEpiRowNorm | kEpiResF32 | kEpiOutF32)
     SGF_EPI2P_CASE(kEpiScale | kEpiBias | kEpiRelu)
     SGF_EPI2P_CASE(kEpiScale | kEpiBias | kEpiRelu | kEpiResBf16)

@@ -61,6 +61,18 @@ def test_gemm_epilogues(ops):
     assert _rel(out, ref) < 2e-5
 
 
+def test_gemm_pair_kernel_gelu(ops):
+    """bias + GELU with a bf16 output on a shape the persistent CTA-pair kernel takes (M >= 2048, N >= 2048)."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, N, K = 2400, 2048, 256
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = ops.gemm(a, b, bias=bias, act=ops.ACT_GELU)
+    assert out.dtype == torch.bfloat16
+    assert _rel(out, F.gelu(a.float() @ b.float().t() + bias)) < 4e-3
+
+
 def test_gemm_batched_heads(ops):
     """abs-pos bias: per-head [T,64] x [T,64]^T out of [T, H*64] buffers, padded fp32 output rows."""
     g = torch.Generator(device="cuda").manual_seed(3)
