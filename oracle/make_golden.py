@@ -170,6 +170,7 @@ def main():
     run_case("base_c15_s128", "segofa_base", 15, 128, 1, prompts)
     run_case("base_c150_s64_b2", "segofa_base", 150, 64, 2, prompts)
     run_grad_case("base_c150_s64_b2")
+    run_grad_case("base_c15_s128")  # cfg 1 shape (B=1, 15 classes): second pin of the oracle's autograd
     if "--full" in sys.argv:  # cfg 2 shape (not saved: 8x901x15 logits only) -- minutes of CPU
         run_case("base_c15_s480", "segofa_base", 15, 480, 2, prompts, save=False)
 
