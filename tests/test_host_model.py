@@ -35,6 +35,19 @@ def test_manifest_150_classes():
     assert {k: list(v.shape) for k, v in sd.items()} == {n: s for n, s, _ in man}
 
 
+@pytest.mark.parametrize("arch,name", [("segofa_tiny", "tiny_c15_s64"), ("segofa_large", "large_c15_s64")])
+def test_other_architectures_match_reference_manifest(arch, name):
+    """state-dict names, order, shapes and dtypes of the reference's tiny / large models (oracle/make_golden.py)."""
+    from ifseg_b200.segofa import SegOFAModel
+
+    m = SegOFAModel.from_config(arch, 15, 64)
+    man = json.load(open(os.path.join(GOLD, f"manifest_{name}.json")))
+    sd = m.state_dict()
+    assert [x[0] for x in man] == list(sd.keys())
+    for n, shape, dtype in man:
+        assert list(sd[n].shape) == shape and str(sd[n].dtype).replace("torch.", "") == dtype, n
+
+
 def test_parameter_counts_and_freezes(model):
     total = sum(p.numel() for p in model.parameters())
     trainable = sum(p.numel() for p in model.parameters() if p.requires_grad)
