@@ -173,6 +173,7 @@ def main():
     run_case("tiny_c15_s64", "segofa_tiny", 15, 64, 1, prompts)
     run_case("medium_c15_s64", "segofa_medium", 15, 64, 1, prompts)
     run_case("large_c15_s64", "segofa_large", 15, 64, 1, prompts)
+    run_case("huge_c15_s64", "segofa_huge", 15, 64, 1, prompts)
     run_grad_case("base_c150_s64_b2")
     run_grad_case("base_c15_s128")  # cfg 1 shape (B=1, 15 classes): second pin of the oracle's autograd
     if "--full" in sys.argv:  # cfg 2 shape (not saved: 8x901x15 logits only) -- minutes of CPU

@@ -36,7 +36,7 @@ def test_manifest_150_classes():
 
 
 @pytest.mark.parametrize("arch,name", [("segofa_tiny", "tiny_c15_s64"), ("segofa_medium", "medium_c15_s64"),
-                                       ("segofa_large", "large_c15_s64")])
+                                       ("segofa_large", "large_c15_s64"), ("segofa_huge", "huge_c15_s64")])
 def test_other_architectures_match_reference_manifest(arch, name):
     """state-dict names, order, shapes and dtypes of the reference's tiny / large models (oracle/make_golden.py)."""
     from ifseg_b200.segofa import SegOFAModel
