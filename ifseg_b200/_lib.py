@@ -87,6 +87,7 @@ class SegmaskArgs(C.Structure):
         ("B", _i32), ("C", _i32), ("hp", _i32), ("wp", _i32), ("h", _i32), ("w", _i32),
         ("mask", _vp), ("target", _vp),
         ("area_intersect", _vp), ("area_pred", _vp), ("area_label", _vp),
+        ("arith", _i32),
     ]
 
 

@@ -37,15 +37,21 @@ def build(force=False, verbose=False):
         return LIB
     objs = []
     logs = []
-    for src in SOURCES:
+    procs = []
+    for src in SOURCES:  # one nvcc per translation unit, all at once (gemm.cu alone takes minutes)
         obj = os.path.join(HERE, src.replace(".cu", ".o"))
         cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(HERE, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        logs.append(f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
-        if r.returncode != 0:
-            sys.stderr.write(logs[-1])
-            raise RuntimeError(f"nvcc failed on {src}")
+        procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
+    failed = None
+    for src, cmd, pr in procs:
+        out, _ = pr.communicate()
+        logs.append(f"$ {' '.join(cmd)}\n{out}")
+        if pr.returncode != 0 and failed is None:
+            failed = src
+            sys.stderr.write(logs[-1])
+    if failed:
+        raise RuntimeError(f"nvcc failed on {failed}")
     cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

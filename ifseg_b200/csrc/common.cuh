@@ -397,7 +397,9 @@ SGF_DEVICE void drop_mult8(const DropCtx& c, int64_t row, int chunk, float (&m)[
   }
   if (c.thresh16) {
     const uint64_t base = c.key ^ (static_cast<uint64_t>(row) << 22) ^ (static_cast<uint64_t>(chunk) << 1);
-    const uint64_t a = mix64(base), b2 = mix64(base | 1ull);
+    // two independent 64-bit streams per chunk: the second one is keyed by a distinct odd constant (base | 1 would
+    // coincide with base whenever the key's bit 0 is set, tying elements j and j+4)
+    const uint64_t a = mix64(base), b2 = mix64(base ^ 0xA0761D6478BD642Full);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       m[j] = (static_cast<uint32_t>(a >> (16 * j)) & 0xFFFFu) >= c.thresh16 ? c.inv_keep * path : 0.f;

@@ -8,6 +8,7 @@
 // s = max(0, scale*(d+0.5)-0.5), i0 = (int)s, i1 = i0 + (i0 < in-1), l1 = s - i0, l0 = 1 - l1,
 // value = h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11), evaluated without FMA contraction.
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -25,8 +26,35 @@ struct SegmaskParams {
   float scale_h, scale_w;
 };
 
+// Rounding sequence of the interpolation (the argmax of near-tied classes depends on the last bit):
+//   kArithPlain     every product and sum rounded separately (ATen's CPU contiguous kernel)
+//   kArithFma + v   nvcc-contracted forms of ATen's CUDA expression (aten/native/cuda/UpSampleBilinear2d.cu)
+//                     val = h0 * (w0*v00 + w1*v01) + h1 * (w0*v10 + w1*v11),   src = fma(scale, dst + 0.5, -0.5)
+//                   each of the three sums becomes one multiply + one fma; which product stays a multiply is the
+//                   compiler's choice and differs between ATen's two CUDA kernels, so all 8 forms exist:
+//                     bit 0: top  = fma(w1, v01, w0*v00)   instead of fma(w0, v00, w1*v01)
+//                     bit 1: bot  = fma(w1, v11, w0*v10)   instead of fma(w0, v10, w1*v11)
+//                     bit 2: val  = fma(h1, bot, h0*top)   instead of fma(h0, top, h1*bot)
+enum : int { kArithPlain = 0, kArithFma = 8 };
+
+template <int kArith>
+SGF_DEVICE float lerp4(float hl0, float hl1, float wl0, float wl1, float v00, float v01, float v10, float v11) {
+  if constexpr (kArith == kArithPlain) {
+    const float top = __fadd_rn(__fmul_rn(wl0, v00), __fmul_rn(wl1, v01));
+    const float bot = __fadd_rn(__fmul_rn(wl0, v10), __fmul_rn(wl1, v11));
+    return __fadd_rn(__fmul_rn(hl0, top), __fmul_rn(hl1, bot));
+  } else {
+    constexpr int v = kArith - kArithFma;
+    const float top = (v & 1) ? __fmaf_rn(wl1, v01, __fmul_rn(wl0, v00)) : __fmaf_rn(wl0, v00, __fmul_rn(wl1, v01));
+    const float bot = (v & 2) ? __fmaf_rn(wl1, v11, __fmul_rn(wl0, v10)) : __fmaf_rn(wl0, v10, __fmul_rn(wl1, v11));
+    return (v & 4) ? __fmaf_rn(hl1, bot, __fmul_rn(hl0, top)) : __fmaf_rn(hl0, top, __fmul_rn(hl1, bot));
+  }
+}
+
+template <int kArith = kArithPlain>
 SGF_DEVICE void src_index(float scale, int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
-  float s = __fsub_rn(__fmul_rn(scale, static_cast<float>(dst) + 0.5f), 0.5f);
+  float s = kArith == kArithPlain ? __fsub_rn(__fmul_rn(scale, static_cast<float>(dst) + 0.5f), 0.5f)
+                                  : __fmaf_rn(scale, static_cast<float>(dst) + 0.5f, -0.5f);
   s = s < 0.f ? 0.f : s;
   i0 = static_cast<int>(s);
   if (i0 > in_size - 1) i0 = in_size - 1;
@@ -35,6 +63,7 @@ SGF_DEVICE void src_index(float scale, int dst, int in_size, int& i0, int& i1, f
   l0 = __fsub_rn(1.0f, l1);
 }
 
+template <int kArith>
 __global__ void __launch_bounds__(256) upsample_argmax_kernel(const SegmaskParams p) {
   extern __shared__ float hist[];  // [3][C] when histograms are requested
   const bool want_hist = p.area_pred != nullptr;
@@ -48,8 +77,8 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(const SegmaskParam
   if (x < p.w) {
     int y0, y1, x0, x1;
     float hl0, hl1, wl0, wl1;
-    src_index(p.scale_h, y, p.hp, y0, y1, hl0, hl1);
-    src_index(p.scale_w, x, p.wp, x0, x1, wl0, wl1);
+    src_index<kArith>(p.scale_h, y, p.hp, y0, y1, hl0, hl1);
+    src_index<kArith>(p.scale_w, x, p.wp, x0, x1, wl0, wl1);
     const float* base = p.logits + static_cast<int64_t>(b) * p.batch_stride;
     const float* p00 = base + static_cast<int64_t>(y0 * p.wp + x0) * p.tok_stride;
     const float* p01 = base + static_cast<int64_t>(y0 * p.wp + x1) * p.tok_stride;
@@ -58,9 +87,7 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(const SegmaskParam
     float best = -INFINITY;
     int best_c = 0;
     for (int c = 0; c < p.C; ++c) {
-      const float top = __fadd_rn(__fmul_rn(wl0, __ldg(p00 + c)), __fmul_rn(wl1, __ldg(p01 + c)));
-      const float bot = __fadd_rn(__fmul_rn(wl0, __ldg(p10 + c)), __fmul_rn(wl1, __ldg(p11 + c)));
-      const float v = __fadd_rn(__fmul_rn(hl0, top), __fmul_rn(hl1, bot));
+      const float v = lerp4<kArith>(hl0, hl1, wl0, wl1, __ldg(p00 + c), __ldg(p01 + c), __ldg(p10 + c), __ldg(p11 + c));
       if (v > best || (c == 0)) {  // first maximum wins, NaN-free inputs assumed
         if (c == 0 || v > best) {
           best = v;
@@ -566,7 +593,23 @@ extern "C" int sgf_upsample_argmax(const sgf_segmask_args* a, void* stream) {
                   static_cast<float>(a->wp) / static_cast<float>(a->w)};
   dim3 block(256), grid((a->w + 255) / 256, a->h, a->B);
   const size_t smem = a->area_pred ? 3 * a->C * sizeof(float) : 0;
-  upsample_argmax_kernel<<<grid, block, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  // default: what ATen executes on a GPU for the reference's input -- the NCHW kernel below 16 channels, the NHWC
+  // kernel from 16 channels on (the reference hands F.interpolate a channels-last view, seg_criterion.py:238-240)
+  int mode = a->arith;
+  if (mode == SGF_LERP_DEFAULT) mode = a->C >= 16 ? SGF_LERP_ATEN_CUDA_NHWC : SGF_LERP_ATEN_CUDA;
+  SGF_REQUIRE(mode == SGF_LERP_PLAIN || (mode >= 8 && mode < 16), "upsample_argmax: unknown arith mode %d", mode);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (mode) {
+    case 0: upsample_argmax_kernel<kArithPlain><<<grid, block, smem, st>>>(p); break;
+    case 8: upsample_argmax_kernel<kArithFma + 0><<<grid, block, smem, st>>>(p); break;
+    case 9: upsample_argmax_kernel<kArithFma + 1><<<grid, block, smem, st>>>(p); break;
+    case 10: upsample_argmax_kernel<kArithFma + 2><<<grid, block, smem, st>>>(p); break;
+    case 11: upsample_argmax_kernel<kArithFma + 3><<<grid, block, smem, st>>>(p); break;
+    case 12: upsample_argmax_kernel<kArithFma + 4><<<grid, block, smem, st>>>(p); break;
+    case 13: upsample_argmax_kernel<kArithFma + 5><<<grid, block, smem, st>>>(p); break;
+    case 14: upsample_argmax_kernel<kArithFma + 6><<<grid, block, smem, st>>>(p); break;
+    default: upsample_argmax_kernel<kArithFma + 7><<<grid, block, smem, st>>>(p); break;
+  }
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return SGF_OK;

@@ -1155,7 +1155,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 }
 
 // ----------------------------------------------------------------------------------------
-// fused Adam(W) over a flat fp32 buffer; sum of squares
+// fused Adam over a flat fp32 buffer, fairseq's formulation (custom_fairseq/fairseq/optim/adam.py:159-240); sum of squares
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
@@ -1180,8 +1180,11 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, c
       const float gr = G[j] * gs;
       Mo[j] = b1 * Mo[j] + (1.f - b1) * gr;
       V[j] = b2 * V[j] + (1.f - b2) * gr * gr;
-      const float den = sqrtf(V[j]) / bc2 + eps;  // bc2 = sqrt(1 - beta2^t)
-      P[j] = P[j] - lr * wd * P[j] - (lr / bc1) * (Mo[j] / den);
+      // custom_fairseq/fairseq/optim/adam.py:222-235: denom = sqrt(v) + eps, step = lr * sqrt(1 - b2^t) / (1 - b1^t),
+      // decoupled weight decay p -= wd * lr * p applied to the parameter before the update
+      const float den = sqrtf(V[j]) + eps;
+      const float pd = P[j] - lr * wd * P[j];
+      P[j] = pd - (lr * bc2 / bc1) * (Mo[j] / den);  // bc2 = sqrt(1 - beta2^t)
     }
     *reinterpret_cast<float4*>(p + i0) = pp;
     *reinterpret_cast<float4*>(m + i0) = mm;
@@ -1191,8 +1194,9 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, c
       const float gr = g[i] * gs;
       m[i] = b1 * m[i] + (1.f - b1) * gr;
       v[i] = b2 * v[i] + (1.f - b2) * gr * gr;
-      const float den = sqrtf(v[i]) / bc2 + eps;
-      p[i] = p[i] - lr * wd * p[i] - (lr / bc1) * (m[i] / den);
+      const float den = sqrtf(v[i]) + eps;
+      const float pd = p[i] - lr * wd * p[i];
+      p[i] = pd - (lr * bc2 / bc1) * (m[i] / den);
     }
   }
 }

@@ -77,6 +77,17 @@ class _timed:
         return False
 
 
+# Optional launch tap (tests only): an object with before(kind, **inputs) -> token and after(token, out) called around every
+# GEMM / convolution / attention / row-kernel launch, so a test can replay each launch of a real forward on the CPU from the
+# launch's OWN inputs (tests/test_parity_gpu.py: single-storage-point parity).  None by default: zero overhead.
+_TAP = None
+
+
+def set_tap(tap):
+    global _TAP
+    _TAP = tap
+
+
 def launch_count():
     return int(_lib.load().sgf_launch_count())
 
@@ -112,8 +123,17 @@ def gemm(a, b, out=None, *, bias=None, scale=None, residual=None, act=ACT_NONE, 
         _DT[residual.dtype] if residual is not None else SGF_BF16, act, float(alpha), int(alpha_cols),
         _p(rowstats_out), _p(rownorm[0]) if rownorm else None, _p(rownorm[1]) if rownorm else None,
         int(rownorm[2]) if rownorm else 0)
+    tok = None
+    if _TAP is not None:
+        tok = _TAP.before("gemm", a=a, b=b, M=M, N=N, K=K, lda=lda, ldb=ldb, ldc=ldc, batch=batch, bias=bias, scale=scale,
+                          residual=residual, ldr=(residual.stride(-2) if ldr is None else ldr) if residual is not None else 0,
+                          act=act, alpha=alpha, alpha_cols=alpha_cols, a_batch_stride=a_batch_stride,
+                          b_batch_stride=b_batch_stride, c_batch_stride=c_batch_stride, r_batch_stride=r_batch_stride,
+                          rowstats_out=rowstats_out, rownorm=rownorm, tag=tag)
     with _timed("gemm_tcgen05" + (":" + tag if tag and _TIMER is not None and _TIMER.fine else ""), 2.0 * M * N * K * batch):
         _lib.check(lib.sgf_gemm_bf16(C.byref(args), _stream()), "sgf_gemm_bf16")
+    if tok is not None:
+        _TAP.after(tok, out)
     return out
 
 
@@ -147,8 +167,11 @@ def conv3x3_s1(x, w, scale, bias, act=ACT_RELU, out=None, tag=None):
     if out is None:
         out = torch.empty((n, h, wd, cout), dtype=torch.bfloat16, device=x.device)
     args = _lib.Conv3x3Args(_p(x), _p(w), _p(out), n, h, wd, cin, cout, _p(scale), _p(bias), act)
+    tok = _TAP.before("conv3x3", x=x, w=w, scale=scale, bias=bias, act=act, tag=tag) if _TAP is not None else None
     with _timed("gemm_tcgen05" + (":" + tag if tag and _TIMER is not None and _TIMER.fine else ""), 2.0 * n * h * wd * cout * 9 * cin):
         _lib.check(lib.sgf_conv3x3_s1_nhwc(C.byref(args), _stream()), "sgf_conv3x3_s1_nhwc")
+    if tok is not None:
+        _TAP.after(tok, out)
     return out
 
 
@@ -225,8 +248,15 @@ def row_layernorm(x, *, rows=None, D=None, ldx=None, gather_idx=None, pre_add=No
         _p(zero_row), rows, D, seg_len, seg_stride, seg_off, _p(clear_rowstats), int(x_act), *_drop_fields(drop))
     nb = rows * D * (x.element_size() + (residual.element_size() if residual is not None else 0)
                      + (out1.element_size() if out1 is not None else 0) + (2 if out2 is not None else 0))
+    tok = None
+    if _TAP is not None:
+        tok = _TAP.before("row_layernorm", x=x, rows=rows, D=D, ldx=x.stride(-2) if ldx is None else ldx, gather_idx=gather_idx,
+                          pre_add=pre_add, ln1=ln1, residual=residual, ln2=ln2, zero_row=zero_row, seg=seg, x_act=x_act,
+                          drop=drop)
     with _timed("row_layernorm" + (f":D{D}{'g1' if ln1 else ''}" if _TIMER is not None and _TIMER.fine else ""), nbytes=float(nb)):
         _lib.check(lib.sgf_row_layernorm(C.byref(args), _stream()), "sgf_row_layernorm")
+    if tok is not None:
+        _TAP.after(tok, (out1, out2))
 
 
 def build_attn_bias(abs_bias, Tk, blocks=(), out=None, dense_add=None, f16=False, keep_f32=False):
@@ -277,13 +307,24 @@ def attention(q, k, v, out, *, B, H, Tq, Tk, q_strides, k_strides, v_strides, o_
         _p(bias), bias.stride(0) if bias is not None else 0, bias.stride(1) if bias is not None else 0,
         _p(head_scale), _p(key_padding_mask), B, H, Tq, Tk, 1 if causal else 0, _p(lse))
     pairs = Tq * Tk if not causal else Tq * (Tq + 1) / 2.0
+    tok = None
+    if _TAP is not None:
+        tok = _TAP.before("attention", q=q, k=k, v=v, B=B, H=H, Tq=Tq, Tk=Tk, q_strides=q_strides, k_strides=k_strides,
+                          v_strides=v_strides, o_strides=o_strides, bias=bias, head_scale=head_scale,
+                          key_padding_mask=key_padding_mask, causal=causal)
     with _timed("attention_tcgen05", 4.0 * B * H * pairs * 64):
         _lib.check(lib.sgf_attention_bf16(C.byref(args), _stream()), "sgf_attention_bf16")
+    if tok is not None:
+        _TAP.after(tok, out)
     return out
 
 
-def upsample_argmax(logits, hp, wp, h, w, target=None, num_tokens=None):
-    """logits fp32 [B, >=hp*wp, C] -> mask int64 [B,h,w] (+ optional (intersect, pred, label) areas)."""
+LERP_DEFAULT, LERP_PLAIN, LERP_ATEN_CUDA, LERP_ATEN_CUDA_NHWC = -1, 0, 8, 15  # SGF_LERP_* (include/segofa_b200.h)
+
+
+def upsample_argmax(logits, hp, wp, h, w, target=None, num_tokens=None, arith=LERP_DEFAULT):
+    """logits fp32 [B, >=hp*wp, C] -> mask int64 [B,h,w] (+ optional (intersect, pred, label) areas).  `arith`: rounding
+    sequence of the interpolation (default = ATen's CUDA kernel, the reference's execution path)."""
     lib = _lib.load()
     _req(logits, torch.float32, "logits")
     B, _, Cn = logits.shape
@@ -296,7 +337,7 @@ def upsample_argmax(logits, hp, wp, h, w, target=None, num_tokens=None):
     args = _lib.SegmaskArgs(_p(logits), logits.stride(0), logits.stride(1), B, Cn, hp, wp, h, w, _p(mask),
                             _p(target), _p(areas[0]) if areas is not None else None,
                             _p(areas[1]) if areas is not None else None,
-                            _p(areas[2]) if areas is not None else None)
+                            _p(areas[2]) if areas is not None else None, int(arith))
     with _timed("upsample_argmax", nbytes=float(mask.numel() * 8 + B * hp * wp * Cn * 4)):
         _lib.check(lib.sgf_upsample_argmax(C.byref(args), _stream()), "sgf_upsample_argmax")
     return (mask, areas) if target is not None else mask

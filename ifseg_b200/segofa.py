@@ -450,6 +450,14 @@ class SegOFAModel(FairseqEncoderDecoderModel):
         anything that may change parameters."""
         self._engine = None
 
+    def parameters_changed(self):
+        """Parameters were written in place by something other than the training engine's own optimizer step
+        (load_state_dict, SegCriterion.lazy_initialization, an external optimizer on frozen tensors): drop the
+        inference engine's derived copies and make the training engine re-derive EVERY operand, frozen ones included."""
+        self.invalidate_engine()
+        if self._train_engine is not None:
+            self._train_engine.parameters_changed()
+
     def train_engine(self):
         """The training engine (flat fp32 master arena + hand-written backward); created on first use."""
         if self._train_engine is None:
@@ -468,11 +476,10 @@ class SegOFAModel(FairseqEncoderDecoderModel):
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict=True, model_cfg=None, args=None, **kw):
-        self.invalidate_engine()
-        if self._train_engine is not None:  # parameters are copied in place into the arena: re-derive the bf16 operands
-            self._train_engine._fresh = False
         self.upgrade_state_dict_named(state_dict, "")
-        return super().load_state_dict(state_dict, strict, **kw)
+        out = super().load_state_dict(state_dict, strict, **kw)
+        self.parameters_changed()  # values are copied in place (arena views stay valid); every derived copy is stale
+        return out
 
     def upgrade_state_dict_named(self, state_dict, name):
         """Checkpoint compatibility (segofa.py:197-299, encoder_module.py:943-987,
@@ -544,7 +551,7 @@ class SegOFAModel(FairseqEncoderDecoderModel):
                 "branch and runs this one under torch.inference_mode(), seg_criterion.py:185) -- wrap the call in "
                 "torch.no_grad()/inference_mode() or use model.eval()")
         # while a training engine exists its live-operand inference engine follows every optimizer update
-        eng = self._train_engine.inf if (self._train_engine is not None and self.training) else self.engine()
+        eng = self._train_engine.live_inference_engine() if (self._train_engine is not None and self.training) else self.engine()
         x, extra = None, {}
         if src_tokens is not None:
             enc = eng.encode(src_tokens, patch_images=patch_images, patch_masks=patch_masks)

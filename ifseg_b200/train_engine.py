@@ -42,7 +42,12 @@ def _pad8(n):
 
 
 class ParamArena:
-    """Flat fp32 master / gradient / Adam-moment buffers holding every trainable parameter."""
+    """Flat fp32 master / gradient / Adam-moment buffers holding every trainable parameter.
+
+    fp32 model (`alias`): the nn.Parameters and their .grad ARE views of the flat buffers.  Half-precision model
+    (`--fp16` / `--bf16`: trainer.py:95-101 calls model.half() / .to(bfloat16) and keeps the fp32 masters in
+    FP16Optimizer): the parameters keep their own storage; `pull()` mirrors them into the flat fp32 buffer before a
+    forward and gradients are handed back in the parameter dtype (ImFreeBranchFunction)."""
 
     def __init__(self, groups: List[List[torch.nn.Parameter]], device):
         self.slots: Dict[int, tuple] = {}  # id(param) -> (offset, numel)
@@ -62,15 +67,47 @@ class ParamArena:
         self.exp_avg = None
         self.exp_avg_sq = None
         self.params = [p for grp in groups for p in grp]
+        self.alias = all(p.dtype == torch.float32 for p in self.params)
+        self.param_dtype = self.params[0].dtype if self.params else torch.float32
         with torch.no_grad():
             for p in self.params:
                 o, n = self.slots[id(p)]
                 self.flat32[o:o + n].copy_(p.detach().reshape(-1).float())
-                p.data = self.flat32[o:o + n].view(p.shape)
-                p.grad = self.grad32[o:o + n].view(p.shape)
+                if self.alias:
+                    p.data = self.flat32[o:o + n].view(p.shape)
+                    p.grad = self.grad32[o:o + n].view(p.shape)
 
     def has(self, p):
         return p is not None and id(p) in self.slots
+
+    def value(self, p):
+        """fp32 master view of parameter p"""
+        o, n = self.slots[id(p)]
+        return self.flat32[o:o + n].view(p.shape)
+
+    def grad(self, p):
+        o, n = self.slots[id(p)]
+        return self.grad32[o:o + n].view(p.shape)
+
+    def push(self):
+        """mirror mode: fp32 masters -> the parameters (after the engine's own optimizer step; FP16Optimizer's copy-back)"""
+        if self.alias:
+            return
+        with torch.no_grad():
+            for p in self.params:
+                p.copy_(self.value(p))
+
+    def pull(self):
+        """mirror mode: parameter values -> the fp32 master buffer (the caller's optimizer owns the truth)"""
+        if self.alias:
+            return
+        with torch.no_grad():
+            dst = [self.value(p) for p in self.params]
+            try:
+                torch._foreach_copy_(dst, [p.detach() for p in self.params])
+            except Exception:  # noqa: BLE001 -- older foreach without dtype conversion
+                for d, p in zip(dst, self.params):
+                    d.copy_(p.detach())
 
     def view(self, buf, params, shape):
         """view of `buf` covering the adjacent parameters `params` with the given shape."""
@@ -90,14 +127,23 @@ class ParamArena:
 
 
 class ImFreeBranchFunction(torch.autograd.Function):
-    """autograd bridge for drop-in callers (optimizer.backward(loss), fp16_optimizer.py:96-106): the forward runs
-    SegOFATrainEngine.forward_train, the backward runs the hand-written adjoint chain and ACCUMULATES the parameter
-    gradients straight into param.grad (views of the flat gradient arena) -- so fairseq's legacy_ddp / our own
-    bucketed all-reduce, which reduce whatever .grad holds after backward, work unchanged.  (`hook` is a dummy
-    leaf that makes the output require grad; parameters are not autograd inputs.)"""
+    """autograd bridge for drop-in callers (optimizer.backward(loss), fp16_optimizer.py:96-106).  The forward runs
+    SegOFATrainEngine.forward_train, the backward runs the hand-written adjoint chain.  Every parameter that receives a
+    gradient is an INPUT of this node, so whatever hangs on the parameters' gradient accumulators keeps working --
+    torch.nn.parallel.DistributedDataParallel's reducer hooks (fairseq's default `pytorch_ddp` backend with
+    --find-unused-parameters, distributed_fairseq_model.py:57-83), legacy_ddp's post-backward all-reduce of .grad,
+    gradient accumulation over several backward calls (--update-freq).
+
+    The adjoint chain writes into the flat fp32 gradient arena.  What the node returns:
+      * fp32 model, parameters without a .grad yet (the usual zero_grad(set_to_none) loop): fresh VIEWS of the arena --
+        AccumulateGrad adopts them as param.grad without a copy, so .grad stays inside the flat buffer (one contiguous
+        range per all-reduce bucket / fused optimizer);
+      * fp32 model, .grad already present (a second backward before the update): the chain accumulates in place and the
+        node returns stride-0 zeros, so AccumulateGrad's own `grad += returned` changes nothing but still fires the hooks;
+      * half-precision model: one cast of the arena to the parameter dtype, returned as per-parameter views."""
 
     @staticmethod
-    def forward(ctx, hook, engine, aux_input):
+    def forward(ctx, engine, aux_input, *params):
         c = engine.forward_train(aux_input)
         ctx.engine, ctx.c = engine, c
         return c["logits"]
@@ -105,22 +151,34 @@ class ImFreeBranchFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         eng, c = ctx.engine, ctx.c
+        ar = eng.arena
         C = eng.cfg.num_seg
         dl = torch.zeros((c["B"], c["Td"], _pad8(C)), dtype=_BF16, device=dlogits.device)
         dl[..., :C] = dlogits
-        eng.attach_grads()
-        prev, eng.accumulate = eng.accumulate, True
+        in_place = ar.alias and any(p.grad is not None for p in ar.params)
+        if in_place:
+            eng.attach_grads()
+        prev, eng.accumulate = eng.accumulate, in_place
         try:
-            eng.backward_from(c, dl)
+            eng.backward_from(c, dl)  # zeroes the arena first unless accumulating
         finally:
             eng.accumulate = prev
         ctx.c = None
-        return None, None, None
+        if in_place:
+            z = torch.zeros((), dtype=torch.float32, device=dlogits.device)
+            grads = [z.expand(p.shape) for p in ar.params]
+        elif ar.alias:
+            grads = [ar.grad(p) for p in ar.params]
+        else:
+            g16 = ar.grad32.to(ar.param_dtype)
+            grads = [g16[o:o + n].view(p.shape) for p in ar.params for (o, n) in (ar.slots[id(p)],)]
+        return (None, None, *grads)
 
 
 class _Dense:
-    """One GEMM operand set: fp32 master view(s), bf16 W [N,K], bf16 W^T [K,pad8(N)], grads."""
-    __slots__ = ("src", "w16", "w16t", "b32", "gw", "gb", "N", "K")
+    """One GEMM operand set: fp32 master view(s), bf16 W [N,K], bf16 W^T [K,pad8(N)], grads.  `frozen` = the
+    nn.Parameters behind a non-arena operand (re-read whenever the model reports an external parameter change)."""
+    __slots__ = ("src", "w16", "w16t", "b32", "gw", "gb", "N", "K", "frozen", "frozen_b")
 
 
 class SegOFATrainEngine:
@@ -131,9 +189,9 @@ class SegOFATrainEngine:
         p0 = next(model.parameters())
         if not p0.is_cuda:
             raise RuntimeError("segofa_b200: training runs on a B200 only (no CPU fallback) -- call model.cuda() first")
-        if any(p.dtype != torch.float32 for p in model.parameters() if p.requires_grad):
-            raise RuntimeError("segofa_b200 training keeps fp32 master parameters and makes its own bf16 operand "
-                               "copies (cf. fp16_optimizer.py:108-222); keep the model in fp32")
+        dts = {p.dtype for p in model.parameters() if p.requires_grad}
+        if len(dts) > 1 or not dts <= {torch.float32, torch.float16, torch.bfloat16}:
+            raise RuntimeError(f"segofa_b200 training: trainable parameters must share one floating dtype, got {dts}")
         self.model = model
         self.cfg = model.cfg
         self.device = p0.device
@@ -242,22 +300,38 @@ class SegOFATrainEngine:
             elif p.requires_grad and id(p) not in covered:
                 raise RuntimeError(f"trainable parameter {name} is not covered by the training engine")
 
+    def parameters_changed(self):
+        """Somebody wrote parameters in place (load_state_dict, lazy seg-token initialisation): the next forward re-casts
+        every operand -- frozen ones too -- and the live inference engine (folded BN, stem weights, frozen tables) is
+        rebuilt.  CUDA graphs captured before the change replay the old buffers and must be re-captured."""
+        self._fresh = False
+        self._frozen_stale = True
+        self.inf = None
+
+    def live_inference_engine(self):
+        """The no-grad engine that shares this engine's operands (rebuilt after parameters_changed())."""
+        if self.inf is None:
+            self.refresh_weights()
+        return self.inf
+
     def attach_grads(self):
         """param.grad <- views of arena.grad32 (again).  zero_grad(set_to_none=True) drops them: the arena is then
         cleared, which is exactly what the caller asked for."""
         ar = self.arena
+        if not ar.alias:
+            return
         missing = [p for p in ar.params if p.grad is None]
-        if missing:
+        if len(missing) == len(ar.params):
             ar.grad32.zero_()
-            for p in ar.params:
-                o, n = ar.slots[id(p)]
-                p.grad = ar.grad32[o:o + n].view(p.shape)
+        for p in missing:
+            g = ar.grad(p)
+            if len(missing) != len(ar.params):
+                g.zero_()
+            p.grad = g
 
     def imfree_logits(self, aux_input):
         """logits [B,Td,C] of the image-free branch, attached to autograd (see ImFreeBranchFunction)."""
-        if self._hook is None:
-            self._hook = torch.zeros((), device=self.device, requires_grad=True)
-        return ImFreeBranchFunction.apply(self._hook, self, aux_input)
+        return ImFreeBranchFunction.apply(self, aux_input, *self.arena.params)
 
     def _wgrad_stream(self):
         if self._wstream is None:
@@ -288,10 +362,12 @@ class SegOFATrainEngine:
         K = weights[0].shape[1]
         d.N, d.K = N, K
         ar = self.arena
+        d.frozen, d.frozen_b = None, None
         if ar.has(weights[0]):
             d.src = ar.view(ar.flat32, weights, (N, K))
             d.gw = ar.view(ar.grad32, weights, (N, K))
         else:
+            d.frozen = list(weights)
             d.src = torch.cat([w.detach().float() for w in weights], 0).contiguous()
             d.gw = None
         d.w16 = torch.empty((N, K), dtype=_BF16, device=self.device)
@@ -302,20 +378,21 @@ class SegOFATrainEngine:
                 d.b32 = ar.view(ar.flat32, biases, (N,))
                 d.gb = ar.view(ar.grad32, biases, (N,))
             else:
+                d.frozen_b = list(biases)
                 d.b32 = torch.cat([b.detach().float() for b in biases], 0).contiguous()
         return d
 
     def _ln(self, mod):
         ar = self.arena
         if ar.has(mod.weight):
-            return (mod.weight.data, mod.bias.data, mod.weight.grad, mod.bias.grad)
+            return (ar.value(mod.weight), ar.value(mod.bias), ar.grad(mod.weight), ar.grad(mod.bias))
         return (mod.weight.detach().float().contiguous(), mod.bias.detach().float().contiguous(), None, None)
 
     def _vec(self, p):
         if p is None:
             return None, None
         if self.arena.has(p):
-            return p.data, p.grad
+            return self.arena.value(p), self.arena.grad(p)
         return p.detach().float().contiguous(), None
 
     def refresh_weights(self):
@@ -378,12 +455,25 @@ class SegOFATrainEngine:
             te, self.g_type = self._vec(enc.type_embedding.weight)
             self.type_txt, self.type_img = te[0], te[1]
             self.embed_tokens = enc.embed_tokens.weight.detach()
+            self._embed_copy = self.embed_tokens.dtype not in (torch.float32, _BF16) or not self.embed_tokens.is_contiguous()
+            if self._embed_copy:  # fp16 table (model.half()): the row kernels read fp32 / bf16
+                self.embed_tokens = self.embed_tokens.float().contiguous()
             if enc.embed_tokens.weight.requires_grad:
                 raise NotImplementedError("training requires --freeze-encoder-embedding/--freeze-decoder-embedding "
                                           "(the shipped recipe); token-embedding gradients are not implemented")
+        stale = getattr(self, "_frozen_stale", False)
+        if not first:
+            self.arena.pull()  # half-precision model: the caller's optimizer owns the parameters, mirror them
+        if stale and self._embed_copy:
+            self.embed_tokens = self.model.encoder.embed_tokens.weight.detach().float().contiguous()
         for d in self.dense:
-            if first or d.gw is not None:
+            if stale and d.frozen is not None:  # frozen operand (e.g. the tied seg_projection): re-read the parameters
+                d.src.copy_(torch.cat([w.detach().float() for w in d.frozen], 0))
+                if d.frozen_b is not None:
+                    d.b32.copy_(torch.cat([b.detach().float() for b in d.frozen_b], 0))
+            if first or stale or d.gw is not None:
                 ops.transpose_cast(d.src, out_t=d.w16t, out_c=d.w16)
+        self._frozen_stale = False
         self._fresh = True
         if self.inf is None:
             self.inf = SegOFAEngine(self.model, live=self)
@@ -885,5 +975,6 @@ class SegOFATrainEngine:
             scale = scale * (clip_norm / (gnorm + 1e-6)).clamp(max=1.0)
         ops.adam_step(ar.flat32, ar.grad32, ar.exp_avg, ar.exp_avg_sq, lr=lr, beta1=betas[0], beta2=betas[1], eps=eps,
                       weight_decay=weight_decay, step=self.step_count, step_dev=self._step_dev, grad_scale=scale)
+        ar.push()
         self.refresh_weights()
         return gnorm

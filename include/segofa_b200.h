@@ -213,14 +213,29 @@ int sgf_attention_bf16(const sgf_attention_args* args, void* stream);
  *   optional per-class histograms (float [C] each, accumulated with atomics):
  *   area_pred, and with `target` (int64 [B,h,w], class ids, <0 or >=C = ignore): area_label,
  *   area_intersect  (seg_criterion.py:349-362).
+ * `arith` selects the rounding sequence of the four-tap interpolation -- the argmax of two near-tied classes depends on
+ * the last bit, and ATen rounds differently in each of its kernels:
+ *   SGF_LERP_DEFAULT        what ATen executes on a GPU for the reference's call (mmseg.ops.resize -> F.interpolate on a
+ *                           channels-last CUDA view): SGF_LERP_ATEN_CUDA below 16 classes, SGF_LERP_ATEN_CUDA_NHWC from 16 on
+ *   SGF_LERP_ATEN_CUDA      src = fma(scale, d+0.5, -0.5); v = fma(h0, fma(w0,v00, w1*v01), h1*fma(w0,v10, w1*v11))
+ *                           = nvcc's contraction of upsample_bilinear2d_out_frame (aten/native/cuda/UpSampleBilinear2d.cu)
+ *   SGF_LERP_ATEN_CUDA_NHWC nvcc's contraction of upsample_bilinear2d_nhwc_out_frame (other operand order; found by
+ *                           tests/test_ops_gpu.py against torch on the GPU box)
+ *   SGF_LERP_PLAIN          every product and sum rounded separately (ATen CPU, contiguous kernel)
+ *   8 + v (v = 0..7)        the eight possible contractions (bit 0/1/2: operand order of the top / bottom / final sum)
  * Replaces seg_criterion.py:237-244 + :351 (and visualize_segmentation_web.ipynb cell 4).
  * ------------------------------------------------------------------------------------- */
+#define SGF_LERP_DEFAULT (-1)
+#define SGF_LERP_PLAIN 0
+#define SGF_LERP_ATEN_CUDA 8
+#define SGF_LERP_ATEN_CUDA_NHWC 15
 typedef struct {
   const float* logits; int64_t batch_stride; int64_t tok_stride;
   int32_t B, C, hp, wp, h, w;
   int64_t* mask;
   const int64_t* target;
   float* area_intersect; float* area_pred; float* area_label;
+  int32_t arith; /* SGF_LERP_* */
 } sgf_segmask_args;
 int sgf_upsample_argmax(const sgf_segmask_args* args, void* stream);
 

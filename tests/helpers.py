@@ -38,3 +38,26 @@ def build_cuda_model(arch, num_seg, size, seed=0):
     sd = generate_state_dict(model.cfg, seed)
     model.load_state_dict(sd, strict=True)
     return model.cuda().eval(), sd
+
+
+def make_task(num_seg, names=None):
+    """Stand-in for SegmentationTask: target_dictionary / tgt_dict with encode_line, cfg, and a bpe whose encode maps a
+    word to a deterministic string of 1-3 'subword' ids (what GPT2BPE.encode returns: space-separated id strings)."""
+    import types
+    import zlib
+
+    from ifseg_b200.fairseq_compat import StubDictionary
+
+    class _Dict(StubDictionary):
+        def encode_line(self, line, add_if_not_exist=False, append_eos=False):
+            return torch.tensor([4 + int(t) % 50000 for t in line.split()], dtype=torch.int32)
+
+    class _Bpe:
+        def encode(self, x):
+            h = zlib.crc32(x.encode())
+            return " ".join(str((h >> (8 * i)) & 0xFFFF) for i in range(1 + h % 3))
+
+    d = _Dict(num_seg)
+    names = names or [f"thing{i} part" if i % 4 == 0 else f"thing{i}" for i in range(num_seg)]
+    return types.SimpleNamespace(target_dictionary=d, tgt_dict=d, bpe=_Bpe(),
+                                 cfg=types.SimpleNamespace(num_seg_tokens=num_seg, category_list=",".join(names)))

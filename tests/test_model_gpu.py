@@ -151,7 +151,7 @@ def test_criterion_eval_branch(case15):
     S, C = g["image_size"], g["num_seg"]
     task = types.SimpleNamespace(target_dictionary=StubDictionary(C),
                                  cfg=types.SimpleNamespace(num_seg_tokens=C, category_list=",".join(f"c{i}" for i in range(C))))
-    crit = SegCriterion(task)
+    crit = SegCriterion(task, init_seg_with_text="false")
     gen = torch.Generator().manual_seed(9)
     classes = torch.randint(0, C + 1, (g["batch"], S * S), generator=gen)  # includes the 'unknown' id C
     target = torch.cat([classes + 59457, torch.full((g["batch"], 1), 2)], 1)
@@ -174,7 +174,7 @@ def test_criterion_eval_branch(case15):
     m = derive_metrics(ai, ap, al, au)
     assert 0 <= m["mIoU"] <= 1 and 0 <= m["aAcc"] <= 1
     # validation post-processing (resnet_iters > 0): the propagated probabilities give a second set of areas
-    crit_pp = SegCriterion(task, resnet_iters=5, resnet_topk=3)
+    crit_pp = SegCriterion(task, resnet_iters=5, resnet_topk=3, init_seg_with_text="false")
     _, _, log_pp = crit_pp(model, sample)
     for k in ("area_intersect_resnet_postprocess", "area_pred_label_resnet_postprocess", "area_label_resnet_postprocess",
               "area_union_resnet_postprocess"):

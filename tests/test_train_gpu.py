@@ -127,7 +127,7 @@ def test_criterion_training_branch_through_autograd(cuda_device):
     C, S, B = g["num_seg"], g["image_size"], g["batch"]
     task = types.SimpleNamespace(target_dictionary=StubDictionary(C),
                                  cfg=types.SimpleNamespace(num_seg_tokens=C, category_list=",".join(f"c{i}" for i in range(C))))
-    crit = SegCriterion(task)
+    crit = SegCriterion(task, init_seg_with_text="false")
     inp = {k: v.cuda() for k, v in synthetic_inputs(model.cfg, B, S, seed=1, src_tokens=g["src_tokens"][0]).items()}
     gen = torch.Generator().manual_seed(9)
     target = torch.cat([torch.randint(0, C + 1, (B, S * S), generator=gen) + 59457, torch.full((B, 1), 2)], 1)
