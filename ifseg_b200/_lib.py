@@ -178,7 +178,6 @@ EXPORTS = [
     ("sgf_reset_launch_count", None, []),
     ("sgf_gemm_bf16", C.c_int, [C.POINTER(GemmArgs), _vp]),
     ("sgf_gemm_bf16_ex", C.c_int, [C.POINTER(GemmArgs), _i32, _i32, _i32, _vp]),
-    ("sgf_gemm_force_variant", None, [C.c_int, C.c_int]),
     ("sgf_conv3x3_s1_nhwc", C.c_int, [C.POINTER(Conv3x3Args), _vp]),
     ("sgf_nchw_f32_to_nhwc_bf16", C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     ("sgf_im2col_nhwc", C.c_int, [_vp, _vp] + [_i32] * 10 + [_i64, _vp]),

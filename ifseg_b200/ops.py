@@ -319,7 +319,7 @@ def attention(q, k, v, out, *, B, H, Tq, Tk, q_strides, k_strides, v_strides, o_
     return out
 
 
-LERP_DEFAULT, LERP_PLAIN, LERP_ATEN_CUDA, LERP_ATEN_CUDA_NHWC = -1, 0, 8, 15  # SGF_LERP_* (include/segofa_b200.h)
+LERP_DEFAULT, LERP_PLAIN, LERP_ATEN_CUDA, LERP_ATEN_CUDA_NHWC = -1, 0, 8, 9  # SGF_LERP_* (include/segofa_b200.h)
 
 
 def upsample_argmax(logits, hp, wp, h, w, target=None, num_tokens=None, arith=LERP_DEFAULT):

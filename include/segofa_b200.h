@@ -78,8 +78,6 @@ int sgf_gemm_bf16(const sgf_gemm_args* args, void* stream);
  * blockIdx.z and REDUCES the partial tiles into C with vector fp32 atomics: C must be fp32 and hold the value to
  * accumulate onto (zeros, or a running gradient for gradient accumulation).  N % 32 == 0. */
 int sgf_gemm_bf16_ex(const sgf_gemm_args* args, int32_t a_mn_major, int32_t b_mn_major, int32_t split_k, void* stream);
-/* tuning hook: force the N-tile (32/64/128/256, 0 = heuristic) and pipeline depth of sgf_gemm_bf16 */
-void sgf_gemm_force_variant(int bn, int stages);
 
 /* ---------------------------------------------------------------------------------------
  * 3x3 / stride 1 / pad 1 convolution as an im2col-free implicit GEMM over NHWC bf16:
@@ -219,8 +217,9 @@ int sgf_attention_bf16(const sgf_attention_args* args, void* stream);
  *                           channels-last CUDA view): SGF_LERP_ATEN_CUDA below 16 classes, SGF_LERP_ATEN_CUDA_NHWC from 16 on
  *   SGF_LERP_ATEN_CUDA      src = fma(scale, d+0.5, -0.5); v = fma(h0, fma(w0,v00, w1*v01), h1*fma(w0,v10, w1*v11))
  *                           = nvcc's contraction of upsample_bilinear2d_out_frame (aten/native/cuda/UpSampleBilinear2d.cu)
- *   SGF_LERP_ATEN_CUDA_NHWC nvcc's contraction of upsample_bilinear2d_nhwc_out_frame (other operand order; found by
- *                           tests/test_ops_gpu.py against torch on the GPU box)
+ *   SGF_LERP_ATEN_CUDA_NHWC nvcc's contraction of upsample_bilinear2d_nhwc_out_frame: as above with top = fma(w1,v01, w0*v00)
+ *                           (identified on a B200 against torch 2.11: 0 mismatches on adversarial near-tie logits,
+ *                           profiles/r02_upsample_arith.txt)
  *   SGF_LERP_PLAIN          every product and sum rounded separately (ATen CPU, contiguous kernel)
  *   8 + v (v = 0..7)        the eight possible contractions (bit 0/1/2: operand order of the top / bottom / final sum)
  * Replaces seg_criterion.py:237-244 + :351 (and visualize_segmentation_web.ipynb cell 4).
@@ -228,7 +227,7 @@ int sgf_attention_bf16(const sgf_attention_args* args, void* stream);
 #define SGF_LERP_DEFAULT (-1)
 #define SGF_LERP_PLAIN 0
 #define SGF_LERP_ATEN_CUDA 8
-#define SGF_LERP_ATEN_CUDA_NHWC 15
+#define SGF_LERP_ATEN_CUDA_NHWC 9
 typedef struct {
   const float* logits; int64_t batch_stride; int64_t tok_stride;
   int32_t B, C, hp, wp, h, w;

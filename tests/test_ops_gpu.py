@@ -270,6 +270,7 @@ def test_upsample_argmax_bit_exact(ops, B, C, hp, wp, h, w):
         f.write(json.dumps(dict(shape=[B, C, hp, wp, h, w], mismatches=mism)) + "\n")
     mask = ops.upsample_argmax(logits, hp, wp, h, w)  # default = ATen CUDA arithmetic for this channel count / layout
     assert mism["fma0"]["vs_aten_cuda_contiguous"] == 0, mism   # SGF_LERP_ATEN_CUDA == ATen's NCHW kernel, near-ties included
+    assert mism["fma1" if C >= 16 else "fma0"]["vs_aten_cuda"] == 0, mism  # ... and its NHWC kernel from 16 channels on
     assert torch.equal(mask, ref_gpu), mism                     # bit-exact against the reference's op on the reference's layout
     assert torch.equal(mask[1:], ref_gpu[1:]) and (mask[1:].cpu() != ref_cpu[1:]).sum().item() == 0  # separated logits: every path agrees
     # against the CPU oracle a pixel may differ only where its top-2 margin is within a few fp32 ulps
