@@ -2,9 +2,14 @@
 //
 //   O[b,i,h,:] = head_scale[h] * softmax_j( Q[b,i,h,:].K[b,j,h,:] + bias[h,i,j] + mask ) V[b,j,h,:]
 //
-// One CTA per (128-query tile, head, batch); 5 warps:
-//   warps 0..3 : softmax, thread r owns query row r (TMEM lane r)
-//   warp 4     : control -- one lane issues every TMA load and every tcgen05.mma
+// One CTA per (128-query tile, head, batch); 9 warps:
+//   warps 0..7 : softmax, TWO threads per query row: warp w and warp w+4 share TMEM lane quarter w&3 and split the 64 keys
+//                of a tile in halves (32 score columns, 32 P columns, 32 O columns each).  The r01 kernel had one thread
+//                per row: 164 registers, 8 softmax warps per SM, every warp a 375-instruction dependent chain per tile
+//                (ncu: warps active 13.5 %, issue active 29 %, tensor pipe 12 %).  Halving the chain and doubling the
+//                warps is what hides the tcgen05.ld / MUFU / shared-memory latencies.  The two halves of a row agree on
+//                the running maximum through a 4-byte exchange in shared memory and a 64-thread named barrier per tile.
+//   warp 8     : control -- one lane issues every TMA load and every tcgen05.mma
 // Per 64-key tile j (all asynchronous, mbarrier hand-offs, nothing waits on the tensor core in line):
 //   S(j) = Q K(j)^T      tcgen05.mma M128 N64 K64 into one of two TMEM score buffers, issued one tile
 //                        ahead so it runs under the softmax of tile j-1
@@ -29,7 +34,8 @@ namespace sgf {
 static constexpr int kQTile = 128;
 static constexpr int kKTile = 64;
 static constexpr int kHeadDim = 64;
-static constexpr int kAttnThreads = 160;
+static constexpr int kAttnThreads = 288;
+static constexpr int kSoftmaxWarps = 8;
 static constexpr int kKvStages = 3;
 static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr float kRescaleThreshold = 8.0f;  // log2 domain: probabilities stay below 2^8
@@ -94,15 +100,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->s_full[i], p.bias ? 2 : 1);  // tcgen05.commit of S(j) (+ the expect_tx arrive of bias(j))
-      mbar_init(&bars->s_empty[i], 128);
+      mbar_init(&bars->s_empty[i], kSoftmaxWarps);  // one arrival per softmax warp (lane 0 after __syncwarp)
     }
-    mbar_init(&bars->p_full, 128);
-    mbar_init(&bars->b_empty[0], 128);
-    mbar_init(&bars->b_empty[1], 128);
+    mbar_init(&bars->p_full, kSoftmaxWarps);
+    mbar_init(&bars->b_empty[0], kSoftmaxWarps);
+    mbar_init(&bars->b_empty[1], kSoftmaxWarps);
     mbar_init(&bars->o_done, 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == kSoftmaxWarps) {
     if ((tid & 31) == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
   const uint32_t tmem_o = tmem_base + 128;  // output accumulator: columns [128,192)
   pdl_wait();
 
-  if (warp == 4) {
+  if (warp == kSoftmaxWarps) {
     // =========================== control lane: TMA + MMA issue ===========================
     if ((tid & 31) == 0 && n_kt > 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(kQTile, kKTile, 0, 0);
@@ -198,39 +204,46 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
     }
   } else {
     // =================================== softmax warps ===================================
-    const int row = q0 + tid;
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    const uint8_t* bias_row = smem + AttnSmem::offBias + tid * 128;  // this thread's 64-half row inside a bias buffer
+    const int lane = tid & 31;
+    const int qd = warp & 3;        // TMEM lane quarter
+    const int half = warp >> 2;     // which 32 of the tile's 64 keys (and of the 64 output columns) this thread owns
+    const int rowl = qd * 32 + lane;
+    const int row = q0 + rowl;
+    const uint32_t sw = static_cast<uint32_t>(rowl & 7);
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const uint8_t* kpm_row = p.kpm ? p.kpm + static_cast<int64_t>(b) * p.Tk : nullptr;
-    uint8_t* p_row0 = smem + AttnSmem::offP + tid * 128;
-    float m_used = 0.f;  // log2-domain reference max the probabilities are expressed against
-    float l_run = 0.f;
+    uint8_t* p_row0 = smem + AttnSmem::offP + rowl * 128;
+    // row-maximum exchange slots: the first 4 bytes of the bias chunks this thread has already consumed (the bias buffers
+    // are idle when there is no bias); the partner reads them after the pair barrier, before the buffer is handed back
+    const uint32_t my_slot = ((static_cast<uint32_t>(4 * half) ^ sw) << 4);
+    const uint32_t peer_slot = ((static_cast<uint32_t>(4 * (half ^ 1)) ^ sw) << 4);
+    float m_used = 0.f;  // log2-domain reference max the probabilities are expressed against (identical in both halves)
+    float l_run = 0.f;   // this half's share of the row sum
 
 #pragma unroll 1
     for (int j = 0; j < n_kt; ++j) {
-      const int k0 = j * kKTile;
+      const int k0 = j * kKTile + half * 32;
+      uint8_t* bias_buf = smem + AttnSmem::offBias + (j & 1) * AttnSmem::kBias + rowl * 128;
       mbar_wait(&bars->s_full[j & 1], (j >> 1) & 1);  // S(j) retired and bias(j) landed (P V(j-2) retired too)
       tc_fence_after();
-      float s[kKTile];
+      float s[32];
       {
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32(tmem_s + (j & 1) * 64 + lane_addr, r0);
-        tmem_ld_32x32(tmem_s + (j & 1) * 64 + lane_addr + 32, r1);
+        uint32_t r0[32];
+        tmem_ld_32x32(tmem_s + (j & 1) * 64 + half * 32 + lane_addr, r0);
         if (p.bias) {  // the swizzled smem reads of the fp16 bias tile overlap the TMEM load latency
-          uint4 bb[8];
+          uint4 bb[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            bb[c] = *reinterpret_cast<const uint4*>(bias_row + (j & 1) * AttnSmem::kBias + ((c ^ (tid & 7)) << 4));
+          for (int c = 0; c < 4; ++c)
+            bb[c] = *reinterpret_cast<const uint4*>(bias_buf + ((static_cast<uint32_t>(4 * half + c) ^ sw) << 4));
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {  // chunk c = columns 8c .. 8c+7
+          for (int c = 0; c < 4; ++c) {  // chunk c = columns 8c .. 8c+7 of this half
             const uint32_t w[4] = {bb[c].x, bb[c].y, bb[c].z, bb[c].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
               const int col = 8 * c + 2 * q;
-              const float2 sv = add2(make_float2(__uint_as_float(col < 32 ? r0[col] : r1[col - 32]),
-                                                 __uint_as_float(col < 32 ? r0[col + 1] : r1[col - 31])), f);
+              const float2 sv = add2(make_float2(__uint_as_float(r0[col]), __uint_as_float(r0[col + 1])), f);
               s[col] = sv.x;
               s[col + 1] = sv.y;
             }
@@ -238,52 +251,55 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         } else {
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            s[i] = __uint_as_float(r0[i]);
-            s[32 + i] = __uint_as_float(r1[i]);
-          }
+          for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r0[i]);
         }
       }
       tc_fence_before();
-      mbar_arrive(&bars->s_empty[j & 1]);
-      if (p.bias) mbar_arrive(&bars->b_empty[j & 1]);
-      const bool need_mask = (k0 + kKTile > p.Tk) || (p.causal && (k0 + kKTile - 1 > q0)) || (kpm_row != nullptr);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_empty[j & 1]);
+      const bool need_mask = (j * kKTile + kKTile > p.Tk) || (p.causal && (j * kKTile + kKTile - 1 > q0)) || (kpm_row != nullptr);
       if (need_mask) {
 #pragma unroll
-        for (int i = 0; i < kKTile; ++i) {
+        for (int i = 0; i < 32; ++i) {
           const int col = k0 + i;
           bool dead = col >= p.Tk || (p.causal && col > row);
           if (!dead && kpm_row) dead = kpm_row[col] != 0;
           if (dead) s[i] = -INFINITY;
         }
       }
-      // 8 independent partial maxima (a single 64-deep fmax chain would serialise on FP latency)
-      float mxp[8];
+      // 4 independent partial maxima (a single 32-deep fmax chain would serialise on FP latency)
+      float mxp[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mxp[i] = s[i];
+      for (int i = 0; i < 4; ++i) mxp[i] = s[i];
 #pragma unroll
-      for (int i = 8; i < kKTile; ++i) mxp[i & 7] = fmaxf(mxp[i & 7], s[i]);
-      const float mx = fmaxf(fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])),
-                             fmaxf(fmaxf(mxp[4], mxp[5]), fmaxf(mxp[6], mxp[7])));
+      for (int i = 4; i < 32; ++i) mxp[i & 3] = fmaxf(mxp[i & 3], s[i]);
+      float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
+      // the other half of the row: exchange through shared memory, 64-thread named barrier of the warp pair
+      *reinterpret_cast<float*>(bias_buf + my_slot) = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+      mx = fmaxf(mx, *reinterpret_cast<const float*>(bias_buf + peer_slot));
+      if (p.bias) {  // the bias buffer (and the exchange slot in it) goes back to the TMA producer
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->b_empty[j & 1]);
+      }
       const float m_new = mx * kLog2e;
       if (j == 0) {
         m_used = (m_new == -INFINITY) ? 0.f : m_new;
       } else {
-        // lazy rescale: only when some row of the warp outgrew its reference max by more than 2^8
+        // lazy rescale: only when some row of the warp outgrew its reference max by more than 2^8 (both halves of a
+        // row see the same m_new and m_used, so the partner warp takes the same branch for its 32 output columns)
         const bool grow = m_new > m_used + kRescaleThreshold;
         if (__any_sync(0xffffffffu, grow)) {
           mbar_wait(&bars->o_done, (j - 1) & 1);  // every P V issued so far has retired
           tc_fence_after();
           const float f = grow ? fast_exp2(m_used - m_new) : 1.0f;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_o + lane_addr + half * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int hb = 0; hb < 2; ++hb) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_o + lane_addr + hb * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-            tmem_st_32x32(tmem_o + lane_addr + hb * 32, r);
-          }
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          tmem_st_32x32(tmem_o + lane_addr + half * 32, r);
           tmem_st_wait();
           tc_fence_before();
           if (grow) {
@@ -295,7 +311,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       float2 ps[4] = {splat2(0.f), splat2(0.f), splat2(0.f), splat2(0.f)};
       const float2 l2e = splat2(kLog2e), nm = splat2(-m_used);
 #pragma unroll
-      for (int i = 0; i < kKTile; i += 2) {
+      for (int i = 0; i < 32; i += 2) {
         const float2 e = fma2(make_float2(s[i], s[i + 1]), l2e, nm);
         s[i] = fast_exp2(e.x);
         s[i + 1] = fast_exp2(e.y);
@@ -305,18 +321,18 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       l_run += pt.x + pt.y;
       // P (bf16) -> the single smem buffer once its previous reader P V(j-1) has retired (issued a tile ago)
       if (j >= 1) mbar_wait(&bars->o_done, (j - 1) & 1);
-      uint8_t* p_row = p_row0;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint4 u;
         u.x = pack_bf16x2(s[8 * c + 0], s[8 * c + 1]);
         u.y = pack_bf16x2(s[8 * c + 2], s[8 * c + 3]);
         u.z = pack_bf16x2(s[8 * c + 4], s[8 * c + 5]);
         u.w = pack_bf16x2(s[8 * c + 6], s[8 * c + 7]);
-        *reinterpret_cast<uint4*>(p_row + ((c ^ (tid & 7)) << 4)) = u;
+        *reinterpret_cast<uint4*>(p_row0 + ((static_cast<uint32_t>(4 * half + c) ^ sw) << 4)) = u;
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&bars->p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full);
     }
 
     if (n_kt > 0) {
@@ -324,27 +340,30 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       tc_fence_after();
     }
     {
+      // total row sum = both halves (every bias tile has been consumed: buffer 0 is free for the exchange)
+      uint8_t* xbuf = smem + AttnSmem::offBias + rowl * 128;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");  // the partner is past its last read of the max slot
+      *reinterpret_cast<float*>(xbuf + my_slot) = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+      const float l_tot = l_run + *reinterpret_cast<const float*>(xbuf + peer_slot);
       // the TMEM loads are warp-collective: every lane executes them, rows >= Tq only skip the stores
-      const float inv = (1.0f / l_run) * (p.head_scale ? p.head_scale[h] : 1.0f);
-      if (p.lse && row < p.Tq)  // log2-domain log-sum-exp of the (biased, masked) score row, for the backward
-        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Tq + row] = m_used + __log2f(l_run);
+      const float inv = (1.0f / l_tot) * (p.head_scale ? p.head_scale[h] : 1.0f);
+      if (p.lse && half == 0 && row < p.Tq)  // log2-domain log-sum-exp of the (biased, masked) score row, for the backward
+        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Tq + row] = m_used + __log2f(l_tot);
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(b) * p.o_batch_stride +
-                           static_cast<int64_t>(row) * p.o_row_stride + h * kHeadDim;
+                           static_cast<int64_t>(row) * p.o_row_stride + h * kHeadDim + half * 32;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_o + lane_addr + half * 32, r);
+      tmem_ld_wait();
+      if (row < p.Tq) {
 #pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_o + lane_addr + hb * 32, r);
-        tmem_ld_wait();
-        if (row < p.Tq) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]) * inv, __uint_as_float(r[8 * c + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + hb * 32 + 8 * c) = u;
-          }
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]) * inv, __uint_as_float(r[8 * c + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + 8 * c) = u;
         }
       }
     }
@@ -352,7 +371,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kSoftmaxWarps) {
     tc_fence_after();
     tmem_dealloc<256>(tmem_base);
   }

@@ -15,63 +15,9 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "gemm_common.cuh"
 
 namespace sgf {
-
-static constexpr int BM = 128;
-static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-static constexpr int UMMA_K = 16;
-template <int BN>
-static constexpr int gemm_epi_warps() { return BN >= 128 ? 8 : 4; }
-template <int BN>
-static constexpr int gemm_threads() { return 64 + 32 * gemm_epi_warps<BN>(); }
-
-struct GemmEpilogue {
-  void* c;
-  int64_t ldc, c_batch_stride;
-  int c_dtype;
-  const float* col_scale;
-  const float* col_bias;
-  const void* residual;
-  int64_t ldr, r_batch_stride;
-  int r_dtype;
-  int act;
-  float alpha;
-  int alpha_cols;
-  float* rowstats_out;
-  const float* rownorm_stats;
-  const float* rownorm_u;
-  float rownorm_inv_dim;
-  int rownorm_parts;
-};
-
-struct GemmShape {
-  int M, N, K;
-  // conv mode only
-  int H, W, bw, bh, tiles_w, tiles_h, cin_blocks;
-};
-
-template <int BN>
-struct GemmSmem {
-  static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-};
-
-// Epilogue feature set.  Specialised kernels carry the flags as a template argument so that each
-// instantiation contains only its own code path (the all-runtime kernel was 130 KB of SASS and
-// stalled on instruction fetch: every CTA runs its epilogue exactly once); kEpiRuntime keeps the
-// fully general path for odd shapes (N not a multiple of 32, rare operand combinations).
-enum : int {
-  kEpiScale = 1, kEpiBias = 2, kEpiAlpha = 4, kEpiGelu = 8, kEpiRelu = 16, kEpiResBf16 = 32, kEpiResF32 = 64,
-  kEpiOutF32 = 128, kEpiRowStats = 256, kEpiRowNorm = 512, kEpiAtomic = 1024, kEpiRuntime = 1 << 15
-};
-template <int kEpi, int kFlag>
-SGF_DEVICE bool epi_has(bool runtime_value) {
-  if constexpr ((kEpi & kEpiRuntime) != 0) return runtime_value;
-  else return (kEpi & kFlag) != 0;
-}
 
 // Epilogue shared by the 1-CTA and the 2-CTA kernels.  Executed by the kEpiWarps epilogue warps
 // (warp index 2..): `stage_bytes_avail` bytes at `smem` (the retired pipeline stages) hold the staging tiles.
@@ -1128,21 +1074,6 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return SGF_OK;
 }
 
-// feature mask of a call; specialised kernels exist for the combinations the segofa path uses
-static int epilogue_mask(const GemmEpilogue& ep) {
-  int m = 0;
-  if (ep.col_scale) m |= kEpiScale;
-  if (ep.col_bias) m |= kEpiBias;
-  if (ep.alpha_cols > 0) m |= kEpiAlpha;
-  if (ep.act == SGF_ACT_GELU) m |= kEpiGelu;
-  if (ep.act == SGF_ACT_RELU) m |= kEpiRelu;
-  if (ep.residual) m |= (ep.r_dtype == SGF_F32 ? kEpiResF32 : kEpiResBf16);
-  if (ep.c_dtype == SGF_F32) m |= kEpiOutF32;
-  if (ep.rowstats_out) m |= kEpiRowStats;
-  if (ep.rownorm_stats) m |= kEpiRowNorm;
-  return m;
-}
-
 #define SGF_EPI_CASE(MASK)                                                                              \
   case (MASK):                                                                                          \
     return launch_gemm<BN, kStages, kConv, (MASK)>(tmA, tmB, shp, ep, grid, st);
@@ -1296,14 +1227,16 @@ static int check_epilogue_alignment(const GemmEpilogue& ep, int N) {
 }
 
 // Kernel-family selection can be pinned from the environment for A/B measurements (tools/bench_gemm.py):
-//   SGF_GEMM_FAMILY = tile (one tile per CTA) | persist (persistent 1-CTA) | pair (persistent CTA pair) ; unset = automatic
-enum { kFamAuto = 0, kFamTile = 1, kFamPersist = 2, kFamPair = 3 };
+//   SGF_GEMM_FAMILY = tile (one tile per CTA) | persist (persistent 1-CTA) | pair (persistent CTA pair, direct stores)
+//                     | ts (persistent CTA pair, TMA-store epilogue: gemm_ts.cu) ; unset = automatic
+enum { kFamAuto = 0, kFamTile = 1, kFamPersist = 2, kFamPair = 3, kFamTs = 4 };
 static int gemm_family_override() {
   const char* e = getenv("SGF_GEMM_FAMILY");
   if (!e) return kFamAuto;
   if (!strcmp(e, "tile")) return kFamTile;
   if (!strcmp(e, "persist")) return kFamPersist;
   if (!strcmp(e, "pair")) return kFamPair;
+  if (!strcmp(e, "ts")) return kFamTs;
   return kFamAuto;
 }
 
@@ -1347,6 +1280,11 @@ extern "C" int sgf_gemm_bf16(const sgf_gemm_args* a, void* stream) {
   const int m_tiles = (a->M + BM - 1) / BM;
   int bn = pick_bn(m_tiles, a->N, a->batch);
   const int fam = gemm_family_override();
+  // persistent CTA-pair kernel with the TMA-store epilogue: everything with N % 64 == 0 and at least a few tiles
+  if (a->batch == 1 && (fam == kFamTs || (fam == kFamAuto && static_cast<long>(a->M) * a->N >= 128L * 1024))) {
+    const int rc = gemm_ts_dispatch(shp, ep, a->a, a->lda, a->b, a->ldb, false, 0, 0, st);
+    if (rc >= 0) return rc;
+  }
   // persistent CTA-pair kernel (256 x 256 tiles) for the large transformer GEMMs: full N tiles only
   const bool pair_ok = a->N % 256 == 0 && a->K >= 64;
   if ((fam == kFamPair && pair_ok) || (fam == kFamAuto && pair_ok && a->M >= 2048 && a->N >= 2048 && a->K >= 256)) {
@@ -1521,6 +1459,10 @@ extern "C" int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* a, void* stream) {
 
   const int m_tiles = a->n * shp.tiles_w * shp.tiles_h;
   const int fam = gemm_family_override();
+  if (fam == kFamTs || fam == kFamAuto) {
+    const int rc = gemm_ts_dispatch(shp, ep, a->x, 0, a->w, shp.K, true, a->n, a->cin, st);
+    if (rc >= 0) return rc;
+  }
   const int bnp = a->cout % 128 == 0 ? 128 : (a->cout % 64 == 0 ? 64 : 0);
   const bool persist = bnp && fam != kFamTile && (fam == kFamPersist || static_cast<long>(m_tiles) * (a->cout / bnp) >= 96);
   const int bn = persist ? bnp : pick_bn(m_tiles, a->cout, 1);

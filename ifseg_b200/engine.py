@@ -74,7 +74,7 @@ class SegOFAEngine:
     # ------------------------------------------------------------------------------------
     def _f32(self, t):
         if self.live is not None and self.live.arena.has(t):
-            return t.data  # live view of the fp32 master
+            return self.live.arena.value(t)  # live view of the fp32 master (== t.data only for an fp32 model)
         return t.detach().to(device=self.device, dtype=torch.float32).contiguous()
 
     def _b16(self, t):

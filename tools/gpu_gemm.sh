@@ -1,8 +1,3 @@
 set -x
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:gemm --csv --log-file gpurun_out/ab_gemm.csv python tools/ab_gemm_once.py tile persist > gpurun_out/ab_gemm.log 2>&1
-tail -2 gpurun_out/ab_gemm.log | cut -c1-2000
-python - <<'PY'
-import csv
-rows=[r for r in csv.reader(open('gpurun_out/ab_gemm.csv')) if len(r)>10 and r[0].isdigit()]
-for r in rows: print(r[4][:60], r[-1])
-PY
+ncu --set full --clock-control none --import-source on -k regex:gemm_ts -s 7 -c 7 -f -o gpurun_out/prof_gemm_ts_r02 python tools/prof_gemm_ts.py > gpurun_out/ncu_gts.log 2>&1
+tail -3 gpurun_out/ncu_gts.log
