@@ -9,7 +9,8 @@
 //                (ncu: warps active 13.5 %, issue active 29 %, tensor pipe 12 %).  Halving the chain and doubling the
 //                warps is what hides the tcgen05.ld / MUFU / shared-memory latencies.  The two halves of a row agree on
 //                the running maximum through a 4-byte exchange in shared memory and a 64-thread named barrier per tile.
-//   warp 8     : control -- one lane issues every TMA load and every tcgen05.mma
+//   warp 8     : score issuer  -- one lane: Q/K/bias TMA loads and the S = Q K^T tcgen05.mma, up to two tiles ahead
+//   warp 9     : output issuer -- one lane: V TMA loads and the O += P V tcgen05.mma
 // Per 64-key tile j (all asynchronous, mbarrier hand-offs, nothing waits on the tensor core in line):
 //   S(j) = Q K(j)^T      tcgen05.mma M128 N64 K64 into one of two TMEM score buffers, issued one tile
 //                        ahead so it runs under the softmax of tile j-1
@@ -34,9 +35,9 @@ namespace sgf {
 static constexpr int kQTile = 128;
 static constexpr int kKTile = 64;
 static constexpr int kHeadDim = 64;
-static constexpr int kAttnThreads = 288;
+static constexpr int kAttnThreads = 320;
 static constexpr int kSoftmaxWarps = 8;
-static constexpr int kKvStages = 3;
+static constexpr int kKvStages = 2;  // K and V rings (each refilled the moment its reader retires, two tiles ahead)
 static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr float kRescaleThreshold = 8.0f;  // log2 domain: probabilities stay below 2^8
 
@@ -48,6 +49,7 @@ struct AttnParams {
   const uint8_t* kpm;
   int B, H, Tq, Tk, causal;
   float* lse;
+  unsigned long long* trace;  // debug: per-role clock64 timeline of a few CTAs (sgf_debug_set_attention_trace)
 };
 
 struct AttnSmem {
@@ -58,18 +60,24 @@ struct AttnSmem {
   static constexpr int offQ = 0;
   static constexpr int offK = offQ + kQ;
   static constexpr int offV = offK + kKvStages * kKV;
-  static constexpr int offP = offV + kKvStages * kKV;  // one P buffer
-  static constexpr int offBias = offP + kP;            // two bias buffers
+  static constexpr int offP = offV + kKvStages * kKV;  // two P buffers: softmax(j+1) never waits for P V(j)
+  static constexpr int offBias = offP + 2 * kP;        // two bias buffers
   static constexpr int offBar = offBias + 2 * kBias;
   static constexpr int kTotal = offBar + 256;
 };
 
 struct AttnBars {
   uint64_t q_full, k_full[kKvStages], k_empty[kKvStages], v_full[kKvStages], v_empty[kKvStages];
-  uint64_t s_full[2], s_empty[2], p_full, b_empty[2], o_done;  // s_full also carries the bias-tile bytes
+  uint64_t s_full[2], s_empty[2], p_full[2], b_empty[2], o_done[2];  // s_full also carries the bias-tile bytes
   uint32_t tmem_slot;
 };
 static_assert(sizeof(AttnBars) <= 256, "barrier block");
+
+// debug timeline: slot = (cta, role, iteration, event); 4 CTAs x 4 roles x 32 iterations x 4 events
+SGF_DEVICE void attn_trace(const AttnParams& p, int cta_slot, int role, int j, int ev) {
+  if (p.trace && cta_slot >= 0 && j < 32)
+    p.trace[((cta_slot * 4 + role) * 32 + j) * 4 + ev] = static_cast<unsigned long long>(clock64());
+}
 
 __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                             const __grid_constant__ CUtensorMap tmK,
@@ -83,9 +91,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int b = blockIdx.x;  // batch fastest: the CTAs streaming the same (batch-invariant) bias tiles run together
-  const int q0 = blockIdx.y * kQTile;
+  // causal: the query tiles with the most key tiles are scheduled first (longest processing time first)
+  const int q0 = static_cast<int>(p.causal ? gridDim.y - 1 - blockIdx.y : blockIdx.y) * kQTile;
   const int h = blockIdx.z;
 
+  const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  const int tslot = !p.trace ? -1 : (lin == 0 ? 0 : (lin == 1 ? 1 : (lin == 300 ? 2 : (lin == 600 ? 3 : -1))));
   int n_kt = (p.Tk + kKTile - 1) / kKTile;
   if (p.causal) n_kt = min(n_kt, (min(q0 + kQTile, p.Tq) + kKTile - 1) / kKTile);  // keys j <= max row of the tile
 
@@ -102,10 +113,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       mbar_init(&bars->s_full[i], p.bias ? 2 : 1);  // tcgen05.commit of S(j) (+ the expect_tx arrive of bias(j))
       mbar_init(&bars->s_empty[i], kSoftmaxWarps);  // one arrival per softmax warp (lane 0 after __syncwarp)
     }
-    mbar_init(&bars->p_full, kSoftmaxWarps);
-    mbar_init(&bars->b_empty[0], kSoftmaxWarps);
-    mbar_init(&bars->b_empty[1], kSoftmaxWarps);
-    mbar_init(&bars->o_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->p_full[i], kSoftmaxWarps);
+      mbar_init(&bars->b_empty[i], kSoftmaxWarps);
+      mbar_init(&bars->o_done[i], 1);  // P V(t) retired -> o_done[t & 1]
+    }
     fence_mbar_init();
   }
   if (warp == kSoftmaxWarps) {
@@ -126,19 +138,17 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
   pdl_wait();
 
   if (warp == kSoftmaxWarps) {
-    // =========================== control lane: TMA + MMA issue ===========================
+    // ============ score issuer: Q / K / bias loads and S(j) = Q K(j)^T, up to two tiles ahead of the softmax ============
+    // (r01 issued S and P V from ONE thread in program order S(j), P V(j-1): S(j) then waited for softmax(j-2) to FINISH
+    //  although it only needs softmax(j-2) to have READ its score buffer, and the ~1700-cycle round trip
+    //  p_full -> wake -> issue -> retire -> s_full sat on the critical path of every tile: ncu showed the softmax warps
+    //  parked on s_full while the issuing thread was parked on p_full.)
     if ((tid & 31) == 0 && n_kt > 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(kQTile, kKTile, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(kQTile, kHeadDim, 0, 1);  // B (= V) is MN-major
       auto load_k = [&](int t) {
         const int st = t % kKvStages;
         mbar_expect_tx(&bars->k_full[st], AttnSmem::kKV);
         tma_load_4d(smem + AttnSmem::offK + st * AttnSmem::kKV, &tmK, &bars->k_full[st], 0, h, t * kKTile, b);
-      };
-      auto load_v = [&](int t) {
-        const int st = t % kKvStages;
-        mbar_expect_tx(&bars->v_full[st], AttnSmem::kKV);
-        tma_load_4d(smem + AttnSmem::offV + st * AttnSmem::kKV, &tmV, &bars->v_full[st], 0, h, t * kKTile, b);
       };
       auto load_bias = [&](int t) {  // completes on the same barrier as S(t): one wait per tile for the softmax warps
         mbar_expect_tx(&bars->s_full[t & 1], AttnSmem::kBias);
@@ -151,54 +161,67 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         load_bias(0);
         if (n_kt > 1) load_bias(1);
       }
-      for (int t = 0; t < 2 && t < n_kt; ++t) load_v(t);
       const uint64_t dq = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offQ));
-
 #pragma unroll 1
-      for (int j = 0; j <= n_kt; ++j) {
-        if (j < n_kt) {
-          // ---- S(j) = Q K(j)^T into score buffer j&1 (free once softmax(j-2) has read it) ----
-          const int st = j % kKvStages;
-          if (j == 0) mbar_wait(&bars->q_full, 0);
-          mbar_wait(&bars->k_full[st], (j / kKvStages) & 1);
-          mbar_wait(&bars->s_empty[j & 1], ((j >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint64_t dk = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offK + st * AttnSmem::kKV));
+      for (int j = 0; j < n_kt; ++j) {
+        // ---- S(j) into score buffer j&1 (free once softmax(j-2) has read it) ----
+        const int st = j % kKvStages;
+        attn_trace(p, tslot, 0, j, 0);
+        if (j == 0) mbar_wait(&bars->q_full, 0);
+        mbar_wait(&bars->k_full[st], (j / kKvStages) & 1);
+        attn_trace(p, tslot, 0, j, 1);
+        mbar_wait(&bars->s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        attn_trace(p, tslot, 0, j, 2);
+        tc_fence_after();
+        const uint64_t dk = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offK + st * AttnSmem::kKV));
 #pragma unroll
-          for (int k = 0; k < kHeadDim / 16; ++k)
-            umma_f16(tmem_s + (j & 1) * 64, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-          umma_commit(&bars->s_full[j & 1]);
-          umma_commit(&bars->k_empty[st]);
-          // K(j-1)'s stage is free (S(j-1) retired a tile ago): prefetch K(j+2) into it
-          if (j >= 1 && j + 2 < n_kt) {
-            mbar_wait(&bars->k_empty[(j - 1) % kKvStages], ((j - 1) / kKvStages) & 1);
-            load_k(j + 2);
-          }
-          // V(j+1) goes into the stage of V(j-2) (P V(j-2) was issued a tile ago); V(0), V(1) were loaded up front
-          if (j >= 1 && j + 1 < n_kt) {
-            if (j >= 2) mbar_wait(&bars->v_empty[(j - 2) % kKvStages], ((j - 2) / kKvStages) & 1);
-            load_v(j + 1);
-          }
-          // bias(j+1) goes into the buffer softmax(j-1) has read
-          if (p.bias && j >= 1 && j + 1 < n_kt) {
-            mbar_wait(&bars->b_empty[(j + 1) & 1], ((j - 1) >> 1) & 1);
-            load_bias(j + 1);
-          }
+        for (int k = 0; k < kHeadDim / 16; ++k)
+          umma_f16(tmem_s + (j & 1) * 64, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&bars->s_full[j & 1]);
+        umma_commit(&bars->k_empty[st]);
+        attn_trace(p, tslot, 0, j, 3);
+        // bias(j+1) goes into the buffer softmax(j-1) has consumed (it hands it back right after its row-max exchange)
+        if (p.bias && j >= 1 && j + 1 < n_kt) {
+          mbar_wait(&bars->b_empty[(j + 1) & 1], ((j - 1) >> 1) & 1);
+          load_bias(j + 1);
         }
-        if (j >= 1) {
-          // ---- O += P(j-1) V(j-1) once softmax(j-1) has published P ----
-          const int t = j - 1;
-          const int st = t % kKvStages;
-          mbar_wait(&bars->v_full[st], (t / kKvStages) & 1);
-          mbar_wait(&bars->p_full, t & 1);
-          tc_fence_after();
-          const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offV + st * AttnSmem::kKV));
-          const uint64_t dp = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offP));
+        // K(j+2) goes into the stage S(j) is reading
+        if (j + kKvStages < n_kt) {
+          mbar_wait(&bars->k_empty[st], (j / kKvStages) & 1);
+          load_k(j + kKvStages);
+        }
+      }
+    }
+  } else if (warp == kSoftmaxWarps + 1) {
+    // ============ output issuer: V loads and O += P(t) V(t) as soon as softmax(t) has published P ============
+    if ((tid & 31) == 0 && n_kt > 0) {
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kQTile, kHeadDim, 0, 1);  // B (= V) is MN-major
+      auto load_v = [&](int t) {
+        const int st = t % kKvStages;
+        mbar_expect_tx(&bars->v_full[st], AttnSmem::kKV);
+        tma_load_4d(smem + AttnSmem::offV + st * AttnSmem::kKV, &tmV, &bars->v_full[st], 0, h, t * kKTile, b);
+      };
+      for (int t = 0; t < kKvStages && t < n_kt; ++t) load_v(t);
+#pragma unroll 1
+      for (int t = 0; t < n_kt; ++t) {
+        const int st = t % kKvStages;
+        attn_trace(p, tslot, 1, t, 0);
+        mbar_wait(&bars->v_full[st], (t / kKvStages) & 1);
+        attn_trace(p, tslot, 1, t, 1);
+        mbar_wait(&bars->p_full[t & 1], (t >> 1) & 1);
+        attn_trace(p, tslot, 1, t, 2);
+        tc_fence_after();
+        const uint64_t dp = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offP + (t & 1) * AttnSmem::kP));
+        const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offV + st * AttnSmem::kKV));
 #pragma unroll
-          for (int k = 0; k < kKTile / 16; ++k)  // V: 16 key rows = 2048 B per K step -> +128 in the address field
-            umma_f16(tmem_o, dp + 2 * k, dv + 128 * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
-          umma_commit(&bars->v_empty[st]);
-          umma_commit(&bars->o_done);
+        for (int k = 0; k < kKTile / 16; ++k)  // V: 16 key rows = 2048 B per K step -> +128 in the address field
+          umma_f16(tmem_o, dp + 2 * k, dv + 128 * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
+        umma_commit(&bars->v_empty[st]);
+        umma_commit(&bars->o_done[t & 1]);
+        attn_trace(p, tslot, 1, t, 3);
+        if (t + kKvStages < n_kt) {  // V(t+2) goes into the stage P V(t) is reading
+          mbar_wait(&bars->v_empty[st], (t / kKvStages) & 1);
+          load_v(t + kKvStages);
         }
       }
     }
@@ -212,7 +235,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
     const uint32_t sw = static_cast<uint32_t>(rowl & 7);
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const uint8_t* kpm_row = p.kpm ? p.kpm + static_cast<int64_t>(b) * p.Tk : nullptr;
-    uint8_t* p_row0 = smem + AttnSmem::offP + rowl * 128;
+    uint8_t* p_row0 = smem + AttnSmem::offP + rowl * 128;  // + (j & 1) * kP
     // row-maximum exchange slots: the first 4 bytes of the bias chunks this thread has already consumed (the bias buffers
     // are idle when there is no bias); the partner reads them after the pair barrier, before the buffer is handed back
     const uint32_t my_slot = ((static_cast<uint32_t>(4 * half) ^ sw) << 4);
@@ -224,8 +247,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
     for (int j = 0; j < n_kt; ++j) {
       const int k0 = j * kKTile + half * 32;
       uint8_t* bias_buf = smem + AttnSmem::offBias + (j & 1) * AttnSmem::kBias + rowl * 128;
+      const int trole = (lane == 0 && (warp == 0 || warp == 7)) ? (warp == 0 ? 2 : 3) : -1;
+      if (trole >= 0) attn_trace(p, tslot, trole, j, 0);
       mbar_wait(&bars->s_full[j & 1], (j >> 1) & 1);  // S(j) retired and bias(j) landed (P V(j-2) retired too)
       tc_fence_after();
+      if (trole >= 0) attn_trace(p, tslot, trole, j, 1);
       float s[32];
       {
         uint32_t r0[32];
@@ -278,6 +304,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       *reinterpret_cast<float*>(bias_buf + my_slot) = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
       mx = fmaxf(mx, *reinterpret_cast<const float*>(bias_buf + peer_slot));
+      if (trole >= 0) attn_trace(p, tslot, trole, j, 2);
       if (p.bias) {  // the bias buffer (and the exchange slot in it) goes back to the TMA producer
         fence_proxy_async();
         __syncwarp();
@@ -291,7 +318,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         // row see the same m_new and m_used, so the partner warp takes the same branch for its 32 output columns)
         const bool grow = m_new > m_used + kRescaleThreshold;
         if (__any_sync(0xffffffffu, grow)) {
-          mbar_wait(&bars->o_done, (j - 1) & 1);  // every P V issued so far has retired
+          mbar_wait(&bars->o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);  // every P V issued so far has retired
           tc_fence_after();
           const float f = grow ? fast_exp2(m_used - m_new) : 1.0f;
           uint32_t r[32];
@@ -319,8 +346,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       }
       const float2 pt = add2(add2(ps[0], ps[1]), add2(ps[2], ps[3]));
       l_run += pt.x + pt.y;
-      // P (bf16) -> the single smem buffer once its previous reader P V(j-1) has retired (issued a tile ago)
-      if (j >= 1) mbar_wait(&bars->o_done, (j - 1) & 1);
+      // P (bf16) -> buffer j&1 once its previous reader P V(j-2) has retired (issued two tiles ago)
+      if (trole >= 0) attn_trace(p, tslot, trole, j, 3);
+      if (j >= 2) mbar_wait(&bars->o_done[j & 1], ((j - 2) >> 1) & 1);
+      uint8_t* p_row = p_row0 + (j & 1) * AttnSmem::kP;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 u;
@@ -328,15 +357,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         u.y = pack_bf16x2(s[8 * c + 2], s[8 * c + 3]);
         u.z = pack_bf16x2(s[8 * c + 4], s[8 * c + 5]);
         u.w = pack_bf16x2(s[8 * c + 6], s[8 * c + 7]);
-        *reinterpret_cast<uint4*>(p_row0 + ((static_cast<uint32_t>(4 * half + c) ^ sw) << 4)) = u;
+        *reinterpret_cast<uint4*>(p_row + ((static_cast<uint32_t>(4 * half + c) ^ sw) << 4)) = u;
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->p_full);
+      if (lane == 0) mbar_arrive(&bars->p_full[j & 1]);
     }
 
     if (n_kt > 0) {
-      mbar_wait(&bars->o_done, (n_kt - 1) & 1);
+      mbar_wait(&bars->o_done[(n_kt - 1) & 1], ((n_kt - 1) >> 1) & 1);
       tc_fence_after();
     }
     {
@@ -389,6 +418,9 @@ static int make_qkv_map(CUtensorMap* m, const void* base, int64_t row_stride, in
 
 using namespace sgf;
 
+static unsigned long long* g_attention_trace = nullptr;
+extern "C" void sgf_debug_set_attention_trace(void* buf) { g_attention_trace = reinterpret_cast<unsigned long long*>(buf); }
+
 extern "C" int sgf_attention_bf16(const sgf_attention_args* a, void* stream) {
   SGF_REQUIRE(a != nullptr && a->q && a->k && a->v && a->out, "attention: null pointer");
   SGF_REQUIRE(a->B > 0 && a->H > 0 && a->Tq > 0 && a->Tk > 0, "attention: bad shape");
@@ -417,7 +449,7 @@ extern "C" int sgf_attention_bf16(const sgf_attention_args* a, void* stream) {
       return rc;
   }
   AttnParams p{a->out, a->o_row_stride, a->o_batch_stride, a->bias, a->head_scale, a->key_padding_mask,
-               a->B, a->H, a->Tq, a->Tk, a->causal, a->lse};
+               a->B, a->H, a->Tq, a->Tk, a->causal, a->lse, g_attention_trace};
   constexpr int smem = AttnSmem::kTotal;
   static bool configured = false;
   if (!configured) {
