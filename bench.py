@@ -42,11 +42,12 @@ sys.path.insert(0, ROOT)
 # committed `ncu --set full` captures (the roofline is tensor-bound; traffic is reported to show there are no wasted
 # re-reads: it is below the algorithmic operand bytes because C tiles stay in the 126 MB L2)
 NCU_TRAFFIC = {
-    2: (15.79e6, "gemm2p_tcgen05_kernel<6> (fc1: M=7208 N=3072 K=768; algorithmic operand bytes 60.1 MB), "
-                 "profiles/r01_gemm2p_final_full.txt"),
+    2: (17.14e6, "gemm_ts_kernel<256,0,2> (fc1 shape: M=7488 N=3072 K=768; algorithmic operand bytes 62.2 MB: A and B are "
+                 "read once from HBM, the bf16 C tile is still in L2 when the kernel ends), profiles/r02_gemm_ts_full.txt"),
     3: (68.95e6, "gemm_mm_tcgen05_kernel<128,3,1,1,1152> (split-K weight gradient, fp32 accumulate; "
                  "algorithmic 77.9 MB for the fc weight gradient), profiles/r01_trainmisc_final_full.txt"),
 }
+# forward FLOPs of the attention launches of one image (QK^T + PV, causal decoder self-attention counted as executed)
 FLOPS_PER_IMG = {2: 286.8e9, 4: 364.6e9, 3: 1061.2e9, 5: 6465.3e9}  # SURVEY.md s8d (forward / train step, algorithmic)
 CONFIGS = {
     # id: (arch, image, classes, batch, description)
@@ -131,7 +132,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(cfg_id, steps, warmup, sample_batch=None):
+def cpu_reference_run(cfg_id, steps, warmup, sample_batch=None, want_outputs=False):
     """Times the oracle port (reference algorithm, fp32 torch CPU) on all host threads."""
     import torch
 
@@ -149,10 +150,12 @@ def cpu_reference_run(cfg_id, steps, warmup, sample_batch=None):
     inp = synthetic_inputs(cfg, b, size, seed=1, src_tokens=prompt_tokens(nseg))
     hp = size // 16
 
+    last = {}
+
     def step():
         with torch.no_grad():
             lg, _ = R.segofa_forward(sd, ocfg, inp["src_tokens"], inp["patch_images"], inp["patch_masks"])
-            return R.predict_mask(lg, hp, hp, size, size)
+            last["logits"], last["mask"] = lg, R.predict_mask(lg, hp, hp, size, size)
 
     for _ in range(warmup):
         step()
@@ -160,9 +163,40 @@ def cpu_reference_run(cfg_id, steps, warmup, sample_batch=None):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return dict(value=b / dt, unit="images/s", cores=cores, kind="port",
-                sample=f"{steps} timed + {warmup} warm-up forward->mask passes of batch {b} (of {batch}) at {size}x{size}, "
-                       f"fp32 torch CPU, {cores} threads; oracle/restated.py pinned on the reference"), dt
+    last["inputs"] = inp
+    cb = dict(value=b / dt, unit="images/s", cores=cores, kind="port",
+              sample=f"{steps} timed + {warmup} warm-up forward->mask passes of batch {b} (of {batch}) at {size}x{size}, "
+                     f"fp32 torch CPU, {cores} threads; oracle/restated.py pinned on the reference")
+    return (cb, dt, last) if want_outputs else (cb, dt)
+
+
+def parity_against_oracle(model, last, size):
+    """The timed configuration checked against the oracle run of the cpu_baseline leg (same seeded weights and inputs):
+    logits rel-L2 against the fp32 oracle, mask agreement, and how many disagreeing pixels have a top-2 margin the logit
+    error cannot explain (must be 0).  tests/test_parity_gpu.py holds the gates; this is the record next to the number."""
+    import torch
+
+    inp = last["inputs"]
+    with torch.no_grad():
+        x, extra = model(**{k: v.cuda() for k, v in inp.items()})
+        hp, wp = extra["encoder_returns"]["image_embed_shape"][0]
+        mask = model.engine().predict_mask(x, (hp, wp), (size, size)).view(x.shape[0], -1).cpu()
+    ref, ref_mask = last["logits"].float(), last["mask"].view(x.shape[0], -1)
+    xc = x.float().cpu()
+    rel = ((xc - ref).norm() / ref.norm()).item()
+    max_err = (xc - ref).abs().max().item()
+    from oracle import restated as R
+
+    up = R.upsample_logits(ref, hp, wp, size, size)[:, :-1]
+    top2 = up.topk(2, dim=-1).values
+    margin = (top2[..., 0] - top2[..., 1]).view(x.shape[0], -1)
+    dis = mask != ref_mask
+    return {"against": "oracle/restated.py (fp32, pinned on the reference), same seeded weights and inputs",
+            "batch": int(x.shape[0]), "logits_rel_l2": rel, "logits_max_abs_err": max_err,
+            "mask_agree": 1.0 - dis.float().mean().item(), "mask_pixels": int(dis.numel()),
+            "mask_disagree_beyond_4x_logit_err": int((dis & (margin > 4 * max_err)).sum()),
+            "bf16_floor_note": "the reference's own bf16 autocast forward sits at rel-L2 1.4e-2 from its fp32 forward "
+                               "(tests/test_model_gpu.py); gates and the rounding-matched oracle: tests/test_parity_gpu.py"}
 
 
 def cpu_reference_train_run(cfg_id, steps, warmup):
@@ -210,6 +244,34 @@ def cpu_reference_train_run(cfg_id, steps, warmup):
 
 
 def bench_train(args, rank, world, local_rank, config):
+    import torch.distributed as dist
+
+    out = measure_train(args, rank, world, local_rank, args.config, config, args.steps, max(args.warmup, 3),
+                        cpu_baseline=not args.no_cpu_baseline)
+    if rank == 0:
+        emit(out)
+    teardown(world)
+
+
+def teardown(world):
+    """Multi-rank exit.  A CUDA graph that captured NCCL all-reduces keeps the communicator's stream dependencies alive and
+    destroy_process_group() then hangs with this torch/NCCL build (r01); the process has nothing left to flush, so every
+    rank synchronises, meets the others at a barrier and leaves without tearing the communicator down."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stderr.flush()
+    os._exit(0)
+
+
+def measure_train(args, rank, world, local_rank, cfg_id, config, steps, warmup, cpu_baseline=False):
+    """One image-free finetune step (aux fwd+bwd + no-grad real-image fwd + metrics + gradient all-reduce + Adam) timed
+    on the device as the max over ranks; returns the record on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
 
@@ -218,12 +280,14 @@ def bench_train(args, rank, world, local_rank, config):
     from ifseg_b200.synthetic import generate_state_dict, synthetic_train_sample
     from ifseg_b200.trainer import SegOFATrainer, TrainSession
 
-    arch, size, nseg, batch, desc = CONFIGS[args.config]
+    arch, size, nseg, batch, desc = CONFIGS[cfg_id]
     peaks = load_peaks()
     model = SegOFAModel.from_config(arch, nseg, size)
     model.load_state_dict(generate_state_dict(model.cfg, 0), strict=True)
     model = model.cuda()
     trainer = SegOFATrainer(model)  # shipped recipe: Adam lr 5e-5, wd 0.1, clip 1.0 (Appendix B)
+    if world > 1:
+        os.environ.setdefault("SGF_GRAPH_NCCL", "1")  # capture the bucketed all-reduces too (see teardown())
     smp = synthetic_train_sample(model.cfg, batch, size, seed=1 + rank, src_tokens=prompt_tokens(nseg))
     pinned = {k: ({kk: vv.pin_memory() for kk, vv in v.items()} if isinstance(v, dict) else
                   (v.pin_memory() if torch.is_tensor(v) else v)) for k, v in smp.items()}
@@ -235,7 +299,7 @@ def bench_train(args, rank, world, local_rank, config):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         sess.step()
     barrier()
     sampler = ClockSampler(local_rank)
@@ -243,7 +307,7 @@ def bench_train(args, rank, world, local_rank, config):
         sampler.start()
     evs = []
     with torch.cuda.stream(sess.stream):
-        for _ in range(args.steps):
+        for _ in range(steps):
             flush.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record(sess.stream)
@@ -252,7 +316,7 @@ def bench_train(args, rank, world, local_rank, config):
             evs.append((s, e))
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    dev_ms = sum(s.elapsed_time(e) for s, e in evs) / args.steps
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs) / steps
     # end to end: pinned host sample -> device buffers -> step -> loss back on the host, every step
     def e2e_step():
         sess.load(pinned)
@@ -264,7 +328,7 @@ def bench_train(args, rank, world, local_rank, config):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -294,35 +358,38 @@ def bench_train(args, rank, world, local_rank, config):
     n = max(world, 1)
     if rank == 0:
         d = fam["gemm_tcgen05"]
-        achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
-        step_tflops = FLOPS_PER_IMG[args.config] * batch / (dev_ms / 1e3) / 1e12
+        # family time inside the timed (graph) step = its share of the per-launch CUDA-event times x the step time
+        achieved = d["flops"] / (d["ms"] / total_k_ms * dev_ms / 1e3) / 1e12
+        step_tflops = FLOPS_PER_IMG[cfg_id] * batch / (dev_ms / 1e3) / 1e12
         out = {
             "metric": "images/sec (train step)", "value": n * batch / (dev_ms / 1e3), "unit": "images/s", "n_gpus": n,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True,
+            "steps": steps, "warmup": warmup, "ms_per_step": dev_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
-            "e2e": {"value": n * batch * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
+            "e2e": {"value": n * batch * steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
-            "gpu_launches": sess.launches_per_step * args.steps, "clocks": clocks,
+            "gpu_launches": sess.launches_per_step * steps, "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05", "achieved": achieved,
                          "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                         "traffic": NCU_TRAFFIC.get(args.config, (None, None))[0],
-                         "traffic_source": NCU_TRAFFIC.get(args.config, (None, None))[1],
+                         "traffic": NCU_TRAFFIC.get(cfg_id, (None, None))[0],
+                         "traffic_source": NCU_TRAFFIC.get(cfg_id, (None, None))[1],
                          "peak_source": peaks["source"] + " (bf16 sustained)",
                          "launches_per_step": d["launches"], "share_of_step_kernel_time": d["ms"] / total_k_ms,
                          "step": {"achieved": step_tflops, "frac": step_tflops / peaks["bf16_sustained"],
-                                  "flops_per_image": FLOPS_PER_IMG[args.config]}},
+                                  "flops_per_image": FLOPS_PER_IMG[cfg_id]}},
             "kernel_families": {k: {"launches": v["launches"], "ms": round(v["ms"], 4)} for k, v in fam.items()},
             "cuda_graph": sess.graph is not None,
             "train": {"dropout": trainer.engine.drop_p if trainer.engine.stochastic else 0.0,
                       "drop_path_max": max(trainer.engine.enc_dpr) if trainer.engine.stochastic else 0.0,
                       "note": "shipped recipe noise (dropout 0.1, DropPath 0..0.1) on; all 380 gradient tensors; Adam + clip"},
         }
-        if not args.no_cpu_baseline:
-            cb, _ = cpu_reference_train_run(args.config, 1, 0)
+        out["grad_allreduce"] = {"world": n, "bytes_per_step": int(trainer.engine.arena.grad32.numel() * 4) if n > 1 else 0,
+                                 "dtype": "f32", "how": "bucketed NCCL all-reduce of the flat fp32 gradient arena, launched "
+                                 "per layer bucket as the backward reaches it" if n > 1 else "single rank: none"}
+        if cpu_baseline:
+            cb, _ = cpu_reference_train_run(cfg_id, 1, 0)
             out["cpu_baseline"] = cb
-        emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+        return out
+    return None
 
 
 def main():
@@ -334,6 +401,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-record", action="store_true",
+                    help="skip the short cfg-3 train-step measurement that is attached to the inference line as `train_step`")
     ap.add_argument("--kernel-breakdown", action="store_true", help="print the per-kernel-family table to stderr")
     ap.add_argument("--profile-step", action="store_true",
                     help="wrap ONE eager forward->mask step in cudaProfilerStart/Stop (ncu --profile-from-start off)")
@@ -344,7 +413,8 @@ def main():
     arch, size, nseg, batch, desc = CONFIGS[args.config]
     config = {"workload": desc, "arch": arch, "image_size": size, "num_classes": nseg, "per_gpu_batch": batch,
               "global_batch": batch * max(world, 1), "parallelism": f"dp{max(world, 1)} (independent replicas)",
-              "l2_policy": "256 MB memset between timed steps (not timed)"}
+              "l2_policy": "256 MB memset between timed steps (not timed)",
+              "bias_cached": True}  # the additive position bias is parameter-only: built once per shape, not per step
 
     if args.impl == "reference":
         if rank != 0:
@@ -470,11 +540,29 @@ def main():
     e2e_value = n * batch * args.steps / e2e_s
 
     if rank == 0:
-        gemm = fam.get("gemm_tcgen05", dom[1])
         dom_name = "gemm_tcgen05" if "gemm_tcgen05" in fam and fam["gemm_tcgen05"]["ms"] >= 0.3 * dom[1]["ms"] else dom[0]
         d = fam[dom_name]
-        achieved = d["flops"] / (d["ms"] / 1e3) / 1e12
+        # time of a kernel family inside the timed (CUDA-graph) step = its share of the per-launch CUDA-event times of one
+        # eager step x the graph step time (the eager per-launch events carry ~3 us of launch gap each; the SHARES agree
+        # with the ncu launch list, profiles/r02_launches_*.txt)
+        fam_ms = lambda v: v["ms"] / total_k_ms * dev_ms  # noqa: E731
+        achieved = d["flops"] / (fam_ms(d) / 1e3) / 1e12
         step_tflops = FLOPS_PER_IMG.get(args.config, 0.0) * batch / (dev_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peaks["bf16_sustained"],
+                "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                "traffic": NCU_TRAFFIC.get(args.config, (None, None))[0],
+                "traffic_source": NCU_TRAFFIC.get(args.config, (None, None))[1],
+                "peak_source": peaks["source"] + " (bf16 sustained: kernel timed inside a long step)",
+                "launches_per_step": d["launches"], "share_of_step_kernel_time": d["ms"] / total_k_ms,
+                "ms_in_step": fam_ms(d),
+                "step": {"achieved": step_tflops, "frac": step_tflops / peaks["bf16_sustained"],
+                         "flops_per_image": FLOPS_PER_IMG.get(args.config)}}
+        if "attention_tcgen05" in fam:  # north_star: achieved fraction of the attention-GEMM roofline
+            a = fam["attention_tcgen05"]
+            a_tf = a["flops"] / (fam_ms(a) / 1e3) / 1e12
+            roof["attention"] = {"kernel": "attention_tcgen05 (QK^T + PV tcgen05.mma, fused bias/softmax)", "achieved": a_tf,
+                                 "frac": a_tf / peaks["bf16_sustained"], "unit": "TFLOP/s", "launches_per_step": a["launches"],
+                                 "ms_in_step": fam_ms(a), "share_of_step_kernel_time": a["ms"] / total_k_ms}
         out = {
             "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": n, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
@@ -483,23 +571,31 @@ def main():
                     "d2h_bytes_per_step": sess.d2h_bytes_per_step},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": dom_name, "achieved": achieved, "peak": peaks["bf16_sustained"],
-                         "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                         "traffic": NCU_TRAFFIC.get(args.config, (None, None))[0],
-                         "traffic_source": NCU_TRAFFIC.get(args.config, (None, None))[1],
-                         "peak_source": peaks["source"] + " (bf16 sustained: kernel timed inside a long step)",
-                         "launches_per_step": d["launches"], "share_of_step_kernel_time": d["ms"] / total_k_ms,
-                         "step": {"achieved": step_tflops, "frac": step_tflops / peaks["bf16_sustained"],
-                                  "flops_per_image": FLOPS_PER_IMG.get(args.config)}},
+            "roofline": roof,
             "kernel_families": {k: {"launches": v["launches"], "ms": round(v["ms"], 4)} for k, v in fam.items()},
             "cuda_graph": not args.no_graph,
         }
         if not args.no_cpu_baseline:
-            cb, _ = cpu_reference_run(args.config, 1, 1, sample_batch=1 if size >= 256 else None)
+            cb, _, last = cpu_reference_run(args.config, 1, 1, sample_batch=1 if size >= 256 else None, want_outputs=True)
             out["cpu_baseline"] = cb
+            out["parity"] = parity_against_oracle(model, last, size)
+    else:
+        out = None
+    # ---------------- the training step of the same recipe on the same N ranks (cfg 3), as a sub-record ----------------
+    if not args.no_train_record:
+        del sess
+        torch.cuda.empty_cache()
+        t_arch, t_size, t_nseg, t_batch, t_desc = CONFIGS[3]
+        t_cfg = {"workload": t_desc, "arch": t_arch, "image_size": t_size, "num_classes": t_nseg, "per_gpu_batch": t_batch,
+                 "global_batch": t_batch * n, "parallelism": f"dp{n} (gradient all-reduce over NCCL)"}
+        tr = measure_train(args, rank, world, local_rank, 3, t_cfg, min(args.steps, 8), 3, cpu_baseline=False)
+        if rank == 0:
+            keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "config", "e2e", "gpu_launches",
+                    "roofline", "cuda_graph", "grad_allreduce", "train")
+            out["train_step"] = {k: tr[k] for k in keep if k in tr}
+    if rank == 0:
         emit(out)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown(world)
 
 
 if __name__ == "__main__":

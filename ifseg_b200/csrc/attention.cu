@@ -2,15 +2,17 @@
 //
 //   O[b,i,h,:] = head_scale[h] * softmax_j( Q[b,i,h,:].K[b,j,h,:] + bias[h,i,j] + mask ) V[b,j,h,:]
 //
-// One CTA per (128-query tile, head, batch); 9 warps:
-//   warps 0..7 : softmax, TWO threads per query row: warp w and warp w+4 share TMEM lane quarter w&3 and split the 64 keys
-//                of a tile in halves (32 score columns, 32 P columns, 32 O columns each).  The r01 kernel had one thread
-//                per row: 164 registers, 8 softmax warps per SM, every warp a 375-instruction dependent chain per tile
-//                (ncu: warps active 13.5 %, issue active 29 %, tensor pipe 12 %).  Halving the chain and doubling the
-//                warps is what hides the tcgen05.ld / MUFU / shared-memory latencies.  The two halves of a row agree on
-//                the running maximum through a 4-byte exchange in shared memory and a 64-thread named barrier per tile.
-//   warp 8     : score issuer  -- one lane: Q/K/bias TMA loads and the S = Q K^T tcgen05.mma, up to two tiles ahead
-//   warp 9     : output issuer -- one lane: V TMA loads and the O += P V tcgen05.mma
+// One CTA per (128-query tile, head, batch); 6 warps, two CTAs per SM:
+//   warps 0..3 : softmax, thread r owns query row r (TMEM lane r); the 64 keys of a tile are processed as two 32-key
+//                sub-tiles of the online softmax (32 scores live at a time; the TMEM load of the second half runs
+//                under the arithmetic of the first)
+//   warp 4     : score issuer  -- one lane: Q/K/bias TMA loads and the S = Q K^T tcgen05.mma, up to two tiles ahead
+//   warp 5     : output issuer -- one lane: V TMA loads and the O += P V tcgen05.mma
+// What the r02 timeline and ablation measurements say (profiles/r02_attention_analysis.txt): the tile loop is bound by
+// the fixed per-tile hand-off latencies (mbarrier wake-ups, tcgen05.ld, fence.proxy.async, single-thread MMA issue:
+// ~1850 of ~2200 cycles per tile survive when ALL softmax arithmetic is removed), not by MUFU / FMA throughput and not
+// by the number of softmax warps (4, 8 per CTA measured: same time).  Hence: issuers split so S runs two tiles ahead of
+// the softmax instead of behind P V, P double-buffered so softmax(j+1) never waits for P V(j), 2-stage K/V rings.
 // Per 64-key tile j (all asynchronous, mbarrier hand-offs, nothing waits on the tensor core in line):
 //   S(j) = Q K(j)^T      tcgen05.mma M128 N64 K64 into one of two TMEM score buffers, issued one tile
 //                        ahead so it runs under the softmax of tile j-1
@@ -19,11 +21,9 @@
 //                        more than 2^8), exp2, row sum; P(j) -> smem as bf16 in the swizzled K-major
 //                        layout the tensor core reads
 //   O += P(j) V(j)       tcgen05.mma M128 N64 K64 accumulating in TMEM (V tile is the MN-major B operand)
-// The loop is TMA-latency bound unless every stream is prefetched at least two tiles ahead (a tile costs ~2000
-// cycles of softmax work, an L2->smem TMA round trip under load ~3500): K and V tiles are triple-buffered, the bias
-// tile is FP16 (half the bytes of the dominant L2 stream) and double-buffered, P is single-buffered (its reader
-// P V(j-1) retires long before softmax(j) has its probabilities).  112 KB of shared memory and 256 TMEM columns per
-// CTA keep two CTAs per SM, so the eight softmax warps of an SM cover each other's waits.
+// K, V (2-stage rings), the FP16 bias tile and P are double-buffered: 112 KB of shared memory and 256 TMEM columns per
+// CTA keep two CTAs per SM.
+#include <stdlib.h>
 #include <string.h>
 
 #include <cuda_fp16.h>
@@ -35,8 +35,8 @@ namespace sgf {
 static constexpr int kQTile = 128;
 static constexpr int kKTile = 64;
 static constexpr int kHeadDim = 64;
-static constexpr int kAttnThreads = 320;
-static constexpr int kSoftmaxWarps = 8;
+static constexpr int kAttnThreads = 192;
+static constexpr int kSoftmaxWarps = 4;
 static constexpr int kKvStages = 2;  // K and V rings (each refilled the moment its reader retires, two tiles ahead)
 static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr float kRescaleThreshold = 8.0f;  // log2 domain: probabilities stay below 2^8
@@ -227,40 +227,42 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
     }
   } else {
     // =================================== softmax warps ===================================
+    // thread = query row (TMEM lane); the 64 keys of a tile are taken as two 32-key sub-tiles of the online softmax so
+    // that only 32 scores are live at a time (~100 registers instead of the 164 of a 64-wide row) and the TMEM load of
+    // the second half overlaps the arithmetic of the first
     const int lane = tid & 31;
-    const int qd = warp & 3;        // TMEM lane quarter
-    const int half = warp >> 2;     // which 32 of the tile's 64 keys (and of the 64 output columns) this thread owns
-    const int rowl = qd * 32 + lane;
+    const int rowl = warp * 32 + lane;
     const int row = q0 + rowl;
     const uint32_t sw = static_cast<uint32_t>(rowl & 7);
-    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
     const uint8_t* kpm_row = p.kpm ? p.kpm + static_cast<int64_t>(b) * p.Tk : nullptr;
     uint8_t* p_row0 = smem + AttnSmem::offP + rowl * 128;  // + (j & 1) * kP
-    // row-maximum exchange slots: the first 4 bytes of the bias chunks this thread has already consumed (the bias buffers
-    // are idle when there is no bias); the partner reads them after the pair barrier, before the buffer is handed back
-    const uint32_t my_slot = ((static_cast<uint32_t>(4 * half) ^ sw) << 4);
-    const uint32_t peer_slot = ((static_cast<uint32_t>(4 * (half ^ 1)) ^ sw) << 4);
-    float m_used = 0.f;  // log2-domain reference max the probabilities are expressed against (identical in both halves)
-    float l_run = 0.f;   // this half's share of the row sum
+    float m_used = 0.f;  // log2-domain reference max the probabilities are expressed against
+    float l_run = 0.f;
+    const int trole = (lane == 0 && (warp == 0 || warp == 3)) ? (warp == 0 ? 2 : 3) : -1;
 
 #pragma unroll 1
     for (int j = 0; j < n_kt; ++j) {
-      const int k0 = j * kKTile + half * 32;
-      uint8_t* bias_buf = smem + AttnSmem::offBias + (j & 1) * AttnSmem::kBias + rowl * 128;
-      const int trole = (lane == 0 && (warp == 0 || warp == 7)) ? (warp == 0 ? 2 : 3) : -1;
+      const uint8_t* bias_buf = smem + AttnSmem::offBias + (j & 1) * AttnSmem::kBias + rowl * 128;
+      uint8_t* p_row = p_row0 + (j & 1) * AttnSmem::kP;
       if (trole >= 0) attn_trace(p, tslot, trole, j, 0);
-      mbar_wait(&bars->s_full[j & 1], (j >> 1) & 1);  // S(j) retired and bias(j) landed (P V(j-2) retired too)
+      mbar_wait(&bars->s_full[j & 1], (j >> 1) & 1);  // S(j) retired and bias(j) landed
       tc_fence_after();
       if (trole >= 0) attn_trace(p, tslot, trole, j, 1);
-      float s[32];
-      {
-        uint32_t r0[32];
-        tmem_ld_32x32(tmem_s + (j & 1) * 64 + half * 32 + lane_addr, r0);
+      // keys of this tile a row may attend to: [0, lim) (tail of the sequence, causal diagonal)
+      int lim = p.Tk - j * kKTile;
+      if (p.causal) lim = min(lim, row - j * kKTile + 1);
+      const bool need_mask = lim < kKTile || kpm_row != nullptr;  // (rows differ under the causal mask: per thread)
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_s + (j & 1) * 64 + lane_addr, acc);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float s[32];
         if (p.bias) {  // the swizzled smem reads of the fp16 bias tile overlap the TMEM load latency
           uint4 bb[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            bb[c] = *reinterpret_cast<const uint4*>(bias_buf + ((static_cast<uint32_t>(4 * half + c) ^ sw) << 4));
+            bb[c] = *reinterpret_cast<const uint4*>(bias_buf + ((static_cast<uint32_t>(4 * hf + c) ^ sw) << 4));
           tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 4; ++c) {  // chunk c = columns 8c .. 8c+7 of this half
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
             for (int q = 0; q < 4; ++q) {
               const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
               const int col = 8 * c + 2 * q;
-              const float2 sv = add2(make_float2(__uint_as_float(r0[col]), __uint_as_float(r0[col + 1])), f);
+              const float2 sv = add2(make_float2(__uint_as_float(acc[col]), __uint_as_float(acc[col + 1])), f);
               s[col] = sv.x;
               s[col + 1] = sv.y;
             }
@@ -277,87 +279,103 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         } else {
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r0[i]);
+          for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(acc[i]);
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_empty[j & 1]);
-      const bool need_mask = (j * kKTile + kKTile > p.Tk) || (p.causal && (j * kKTile + kKTile - 1 > q0)) || (kpm_row != nullptr);
-      if (need_mask) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = k0 + i;
-          bool dead = col >= p.Tk || (p.causal && col > row);
-          if (!dead && kpm_row) dead = kpm_row[col] != 0;
-          if (dead) s[i] = -INFINITY;
-        }
-      }
-      // 4 independent partial maxima (a single 32-deep fmax chain would serialise on FP latency)
-      float mxp[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) mxp[i] = s[i];
-#pragma unroll
-      for (int i = 4; i < 32; ++i) mxp[i & 3] = fmaxf(mxp[i & 3], s[i]);
-      float mx = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3]));
-      // the other half of the row: exchange through shared memory, 64-thread named barrier of the warp pair
-      *reinterpret_cast<float*>(bias_buf + my_slot) = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-      mx = fmaxf(mx, *reinterpret_cast<const float*>(bias_buf + peer_slot));
-      if (trole >= 0) attn_trace(p, tslot, trole, j, 2);
-      if (p.bias) {  // the bias buffer (and the exchange slot in it) goes back to the TMA producer
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->b_empty[j & 1]);
-      }
-      const float m_new = mx * kLog2e;
-      if (j == 0) {
-        m_used = (m_new == -INFINITY) ? 0.f : m_new;
-      } else {
-        // lazy rescale: only when some row of the warp outgrew its reference max by more than 2^8 (both halves of a
-        // row see the same m_new and m_used, so the partner warp takes the same branch for its 32 output columns)
-        const bool grow = m_new > m_used + kRescaleThreshold;
-        if (__any_sync(0xffffffffu, grow)) {
-          mbar_wait(&bars->o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);  // every P V issued so far has retired
-          tc_fence_after();
-          const float f = grow ? fast_exp2(m_used - m_new) : 1.0f;
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_o + lane_addr + half * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-          tmem_st_32x32(tmem_o + lane_addr + half * 32, r);
-          tmem_st_wait();
+        if (hf == 0) {
+          tmem_ld_32x32(tmem_s + (j & 1) * 64 + 32 + lane_addr, acc);  // second half: in flight under the math below
+        } else {  // both halves of S(j) and of bias(j) are in registers: hand the buffers back
           tc_fence_before();
-          if (grow) {
-            l_run *= f;
-            m_used = m_new;
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&bars->s_empty[j & 1]);
+            if (p.bias) mbar_arrive(&bars->b_empty[j & 1]);
           }
         }
-      }
-      float2 ps[4] = {splat2(0.f), splat2(0.f), splat2(0.f), splat2(0.f)};
-      const float2 l2e = splat2(kLog2e), nm = splat2(-m_used);
+        if (need_mask) {
+          const int l2 = lim - hf * 32;
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float2 e = fma2(make_float2(s[i], s[i + 1]), l2e, nm);
-        s[i] = fast_exp2(e.x);
-        s[i + 1] = fast_exp2(e.y);
-        ps[(i >> 1) & 3] = add2(ps[(i >> 1) & 3], make_float2(s[i], s[i + 1]));
-      }
-      const float2 pt = add2(add2(ps[0], ps[1]), add2(ps[2], ps[3]));
-      l_run += pt.x + pt.y;
-      // P (bf16) -> buffer j&1 once its previous reader P V(j-2) has retired (issued two tiles ago)
-      if (trole >= 0) attn_trace(p, tslot, trole, j, 3);
-      if (j >= 2) mbar_wait(&bars->o_done[j & 1], ((j - 2) >> 1) & 1);
-      uint8_t* p_row = p_row0 + (j & 1) * AttnSmem::kP;
+          for (int i = 0; i < 32; ++i)
+            if (i >= l2) s[i] = -INFINITY;
+          if (kpm_row) {
+            const int c0 = j * kKTile + hf * 32;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 u;
-        u.x = pack_bf16x2(s[8 * c + 0], s[8 * c + 1]);
-        u.y = pack_bf16x2(s[8 * c + 2], s[8 * c + 3]);
-        u.z = pack_bf16x2(s[8 * c + 4], s[8 * c + 5]);
-        u.w = pack_bf16x2(s[8 * c + 6], s[8 * c + 7]);
-        *reinterpret_cast<uint4*>(p_row + ((static_cast<uint32_t>(4 * half + c) ^ sw) << 4)) = u;
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < p.Tk && kpm_row[c0 + i] != 0) s[i] = -INFINITY;
+          }
+        }
+        // 4 independent partial maxima (a single 32-deep fmax chain would serialise on FP latency)
+        float mxp[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mxp[i] = s[i];
+#pragma unroll
+        for (int i = 4; i < 32; ++i) mxp[i & 3] = fmaxf(mxp[i & 3], s[i]);
+        const float m_new = fmaxf(fmaxf(mxp[0], mxp[1]), fmaxf(mxp[2], mxp[3])) * kLog2e;
+        if (j == 0 && hf == 0) {
+          m_used = (m_new == -INFINITY) ? 0.f : m_new;
+        } else {
+          // lazy rescale: only when some row of the warp outgrew its reference max by more than 2^8
+          const bool grow = m_new > m_used + kRescaleThreshold;
+          if (__any_sync(0xffffffffu, grow)) {
+            const float f = grow ? fast_exp2(m_used - m_new) : 1.0f;
+            if (j >= 1) {
+              mbar_wait(&bars->o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);  // every P V issued so far has retired
+              tc_fence_after();
+#pragma unroll
+              for (int hb = 0; hb < 2; ++hb) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_o + lane_addr + hb * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+                tmem_st_32x32(tmem_o + lane_addr + hb * 32, r);
+              }
+              tmem_st_wait();
+              tc_fence_before();
+            }
+            if (hf == 1) {  // the first half of P(j) is already in shared memory against the old reference
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint4* pp = reinterpret_cast<uint4*>(p_row + ((static_cast<uint32_t>(c) ^ sw) << 4));
+                uint4 u = *pp;
+                uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 v = unpack_bf16x2(w[q]);
+                  w[q] = pack_bf16x2(v.x * f, v.y * f);
+                }
+                *pp = u;
+              }
+            }
+            if (grow) {
+              l_run *= f;
+              m_used = m_new;
+            }
+          }
+        }
+        if (trole >= 0 && hf == 0) attn_trace(p, tslot, trole, j, 2);
+        float2 ps[4] = {splat2(0.f), splat2(0.f), splat2(0.f), splat2(0.f)};
+        const float2 l2e = splat2(kLog2e), nm = splat2(-m_used);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 e = fma2(make_float2(s[i], s[i + 1]), l2e, nm);
+          s[i] = fast_exp2(e.x);
+          s[i + 1] = fast_exp2(e.y);
+          ps[(i >> 1) & 3] = add2(ps[(i >> 1) & 3], make_float2(s[i], s[i + 1]));
+        }
+        const float2 pt = add2(add2(ps[0], ps[1]), add2(ps[2], ps[3]));
+        l_run += pt.x + pt.y;
+        if (trole >= 0 && hf == 0) attn_trace(p, tslot, trole, j, 3);
+        // P (bf16) -> buffer j&1 once its previous reader P V(j-2) has retired (issued two tiles ago)
+        if (hf == 0 && j >= 2) mbar_wait(&bars->o_done[j & 1], ((j - 2) >> 1) & 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 u;
+          u.x = pack_bf16x2(s[8 * c + 0], s[8 * c + 1]);
+          u.y = pack_bf16x2(s[8 * c + 2], s[8 * c + 3]);
+          u.z = pack_bf16x2(s[8 * c + 4], s[8 * c + 5]);
+          u.w = pack_bf16x2(s[8 * c + 6], s[8 * c + 7]);
+          *reinterpret_cast<uint4*>(p_row + ((static_cast<uint32_t>(4 * hf + c) ^ sw) << 4)) = u;
+        }
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -369,30 +387,27 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       tc_fence_after();
     }
     {
-      // total row sum = both halves (every bias tile has been consumed: buffer 0 is free for the exchange)
-      uint8_t* xbuf = smem + AttnSmem::offBias + rowl * 128;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");  // the partner is past its last read of the max slot
-      *reinterpret_cast<float*>(xbuf + my_slot) = l_run;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-      const float l_tot = l_run + *reinterpret_cast<const float*>(xbuf + peer_slot);
       // the TMEM loads are warp-collective: every lane executes them, rows >= Tq only skip the stores
-      const float inv = (1.0f / l_tot) * (p.head_scale ? p.head_scale[h] : 1.0f);
-      if (p.lse && half == 0 && row < p.Tq)  // log2-domain log-sum-exp of the (biased, masked) score row, for the backward
-        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Tq + row] = m_used + __log2f(l_tot);
+      const float inv = (1.0f / l_run) * (p.head_scale ? p.head_scale[h] : 1.0f);
+      if (p.lse && row < p.Tq)  // log2-domain log-sum-exp of the (biased, masked) score row, for the backward
+        p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Tq + row] = m_used + __log2f(l_run);
       __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(b) * p.o_batch_stride +
-                           static_cast<int64_t>(row) * p.o_row_stride + h * kHeadDim + half * 32;
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_o + lane_addr + half * 32, r);
-      tmem_ld_wait();
-      if (row < p.Tq) {
+                           static_cast<int64_t>(row) * p.o_row_stride + h * kHeadDim;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]) * inv, __uint_as_float(r[8 * c + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + 8 * c) = u;
+      for (int hb = 0; hb < 2; ++hb) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_o + lane_addr + hb * 32, r);
+        tmem_ld_wait();
+        if (row < p.Tq) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]) * inv, __uint_as_float(r[8 * c + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + hb * 32 + 8 * c) = u;
+          }
         }
       }
     }

@@ -1,3 +1,2 @@
 set -x
-timeout 300 python tools/trace_attn.py > gpurun_out/trace_attn.log 2>&1
-tail -5 gpurun_out/trace_attn.log
+SGF_ATTN_DBG=15 timeout 300 python tools/trace_attn.py > gpurun_out/trace_attn_dbg15.log 2>&1

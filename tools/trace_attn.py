@@ -41,7 +41,7 @@ for use_bias in (True, False):
         t0 = int(t[cta][t[cta] > 0].min()) if (t[cta] > 0).any() else 0
         print(f"-- cta slot {cta}")
         names = ["S-issuer  (loop top, k_full ok, s_empty ok, issued)", "PV-issuer (loop top, v_full ok, p_full ok, issued)",
-                 "softmax w0 (top, s_full ok, exchanged, exp done)", "softmax w7 (top, s_full ok, exchanged, exp done)"]
+                 "softmax w0 (top, s_full ok, max0 done, exp0 done)", "softmax w3 (top, s_full ok, max0 done, exp0 done)"]
         for role in range(4):
             print("  " + names[role])
             for j in range(15):
