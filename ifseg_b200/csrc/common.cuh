@@ -70,6 +70,14 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 // ----------------------------------------------------------------------------------------
 SGF_DEVICE uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// 16-byte shared-memory load in the shared state space (a plain C++ load through a pointer derived from the generic
+// dynamic-smem base compiles to a generic LD.E)
+SGF_DEVICE uint4 lds128(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+
 SGF_DEVICE uint32_t elect_one_sync() {
   uint32_t pred = 0;
   asm volatile(

@@ -2,6 +2,9 @@
 //
 //   C[M,N] = epilogue( A[M,K] * B[N,K]^T )     bf16 operands, fp32 accumulation in TMEM.
 //
+// This file: the one-tile-per-CTA kernel -- the general path (any N, batched operands, runtime epilogue) and the
+// fallback of the persistent CTA-pair kernel in gemm_ts.cu, which takes every hot GEMM / convolution of the segofa path --
+// and the mixed-major kernel of the dense adjoints.
 // One CTA per 128 x BN output tile, 192/320 threads, warp-specialised:
 //   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (tcgen05.commit frees stages)
@@ -486,572 +489,6 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), (BN <= 128 ? 2 : 1)) gemm_
 }
 
 // ----------------------------------------------------------------------------------------
-// CTA pair: a cluster of two CTAs (two SMs of a TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2.
-// Each CTA stages its own 128 rows of A and only HALF of the B tile (BN/2 rows), so the shared-memory fill
-// traffic per MMA cycle -- the limiter of the 1-CTA kernels -- is halved; the leader CTA's single MMA thread
-// drives both tensor cores.
-//   full[s]   (leader only): 1 arrival (leader's expect_tx of both CTAs' bytes) + TMA bytes of both CTAs
-//   empty[s]  (per CTA)    : multicast tcgen05.commit from the leader
-// ----------------------------------------------------------------------------------------
-template <int BN>
-struct Gemm2Smem {
-  static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = (BN / 2) * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-};
-// ----------------------------------------------------------------------------------------
-// Persistent CTA-pair kernel: one cluster of two CTAs per SM pair loops over 256 x 256 output tiles.
-// The 512 TMEM columns hold TWO accumulators, so the epilogue of tile i (8 warps per CTA, thread =
-// row, straight from TMEM to global memory) runs while the tensor cores already work on tile i+1;
-// barrier set-up, TMEM allocation and descriptor fetches are paid once per SM instead of once per tile.
-//   full[s]/empty[s]        : smem ring, as in the non-persistent pair kernel, running across tiles
-//   tmem_full[2]  (per CTA) : multicast tcgen05.commit when an accumulator is complete
-//   tmem_empty[2] (leader)  : 2 x 8 epilogue-warp arrivals (both CTAs) once an accumulator is drained
-// ----------------------------------------------------------------------------------------
-static constexpr int kP2BN = 256;
-static constexpr int kP2Stages = 6;
-static constexpr int kP2EpiWarps = 16;  // 4 per TMEM lane quarter, 64 columns each: the epilogue (GELU, bias, packing) is
-                                         // issue-bound and must keep up with a 12-k-block main loop
-static constexpr int kP2Threads = 64 + 32 * kP2EpiWarps;
-
-template <int kEpi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kP2Threads, 1)
-    gemm2p_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                          const GemmShape shp, const GemmEpilogue ep, const int num_m_pairs, const int num_tiles) {
-  using S = Gemm2Smem<kP2BN>;
-  constexpr int BN = kP2BN;
-  constexpr int kStages = kP2Stages;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
-  pdl_trigger();
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1;
-  const int num_clusters = gridDim.x >> 1;
-  const int z = blockIdx.z;
-  const int num_kb = (shp.K + BK - 1) / BK;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 2 * kP2EpiWarps);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc_2cta<512>(tmem_slot);
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t g = 0;  // running k-block counter across tiles
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int m0 = (t % num_m_pairs) * (2 * BM) + static_cast<int>(rank) * BM;
-        const int n0 = (t / num_m_pairs) * BN;
-#pragma unroll 1
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
-          const int s = g % kStages;
-          mbar_wait(&empty_bar[s], ((g / kStages) & 1) ^ 1);
-          uint8_t* sa = smem + s * S::kStageBytes;
-          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * S::kStageBytes);
-          tma_load_3d_2cta(sa, &tmA, &full_bar[s], kb * BK, m0, z);
-          tma_load_3d_2cta(sa + S::kABytes, &tmB, &full_bar[s], kb * BK, n0 + static_cast<int>(rank) * (BN / 2), z);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
-      uint32_t g = 0;
-      int it = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
-        const int ab = it & 1;
-        mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);  // both CTAs drained this accumulator
-        tc_fence_after();
-#pragma unroll 1
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
-          const int s = g % kStages;
-          mbar_wait(&full_bar[s], (g / kStages) & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
-          const uint64_t da = make_smem_desc_sw128(sa);
-          const uint64_t db = make_smem_desc_sw128(sa + S::kABytes);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_f16_2cta(tmem_base + ab * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2cta(&empty_bar[s], 0b11);
-        }
-        umma_commit_2cta(&tmem_full[ab], 0b11);
-      }
-    }
-  } else {
-    // ---------------- epilogue warps: thread = row, straight from TMEM to global memory ----------------
-    const int ew = warp - 2;
-    const int quarter = warp & 3;
-    constexpr int kParts = kP2EpiWarps / 4;
-    constexpr int kColsPerWarp = BN / kParts;
-    const int half = ew >> 2;  // columns [half*kColsPerWarp, +kColsPerWarp) of the tile
-    const bool out_f32 = (kEpi & kEpiOutF32) != 0;
-    const int csz = out_f32 ? 4 : 2;
-    int it = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
-      const int ab = it & 1;
-      const int m0 = (t % num_m_pairs) * (2 * BM) + static_cast<int>(rank) * BM;
-      const int n0 = (t / num_m_pairs) * BN;
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < shp.M;
-      const int rrow = row_ok ? row : shp.M - 1;
-      float rn_mean = 0.f, rn_rstd = 1.f;
-      if constexpr ((kEpi & kEpiRowNorm) != 0) {
-        const float4* sp = reinterpret_cast<const float4*>(ep.rownorm_stats) +
-                           (static_cast<int64_t>(z) * shp.M + rrow) * (ep.rownorm_parts / 2);
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll 4
-        for (int q = 0; q < ep.rownorm_parts / 2; ++q) {
-          const float4 u = __ldg(sp + q);
-          s0 += u.x; s1 += u.y; s0 += u.z; s1 += u.w;
-        }
-        rn_mean = s0 * ep.rownorm_inv_dim;
-        rn_rstd = rsqrtf(fmaxf(s1 * ep.rownorm_inv_dim - rn_mean * rn_mean, 0.f) + 1e-5f);
-      }
-      mbar_wait(&tmem_full[ab], (it >> 1) & 1);
-      tc_fence_after();
-      uint8_t* crow = reinterpret_cast<uint8_t*>(ep.c) + (static_cast<int64_t>(z) * ep.c_batch_stride + static_cast<int64_t>(rrow) * ep.ldc) * csz;
-      float st_sum = 0.f, st_sq = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < kColsPerWarp / 32; ++ch) {
-        const int c0 = n0 + half * kColsPerWarp + ch * 32;
-        uint32_t acc[32];
-        tmem_ld_32x32(tmem_base + ab * BN + (static_cast<uint32_t>(quarter * 32) << 16) + half * kColsPerWarp + ch * 32, acc);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-        if constexpr ((kEpi & kEpiRowNorm) != 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 u4 = __ldg(reinterpret_cast<const float4*>(ep.rownorm_u + c0 + j));
-            v[j] = rn_rstd * (v[j] - rn_mean * u4.x); v[j + 1] = rn_rstd * (v[j + 1] - rn_mean * u4.y);
-            v[j + 2] = rn_rstd * (v[j + 2] - rn_mean * u4.z); v[j + 3] = rn_rstd * (v[j + 3] - rn_mean * u4.w);
-          }
-        }
-        if constexpr ((kEpi & kEpiScale) != 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + c0 + j));
-            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-          }
-        }
-        if constexpr ((kEpi & kEpiBias) != 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.col_bias + c0 + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
-        }
-        if constexpr ((kEpi & kEpiAlpha) != 0) {
-          if (ep.alpha_cols >= c0 + 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
-          } else if (ep.alpha_cols > c0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < ep.alpha_cols) v[j] *= ep.alpha;
-          }
-        }
-        if constexpr ((kEpi & kEpiGelu) != 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float2 y = gelu_erf2(make_float2(v[j], v[j + 1]));
-            v[j] = y.x;
-            v[j + 1] = y.y;
-          }
-        }
-        if constexpr ((kEpi & kEpiResF32) != 0) {
-          const float4* rp = reinterpret_cast<const float4*>(
-              reinterpret_cast<const float*>(ep.residual) + static_cast<int64_t>(z) * ep.r_batch_stride +
-              static_cast<int64_t>(rrow) * ep.ldr + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 r4 = rp[j];
-            v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
-          }
-        }
-        if constexpr ((kEpi & kEpiResBf16) != 0) {
-          const uint4* rp = reinterpret_cast<const uint4*>(
-              reinterpret_cast<const __nv_bfloat16*>(ep.residual) + static_cast<int64_t>(z) * ep.r_batch_stride +
-              static_cast<int64_t>(rrow) * ep.ldr + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 r4 = rp[j];
-            const float2 a = unpack_bf16x2(r4.x), b2 = unpack_bf16x2(r4.y), c2 = unpack_bf16x2(r4.z), d = unpack_bf16x2(r4.w);
-            v[8 * j] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += b2.x; v[8 * j + 3] += b2.y;
-            v[8 * j + 4] += c2.x; v[8 * j + 5] += c2.y; v[8 * j + 6] += d.x; v[8 * j + 7] += d.y;
-          }
-        }
-        if constexpr ((kEpi & kEpiRelu) != 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (row_ok) {
-          if (out_f32) {
-            float4* cp = reinterpret_cast<float4*>(crow + static_cast<int64_t>(c0) * 4);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* cp = reinterpret_cast<uint4*>(crow + static_cast<int64_t>(c0) * 2);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              cp[j] = o;
-              if constexpr ((kEpi & kEpiRowStats) != 0) {
-                const float2 a = unpack_bf16x2(o.x), b2 = unpack_bf16x2(o.y), c2 = unpack_bf16x2(o.z), d = unpack_bf16x2(o.w);
-                st_sum += ((a.x + a.y) + (b2.x + b2.y)) + ((c2.x + c2.y) + (d.x + d.y));
-                st_sq += ((a.x * a.x + a.y * a.y) + (b2.x * b2.x + b2.y * b2.y)) +
-                         ((c2.x * c2.x + c2.y * c2.y) + (d.x * d.x + d.y * d.y));
-              }
-            }
-          }
-        }
-        if constexpr ((kEpi & kEpiRowStats) != 0) {
-          if (ch & 1) {  // one deterministic (sum, sumsq) slot per 64-column block of the row
-            if (row_ok) {
-              const int nparts = (shp.N + 63) / 64;
-              reinterpret_cast<float2*>(ep.rowstats_out)[(static_cast<int64_t>(z) * shp.M + row) * nparts + (c0 - 32) / 64] =
-                  make_float2(st_sum, st_sq);
-            }
-            st_sum = 0.f;
-            st_sq = 0.f;
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[ab]);
-    }
-  }
-
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc_2cta<512>(tmem_base);
-  }
-}
-
-// ----------------------------------------------------------------------------------------
-// Persistent single-CTA kernel for the many GEMMs / convolutions whose grids are only 1-3 waves of short-lived
-// CTAs (N <= 1024: out_proj, fc2, cross-q, every stem convolution).  One CTA per SM loops over 128 x BN output tiles
-// (n fastest: the CTAs running side by side share their A tiles in L2):
-//   * barrier set-up, TMEM allocation and descriptor fetches are paid once per SM, not once per tile;
-//   * the TMA ring runs ACROSS tiles, so the first k-blocks of tile i+1 are already in flight while tile i finishes --
-//     a K = 64 ... 256 stem GEMM no longer sees one full TMA latency per tile;
-//   * the 2 x BN TMEM columns hold two accumulators: the epilogue of tile i (thread = row, straight from TMEM to
-//     global memory) overlaps the tensor-core work of tile i+1.
-// Conv mode = the im2col-free 3x3/s1 convolution of the 1-CTA kernel (A tile of tap (ky,kx) = shifted 4-D TMA box).
-//   full[s]/empty[s] : smem ring; tmem_full[2]: tcgen05.commit per finished accumulator; tmem_empty[2]: one arrival
-//   per epilogue warp once the accumulator has been drained.
-// ----------------------------------------------------------------------------------------
-template <int BN>
-struct GemmPCfg {
-  static constexpr int kStages = BN >= 128 ? 6 : 8;  // 32 KB / 24 KB per stage -> 192 KB
-  static constexpr int kEpiWarps = BN >= 128 ? 8 : 4;
-  static constexpr int kThreads = 64 + 32 * kEpiWarps;
-  static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmem = kStages * GemmSmem<BN>::kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
-};
-
-template <int BN, bool kConv, int kEpi>
-__global__ void __launch_bounds__(GemmPCfg<BN>::kThreads, 1)
-    gemmp_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape shp,
-                         const GemmEpilogue ep, const int num_tiles, const int tiles_n) {
-  using S = GemmSmem<BN>;
-  using Cfg = GemmPCfg<BN>;
-  constexpr int kStages = Cfg::kStages;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full = empty_bar + kStages;  // [2]
-  uint64_t* tmem_empty = tmem_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
-  pdl_trigger();
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int num_kb = (shp.K + BK - 1) / BK;
-  const int first = blockIdx.x, step = gridDim.x;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], Cfg::kEpiWarps);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
-
-  // tile -> (m-tile, n-tile) and, in conv mode, (image, h0, w0)
-  auto decode = [&](int t, int& m0, int& n0, int& img, int& h0, int& w0) {
-    const int mt = t / tiles_n;
-    n0 = (t - mt * tiles_n) * BN;
-    m0 = mt * BM;
-    img = 0; h0 = 0; w0 = 0;
-    if constexpr (kConv) {
-      const int per_img = shp.tiles_w * shp.tiles_h;
-      img = mt / per_img;
-      const int r = mt - img * per_img;
-      h0 = (r / shp.tiles_w) * shp.bh;
-      w0 = (r % shp.tiles_w) * shp.bw;
-    }
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t g = 0;  // running k-block counter across tiles
-      for (int t = first; t < num_tiles; t += step) {
-        int m0, n0, img, h0, w0;
-        decode(t, m0, n0, img, h0, w0);
-#pragma unroll 1
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
-          const int s = g % kStages;
-          mbar_wait(&empty_bar[s], ((g / kStages) & 1) ^ 1);
-          uint8_t* sa = smem + s * S::kStageBytes;
-          mbar_expect_tx(&full_bar[s], S::kStageBytes);
-          if constexpr (kConv) {
-            const int tap = kb / shp.cin_blocks;
-            const int kc = kb - tap * shp.cin_blocks;
-            tma_load_4d(sa, &tmA, &full_bar[s], kc * BK, w0 + tap % 3 - 1, h0 + tap / 3 - 1, img);
-          } else {
-            tma_load_3d(sa, &tmA, &full_bar[s], kb * BK, m0, 0);
-          }
-          tma_load_3d(sa + S::kABytes, &tmB, &full_bar[s], kb * BK, n0, 0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      uint32_t g = 0;
-      int it = 0;
-      for (int t = first; t < num_tiles; t += step, ++it) {
-        const int ab = it & 1;
-        mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);  // the epilogue drained this accumulator
-        tc_fence_after();
-#pragma unroll 1
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
-          const int s = g % kStages;
-          mbar_wait(&full_bar[s], (g / kStages) & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
-          const uint64_t da = make_smem_desc_sw128(sa);
-          const uint64_t db = make_smem_desc_sw128(sa + S::kABytes);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(tmem_base + ab * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
-        }
-        umma_commit(&tmem_full[ab]);
-      }
-    }
-  } else {
-    // ---------------- epilogue warps: thread = row, straight from TMEM to global memory ----------------
-    const int ew = warp - 2;
-    const int quarter = warp & 3;  // the TMEM lane quarter this warp may access
-    constexpr int kParts = Cfg::kEpiWarps / 4;
-    constexpr int kColsPerWarp = BN / kParts;
-    const int part = ew >> 2;
-    constexpr bool out_f32 = (kEpi & kEpiOutF32) != 0;
-    constexpr int csz = out_f32 ? 4 : 2;
-    int it = 0;
-    for (int t = first; t < num_tiles; t += step, ++it) {
-      const int ab = it & 1;
-      int m0, n0, img, h0, w0;
-      decode(t, m0, n0, img, h0, w0);
-      const int r = quarter * 32 + lane;
-      int64_t row;
-      bool row_ok;
-      if constexpr (kConv) {
-        const int hh = h0 + r / shp.bw, ww = w0 + r % shp.bw;
-        row_ok = hh < shp.H && ww < shp.W;
-        row = (static_cast<int64_t>(img) * shp.H + hh) * shp.W + ww;
-      } else {
-        row = m0 + r;
-        row_ok = row < shp.M;
-      }
-      const int64_t rrow = row_ok ? row : 0;
-      float rn_mean = 0.f, rn_rstd = 1.f;
-      if constexpr ((kEpi & kEpiRowNorm) != 0) {
-        const float4* sp = reinterpret_cast<const float4*>(ep.rownorm_stats) + rrow * (ep.rownorm_parts / 2);
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll 4
-        for (int q = 0; q < ep.rownorm_parts / 2; ++q) {
-          const float4 u = __ldg(sp + q);
-          s0 += u.x; s1 += u.y; s0 += u.z; s1 += u.w;
-        }
-        rn_mean = s0 * ep.rownorm_inv_dim;
-        rn_rstd = rsqrtf(fmaxf(s1 * ep.rownorm_inv_dim - rn_mean * rn_mean, 0.f) + 1e-5f);
-      }
-      mbar_wait(&tmem_full[ab], (it >> 1) & 1);
-      tc_fence_after();
-      uint8_t* crow = reinterpret_cast<uint8_t*>(ep.c) + rrow * ep.ldc * csz;
-      float st_sum = 0.f, st_sq = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < kColsPerWarp / 32; ++ch) {
-        const int c0 = n0 + part * kColsPerWarp + ch * 32;
-        uint32_t acc[32];
-        tmem_ld_32x32(tmem_base + ab * BN + (static_cast<uint32_t>(quarter * 32) << 16) + part * kColsPerWarp + ch * 32, acc);
-        // the residual row segment is fetched while the TMEM load is in flight
-        uint4 rq[8];
-        if constexpr ((kEpi & kEpiResF32) != 0) {
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(ep.residual) + rrow * ep.ldr + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rq[j] = rp[j];
-        }
-        if constexpr ((kEpi & kEpiResBf16) != 0) {
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + rrow * ep.ldr + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rq[j] = rp[j];
-        }
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-        if constexpr ((kEpi & kEpiRowNorm) != 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 u4 = __ldg(reinterpret_cast<const float4*>(ep.rownorm_u + c0 + j));
-            v[j] = rn_rstd * (v[j] - rn_mean * u4.x); v[j + 1] = rn_rstd * (v[j + 1] - rn_mean * u4.y);
-            v[j + 2] = rn_rstd * (v[j + 2] - rn_mean * u4.z); v[j + 3] = rn_rstd * (v[j + 3] - rn_mean * u4.w);
-          }
-        }
-        if constexpr ((kEpi & kEpiScale) != 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(ep.col_scale + c0 + j));
-            v[j] *= s4.x; v[j + 1] *= s4.y; v[j + 2] *= s4.z; v[j + 3] *= s4.w;
-          }
-        }
-        if constexpr ((kEpi & kEpiBias) != 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.col_bias + c0 + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
-        }
-        if constexpr ((kEpi & kEpiAlpha) != 0) {
-          if (ep.alpha_cols >= c0 + 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
-          } else if (ep.alpha_cols > c0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < ep.alpha_cols) v[j] *= ep.alpha;
-          }
-        }
-        if constexpr ((kEpi & kEpiGelu) != 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float2 y = gelu_erf2(make_float2(v[j], v[j + 1]));
-            v[j] = y.x;
-            v[j + 1] = y.y;
-          }
-        }
-        if constexpr ((kEpi & kEpiResF32) != 0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[4 * j] += __uint_as_float(rq[j].x); v[4 * j + 1] += __uint_as_float(rq[j].y);
-            v[4 * j + 2] += __uint_as_float(rq[j].z); v[4 * j + 3] += __uint_as_float(rq[j].w);
-          }
-        }
-        if constexpr ((kEpi & kEpiResBf16) != 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 a = unpack_bf16x2(rq[j].x), b2 = unpack_bf16x2(rq[j].y), c2 = unpack_bf16x2(rq[j].z), d = unpack_bf16x2(rq[j].w);
-            v[8 * j] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += b2.x; v[8 * j + 3] += b2.y;
-            v[8 * j + 4] += c2.x; v[8 * j + 5] += c2.y; v[8 * j + 6] += d.x; v[8 * j + 7] += d.y;
-          }
-        }
-        if constexpr ((kEpi & kEpiRelu) != 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (row_ok) {
-          if constexpr (out_f32) {
-            float4* cp = reinterpret_cast<float4*>(crow + static_cast<int64_t>(c0) * 4);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* cp = reinterpret_cast<uint4*>(crow + static_cast<int64_t>(c0) * 2);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              cp[j] = o;
-              if constexpr ((kEpi & kEpiRowStats) != 0) {
-                const float2 a = unpack_bf16x2(o.x), b2 = unpack_bf16x2(o.y), c2 = unpack_bf16x2(o.z), d = unpack_bf16x2(o.w);
-                st_sum += ((a.x + a.y) + (b2.x + b2.y)) + ((c2.x + c2.y) + (d.x + d.y));
-                st_sq += ((a.x * a.x + a.y * a.y) + (b2.x * b2.x + b2.y * b2.y)) +
-                         ((c2.x * c2.x + c2.y * c2.y) + (d.x * d.x + d.y * d.y));
-              }
-            }
-          }
-        }
-        if constexpr ((kEpi & kEpiRowStats) != 0) {
-          if (ch & 1) {  // one deterministic (sum, sumsq) slot per 64-column block of the row
-            if (row_ok) {
-              const int nparts = (shp.N + 63) / 64;
-              reinterpret_cast<float2*>(ep.rowstats_out)[row * nparts + (c0 - 32) / 64] = make_float2(st_sum, st_sq);
-            }
-            st_sum = 0.f;
-            st_sq = 0.f;
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[ab]);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-  }
-}
-
-// ----------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------
 template <int BN, int kStages>
@@ -1107,107 +544,6 @@ static int dispatch_epilogue(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   return launch_gemm<BN, kStages, kConv, kEpiRuntime>(tmA, tmB, shp, ep, grid, st);
 }
 
-template <int kEpi>
-static int launch_gemm2p(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
-                         int batch, cudaStream_t st) {
-  auto kern = gemm2p_tcgen05_kernel<kEpi>;
-  constexpr int smem = kP2Stages * Gemm2Smem<kP2BN>::kStageBytes + (2 * kP2Stages + 4) * 8 + 16 + 1024;
-  static bool configured = false;
-  static int num_sms = 0;
-  if (!configured) {
-    SGF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int dev = 0;
-    SGF_CHECK_CUDA(cudaGetDevice(&dev));
-    SGF_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
-  const int num_m_pairs = (shp.M + 2 * BM - 1) / (2 * BM);
-  const int num_tiles = num_m_pairs * (shp.N / kP2BN);
-  int clusters = num_sms / 2;
-  if (batch > 1) clusters = clusters / batch > 0 ? clusters / batch : 1;
-  if (clusters > num_tiles) clusters = num_tiles;
-  dim3 grid(2 * clusters, 1, batch);
-  SGF_CHECK_CUDA(launch_pdl(kern, grid, dim3(kP2Threads), smem, st, tmA, tmB, shp, ep, num_m_pairs, num_tiles));
-  count_launch();
-  return SGF_OK;
-}
-
-#define SGF_EPI2P_CASE(MASK)                                                                           \
-  case (MASK):                                                                                          \
-    return launch_gemm2p<(MASK)>(tmA, tmB, shp, ep, batch, st);
-
-static int dispatch_epilogue2p(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
-                               int batch, cudaStream_t st) {
-  switch (epilogue_mask(ep)) {
-    SGF_EPI2P_CASE(kEpiBias | kEpiAlpha)
-    SGF_EPI2P_CASE(kEpiBias | kEpiOutF32)
-    SGF_EPI2P_CASE(kEpiBias)
-    SGF_EPI2P_CASE(kEpiBias | kEpiGelu | kEpiRowStats)
-    SGF_EPI2P_CASE(kEpiBias | kEpiGelu)
-    SGF_EPI2P_CASE(kEpiBias | kEpiRowNorm | kEpiResF32 | kEpiOutF32)
-    SGF_EPI2P_CASE(kEpiScale | kEpiBias | kEpiRelu)
-    SGF_EPI2P_CASE(kEpiScale | kEpiBias | kEpiRelu | kEpiResBf16)
-    SGF_EPI2P_CASE(kEpiScale | kEpiBias)
-    SGF_EPI2P_CASE(0)
-    SGF_EPI2P_CASE(kEpiOutF32)
-    default: return -1;
-  }
-}
-
-template <int BN, bool kConv, int kEpi>
-static int launch_gemmp(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
-                        int m_tiles, cudaStream_t st) {
-  auto kern = gemmp_tcgen05_kernel<BN, kConv, kEpi>;
-  using Cfg = GemmPCfg<BN>;
-  static bool configured = false;
-  static int num_sms = 0;
-  if (!configured) {
-    SGF_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    int dev = 0;
-    SGF_CHECK_CUDA(cudaGetDevice(&dev));
-    SGF_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
-  const int tiles_n = shp.N / BN;
-  const int num_tiles = m_tiles * tiles_n;
-  // equal share per CTA: with e.g. 354 tiles on 148 SMs every CTA would run 3 rounds anyway -- use only as many CTAs
-  // as keep the rounds full, so the tail is not 56 SMs idling while 92 run a third tile
-  const int rounds = (num_tiles + num_sms - 1) / num_sms;
-  const int ctas = (num_tiles + rounds - 1) / rounds;
-  SGF_CHECK_CUDA(launch_pdl(kern, dim3(ctas), dim3(Cfg::kThreads), Cfg::kSmem, st, tmA, tmB, shp, ep, num_tiles, tiles_n));
-  count_launch();
-  return SGF_OK;
-}
-
-#define SGF_EPIP_CASE(MASK)                                                                            \
-  case (MASK):                                                                                          \
-    return launch_gemmp<BN, kConv, (MASK)>(tmA, tmB, shp, ep, m_tiles, st);
-
-// returns -1 when no persistent specialisation exists for the epilogue (the caller uses the one-tile-per-CTA kernel)
-template <int BN, bool kConv>
-static int dispatch_epiloguep(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp, const GemmEpilogue& ep,
-                              int m_tiles, cudaStream_t st) {
-  switch (epilogue_mask(ep)) {
-    SGF_EPIP_CASE(kEpiScale | kEpiBias | kEpiRelu)                 // stem conv + BN + ReLU
-    SGF_EPIP_CASE(kEpiScale | kEpiBias | kEpiRelu | kEpiResBf16)   // bottleneck conv3 + BN + residual + ReLU
-    SGF_EPIP_CASE(kEpiScale | kEpiBias)                            // downsample conv + BN
-    default: break;
-  }
-  if constexpr (!kConv) {
-    switch (epilogue_mask(ep)) {
-      SGF_EPIP_CASE(kEpiBias | kEpiAlpha)                          // cross q
-      SGF_EPIP_CASE(kEpiBias | kEpiOutF32)                         // out_proj, image_proj
-      SGF_EPIP_CASE(kEpiBias)                                      // position projections
-      SGF_EPIP_CASE(kEpiBias | kEpiRowNorm | kEpiResF32 | kEpiOutF32)  // fc2 with folded ffn_layernorm
-      SGF_EPIP_CASE(kEpiBias | kEpiResF32 | kEpiOutF32)            // fc2
-      SGF_EPIP_CASE(0)                                             // dX = dY W (bf16)
-      SGF_EPIP_CASE(kEpiOutF32)                                    // d(encoder_out)
-      default: break;
-    }
-  }
-  return -1;
-}
-
 static int check_epilogue_alignment(const GemmEpilogue& ep, int N) {
   if (N % 8 == 0) {
     const int cs = ep.c_dtype == SGF_F32 ? 4 : 2;
@@ -1227,15 +563,14 @@ static int check_epilogue_alignment(const GemmEpilogue& ep, int N) {
 }
 
 // Kernel-family selection can be pinned from the environment for A/B measurements (tools/bench_gemm.py):
-//   SGF_GEMM_FAMILY = tile (one tile per CTA) | persist (persistent 1-CTA) | pair (persistent CTA pair, direct stores)
-//                     | ts (persistent CTA pair, TMA-store epilogue: gemm_ts.cu) ; unset = automatic
-enum { kFamAuto = 0, kFamTile = 1, kFamPersist = 2, kFamPair = 3, kFamTs = 4 };
+//   SGF_GEMM_FAMILY = tile (one 128 x BN tile per CTA, this file) | ts (persistent CTA pair, TMA-store epilogue: gemm_ts.cu)
+//   unset = ts wherever it applies.  (The r01/r02 persistent kernels with direct TMEM -> global stores were removed after
+//   the A/B in profiles/r02_gemm_family_ab.txt: their epilogue was the bottleneck.)
+enum { kFamAuto = 0, kFamTile = 1, kFamTs = 4 };
 static int gemm_family_override() {
   const char* e = getenv("SGF_GEMM_FAMILY");
   if (!e) return kFamAuto;
   if (!strcmp(e, "tile")) return kFamTile;
-  if (!strcmp(e, "persist")) return kFamPersist;
-  if (!strcmp(e, "pair")) return kFamPair;
   if (!strcmp(e, "ts")) return kFamTs;
   return kFamAuto;
 }
@@ -1284,47 +619,6 @@ extern "C" int sgf_gemm_bf16(const sgf_gemm_args* a, void* stream) {
   if (a->batch == 1 && (fam == kFamTs || (fam == kFamAuto && static_cast<long>(a->M) * a->N >= 128L * 1024))) {
     const int rc = gemm_ts_dispatch(shp, ep, a->a, a->lda, a->b, a->ldb, false, 0, 0, st);
     if (rc >= 0) return rc;
-  }
-  // persistent CTA-pair kernel (256 x 256 tiles) for the large transformer GEMMs: full N tiles only
-  const bool pair_ok = a->N % 256 == 0 && a->K >= 64;
-  if ((fam == kFamPair && pair_ok) || (fam == kFamAuto && pair_ok && a->M >= 2048 && a->N >= 2048 && a->K >= 256)) {
-    CUtensorMap tmA2, tmB2;
-    uint64_t dimsA[3] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M), static_cast<uint64_t>(a->batch)};
-    uint64_t strA[2] = {static_cast<uint64_t>(a->lda) * 2,
-                        static_cast<uint64_t>(a->batch > 1 ? a->a_batch_stride : a->lda * (int64_t)a->M) * 2};
-    uint32_t boxA[3] = {BK, BM, 1};
-    uint64_t dimsB[3] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->batch)};
-    uint64_t strB[2] = {static_cast<uint64_t>(a->ldb) * 2,
-                        static_cast<uint64_t>(a->batch > 1 ? a->b_batch_stride : a->ldb * (int64_t)a->N) * 2};
-    uint32_t boxB[3] = {BK, static_cast<uint32_t>(kP2BN / 2), 1};
-    if (int rc = encode_tmap(&tmA2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dimsA, strA, boxA, CU_TENSOR_MAP_SWIZZLE_128B))
-      return rc;
-    if (int rc = encode_tmap(&tmB2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->b, dimsB, strB, boxB, CU_TENSOR_MAP_SWIZZLE_128B))
-      return rc;
-    const int rc = dispatch_epilogue2p(tmA2, tmB2, shp, ep, a->batch, st);
-    if (rc >= 0) return rc;
-  }
-  // persistent 1-CTA kernel (128 x 128 / 128 x 64 tiles) for everything else that has enough tiles to keep the SMs busy
-  // for more than one round trip of set-up cost: out_proj, fc2, cross-q, the 1x1 convolutions of the stem
-  {
-    const int bnp = a->N % 128 == 0 ? 128 : (a->N % 64 == 0 ? 64 : 0);
-    const long tiles = bnp ? static_cast<long>(m_tiles) * (a->N / bnp) : 0;
-    if (a->batch == 1 && bnp && !a->rowstats_out && (fam == kFamPersist || (fam == kFamAuto && tiles >= 96))) {
-      CUtensorMap tmAp, tmBp;
-      uint64_t dimsA[3] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M), 1};
-      uint64_t strA[2] = {static_cast<uint64_t>(a->lda) * 2, static_cast<uint64_t>(a->lda) * a->M * 2};
-      uint32_t boxA[3] = {BK, BM, 1};
-      uint64_t dimsB[3] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->N), 1};
-      uint64_t strB[2] = {static_cast<uint64_t>(a->ldb) * 2, static_cast<uint64_t>(a->ldb) * a->N * 2};
-      uint32_t boxB[3] = {BK, static_cast<uint32_t>(bnp), 1};
-      if (int rc = encode_tmap(&tmAp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->a, dimsA, strA, boxA, CU_TENSOR_MAP_SWIZZLE_128B))
-        return rc;
-      if (int rc = encode_tmap(&tmBp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->b, dimsB, strB, boxB, CU_TENSOR_MAP_SWIZZLE_128B))
-        return rc;
-      const int rc = bnp == 128 ? dispatch_epiloguep<128, false>(tmAp, tmBp, shp, ep, m_tiles, st)
-                                : dispatch_epiloguep<64, false>(tmAp, tmBp, shp, ep, m_tiles, st);
-      if (rc >= 0) return rc;
-    }
   }
   if (a->rowstats_out && bn != 64 && bn != 128) bn = 128;  // statistics are kept per 64-column block
 
@@ -1463,9 +757,7 @@ extern "C" int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* a, void* stream) {
     const int rc = gemm_ts_dispatch(shp, ep, a->x, 0, a->w, shp.K, true, a->n, a->cin, st);
     if (rc >= 0) return rc;
   }
-  const int bnp = a->cout % 128 == 0 ? 128 : (a->cout % 64 == 0 ? 64 : 0);
-  const bool persist = bnp && fam != kFamTile && (fam == kFamPersist || static_cast<long>(m_tiles) * (a->cout / bnp) >= 96);
-  const int bn = persist ? bnp : pick_bn(m_tiles, a->cout, 1);
+  const int bn = pick_bn(m_tiles, a->cout, 1);
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {static_cast<uint64_t>(a->cin), static_cast<uint64_t>(a->w_), static_cast<uint64_t>(a->h),
@@ -1484,11 +776,6 @@ extern "C" int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* a, void* stream) {
     if (int rc = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a->w, dims, strides, box,
                              CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
-  }
-  if (persist) {
-    const int rc = bn == 128 ? dispatch_epiloguep<128, true>(tmA, tmB, shp, ep, m_tiles, st)
-                             : dispatch_epiloguep<64, true>(tmA, tmB, shp, ep, m_tiles, st);
-    if (rc >= 0) return rc;
   }
   dim3 grid((a->cout + bn - 1) / bn, m_tiles, 1);
   switch (bn) {

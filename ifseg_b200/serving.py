@@ -55,7 +55,8 @@ class SegmentationSession:
                     with torch.cuda.graph(self.graph, stream=self.compute):
                         self._forward()
         self._stage_out = [torch.empty_like(self.masks) for _ in range(2)]
-        self._pin_out = [torch.empty(self.masks.shape, dtype=self.masks.dtype).pin_memory() for _ in range(2)]
+        # three pinned result buffers: the one handed to the caller is not written again before the NEXT yield
+        self._pin_out = [torch.empty(self.masks.shape, dtype=self.masks.dtype).pin_memory() for _ in range(3)]
         torch.cuda.synchronize(self.device)
 
     def _forward(self):
@@ -83,18 +84,19 @@ class SegmentationSession:
             return out.clone()
 
     def infer_stream(self, batches: Iterable[torch.Tensor], pinned_inputs: bool = False) -> Iterator[torch.Tensor]:
-        """Pipelined: yields the host mask tensor of each batch (valid until the next-but-one
-        yield).  With pinned_inputs=True the given tensors are used as the pinned H2D source
-        directly (no staging memcpy on the host)."""
+        """Pipelined: yields the host mask tensor of each batch.  The yielded tensor is one of three rotating pinned
+        buffers and stays valid until the generator is resumed TWICE more (i.e. across the next yield); clone it to keep
+        it longer.  With pinned_inputs=True the given tensors are used as the pinned H2D source directly (no staging
+        memcpy on the host)."""
         ev_in = [torch.cuda.Event() for _ in range(2)]
         ev_free = [torch.cuda.Event() for _ in range(2)]
         ev_done = [torch.cuda.Event() for _ in range(2)]
-        ev_out = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(3)]
         pending = []
         for i, hb in enumerate(batches):
-            s = i & 1
+            s, o = i & 1, i % 3
             if i >= 2:
-                ev_out[s].synchronize()  # pinned_out[s]/stage buffers of batch i-2 are free again
+                ev_out[(i - 2) % 3].synchronize()  # batch i-2 is on the host; its stage buffers (slot s) are free again
                 yield pending.pop(0)
             src = hb
             if not (pinned_inputs and hb.is_pinned()):
@@ -110,15 +112,15 @@ class SegmentationSession:
                 self.images.copy_(self._stage_in[s], non_blocking=True)
                 ev_free[s].record(self.compute)
                 if i >= 2:
-                    self.compute.wait_event(ev_out[s])
+                    self.compute.wait_event(ev_out[(i - 2) % 3])  # _stage_out[s] has been drained by the D2H of batch i-2
                 self.step_device()
                 self._stage_out[s].copy_(self.masks, non_blocking=True)
                 ev_done[s].record(self.compute)
             with torch.cuda.stream(self.d2h):
                 self.d2h.wait_event(ev_done[s])
-                self._pin_out[s].copy_(self._stage_out[s], non_blocking=True)
-                ev_out[s].record(self.d2h)
-            pending.append(self._pin_out[s])
+                self._pin_out[o].copy_(self._stage_out[s], non_blocking=True)
+                ev_out[o].record(self.d2h)
+            pending.append(self._pin_out[o])
         for k, out in enumerate(pending):
             self.d2h.synchronize()
             yield out

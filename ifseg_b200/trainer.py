@@ -80,6 +80,10 @@ class SegOFATrainer:
                 self._side = torch.cuda.Stream()
             self._side.wait_stream(main)
             ni = sample["net_input"]
+            if check_pads and bool(ni["src_tokens"].eq(cfg.padding_idx).any()):
+                # the metric pass runs the no-padding fast path; a padded prompt would silently change the metrics
+                raise NotImplementedError("segofa_b200 trainer: padded prompts in net_input are not supported in the "
+                                          "real-image metric pass (the shipped recipe uses one fixed prompt per batch)")
             with torch.cuda.stream(self._side), torch.no_grad():
                 enc = eng.inf.encode(ni["src_tokens"], patch_images=ni["patch_images"], patch_masks=ni["patch_masks"],
                                      has_pads=False)

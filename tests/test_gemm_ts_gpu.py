@@ -48,7 +48,7 @@ def _both(ops, bn, fn):
 
 
 # M covers: odd number of 128-row tiles (phantom half of the last pair), a ragged last tile, many rounds per cluster
-@pytest.mark.parametrize("bn", [64, 128, 192, 256])
+@pytest.mark.parametrize("bn", [64, 128, 192, 256, 384])
 @pytest.mark.parametrize("M", [515, 128, 7208, 33000])
 def test_ts_epilogues(ops, bn, M):
     g = torch.Generator(device="cuda").manual_seed(bn + M)
@@ -107,7 +107,7 @@ def test_ts_epilogues(ops, bn, M):
     assert _rel(o, acc + bias + res32) < 2e-5 and torch.equal(o, t)
 
 
-@pytest.mark.parametrize("bn", [64, 256])
+@pytest.mark.parametrize("bn", [64, 256, 384])
 def test_ts_folded_layernorm(ops, bn):
     """fc1 -> ffn_layernorm -> fc2 with the LayerNorm folded into the two epilogues, x updated in place."""
     g = torch.Generator(device="cuda").manual_seed(77)

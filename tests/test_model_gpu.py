@@ -232,6 +232,13 @@ def test_serving_session_matches_eager(case15):
             ref = eng.predict_mask(x, extra["encoder_returns"]["image_embed_shape"][0], (S, S))
         assert torch.equal(m, ref.cpu())
     assert torch.equal(sess.infer(batches[0]), outs[0])
+    # a yielded tensor stays intact across the NEXT yield (three rotating pinned buffers): hold it without cloning
+    held = []
+    for k, m in enumerate(sess.infer_stream(batches)):
+        if held:
+            torch.cuda.synchronize()  # everything the generator has queued so far has landed
+            assert torch.equal(held[-1], outs[k - 1]), "result buffer overwritten while the caller still held it"
+        held.append(m)
 
 
 @pytest.mark.parametrize("Hi,Wi", [(128, 192), (96, 160), (160, 128)])

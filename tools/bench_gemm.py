@@ -1,4 +1,4 @@
-"""A/B of the GEMM kernel families (SGF_GEMM_FAMILY = tile | persist | pair) on the call sites of the cfg-2 forward, with
+"""A/B of the GEMM kernel families (SGF_GEMM_FAMILY = tile | ts) on the call sites of the cfg-2 forward, with
 their real epilogues, checked against each other bit for bit and timed L2-cold next to cuBLAS (plain GEMM only)."""
 import os
 import sys
@@ -10,7 +10,7 @@ from ifseg_b200 import ops
 from tools.bench_ops import timeit
 
 
-def run(name, fn, out, flops, fams=("tile", "pair", "ts")):
+def run(name, fn, out, flops, fams=("tile", "ts")):
     row, ref = {}, None
     for fam in fams:
         os.environ["SGF_GEMM_FAMILY"] = fam
@@ -69,13 +69,13 @@ def main():
         idn = rn(M, N).bfloat16() if res else None
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
         run(tag, lambda: ops.gemm(a, b, out, scale=sc, bias=bi, act=ops.ACT_RELU, residual=idn), out, 2.0 * M * N * K,
-            fams=("tile", "persist", "ts"))
+            fams=("tile", "ts"))
     for (tag, n, h, c) in [("l3.conv2", 8, 30, 256), ("l2.conv2", 8, 60, 128), ("l1.conv2", 8, 120, 64)]:
         x = rn(n, h, h, c).bfloat16()
         w = (rn(c, 9 * c) * 0.05).bfloat16()
         sc, bi = rn(c), rn(c)
         out = torch.empty(n, h, h, c, device="cuda", dtype=torch.bfloat16)
-        run(tag, lambda: ops.conv3x3_s1(x, w, sc, bi, out=out), out, 2.0 * n * h * h * c * 9 * c, fams=("tile", "persist", "ts"))
+        run(tag, lambda: ops.conv3x3_s1(x, w, sc, bi, out=out), out, 2.0 * n * h * h * c * 9 * c, fams=("tile", "ts"))
 
 
 if __name__ == "__main__":
