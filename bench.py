@@ -170,6 +170,48 @@ def cpu_reference_run(cfg_id, steps, warmup, sample_batch=None, want_outputs=Fal
     return (cb, dt, last) if want_outputs else (cb, dt)
 
 
+def gpu_eager_context(cfg_id):
+    """Context, not a target: the oracle port (the reference's algorithm, op for op) run by PyTorch eager on THIS GPU under
+    bf16 autocast (ATen elementwise kernels + cuBLAS GEMMs), forward -> mask, full batch.  It answers "what does the
+    reference's own PyTorch path do on one B200" (BASELINE.md s4.4); part of the cpu_baseline leg because it executes
+    oracle/."""
+    import torch
+
+    from ifseg_b200.config import preset
+    from ifseg_b200.synthetic import generate_state_dict, synthetic_inputs
+    from oracle import restated as R
+
+    arch, size, nseg, batch, _ = CONFIGS[cfg_id]
+    try:
+        cfg = preset(arch, num_seg=nseg, patch_image_size=size, orig_patch_image_size=size)
+        sd = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in generate_state_dict(cfg, 0).items()}
+        ocfg = R.SegOFAConfig(**{k: getattr(cfg, k) for k in R.SegOFAConfig.__dataclass_fields__ if hasattr(cfg, k)})
+        inp = {k: v.cuda() for k, v in synthetic_inputs(cfg, batch, size, seed=1, src_tokens=prompt_tokens(nseg)).items()}
+        hp = size // 16
+
+        def step():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                lg, _ = R.segofa_forward(sd, ocfg, inp["src_tokens"], inp["patch_images"], inp["patch_masks"])
+            return R.predict_mask(lg, hp, hp, size, size)
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(3):
+            step()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 3
+        return {"value": batch / (ms / 1e3), "unit": "images/s", "ms_per_step": ms, "batch": batch,
+                "what": "oracle/restated.py under torch eager + bf16 autocast on this GPU (ATen + cuBLAS), 3 timed steps"}
+    except Exception as ex:  # noqa: BLE001 -- context only
+        return {"unavailable": f"{type(ex).__name__}: {str(ex)[:160]}"}
+    finally:
+        torch.cuda.empty_cache()
+
+
 def parity_against_oracle(model, last, size):
     """The timed configuration checked against the oracle run of the cpu_baseline leg (same seeded weights and inputs):
     logits rel-L2 against the fp32 oracle, mask agreement, and how many disagreeing pixels have a top-2 margin the logit
@@ -579,6 +621,7 @@ def main():
             cb, _, last = cpu_reference_run(args.config, 1, 1, sample_batch=1 if size >= 256 else None, want_outputs=True)
             out["cpu_baseline"] = cb
             out["parity"] = parity_against_oracle(model, last, size)
+            out["gpu_eager_context"] = gpu_eager_context(args.config)
     else:
         out = None
     # ---------------- the training step of the same recipe on the same N ranks (cfg 3), as a sub-record ----------------

@@ -37,6 +37,16 @@ class Conv3x3Args(C.Structure):
     ]
 
 
+class Conv2dArgs(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("n", _i32), ("h", _i32), ("w_", _i32), ("cin", _i32),
+        ("x_w_stride", _i64), ("x_h_stride", _i64), ("x_n_stride", _i64),
+        ("w", _vp), ("y", _vp), ("ho", _i32), ("wo", _i32), ("cout", _i32),
+        ("kh", _i32), ("kw", _i32), ("stride_h", _i32), ("stride_w", _i32), ("pad_h", _i32), ("pad_w", _i32),
+        ("col_scale", _vp), ("col_bias", _vp), ("act", _i32),
+    ]
+
+
 class RowLnArgs(C.Structure):
     _fields_ = [
         ("x", _vp), ("ldx", _i64), ("x_dtype", _i32),
@@ -179,7 +189,9 @@ EXPORTS = [
     ("sgf_gemm_bf16", C.c_int, [C.POINTER(GemmArgs), _vp]),
     ("sgf_gemm_bf16_ex", C.c_int, [C.POINTER(GemmArgs), _i32, _i32, _i32, _vp]),
     ("sgf_conv3x3_s1_nhwc", C.c_int, [C.POINTER(Conv3x3Args), _vp]),
+    ("sgf_conv2d_nhwc", C.c_int, [C.POINTER(Conv2dArgs), _vp]),
     ("sgf_nchw_f32_to_nhwc_bf16", C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    ("sgf_nchw_f32_to_nhwc8_padded", C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     ("sgf_im2col_nhwc", C.c_int, [_vp, _vp] + [_i32] * 10 + [_i64, _vp]),
     ("sgf_maxpool3x3s2_nhwc", C.c_int, [_vp, _vp] + [_i32] * 6 + [_vp]),
     ("sgf_row_layernorm", C.c_int, [C.POINTER(RowLnArgs), _vp]),

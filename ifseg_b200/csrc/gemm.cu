@@ -617,7 +617,7 @@ extern "C" int sgf_gemm_bf16(const sgf_gemm_args* a, void* stream) {
   const int fam = gemm_family_override();
   // persistent CTA-pair kernel with the TMA-store epilogue: everything with N % 64 == 0 and at least a few tiles
   if (a->batch == 1 && (fam == kFamTs || (fam == kFamAuto && static_cast<long>(a->M) * a->N >= 128L * 1024))) {
-    const int rc = gemm_ts_dispatch(shp, ep, a->a, a->lda, a->b, a->ldb, false, 0, 0, st);
+    const int rc = gemm_ts_dispatch(shp, ep, a->a, a->lda, a->b, a->ldb, nullptr, st);
     if (rc >= 0) return rc;
   }
   if (a->rowstats_out && bn != 64 && bn != 128) bn = 128;  // statistics are kept per 64-column block
@@ -747,6 +747,7 @@ extern "C" int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* a, void* stream) {
   shp.tiles_w = (a->w_ + bw - 1) / bw;
   shp.tiles_h = (a->h + bh - 1) / bh;
   shp.cin_blocks = a->cin / 64;
+  shp.kw = 3; shp.stride_h = shp.stride_w = 1; shp.pad_h = shp.pad_w = 1;
   GemmEpilogue ep{a->y, a->cout, 0, SGF_BF16, a->col_scale, a->col_bias, nullptr, 0, 0, SGF_BF16, a->act, 1.0f, 0,
                   nullptr, nullptr, nullptr, 0.f, 0};
   if (int rc = check_epilogue_alignment(ep, a->cout)) return rc;
@@ -754,7 +755,9 @@ extern "C" int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* a, void* stream) {
   const int m_tiles = a->n * shp.tiles_w * shp.tiles_h;
   const int fam = gemm_family_override();
   if (fam == kFamTs || fam == kFamAuto) {
-    const int rc = gemm_ts_dispatch(shp, ep, a->x, 0, a->w, shp.K, true, a->n, a->cin, st);
+    const ConvInput cv{a->x, a->n, a->h, a->w_, a->cin, a->cin, static_cast<int64_t>(a->cin) * a->w_,
+                       static_cast<int64_t>(a->cin) * a->w_ * a->h};
+    const int rc = gemm_ts_dispatch(shp, ep, nullptr, 0, a->w, shp.K, &cv, st);
     if (rc >= 0) return rc;
   }
   const int bn = pick_bn(m_tiles, a->cout, 1);
@@ -783,4 +786,39 @@ extern "C" int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* a, void* stream) {
     case 64: return dispatch_epilogue<64, 4, true>(tmA, tmB, shp, ep, grid, st);
     default: return dispatch_epilogue<128, 3, true>(tmA, tmB, shp, ep, grid, st);
   }
+}
+
+extern "C" int sgf_conv2d_nhwc(const sgf_conv2d_args* a, void* stream) {
+  SGF_REQUIRE(a != nullptr && a->x && a->w && a->y, "conv2d: null pointer");
+  SGF_REQUIRE(a->cin % 64 == 0, "conv2d: the innermost input extent must be a multiple of 64 (got %d)", a->cin);
+  SGF_REQUIRE(a->cout % 64 == 0, "conv2d: Cout must be a multiple of 64 (got %d)", a->cout);
+  SGF_REQUIRE(a->n > 0 && a->h > 0 && a->w_ > 0 && a->ho > 0 && a->wo > 0 && a->kh > 0 && a->kw > 0 && a->stride_h > 0 &&
+                  a->stride_w > 0 && a->pad_h >= 0 && a->pad_w >= 0,
+              "conv2d: bad shape");
+  SGF_REQUIRE(a->x_w_stride % 8 == 0 && a->x_h_stride % 8 == 0 && a->x_n_stride % 8 == 0 &&
+                  reinterpret_cast<uintptr_t>(a->x) % 16 == 0 && reinterpret_cast<uintptr_t>(a->w) % 16 == 0,
+              "conv2d: input strides must be multiples of 8 elements and x / w 16-byte aligned (TMA)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // 128-pixel output tile = bw x bh rectangle; bw = smallest power of two >= min(Wo, 128)
+  int bw = 1;
+  while (bw < a->wo && bw < 128) bw <<= 1;
+  const int bh = 128 / bw;
+  SGF_REQUIRE(bw * a->stride_w <= 256 && bh * a->stride_h <= 256, "conv2d: stride too large for one TMA box");
+  GemmShape shp{};
+  shp.M = a->n * a->ho * a->wo;
+  shp.N = a->cout;
+  shp.K = a->kh * a->kw * a->cin;
+  shp.H = a->ho; shp.W = a->wo; shp.bw = bw; shp.bh = bh;
+  shp.tiles_w = (a->wo + bw - 1) / bw;
+  shp.tiles_h = (a->ho + bh - 1) / bh;
+  shp.cin_blocks = a->cin / 64;
+  shp.kw = a->kw; shp.stride_h = a->stride_h; shp.stride_w = a->stride_w; shp.pad_h = a->pad_h; shp.pad_w = a->pad_w;
+  GemmEpilogue ep{a->y, a->cout, 0, SGF_BF16, a->col_scale, a->col_bias, nullptr, 0, 0, SGF_BF16, a->act, 1.0f, 0,
+                  nullptr, nullptr, nullptr, 0.f, 0};
+  if (int rc = check_epilogue_alignment(ep, a->cout)) return rc;
+  const ConvInput cv{a->x, a->n, a->h, a->w_, a->cin, a->x_w_stride, a->x_h_stride, a->x_n_stride};
+  const int rc = gemm_ts_dispatch(shp, ep, nullptr, 0, a->w, shp.K, &cv, st);
+  if (rc >= 0) return rc;
+  set_last_error("conv2d: no kernel for this epilogue (supported: BN affine with or without ReLU)");
+  return SGF_ERR_UNSUPPORTED;
 }

@@ -34,8 +34,17 @@ struct GemmEpilogue {
 
 struct GemmShape {
   int M, N, K;
-  // conv mode only
+  // conv mode only: H, W = OUTPUT height / width (the 128-pixel tiles are bw x bh rectangles of the output)
   int H, W, bw, bh, tiles_w, tiles_h, cin_blocks;
+  // general convolution (gemm_ts.cu): filter width, stride and padding; the one-tile kernel is 3x3 / 1 / 1 only
+  int kw, stride_h, stride_w, pad_h, pad_w;
+};
+
+// input side of a convolution launch of gemm_ts.cu: a 4-D TMA view (c, w, h, n) with explicit element strides
+struct ConvInput {
+  const void* x;
+  int n, h, w, cin;                         // tensor-map extents along n, h, w and the 64-multiple innermost extent
+  int64_t w_stride, h_stride, n_stride;     // in bf16 elements (w_stride < cin = overlapping windows is allowed)
 };
 
 template <int BN>
@@ -77,6 +86,6 @@ static inline int epilogue_mask(const GemmEpilogue& ep) {
 
 // gemm_ts.cu: returns -1 when the call is outside the kernel's envelope (the caller falls back to the tile kernels)
 int gemm_ts_dispatch(const GemmShape& shp, const GemmEpilogue& ep, const void* a, int64_t lda, const void* b, int64_t ldb,
-                     bool conv, int conv_n, int conv_cin, cudaStream_t st);
+                     const ConvInput* conv, cudaStream_t st);
 
 }  // namespace sgf

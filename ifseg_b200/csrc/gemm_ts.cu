@@ -175,7 +175,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTsThreads, 1)
             if constexpr (kConv) {
               const int tap = kb / shp.cin_blocks;
               const int kc = kb - tap * shp.cin_blocks;
-              tma_load_4d_2cta(sa, &tmA, &bars->full[s], kc * BK, w0 + tap % 3 - 1, h0 + tap / 3 - 1, img);
+              const int ky = tap / shp.kw, kx = tap - ky * shp.kw;
+              tma_load_4d_2cta(sa, &tmA, &bars->full[s], kc * BK, w0 * shp.stride_w + kx - shp.pad_w,
+                               h0 * shp.stride_h + ky - shp.pad_h, img);
             } else {
               tma_load_2d_2cta(sa, &tmA, &bars->full[s], kb * BK, m0);
             }
@@ -556,7 +558,8 @@ static int pick_bn_ts(int m_tiles, int N, int num_kb, int max_clusters, bool out
 }
 
 int gemm_ts_dispatch(const GemmShape& shp, const GemmEpilogue& ep, const void* a, int64_t lda, const void* b, int64_t ldb,
-                     bool conv, int conv_n, int conv_cin, cudaStream_t st) {
+                     const ConvInput* cv, cudaStream_t st) {
+  const bool conv = cv != nullptr;
   if (shp.N % 64 != 0 || shp.K < 1) return -1;
   const int mask = epilogue_mask(ep);
   if ((mask & kEpiResF32) && !(ep.residual == ep.c && ep.ldr == ep.ldc && (mask & kEpiOutF32))) return -1;  // in place only
@@ -568,7 +571,7 @@ int gemm_ts_dispatch(const GemmShape& shp, const GemmEpilogue& ep, const void* a
     SGF_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int max_clusters = num_sms / 2;
-  const int m_tiles = conv ? conv_n * shp.tiles_w * shp.tiles_h : (shp.M + BM - 1) / BM;
+  const int m_tiles = conv ? cv->n * shp.tiles_w * shp.tiles_h : (shp.M + BM - 1) / BM;
   const int num_kb = (shp.K + BK - 1) / BK;
   const bool out_f32 = ep.c_dtype == SGF_F32;
   const int bn = pick_bn_ts(m_tiles, shp.N, num_kb, max_clusters, out_f32);
@@ -577,15 +580,19 @@ int gemm_ts_dispatch(const GemmShape& shp, const GemmEpilogue& ep, const void* a
   TsMaps tm;
   memset(&tm, 0, sizeof(tm));
   if (conv) {
-    uint64_t dims[4] = {static_cast<uint64_t>(conv_cin), static_cast<uint64_t>(shp.W), static_cast<uint64_t>(shp.H),
-                        static_cast<uint64_t>(conv_n)};
-    uint64_t strides[3] = {static_cast<uint64_t>(conv_cin) * 2, static_cast<uint64_t>(conv_cin) * shp.W * 2,
-                           static_cast<uint64_t>(conv_cin) * shp.W * shp.H * 2};
-    uint32_t box[4] = {BK, static_cast<uint32_t>(shp.bw), static_cast<uint32_t>(shp.bh), 1};
-    if (int rc = encode_tmap(&tm.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+    // input: (c, w, h, n) view with the caller's strides; a strided convolution samples every stride-th pixel through the
+    // TMA element strides (box extent = samples x stride), out-of-bounds coordinates are zero fill = the padding
+    uint64_t dims[4] = {static_cast<uint64_t>(cv->cin), static_cast<uint64_t>(cv->w), static_cast<uint64_t>(cv->h),
+                        static_cast<uint64_t>(cv->n)};
+    uint64_t strides[3] = {static_cast<uint64_t>(cv->w_stride) * 2, static_cast<uint64_t>(cv->h_stride) * 2,
+                           static_cast<uint64_t>(cv->n_stride) * 2};
+    uint32_t box[4] = {BK, static_cast<uint32_t>(shp.bw * shp.stride_w), static_cast<uint32_t>(shp.bh * shp.stride_h), 1};
+    uint32_t est[4] = {1, static_cast<uint32_t>(shp.stride_w), static_cast<uint32_t>(shp.stride_h), 1};
+    if (box[1] > 256 || box[2] > 256) return -1;
+    if (int rc = encode_tmap(&tm.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, cv->x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, est))
       return rc;
     uint64_t cdims[4] = {static_cast<uint64_t>(shp.N), static_cast<uint64_t>(shp.W), static_cast<uint64_t>(shp.H),
-                         static_cast<uint64_t>(conv_n)};
+                         static_cast<uint64_t>(cv->n)};
     uint64_t cstr[3] = {static_cast<uint64_t>(shp.N) * 2, static_cast<uint64_t>(shp.N) * shp.W * 2,
                         static_cast<uint64_t>(shp.N) * shp.W * shp.H * 2};
     uint32_t cbox[4] = {64, static_cast<uint32_t>(shp.bw), static_cast<uint32_t>(shp.bh), 1};

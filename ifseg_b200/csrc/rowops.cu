@@ -510,6 +510,25 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
     y[pix * c + cc] = __float2bfloat16_rn(x[(img * c + cc) * static_cast<int64_t>(h) * w + hw]);
 }
 
+// [N,C<=8,H,W] fp32 -> zero-padded [N, H+2*pad, Wp, 8] bf16 (channels C..7 and the border are zero): the input layout of
+// the im2col-free 7x7/2 stem convolution (one 16-byte store per padded pixel)
+__global__ void nchw_to_nhwc8_padded_kernel(const float* __restrict__ x, uint4* __restrict__ y, int n, int c, int h, int w,
+                                            int pad, int hp, int wp) {
+  const int64_t total = static_cast<int64_t>(n) * hp * wp;
+  const int64_t pix = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (pix >= total) return;
+  const int xx = static_cast<int>(pix % wp) - pad;
+  const int yy = static_cast<int>((pix / wp) % hp) - pad;
+  const int64_t img = pix / (static_cast<int64_t>(wp) * hp);
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (xx >= 0 && xx < w && yy >= 0 && yy < h) {
+    for (int cc = 0; cc < c; ++cc) v[cc] = x[((img * c + cc) * h + yy) * static_cast<int64_t>(w) + xx];
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  y[pix] = o;
+}
+
 // generic im2col, one thread per (output pixel, tap, 8-channel group or single channel)
 template <bool kVec>
 __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int n, int h,
@@ -799,6 +818,19 @@ extern "C" int sgf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int
   const int64_t total = static_cast<int64_t>(n) * h * w;
   nchw_to_nhwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, reinterpret_cast<__nv_bfloat16*>(y), n, c, h, w);
+  SGF_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return SGF_OK;
+}
+
+extern "C" int sgf_nchw_f32_to_nhwc8_padded(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad,
+                                            int32_t hp, int32_t wp, void* stream) {
+  SGF_REQUIRE(x && y && n > 0 && c > 0 && c <= 8 && h > 0 && w > 0 && pad >= 0 && hp >= h + pad && wp >= w + pad,
+              "nchw_to_nhwc8_padded: bad args");
+  SGF_REQUIRE(reinterpret_cast<uintptr_t>(y) % 16 == 0, "nchw_to_nhwc8_padded: y must be 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(n) * hp * wp;
+  nchw_to_nhwc8_padded_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<uint4*>(y), n, c, h, w, pad, hp, wp);
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return SGF_OK;

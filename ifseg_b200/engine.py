@@ -101,13 +101,20 @@ class SegOFAEngine:
         w = conv.weight.detach().float()
         c.cout, c.cin, c.kh, c.kw = w.shape
         c.stride, c.pad = conv.stride[0], conv.padding[0]
-        pitch = ops.im2col_pitch(c.kw, c.cin)  # filter-row pitch of the patch matrix (conv1: 21 -> 24)
-        c.k = c.kh * pitch
+        if c.cin % 8 == 0:
+            # [Cout, ky, kx, cin] tap-major: the K order of the implicit-GEMM convolutions and of a 1x1 GEMM alike
+            c.k = c.kh * c.kw * c.cin
+            wm = w.permute(0, 2, 3, 1).reshape(c.cout, c.k)
+        else:
+            # conv1 (7x7/2 over 3 channels): 7 filter-row taps of an 8-pixel x 8-channel window, zero weights for the
+            # eighth pixel and for channels 3..7 (ops.conv2d window mode) -- K = 7 * 64
+            assert c.kw <= 8 and c.cin <= 8
+            c.k = c.kh * 64
+            wm = torch.zeros(c.cout, c.kh, 8, 8, dtype=torch.float32, device=w.device)
+            wm[:, :, : c.kw, : c.cin] = w.permute(0, 2, 3, 1)
+            wm = wm.reshape(c.cout, c.k)
         c.ldk = c.k
-        wm = torch.zeros(c.cout, c.kh, pitch, dtype=torch.float32, device=w.device)
-        wm[:, :, : c.kw * c.cin] = w.permute(0, 2, 3, 1).reshape(c.cout, c.kh, c.kw * c.cin)  # [Cout, ky, (kx,cin)]
-        wm = wm.reshape(c.cout, c.k)
-        c.w = self._b16(wm)
+        c.w = self._b16(wm.contiguous())
         scale = bn.weight.detach().float() * (bn.running_var.detach().float() + bn.eps).rsqrt()  # frozen_bn.py:40-41
         c.scale = self._f32(scale)
         c.bias = self._f32(bn.bias.detach().float() - bn.running_mean.detach().float() * scale)
@@ -208,24 +215,31 @@ class SegOFAEngine:
     # stem: resnet.py:215-229
     # ------------------------------------------------------------------------------------
     def _conv_gemm(self, x, c: _ConvW, act, residual=None):
-        """x [N,H,W,Cin] bf16 NHWC -> [N,Ho,Wo,Cout] bf16."""
+        """x [N,H,W,Cin] bf16 NHWC -> [N,Ho,Wo,Cout] bf16.  Every convolution is an im2col-free implicit GEMM: 1x1/1 is a
+        plain GEMM over the pixel rows, everything else (3x3/1, 3x3/2, 1x1/2) goes through the TMA-box convolution."""
         n, h, w, _ = x.shape
-        if c.kh == 3 and c.stride == 1 and c.cin % 64 == 0 and residual is None:
-            return ops.conv3x3_s1(x, c.w, c.scale, c.bias, act=act, tag=f"stem3x3_{h}")
         if c.kh == 1 and c.stride == 1:
-            a, ho, wo = x.view(n * h * w, c.cin), h, w
-        else:  # the few strided convs: explicit patch matrix (7x7/2, 3x3/2, 1x1/2)
-            a, ho, wo = ops.im2col(x, c.kh, c.kw, c.stride, c.pad, ld_out=c.ldk)
-        out = torch.empty((n, ho, wo, c.cout), dtype=_BF16, device=x.device)
-        ops.gemm(a, c.w, out.view(-1, c.cout), M=n * ho * wo, N=c.cout, K=c.k, lda=a.stride(0), ldb=c.ldk,
-                 scale=c.scale, bias=c.bias, act=act,
-                 residual=residual.view(-1, c.cout) if residual is not None else None,
-                 tag=f"stem{c.kh}x{c.kh}s{c.stride}_{ho}_k{c.k}_n{c.cout}")
-        return out
+            out = torch.empty((n, h, w, c.cout), dtype=_BF16, device=x.device)
+            ops.gemm(x.view(n * h * w, c.cin), c.w, out.view(-1, c.cout), M=n * h * w, N=c.cout, K=c.k, lda=c.cin, ldb=c.ldk,
+                     scale=c.scale, bias=c.bias, act=act,
+                     residual=residual.view(-1, c.cout) if residual is not None else None,
+                     tag=f"stem1x1s1_{h}_k{c.k}_n{c.cout}")
+            return out
+        assert residual is None
+        if c.kh == 3 and c.stride == 1:
+            return ops.conv3x3_s1(x, c.w, c.scale, c.bias, act=act, tag=f"stem3x3_{h}")
+        return ops.conv2d(x, c.w, c.scale, c.bias, kh=c.kh, kw=c.kw, stride=c.stride, pad=c.pad, act=act,
+                          tag=f"stem{c.kh}x{c.kw}s{c.stride}_{h}")
 
     def stem(self, patch_images):
-        x = ops.nchw_to_nhwc_bf16(patch_images.float())
-        x = self._conv_gemm(x, self.stem_conv1, ops.ACT_RELU)
+        c1 = self.stem_conv1
+        _, _, H, W = patch_images.shape
+        # conv1 7x7/2 (resnet.py:189-213): the image goes to a zero-padded 8-channel NHWC buffer once; the convolution reads
+        # it as overlapping 128-byte windows (8 pixels x 8 channels) -- 7 k-blocks, no patch matrix
+        hp, wp = H + 2 * c1.pad, (W + 2 * c1.pad + 8 + 7) // 8 * 8
+        xp = ops.nchw_to_nhwc8_padded(patch_images.float(), c1.pad, hp, wp)
+        x = ops.conv2d(xp, c1.w, c1.scale, c1.bias, kh=c1.kh, kw=1, stride=c1.stride, act=ops.ACT_RELU,
+                       window=(H, W, c1.pad, c1.cin, c1.kw), tag="stem_conv1")
         x = ops.maxpool3x3s2(x)
         for b in self.stem_blocks:
             idn = x if b["down"] is None else self._conv_gemm(x, b["down"], ops.ACT_NONE)

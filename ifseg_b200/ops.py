@@ -175,6 +175,55 @@ def conv3x3_s1(x, w, scale, bias, act=ACT_RELU, out=None, tag=None):
     return out
 
 
+def conv2d(x, w, scale, bias, *, kh, kw, stride=1, pad=0, act=ACT_RELU, out=None, tag=None, window=None):
+    """im2col-free convolution + BN affine (+ ReLU) over bf16 NHWC (sgf_conv2d_nhwc).
+    x [N,H,W,Cin] (Cin % 64 == 0), w [Cout, kh*kw*Cin] tap-major -> [N,Ho,Wo,Cout] bf16.
+    window=(H, W, pad_phys, cin_real, kw_real): x is instead the zero-padded [N,Hp,Wp,8] image of the 7x7/2 stem convolution
+    (ops.nchw_to_nhwc8_padded) read as overlapping 8-pixel x 8-channel windows (kh taps of 64 'channels', kw = 1)."""
+    lib = _lib.load()
+    _req(x, torch.bfloat16, "x")
+    _req(w, torch.bfloat16, "w")
+    assert x.is_contiguous() and w.is_contiguous()
+    cout = w.shape[0]
+    if window is None:
+        n, h, wd, cin = x.shape
+        ho, wo = (h + 2 * pad - kh) // stride + 1, (wd + 2 * pad - kw) // stride + 1
+        geo = (n, h, wd, cin, cin, cin * wd, cin * wd * h, ho, wo, kh, kw, stride, stride, pad, pad)
+    else:
+        H, W, pad_phys, _, kw_real = window
+        n, hp, wp, c8 = x.shape
+        assert c8 == 8 and kw == 1 and kw_real <= 8
+        ho, wo = (H + 2 * pad_phys - kh) // stride + 1, (W + 2 * pad_phys - kw_real) // stride + 1
+        assert (wo - 1) * stride + 8 <= wp and (ho - 1) * stride + kh <= hp
+        # (c = 64-element window, w = window index with a pitch of `stride` pixels, h = padded row, n)
+        geo = (n, hp, wo, 64, stride * 8, wp * 8, wp * 8 * hp, ho, wo, kh, 1, stride, 1, 0, 0)
+    if out is None:
+        out = torch.empty((n, geo[7], geo[8], cout), dtype=torch.bfloat16, device=x.device)
+    args = _lib.Conv2dArgs(_p(x), geo[0], geo[1], geo[2], geo[3], geo[4], geo[5], geo[6], _p(w), _p(out), geo[7], geo[8], cout,
+                           geo[9], geo[10], geo[11], geo[12], geo[13], geo[14], _p(scale), _p(bias), act)
+    tok = _TAP.before("conv2d", x=x, w=w, scale=scale, bias=bias, act=act, kh=kh, kw=kw, stride=stride, pad=pad, window=window,
+                      tag=tag) if _TAP is not None else None
+    with _timed("gemm_tcgen05" + (":" + tag if tag and _TIMER is not None and _TIMER.fine else ""),
+                2.0 * n * geo[7] * geo[8] * cout * (kh * kw * geo[3] if window is None else kh * window[4] * window[3])):
+        _lib.check(lib.sgf_conv2d_nhwc(C.byref(args), _stream()), "sgf_conv2d_nhwc")
+    if tok is not None:
+        _TAP.after(tok, out)
+    return out
+
+
+def nchw_to_nhwc8_padded(x, pad, hp, wp):
+    """[N,C<=8,H,W] fp32 -> zero-padded [N,hp,wp,8] bf16 with the image at (pad, pad)."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    n, c, h, w = x.shape
+    x = x.contiguous()
+    y = torch.empty((n, hp, wp, 8), dtype=torch.bfloat16, device=x.device)
+    with _timed("layout", nbytes=x.numel() * 4.0 + y.numel() * 2.0):
+        _lib.check(lib.sgf_nchw_f32_to_nhwc8_padded(_p(x), _p(y), n, c, h, w, pad, hp, wp, _stream()),
+                   "sgf_nchw_f32_to_nhwc8_padded")
+    return y
+
+
 def nchw_to_nhwc_bf16(x):
     lib = _lib.load()
     _req(x, torch.float32, "x")

@@ -95,6 +95,30 @@ typedef struct {
 int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * General im2col-free convolution + FrozenBatchNorm affine (+ ReLU) over bf16 NHWC as an implicit GEMM on the persistent
+ * CTA-pair kernel: for filter tap (ky,kx) and 64-channel block the A tile is ONE 4-D TMA box of the input; a strided
+ * convolution samples every stride-th pixel through the TMA element strides, out-of-bounds coordinates are zero fill
+ * (= the padding).  No patch matrix is ever written.
+ *   x   : a (c, w, h, n) view given by extents (cin % 64 == 0, w_, h, n) and ELEMENT strides x_w_stride / x_h_stride /
+ *         x_n_stride (multiples of 8).  Plain NHWC: x_w_stride = cin, x_h_stride = cin*W, x_n_stride = cin*W*H.
+ *         x_w_stride < cin describes overlapping windows: the 7x7/2 stem convolution over a zero-padded [N,Hp,Wp,8] image
+ *         is kh = 7, kw = 1, cin = 64 (8 pixels x 8 channels = one 128-byte window), x_w_stride = 16 (two pixels),
+ *         stride_h = 2, stride_w = 1, pad = 0 (the padding is physically there) -- see sgf_nchw_f32_to_nhwc8_padded.
+ *   w   : [cout, kh*kw*cin] bf16, tap-major (ky, kx, c);   y : [n, ho, wo, cout] bf16 contiguous;   cout % 64 == 0
+ *   y[n,oh,ow,:] = act( scale * sum_{ky,kx,c} x[n, oh*stride_h + ky - pad_h, ow*stride_w + kx - pad_w, c] w[:,ky,kx,c] + bias )
+ * Replaces nn.Conv2d + FrozenBatchNorm2d (+ ReLU) at models/segofa/resnet.py:117-137 (3x3/1, 3x3/2), :161-170 (the 1x1/2
+ * downsample convolutions) and :189-213 (conv1 7x7/2).
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x; int32_t n, h, w_, cin;
+  int64_t x_w_stride, x_h_stride, x_n_stride;
+  const void* w; void* y; int32_t ho, wo, cout;
+  int32_t kh, kw, stride_h, stride_w, pad_h, pad_w;
+  const float* col_scale; const float* col_bias; int32_t act;
+} sgf_conv2d_args;
+int sgf_conv2d_nhwc(const sgf_conv2d_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Stem helpers (HBM-bound layout/gather kernels), models/segofa/resnet.py:215-220:
  *  - sgf_nchw_f32_to_nhwc_bf16: patch_images [N,3,H,W] fp32 -> [N,H,W,C] bf16
  *  - sgf_im2col_nhwc: explicit patch matrix for the few strided convs (7x7/2 conv1, the two
@@ -104,6 +128,10 @@ int sgf_conv3x3_s1_nhwc(const sgf_conv3x3_args* args, void* stream);
  *  - sgf_maxpool3x3s2_nhwc: nn.MaxPool2d(3,2,1)
  * ------------------------------------------------------------------------------------- */
 int sgf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
+/* patch_images [N,C<=8,H,W] fp32 -> zero-padded [N, hp, wp, 8] bf16 with the image at offset (pad, pad): channels C..7 and
+ * the border are written as zeros (the whole buffer is written, it needs no clearing) */
+int sgf_nchw_f32_to_nhwc8_padded(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad,
+                                 int32_t hp, int32_t wp, void* stream);
 int sgf_im2col_nhwc(const void* x, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t kh, int32_t kw,
                     int32_t stride, int32_t pad, int32_t ho, int32_t wo, int64_t ld_out, void* stream);
 int sgf_maxpool3x3s2_nhwc(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho,

@@ -48,6 +48,10 @@ class ReplayTap:
         elif kind == "conv3x3":
             snap.update(x=kw["x"].float().cpu(), w=kw["w"].float().cpu(), scale=kw["scale"].float().cpu(),
                         bias=kw["bias"].float().cpu(), act=kw["act"])
+        elif kind == "conv2d":
+            snap.update(x=kw["x"].float().cpu(), w=kw["w"].float().cpu(), scale=kw["scale"].float().cpu(),
+                        bias=kw["bias"].float().cpu(), act=kw["act"], kh=kw["kh"], kw=kw["kw"], stride=kw["stride"],
+                        pad=kw["pad"], window=kw["window"])
         elif kind == "attention":
             B, H, Tq, Tk = kw["B"], kw["H"], kw["Tq"], kw["Tk"]
             snap.update(B=B, H=H, Tq=Tq, Tk=Tk, causal=kw["causal"], o_strides=kw["o_strides"])
@@ -117,6 +121,23 @@ class ReplayTap:
             cin = s["x"].shape[-1]
             w4 = s["w"].reshape(s["w"].shape[0], 3, 3, cin)  # [Cout, ky, kx, Cin] (the engine keeps it as a [Cout, 9*Cin] matrix)
             y = F.conv2d(s["x"].permute(0, 3, 1, 2), w4.permute(0, 3, 1, 2), padding=1)
+            y = y * s["scale"].view(1, -1, 1, 1) + s["bias"].view(1, -1, 1, 1)
+            if s["act"] == ACT_RELU:
+                y = F.relu(y)
+            exp = y.permute(0, 2, 3, 1).to(torch.bfloat16).float()
+            rec.update(shape=tuple(exp.shape), rel_l2=_rel(out.float().cpu(), exp))
+        elif kind == "conv2d":
+            x, w, cout = s["x"], s["w"], s["w"].shape[0]
+            if s["window"] is None:
+                cin = x.shape[-1]
+                w4 = w.reshape(cout, s["kh"], s["kw"], cin)
+                y = F.conv2d(x.permute(0, 3, 1, 2), w4.permute(0, 3, 1, 2), stride=s["stride"], padding=s["pad"])
+            else:  # the 7x7/2 stem convolution: the kernel read a zero-padded 8-channel image as 8-pixel windows
+                H, W, pad, cin, kw_real = s["window"]
+                xl = x[:, pad:pad + H, pad:pad + W, :cin]
+                w4 = w.reshape(cout, s["kh"], 8, 8)[:, :, :kw_real, :cin]
+                assert w.reshape(cout, s["kh"], 8, 8)[:, :, kw_real:].abs().max() == 0 and x[..., cin:].abs().max() == 0
+                y = F.conv2d(xl.permute(0, 3, 1, 2), w4.permute(0, 3, 1, 2), stride=s["stride"], padding=pad)
             y = y * s["scale"].view(1, -1, 1, 1) + s["bias"].view(1, -1, 1, 1)
             if s["act"] == ACT_RELU:
                 y = F.relu(y)

@@ -40,7 +40,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_layouts_match_the_header(tmp_path):
     from ifseg_b200 import _lib
 
-    structs = {"sgf_gemm_args": _lib.GemmArgs, "sgf_conv3x3_args": _lib.Conv3x3Args, "sgf_rowln_args": _lib.RowLnArgs,
+    structs = {"sgf_gemm_args": _lib.GemmArgs, "sgf_conv3x3_args": _lib.Conv3x3Args, "sgf_conv2d_args": _lib.Conv2dArgs, "sgf_rowln_args": _lib.RowLnArgs,
                "sgf_relblock": _lib.RelBlock, "sgf_bias_args": _lib.BiasArgs, "sgf_attention_args": _lib.AttentionArgs,
                "sgf_segmask_args": _lib.SegmaskArgs, "sgf_segloss_args": _lib.SeglossArgs,
                "sgf_segloss_bwd_args": _lib.SeglossBwdArgs, "sgf_rowln_bwd_args": _lib.RowLnBwdArgs,

@@ -160,3 +160,55 @@ def test_ts_conv3x3(ops, n, h, w, cin, cout):
             out_t = ops.conv3x3_s1(x, wk, scale, bias, act=ops.ACT_RELU)
         assert _rel(out, ref) < 4e-3, (bn, _rel(out, ref))
         assert torch.equal(out, out_t), bn
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,stride,pad", [
+    (2, 60, 60, 128, 128, 3, 2, 1),    # layer2 block 0 conv2 (3x3/2)
+    (2, 120, 120, 256, 512, 1, 2, 0),  # layer2 downsample (1x1/2)
+    (1, 60, 60, 512, 1024, 1, 2, 0),   # layer3 downsample
+    (2, 30, 30, 256, 256, 3, 1, 1),    # 3x3/1 through the general entry
+    (1, 33, 17, 64, 128, 3, 2, 1),     # odd extents, ragged tiles
+    (3, 31, 45, 64, 64, 1, 2, 0),
+])
+def test_conv2d_strided_im2col_free(ops, n, h, w, cin, cout, k, stride, pad):
+    """Strided / padded convolutions read their input through TMA element strides: against F.conv2d."""
+    g = torch.Generator(device="cuda").manual_seed(n * h + cin + k)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(k * k * cin)).bfloat16()
+    scale = torch.rand(cout, device="cuda", generator=g) + 0.5
+    bias = torch.randn(cout, device="cuda", generator=g)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), stride=stride, padding=pad)
+    ref = ref * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    wk = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    for act in (ops.ACT_RELU, ops.ACT_NONE):
+        out = ops.conv2d(x, wk, scale, bias, kh=k, kw=k, stride=stride, pad=pad, act=act)
+        exp = (F.relu(ref) if act == ops.ACT_RELU else ref).permute(0, 2, 3, 1)
+        assert out.shape == exp.shape
+        assert _rel(out, exp) < 4e-3, _rel(out, exp)
+        # one storage rounding away from the fp32 result: elementwise within 1 bf16 ulp (+ accumulation noise)
+        assert (out.float() - exp).abs().max() <= 2e-2 * exp.abs().max()
+
+
+@pytest.mark.parametrize("n,H,W", [(2, 64, 48), (1, 480, 480), (2, 130, 70)])
+def test_conv1_7x7_stride2_window_mode(ops, n, H, W):
+    """conv1 of the stem: [N,3,H,W] fp32 -> zero-padded NHWC8 -> 7 filter-row taps of overlapping 128-byte windows."""
+    g = torch.Generator(device="cuda").manual_seed(H + W)
+    x = torch.randn(n, 3, H, W, device="cuda", generator=g)
+    wt = (torch.randn(64, 3, 7, 7, device="cuda", generator=g) / 12).bfloat16()
+    scale = torch.rand(64, device="cuda", generator=g) + 0.5
+    bias = torch.randn(64, device="cuda", generator=g)
+    pad = 3
+    hp, wp = H + 2 * pad, (W + 2 * pad + 8 + 7) // 8 * 8
+    xp = ops.nchw_to_nhwc8_padded(x, pad, hp, wp)
+    assert xp.shape == (n, hp, wp, 8)
+    assert torch.equal(xp[:, pad:pad + H, pad:pad + W, :3], x.permute(0, 2, 3, 1).bfloat16())
+    assert xp[..., 3:].abs().max() == 0 and xp[:, :pad].abs().max() == 0 and xp[:, :, :pad].abs().max() == 0
+    assert xp[:, pad + H:].abs().max() == 0 and xp[:, :, pad + W:].abs().max() == 0
+    wm = torch.zeros(64, 7, 8, 8, device="cuda")
+    wm[:, :, :7, :3] = wt.float().permute(0, 2, 3, 1)
+    out = ops.conv2d(xp, wm.reshape(64, 448).bfloat16().contiguous(), scale, bias, kh=7, kw=1, stride=2, act=ops.ACT_RELU,
+                     window=(H, W, pad, 3, 7))
+    ref = F.conv2d(x.bfloat16().float(), wt.float(), stride=2, padding=3)
+    ref = F.relu(ref * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    assert _rel(out, ref) < 4e-3, _rel(out, ref)

@@ -1,1 +1,2 @@
-for p in 1 2; do echo "== producers $p"; SGF_GEMM_TS_PRODUCERS=$p timeout 600 python tools/sweep_gemm_ts.py 2>&1 | grep "BN=256\|BN=384" | head -6; SGF_GEMM_TS_PRODUCERS=$p python bench.py --no-cpu-baseline --no-train-record 2>/dev/null | cut -c1-200; done
+timeout 900 python -m pytest tests/test_gemm_ts_gpu.py -q -x -k "conv" > gpurun_out/conv_tests.log 2>&1; echo "rc=$?" >> gpurun_out/conv_tests.log
+tail -30 gpurun_out/conv_tests.log
