@@ -192,7 +192,6 @@ EXPORTS = [
     ("sgf_conv2d_nhwc", C.c_int, [C.POINTER(Conv2dArgs), _vp]),
     ("sgf_nchw_f32_to_nhwc_bf16", C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     ("sgf_nchw_f32_to_nhwc8_padded", C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    ("sgf_im2col_nhwc", C.c_int, [_vp, _vp] + [_i32] * 10 + [_i64, _vp]),
     ("sgf_maxpool3x3s2_nhwc", C.c_int, [_vp, _vp] + [_i32] * 6 + [_vp]),
     ("sgf_row_layernorm", C.c_int, [C.POINTER(RowLnArgs), _vp]),
     ("sgf_build_attn_bias", C.c_int, [C.POINTER(BiasArgs), _vp]),

@@ -7,22 +7,24 @@
 //                sub-tiles of the online softmax (32 scores live at a time; the TMEM load of the second half runs
 //                under the arithmetic of the first)
 //   warp 4     : score issuer  -- one lane: Q/K/bias TMA loads and the S = Q K^T tcgen05.mma, up to two tiles ahead
-//   warp 5     : output issuer -- one lane: V TMA loads and the O += P V tcgen05.mma
+//   warp 5     : output issuer -- one lane: V TMA loads, the bias MMAs S += I * bias and the O += P V tcgen05.mma
 // What the r02 timeline and ablation measurements say (profiles/r02_attention_analysis.txt): the tile loop is bound by
-// the fixed per-tile hand-off latencies (mbarrier wake-ups, tcgen05.ld, fence.proxy.async, single-thread MMA issue:
-// ~1850 of ~2200 cycles per tile survive when ALL softmax arithmetic is removed), not by MUFU / FMA throughput and not
-// by the number of softmax warps (4, 8 per CTA measured: same time).  Hence: issuers split so S runs two tiles ahead of
-// the softmax instead of behind P V, P double-buffered so softmax(j+1) never waits for P V(j), 2-stage K/V rings.
+// the fixed per-tile hand-off latencies (mbarrier wake-ups, tcgen05.ld, fence.proxy.async, single-thread MMA issue at
+// ~70 clocks per tcgen05.mma: ~1850 of ~2200 cycles per tile survive when ALL softmax arithmetic is removed), not by
+// MUFU / FMA throughput and not by the number of softmax warps (4, 8 per CTA measured: same time).  Hence: issuers split
+// so S runs two tiles ahead of the softmax instead of behind P V, P double-buffered so softmax(j+1) never waits for
+// P V(j), 2-stage K/V rings, and the additive bias added by the tensor core instead of by the softmax threads.
 // Per 64-key tile j (all asynchronous, mbarrier hand-offs, nothing waits on the tensor core in line):
-//   S(j) = Q K(j)^T      tcgen05.mma M128 N64 K64 into one of two TMEM score buffers, issued one tile
-//                        ahead so it runs under the softmax of tile j-1
-//   softmax(j)           tcgen05.ld the row, + bias tile (TMA-staged, 128B swizzle), masks, running max
-//                        with LAZY rescaling (the accumulator is only touched when the row max grows by
-//                        more than 2^8), exp2, row sum; P(j) -> smem as bf16 in the swizzled K-major
-//                        layout the tensor core reads
+//   S(j) = Q K(j)^T      tcgen05.mma M128 N64 K64 into one of two TMEM score buffers (score issuer)
+//   S(j) += I bias(j)    the TMA-staged fp16 bias tile [128 queries x 64 keys] is the MN-major B operand of a K = 128
+//                        tcgen05.mma whose A operand is the fp16 identity kept in TMEM (1.0 * b is exact, fp32
+//                        accumulate): 8 MMAs issued by the output issuer once Q K^T has retired
+//   softmax(j)           tcgen05.ld the row, masks, running max with LAZY rescaling (the accumulator is only touched when
+//                        the row max grows by more than 2^8), exp2, row sum; P(j) -> smem as bf16 in the swizzled
+//                        K-major layout the tensor core reads
 //   O += P(j) V(j)       tcgen05.mma M128 N64 K64 accumulating in TMEM (V tile is the MN-major B operand)
-// K, V (2-stage rings), the FP16 bias tile and P are double-buffered: 112 KB of shared memory and 256 TMEM columns per
-// CTA keep two CTAs per SM.
+// K, V (2-stage rings), the fp16 bias tile and P are double-buffered: 112 KB of shared memory and 256 TMEM columns
+// (2 x 64 scores, 64 output, 64 identity) per CTA keep two CTAs per SM.
 #include <stdlib.h>
 #include <string.h>
 
@@ -68,7 +70,7 @@ struct AttnSmem {
 
 struct AttnBars {
   uint64_t q_full, k_full[kKvStages], k_empty[kKvStages], v_full[kKvStages], v_empty[kKvStages];
-  uint64_t s_full[2], s_empty[2], p_full[2], b_empty[2], o_done[2];  // s_full also carries the bias-tile bytes
+  uint64_t s_full[2], s_empty[2], p_full[2], b_full[2], b_empty[2], o_done[2], qk_done[2];
   uint32_t tmem_slot;
 };
 static_assert(sizeof(AttnBars) <= 256, "barrier block");
@@ -110,12 +112,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       mbar_init(&bars->v_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->s_full[i], p.bias ? 2 : 1);  // tcgen05.commit of S(j) (+ the expect_tx arrive of bias(j))
+      mbar_init(&bars->s_full[i], 1);  // tcgen05.commit of S(j) (scores AND bias MMAs)
       mbar_init(&bars->s_empty[i], kSoftmaxWarps);  // one arrival per softmax warp (lane 0 after __syncwarp)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->p_full[i], kSoftmaxWarps);
-      mbar_init(&bars->b_empty[i], kSoftmaxWarps);
+      mbar_init(&bars->b_full[i], 1);   // bias(j) tile landed (TMA)
+      mbar_init(&bars->b_empty[i], 1);  // tcgen05.commit: the bias MMAs of S(j) have read it
+      mbar_init(&bars->qk_done[i], 1);  // tcgen05.commit of Q K(j)^T: the output issuer may add the bias on top
       mbar_init(&bars->o_done[i], 1);  // P V(t) retired -> o_done[t & 1]
     }
     fence_mbar_init();
@@ -135,6 +139,27 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
   const uint32_t tmem_base = bars->tmem_slot;
   const uint32_t tmem_s = tmem_base;        // score ping-pong: columns [0,64) and [64,128)
   const uint32_t tmem_o = tmem_base + 128;  // output accumulator: columns [128,192)
+  const uint32_t tmem_i = tmem_base + 192;  // fp16 identity [128 x 128] as the A operand of the bias MMAs: columns [192,256)
+  if (p.bias) {
+    // The additive bias tile is added to the scores BY THE TENSOR CORE: S += I * bias(j) with I the fp16 identity kept in
+    // TMEM (1.0 * b is exact, fp32 accumulate), bias(j) the TMA-staged fp16 tile read as the MN-major B operand.  The
+    // softmax threads no longer read the bias (r01/r02a: 4 x LDS.128 + 32 conversions + 16 packed adds per thread and
+    // tile, 10 us of an 85 us launch by ablation).
+    if (warp < kSoftmaxWarps) {
+      const int r = warp * 32 + (tid & 31);  // row r: element k = r is 1.0 -> column r/2, low or high half
+      uint32_t v[32];
+#pragma unroll
+      for (int hb = 0; hb < 2; ++hb) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (hb * 32 + i == (r >> 1)) ? ((r & 1) ? 0x3C000000u : 0x00003C00u) : 0u;
+        tmem_st_32x32(tmem_i + (static_cast<uint32_t>(warp * 32) << 16) + hb * 32, v);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   pdl_wait();
 
   if (warp == kSoftmaxWarps) {
@@ -150,9 +175,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         mbar_expect_tx(&bars->k_full[st], AttnSmem::kKV);
         tma_load_4d(smem + AttnSmem::offK + st * AttnSmem::kKV, &tmK, &bars->k_full[st], 0, h, t * kKTile, b);
       };
-      auto load_bias = [&](int t) {  // completes on the same barrier as S(t): one wait per tile for the softmax warps
-        mbar_expect_tx(&bars->s_full[t & 1], AttnSmem::kBias);
-        tma_load_3d(smem + AttnSmem::offBias + (t & 1) * AttnSmem::kBias, &tmB, &bars->s_full[t & 1], t * kKTile, q0, h);
+      auto load_bias = [&](int t) {
+        mbar_expect_tx(&bars->b_full[t & 1], AttnSmem::kBias);
+        tma_load_3d(smem + AttnSmem::offBias + (t & 1) * AttnSmem::kBias, &tmB, &bars->b_full[t & 1], t * kKTile, q0, h);
       };
       mbar_expect_tx(&bars->q_full, AttnSmem::kQ);
       tma_load_4d(smem + AttnSmem::offQ, &tmQ, &bars->q_full, 0, h, q0, b);
@@ -164,6 +189,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       const uint64_t dq = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offQ));
 #pragma unroll 1
       for (int j = 0; j < n_kt; ++j) {
+        // ---- refill the K stage S(j-1) has released (its tcgen05.commit fired about a tile ago: no stall) ----
+        if (j >= 1 && j + 1 < n_kt) {
+          const int pj = j - 1, pst = pj % kKvStages;
+          mbar_wait(&bars->k_empty[pst], (pj / kKvStages) & 1);
+          load_k(j + 1);  // stage (j+1) % 2 == (j-1) % 2
+        }
         // ---- S(j) into score buffer j&1 (free once softmax(j-2) has read it) ----
         const int st = j % kKvStages;
         attn_trace(p, tslot, 0, j, 0);
@@ -177,18 +208,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k)
           umma_f16(tmem_s + (j & 1) * 64, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        umma_commit(&bars->s_full[j & 1]);
+        // with a bias the score buffer is completed by the OUTPUT issuer (S(j) += I * bias(j)): the twelve tcgen05.mma of a
+        // tile issued from one thread (~70 clocks each) made this thread the pace-setter of the whole CTA
+        umma_commit(p.bias ? &bars->qk_done[j & 1] : &bars->s_full[j & 1]);
         umma_commit(&bars->k_empty[st]);
         attn_trace(p, tslot, 0, j, 3);
-        // bias(j+1) goes into the buffer softmax(j-1) has consumed (it hands it back right after its row-max exchange)
+        // bias(j+1) goes into the buffer the bias MMAs of S(j-1) (output issuer) have read
         if (p.bias && j >= 1 && j + 1 < n_kt) {
-          mbar_wait(&bars->b_empty[(j + 1) & 1], ((j - 1) >> 1) & 1);
+          mbar_wait(&bars->b_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
           load_bias(j + 1);
-        }
-        // K(j+2) goes into the stage S(j) is reading
-        if (j + kKvStages < n_kt) {
-          mbar_wait(&bars->k_empty[st], (j / kKvStages) & 1);
-          load_k(j + kKvStages);
         }
       }
     }
@@ -202,8 +230,21 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         tma_load_4d(smem + AttnSmem::offV + st * AttnSmem::kKV, &tmV, &bars->v_full[st], 0, h, t * kKTile, b);
       };
       for (int t = 0; t < kKvStages && t < n_kt; ++t) load_v(t);
+      constexpr uint32_t idesc_bias = make_idesc_f16(kQTile, kKTile, 0, 1);  // A = identity (TMEM), B = bias tile, MN-major
+      auto add_bias = [&](int j) {  // S(j) += I * bias(j): 128 query rows = the contraction, 16 rows (2048 B) per K step
+        mbar_wait(&bars->b_full[j & 1], (j >> 1) & 1);
+        mbar_wait(&bars->qk_done[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t db = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offBias + (j & 1) * AttnSmem::kBias));
+#pragma unroll
+        for (int k = 0; k < kQTile / 16; ++k) umma_f16_ts(tmem_s + (j & 1) * 64, tmem_i + 8 * k, db + 128 * k, idesc_bias, 1u);
+        umma_commit(&bars->b_empty[j & 1]);
+        umma_commit(&bars->s_full[j & 1]);
+      };
+      if (p.bias) add_bias(0);
 #pragma unroll 1
       for (int t = 0; t < n_kt; ++t) {
+        if (p.bias && t + 1 < n_kt) add_bias(t + 1);  // the scores run one tile ahead of the probabilities
         const int st = t % kKvStages;
         attn_trace(p, tslot, 1, t, 0);
         mbar_wait(&bars->v_full[st], (t / kKvStages) & 1);
@@ -243,10 +284,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
 
 #pragma unroll 1
     for (int j = 0; j < n_kt; ++j) {
-      const uint8_t* bias_buf = smem + AttnSmem::offBias + (j & 1) * AttnSmem::kBias + rowl * 128;
       uint8_t* p_row = p_row0 + (j & 1) * AttnSmem::kP;
       if (trole >= 0) attn_trace(p, tslot, trole, j, 0);
-      mbar_wait(&bars->s_full[j & 1], (j >> 1) & 1);  // S(j) retired and bias(j) landed
+      mbar_wait(&bars->s_full[j & 1], (j >> 1) & 1);  // S(j) = Q K(j)^T + bias(j) retired
       tc_fence_after();
       if (trole >= 0) attn_trace(p, tslot, trole, j, 1);
       // keys of this tile a row may attend to: [0, lim) (tail of the sequence, causal diagonal)
@@ -258,38 +298,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         float s[32];
-        if (p.bias) {  // the swizzled smem reads of the fp16 bias tile overlap the TMEM load latency
-          uint4 bb[4];
+        tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            bb[c] = *reinterpret_cast<const uint4*>(bias_buf + ((static_cast<uint32_t>(4 * hf + c) ^ sw) << 4));
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {  // chunk c = columns 8c .. 8c+7 of this half
-            const uint32_t w[4] = {bb[c].x, bb[c].y, bb[c].z, bb[c].w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
-              const int col = 8 * c + 2 * q;
-              const float2 sv = add2(make_float2(__uint_as_float(acc[col]), __uint_as_float(acc[col + 1])), f);
-              s[col] = sv.x;
-              s[col + 1] = sv.y;
-            }
-          }
-        } else {
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(acc[i]);
-        }
+        for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(acc[i]);
         if (hf == 0) {
           tmem_ld_32x32(tmem_s + (j & 1) * 64 + 32 + lane_addr, acc);  // second half: in flight under the math below
-        } else {  // both halves of S(j) and of bias(j) are in registers: hand the buffers back
+        } else {  // both halves of S(j) are in registers: hand the score buffer back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&bars->s_empty[j & 1]);
-            if (p.bias) mbar_arrive(&bars->b_empty[j & 1]);
-          }
+          if (lane == 0) mbar_arrive(&bars->s_empty[j & 1]);
         }
         if (need_mask) {
           const int l2 = lim - hf * 32;

@@ -1,5 +1,5 @@
 // HBM-bound row / layout kernels: fused LayerNorm(+gather, +residual, +second LayerNorm),
-// attention rel-pos bias assembly, stem layout helpers (NCHW->NHWC, im2col for the few strided
+// attention rel-pos bias assembly, stem layout helpers (NCHW->NHWC, zero-padded NHWC8 for the 7x7/2 stem convolution; the strided
 // convolutions, max-pool).  Warp-shuffle reductions, 128-bit global accesses.
 #include <cuda_fp16.h>
 
@@ -529,86 +529,6 @@ __global__ void nchw_to_nhwc8_padded_kernel(const float* __restrict__ x, uint4* 
   y[pix] = o;
 }
 
-// generic im2col, one thread per (output pixel, tap, 8-channel group or single channel)
-template <bool kVec>
-__global__ void im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int n, int h,
-                              int w, int c, int kh, int kw, int stride, int pad, int ho, int wo, int64_t ld_out) {
-  const int cg = kVec ? c / 8 : c;
-  const int64_t total = static_cast<int64_t>(n) * ho * wo * kh * kw * cg;
-  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (idx >= total) return;
-  const int g = idx % cg;
-  int64_t t = idx / cg;
-  const int tap = t % (kh * kw);
-  t /= (kh * kw);
-  const int ox = t % wo;
-  t /= wo;
-  const int oy = t % ho;
-  const int img = t / ho;
-  const int ky = tap / kw, kx = tap % kw;
-  const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
-  const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
-  const int64_t orow = (static_cast<int64_t>(img) * ho + oy) * wo + ox;
-  if (kVec) {
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (ok) v = *reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(img) * h + iy) * w + ix) * c + g * 8);
-    *reinterpret_cast<uint4*>(out + orow * ld_out + static_cast<int64_t>(tap) * c + g * 8) = v;
-  } else {
-    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
-    if (ok) v = x[((static_cast<int64_t>(img) * h + iy) * w + ix) * c + g];
-    out[orow * ld_out + static_cast<int64_t>(tap) * c + g] = v;
-  }
-}
-
-// im2col for narrow channel counts (conv1: C = 3): one thread per (output pixel, ky) copies the
-// kw*C contiguous input elements of that filter row and pads the row to `pitch` (multiple of 8)
-// elements, so that every store is a 16-byte vector.  K index = ky*pitch + kx*C + c.
-__global__ void __launch_bounds__(256) im2col_rows_kernel(const __nv_bfloat16* __restrict__ x,
-                                                          __nv_bfloat16* __restrict__ out, int n, int h, int w, int c,
-                                                          int kh, int kw, int stride, int pad, int ho, int wo,
-                                                          int pitch, int64_t ld_out) {
-  const int64_t total = static_cast<int64_t>(n) * ho * wo * kh;
-  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (idx >= total) return;
-  const int ky = idx % kh;
-  int64_t t = idx / kh;
-  const int ox = t % wo;
-  t /= wo;
-  const int oy = t % ho;
-  const int img = t / ho;
-  const int iy = oy * stride - pad + ky;
-  const int ix0 = ox * stride - pad;
-  const bool row_ok = iy >= 0 && iy < h;
-  const __nv_bfloat16* src = x + (static_cast<int64_t>(img) * h + (row_ok ? iy : 0)) * w * c;
-  __nv_bfloat16* dst = out + ((static_cast<int64_t>(img) * ho + oy) * wo + ox) * ld_out + ky * pitch;
-  const int run = kw * c;
-  for (int e0 = 0; e0 < pitch; e0 += 8) {
-    uint32_t pk[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float lo = 0.f, hi = 0.f;
-      const int e = e0 + 2 * j;
-      if (row_ok && e < run) {
-        const int ix = ix0 + e / c;
-        if (ix >= 0 && ix < w) lo = __bfloat162float(src[ix * c + e % c]);
-      }
-      if (row_ok && e + 1 < run) {
-        const int ix = ix0 + (e + 1) / c;
-        if (ix >= 0 && ix < w) hi = __bfloat162float(src[ix * c + (e + 1) % c]);
-      }
-      pk[j] = pack_bf16x2(lo, hi);
-    }
-    *reinterpret_cast<uint4*>(dst + e0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  }
-}
-
-__global__ void zero_pad_cols_kernel(__nv_bfloat16* out, int64_t rows, int k_valid, int64_t ld_out) {
-  const int padw = static_cast<int>(ld_out) - k_valid;
-  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (idx >= rows * padw) return;
-  out[(idx / padw) * ld_out + k_valid + idx % padw] = __float2bfloat16_rn(0.f);
-}
-
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h,
                                     int w, int c, int ho, int wo) {
   const int cg = c / 8;
@@ -833,40 +753,6 @@ extern "C" int sgf_nchw_f32_to_nhwc8_padded(const float* x, void* y, int32_t n, 
       x, reinterpret_cast<uint4*>(y), n, c, h, w, pad, hp, wp);
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
-  return SGF_OK;
-}
-
-extern "C" int sgf_im2col_nhwc(const void* x, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t kh,
-                               int32_t kw, int32_t stride, int32_t pad, int32_t ho, int32_t wo, int64_t ld_out,
-                               void* stream) {
-  SGF_REQUIRE(x && out, "im2col: null pointer");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool vec = (c % 8) == 0;
-  const int pitch = vec ? kw * c : (kw * c + 7) / 8 * 8;  // elements per filter row in the patch matrix
-  const int k_valid = kh * pitch;
-  SGF_REQUIRE(ld_out >= k_valid && ld_out % 8 == 0, "im2col: ld_out=%lld must be >= %d and a multiple of 8",
-              (long long)ld_out, k_valid);
-  const int64_t rows = static_cast<int64_t>(n) * ho * wo;
-  if (vec) {
-    const int64_t total = rows * kh * kw * (c / 8);
-    im2col_kernel<true><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c, kh, kw, stride,
-        pad, ho, wo, ld_out);
-  } else {
-    const int64_t total = rows * kh;
-    im2col_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), n, h, w, c, kh, kw, stride,
-        pad, ho, wo, pitch, ld_out);
-  }
-  SGF_CHECK_CUDA(cudaGetLastError());
-  count_launch();
-  if (ld_out > k_valid) {
-    const int64_t tp = rows * (ld_out - k_valid);
-    zero_pad_cols_kernel<<<static_cast<unsigned>((tp + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<__nv_bfloat16*>(out), rows, k_valid, ld_out);
-    SGF_CHECK_CUDA(cudaGetLastError());
-    count_launch();
-  }
   return SGF_OK;
 }
 

@@ -235,28 +235,6 @@ def nchw_to_nhwc_bf16(x):
     return y
 
 
-def im2col_pitch(kw, c):
-    """elements per filter row of the patch matrix (kw*c rounded up to a multiple of 8)."""
-    return kw * c if c % 8 == 0 else (kw * c + 7) // 8 * 8
-
-
-def im2col(x, kh, kw, stride, pad, ld_out=None):
-    """x [N,H,W,C] bf16 -> ([N*Ho*Wo, ld_out] bf16, Ho, Wo); K index = ky*pitch + kx*C + c with
-    pitch = im2col_pitch(kw, C)."""
-    lib = _lib.load()
-    _req(x, torch.bfloat16, "x")
-    n, h, w, c = x.shape
-    ho = (h + 2 * pad - kh) // stride + 1
-    wo = (w + 2 * pad - kw) // stride + 1
-    k = kh * im2col_pitch(kw, c)
-    ld_out = k if ld_out is None else ld_out
-    out = torch.empty((n * ho * wo, ld_out), dtype=torch.bfloat16, device=x.device)
-    with _timed("im2col", nbytes=out.numel() * 2.0 + x.numel() * 2.0):
-        _lib.check(lib.sgf_im2col_nhwc(_p(x), _p(out), n, h, w, c, kh, kw, stride, pad, ho, wo, ld_out, _stream()),
-                   "sgf_im2col_nhwc")
-    return out, ho, wo
-
-
 def maxpool3x3s2(x):
     lib = _lib.load()
     _req(x, torch.bfloat16, "x")

@@ -121,10 +121,8 @@ int sgf_conv2d_nhwc(const sgf_conv2d_args* args, void* stream);
 /* ---------------------------------------------------------------------------------------
  * Stem helpers (HBM-bound layout/gather kernels), models/segofa/resnet.py:215-220:
  *  - sgf_nchw_f32_to_nhwc_bf16: patch_images [N,3,H,W] fp32 -> [N,H,W,C] bf16
- *  - sgf_im2col_nhwc: explicit patch matrix for the few strided convs (7x7/2 conv1, the two
- *    3x3/2 convs, the 1x1/2 downsample convs): out [N*Ho*Wo, ld_out] with K index
- *    ky*pitch + kx*C + c where pitch = kw*C rounded up to a multiple of 8 (C % 8 == 0: no
- *    padding; conv1, C = 3: pitch 24), zero padded inside each filter row and up to ld_out
+ *  - sgf_nchw_f32_to_nhwc8_padded: the input layout of the im2col-free 7x7/2 conv1 (sgf_conv2d_nhwc window mode)
+ *    (no patch matrix is written anywhere on the path: the r01 sgf_im2col_nhwc entry point is gone)
  *  - sgf_maxpool3x3s2_nhwc: nn.MaxPool2d(3,2,1)
  * ------------------------------------------------------------------------------------- */
 int sgf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
@@ -132,8 +130,6 @@ int sgf_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int
  * the border are written as zeros (the whole buffer is written, it needs no clearing) */
 int sgf_nchw_f32_to_nhwc8_padded(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad,
                                  int32_t hp, int32_t wp, void* stream);
-int sgf_im2col_nhwc(const void* x, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t kh, int32_t kw,
-                    int32_t stride, int32_t pad, int32_t ho, int32_t wo, int64_t ld_out, void* stream);
 int sgf_maxpool3x3s2_nhwc(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ho,
                           int32_t wo, void* stream);
 

@@ -107,25 +107,9 @@ def test_stem_helpers(ops):
     x = torch.randn(2, 3, 64, 48, device="cuda", generator=g)
     y = ops.nchw_to_nhwc_bf16(x)
     assert torch.equal(y, x.permute(0, 2, 3, 1).bfloat16())
-    # 7x7/2 im2col + GEMM == conv1 (filter rows padded 21 -> 24 elements)
-    wt = (torch.randn(64, 3, 7, 7, device="cuda", generator=g) / 12).bfloat16()
-    cols, ho, wo = ops.im2col(y, 7, 7, 2, 3)
-    assert (ho, wo) == (32, 24) and cols.shape[1] == 168
-    wmat = torch.zeros(64, 7, 24, device="cuda", dtype=torch.bfloat16)
-    wmat[:, :, :21] = wt.permute(0, 2, 3, 1).reshape(64, 7, 21)
-    out = ops.gemm(cols, wmat.view(64, 168), out_dtype=torch.float32).view(2, ho, wo, 64)
-    ref = F.conv2d(y.float().permute(0, 3, 1, 2), wt.float(), stride=2, padding=3).permute(0, 2, 3, 1)
-    assert _rel(out, ref) < 2e-5
-    # 3x3/2 im2col (vector path)
+    # (the strided convolutions and conv1 are im2col-free: tests/test_gemm_ts_gpu.py::test_conv2d_strided_im2col_free,
+    #  ::test_conv1_7x7_stride2_window_mode)
     x2 = torch.randn(2, 20, 20, 64, device="cuda", generator=g).bfloat16()
-    w2 = (torch.randn(128, 64, 3, 3, device="cuda", generator=g) / 24).bfloat16()
-    cols, ho, wo = ops.im2col(x2, 3, 3, 2, 1)
-    out = ops.gemm(cols, w2.permute(0, 2, 3, 1).reshape(128, 576).contiguous(), out_dtype=torch.float32)
-    ref = F.conv2d(x2.float().permute(0, 3, 1, 2), w2.float(), stride=2, padding=1).permute(0, 2, 3, 1)
-    assert _rel(out.view(2, ho, wo, 128), ref) < 2e-5
-    # 1x1/2 "im2col" = strided subsample
-    cols, ho, wo = ops.im2col(x2, 1, 1, 2, 0)
-    assert torch.equal(cols.view(2, ho, wo, 64), x2[:, ::2, ::2])
     # maxpool
     mp = ops.maxpool3x3s2(x2)
     ref = F.max_pool2d(x2.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).bfloat16()

@@ -1,9 +1,12 @@
 set -x
 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -8 gpurun_out/pytest_gpu.log
-python bench.py --no-cpu-baseline --no-train-record > gpurun_out/bench_a.json 2> gpurun_out/bench_a.err; cut -c1-330 gpurun_out/bench_a.json
+tail -6 gpurun_out/pytest_gpu.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_new.json 2> gpurun_out/bench_new.err; echo "bench rc=$?"
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/bench_a.json'))
-print(d['kernel_families'])
+d=json.load(open('gpurun_out/bench_new.json'))
+print(d['ms_per_step'], d['value'], d['e2e']['value'])
+print(d['roofline']['frac'], d['roofline']['attention'], d['roofline']['step'])
+print(d['parity']); print(d['gpu_eager_context']); print(d['cpu_baseline']['value'])
+print(d['train_step']['ms_per_step'], d['train_step']['value'])
 PY
