@@ -7,7 +7,8 @@
 //                sub-tiles of the online softmax (32 scores live at a time; the TMEM load of the second half runs
 //                under the arithmetic of the first)
 //   warp 4     : score issuer  -- one lane: Q/K/bias TMA loads and the S = Q K^T tcgen05.mma, up to two tiles ahead
-//   warp 5     : output issuer -- one lane: V TMA loads, the bias MMAs S += I * bias and the O += P V tcgen05.mma
+//   warp 5     : output issuer -- one lane: V TMA loads, half of the bias MMAs S += I * bias (the score issuer issues the
+//                other half) and the O += P V tcgen05.mma
 // What the r02 timeline and ablation measurements say (profiles/r02_attention_analysis.txt): the tile loop is bound by
 // the fixed per-tile hand-off latencies (mbarrier wake-ups, tcgen05.ld, fence.proxy.async, single-thread MMA issue at
 // ~70 clocks per tcgen05.mma: ~1850 of ~2200 cycles per tile survive when ALL softmax arithmetic is removed), not by
@@ -18,7 +19,7 @@
 //   S(j) = Q K(j)^T      tcgen05.mma M128 N64 K64 into one of two TMEM score buffers (score issuer)
 //   S(j) += I bias(j)    the TMA-staged fp16 bias tile [128 queries x 64 keys] is the MN-major B operand of a K = 128
 //                        tcgen05.mma whose A operand is the fp16 identity kept in TMEM (1.0 * b is exact, fp32
-//                        accumulate): 8 MMAs issued by the output issuer once Q K^T has retired
+//                        accumulate): 8 MMAs, four per issuing thread
 //   softmax(j)           tcgen05.ld the row, masks, running max with LAZY rescaling (the accumulator is only touched when
 //                        the row max grows by more than 2^8), exp2, row sum; P(j) -> smem as bf16 in the swizzled
 //                        K-major layout the tensor core reads
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         mbar_expect_tx(&bars->k_full[st], AttnSmem::kKV);
         tma_load_4d(smem + AttnSmem::offK + st * AttnSmem::kKV, &tmK, &bars->k_full[st], 0, h, t * kKTile, b);
       };
+      constexpr uint32_t idesc_bias = make_idesc_f16(kQTile, kKTile, 0, 1);  // A = identity (TMEM), B = bias tile, MN-major
       auto load_bias = [&](int t) {
         mbar_expect_tx(&bars->b_full[t & 1], AttnSmem::kBias);
         tma_load_3d(smem + AttnSmem::offBias + (t & 1) * AttnSmem::kBias, &tmB, &bars->b_full[t & 1], t * kKTile, q0, h);
@@ -208,8 +210,17 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k)
           umma_f16(tmem_s + (j & 1) * 64, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        // with a bias the score buffer is completed by the OUTPUT issuer (S(j) += I * bias(j)): the twelve tcgen05.mma of a
-        // tile issued from one thread (~70 clocks each) made this thread the pace-setter of the whole CTA
+        // With a bias the score buffer is completed by S(j) += I * bias(j) (8 more MMAs, K = 128 query rows).  Twelve
+        // tcgen05.mma per tile from ONE thread (~70 clocks each, plus ~150 per mbarrier wait) made that thread the
+        // pace-setter of the whole CTA, whichever issuer it was: the bias MMAs are split, K steps 0..3 here, 4..7 on the
+        // output issuer once these have retired (qk_done).
+        if (p.bias) {
+          mbar_wait(&bars->b_full[j & 1], (j >> 1) & 1);
+          tc_fence_after();
+          const uint64_t db = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offBias + (j & 1) * AttnSmem::kBias));
+#pragma unroll
+          for (int k = 0; k < kQTile / 32; ++k) umma_f16_ts(tmem_s + (j & 1) * 64, tmem_i + 8 * k, db + 128 * k, idesc_bias, 1u);
+        }
         umma_commit(p.bias ? &bars->qk_done[j & 1] : &bars->s_full[j & 1]);
         umma_commit(&bars->k_empty[st]);
         attn_trace(p, tslot, 0, j, 3);
@@ -231,13 +242,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
       };
       for (int t = 0; t < kKvStages && t < n_kt; ++t) load_v(t);
       constexpr uint32_t idesc_bias = make_idesc_f16(kQTile, kKTile, 0, 1);  // A = identity (TMEM), B = bias tile, MN-major
-      auto add_bias = [&](int j) {  // S(j) += I * bias(j): 128 query rows = the contraction, 16 rows (2048 B) per K step
-        mbar_wait(&bars->b_full[j & 1], (j >> 1) & 1);
-        mbar_wait(&bars->qk_done[j & 1], (j >> 1) & 1);
+      auto add_bias = [&](int j) {  // second half of S(j) += I * bias(j): query rows 64..127 of the contraction
+        mbar_wait(&bars->qk_done[j & 1], (j >> 1) & 1);  // Q K^T and the first half have retired (the bias tile has landed)
         tc_fence_after();
         const uint64_t db = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offBias + (j & 1) * AttnSmem::kBias));
 #pragma unroll
-        for (int k = 0; k < kQTile / 16; ++k) umma_f16_ts(tmem_s + (j & 1) * 64, tmem_i + 8 * k, db + 128 * k, idesc_bias, 1u);
+        for (int k = kQTile / 32; k < kQTile / 16; ++k) umma_f16_ts(tmem_s + (j & 1) * 64, tmem_i + 8 * k, db + 128 * k, idesc_bias, 1u);
         umma_commit(&bars->b_empty[j & 1]);
         umma_commit(&bars->s_full[j & 1]);
       };

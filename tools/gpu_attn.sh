@@ -2,4 +2,3 @@ timeout 900 python -m pytest tests/test_ops_gpu.py -q -x -k "attention" > gpurun
 tail -3 gpurun_out/attn_tests.log
 timeout 600 python tools/bench_attn.py > gpurun_out/bench_attn.log 2>&1
 tail -20 gpurun_out/bench_attn.log | cut -c1-110
-timeout 300 python tools/trace_attn.py > gpurun_out/trace_attn2.log 2>&1
