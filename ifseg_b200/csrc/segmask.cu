@@ -120,6 +120,85 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(const SegmaskParam
   }
 }
 
+// Four horizontally adjacent pixels per thread.  The scalar kernel above is LSU-bound for wide class counts (4 loads per
+// class and pixel: 325 us at C = 150, 8 x 480^2).  At an upsampling factor >= 4 the four pixels of a thread see at most
+// two adjacent tap-column pairs, (xa, xa+1) or (xa+1, xa+2): six loads per class serve four pixels, and every pixel still
+// runs exactly the per-pixel rounding sequence of the scalar kernel (lerp4<kArith>), so the masks are bit-identical.
+template <int kArith>
+__global__ void __launch_bounds__(128) upsample_argmax4_kernel(const SegmaskParams p) {
+  extern __shared__ float hist[];  // [3][C] when histograms are requested
+  const bool want_hist = p.area_pred != nullptr;
+  if (want_hist) {
+    for (int i = threadIdx.x; i < 3 * p.C; i += blockDim.x) hist[i] = 0.f;
+    __syncthreads();
+  }
+  const int xq = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  if (xq < p.w) {
+    int y0, y1;
+    float hl0, hl1;
+    src_index<kArith>(p.scale_h, y, p.hp, y0, y1, hl0, hl1);
+    int x0[4], x1[4];
+    float wl0[4], wl1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) src_index<kArith>(p.scale_w, min(xq + i, p.w - 1), p.wp, x0[i], x1[i], wl0[i], wl1[i]);
+    const int xa = x0[0], xb = min(xa + 1, p.wp - 1), xc = min(xa + 2, p.wp - 1);
+    bool sel[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sel[i] = x0[i] != xa;  // then x0 == xa + 1 (== xb) and x1 == xc
+    const float* base = p.logits + static_cast<int64_t>(b) * p.batch_stride;
+    const float* qa0 = base + static_cast<int64_t>(y0 * p.wp + xa) * p.tok_stride;
+    const float* qb0 = base + static_cast<int64_t>(y0 * p.wp + xb) * p.tok_stride;
+    const float* qc0 = base + static_cast<int64_t>(y0 * p.wp + xc) * p.tok_stride;
+    const float* qa1 = base + static_cast<int64_t>(y1 * p.wp + xa) * p.tok_stride;
+    const float* qb1 = base + static_cast<int64_t>(y1 * p.wp + xb) * p.tok_stride;
+    const float* qc1 = base + static_cast<int64_t>(y1 * p.wp + xc) * p.tok_stride;
+    float best[4];
+    int best_c[4] = {0, 0, 0, 0};
+#pragma unroll 2
+    for (int c = 0; c < p.C; ++c) {
+      const float a0 = __ldg(qa0 + c), b0 = __ldg(qb0 + c), c0 = __ldg(qc0 + c);
+      const float a1 = __ldg(qa1 + c), b1 = __ldg(qb1 + c), c1 = __ldg(qc1 + c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float v = lerp4<kArith>(hl0, hl1, wl0[i], wl1[i], sel[i] ? b0 : a0, sel[i] ? c0 : b0, sel[i] ? b1 : a1,
+                                      sel[i] ? c1 : b1);
+        if (c == 0 || v > best[i]) {  // first maximum wins, NaN-free inputs assumed
+          best[i] = v;
+          best_c[i] = c;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (xq + i >= p.w) break;
+      const int64_t pix = (static_cast<int64_t>(b) * p.h + y) * p.w + xq + i;
+      p.mask[pix] = best_c[i];
+      if (want_hist) {
+        bool counted = true;
+        if (p.target) {
+          const int64_t t = p.target[pix];
+          counted = t >= 0 && t < p.C;  // ignored pixels (pad / "unknown") contribute to nothing
+          if (counted) {
+            atomicAdd(&hist[2 * p.C + static_cast<int>(t)], 1.f);
+            if (t == best_c[i]) atomicAdd(&hist[best_c[i]], 1.f);
+          }
+        }
+        if (counted) atomicAdd(&hist[p.C + best_c[i]], 1.f);
+      }
+    }
+  }
+  if (want_hist) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+      if (p.area_intersect && hist[i] != 0.f) atomicAdd(&p.area_intersect[i], hist[i]);
+      if (hist[p.C + i] != 0.f) atomicAdd(&p.area_pred[i], hist[p.C + i]);
+      if (p.area_label && hist[2 * p.C + i] != 0.f) atomicAdd(&p.area_label[i], hist[2 * p.C + i]);
+    }
+  }
+}
+
 struct SeglossParams {
   const float* logits;
   int64_t batch_stride, tok_stride;
@@ -188,6 +267,96 @@ __global__ void __launch_bounds__(256) upsample_ce_loss_kernel(const SeglossPara
   }
 }
 
+
+// Four pixels per thread, same tap sharing as upsample_argmax4_kernel; the online logsumexp costs ONE exponential per
+// class and pixel (exp(min(m, v) - max(m, v)); the other term of the textbook update is exp(0) = 1 exactly).
+__global__ void __launch_bounds__(128) upsample_ce_loss4_kernel(const SeglossParams p) {
+  __shared__ float red[2][4];
+  const int xq = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z;
+  float loss = 0.f, cnt = 0.f;
+  if (xq < p.w) {
+    int64_t tg[4];
+    bool live[4], any = false;
+    const int64_t pix0 = (static_cast<int64_t>(b) * p.h + y) * p.w + xq;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      tg[i] = xq + i < p.w ? p.target[pix0 + i] : -1;
+      live[i] = tg[i] >= 0 && tg[i] < p.C;
+      any |= live[i];
+    }
+    if (any) {
+      int y0, y1;
+      float hl0, hl1;
+      src_index(p.scale_h, y, p.hp, y0, y1, hl0, hl1);
+      int x0[4], x1[4];
+      float wl0[4], wl1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) src_index(p.scale_w, min(xq + i, p.w - 1), p.wp, x0[i], x1[i], wl0[i], wl1[i]);
+      const int xa = x0[0], xb = min(xa + 1, p.wp - 1), xc = min(xa + 2, p.wp - 1);
+      bool sel[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sel[i] = x0[i] != xa;
+      const float* base = p.logits + static_cast<int64_t>(b) * p.batch_stride;
+      const float* qa0 = base + static_cast<int64_t>(y0 * p.wp + xa) * p.tok_stride;
+      const float* qb0 = base + static_cast<int64_t>(y0 * p.wp + xb) * p.tok_stride;
+      const float* qc0 = base + static_cast<int64_t>(y0 * p.wp + xc) * p.tok_stride;
+      const float* qa1 = base + static_cast<int64_t>(y1 * p.wp + xa) * p.tok_stride;
+      const float* qb1 = base + static_cast<int64_t>(y1 * p.wp + xb) * p.tok_stride;
+      const float* qc1 = base + static_cast<int64_t>(y1 * p.wp + xc) * p.tok_stride;
+      float m[4], ssum[4], vt[4], vsum[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        m[i] = -INFINITY;
+        ssum[i] = vt[i] = vsum[i] = 0.f;
+      }
+#pragma unroll 2
+      for (int c = 0; c < p.C; ++c) {
+        const float a0 = __ldg(qa0 + c), b0 = __ldg(qb0 + c), c0 = __ldg(qc0 + c);
+        const float a1 = __ldg(qa1 + c), b1 = __ldg(qb1 + c), c1 = __ldg(qc1 + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float top = __fadd_rn(__fmul_rn(wl0[i], sel[i] ? b0 : a0), __fmul_rn(wl1[i], sel[i] ? c0 : b0));
+          const float bot = __fadd_rn(__fmul_rn(wl0[i], sel[i] ? b1 : a1), __fmul_rn(wl1[i], sel[i] ? c1 : b1));
+          const float v = __fadd_rn(__fmul_rn(hl0, top), __fmul_rn(hl1, bot));
+          if (c == tg[i]) vt[i] = v;
+          vsum[i] += v;
+          const bool up = v > m[i];
+          const float e = __expf(fminf(m[i], v) - fmaxf(m[i], v));
+          ssum[i] = up ? fmaf(ssum[i], e, 1.0f) : ssum[i] + e;
+          m[i] = fmaxf(m[i], v);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (!live[i]) continue;
+        const float lse = m[i] + __logf(ssum[i]);
+        if (p.lse_out) p.lse_out[pix0 + i] = lse;
+        loss += (1.f - p.eps) * (lse - vt[i]) + p.eps * (lse - vsum[i] / static_cast<float>(p.C));
+        cnt += 1.f;
+      }
+    }
+  }
+  loss = warp_sum(loss);
+  cnt = warp_sum(cnt);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[0][warp] = loss;
+    red[1][warp] = cnt;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    loss = lane < 4 ? red[0][lane] : 0.f;
+    cnt = lane < 4 ? red[1][lane] : 0.f;
+    loss = warp_sum(loss);
+    cnt = warp_sum(cnt);
+    if (lane == 0 && cnt > 0.f) {
+      atomicAdd(&p.out[0], loss);
+      atomicAdd(&p.out[1], cnt);
+    }
+  }
+}
 
 // ----------------------------------------------------------------------------------------
 // adjoint of upsample + pixel cross-entropy w.r.t. the low-resolution logits (gather form)
@@ -575,8 +744,13 @@ extern "C" int sgf_upsample_ce_loss(const sgf_segloss_args* a, void* stream) {
   SeglossParams p{a->logits, a->batch_stride, a->tok_stride, a->B, a->C, a->hp, a->wp, a->h, a->w, a->target,
                   a->label_smoothing, a->out, static_cast<float>(a->hp) / static_cast<float>(a->h),
                   static_cast<float>(a->wp) / static_cast<float>(a->w), a->lse_out};
-  dim3 block(256), grid((a->w + 255) / 256, a->h, a->B);
-  upsample_ce_loss_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  if (p.scale_w <= 0.25f) {  // upsampling factor >= 4: four pixels per thread share their tap columns
+    dim3 block(128), grid((a->w + 511) / 512, a->h, a->B);
+    upsample_ce_loss4_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  } else {
+    dim3 block(256), grid((a->w + 255) / 256, a->h, a->B);
+    upsample_ce_loss_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  }
   SGF_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return SGF_OK;
@@ -599,6 +773,23 @@ extern "C" int sgf_upsample_argmax(const sgf_segmask_args* a, void* stream) {
   if (mode == SGF_LERP_DEFAULT) mode = a->C >= 16 ? SGF_LERP_ATEN_CUDA_NHWC : SGF_LERP_ATEN_CUDA;
   SGF_REQUIRE(mode == SGF_LERP_PLAIN || (mode >= 8 && mode < 16), "upsample_argmax: unknown arith mode %d", mode);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p.scale_w <= 0.25f) {  // upsampling factor >= 4: four pixels per thread share their tap columns (bit-identical masks)
+    dim3 block4(128), grid4((a->w + 511) / 512, a->h, a->B);
+    switch (mode) {
+      case 0: upsample_argmax4_kernel<kArithPlain><<<grid4, block4, smem, st>>>(p); break;
+      case 8: upsample_argmax4_kernel<kArithFma + 0><<<grid4, block4, smem, st>>>(p); break;
+      case 9: upsample_argmax4_kernel<kArithFma + 1><<<grid4, block4, smem, st>>>(p); break;
+      case 10: upsample_argmax4_kernel<kArithFma + 2><<<grid4, block4, smem, st>>>(p); break;
+      case 11: upsample_argmax4_kernel<kArithFma + 3><<<grid4, block4, smem, st>>>(p); break;
+      case 12: upsample_argmax4_kernel<kArithFma + 4><<<grid4, block4, smem, st>>>(p); break;
+      case 13: upsample_argmax4_kernel<kArithFma + 5><<<grid4, block4, smem, st>>>(p); break;
+      case 14: upsample_argmax4_kernel<kArithFma + 6><<<grid4, block4, smem, st>>>(p); break;
+      default: upsample_argmax4_kernel<kArithFma + 7><<<grid4, block4, smem, st>>>(p); break;
+    }
+    SGF_CHECK_CUDA(cudaGetLastError());
+    count_launch();
+    return SGF_OK;
+  }
   switch (mode) {
     case 0: upsample_argmax_kernel<kArithPlain><<<grid, block, smem, st>>>(p); break;
     case 8: upsample_argmax_kernel<kArithFma + 0><<<grid, block, smem, st>>>(p); break;
