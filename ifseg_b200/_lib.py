@@ -186,6 +186,8 @@ EXPORTS = [
     ("sgf_abi_version", C.c_int, []),
     ("sgf_launch_count", _i64, []),
     ("sgf_reset_launch_count", None, []),
+    ("sgf_debug_set_gemm_trace", None, [_vp]),
+    ("sgf_debug_set_attention_trace", None, [_vp]),
     ("sgf_gemm_bf16", C.c_int, [C.POINTER(GemmArgs), _vp]),
     ("sgf_gemm_bf16_ex", C.c_int, [C.POINTER(GemmArgs), _i32, _i32, _i32, _vp]),
     ("sgf_conv3x3_s1_nhwc", C.c_int, [C.POINTER(Conv3x3Args), _vp]),

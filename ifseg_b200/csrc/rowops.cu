@@ -1,6 +1,8 @@
 // HBM-bound row / layout kernels: fused LayerNorm(+gather, +residual, +second LayerNorm),
 // attention rel-pos bias assembly, stem layout helpers (NCHW->NHWC, zero-padded NHWC8 for the 7x7/2 stem convolution; the strided
 // convolutions, max-pool).  Warp-shuffle reductions, 128-bit global accesses.
+#include <stdlib.h>
+
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -649,7 +651,8 @@ extern "C" int sgf_row_layernorm(const sgf_rowln_args* a, void* stream) {
     const int nc = (a->D + 255) / 256;
     const int ngrp = (a->rows + 3) / 4;
     const int resident = 148 * (nc <= 3 ? 5 : 3);
-    const dim3 grid(ngrp < resident ? ngrp : resident), block(128);
+    static const int grid_policy = getenv("SGF_LN_GRID") ? atoi(getenv("SGF_LN_GRID")) : 0;  // A/B: 1 = one CTA per 4 rows
+    const dim3 grid(grid_policy == 1 ? ngrp : (ngrp < resident ? ngrp : resident)), block(128);
     switch (nc) {
       case 1: SGF_CHECK_CUDA(launch_pdl(row_layernorm_reg_kernel<1>, grid, block, size_t(0), st, p)); break;
       case 2: SGF_CHECK_CUDA(launch_pdl(row_layernorm_reg_kernel<2>, grid, block, size_t(0), st, p)); break;

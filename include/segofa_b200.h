@@ -31,6 +31,15 @@ int sgf_abi_version(void);
 /* number of kernels launched by this library in the calling process since load / last reset */
 int64_t sgf_launch_count(void);
 void sgf_reset_launch_count(void);
+/* Debug / measurement hooks (not on the product path; NULL switches them off again):
+ *  - sgf_debug_set_gemm_trace: the next sgf_gemm_bf16 / sgf_conv* launches taken by the persistent CTA-pair kernel record a
+ *    %globaltimer timeline of their first and last cluster into buf (2 x 8 roles x 64 events of uint64; tools/trace_gemm.py)
+ *  - sgf_debug_set_attention_trace: sgf_attention_bf16 records a clock64 timeline of four CTAs into buf
+ *    (4 x 4 roles x 32 tiles x 4 events of uint64; tools/trace_attn.py)
+ * Environment switches read at launch time: SGF_GEMM_FAMILY = tile | ts, SGF_GEMM_TS_BN = 64..384, SGF_GEMM_TS_PRODUCERS = 1 | 2
+ * (A/B measurements, tools/bench_gemm.py), SGF_NO_PDL (plain stream order instead of programmatic dependent launch). */
+void sgf_debug_set_gemm_trace(void* buf);
+void sgf_debug_set_attention_trace(void* buf);
 
 /* ---------------------------------------------------------------------------------------
  * Dense contraction  C[z] = epilogue( A[z] (MxK, K-major) * B[z]^T (NxK, K-major) )

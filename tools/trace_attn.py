@@ -17,8 +17,6 @@ bias[:, :, :T] = torch.randn(H, T, T, device="cuda", generator=g)
 bias = bias.half()
 out = torch.empty(B, T, D, device="cuda", dtype=torch.bfloat16)
 lib = _lib.load()
-lib.sgf_debug_set_attention_trace.argtypes = [C.c_void_p]
-lib.sgf_debug_set_attention_trace.restype = None
 
 
 def run(use_bias):

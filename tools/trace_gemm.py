@@ -10,8 +10,6 @@ from ifseg_b200 import _lib, ops
 
 os.environ["SGF_GEMM_FAMILY"] = "ts"
 lib = _lib.load()
-lib.sgf_debug_set_gemm_trace.argtypes = [C.c_void_p]
-lib.sgf_debug_set_gemm_trace.restype = None
 g = torch.Generator(device="cuda").manual_seed(0)
 ROLES = ["cta (start, prologue done, pdl_wait done, wg0 last store read, exit)", "producer A: k-block issue",
          "mma: k-block operands landed", "mma: tile committed", "epilogue wg0: box store issued", "-",
