@@ -198,11 +198,8 @@ class SegCriterion(FairseqCriterion):
             self.iter = self.criterion_update_freq * update_num - 1
             self._lazy_initialization(sample, model, ema_model)
         self._update_iteration()
-        if model.training and not self.unsupervised_segmentation:
-            raise NotImplementedError("segofa_b200 trains the image-free branch only (--unsupervised-segmentation=true, "
-                                      "every shipped recipe); the supervised real-image loss has no backward")
         ntokens = 1  # compute_loss returns ntokens = 1 (:345)
-        if model.training:  # seg_criterion.py:178-186
+        if model.training and self.unsupervised_segmentation:  # seg_criterion.py:178-186
             S = model.cfg.patch_image_size
             net_output = model(full_context_alignment=self.full_context_alignment, aux_input=sample["aux_input"])
             logits = net_output[1]["aux_output"][0]
@@ -213,6 +210,11 @@ class SegCriterion(FairseqCriterion):
             with torch.no_grad():
                 seg_logits, seg_extra = model(**sample["net_input"], full_context_alignment=self.full_context_alignment)
                 seg_loss, metric_out = self.compute_loss(seg_logits, seg_extra, sample, training=True)
+        elif model.training:  # supervised: the real-image loss carries the gradient (seg_criterion.py:188-192)
+            logits, extra = model(**sample["net_input"], full_context_alignment=self.full_context_alignment)
+            seg_loss, metric_out = self.compute_loss(logits, extra, sample, training=True)
+            imfree_loss = torch.zeros(1, device=logits.device)
+            loss = seg_loss
         else:
             with torch.no_grad():
                 logits, extra = model(**sample["net_input"], full_context_alignment=self.full_context_alignment)
@@ -264,10 +266,10 @@ class SegCriterion(FairseqCriterion):
         post = extra.get("resnet_postprocess_probability")
         if post is not None:  # :329-336: the same metric on the propagated probabilities
             put("_resnet_postprocess", post, tgt)
-        if self.upscale_lprobs or tgt_low is None:
-            loss = pixel_cross_entropy(logits, tgt, hp, wp, self.eps)  # "just for display" (:338-341)
-        else:
-            loss = pixel_cross_entropy(logits, tgt_low, hp, wp, self.eps)
+        # "just for display" (:338-341) everywhere except the supervised training branch, where this IS the loss
+        ce = (lambda lg, t: PixelCrossEntropyFunction.apply(lg, t, hp, wp, self.eps)) if logits.requires_grad else (
+            lambda lg, t: pixel_cross_entropy(lg, t, hp, wp, self.eps))
+        loss = ce(logits, tgt if (self.upscale_lprobs or tgt_low is None) else tgt_low)
         out["nll_loss"] = loss
         return loss, out
 

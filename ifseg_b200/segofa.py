@@ -545,15 +545,28 @@ class SegOFAModel(FairseqEncoderDecoderModel):
         if return_all_hiddens:
             raise NotImplementedError("segofa_b200: return_all_hiddens is not implemented")
         grad_mode = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
-        if grad_mode and src_tokens is not None:
-            raise NotImplementedError(
-                "segofa_b200: the real-image branch has no backward (every shipped recipe trains the image-free "
-                "branch and runs this one under torch.inference_mode(), seg_criterion.py:185) -- wrap the call in "
-                "torch.no_grad()/inference_mode() or use model.eval()")
+        if grad_mode and src_tokens is not None and aux_input is not None:
+            raise NotImplementedError("segofa_b200: one forward trains ONE branch (seg_criterion.py:178-192 never asks for "
+                                      "gradients of both); call the other one under torch.no_grad()")
         # while a training engine exists its live-operand inference engine follows every optimizer update
-        eng = self._train_engine.live_inference_engine() if (self._train_engine is not None and self.training) else self.engine()
+        def no_grad_engine():
+            return self._train_engine.live_inference_engine() if (self._train_engine is not None and self.training) else self.engine()
+
         x, extra = None, {}
-        if src_tokens is not None:
+        if src_tokens is not None and grad_mode:
+            # supervised real-image branch (seg_criterion.py:188-192): the frozen ResNet + image_proj feed the same
+            # hand-written forward/adjoint chain as the image-free branch (train_engine.py)
+            if encoder_only or features_only:
+                raise NotImplementedError("segofa_b200: encoder_only / features_only with gradients is not implemented")
+            te = self.train_engine()
+            x = te.real_logits(dict(src_tokens=src_tokens, patch_images=patch_images, patch_masks=patch_masks,
+                                    prev_output_tokens=prev_output_tokens), causal=not full_context_alignment)
+            B = src_tokens.shape[0]
+            extra = {"attn": [None], "inner_states": [],
+                     "encoder_returns": {"image_embed_shape": [te.last_grid], "encoder_states": [], "src_tokens": [],
+                                         "src_lengths": [], "patch_images": [], "encoder_embedding": []}}
+        elif src_tokens is not None:
+            eng = no_grad_engine()
             enc = eng.encode(src_tokens, patch_images=patch_images, patch_masks=patch_masks)
             if encoder_only:
                 return eng.encoder_out_dict(enc)
@@ -566,6 +579,7 @@ class SegOFAModel(FairseqEncoderDecoderModel):
             ax = self.train_engine().imfree_logits(aux_input)
             extra["aux_output"] = (ax, {"attn": [None], "inner_states": []})
         elif aux_input is not None:
+            eng = no_grad_engine()
             aenc = eng.encode(aux_input.get("src_tokens"), bag_tokens=aux_input.get("patch_images"),
                               bag_offsets=aux_input.get("patch_masks"))
             ax, aextra = eng.decode(aenc, aux_input.get("prev_output_tokens"), full_context_alignment=False)

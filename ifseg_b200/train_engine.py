@@ -143,8 +143,8 @@ class ImFreeBranchFunction(torch.autograd.Function):
       * half-precision model: one cast of the arena to the parameter dtype, returned as per-parameter views."""
 
     @staticmethod
-    def forward(ctx, engine, aux_input, *params):
-        c = engine.forward_train(aux_input)
+    def forward(ctx, engine, aux_input, causal, *params):
+        c = engine.forward_train(aux_input, causal=causal)
         ctx.engine, ctx.c = engine, c
         return c["logits"]
 
@@ -172,7 +172,7 @@ class ImFreeBranchFunction(torch.autograd.Function):
         else:
             g16 = ar.grad32.to(ar.param_dtype)
             grads = [g16[o:o + n].view(p.shape) for p in ar.params for (o, n) in (ar.slots[id(p)],)]
-        return (None, None, *grads)
+        return (None, None, None, *grads)
 
 
 class _Dense:
@@ -331,7 +331,13 @@ class SegOFATrainEngine:
 
     def imfree_logits(self, aux_input):
         """logits [B,Td,C] of the image-free branch, attached to autograd (see ImFreeBranchFunction)."""
-        return ImFreeBranchFunction.apply(self, aux_input, *self.arena.params)
+        return ImFreeBranchFunction.apply(self, aux_input, True, *self.arena.params)
+
+    def real_logits(self, net_input, causal=True):
+        """logits [B,Td,C] of the real-image branch, attached to autograd: the supervised loss of
+        seg_criterion.py:188-192 (--unsupervised-segmentation=false).  Same node, same adjoint chain: the image rows
+        come from the frozen ResNet + image_proj instead of the category-word bags."""
+        return ImFreeBranchFunction.apply(self, net_input, causal, *self.arena.params)
 
     def _wgrad_stream(self):
         if self._wstream is None:
@@ -669,9 +675,12 @@ class SegOFATrainEngine:
         ops.upsample_ce_loss_bwd(logits, tgt, pix_lse, acc[1:], h, w, dlogits, label_smoothing, grad_scale)
         return loss, dlogits
 
-    def forward_train(self, aux_input, check_pads=True):
-        """Forward of the image-free branch keeping what the adjoints need; returns the context dict
-        (`logits` fp32 [B,Td,C] among it) that backward_from consumes."""
+    def forward_train(self, aux_input, check_pads=True, causal=True):
+        """Forward of one training branch keeping what the adjoints need; returns the context dict (`logits` fp32
+        [B,Td,C] among it) that backward_from consumes.  `patch_images` decides the branch: integer bag tokens = the
+        image-free branch (encoder_module.py:529-551), a float [B,3,S,S] batch = the real-image branch (the frozen
+        ResNet stem and image_proj run without gradient, encoder_module.py:191-197).  causal=False is the real branch
+        under --full-context-alignment (the image-free branch is always causal, segofa.py:145-149)."""
         if not self._fresh:
             self.refresh_weights()  # an external optimizer may have updated the fp32 masters in place
         self._fresh = False
@@ -682,19 +691,36 @@ class SegOFATrainEngine:
         B, T_txt = src_tokens.shape
         if check_pads and bool(src_tokens.eq(cfg.padding_idx).any()):  # host sync (skipped under graph capture)
             raise NotImplementedError("training with padded prompts is not implemented (every IFSeg batch shares one prompt)")
-        h = w = cfg.patch_image_size // 16
+        images = aux_input["patch_images"]
+        real = images.is_floating_point()
+        f32 = torch.float32
+        if real:
+            if self.arena.has(self.model.encoder.image_proj.weight):
+                raise NotImplementedError("training the real-image branch needs --freeze-entire-resnet=true (every shipped "
+                                          "recipe): ResNet / image_proj gradients are not implemented")
+            pm = aux_input.get("patch_masks")
+            if check_pads and pm is not None and not bool(pm.all()):
+                raise NotImplementedError("training with masked-out images (patch_masks=False) is not implemented")
+            with torch.no_grad():
+                feat = self.inf.stem(images.to(dev))  # [B,h,w,1024] bf16, folded FrozenBatchNorm (:170-172)
+            h, w = feat.shape[1], feat.shape[2]
+        else:
+            h = w = cfg.patch_image_size // 16
+        self.last_grid = (h, w)
         P = h * w
         T, Td = P + T_txt, P + 1
         M, Md = B * T, B * Td
-        f32 = torch.float32
         new = lambda shape, dt=_BF16: torch.empty(shape, dtype=dt, device=dev)  # noqa: E731
 
         pb = self._position_bias(h, w, T_txt)
         enc_biases, self_biases, cross_abs = pb["enc_biases"], pb["self_biases"], pb["cross_abs"]
 
         # ------------------------------ encoder forward ------------------------------
-        bag = ops.embedding_bag_mean(aux_input["patch_images"].to(dev).contiguous(),
-                                     aux_input["patch_masks"].to(dev).contiguous(), self.embed_tokens, P)
+        if real:  # image rows = image_proj(ResNet features) (encoder_module.py:416), both frozen
+            bag = ops.gemm(feat.view(B * P, 1024), self.inf.w_image_proj, bias=self.inf.b_image_proj, out_dtype=f32)
+        else:
+            bag = ops.embedding_bag_mean(images.to(dev).contiguous(), aux_input["patch_masks"].to(dev).contiguous(),
+                                         self.embed_tokens, P)
         tok_idx = src_tokens.reshape(-1).contiguous()
         x = new((M, D), f32)
         a = new((M, D))
@@ -757,7 +783,7 @@ class SegOFATrainEngine:
             S["o"], S["lse"] = new((Md, D)), new((B, H, Td), f32)
             ops.attention(S["qkv"], S["qkv"][:, D:], S["qkv"][:, 2 * D:], S["o"], B=B, H=H, Tq=Td, Tk=Td, q_strides=sd3,
                           k_strides=sd3, v_strides=sd3, o_strides=(D, Td * D), bias=self_biases[li],
-                          head_scale=L["attn"]["c_attn"][0], causal=True, lse=S["lse"])
+                          head_scale=L["attn"]["c_attn"][0], causal=causal, lse=S["lse"])
             S["y"] = self._lin_fwd(S["o"], L["attn"]["out"], "out_proj", out_dtype=f32)
             S["x1"], S["a2"] = new((Md, D), f32), new((Md, D))
             S["dS"], S["dC"], S["dB"] = (self._drop(110 + 3 * li + k, Td, self.dec_dpr[li]) for k in range(3))
@@ -791,7 +817,7 @@ class SegOFATrainEngine:
         return dict(logits=logits, h=h, w=w, B=B, T_txt=T_txt, P=P, T=T, Td=Td, M=M, Md=Md, bag=bag, tok_idx=tok_idx,
                     x_emb=x_emb, xd_emb=xd_emb, enc_out=enc_out, kv_all=kv_all, feats=feats, dec_in_idx=dec_in_idx, bos=bos,
                     enc_saved=enc_saved, dec_saved=dec_saved, enc_biases=enc_biases, self_biases=self_biases,
-                    cross_abs=cross_abs, pb=pb)
+                    cross_abs=cross_abs, pb=pb, causal=causal, real=real)
 
     def backward_from(self, c, dlogits):
         """Adjoint of forward_train: dlogits bf16 [B,Td,pad8(C)] = dL/dlogits.  Parameter gradients are written
@@ -867,7 +893,7 @@ class SegOFATrainEngine:
                               dqkv[:, 2 * D:], B=B, H=H, Tq=Td, Tk=Td, q_strides=sd3, k_strides=sd3, v_strides=sd3,
                               o_strides=(D, Td * D), do_strides=(D, Td * D), dq_strides=sd3, dk_strides=sd3,
                               dv_strides=sd3, lse=S["lse"], delta=delta, bias=self_biases[li],
-                              head_scale=L["attn"]["c_attn"][0], d_head_scale=L["attn"]["c_attn"][1], causal=True,
+                              head_scale=L["attn"]["c_attn"][0], d_head_scale=L["attn"]["c_attn"][1], causal=c["causal"],
                               dq_scale=cfg.attn_scaling, dbias=d_self_l, bias_t=pb["self_biases_t"][li])
             ops.attn_bias_bwd(d_self_l, [self._csr("seg", self.seg_rp_bucket, pb["seg_ids"], 0, d_self_l.stride(1),
                                                    self.rel_seg[li][1])], dabs_acc=d_self_abs)

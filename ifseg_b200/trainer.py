@@ -24,8 +24,9 @@ from .train_engine import SegOFATrainEngine
 class SegOFATrainer:
     def __init__(self, model, lr=5e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1, clip_norm=1.0,
                  label_smoothing=0.0, seg_id_offset=59457, process_group=None, eval_real_image=True, stochastic=True,
-                 seed=1):
+                 seed=1, supervised=False):
         self.model = model
+        self.supervised = supervised  # --unsupervised-segmentation=false: the real-image loss trains (seg_criterion.py:188-192)
         self.engine = SegOFATrainEngine(model, stochastic=stochastic, seed=seed)  # dropout / DropPath of the recipe
         self.lr, self.betas, self.eps, self.weight_decay, self.clip_norm = lr, betas, eps, weight_decay, clip_norm
         self.label_smoothing = label_smoothing
@@ -63,11 +64,28 @@ class SegOFATrainer:
         eng = self.engine
         S = cfg.patch_image_size
         C = cfg.num_seg
-        B = sample["aux_input"]["src_tokens"].shape[0]
+        B = sample["net_input"]["src_tokens"].shape[0]
         dev = eng.device
+        self._works = []
+        if self.supervised:
+            ni = sample["net_input"]
+            c = eng.forward_train(ni, check_pads=check_pads)
+            h, w = ni["patch_images"].shape[-2:]
+            rt = class_targets(sample["target"][:, :-1].reshape(B, h, w).to(dev), self.seg_id_offset, C, cfg.padding_idx)
+            seg_loss, dlogits = eng.loss_and_dlogits(c, rt, self.label_smoothing)
+            with torch.no_grad():  # display metrics from the same logits (compute_loss, :301-305)
+                _, areas = ops.upsample_argmax(c["logits"], c["h"], c["w"], h, w, target=rt)
+            eng.backward_from(c, dlogits)
+            for wk in self._works:
+                wk.wait()
+            gnorm = eng.optimizer_step(self.lr, self.betas, self.eps, self.weight_decay, self.clip_norm,
+                                       grad_mult=1.0 / self.world)
+            self.num_updates += 1
+            return {"loss": seg_loss, "seg_loss": seg_loss, "imfree_loss": torch.zeros_like(seg_loss), "gnorm": gnorm,
+                    "area_intersect": areas[0], "area_pred_label": areas[1], "area_label": areas[2],
+                    "area_union": areas[1] + areas[2] - areas[0]}
         ids = sample["text2seg_target"][:, :-1].reshape(B, S, S).to(dev)
         tgt = class_targets(ids, self.seg_id_offset, C, cfg.padding_idx)
-        self._works = []
         c = eng.forward_train(sample["aux_input"], check_pads=check_pads)
         imfree_loss, dlogits = eng.loss_and_dlogits(c, tgt, self.label_smoothing)
         log = {"loss": imfree_loss, "imfree_loss": imfree_loss}

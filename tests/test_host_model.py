@@ -121,7 +121,7 @@ def test_forward_fails_loudly_without_cuda(model):
         with torch.no_grad():
             model(**inp)
     model.train()
-    with pytest.raises(NotImplementedError, match="real-image branch has no backward"):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):  # supervised branch: the training engine is CUDA-only
         model(**inp)
     with pytest.raises(RuntimeError, match="no CPU fallback"):  # the training engine is CUDA-only as well
         model(aux_input=dict(src_tokens=inp["src_tokens"], patch_images=inp["src_tokens"], patch_masks=inp["src_lengths"],

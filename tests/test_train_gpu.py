@@ -189,3 +189,84 @@ def test_stochastic_training_is_seeded_and_learns(cuda_device):
     e.stochastic = False
     last, _ = e.forward_backward(aux, tgt, backward=False)
     assert last.item() < first.item() - 0.05, (first.item(), last.item())
+
+
+def _supervised_sample(g, model, aux, t2s):
+    from ifseg_b200.synthetic import synthetic_inputs
+
+    C, S, B = g["num_seg"], g["image_size"], g["batch"]
+    inp_host = synthetic_inputs(model.cfg, B, S, seed=1, src_tokens=g["src_tokens"][0])
+    gen = torch.Generator().manual_seed(9)
+    # dictionary ids at the network input resolution; class C = the ignore label (seg_criterion.py:296-298), eos last
+    target = torch.cat([torch.randint(0, C + 1, (B, S * S), generator=gen) + 59457, torch.full((B, 1), 2)], 1)
+    sample = {"net_input": {k: v.cuda() for k, v in inp_host.items()}, "aux_input": aux, "target": target,
+              "text2seg_target": t2s, "ntokens": 1, "nsentences": B}
+    return inp_host, target, sample
+
+
+def test_supervised_real_image_branch_gradients_vs_oracle(cuda_device):
+    """--unsupervised-segmentation=false (seg_criterion.py:188-192): the real-image loss carries the gradient.  ResNet
+    and image_proj are frozen (--freeze-entire-resnet=true, encoder_module.py:191-197), every other tensor gets the
+    same adjoint chain as the image-free branch.  Gate as for that branch: global gradient rel-L2 against the fp32
+    oracle's autograd below the reference's own bf16 noise floor."""
+    import types
+
+    from oracle import restated as R
+
+    from ifseg_b200.fairseq_compat import StubDictionary
+    from ifseg_b200.seg_criterion import SegCriterion
+
+    g, gg, model, sd, eng, aux, tgt, t2s = _setup()
+    C, S, B = g["num_seg"], g["image_size"], g["batch"]
+    inp_host, target, sample = _supervised_sample(g, model, aux, t2s)
+    model._train_engine = eng
+    model.train()
+    task = types.SimpleNamespace(target_dictionary=StubDictionary(C),
+                                 cfg=types.SimpleNamespace(num_seg_tokens=C, category_list=",".join(f"c{i}" for i in range(C))))
+    crit = SegCriterion(task, init_seg_with_text="false", unsupervised_segmentation="false")
+    model.zero_grad(set_to_none=True)
+    loss, sample_size, log = crit(model, sample)
+    assert loss.requires_grad and sample_size == 1 and float(log["imfree_loss"]) == 0.0
+    for k in ("loss", "seg_loss", "area_intersect", "area_union", "nll_loss"):
+        assert k in log
+    loss.backward()
+    torch.cuda.synchronize()
+    ours = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    assert len(ours) == 380 and not any(k.startswith(("encoder.embed_images", "encoder.image_proj")) for k in ours)
+
+    torch.set_num_threads(8)
+    ocfg = oracle_cfg(model.cfg)
+    sd_g = {k: (v.clone().requires_grad_() if k in ours else v) for k, v in sd.items()}
+    x_or, _ = R.segofa_forward(sd_g, ocfg, inp_host["src_tokens"], inp_host["patch_images"], inp_host["patch_masks"],
+                               inp_host["prev_output_tokens"])
+    loss_or = R.imfree_loss(x_or, target, ocfg)
+    loss_or.backward()
+    assert abs(loss.item() - loss_or.item()) < 1e-2 * loss_or.item(), (loss.item(), loss_or.item())
+    num = den = 0.0
+    worst = (0.0, None)
+    for k, gr in ours.items():
+        go = sd_g[k].grad
+        if go is None or go.norm().item() < 1e-8:
+            assert gr.norm().item() < 1e-5, (k, gr.norm().item())
+            continue
+        num += ((gr - go) ** 2).sum().item()
+        den += (go ** 2).sum().item()
+        e = rel_l2(gr, go)
+        if e > worst[0]:
+            worst = (e, k)
+    glob = (num / den) ** 0.5
+    print(f"\nsupervised gradient parity: global rel-L2 {glob:.3e} (reference bf16 floor "
+          f"{gg['ref_bf16_grad_rel_l2']:.3e}), worst {worst[0]:.3e} {worst[1]}")
+    assert glob <= gg["ref_bf16_grad_rel_l2"], glob
+    assert worst[0] < 0.25, worst
+
+
+def test_supervised_trainer_reduces_the_real_image_loss(cuda_device):
+    from ifseg_b200.trainer import SegOFATrainer
+
+    g, gg, model, sd, eng, aux, tgt, t2s = _setup()
+    _, _, sample = _supervised_sample(g, model, aux, t2s)
+    tr = SegOFATrainer(model, lr=2e-4, weight_decay=0.01, clip_norm=1.0, supervised=True, stochastic=False)
+    losses = [tr.train_step(sample)["loss"].item() for _ in range(8)]
+    assert losses[-1] < losses[0] - 0.05, losses
+    assert all(x == x for x in losses)
