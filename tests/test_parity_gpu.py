@@ -157,6 +157,69 @@ def test_image_free_branch_at_bench_shapes(cuda_device, name, arch, C, S, B):
     assert e_train <= 1.25 * floor, (e_train, floor)
 
 
+def test_train_step_gradients_at_the_cfg3_shape(cuda_device):
+    """Gradient parity where the train step is quoted (cfg 3: Base, 480x480, 150 classes, T_e = 1115), batch 2 to bound
+    the CPU oracle's autograd: image-free forward + compute_imfree_loss + backward of the training engine against the
+    fp32 oracle.  Tolerance: the reference's own bf16-vs-fp32 gradient distance (4.8e-2 global rel-L2, stored in
+    tests/golden/golden_grads_base_c150_s64_b2.pt)."""
+    from oracle import restated as R
+    from ifseg_b200 import ops
+    from ifseg_b200.seg_criterion import class_targets
+
+    name, arch, C, S, B = CASES[1]
+    torch.set_num_threads(max(8, os.cpu_count() or 8))
+    model, sd = build_cuda_model(arch, C, S, seed=0)
+    prompt = torch.tensor(load_prompts()[str(C)], dtype=torch.long)
+    names = torch.full((C, 4), 1, dtype=torch.long)
+    lens = torch.zeros(C, dtype=torch.int32)
+    g = torch.Generator().manual_seed(4)
+    for c in range(C):
+        n = 1 + c % 3
+        names[c, :n] = torch.randint(4, 50000, (n,), generator=g)
+        lens[c] = n
+    bag, ends, target = ops.artificial_sample(names.cuda(), lens.cuda(), B, S // 16, S, seed=7)
+    aux = dict(src_tokens=prompt.unsqueeze(0).repeat(B, 1), src_lengths=torch.full((B,), prompt.numel()),
+               patch_images=bag.cpu(), patch_masks=ends.cpu(), prev_output_tokens=torch.zeros(B, 1, dtype=torch.long))
+    t2s = target.cpu().long()
+    model.train()
+    te = model.train_engine()
+    te.stochastic = False
+    tgt = class_targets(t2s[:, :-1].reshape(B, S, S), 59457, C).cuda()
+    loss, _ = te.forward_backward({k: v.cuda() for k, v in aux.items()}, tgt)
+    torch.cuda.synchronize()
+    ours = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    t0 = time.time()
+    oc = oracle_cfg(model.cfg)
+    sd_g = {k: (v.clone().requires_grad_() if k in ours else v) for k, v in sd.items()}
+    x_or, _ = R.segofa_forward_aux(sd_g, oc, aux)
+    loss_or = R.imfree_loss(x_or, t2s, oc)
+    loss_or.backward()
+    cpu_s = time.time() - t0
+    num = den = 0.0
+    per, worst = [], (0.0, None)
+    for k, gr in ours.items():
+        go = sd_g[k].grad
+        if go is None or go.norm().item() < 1e-8:
+            assert gr.norm().item() < 1e-5, (k, gr.norm().item())
+            continue
+        num += ((gr - go) ** 2).sum().item()
+        den += (go ** 2).sum().item()
+        e = rel_l2(gr, go)
+        per.append(e)
+        if e > worst[0]:
+            worst = (e, k)
+    per.sort()
+    glob = (num / den) ** 0.5
+    record(case=name, branch="image_free_gradients", T_e=(S // 16) ** 2 + prompt.numel(), batch=B, tensors=len(per),
+           loss=loss.item(), oracle_loss=loss_or.item(), grad_global_rel_l2_vs_fp32_oracle=glob,
+           grad_per_tensor_median=per[len(per) // 2], grad_per_tensor_worst=worst[0], worst_tensor=worst[1],
+           reference_bf16_grad_floor=4.8e-2, cpu_oracle_seconds=round(cpu_s, 1))
+    assert abs(loss.item() - loss_or.item()) < 1e-2 * loss_or.item()
+    assert len(ours) == 380
+    assert glob <= 4.8e-2, glob
+    assert worst[0] < 0.25, worst
+
+
 @pytest.mark.parametrize("name,arch,C,S", [("cfg2_base480_c15", "segofa_base", 15, 480), ("large320_c150", "segofa_large", 150, 320)])
 def test_every_launch_replayed_from_its_own_inputs(cuda_device, name, arch, C, S):
     """Gate (S): the whole forward (stem, position bias, encoder, decoder, head) at batch 1, every GEMM / convolution /
