@@ -689,8 +689,11 @@ class SegOFATrainEngine:
         D, H, Fd, C = cfg.embed_dim, cfg.heads, cfg.ffn_dim, cfg.num_seg
         src_tokens = aux_input["src_tokens"].to(dev)
         B, T_txt = src_tokens.shape
-        if check_pads and bool(src_tokens.eq(cfg.padding_idx).any()):  # host sync (skipped under graph capture)
-            raise NotImplementedError("training with padded prompts is not implemented (every IFSeg batch shares one prompt)")
+        # padded prompts (encoder_module.py:730-742): pad keys are masked in the encoder self-attention and the decoder
+        # cross-attention; nothing else reads a pad row, so its value and its gradient never matter.  The check is a
+        # host sync (as in the reference, :742); a graph-captured session (check_pads=False) asserts "no pads".
+        txt_pad = src_tokens.eq(cfg.padding_idx)
+        has_pads = check_pads and bool(txt_pad.any())
         images = aux_input["patch_images"]
         real = images.is_floating_point()
         f32 = torch.float32
@@ -710,6 +713,10 @@ class SegOFATrainEngine:
         P = h * w
         T, Td = P + T_txt, P + 1
         M, Md = B * T, B * Td
+        kpm = None
+        if has_pads:
+            kpm = torch.zeros((B, T), dtype=torch.uint8, device=dev)
+            kpm[:, P:] = txt_pad
         new = lambda shape, dt=_BF16: torch.empty(shape, dtype=dt, device=dev)  # noqa: E731
 
         pb = self._position_bias(h, w, T_txt)
@@ -739,7 +746,7 @@ class SegOFATrainEngine:
             S["o"], S["lse"] = new((M, D)), new((B, H, T), f32)
             ops.attention(S["qkv"], S["qkv"][:, D:], S["qkv"][:, 2 * D:], S["o"], B=B, H=H, Tq=T, Tk=T, q_strides=s3,
                           k_strides=s3, v_strides=s3, o_strides=(D, T * D), bias=enc_biases[li],
-                          head_scale=L["attn"]["c_attn"][0], lse=S["lse"])
+                          head_scale=L["attn"]["c_attn"][0], key_padding_mask=kpm, lse=S["lse"])
             S["y"] = self._lin_fwd(S["o"], L["attn"]["out"], "out_proj", out_dtype=f32)
             S["x1"], S["a2"] = new((M, D), f32), new((M, D))
             S["dA"], S["dB"] = self._drop(10 + 2 * li, T, self.enc_dpr[li]), self._drop(11 + 2 * li, T, self.enc_dpr[li])
@@ -795,7 +802,7 @@ class SegOFATrainEngine:
             kbase = kv_all[:, li * 2 * D:]
             ops.attention(S["qc"], kbase, kbase[:, D:], S["oc"], B=B, H=H, Tq=Td, Tk=T, q_strides=(D, Td * D),
                           k_strides=kvs, v_strides=kvs, o_strides=(D, Td * D), bias=cross_abs,
-                          head_scale=Cx["c_attn"][0], lse=S["lse_c"])
+                          head_scale=Cx["c_attn"][0], key_padding_mask=kpm, lse=S["lse_c"])
             S["yc"] = self._lin_fwd(S["oc"], Cx["out"], "out_proj", out_dtype=f32)
             S["x2"], S["a3"] = new((Md, D), f32), new((Md, D))
             ops.row_layernorm(S["yc"], ln1=L["ln_cross_attn"][:2], residual=S["x1"], out1=S["x2"], ln2=L["ln_final"][:2],
@@ -817,7 +824,7 @@ class SegOFATrainEngine:
         return dict(logits=logits, h=h, w=w, B=B, T_txt=T_txt, P=P, T=T, Td=Td, M=M, Md=Md, bag=bag, tok_idx=tok_idx,
                     x_emb=x_emb, xd_emb=xd_emb, enc_out=enc_out, kv_all=kv_all, feats=feats, dec_in_idx=dec_in_idx, bos=bos,
                     enc_saved=enc_saved, dec_saved=dec_saved, enc_biases=enc_biases, self_biases=self_biases,
-                    cross_abs=cross_abs, pb=pb, causal=causal, real=real)
+                    cross_abs=cross_abs, pb=pb, causal=causal, real=real, kpm=kpm)
 
     def backward_from(self, c, dlogits):
         """Adjoint of forward_train: dlogits bf16 [B,Td,pad8(C)] = dL/dlogits.  Parameter gradients are written
@@ -879,7 +886,7 @@ class SegOFATrainEngine:
                               do_strides=(D, Td * D), dq_strides=(D, Td * D), dk_strides=kvs, dv_strides=kvs,
                               lse=S["lse_c"], delta=delta, bias=cross_abs, head_scale=Cx["c_attn"][0],
                               d_head_scale=Cx["c_attn"][1], dq_scale=cfg.attn_scaling, dbias=d_cross_abs,
-                              bias_t=pb["cross_abs_t"])
+                              bias_t=pb["cross_abs_t"], key_padding_mask=c["kpm"])
             da2 = self._lin_bwd(dqc, S["a2"], Cx["q"], Md, "cross_q")
             # self-attention block
             dy = new((Md, D))
@@ -952,7 +959,7 @@ class SegOFATrainEngine:
                               o_strides=(D, T * D), do_strides=(D, T * D), dq_strides=s3, dk_strides=s3, dv_strides=s3,
                               lse=S["lse"], delta=delta, bias=enc_biases[li], head_scale=L["attn"]["c_attn"][0],
                               d_head_scale=L["attn"]["c_attn"][1], dq_scale=cfg.attn_scaling, dbias=d_enc_l,
-                              bias_t=pb["enc_biases_t"][li])
+                              bias_t=pb["enc_biases_t"][li], key_padding_mask=c["kpm"])
             rs = d_enc_l.stride(1)
             ops.attn_bias_bwd(d_enc_l, [self._csr("img", self.image_rp_bucket, pb["ids"], 0, rs, self.rel_img[li][1]),
                                         self._csr("tok", self.token_rp_bucket, pb["tok_ids"], P, rs, self.rel_tok[li][1])],

@@ -98,13 +98,11 @@ class SegOFATrainer:
                 self._side = torch.cuda.Stream()
             self._side.wait_stream(main)
             ni = sample["net_input"]
-            if check_pads and bool(ni["src_tokens"].eq(cfg.padding_idx).any()):
-                # the metric pass runs the no-padding fast path; a padded prompt would silently change the metrics
-                raise NotImplementedError("segofa_b200 trainer: padded prompts in net_input are not supported in the "
-                                          "real-image metric pass (the shipped recipe uses one fixed prompt per batch)")
+            # a padded prompt takes the key-padding path (host check as encoder_module.py:742; skipped under graph capture)
+            ni_pads = check_pads and bool(ni["src_tokens"].eq(cfg.padding_idx).any())
             with torch.cuda.stream(self._side), torch.no_grad():
                 enc = eng.inf.encode(ni["src_tokens"], patch_images=ni["patch_images"], patch_masks=ni["patch_masks"],
-                                     has_pads=False)
+                                     has_pads=ni_pads)
                 logits, _ = eng.inf.decode(enc, ni["prev_output_tokens"])
                 hp, wp = enc["hw"]
                 h, w = ni["patch_images"].shape[-2:]

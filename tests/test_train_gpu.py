@@ -270,3 +270,43 @@ def test_supervised_trainer_reduces_the_real_image_loss(cuda_device):
     losses = [tr.train_step(sample)["loss"].item() for _ in range(8)]
     assert losses[-1] < losses[0] - 0.05, losses
     assert all(x == x for x in losses)
+
+
+def test_padded_prompt_gradients_vs_oracle(cuda_device):
+    """Prompts of different lengths in one batch (encoder_module.py:730-752): the shorter one is padded; its pad keys are
+    masked in the encoder self-attention and the decoder cross-attention, forward and adjoint."""
+    from oracle import restated as R
+
+    g, gg, model, sd, eng, aux, tgt, t2s = _setup()
+    pad = model.cfg.padding_idx
+    aux = dict(aux)
+    tok = aux["src_tokens"].clone()
+    n = tok.shape[1] // 2
+    tok[1, n - 1] = 2  # the second prompt is half as long: eos moves up, pads follow
+    tok[1, n:] = pad
+    aux["src_tokens"] = tok
+    loss, logits = eng.forward_backward(aux, tgt)
+    torch.cuda.synchronize()
+    ours = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    torch.set_num_threads(8)
+    ocfg = oracle_cfg(model.cfg)
+    sd_g = {k: (v.clone().requires_grad_() if k in ours else v) for k, v in sd.items()}
+    aux_host = {k: v.cpu() for k, v in aux.items()}
+    x_or, _ = R.segofa_forward_aux(sd_g, ocfg, aux_host)
+    loss_or = R.imfree_loss(x_or, t2s, ocfg)
+    loss_or.backward()
+    assert abs(loss.item() - loss_or.item()) < 1e-2 * loss_or.item()
+    assert rel_l2(logits, x_or.detach()) <= 0.75 * g["ref_bf16_rel_l2"]
+    # the mask matters: the same tokens with the pad keys left visible (check_pads=False skips the detection) are off
+    logits_nm = eng.forward_train(aux, check_pads=False)["logits"]
+    assert rel_l2(logits_nm[1], x_or.detach()[1]) > 3 * rel_l2(logits[1], x_or.detach()[1])
+    num = den = 0.0
+    for k, gr in ours.items():
+        go = sd_g[k].grad
+        if go is None or go.norm().item() < 1e-8:
+            continue
+        num += ((gr - go) ** 2).sum().item()
+        den += (go ** 2).sum().item()
+    glob = (num / den) ** 0.5
+    print(f"\npadded-prompt gradient parity: global rel-L2 {glob:.3e}")
+    assert glob <= gg["ref_bf16_grad_rel_l2"], glob
