@@ -180,6 +180,30 @@ class ArtSampleArgs(C.Structure):
     ]
 
 
+class ImagePrepArgs(C.Structure):
+    _fields_ = [
+        ("src", _vp), ("src_row_stride", _i64), ("src_h", _i32), ("src_w", _i32),
+        ("rs_h", _i32), ("rs_w", _i32),
+        ("crop_y", _i32), ("crop_x", _i32), ("out_h", _i32), ("out_w", _i32),
+        ("flip", _i32),
+        ("mean", _f32 * 3), ("std", _f32 * 3),
+        ("dst", _vp), ("dst_channel_stride", _i64), ("dst_row_stride", _i64),
+    ]
+
+
+class SegmapPrepArgs(C.Structure):
+    _fields_ = [
+        ("src", _vp), ("src_row_stride", _i64), ("src_h", _i32), ("src_w", _i32),
+        ("num_seg", _i32),
+        ("rs_h", _i32), ("rs_w", _i32),
+        ("crop_y", _i32), ("crop_x", _i32), ("out_h", _i32), ("out_w", _i32),
+        ("flip", _i32),
+        ("grid_h", _i32), ("grid_w", _i32),
+        ("seg_id_offset", _i64), ("bos_id", _i64), ("eos_id", _i64),
+        ("target", _vp), ("prev_output_tokens", _vp), ("downsampled_target", _vp), ("ori_classes", _vp),
+    ]
+
+
 # every symbol include/segofa_b200.h declares: (name, restype, argtypes)
 EXPORTS = [
     ("sgf_last_error", C.c_char_p, []),
@@ -211,6 +235,8 @@ EXPORTS = [
     ("sgf_transpose16_batched", C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _i64, _vp]),
     ("sgf_attn_bias_bwd", C.c_int, [C.POINTER(BiasBwdArgs), _vp]),
     ("sgf_artificial_sample", C.c_int, [C.POINTER(ArtSampleArgs), _vp]),
+    ("sgf_image_prep_u8", C.c_int, [C.POINTER(ImagePrepArgs), _vp]),
+    ("sgf_segmap_prep_u8", C.c_int, [C.POINTER(SegmapPrepArgs), _vp]),
     ("sgf_adam_step", C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp, _vp, _vp]),
     ("sgf_sumsq", C.c_int, [_vp, _i64, _vp, _vp]),
 ]

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["runtime.cu", "gemm.cu", "gemm_ts.cu", "attention.cu", "attention_bwd.cu", "rowops.cu", "train.cu", "segmask.cu"]
+SOURCES = ["runtime.cu", "gemm.cu", "gemm_ts.cu", "attention.cu", "attention_bwd.cu", "rowops.cu", "train.cu", "segmask.cu", "preprocess.cu"]
 LIB = os.path.join(PKG, "libsegofa_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

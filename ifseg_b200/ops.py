@@ -604,3 +604,47 @@ def sumsq(x, out):
     with _timed("sumsq", nbytes=float(x.numel() * 4)):
         _lib.check(lib.sgf_sumsq(_p(x), x.numel(), _p(out), _stream()), "sgf_sumsq")
     return out
+
+
+def image_prep_u8(image_u8, rs_hw, *, crop=None, flip=False, mean, std, out=None):
+    """uint8 [H, W, 3] on the device -> fp32 [3, out_h, out_w]: cv2 INTER_LINEAR resize to rs_hw, window `crop` =
+    (y, x, h, w) of it, horizontal flip, /255, (x - mean) / std -- bit-identical to cv2 + torchvision
+    (data/mm_data/segmentation_dataset.py:155-156, 236-240, 253-257)."""
+    lib = _lib.load()
+    _req(image_u8, torch.uint8, "image_u8")
+    assert image_u8.dim() == 3 and image_u8.shape[2] == 3 and image_u8.stride(2) == 1 and image_u8.stride(1) == 3
+    H, W = image_u8.shape[:2]
+    rs_h, rs_w = rs_hw
+    cy, cx, oh, ow = crop if crop is not None else (0, 0, rs_h, rs_w)
+    if out is None:
+        out = torch.empty((3, oh, ow), dtype=torch.float32, device=image_u8.device)
+    _req(out, torch.float32, "out")
+    assert tuple(out.shape) == (3, oh, ow) and out.stride(2) == 1
+    args = _lib.ImagePrepArgs(_p(image_u8), image_u8.stride(0), H, W, rs_h, rs_w, cy, cx, oh, ow, 1 if flip else 0,
+                              (C.c_float * 3)(*mean), (C.c_float * 3)(*std), _p(out), out.stride(0), out.stride(1))
+    with _timed("image_prep", nbytes=float(image_u8.numel() + out.numel() * 4)):
+        _lib.check(lib.sgf_image_prep_u8(C.byref(args), _stream()), "sgf_image_prep_u8")
+    return out
+
+
+def segmap_prep_u8(seg_u8, num_seg, rs_hw, grid_hw, *, crop=None, flip=False, seg_id_offset=59457, bos_id=0, eos_id=2,
+                   want_downsampled=False, want_ori=False):
+    """raw uint8 label map [H, W] on the device -> (target int64 [out_h*out_w+1], prev_output_tokens int64 [grid+1],
+    downsampled_target or None, ori_classes int64 [H, W] or None)  (segmentation_dataset.py:224-227, 241-265)."""
+    lib = _lib.load()
+    _req(seg_u8, torch.uint8, "seg_u8")
+    assert seg_u8.dim() == 2 and seg_u8.stride(1) == 1
+    H, W = seg_u8.shape
+    rs_h, rs_w = rs_hw
+    cy, cx, oh, ow = crop if crop is not None else (0, 0, rs_h, rs_w)
+    gh, gw = grid_hw
+    dev = seg_u8.device
+    target = torch.empty((oh * ow + 1,), dtype=torch.int64, device=dev)
+    prev = torch.empty((gh * gw + 1,), dtype=torch.int64, device=dev)
+    down = torch.empty((gh * gw + 1,), dtype=torch.int64, device=dev) if want_downsampled else None
+    ori = torch.empty((H, W), dtype=torch.int64, device=dev) if want_ori else None
+    args = _lib.SegmapPrepArgs(_p(seg_u8), seg_u8.stride(0), H, W, num_seg, rs_h, rs_w, cy, cx, oh, ow, 1 if flip else 0,
+                               gh, gw, seg_id_offset, bos_id, eos_id, _p(target), _p(prev), _p(down), _p(ori))
+    with _timed("segmap_prep", nbytes=float(seg_u8.numel() + 8 * (target.numel() + prev.numel()))):
+        _lib.check(lib.sgf_segmap_prep_u8(C.byref(args), _stream()), "sgf_segmap_prep_u8")
+    return target, prev, down, ori

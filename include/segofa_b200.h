@@ -451,6 +451,43 @@ typedef struct {
 } sgf_artsample_args;
 int sgf_artificial_sample(const sgf_artsample_args* args, void* stream);
 
+/* Real-image side of the input pipeline (data/mm_data/segmentation_dataset.py:210-301): the decoded
+ * uint8 image / label PNG crosses PCIe as bytes and the per-sample transforms run on the device, bit-identical to the
+ * host libraries the reference calls.
+ * sgf_image_prep_u8 replaces mmseg Resize (mmcv.imrescale -> cv2.resize INTER_LINEAR, 8-bit fixed point) ->
+ * RandomCrop window -> RandomFlip (horizontal) -> transforms.ToTensor (/255) -> transforms.Normalize (:155-156, :236-240,
+ * :253-257): src = uint8 [src_h, src_w, 3] (row stride in bytes; channel order as it should come out), resized to
+ * rs_h x rs_w, window (crop_y, crop_x, out_h, out_w) of it, mirrored when flip != 0, written as fp32 [3, out_h, out_w].
+ * Validation (MultiScaleFlipAug, keep-ratio resize): crop = (0, 0, rs_h, rs_w), flip = 0.  The random choices
+ * (scale, window, flip) are the caller's; PhotoMetricDistortion is not reproduced. */
+typedef struct {
+  const uint8_t* src; int64_t src_row_stride; int32_t src_h, src_w;
+  int32_t rs_h, rs_w;
+  int32_t crop_y, crop_x, out_h, out_w;
+  int32_t flip;
+  float mean[3]; float std[3];
+  float* dst; int64_t dst_channel_stride; int64_t dst_row_stride;
+} sgf_image_prep_args;
+int sgf_image_prep_u8(const sgf_image_prep_args* args, void* stream);
+
+/* Label side of the same sample (:224-227, :241-262, :264-265): src = the raw uint8 label PNG [src_h, src_w] (0 =
+ * unlabelled, k = class k-1) -> remap (0 and 255 -> num_seg, k -> k-1) -> cv2 INTER_NEAREST resize to rs_h x rs_w ->
+ * the same window / flip -> target int64 [out_h*out_w + 1] = seg_id_offset + class, then eos_id (sample["target"]);
+ * prev_output_tokens int64 [grid_h*grid_w + 1] = bos_id, then the codes of torchvision's NEAREST resize of that map to
+ * the patch grid; downsampled_target (optional) int64 [grid_h*grid_w + 1] = those codes, then eos_id; ori_classes
+ * (optional) int64 [src_h, src_w] = the remapped map at the original resolution (sample["ori_semantic_seg"]). */
+typedef struct {
+  const uint8_t* src; int64_t src_row_stride; int32_t src_h, src_w;
+  int32_t num_seg;
+  int32_t rs_h, rs_w;
+  int32_t crop_y, crop_x, out_h, out_w;
+  int32_t flip;
+  int32_t grid_h, grid_w;
+  int64_t seg_id_offset, bos_id, eos_id;
+  int64_t* target; int64_t* prev_output_tokens; int64_t* downsampled_target; int64_t* ori_classes;
+} sgf_segmap_prep_args;
+int sgf_segmap_prep_u8(const sgf_segmap_prep_args* args, void* stream);
+
 /* Multi-tensor-free fused Adam(W) step over one flat fp32 master buffer (cf/optim/adam.py, fp32
  * master weights of cf/optim/fp16_optimizer.py:108-222): p -= lr*(m_hat/(sqrt(v_hat)+eps) + wd*p)
  * with grads scaled by grad_scale[0] (device scalar: 1/sample_size * clip coefficient).  The update
