@@ -605,6 +605,14 @@ def main():
             roof["attention"] = {"kernel": "attention_tcgen05 (QK^T + PV tcgen05.mma, fused bias/softmax)", "achieved": a_tf,
                                  "frac": a_tf / peaks["bf16_sustained"], "unit": "TFLOP/s", "launches_per_step": a["launches"],
                                  "ms_in_step": fam_ms(a), "share_of_step_kernel_time": a["ms"] / total_k_ms}
+        if "row_layernorm" in fam:  # the HBM-bound family: algorithmic bytes (rows*D*(in + residual + outs)) / time in the step
+            ln = fam["row_layernorm"]
+            gbps = ln["bytes"] / (fam_ms(ln) / 1e3) / 1e9
+            roof["row_layernorm"] = {"bound": "hbm", "achieved": gbps, "peak": peaks["hbm"], "unit": "GB/s",
+                                     "frac": gbps / peaks["hbm"], "launches_per_step": ln["launches"],
+                                     "ms_in_step": fam_ms(ln), "algorithmic_bytes_per_step": ln["bytes"],
+                                     "note": "inside the step the rows are L2-resident (written by the preceding GEMM), so the "
+                                             "effective rate can exceed what a cold ncu capture of the same launch shows"}
         out = {
             "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": n, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
