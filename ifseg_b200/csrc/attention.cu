@@ -6,26 +6,25 @@
 //   warps 0..3 : softmax, thread r owns query row r (TMEM lane r); the 64 keys of a tile are processed as two 32-key
 //                sub-tiles of the online softmax (32 scores live at a time; the TMEM load of the second half runs
 //                under the arithmetic of the first)
-//   warp 4     : score issuer  -- one lane: Q/K/bias TMA loads and the S = Q K^T tcgen05.mma, up to two tiles ahead
-//   warp 5     : output issuer -- one lane: V TMA loads, half of the bias MMAs S += I * bias (the score issuer issues the
-//                other half) and the O += P V tcgen05.mma
-// What the r02 timeline and ablation measurements say (profiles/r02_attention_analysis.txt): the tile loop is bound by
-// the fixed per-tile hand-off latencies (mbarrier wake-ups, tcgen05.ld, fence.proxy.async, single-thread MMA issue at
-// ~70 clocks per tcgen05.mma: ~1850 of ~2200 cycles per tile survive when ALL softmax arithmetic is removed), not by
-// MUFU / FMA throughput and not by the number of softmax warps (4, 8 per CTA measured: same time).  Hence: issuers split
-// so S runs two tiles ahead of the softmax instead of behind P V, P double-buffered so softmax(j+1) never waits for
-// P V(j), 2-stage K/V rings, and the additive bias added by the tensor core instead of by the softmax threads.
+//   warp 4     : score issuer  -- one lane: Q/K/bias TMA loads, S = Q K^T and S += bias * I tcgen05.mma, up to two tiles ahead
+//   warp 5     : output issuer -- one lane: V TMA loads and the O += P V tcgen05.mma
+// What the r02 timeline and ablation measurements say (profiles/r02_attention_analysis.txt, r02_attention_pair.txt): without
+// a bias the tile loop is bound by the softmax threads' own chain (TMEM load round trip, max, exp2, pack, hand-off: a warp
+// needs ~1000 clocks per 32-key sub-tile of which the MUFU pipe is busy 256); with a bias the tensor pipe's operand fetch
+// (~90 B/clk/SM for M128 N64 K16 MMAs, which re-read their 4 KB A operand every instruction) comes on top.  Hence: issuers
+// split so S runs two tiles ahead of the softmax instead of behind P V, P double-buffered so softmax(j+1) never waits for
+// P V(j), 3-stage K and bias rings, the additive bias added by the tensor core with the bias tile as the A operand (read
+// once), and P handed over through TENSOR MEMORY (no shared-memory stores, no generic->async proxy fence).
 // Per 64-key tile j (all asynchronous, mbarrier hand-offs, nothing waits on the tensor core in line):
 //   S(j) = Q K(j)^T      tcgen05.mma M128 N64 K64 into one of two TMEM score buffers (score issuer)
-//   S(j) += I bias(j)    the TMA-staged fp16 bias tile [128 queries x 64 keys] is the MN-major B operand of a K = 128
-//                        tcgen05.mma whose A operand is the fp16 identity kept in TMEM (1.0 * b is exact, fp32
-//                        accumulate): 8 MMAs, four per issuing thread
+//   S(j) += bias(j) I    the TMA-staged fp16 bias tile [128 queries x 64 keys] is the K-major A operand, the fp16 identity
+//                        [64 x 64] kept in shared memory the B operand (b * 1.0 is exact, fp32 accumulate): 4 MMAs
 //   softmax(j)           tcgen05.ld the row, masks, running max with LAZY rescaling (the accumulator is only touched when
-//                        the row max grows by more than 2^8), exp2, row sum; P(j) -> smem as bf16 in the swizzled
-//                        K-major layout the tensor core reads
-//   O += P(j) V(j)       tcgen05.mma M128 N64 K64 accumulating in TMEM (V tile is the MN-major B operand)
-// K, V (2-stage rings), the fp16 bias tile and P are double-buffered: 112 KB of shared memory and 256 TMEM columns
-// (2 x 64 scores, 64 output, 64 identity) per CTA keep two CTAs per SM.
+//                        the row max grows by more than 2^8), exp2, row sum; P(j) -> tensor memory as packed bf16 pairs
+//                        (tcgen05.st, 16 columns per 32 keys), the layout tcgen05.mma reads as an A operand
+//   O += P(j) V(j)       tcgen05.mma M128 N64 K64 accumulating in TMEM, A = P(j) from tensor memory, V tile = MN-major B
+// 112 KB of shared memory (Q 16, K 3 x 8, V 2 x 8, identity 8, bias 3 x 16) and 256 TMEM columns (2 x 64 scores, 64 output,
+// 2 x 32 probabilities) per CTA keep two CTAs per SM.
 #include <stdlib.h>
 #include <string.h>
 
@@ -40,7 +39,9 @@ static constexpr int kKTile = 64;
 static constexpr int kHeadDim = 64;
 static constexpr int kAttnThreads = 192;
 static constexpr int kSoftmaxWarps = 4;
-static constexpr int kKvStages = 2;  // K and V rings (each refilled the moment its reader retires, two tiles ahead)
+static constexpr int kKvStages = 2;  // V ring (refilled the moment its reader retires, two tiles ahead)
+static constexpr int kKStages = 3;   // K ring and bias ring: refilled two tiles ahead of the score issuer, which itself runs up to
+static constexpr int kBStages = 3;   // two tiles ahead of the softmax (a 2-deep ring leaves one tile, ~1 us, for the TMA round trip)
 static constexpr float kLog2e = 1.4426950408889634f;
 static constexpr float kRescaleThreshold = 8.0f;  // log2 domain: probabilities stay below 2^8
 
@@ -58,20 +59,20 @@ struct AttnParams {
 struct AttnSmem {
   static constexpr int kQ = kQTile * kHeadDim * 2;     // 16 KB
   static constexpr int kKV = kKTile * kHeadDim * 2;    // 8 KB
-  static constexpr int kP = kQTile * kKTile * 2;       // 16 KB
+  static constexpr int kIdent = kKTile * kKTile * 2;   // 8 KB fp16 identity [64 x 64]: the B operand of the bias MMAs
   static constexpr int kBias = kQTile * kKTile * 2;    // 16 KB fp16 bias tile: one 128B-swizzled [128 x 64] box
   static constexpr int offQ = 0;
   static constexpr int offK = offQ + kQ;
-  static constexpr int offV = offK + kKvStages * kKV;
-  static constexpr int offP = offV + kKvStages * kKV;  // two P buffers: softmax(j+1) never waits for P V(j)
-  static constexpr int offBias = offP + 2 * kP;        // two bias buffers
-  static constexpr int offBar = offBias + 2 * kBias;
+  static constexpr int offV = offK + kKStages * kKV;
+  static constexpr int offIdent = offV + kKvStages * kKV;
+  static constexpr int offBias = offIdent + kIdent;  // bias ring
+  static constexpr int offBar = offBias + kBStages * kBias;
   static constexpr int kTotal = offBar + 256;
 };
 
 struct AttnBars {
-  uint64_t q_full, k_full[kKvStages], k_empty[kKvStages], v_full[kKvStages], v_empty[kKvStages];
-  uint64_t s_full[2], s_empty[2], p_full[2], b_full[2], b_empty[2], o_done[2], qk_done[2];
+  uint64_t q_full, k_full[kKStages], k_empty[kKStages], v_full[kKvStages], v_empty[kKvStages];
+  uint64_t s_full[2], s_empty[2], p_full[2], b_full[kBStages], b_empty[kBStages], o_done[2];
   uint32_t tmem_slot;
 };
 static_assert(sizeof(AttnBars) <= 256, "barrier block");
@@ -106,11 +107,17 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
   if (tid == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();  // the 128B swizzle needs a 1024-byte aligned base
     mbar_init(&bars->q_full, 1);
-    for (int i = 0; i < kKvStages; ++i) {
+    for (int i = 0; i < kKStages; ++i) {
       mbar_init(&bars->k_full[i], 1);
       mbar_init(&bars->k_empty[i], 1);
+    }
+    for (int i = 0; i < kKvStages; ++i) {
       mbar_init(&bars->v_full[i], 1);
       mbar_init(&bars->v_empty[i], 1);
+    }
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(&bars->b_full[i], 1);   // bias(j) tile landed (TMA)
+      mbar_init(&bars->b_empty[i], 1);  // tcgen05.commit: the bias MMAs of S(j) have read it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->s_full[i], 1);  // tcgen05.commit of S(j) (scores AND bias MMAs)
@@ -118,9 +125,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->p_full[i], kSoftmaxWarps);
-      mbar_init(&bars->b_full[i], 1);   // bias(j) tile landed (TMA)
-      mbar_init(&bars->b_empty[i], 1);  // tcgen05.commit: the bias MMAs of S(j) have read it
-      mbar_init(&bars->qk_done[i], 1);  // tcgen05.commit of Q K(j)^T: the output issuer may add the bias on top
       mbar_init(&bars->o_done[i], 1);  // P V(t) retired -> o_done[t & 1]
     }
     fence_mbar_init();
@@ -140,26 +144,24 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
   const uint32_t tmem_base = bars->tmem_slot;
   const uint32_t tmem_s = tmem_base;        // score ping-pong: columns [0,64) and [64,128)
   const uint32_t tmem_o = tmem_base + 128;  // output accumulator: columns [128,192)
-  const uint32_t tmem_i = tmem_base + 192;  // fp16 identity [128 x 128] as the A operand of the bias MMAs: columns [192,256)
+  const uint32_t tmem_p = tmem_base + 192;  // bf16 probabilities, two buffers of 32 columns (64 keys): columns [192,256)
   if (p.bias) {
-    // The additive bias tile is added to the scores BY THE TENSOR CORE: S += I * bias(j) with I the fp16 identity kept in
-    // TMEM (1.0 * b is exact, fp32 accumulate), bias(j) the TMA-staged fp16 tile read as the MN-major B operand.  The
-    // softmax threads no longer read the bias (r01/r02a: 4 x LDS.128 + 32 conversions + 16 packed adds per thread and
-    // tile, 10 us of an 85 us launch by ablation).
-    if (warp < kSoftmaxWarps) {
-      const int r = warp * 32 + (tid & 31);  // row r: element k = r is 1.0 -> column r/2, low or high half
-      uint32_t v[32];
-#pragma unroll
-      for (int hb = 0; hb < 2; ++hb) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = (hb * 32 + i == (r >> 1)) ? ((r & 1) ? 0x3C000000u : 0x00003C00u) : 0u;
-        tmem_st_32x32(tmem_i + (static_cast<uint32_t>(warp * 32) << 16) + hb * 32, v);
-      }
-      tmem_st_wait();
+    // The additive bias tile is added to the scores BY THE TENSOR CORE: S(j) += bias(j) * I, with the TMA-staged fp16 bias
+    // tile [128 queries x 64 keys] as the K-major A operand and the fp16 identity [64 x 64] kept in shared memory as the
+    // B operand -- exact (b * 1.0, fp32 accumulate), four K = 16 steps.  (r02a: the softmax threads added it: 4 x LDS.128 + 32
+    // conversions + 16 packed adds per thread and tile, 10 us of an 85 us launch.  r02b: identity [128 x 128] in TMEM as A
+    // and the bias tile as the MN-major B: eight K steps that re-read the identity for every key tile, 48 KB of operand
+    // fetch per tile -- with Q K^T and P V the tensor pipe's operand fetch, ~90 B/clk, paced the kernel,
+    // profiles/r02_attention_pair.txt.)  Swizzled K-major rows of 128 B: row n holds 1.0 at element n.
+    for (int ci = tid; ci < AttnSmem::kIdent / 16; ci += kAttnThreads) {
+      const int n = ci >> 3;                        // row
+      const int logical = (ci & 7) ^ (n & 7);       // 16-byte chunk of the row stored at position ci & 7
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      if (logical == (n >> 3)) w[(n & 7) >> 1] = (n & 1) ? 0x3C000000u : 0x00003C00u;
+      *reinterpret_cast<uint4*>(smem + AttnSmem::offIdent + ci * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    tc_fence_before();
+    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
-    tc_fence_after();
   }
   pdl_wait();
 
@@ -172,36 +174,36 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
     if ((tid & 31) == 0 && n_kt > 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(kQTile, kKTile, 0, 0);
       auto load_k = [&](int t) {
-        const int st = t % kKvStages;
+        const int st = t % kKStages;
         mbar_expect_tx(&bars->k_full[st], AttnSmem::kKV);
         tma_load_4d(smem + AttnSmem::offK + st * AttnSmem::kKV, &tmK, &bars->k_full[st], 0, h, t * kKTile, b);
       };
-      constexpr uint32_t idesc_bias = make_idesc_f16(kQTile, kKTile, 0, 1);  // A = identity (TMEM), B = bias tile, MN-major
+      constexpr uint32_t idesc_bias = make_idesc_f16(kQTile, kKTile, 0, 0);  // A = bias tile, B = identity, both K-major
+      const uint64_t di = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offIdent));
       auto load_bias = [&](int t) {
-        mbar_expect_tx(&bars->b_full[t & 1], AttnSmem::kBias);
-        tma_load_3d(smem + AttnSmem::offBias + (t & 1) * AttnSmem::kBias, &tmB, &bars->b_full[t & 1], t * kKTile, q0, h);
+        const int st = t % kBStages;
+        mbar_expect_tx(&bars->b_full[st], AttnSmem::kBias);
+        tma_load_3d(smem + AttnSmem::offBias + st * AttnSmem::kBias, &tmB, &bars->b_full[st], t * kKTile, q0, h);
       };
       mbar_expect_tx(&bars->q_full, AttnSmem::kQ);
       tma_load_4d(smem + AttnSmem::offQ, &tmQ, &bars->q_full, 0, h, q0, b);
-      for (int t = 0; t < kKvStages && t < n_kt; ++t) load_k(t);
-      if (p.bias) {
-        load_bias(0);
-        if (n_kt > 1) load_bias(1);
-      }
+      for (int t = 0; t < kKStages && t < n_kt; ++t) load_k(t);
+      if (p.bias)
+        for (int t = 0; t < kBStages && t < n_kt; ++t) load_bias(t);
       const uint64_t dq = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offQ));
 #pragma unroll 1
       for (int j = 0; j < n_kt; ++j) {
         // ---- refill the K stage S(j-1) has released (its tcgen05.commit fired about a tile ago: no stall) ----
-        if (j >= 1 && j + 1 < n_kt) {
-          const int pj = j - 1, pst = pj % kKvStages;
-          mbar_wait(&bars->k_empty[pst], (pj / kKvStages) & 1);
-          load_k(j + 1);  // stage (j+1) % 2 == (j-1) % 2
+        if (j >= 1 && j + kKStages - 1 < n_kt) {
+          const int pj = j - 1, pst = pj % kKStages;
+          mbar_wait(&bars->k_empty[pst], (pj / kKStages) & 1);
+          load_k(j + kKStages - 1);  // the stage S(j-1) read
         }
         // ---- S(j) into score buffer j&1 (free once softmax(j-2) has read it) ----
-        const int st = j % kKvStages;
+        const int st = j % kKStages;
         attn_trace(p, tslot, 0, j, 0);
         if (j == 0) mbar_wait(&bars->q_full, 0);
-        mbar_wait(&bars->k_full[st], (j / kKvStages) & 1);
+        mbar_wait(&bars->k_full[st], (j / kKStages) & 1);
         attn_trace(p, tslot, 0, j, 1);
         mbar_wait(&bars->s_empty[j & 1], ((j >> 1) & 1) ^ 1);
         attn_trace(p, tslot, 0, j, 2);
@@ -210,24 +212,23 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k)
           umma_f16(tmem_s + (j & 1) * 64, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        // With a bias the score buffer is completed by S(j) += I * bias(j) (8 more MMAs, K = 128 query rows).  Twelve
-        // tcgen05.mma per tile from ONE thread (~70 clocks each, plus ~150 per mbarrier wait) made that thread the
-        // pace-setter of the whole CTA, whichever issuer it was: the bias MMAs are split, K steps 0..3 here, 4..7 on the
-        // output issuer once these have retired (qk_done).
+        // with a bias the score buffer is completed by S(j) += bias(j) * I (four more MMAs over the 64 keys)
         if (p.bias) {
-          mbar_wait(&bars->b_full[j & 1], (j >> 1) & 1);
+          const int sb = j % kBStages;
+          mbar_wait(&bars->b_full[sb], (j / kBStages) & 1);
           tc_fence_after();
-          const uint64_t db = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offBias + (j & 1) * AttnSmem::kBias));
+          const uint64_t db = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offBias + sb * AttnSmem::kBias));
 #pragma unroll
-          for (int k = 0; k < kQTile / 32; ++k) umma_f16_ts(tmem_s + (j & 1) * 64, tmem_i + 8 * k, db + 128 * k, idesc_bias, 1u);
+          for (int k = 0; k < kKTile / 16; ++k) umma_f16(tmem_s + (j & 1) * 64, db + 2 * k, di + 2 * k, idesc_bias, 1u);
+          umma_commit(&bars->b_empty[sb]);
         }
-        umma_commit(p.bias ? &bars->qk_done[j & 1] : &bars->s_full[j & 1]);
+        umma_commit(&bars->s_full[j & 1]);
         umma_commit(&bars->k_empty[st]);
         attn_trace(p, tslot, 0, j, 3);
-        // bias(j+1) goes into the buffer the bias MMAs of S(j-1) (output issuer) have read
-        if (p.bias && j >= 1 && j + 1 < n_kt) {
-          mbar_wait(&bars->b_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
-          load_bias(j + 1);
+        // bias(j+1) goes into the buffer the bias MMAs of S(j-1) have read
+        if (p.bias && j >= 1 && j + kBStages - 1 < n_kt) {
+          mbar_wait(&bars->b_empty[(j - 1) % kBStages], ((j - 1) / kBStages) & 1);
+          load_bias(j + kBStages - 1);
         }
       }
     }
@@ -241,20 +242,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         tma_load_4d(smem + AttnSmem::offV + st * AttnSmem::kKV, &tmV, &bars->v_full[st], 0, h, t * kKTile, b);
       };
       for (int t = 0; t < kKvStages && t < n_kt; ++t) load_v(t);
-      constexpr uint32_t idesc_bias = make_idesc_f16(kQTile, kKTile, 0, 1);  // A = identity (TMEM), B = bias tile, MN-major
-      auto add_bias = [&](int j) {  // second half of S(j) += I * bias(j): query rows 64..127 of the contraction
-        mbar_wait(&bars->qk_done[j & 1], (j >> 1) & 1);  // Q K^T and the first half have retired (the bias tile has landed)
-        tc_fence_after();
-        const uint64_t db = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offBias + (j & 1) * AttnSmem::kBias));
-#pragma unroll
-        for (int k = kQTile / 32; k < kQTile / 16; ++k) umma_f16_ts(tmem_s + (j & 1) * 64, tmem_i + 8 * k, db + 128 * k, idesc_bias, 1u);
-        umma_commit(&bars->b_empty[j & 1]);
-        umma_commit(&bars->s_full[j & 1]);
-      };
-      if (p.bias) add_bias(0);
 #pragma unroll 1
       for (int t = 0; t < n_kt; ++t) {
-        if (p.bias && t + 1 < n_kt) add_bias(t + 1);  // the scores run one tile ahead of the probabilities
         const int st = t % kKvStages;
         attn_trace(p, tslot, 1, t, 0);
         mbar_wait(&bars->v_full[st], (t / kKvStages) & 1);
@@ -262,11 +251,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         mbar_wait(&bars->p_full[t & 1], (t >> 1) & 1);
         attn_trace(p, tslot, 1, t, 2);
         tc_fence_after();
-        const uint64_t dp = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offP + (t & 1) * AttnSmem::kP));
+        const uint32_t tp = tmem_p + (t & 1) * 32;  // P(t): bf16 pairs, 8 columns per 16-key K step
         const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offV + st * AttnSmem::kKV));
 #pragma unroll
         for (int k = 0; k < kKTile / 16; ++k)  // V: 16 key rows = 2048 B per K step -> +128 in the address field
-          umma_f16(tmem_o, dp + 2 * k, dv + 128 * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
+          umma_f16_ts(tmem_o, tp + 8 * k, dv + 128 * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
         umma_commit(&bars->v_empty[st]);
         umma_commit(&bars->o_done[t & 1]);
         attn_trace(p, tslot, 1, t, 3);
@@ -284,17 +273,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
     const int lane = tid & 31;
     const int rowl = warp * 32 + lane;
     const int row = q0 + rowl;
-    const uint32_t sw = static_cast<uint32_t>(rowl & 7);
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
     const uint8_t* kpm_row = p.kpm ? p.kpm + static_cast<int64_t>(b) * p.Tk : nullptr;
-    uint8_t* p_row0 = smem + AttnSmem::offP + rowl * 128;  // + (j & 1) * kP
     float m_used = 0.f;  // log2-domain reference max the probabilities are expressed against
     float l_run = 0.f;
     const int trole = (lane == 0 && (warp == 0 || warp == 3)) ? (warp == 0 ? 2 : 3) : -1;
 
 #pragma unroll 1
     for (int j = 0; j < n_kt; ++j) {
-      uint8_t* p_row = p_row0 + (j & 1) * AttnSmem::kP;
+      const uint32_t tp = tmem_p + lane_addr + (j & 1) * 32;  // this row of P(j): 16 columns per 32-key half
       if (trole >= 0) attn_trace(p, tslot, trole, j, 0);
       mbar_wait(&bars->s_full[j & 1], (j >> 1) & 1);  // S(j) = Q K(j)^T + bias(j) retired
       tc_fence_after();
@@ -359,19 +346,16 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
               tmem_st_wait();
               tc_fence_before();
             }
-            if (hf == 1) {  // the first half of P(j) is already in shared memory against the old reference
+            if (hf == 1) {  // the first half of P(j) is already in tensor memory against the old reference
+              uint32_t w[16];
+              tmem_ld_32x16(tp, w);
+              tmem_ld_wait();
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint4* pp = reinterpret_cast<uint4*>(p_row + ((static_cast<uint32_t>(c) ^ sw) << 4));
-                uint4 u = *pp;
-                uint32_t* w = reinterpret_cast<uint32_t*>(&u);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float2 v = unpack_bf16x2(w[q]);
-                  w[q] = pack_bf16x2(v.x * f, v.y * f);
-                }
-                *pp = u;
+              for (int q = 0; q < 16; ++q) {
+                const float2 v = unpack_bf16x2(w[q]);
+                w[q] = pack_bf16x2(v.x * f, v.y * f);
               }
+              tmem_st_32x16(tp, w);
             }
             if (grow) {
               l_run *= f;
@@ -394,17 +378,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         if (trole >= 0 && hf == 0) attn_trace(p, tslot, trole, j, 3);
         // P (bf16) -> buffer j&1 once its previous reader P V(j-2) has retired (issued two tiles ago)
         if (hf == 0 && j >= 2) mbar_wait(&bars->o_done[j & 1], ((j - 2) >> 1) & 1);
+        {
+          uint32_t w[16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 u;
-          u.x = pack_bf16x2(s[8 * c + 0], s[8 * c + 1]);
-          u.y = pack_bf16x2(s[8 * c + 2], s[8 * c + 3]);
-          u.z = pack_bf16x2(s[8 * c + 4], s[8 * c + 5]);
-          u.w = pack_bf16x2(s[8 * c + 6], s[8 * c + 7]);
-          *reinterpret_cast<uint4*>(p_row + ((static_cast<uint32_t>(4 * hf + c) ^ sw) << 4)) = u;
+          for (int q = 0; q < 16; ++q) w[q] = pack_bf16x2(s[2 * q], s[2 * q + 1]);
+          tmem_st_32x16(tp + hf * 16, w);
         }
       }
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tmem_st_wait();
+      tc_fence_before();  // tensor-memory writes of P(j) -> ordered before the arrive the issuing thread waits on
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full[j & 1]);
     }
