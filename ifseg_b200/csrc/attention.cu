@@ -37,7 +37,7 @@ namespace sgf {
 static constexpr int kQTile = 128;
 static constexpr int kKTile = 64;
 static constexpr int kHeadDim = 64;
-static constexpr int kAttnThreads = 192;
+static constexpr int kAttnThreads = 224;
 static constexpr int kSoftmaxWarps = 4;
 static constexpr int kKvStages = 2;  // V ring (refilled the moment its reader retires, two tiles ahead)
 static constexpr int kKStages = 3;   // K ring and bias ring: refilled two tiles ahead of the score issuer, which itself runs up to
@@ -173,32 +173,11 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
     //  parked on s_full while the issuing thread was parked on p_full.)
     if ((tid & 31) == 0 && n_kt > 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(kQTile, kKTile, 0, 0);
-      auto load_k = [&](int t) {
-        const int st = t % kKStages;
-        mbar_expect_tx(&bars->k_full[st], AttnSmem::kKV);
-        tma_load_4d(smem + AttnSmem::offK + st * AttnSmem::kKV, &tmK, &bars->k_full[st], 0, h, t * kKTile, b);
-      };
       constexpr uint32_t idesc_bias = make_idesc_f16(kQTile, kKTile, 0, 0);  // A = bias tile, B = identity, both K-major
       const uint64_t di = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offIdent));
-      auto load_bias = [&](int t) {
-        const int st = t % kBStages;
-        mbar_expect_tx(&bars->b_full[st], AttnSmem::kBias);
-        tma_load_3d(smem + AttnSmem::offBias + st * AttnSmem::kBias, &tmB, &bars->b_full[st], t * kKTile, q0, h);
-      };
-      mbar_expect_tx(&bars->q_full, AttnSmem::kQ);
-      tma_load_4d(smem + AttnSmem::offQ, &tmQ, &bars->q_full, 0, h, q0, b);
-      for (int t = 0; t < kKStages && t < n_kt; ++t) load_k(t);
-      if (p.bias)
-        for (int t = 0; t < kBStages && t < n_kt; ++t) load_bias(t);
       const uint64_t dq = make_smem_desc_sw128(smem_u32(smem + AttnSmem::offQ));
 #pragma unroll 1
       for (int j = 0; j < n_kt; ++j) {
-        // ---- refill the K stage S(j-1) has released (its tcgen05.commit fired about a tile ago: no stall) ----
-        if (j >= 1 && j + kKStages - 1 < n_kt) {
-          const int pj = j - 1, pst = pj % kKStages;
-          mbar_wait(&bars->k_empty[pst], (pj / kKStages) & 1);
-          load_k(j + kKStages - 1);  // the stage S(j-1) read
-        }
         // ---- S(j) into score buffer j&1 (free once softmax(j-2) has read it) ----
         const int st = j % kKStages;
         attn_trace(p, tslot, 0, j, 0);
@@ -225,11 +204,6 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         umma_commit(&bars->s_full[j & 1]);
         umma_commit(&bars->k_empty[st]);
         attn_trace(p, tslot, 0, j, 3);
-        // bias(j+1) goes into the buffer the bias MMAs of S(j-1) have read
-        if (p.bias && j >= 1 && j + kBStages - 1 < n_kt) {
-          mbar_wait(&bars->b_empty[(j - 1) % kBStages], ((j - 1) / kBStages) & 1);
-          load_bias(j + kBStages - 1);
-        }
       }
     }
   } else if (warp == kSoftmaxWarps + 1) {
@@ -262,6 +236,34 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
         if (t + kKvStages < n_kt) {  // V(t+2) goes into the stage P V(t) is reading
           mbar_wait(&bars->v_empty[st], (t / kKvStages) & 1);
           load_v(t + kKvStages);
+        }
+      }
+    }
+  } else if (warp == kSoftmaxWarps + 2) {
+    // ============ loader: Q, then the K and bias rings, each stage refilled the moment its reader S(j-3) retires ============
+    // (the score issuer used to do this itself: five mbarrier round trips, two TMA issues, eight MMAs and three commits per
+    //  tile from ONE thread took ~2200 clocks and starved the softmax warps by 600-800 clocks per tile)
+    if ((tid & 31) == 0 && n_kt > 0) {
+      auto load_k = [&](int t) {
+        const int st = t % kKStages;
+        mbar_expect_tx(&bars->k_full[st], AttnSmem::kKV);
+        tma_load_4d(smem + AttnSmem::offK + st * AttnSmem::kKV, &tmK, &bars->k_full[st], 0, h, t * kKTile, b);
+      };
+      auto load_bias = [&](int t) {
+        const int st = t % kBStages;
+        mbar_expect_tx(&bars->b_full[st], AttnSmem::kBias);
+        tma_load_3d(smem + AttnSmem::offBias + st * AttnSmem::kBias, &tmB, &bars->b_full[st], t * kKTile, q0, h);
+      };
+      static_assert(kKStages == kBStages, "one loop refills both rings");
+      mbar_expect_tx(&bars->q_full, AttnSmem::kQ);
+      tma_load_4d(smem + AttnSmem::offQ, &tmQ, &bars->q_full, 0, h, q0, b);
+#pragma unroll 1
+      for (int t = 0; t < n_kt; ++t) {
+        if (t >= kKStages) mbar_wait(&bars->k_empty[t % kKStages], ((t / kKStages) - 1) & 1);
+        load_k(t);
+        if (p.bias) {
+          if (t >= kBStages) mbar_wait(&bars->b_empty[t % kBStages], ((t / kBStages) - 1) & 1);
+          load_bias(t);
         }
       }
     }
@@ -335,13 +337,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_tcgen05_kernel(cons
               mbar_wait(&bars->o_done[(j - 1) & 1], ((j - 1) >> 1) & 1);  // every P V issued so far has retired
               tc_fence_after();
 #pragma unroll
-              for (int hb = 0; hb < 2; ++hb) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_o + lane_addr + hb * 32, r);
+              for (int hb = 0; hb < 4; ++hb) {
+                uint32_t r[16];
+                tmem_ld_32x16(tmem_o + lane_addr + hb * 16, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-                tmem_st_32x32(tmem_o + lane_addr + hb * 32, r);
+                for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+                tmem_st_32x16(tmem_o + lane_addr + hb * 16, r);
               }
               tmem_st_wait();
               tc_fence_before();
