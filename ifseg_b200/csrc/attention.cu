@@ -2,12 +2,13 @@
 //
 //   O[b,i,h,:] = head_scale[h] * softmax_j( Q[b,i,h,:].K[b,j,h,:] + bias[h,i,j] + mask ) V[b,j,h,:]
 //
-// One CTA per (128-query tile, head, batch); 6 warps, two CTAs per SM:
+// One CTA per (128-query tile, head, batch); 7 warps, two CTAs per SM:
 //   warps 0..3 : softmax, thread r owns query row r (TMEM lane r); the 64 keys of a tile are processed as two 32-key
 //                sub-tiles of the online softmax (32 scores live at a time; the TMEM load of the second half runs
 //                under the arithmetic of the first)
-//   warp 4     : score issuer  -- one lane: Q/K/bias TMA loads, S = Q K^T and S += bias * I tcgen05.mma, up to two tiles ahead
+//   warp 4     : score issuer  -- one lane: S = Q K^T and S += bias * I tcgen05.mma, up to two tiles ahead of the softmax
 //   warp 5     : output issuer -- one lane: V TMA loads and the O += P V tcgen05.mma
+//   warp 6     : loader        -- one lane: Q, then the K ring and the bias ring (TMA), three tiles ahead of the score issuer
 // What the r02 timeline and ablation measurements say (profiles/r02_attention_analysis.txt, r02_attention_pair.txt): without
 // a bias the tile loop is bound by the softmax threads' own chain (TMEM load round trip, max, exp2, pack, hand-off: a warp
 // needs ~1000 clocks per 32-key sub-tile of which the MUFU pipe is busy 256); with a bias the tensor pipe's operand fetch

@@ -213,6 +213,43 @@ def test_attention(ops, B, H, Tq, Tk, causal, use_bias, use_kpm):
     assert err < 8e-3, err
 
 
+@pytest.mark.parametrize("Tq,Tk,causal,use_bias", [(200, 333, False, True), (260, 260, True, False), (130, 700, False, False)])
+def test_attention_lazy_rescale_paths(ops, Tq, Tk, causal, use_bias):
+    """Scores that keep GROWING along the keys (by far more than the lazy-rescaling threshold 2^8 per 32-key sub-tile, at a
+    row-dependent rate, so that within a warp some rows move their reference maximum and others do not): exercises the rare
+    paths of the online softmax -- the output accumulator rescaled in tensor memory, the first half of P(j) rescaled after
+    the second half raised the reference, the running sum -- and the log-sum-exp side output, against fp32 softmax."""
+    g = torch.Generator(device="cuda").manual_seed(Tq + Tk)
+    B, H, dh = 2, 2, 64
+    D = H * dh
+    rate = torch.rand(B, Tq, H, 1, device="cuda", generator=g) * 1.5 + 0.05  # per-row growth rate
+    q = (torch.randn(B, Tq, H, dh, device="cuda", generator=g) * 0.05 + rate / 8).bfloat16()
+    ramp = torch.linspace(-4.0, 4.0, Tk, device="cuda").view(1, Tk, 1, 1)    # key scale: scores ~ 8 * rate * ramp * 8
+    k = (torch.randn(B, Tk, H, dh, device="cuda", generator=g) * 0.05 + ramp).bfloat16()
+    v = torch.randn(B, Tk, H, dh, device="cuda", generator=g).bfloat16()
+    Tkp = (Tk + 63) // 64 * 64
+    bias = None
+    if use_bias:
+        bias = torch.zeros(H, Tq, Tkp, device="cuda")
+        bias[:, :, :Tk] = torch.randn(H, Tq, Tk, device="cuda", generator=g) * 3
+        bias = bias.half()
+    s = torch.einsum("bihd,bjhd->bhij", q.float(), k.float())
+    assert (s.max(-1).values - s[..., :32].max(-1).values).max() > 40  # the reference maximum really has to move, many times
+    out = torch.empty(B, Tq, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, H, Tq, device="cuda")
+    ops.attention(q, k, v, out, B=B, H=H, Tq=Tq, Tk=Tk, q_strides=(D, Tq * D), k_strides=(D, Tk * D),
+                  v_strides=(D, Tk * D), o_strides=(D, Tq * D), bias=bias, causal=causal, lse=lse)
+    ref = _attn_ref(q, k, v, bias.float() if bias is not None else None, causal, None, None).reshape(B, Tq, D)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 8e-3, _rel(out, ref)
+    if bias is not None:
+        s = s + bias.float()[None, :, :Tq, :Tk]
+    if causal:
+        s = s + torch.full(s.shape[-2:], float("-inf"), device=s.device).triu(1)
+    ref_lse = torch.logsumexp(s, dim=-1) * 1.4426950408889634  # the kernel reports log2-domain log-sum-exp
+    assert torch.allclose(lse, ref_lse, rtol=1e-4, atol=2e-3), (lse - ref_lse).abs().max()
+
+
 def test_attention_fused_qkv_layout(ops):
     g = torch.Generator(device="cuda").manual_seed(99)
     B, T, H, dh = 2, 150, 12, 64
